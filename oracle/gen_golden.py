@@ -1,0 +1,612 @@
+"""
+TEST INFRASTRUCTURE - golden fixture generator.
+
+Runs the UNMODIFIED reference (/root/reference/ngmix, numba + scipy) on seeded
+synthetic inputs and writes input/output vectors to tests/golden/*.npz.  The
+reference is a Python package and cannot travel to the GPU box, so the
+vectors are committed together with this script (task statement, section 3).
+
+Usage (in the build container only; needs /root/reference):
+
+    python oracle/gen_golden.py [--only NAME ...]
+
+galsim is not installed; ngmix/__init__.py imports ngmix.metacal, which does
+a module-level `import galsim`, so an EMPTY stub package is put on sys.path.
+No galsim function is ever called by anything used here.
+"""
+import argparse
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+
+def _import_reference():
+    stub = tempfile.mkdtemp(prefix="galsim_stub_")
+    os.makedirs(os.path.join(stub, "galsim"))
+    open(os.path.join(stub, "galsim", "__init__.py"), "w").close()
+    os.environ.setdefault("NUMBA_CACHE_DIR",
+                          os.path.join(tempfile.gettempdir(), "numba_cache"))
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, stub)
+    sys.path.insert(0, "/root/reference")
+    import ngmix
+    assert ngmix.__file__.startswith("/root/reference"), ngmix.__file__
+    return ngmix
+
+
+ngmix = _import_reference()
+from ngmix_b200 import sims  # noqa: E402
+
+
+def jac_from_record(rec):
+    return ngmix.Jacobian(row=rec[0], col=rec[1], dvdrow=rec[2],
+                          dvdcol=rec[3], dudrow=rec[4], dudcol=rec[5])
+
+
+def gm_records(gm):
+    """(ngauss, 12) float view of a gmix record array, norm_set dropped"""
+    d = gm.get_data()
+    names = ["p", "row", "col", "irr", "irc", "icc", "det",
+             "drr", "drc", "dcc", "norm", "pnorm"]
+    return np.array([[d[n][i] for n in names] for i in range(d.size)])
+
+
+def save(name, **arrs):
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print("wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024))
+
+
+# ---------------------------------------------------------------- fastexp
+def gen_fastexp():
+    from ngmix.fastexp_nb import (
+        fexp_arr, apod_window, apod_window_deriv, _EXP5_SMOOTH_COEFFS,
+        _EXP_LOOKUP,
+    )
+    from numba import vectorize
+
+    rng = np.random.RandomState(1)
+    x = np.concatenate([
+        np.array([-0.25, -0.5, -0.75, -3.3, -7.8864744, -12.4999, 0.0,
+                  -1e-300, -1e-17, -12.5]),
+        -0.5 * np.arange(0, 26),            # integers and half integers
+        np.nextafter(-0.5 * np.arange(0, 26) - 0.0, 1.0),
+        np.nextafter(-0.5 * np.arange(0, 26) - 0.0, -20.0),
+        rng.uniform(-12.5, 0.0, size=4000),
+    ])
+    x = x[(x >= -12.5) & (x <= 0)]
+
+    @vectorize
+    def aw(c):
+        return apod_window(c)
+
+    @vectorize
+    def awd(c):
+        return apod_window_deriv(c)
+
+    chi2 = np.concatenate([np.array([20.0, 21.0, 22.5, 24.0, 25.0]),
+                           rng.uniform(20.0, 25.0, size=500)])
+    save("fastexp", x=x, fexp=fexp_arr(x), chi2=chi2, apod=aw(chi2),
+         apod_deriv=awd(chi2), coeffs=_EXP5_SMOOTH_COEFFS,
+         lookup=_EXP_LOOKUP)
+
+
+# ---------------------------------------------------------------- gmix
+def gen_gmix():
+    from ngmix.gmix.gmix_nb import get_cm_Tfactor
+    rng = np.random.RandomState(2)
+    out = {}
+    models = ["gauss", "turb", "exp", "dev", "bdf", "bd"]
+    for model in models:
+        npars = ngmix.gmix.get_model_npars(model)
+        pars = np.zeros((8, npars))
+        recs = []
+        for i in range(8):
+            p = np.zeros(npars)
+            p[0:2] = rng.uniform(-0.5, 0.5, size=2)
+            p[2:4] = rng.uniform(-0.4, 0.4, size=2)
+            if i == 0:
+                p[2:4] = 0.0            # g == 0 branch
+            p[4] = rng.uniform(0.1, 4.0)
+            if model == "bdf":
+                p[5] = rng.uniform(0.0, 1.0)
+            elif model == "bd":
+                p[5] = rng.uniform(-0.5, 0.5)
+                p[6] = rng.uniform(0.0, 1.0)
+            p[-1] = rng.uniform(1.0, 500.0)
+            pars[i] = p
+            gm = ngmix.GMixModel(p, model)
+            gm.set_norms()
+            recs.append(gm_records(gm))
+        out["pars_" + model] = pars
+        out["recs_" + model] = np.array(recs)
+
+    # coellip (3 gaussians) and full
+    cpars = np.zeros((4, 10))
+    crecs = []
+    for i in range(4):
+        p = np.concatenate([rng.uniform(-0.3, 0.3, size=2),
+                            rng.uniform(-0.3, 0.3, size=2),
+                            rng.uniform(0.1, 2.0, size=3),
+                            rng.uniform(0.1, 10.0, size=3)])
+        cpars[i] = p
+        gm = ngmix.GMixCoellip(p)
+        gm.set_norms()
+        crecs.append(gm_records(gm))
+    out["pars_coellip"] = cpars
+    out["recs_coellip"] = np.array(crecs)
+
+    # cm: fracdev, TdByTe, pars
+    cm_in = np.zeros((4, 8))
+    cm_recs = []
+    cm_tf = []
+    for i in range(4):
+        fracdev = rng.uniform(0, 1)
+        TdByTe = rng.uniform(0.5, 3.0)
+        p = np.array([0.1, -0.1, rng.uniform(-0.3, 0.3),
+                      rng.uniform(-0.3, 0.3), rng.uniform(0.2, 2.0), 100.0])
+        cm_in[i] = np.concatenate([[fracdev, TdByTe], p])
+        gm = ngmix.gmix.GMixCM(fracdev, TdByTe, p)
+        gm.set_norms()
+        cm_recs.append(gm_records(gm))
+        cm_tf.append(get_cm_Tfactor(fracdev, TdByTe))
+    out["cm_in"] = cm_in
+    out["recs_cm"] = np.array(cm_recs)
+    out["cm_tfactor"] = np.array(cm_tf)
+
+    # convolution: exp (6) x 3-gaussian psf with offset centres
+    conv_obj = np.zeros((4, 6))
+    conv_psf = np.zeros((4, 18))
+    conv_out = []
+    for i in range(4):
+        p = np.array([0.2, -0.1, rng.uniform(-0.3, 0.3),
+                      rng.uniform(-0.3, 0.3), rng.uniform(0.2, 2.0), 77.0])
+        conv_obj[i] = p
+        ppars = []
+        for k in range(3):
+            ppars += [rng.uniform(0.1, 1.0), rng.uniform(-0.05, 0.05),
+                      rng.uniform(-0.05, 0.05), rng.uniform(0.05, 0.3),
+                      rng.uniform(-0.01, 0.01), rng.uniform(0.05, 0.3)]
+        conv_psf[i] = ppars
+        gm = ngmix.GMixModel(p, "exp").convolve(ngmix.GMix(pars=ppars))
+        gm.set_norms()
+        conv_out.append(gm_records(gm))
+    out["conv_obj"] = conv_obj
+    out["conv_psf"] = conv_psf
+    out["conv_recs"] = np.array(conv_out)
+    save("gmix", **out)
+
+
+# ---------------------------------------------------------------- pixels
+def gen_pixels():
+    rng = np.random.RandomState(3)
+    H, W = 11, 13
+    image = rng.normal(size=(H, W))
+    weight = rng.uniform(0.5, 2.0, size=(H, W))
+    weight[2, 3] = 0.0
+    weight[0, 0] = -1.0
+    weight[10, 12] = 0.0
+    jac = ngmix.Jacobian(row=4.7, col=6.1, dvdrow=0.26, dvdcol=0.01,
+                         dudrow=-0.02, dudcol=0.27)
+    rec = np.array([jac._data[n][0] for n in jac._data.dtype.names])
+    out = dict(image=image, weight=weight, jac=rec)
+    for tag, ignore in (("ign", True), ("all", False)):
+        pix = ngmix.pixels.make_pixels(image, weight, jac,
+                                       ignore_zero_weight=ignore)
+        out["pixels_" + tag] = np.array(
+            [pix[n] for n in ("u", "v", "area", "val", "ierr")]).T
+    coords = ngmix.pixels.make_coords((H, W), jac)
+    out["coords"] = np.array([coords[n] for n in ("u", "v", "area")]).T
+    save("pixels", **out)
+
+
+# ---------------------------------------------------------------- render
+def gen_render():
+    from ngmix.fitting.derivs_nb import deriv_images
+    from ngmix.fitting.results import get_model_deriv_data
+    rng = np.random.RandomState(4)
+    out = {}
+
+    # Appendix B mixture of SURVEY.md + a few random ones, incl. an offset
+    # non-diagonal jacobian and a psf with off-centre components
+    cases = []
+    jac0 = sims.diag_jacobian(23.5, 23.5, 0.263)
+    cases.append(([0.1, -0.2, 0.1, 0.05, 0.4, 100.0], "exp",
+                  sims.simple_full_pars([0, 0, 0.01, -0.01, 0.27, 1.0],
+                                        "turb"), jac0, (48, 48)))
+    for i in range(3):
+        jr = ngmix.Jacobian(row=15.3 + i, col=16.9 - i, dvdrow=0.25,
+                            dvdcol=0.02 * i, dudrow=-0.015, dudcol=0.27)
+        jrec = np.array([jr._data[n][0] for n in jr._data.dtype.names])
+        psf = np.array([
+            [0.6, 0.02, -0.01, 0.09, 0.004, 0.11],
+            [0.3, -0.03, 0.02, 0.2, -0.01, 0.18],
+            [0.1, 0.0, 0.0, 0.6, 0.02, 0.5]])
+        model = ["exp", "dev", "gauss"][i]
+        pars = [rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3),
+                rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3),
+                rng.uniform(0.2, 1.5), rng.uniform(10, 100)]
+        cases.append((pars, model, psf, jrec, (32, 34)))
+
+    for k, (pars, model, psf, jrec, dims) in enumerate(cases):
+        gm0 = ngmix.GMixModel(pars, model)
+        gpsf = ngmix.GMix(pars=psf.ravel())
+        gm = gm0.convolve(gpsf)
+        jac = jac_from_record(jrec)
+        fast = gm.make_image(dims, jacobian=jac, fast_exp=True)
+        exact = gm.make_image(dims, jacobian=jac)
+        rs = np.random.RandomState(100 + k)
+        image = exact + rs.normal(scale=0.05, size=dims)
+        weight = np.zeros(dims) + rs.uniform(2.0, 6.0)
+        weight[3, 4] = 0.0
+        obs = ngmix.Observation(image, weight=weight, jacobian=jac)
+        ll = gm.get_loglike(obs, more=True)
+        s2n_sum = gm.get_model_s2n_sum(obs)
+        fdiff = np.zeros(image.size + 13)
+        gm.fill_fdiff(obs, fdiff, start=13)
+
+        # derivative images on ALL pixels
+        coords = ngmix.pixels.make_coords(dims, jac)
+        gpars, dcov = get_model_deriv_data(
+            gm0=gm0, gmc=gm, g1=pars[2], g2=pars[3], T=pars[4])
+        dout = np.zeros((6, coords.size))
+        deriv_images(gpars, dcov, coords["v"].copy(), coords["u"].copy(),
+                     coords["area"].copy(), dout)
+
+        p = "c%d_" % k
+        out[p + "pars"] = np.array(pars)
+        out[p + "model"] = np.array(model)
+        out[p + "psf"] = psf
+        out[p + "jac"] = jrec
+        out[p + "dims"] = np.array(dims)
+        out[p + "fast"] = fast
+        out[p + "exact"] = exact
+        out[p + "image"] = image
+        out[p + "weight"] = weight
+        out[p + "loglike"] = np.array(
+            [ll["loglike"], ll["s2n_numer"], ll["s2n_denom"], ll["npix"]])
+        out[p + "s2n_sum"] = np.array(s2n_sum)
+        out[p + "fdiff"] = fdiff
+        out[p + "gpars"] = gpars
+        out[p + "dcov"] = dcov
+        out[p + "deriv"] = dout
+    out["ncases"] = np.array(len(cases))
+    save("render", **out)
+
+
+# ---------------------------------------------------------------- LM
+LM_KEYS_F = ["lnprob", "s2n_numer", "s2n_denom", "chi2per", "s2n", "T",
+             "T_err", "flux", "flux_err"]
+
+
+def _get_priors(kind, rng):
+    from ngmix import priors, joint_prior
+    if kind == "none":
+        return None
+    cen = priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng)
+    g = priors.GPriorBA(0.3, rng=rng)
+    if kind == "flat":
+        T = priors.FlatPrior(-1.0, 1.0e3, rng=rng)
+        F = priors.FlatPrior(-100.0, 1.0e9, rng=rng)
+    elif kind == "erf":
+        T = priors.TwoSidedErf(-1.0, 0.1, 1.0e3, 1.0, rng=rng)
+        F = priors.TwoSidedErf(-1.0e2, 1.0, 1.0e9, 1.0e8, rng=rng)
+    else:
+        raise ValueError(kind)
+    return joint_prior.PriorSimpleSep(cen, g, T, F)
+
+
+def _run_lm_set(batch, prior_kind, analytic=True, model=None):
+    from ngmix.fitting import Fitter
+    model = model or batch["model"]
+    n = batch["images"].shape[0]
+    npars = batch["guess"].shape[1]
+    res = dict(
+        flags=np.zeros(n, "i4"), nfev=np.zeros(n, "i4"),
+        ier=np.zeros(n, "i4"), npix=np.zeros(n, "i4"),
+        dof=np.zeros(n, "i4"),
+        pars=np.zeros((n, npars)), pars_err=np.zeros((n, npars)),
+        pars_cov0=np.zeros((n, npars, npars)),
+        pars_cov=np.zeros((n, npars, npars)),
+    )
+    for k in LM_KEYS_F:
+        res[k] = np.full(n, np.nan)
+    rng = np.random.RandomState(99)
+    prior = _get_priors(prior_kind, rng)
+    fitter = Fitter(model=model, prior=prior, analytic_jacobian=analytic)
+    for i in range(n):
+        jac = jac_from_record(batch["jac"][i])
+        psf_gm = ngmix.GMix(pars=batch["psf"][i].ravel())
+        psf_obs = ngmix.Observation(np.zeros((5, 5)) + 1.0,
+                                    jacobian=ngmix.DiagonalJacobian(
+                                        row=2, col=2, scale=0.263),
+                                    gmix=psf_gm)
+        obs = ngmix.Observation(batch["images"][i],
+                                weight=batch["weights"][i],
+                                jacobian=jac, psf=psf_obs)
+        r = fitter.go(obs, batch["guess"][i].copy())
+        res["flags"][i] = r["flags"]
+        res["nfev"][i] = r["nfev"]
+        res["ier"][i] = r.get("ier", -1)
+        res["pars"][i] = r["pars"]
+        res["pars_err"][i] = r.get("pars_err", np.nan)
+        c0 = r["pars_cov0"]
+        res["pars_cov0"][i] = np.nan if c0 is None else c0
+        res["pars_cov"][i] = r["pars_cov"]
+        if r["flags"] == 0:
+            res["npix"][i] = r["npix"]
+            res["dof"][i] = r["dof"]
+            for k in LM_KEYS_F:
+                res[k][i] = r[k]
+    return res
+
+
+def gen_lm_exp():
+    out = {}
+    # config 1: one stamp, 1-gaussian psf, RandomState(42)
+    b1 = sims.make_lm_batch(1, seed0=42, psf_model="gauss")
+    # config 2 subsets: high S/N and low S/N, 3-gaussian psf
+    bhi = sims.make_lm_batch(24, seed0=1000, noise=0.01)
+    blo = sims.make_lm_batch(24, seed0=2000, noise=1.0, guess_frac=0.3)
+    for tag, b, priors_ in (("c1", b1, ["none"]),
+                            ("hi", bhi, ["none", "flat"]),
+                            ("lo", blo, ["none", "flat", "erf"])):
+        for k in ("images", "weights", "jac", "psf", "guess", "truth"):
+            out["%s_%s" % (tag, k)] = b[k]
+        for pk in priors_:
+            r = _run_lm_set(b, pk)
+            for k, v in r.items():
+                out["%s_%s_%s" % (tag, pk, k)] = v
+            print(tag, pk, "flags", np.bincount(r["flags"] != 0),
+                  "nfev med", np.median(r["nfev"]), "ier", r["ier"][:8])
+    save("lm_exp", **out)
+
+    # intermediate trace: calc_fdiff / calc_jacobian at the guess, 2 objects
+    from ngmix.fitting.results import FitModel
+    tr = {}
+    rng = np.random.RandomState(99)
+    for pk in ("none", "flat", "erf"):
+        prior = _get_priors(pk, rng)
+        for i in range(2):
+            b = blo
+            jac = jac_from_record(b["jac"][i])
+            psf_obs = ngmix.Observation(
+                np.ones((5, 5)),
+                jacobian=ngmix.DiagonalJacobian(row=2, col=2, scale=0.263),
+                gmix=ngmix.GMix(pars=b["psf"][i].ravel()))
+            obs = ngmix.Observation(b["images"][i], weight=b["weights"][i],
+                                    jacobian=jac, psf=psf_obs)
+            fm = FitModel(obs=obs, model="exp", guess=b["guess"][i],
+                          prior=prior)
+            fd = fm.calc_fdiff(b["guess"][i])
+            jc = fm.calc_jacobian(b["guess"][i])
+            tr["%s_%d_fdiff" % (pk, i)] = fd
+            tr["%s_%d_jtj" % (pk, i)] = jc.T @ jc
+            tr["%s_%d_jtf" % (pk, i)] = jc.T @ fd
+            tr["%s_%d_jac_prior" % (pk, i)] = jc[:fm.n_prior_pars + 2]
+    save("lm_trace", **tr)
+
+
+def gen_lm_other():
+    """gauss and dev models (analytic jacobian) + lmdif path for exp"""
+    out = {}
+    b = sims.make_lm_batch(8, seed0=3000, noise=0.1, model="gauss",
+                           dims=(32, 32))
+    for k in ("images", "weights", "jac", "psf", "guess"):
+        out["gauss_" + k] = b[k]
+    for k, v in _run_lm_set(b, "none").items():
+        out["gauss_none_" + k] = v
+    b = sims.make_lm_batch(8, seed0=4000, noise=0.1, model="dev",
+                           dims=(32, 32))
+    for k in ("images", "weights", "jac", "psf", "guess"):
+        out["dev_" + k] = b[k]
+    for k, v in _run_lm_set(b, "flat").items():
+        out["dev_flat_" + k] = v
+    # exp via forward differences (MINPACK lmdif)
+    b = sims.make_lm_batch(8, seed0=5000, noise=0.1, dims=(32, 32))
+    for k in ("images", "weights", "jac", "psf", "guess"):
+        out["expfd_" + k] = b[k]
+    for k, v in _run_lm_set(b, "none", analytic=False).items():
+        out["expfd_none_" + k] = v
+    save("lm_other", **out)
+
+
+# ---------------------------------------------------------------- EM / admom
+def _em_obs(image, weight, jrec):
+    return ngmix.Observation(image, weight=weight,
+                             jacobian=jac_from_record(jrec))
+
+
+def gen_em_admom():
+    from ngmix.em import EMFitter, run_em
+    from ngmix.admom import AdmomFitter
+    b = sims.make_psf_batch(64, seed0=7000)
+    n = b["images"].shape[0]
+    out = {k: b[k] for k in ("images", "weights", "jac", "em_guess",
+                             "am_guess")}
+    em = dict(flags=np.zeros(n, "i4"), numiter=np.zeros(n, "i4"),
+              fdiff=np.zeros(n), sky=np.zeros(n), pars=np.zeros((n, 18)))
+    fitter = EMFitter(tol=1e-5)
+    for i in range(n):
+        obs = _em_obs(b["images"][i], b["weights"][i], b["jac"][i])
+        r = fitter.go(obs, ngmix.GMix(pars=b["em_guess"][i].ravel()))
+        em["flags"][i] = r["flags"]
+        if r["flags"] & ngmix.flags.EM_RANGE_ERROR == 0:
+            em["numiter"][i] = r["numiter"]
+            em["fdiff"][i] = r["fdiff"]
+            em["sky"][i] = r["sky"]
+            em["pars"][i] = r.get_gmix().get_full_pars()
+    print("em numiter", em["numiter"][:16], "flags", em["flags"][:16])
+    for k, v in em.items():
+        out["em_" + k] = v
+
+    # EM with a psf, the variants, vary_sky, and a zero-weight stamp
+    var = {}
+    psf = sims.simple_full_pars([0, 0, 0.0, 0.0, 0.05, 1.0], "gauss")
+    for tag, kw in (("psf", {}), ("fixcen", dict(fixcen=True)),
+                    ("fixcov", dict(fixcov=True)),
+                    ("fluxonly", dict(fluxonly=True)),
+                    ("varysky", dict(vary_sky=True)),
+                    ("zerowt", {}), ("sky", dict(sky=0.0))):
+        nv = 8
+        numiter = np.zeros(nv, "i4")
+        flags = np.zeros(nv, "i4")
+        fdiff = np.zeros(nv)
+        sky = np.zeros(nv)
+        pars = np.zeros((nv, 12))
+        for i in range(nv):
+            image = b["images"][i]
+            weight = b["weights"][i].copy()
+            ignore = True
+            if tag == "zerowt":
+                weight[5:8, 6:9] = 0.0
+                ignore = False
+            psf_obs = ngmix.Observation(
+                np.ones((5, 5)),
+                jacobian=ngmix.DiagonalJacobian(row=2, col=2, scale=0.263),
+                gmix=ngmix.GMix(pars=psf.ravel()))
+            use_psf = tag in ("psf", "fixcen", "fixcov", "fluxonly")
+            obs = ngmix.Observation(
+                image if tag != "sky" else np.abs(image) + 1e-3,
+                weight=weight, jacobian=jac_from_record(b["jac"][i]),
+                psf=psf_obs if use_psf else None,
+                ignore_zero_weight=ignore)
+            guess = ngmix.GMix(pars=b["em_guess"][i][:2].ravel())
+            r = run_em(obs, guess, **kw)
+            flags[i] = r["flags"]
+            if flags[i] & ngmix.flags.EM_RANGE_ERROR == 0:
+                numiter[i] = r["numiter"]
+                fdiff[i] = r["fdiff"]
+                sky[i] = r["sky"]
+                pars[i] = r.get_gmix().get_full_pars()
+        var[tag + "_numiter"] = numiter
+        var[tag + "_flags"] = flags
+        var[tag + "_fdiff"] = fdiff
+        var[tag + "_sky"] = sky
+        var[tag + "_pars"] = pars
+        print("em", tag, numiter, flags)
+    var["psf"] = psf
+    for k, v in var.items():
+        out["emv_" + k] = v
+
+    # admom
+    am = dict(flags=np.zeros(n, "i4"), numiter=np.zeros(n, "i4"),
+              npix=np.zeros(n, "i4"), wsum=np.zeros(n),
+              sums=np.zeros((n, 7)), sums_cov=np.zeros((n, 7, 7)),
+              pars=np.zeros((n, 6)), rho4=np.zeros(n),
+              flux=np.zeros(n), flux_err=np.zeros(n), T=np.zeros(n),
+              T_err=np.zeros(n), e=np.zeros((n, 2)), e_err=np.zeros((n, 2)),
+              s2n=np.zeros(n), flags_final=np.zeros(n, "i4"))
+    afit = AdmomFitter()
+    for i in range(n):
+        obs = _em_obs(b["images"][i], b["weights"][i], b["jac"][i])
+        guess = ngmix.GMix(pars=b["am_guess"][i])
+        r = afit.go(obs, guess)
+        am["flags_final"][i] = r["flags"]
+        for k in ("numiter", "npix", "wsum", "sums", "sums_cov", "pars",
+                  "rho4", "flux", "flux_err", "T", "T_err", "e", "e_err",
+                  "s2n"):
+            am[k][i] = r[k]
+    print("admom numiter", am["numiter"][:16], "flags", am["flags_final"][:16])
+    for k, v in am.items():
+        out["am_" + k] = v
+
+    # admom failure modes: noise-only stamp, negative stamp, far-off guess
+    rs = np.random.RandomState(5)
+    fail_images = np.array([
+        rs.normal(scale=1.0, size=(25, 25)),
+        -np.abs(b["images"][0]),
+        b["images"][1],
+        b["images"][2],
+    ])
+    fail_guess = np.array([
+        b["am_guess"][0], b["am_guess"][0],
+        [1.0, 3.0, -3.0, 0.05, 0.0, 0.05],        # centre far off
+        [1.0, 0.0, 0.0, 1e-3, 0.0, 1e-3],         # tiny weight
+    ])
+    ff = np.zeros(4, "i4")
+    fn = np.zeros(4, "i4")
+    for i in range(4):
+        obs = _em_obs(fail_images[i], b["weights"][0], b["jac"][i])
+        r = afit.go(obs, ngmix.GMix(pars=fail_guess[i]))
+        ff[i] = r["flags"]
+        fn[i] = r["numiter"]
+    print("admom fail flags", ff, fn)
+    out["amf_images"] = fail_images
+    out["amf_guess"] = fail_guess
+    out["amf_flags"] = ff
+    out["amf_numiter"] = fn
+    save("em_admom", **out)
+
+
+def gen_lm_bdf():
+    from ngmix import priors, joint_prior
+    from ngmix.fitting import Fitter
+    b = sims.make_bdf_batch(6, seed0=9000, dims=(48, 48), noise=0.02)
+    rng = np.random.RandomState(7)
+    prior = joint_prior.PriorBDFSep(
+        cen_prior=priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng),
+        g_prior=priors.GPriorBA(0.3, rng=rng),
+        T_prior=priors.FlatPrior(-1.0, 1.0e3, rng=rng),
+        fracdev_prior=priors.Normal(0.5, 0.1, rng=rng),
+        F_prior=priors.FlatPrior(-100.0, 1.0e9, rng=rng))
+    out = {k: b[k] for k in ("images", "weights", "jac", "psf", "guess")}
+    n = b["images"].shape[0]
+    res = dict(flags=np.zeros(n, "i4"), nfev=np.zeros(n, "i4"),
+               ier=np.zeros(n, "i4"), pars=np.zeros((n, 7)),
+               pars_err=np.zeros((n, 7)), pars_cov=np.zeros((n, 7, 7)),
+               lnprob=np.zeros(n), s2n=np.zeros(n), chi2per=np.zeros(n))
+    fitter = Fitter(model="bdf", prior=prior)
+    for i in range(n):
+        psf_obs = ngmix.Observation(
+            np.ones((5, 5)),
+            jacobian=ngmix.DiagonalJacobian(row=2, col=2, scale=0.263),
+            gmix=ngmix.GMix(pars=b["psf"][i].ravel()))
+        obs = ngmix.Observation(b["images"][i], weight=b["weights"][i],
+                                jacobian=jac_from_record(b["jac"][i]),
+                                psf=psf_obs)
+        r = fitter.go(obs, b["guess"][i].copy())
+        res["flags"][i] = r["flags"]
+        res["nfev"][i] = r["nfev"]
+        res["ier"][i] = r["ier"]
+        res["pars"][i] = r["pars"]
+        res["pars_err"][i] = r["pars_err"]
+        res["pars_cov"][i] = r["pars_cov"]
+        if r["flags"] == 0:
+            res["lnprob"][i] = r["lnprob"]
+            res["s2n"][i] = r["s2n"]
+            res["chi2per"][i] = r["chi2per"]
+    print("bdf flags", res["flags"], "nfev", res["nfev"], "ier", res["ier"])
+    for k, v in res.items():
+        out["res_" + k] = v
+    save("lm_bdf", **out)
+
+
+GENERATORS = {
+    "fastexp": gen_fastexp,
+    "gmix": gen_gmix,
+    "pixels": gen_pixels,
+    "render": gen_render,
+    "lm_exp": gen_lm_exp,
+    "lm_other": gen_lm_other,
+    "em_admom": gen_em_admom,
+    "lm_bdf": gen_lm_bdf,
+}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", nargs="*", default=None)
+    args = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+    for name, fn in GENERATORS.items():
+        if args.only and name not in args.only:
+            continue
+        print("== generating", name)
+        fn()
