@@ -1,0 +1,331 @@
+/*
+ * ngx.h - C ABI of the B200-native batched Gaussian-mixture fitting engine.
+ *
+ * This is the drop-in boundary for the fitting hot path of esheldon/ngmix.
+ * The reference has no FFI: its boundary is "Python method -> @njit function
+ * on numpy structured arrays".  Every entry point below names the @njit
+ * function(s) (reference file:line) it replaces.  Record layouts are byte
+ * identical to the reference's numpy dtypes, so a ctypes binding can hand the
+ * reference's own arrays (GMix._data, Observation.pixels, Jacobian._data)
+ * straight to the *_host entry points.
+ *
+ * Conventions
+ *  - Every function processes a BATCH of n independent objects (stamps);
+ *    n = 1 reproduces the reference's per-object call.
+ *  - ngx_xxx(...)      : all array pointers are DEVICE pointers, work is
+ *                        enqueued on `stream` (a cudaStream_t, NULL = legacy
+ *                        default stream) and the call returns without
+ *                        synchronising.  No allocation on the hot path.
+ *  - ngx_xxx_host(...) : all array pointers are HOST pointers; the library
+ *                        stages them through its own device buffers and
+ *                        returns when the results are in the host arrays.
+ *  - Small configuration structs (ngx_prior, ngx_lm_pars, ngx_em_conf,
+ *    ngx_admom_conf) are always HOST pointers, passed by value to kernels.
+ *  - Return value: NGX_OK or an NGX_ERR_* code for API misuse / CUDA errors
+ *    (text via ngx_last_error()).  Numerical outcomes never use the return
+ *    value: they are per-object int32 flags with the reference's bit values
+ *    (ngmix/flags.py:3-23) or per-object status codes (NGX_ST_*), standing in
+ *    for the GMixRangeError / ZeroDivisionError exceptions numba raises.
+ *  - All arithmetic is IEEE fp64.  No exceptions cross this boundary.
+ */
+#ifndef NGX_H
+#define NGX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGX_VERSION 100
+
+/* return codes */
+#define NGX_OK 0
+#define NGX_ERR_ARG 1       /* bad size / null pointer / unsupported model */
+#define NGX_ERR_CUDA 2      /* a CUDA runtime call failed */
+#define NGX_ERR_NODEVICE 3  /* no CUDA device: there is no CPU fallback */
+
+/* per-object status (the reference's exceptions) */
+#define NGX_ST_OK 0
+#define NGX_ST_RANGE_ERROR 1   /* GMixRangeError, gexceptions.py:24 */
+#define NGX_ST_ZERO_DIV 2      /* ZeroDivisionError raised by numba */
+#define NGX_ST_FATAL 3         /* GMixFatalError("no weights > 0") */
+
+/* model ids, ngmix/gmix/gmix.py:1100-1110 */
+#define NGX_FULL 0
+#define NGX_GAUSS 1
+#define NGX_TURB 2
+#define NGX_EXP 3
+#define NGX_DEV 4
+#define NGX_BDF 6
+#define NGX_COELLIP 7
+#define NGX_CM 9
+#define NGX_BD 10
+
+/* flag bits, ngmix/flags.py:3-23 */
+#define NGX_NO_ATTEMPT 1
+#define NGX_CEN_SHIFT 2
+#define NGX_NONPOS_FLUX 4
+#define NGX_NONPOS_SIZE 8
+#define NGX_LOW_DET 16
+#define NGX_MAXITER 32
+#define NGX_NONPOS_VAR 64
+#define NGX_GMIX_RANGE_ERROR 128
+#define NGX_NONPOS_SHAPE_VAR 256
+#define NGX_LM_SINGULAR_MATRIX 512
+#define NGX_LM_NEG_COV_EIG 1024
+#define NGX_LM_NEG_COV_DIAG 2048
+#define NGX_LM_FUNC_NOTFINITE 4096
+#define NGX_EIG_NOTFINITE 8192
+#define NGX_DIV_ZERO 16384
+#define NGX_ZERO_DOF 32768
+#define NGX_EM_RANGE_ERROR NGX_GMIX_RANGE_ERROR
+#define NGX_EM_MAXITER NGX_MAXITER
+
+/* _gauss2d_dtype, ngmix/gmix/gmix.py:1196-1210 (104 bytes) */
+typedef struct {
+    double p, row, col, irr, irc, icc, det;
+    int64_t norm_set;
+    double drr, drc, dcc, norm, pnorm;
+} ngx_gauss;
+
+/* _pixels_dtype, ngmix/pixels/pixels.py:72-79 (48 bytes) */
+typedef struct { double u, v, area, val, ierr, fdiff; } ngx_pixel;
+
+/* _coords_dtype, ngmix/pixels/pixels.py:82-86 (24 bytes) */
+typedef struct { double u, v, area; } ngx_coord;
+
+/* _jacobian_dtype, ngmix/jacobian/jacobian.py:406-414 (64 bytes) */
+typedef struct {
+    double row0, col0, dvdrow, dvdcol, dudrow, dudcol, det, scale;
+} ngx_jacobian;
+
+/* ------------------------------------------------------------------ */
+/* library / device management */
+int ngx_version(void);
+const char *ngx_last_error(void);
+/* select the CUDA device for the calling thread; NGX_ERR_NODEVICE if none */
+int ngx_init(int device);
+/* sm count, shared memory per block, device name (name may be NULL) */
+int ngx_device_info(int *sm_count, int *smem_optin, char *name, int name_len);
+
+/* ------------------------------------------------------------------ */
+/* mixtures: replace gmix_fill_<model> (gmix_nb.py:307-558), gmix_set_norms
+ * (:176-218), gmix_convolve_fill (:609-649).  status[n] receives NGX_ST_*.
+ * pars is [n, npars]; gmix is [n, ngauss]. */
+int ngx_gmix_fill(int n, int model, int ngauss, const double *pars, int npars,
+                  ngx_gauss *gmix, int32_t *status, void *stream);
+/* composite model with fixed fracdev, TdByTe (gmix_nb.py:430-466);
+ * cm is [n, 3] = fracdev, TdByTe, Tfactor (get_cm_Tfactor :561-593) */
+int ngx_gmix_fill_cm(int n, const double *cm, const double *pars,
+                     ngx_gauss *gmix, int32_t *status, void *stream);
+int ngx_gmix_set_norms(int n, int ngauss, ngx_gauss *gmix, int32_t *status,
+                       void *stream);
+int ngx_gmix_convolve(int n, int nobj, int npsf, const ngx_gauss *obj,
+                      const ngx_gauss *psf, ngx_gauss *out, void *stream);
+
+/* pixels: replace fill_pixels / fill_coords (pixels_nb.py:6-94) and
+ * jacobian_get_vu (jacobian_nb.py:4-16).  pixels is [n, nrow*ncol]; the
+ * first npix[i] records of object i are valid (zero-weight pixels are
+ * dropped, in row-major order, when ignore_zero_weight != 0). */
+int ngx_make_pixels(int n, int nrow, int ncol, const double *images,
+                    const double *weights, const ngx_jacobian *jac,
+                    int ignore_zero_weight, ngx_pixel *pixels, int32_t *npix,
+                    void *stream);
+int ngx_make_coords(int n, int nrow, int ncol, const ngx_jacobian *jac,
+                    ngx_coord *coords, void *stream);
+
+/* render: replaces render (render_nb.py:9-36) + fill_coords.  Adds the
+ * mixture into images [n, nrow, ncol]; fast_exp != 0 uses the apodized
+ * fexp evaluation (gmix_nb.py:28-63), else exact exp (gmix_nb.py:66-92). */
+int ngx_render(int n, int ngauss, const ngx_gauss *gmix,
+               const ngx_jacobian *jac, int nrow, int ncol, int fast_exp,
+               double *images, int32_t *status, void *stream);
+
+/* one fused pixel pass replacing fill_fdiff (gmix_nb.py:877-900),
+ * get_loglike (:824-874) and get_model_s2n_sum (:903-937):
+ *   out4 [n,4] = loglike, s2n_numer, s2n_denom, npix
+ *   fdiff [n, nrow*ncol] (nullable) = (model-val)*ierr for the valid pixels
+ *   of object i, compacted in the reference's pixel order. */
+int ngx_loglike(int n, int ngauss, const ngx_gauss *gmix, const double *images,
+                const double *weights, const ngx_jacobian *jac, int nrow,
+                int ncol, int ignore_zero_weight, double *out4, double *fdiff,
+                int32_t *status, void *stream);
+
+/* same pass on a pre-built pixel array (the reference's own calling
+ * convention: fill_fdiff(gmix, pixels, fdiff, start)); pixels [n, maxpix],
+ * npix[n] valid records each; fdiff [n, maxpix] nullable */
+int ngx_loglike_pixels(int n, int ngauss, const ngx_gauss *gmix,
+                       const ngx_pixel *pixels, int maxpix,
+                       const int32_t *npix, double *out4, double *fdiff,
+                       int32_t *status, void *stream);
+
+/* deriv_images (fitting/derivs_nb.py:40-127): gpars [n,ngauss,6], dcov
+ * [n,ngauss,3,3], evaluated on the full nrow x ncol grid of jac;
+ * out [n,6,nrow*ncol] is ADDED to (zero it first, as the reference does) */
+int ngx_deriv_images(int n, int ngauss, const double *gpars,
+                     const double *dcov, const ngx_jacobian *jac, int nrow,
+                     int ncol, double *out, void *stream);
+
+/* ------------------------------------------------------------------ */
+/* priors of the LM residual vector (PriorSimpleSep joint_prior.py:5-236,
+ * PriorBDFSep :484-676) over CenPrior, GPriorBA, FlatPrior, TwoSidedErf,
+ * Normal */
+#define NGX_P_NONE 0
+#define NGX_P_FLAT 1      /* a=minval b=maxval */
+#define NGX_P_ERF 2       /* a=minval b=width_at_min c=maxval d=width_at_max */
+#define NGX_P_NORMAL 3    /* a=mean b=sigma */
+typedef struct { int32_t kind; int32_t pad; double a, b, c, d; } ngx_prior1d;
+typedef struct {
+    int32_t present;      /* 0 = fit without prior */
+    int32_t g_kind;       /* 1 = GPriorBA(g_sigma) */
+    double cen1, cen2, sigma1, sigma2;   /* CenPrior */
+    double g_sigma;
+    ngx_prior1d T;
+    ngx_prior1d fracdev;  /* bdf only */
+    ngx_prior1d F;
+} ngx_prior;
+
+/* DEFAULT_LM_PARS, ngmix/defaults.py:17 */
+typedef struct {
+    int32_t maxfev;             /* 4000 */
+    int32_t analytic_jacobian;  /* Fitter(analytic_jacobian=True) */
+    double ftol, xtol;          /* 1e-5, 1e-5 */
+} ngx_lm_pars;
+
+/* result record of one fit: the keys of run_leastsq
+ * (fitting/leastsqbound.py:118-126) + FitModel.set_fit_result
+ * (fitting/results.py:45-72).  Matrices are row major npars x npars. */
+typedef struct {
+    int32_t flags, nfev, ier, npix, dof, njev;
+    double lnprob, s2n_numer, s2n_denom, chi2per, s2n, T, T_err, flux,
+        flux_err;
+    double pars[8], pars_err[8], pars_cov0[64], pars_cov[64];
+} ngx_lm_result;
+
+/* Fitter(model, prior, fit_pars).go(obs, guess) for n stamps
+ * (fitting/fitters.py:64-112): FitModel.calc_fdiff/calc_jacobian
+ * (results.py:439-625), the MINPACK lmder/lmdif iteration reached through
+ * scipy.optimize.leastsq (leastsqbound.py:445-447), run_leastsq's epilogue
+ * (:70-126) and set_fit_result, all on the device.
+ * images/weights [n,nrow,ncol]; psf_pars [n,npsf,6] full gaussian pars of
+ * obs.psf.gmix (npsf = 0: no psf); guess [n,npars]. */
+int ngx_lm_fit(int n, int model, const double *images, const double *weights,
+               const ngx_jacobian *jac, int nrow, int ncol,
+               const double *psf_pars, int npsf, const double *guess,
+               const ngx_prior *prior, const ngx_lm_pars *lm_pars,
+               int ignore_zero_weight, ngx_lm_result *res, void *stream);
+
+/* counters of the last ngx_lm_fit launch on this thread's device: number of
+ * residual-pass and jacobian-pass pixel evaluations actually executed */
+int ngx_lm_work(int n, const ngx_lm_result *res_host, int nrow, int ncol,
+                int ngauss, double *value_evals, double *deriv_evals);
+
+/* ------------------------------------------------------------------ */
+/* EM: EMFitter*.go (em/em.py:228-317) = prep_image (:95-120) + em_run /
+ * em_run_fixcen / em_run_fixcov / em_run_fluxonly (em/em_nb.py:15-1257) */
+#define NGX_EM_FULL 0
+#define NGX_EM_FIXCEN 1
+#define NGX_EM_FIXCOV 2
+#define NGX_EM_FLUXONLY 3
+typedef struct {
+    double tol;          /* 1e-5 */
+    int32_t maxiter;     /* 500 */
+    int32_t miniter;     /* 40 (20 for fluxonly) */
+    double sky;          /* used when have_sky != 0 */
+    int32_t vary_sky;
+    int32_t have_sky;    /* 0: run prep_image to choose the sky */
+} ngx_em_conf;
+typedef struct {
+    int32_t flags, numiter;
+    double fdiff, sky;
+} ngx_em_result;
+/* guess [n,ngauss,6] full pars before psf convolution; psf_pars [n,npsf,6]
+ * (npsf = 0 -> delta psf); pars_out [n,ngauss,6] */
+int ngx_em(int n, int variant, const double *images, const double *weights,
+           const ngx_jacobian *jac, int nrow, int ncol, const double *guess,
+           int ngauss, const double *psf_pars, int npsf,
+           const ngx_em_conf *conf, int ignore_zero_weight, double *pars_out,
+           ngx_em_result *res, void *stream);
+
+/* admom (admom/admom_nb.py:13-243); result = _admom_result_dtype
+ * (admom/admom.py:571-583, aligned) */
+typedef struct {
+    int32_t maxiter;     /* 200 */
+    int32_t cenonly;
+    double shiftmax;     /* 5.0 */
+    double etol;         /* 1e-5 */
+    double Ttol;         /* 1e-3 */
+} ngx_admom_conf;
+typedef struct {
+    int32_t flags, numiter, npix, pad;
+    double wsum;
+    double sums[7];
+    double sums_cov[49];
+    double pars[6];
+    double rho4;
+    double F[7];
+    double wt_norm;      /* wt_gmix["norm"][0] at exit, for get_result */
+} ngx_admom_result;
+/* guess [n,6] full pars of the 1-gaussian weight */
+int ngx_admom(int n, const double *images, const double *weights,
+              const ngx_jacobian *jac, int nrow, int ncol, const double *guess,
+              const ngx_admom_conf *conf, ngx_admom_result *res, void *stream);
+
+/* ------------------------------------------------------------------ */
+/* host-buffer variants (synchronous; H2D/D2H inside) */
+int ngx_gmix_fill_host(int n, int model, int ngauss, const double *pars,
+                       int npars, ngx_gauss *gmix, int32_t *status);
+int ngx_gmix_fill_cm_host(int n, const double *cm, const double *pars,
+                          ngx_gauss *gmix, int32_t *status);
+int ngx_gmix_set_norms_host(int n, int ngauss, ngx_gauss *gmix,
+                            int32_t *status);
+int ngx_gmix_convolve_host(int n, int nobj, int npsf, const ngx_gauss *obj,
+                           const ngx_gauss *psf, ngx_gauss *out);
+int ngx_make_pixels_host(int n, int nrow, int ncol, const double *images,
+                         const double *weights, const ngx_jacobian *jac,
+                         int ignore_zero_weight, ngx_pixel *pixels,
+                         int32_t *npix);
+int ngx_make_coords_host(int n, int nrow, int ncol, const ngx_jacobian *jac,
+                         ngx_coord *coords);
+int ngx_render_host(int n, int ngauss, const ngx_gauss *gmix,
+                    const ngx_jacobian *jac, int nrow, int ncol, int fast_exp,
+                    double *images, int32_t *status);
+int ngx_loglike_host(int n, int ngauss, const ngx_gauss *gmix,
+                     const double *images, const double *weights,
+                     const ngx_jacobian *jac, int nrow, int ncol,
+                     int ignore_zero_weight, double *out4, double *fdiff,
+                     int32_t *status);
+int ngx_loglike_pixels_host(int n, int ngauss, const ngx_gauss *gmix,
+                            const ngx_pixel *pixels, int maxpix,
+                            const int32_t *npix, double *out4, double *fdiff,
+                            int32_t *status);
+int ngx_deriv_images_host(int n, int ngauss, const double *gpars,
+                          const double *dcov, const ngx_jacobian *jac,
+                          int nrow, int ncol, double *out);
+int ngx_lm_fit_host(int n, int model, const double *images,
+                    const double *weights, const ngx_jacobian *jac, int nrow,
+                    int ncol, const double *psf_pars, int npsf,
+                    const double *guess, const ngx_prior *prior,
+                    const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                    ngx_lm_result *res);
+int ngx_em_host(int n, int variant, const double *images,
+                const double *weights, const ngx_jacobian *jac, int nrow,
+                int ncol, const double *guess, int ngauss,
+                const double *psf_pars, int npsf, const ngx_em_conf *conf,
+                int ignore_zero_weight, double *pars_out, ngx_em_result *res);
+int ngx_admom_host(int n, const double *images, const double *weights,
+                   const ngx_jacobian *jac, int nrow, int ncol,
+                   const double *guess, const ngx_admom_conf *conf,
+                   ngx_admom_result *res);
+
+/* FP64 pipe micro-benchmark used for the roofline denominator: runs a
+ * register-resident chain of `iters` x 8 independent DFMAs per thread on a
+ * full grid and returns the measured fp64 FMA instructions (lane ops) per
+ * second in *dfma_per_s.  Device pointers are not needed. */
+int ngx_peak_dfma(int iters, double *dfma_per_s, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGX_H */

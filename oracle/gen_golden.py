@@ -415,6 +415,25 @@ def gen_lm_other():
         out["expfd_" + k] = b[k]
     for k, v in _run_lm_set(b, "none", analytic=False).items():
         out["expfd_none_" + k] = v
+    # poor guesses: trial steps leave the model's domain (|g| >= 1, T < 0),
+    # calc_fdiff returns -inf and MINPACK must reject the step
+    b = sims.make_lm_batch(24, seed0=12000, noise=1.0, guess_frac=0.0,
+                           dims=(32, 32))
+    rng = np.random.RandomState(5)
+    for i in range(24):
+        guess = b["truth"][i].copy()
+        guess[0:2] = rng.uniform(-0.3, 0.3, 2)
+        guess[2:4] = rng.uniform(-0.65, 0.65, 2)
+        guess[4] = rng.uniform(0.02, 3.0)
+        guess[5] *= rng.uniform(0.1, 5)
+        b["guess"][i] = guess
+    for k in ("images", "weights", "jac", "psf", "guess"):
+        out["bad_" + k] = b[k]
+    for pk in ("none", "flat"):
+        r = _run_lm_set(b, pk)
+        print("bad", pk, "nfev", r["nfev"], "flags", r["flags"])
+        for k, v in r.items():
+            out["bad_%s_%s" % (pk, k)] = v
     save("lm_other", **out)
 
 

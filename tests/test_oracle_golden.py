@@ -221,7 +221,9 @@ def test_lm_other_models(ora):
     g = load_golden("lm_other")
     for tag, pk, model, analytic in (("gauss", "none", "gauss", True),
                                      ("dev", "flat", "dev", True),
-                                     ("expfd", "none", "exp", False)):
+                                     ("expfd", "none", "exp", False),
+                                     ("bad", "none", "exp", True),
+                                     ("bad", "flat", "exp", True)):
         nbad, n = _check_lm(ora, g, tag, pk, model=model, analytic=analytic)
         assert nbad == 0, (tag, nbad)
 
