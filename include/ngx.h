@@ -216,11 +216,6 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
                const ngx_prior *prior, const ngx_lm_pars *lm_pars,
                int ignore_zero_weight, ngx_lm_result *res, void *stream);
 
-/* counters of the last ngx_lm_fit launch on this thread's device: number of
- * residual-pass and jacobian-pass pixel evaluations actually executed */
-int ngx_lm_work(int n, const ngx_lm_result *res_host, int nrow, int ncol,
-                int ngauss, double *value_evals, double *deriv_evals);
-
 /* ------------------------------------------------------------------ */
 /* EM: EMFitter*.go (em/em.py:228-317) = prep_image (:95-120) + em_run /
  * em_run_fixcen / em_run_fixcov / em_run_fluxonly (em/em_nb.py:15-1257) */

@@ -1,0 +1,439 @@
+"""
+ctypes binding of the engine's C ABI (include/ngx.h, built into
+ngmix_b200/csrc/libngx.so by ngmix_b200/csrc/Makefile).
+
+There is NO CPU fallback: if the library is missing, or no CUDA device is
+visible when a compute entry point is called, an error is raised.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBPATH = os.path.join(CSRC, "libngx.so")
+
+
+class NgxError(RuntimeError):
+    """API misuse or CUDA failure reported by libngx"""
+
+
+# ---- record layouts (byte-identical to the reference's numpy dtypes)
+GAUSS_DTYPE = np.dtype([
+    ("p", "f8"), ("row", "f8"), ("col", "f8"), ("irr", "f8"), ("irc", "f8"),
+    ("icc", "f8"), ("det", "f8"), ("norm_set", "i8"), ("drr", "f8"),
+    ("drc", "f8"), ("dcc", "f8"), ("norm", "f8"), ("pnorm", "f8")])
+PIXEL_DTYPE = np.dtype([
+    ("u", "f8"), ("v", "f8"), ("area", "f8"), ("val", "f8"), ("ierr", "f8"),
+    ("fdiff", "f8")])
+COORD_DTYPE = np.dtype([("u", "f8"), ("v", "f8"), ("area", "f8")])
+JACOBIAN_DTYPE = np.dtype([
+    ("row0", "f8"), ("col0", "f8"), ("dvdrow", "f8"), ("dvdcol", "f8"),
+    ("dudrow", "f8"), ("dudcol", "f8"), ("det", "f8"), ("scale", "f8")])
+
+LM_RESULT_DTYPE = np.dtype([
+    ("flags", "i4"), ("nfev", "i4"), ("ier", "i4"), ("npix", "i4"),
+    ("dof", "i4"), ("njev", "i4"), ("lnprob", "f8"), ("s2n_numer", "f8"),
+    ("s2n_denom", "f8"), ("chi2per", "f8"), ("s2n", "f8"), ("T", "f8"),
+    ("T_err", "f8"), ("flux", "f8"), ("flux_err", "f8"), ("pars", "f8", 8),
+    ("pars_err", "f8", 8), ("pars_cov0", "f8", 64), ("pars_cov", "f8", 64)])
+EM_RESULT_DTYPE = np.dtype([("flags", "i4"), ("numiter", "i4"),
+                            ("fdiff", "f8"), ("sky", "f8")])
+ADMOM_RESULT_DTYPE = np.dtype([
+    ("flags", "i4"), ("numiter", "i4"), ("npix", "i4"), ("pad", "i4"),
+    ("wsum", "f8"), ("sums", "f8", 7), ("sums_cov", "f8", (7, 7)),
+    ("pars", "f8", 6), ("rho4", "f8"), ("F", "f8", 7), ("wt_norm", "f8")])
+
+assert GAUSS_DTYPE.itemsize == 104 and PIXEL_DTYPE.itemsize == 48
+assert LM_RESULT_DTYPE.itemsize == 1248 and ADMOM_RESULT_DTYPE.itemsize == 592
+
+MODELS = {"full": 0, "gauss": 1, "turb": 2, "exp": 3, "dev": 4, "bdf": 6,
+          "coellip": 7, "cm": 9, "bd": 10}
+EM_VARIANTS = {"full": 0, "fixcen": 1, "fixcov": 2, "fluxonly": 3}
+
+ST_OK, ST_RANGE_ERROR, ST_ZERO_DIV, ST_FATAL = 0, 1, 2, 3
+
+
+class Prior1D(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("pad", C.c_int32), ("a", C.c_double),
+                ("b", C.c_double), ("c", C.c_double), ("d", C.c_double)]
+
+
+class Prior(C.Structure):
+    _fields_ = [("present", C.c_int32), ("g_kind", C.c_int32),
+                ("cen1", C.c_double), ("cen2", C.c_double),
+                ("sigma1", C.c_double), ("sigma2", C.c_double),
+                ("g_sigma", C.c_double), ("T", Prior1D),
+                ("fracdev", Prior1D), ("F", Prior1D)]
+
+
+class LMPars(C.Structure):
+    _fields_ = [("maxfev", C.c_int32), ("analytic_jacobian", C.c_int32),
+                ("ftol", C.c_double), ("xtol", C.c_double)]
+
+
+class EMConf(C.Structure):
+    _fields_ = [("tol", C.c_double), ("maxiter", C.c_int32),
+                ("miniter", C.c_int32), ("sky", C.c_double),
+                ("vary_sky", C.c_int32), ("have_sky", C.c_int32)]
+
+
+class AdmomConf(C.Structure):
+    _fields_ = [("maxiter", C.c_int32), ("cenonly", C.c_int32),
+                ("shiftmax", C.c_double), ("etol", C.c_double),
+                ("Ttol", C.c_double)]
+
+
+# every symbol include/ngx.h declares
+SYMBOLS = [
+    "ngx_version", "ngx_last_error", "ngx_init", "ngx_device_info",
+    "ngx_gmix_fill", "ngx_gmix_fill_cm", "ngx_gmix_set_norms",
+    "ngx_gmix_convolve", "ngx_make_pixels", "ngx_make_coords", "ngx_render",
+    "ngx_loglike", "ngx_loglike_pixels", "ngx_deriv_images", "ngx_lm_fit",
+    "ngx_em", "ngx_admom",
+    "ngx_gmix_fill_host", "ngx_gmix_fill_cm_host", "ngx_gmix_set_norms_host",
+    "ngx_gmix_convolve_host", "ngx_make_pixels_host", "ngx_make_coords_host",
+    "ngx_render_host", "ngx_loglike_host", "ngx_loglike_pixels_host",
+    "ngx_deriv_images_host", "ngx_lm_fit_host", "ngx_em_host",
+    "ngx_admom_host", "ngx_peak_dfma",
+]
+
+_lib = None
+_inited_device = None
+
+
+def build(force=False):
+    """compile libngx.so for sm_100a (nvcc cross-compiles without a GPU)"""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+            if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(HERE), "include", "ngx.h"))
+    if not force and os.path.exists(LIBPATH):
+        mt = os.path.getmtime(LIBPATH)
+        if all(os.path.getmtime(s) <= mt for s in srcs):
+            return LIBPATH
+    subprocess.check_call(["make", "-C", CSRC, "libngx.so"])
+    return LIBPATH
+
+
+def lib():
+    """load libngx.so; raises if it is missing (no fallback)"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIBPATH):
+            raise NgxError(
+                "libngx.so is not built (%s); run `python -c 'import "
+                "__graft_entry__ as g; g.build()'` or `make -C "
+                "ngmix_b200/csrc`.  There is no CPU fallback." % LIBPATH)
+        _lib = C.CDLL(LIBPATH)
+        _lib.ngx_last_error.restype = C.c_char_p
+        for name in SYMBOLS:
+            getattr(_lib, name)      # AttributeError if a symbol is missing
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise NgxError("libngx error %d: %s"
+                       % (rc, lib().ngx_last_error().decode()))
+
+
+def init(device=None):
+    """select the CUDA device; raises NgxError when there is none"""
+    global _inited_device
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) \
+            if _inited_device is None else _inited_device
+    if _inited_device != device:
+        check(lib().ngx_init(C.c_int(device)))
+        _inited_device = device
+    return device
+
+
+def _p(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f8(a):
+    return np.ascontiguousarray(a, dtype="f8")
+
+
+def as_jac(jac, n=None):
+    """[n,8] float or structured jacobian records -> contiguous f8 [n,8]"""
+    if isinstance(jac, np.ndarray) and jac.dtype == JACOBIAN_DTYPE:
+        jac = jac.view("f8").reshape(-1, 8)
+    jac = _f8(jac).reshape(-1, 8)
+    if n is not None:
+        assert jac.shape[0] == n, "one jacobian per object"
+    return jac
+
+
+# ---------------------------------------------------------------- mixtures
+def gmix_fill(model, pars):
+    """pars [n, npars] -> (gmix [n, ngauss] GAUSS_DTYPE, status [n])"""
+    init()
+    pars = np.atleast_2d(_f8(pars))
+    n, npars = pars.shape
+    if model == "coellip":
+        ngauss = (npars - 4) // 2
+    elif model == "full":
+        ngauss = npars // 6
+    else:
+        ngauss = {"gauss": 1, "turb": 3, "exp": 6, "dev": 10, "bdf": 16,
+                  "bd": 16}[model]
+    gm = np.zeros((n, ngauss), dtype=GAUSS_DTYPE)
+    st = np.zeros(n, dtype="i4")
+    check(lib().ngx_gmix_fill_host(C.c_int(n), C.c_int(MODELS[model]),
+                                   C.c_int(ngauss), _p(pars), C.c_int(npars),
+                                   _p(gm), _p(st)))
+    return gm, st
+
+
+def gmix_fill_cm(cm, pars):
+    init()
+    cm = np.atleast_2d(_f8(cm))
+    pars = np.atleast_2d(_f8(pars))
+    n = pars.shape[0]
+    gm = np.zeros((n, 16), dtype=GAUSS_DTYPE)
+    st = np.zeros(n, dtype="i4")
+    check(lib().ngx_gmix_fill_cm_host(C.c_int(n), _p(cm), _p(pars), _p(gm),
+                                      _p(st)))
+    return gm, st
+
+
+def gmix_set_norms(gm):
+    """in place on gm [n, ngauss]; returns status [n]"""
+    init()
+    assert gm.dtype == GAUSS_DTYPE and gm.flags.c_contiguous
+    g2 = gm.reshape(-1, gm.shape[-1])
+    st = np.zeros(g2.shape[0], dtype="i4")
+    check(lib().ngx_gmix_set_norms_host(C.c_int(g2.shape[0]),
+                                        C.c_int(g2.shape[1]), _p(g2), _p(st)))
+    return st
+
+
+def gmix_convolve(obj, psf):
+    init()
+    obj = np.ascontiguousarray(obj).reshape(-1, obj.shape[-1])
+    psf = np.ascontiguousarray(psf).reshape(-1, psf.shape[-1])
+    n = obj.shape[0]
+    out = np.zeros((n, obj.shape[1] * psf.shape[1]), dtype=GAUSS_DTYPE)
+    check(lib().ngx_gmix_convolve_host(C.c_int(n), C.c_int(obj.shape[1]),
+                                       C.c_int(psf.shape[1]), _p(obj),
+                                       _p(psf), _p(out)))
+    return out
+
+
+# ---------------------------------------------------------------- pixels
+def make_pixels(images, weights, jac, ignore_zero_weight=True):
+    """images/weights [n,H,W] -> (pixels [n,H*W] PIXEL_DTYPE, npix [n])"""
+    init()
+    images = _f8(images)
+    weights = _f8(weights)
+    if images.ndim == 2:
+        images, weights = images[None], weights[None]
+    n, H, W = images.shape
+    jac = as_jac(jac, n)
+    pixels = np.zeros((n, H * W), dtype=PIXEL_DTYPE)
+    npix = np.zeros(n, dtype="i4")
+    check(lib().ngx_make_pixels_host(
+        C.c_int(n), C.c_int(H), C.c_int(W), _p(images), _p(weights), _p(jac),
+        C.c_int(int(ignore_zero_weight)), _p(pixels), _p(npix)))
+    return pixels, npix
+
+
+def make_coords(dims, jac):
+    init()
+    jac = as_jac(jac)
+    n = jac.shape[0]
+    coords = np.zeros((n, dims[0] * dims[1]), dtype=COORD_DTYPE)
+    check(lib().ngx_make_coords_host(C.c_int(n), C.c_int(dims[0]),
+                                     C.c_int(dims[1]), _p(jac), _p(coords)))
+    return coords
+
+
+# ---------------------------------------------------------------- passes
+def render(gm, jac, dims, fast_exp=False, images=None):
+    """adds gm [n, ngauss] into images [n,H,W] (zeros if None)"""
+    init()
+    gm = np.ascontiguousarray(gm).reshape(-1, gm.shape[-1])
+    n = gm.shape[0]
+    jac = as_jac(jac, n)
+    if images is None:
+        images = np.zeros((n, dims[0], dims[1]))
+    else:
+        images = _f8(images).reshape(n, dims[0], dims[1])
+    st = np.zeros(n, dtype="i4")
+    check(lib().ngx_render_host(C.c_int(n), C.c_int(gm.shape[1]), _p(gm),
+                                _p(jac), C.c_int(dims[0]), C.c_int(dims[1]),
+                                C.c_int(int(fast_exp)), _p(images), _p(st)))
+    return images, st
+
+
+def loglike(gm, images, weights, jac, ignore_zero_weight=True,
+            want_fdiff=False):
+    """fused fdiff/loglike/s2n pass; returns (out4 [n,4], fdiff|None, status)"""
+    init()
+    gm = np.ascontiguousarray(gm).reshape(-1, gm.shape[-1])
+    n = gm.shape[0]
+    images = _f8(images).reshape(n, *np.shape(images)[-2:])
+    weights = _f8(weights).reshape(images.shape)
+    H, W = images.shape[1:]
+    jac = as_jac(jac, n)
+    out4 = np.zeros((n, 4))
+    fdiff = np.zeros((n, H * W)) if want_fdiff else None
+    st = np.zeros(n, dtype="i4")
+    check(lib().ngx_loglike_host(
+        C.c_int(n), C.c_int(gm.shape[1]), _p(gm), _p(images), _p(weights),
+        _p(jac), C.c_int(H), C.c_int(W), C.c_int(int(ignore_zero_weight)),
+        _p(out4), _p(fdiff), _p(st)))
+    return out4, fdiff, st
+
+
+def loglike_pixels(gm, pixels, npix=None, want_fdiff=False):
+    """same pass on pre-built pixel records [n, maxpix]"""
+    init()
+    gm = np.ascontiguousarray(gm).reshape(-1, gm.shape[-1])
+    n = gm.shape[0]
+    pixels = np.ascontiguousarray(pixels).reshape(n, -1)
+    maxpix = pixels.shape[1]
+    if npix is None:
+        npix = np.full(n, maxpix, dtype="i4")
+    npix = np.ascontiguousarray(npix, dtype="i4")
+    out4 = np.zeros((n, 4))
+    fdiff = np.zeros((n, maxpix)) if want_fdiff else None
+    st = np.zeros(n, dtype="i4")
+    check(lib().ngx_loglike_pixels_host(
+        C.c_int(n), C.c_int(gm.shape[1]), _p(gm), _p(pixels), C.c_int(maxpix),
+        _p(npix), _p(out4), _p(fdiff), _p(st)))
+    return out4, fdiff, st
+
+
+def deriv_images(gpars, dcov, jac, dims):
+    init()
+    gpars = _f8(gpars)
+    if gpars.ndim == 2:
+        gpars = gpars[None]
+    n, ngauss = gpars.shape[:2]
+    dcov = _f8(dcov).reshape(n, ngauss, 3, 3)
+    jac = as_jac(jac, n)
+    out = np.zeros((n, 6, dims[0] * dims[1]))
+    check(lib().ngx_deriv_images_host(C.c_int(n), C.c_int(ngauss), _p(gpars),
+                                      _p(dcov), _p(jac), C.c_int(dims[0]),
+                                      C.c_int(dims[1]), _p(out)))
+    return out
+
+
+# ---------------------------------------------------------------- LM
+def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
+           maxfev=4000, ftol=1.0e-5, xtol=1.0e-5, analytic_jacobian=True,
+           ignore_zero_weight=True):
+    """
+    batched Fitter.go through the host-buffer entry point.
+    images/weights [n,H,W]; psf_pars [n,npsf,6] or None; guess [n,npars].
+    Returns LM_RESULT_DTYPE [n].
+    """
+    init()
+    images = _f8(images)
+    weights = _f8(weights)
+    if images.ndim == 2:
+        images, weights = images[None], weights[None]
+    n, H, W = images.shape
+    jac = as_jac(jac, n)
+    guess = np.atleast_2d(_f8(guess))
+    if psf_pars is None:
+        npsf = 0
+    else:
+        psf_pars = _f8(psf_pars).reshape(n, -1, 6)
+        npsf = psf_pars.shape[1]
+    pr = prior if prior is not None else Prior()
+    lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)
+    res = np.zeros(n, dtype=LM_RESULT_DTYPE)
+    check(lib().ngx_lm_fit_host(
+        C.c_int(n), C.c_int(MODELS[model]), _p(images), _p(weights), _p(jac),
+        C.c_int(H), C.c_int(W), _p(psf_pars), C.c_int(npsf), _p(guess),
+        C.byref(pr), C.byref(lmp), C.c_int(int(ignore_zero_weight)), _p(res)))
+    return res
+
+
+def lm_fit_device(model, n, d_images, d_weights, d_jac, nrow, ncol, d_psf,
+                  npsf, d_guess, d_res, prior=None, maxfev=4000, ftol=1.0e-5,
+                  xtol=1.0e-5, analytic_jacobian=True, ignore_zero_weight=True,
+                  stream=0):
+    """
+    device-pointer entry point: d_* are integer device addresses (for example
+    torch tensors' data_ptr()); enqueues on `stream` and returns at once.
+    """
+    pr = prior if prior is not None else Prior()
+    lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)
+    check(lib().ngx_lm_fit(
+        C.c_int(n), C.c_int(MODELS[model]), C.c_void_p(d_images),
+        C.c_void_p(d_weights), C.c_void_p(d_jac), C.c_int(nrow),
+        C.c_int(ncol), C.c_void_p(d_psf) if npsf else None, C.c_int(npsf),
+        C.c_void_p(d_guess), C.byref(pr), C.byref(lmp),
+        C.c_int(int(ignore_zero_weight)), C.c_void_p(d_res),
+        C.c_void_p(stream)))
+
+
+# ---------------------------------------------------------------- EM / admom
+def em(images, weights, jac, guess, psf_pars=None, variant="full",
+       tol=1.0e-5, miniter=None, maxiter=500, vary_sky=False, sky=None,
+       ignore_zero_weight=True):
+    """batched EMFitter*.go; guess [n,ngauss,6]; returns (res, pars_out)"""
+    init()
+    images = _f8(images)
+    weights = _f8(weights)
+    if images.ndim == 2:
+        images, weights = images[None], weights[None]
+    n, H, W = images.shape
+    jac = as_jac(jac, n)
+    guess = _f8(guess).reshape(n, -1, 6)
+    ngauss = guess.shape[1]
+    if psf_pars is None:
+        npsf = 0
+    else:
+        psf_pars = _f8(psf_pars).reshape(n, -1, 6)
+        npsf = psf_pars.shape[1]
+    if miniter is None:
+        miniter = 20 if variant == "fluxonly" else 40
+    conf = EMConf(tol, maxiter, miniter, 0.0 if sky is None else sky,
+                  int(vary_sky), int(sky is not None))
+    pars_out = np.zeros((n, ngauss, 6))
+    res = np.zeros(n, dtype=EM_RESULT_DTYPE)
+    check(lib().ngx_em_host(
+        C.c_int(n), C.c_int(EM_VARIANTS[variant]), _p(images), _p(weights),
+        _p(jac), C.c_int(H), C.c_int(W), _p(guess), C.c_int(ngauss),
+        _p(psf_pars), C.c_int(npsf), C.byref(conf),
+        C.c_int(int(ignore_zero_weight)), _p(pars_out), _p(res)))
+    return res, pars_out
+
+
+def admom(images, weights, jac, guess, maxiter=200, shiftmax=5.0,
+          etol=1.0e-5, Ttol=1.0e-3, cenonly=False):
+    """batched admom; guess [n,6] full pars of the weight gaussian"""
+    init()
+    images = _f8(images)
+    weights = _f8(weights)
+    if images.ndim == 2:
+        images, weights = images[None], weights[None]
+    n, H, W = images.shape
+    jac = as_jac(jac, n)
+    guess = np.atleast_2d(_f8(guess))
+    conf = AdmomConf(maxiter, int(cenonly), shiftmax, etol, Ttol)
+    res = np.zeros(n, dtype=ADMOM_RESULT_DTYPE)
+    check(lib().ngx_admom_host(C.c_int(n), _p(images), _p(weights), _p(jac),
+                               C.c_int(H), C.c_int(W), _p(guess),
+                               C.byref(conf), _p(res)))
+    return res
+
+
+def peak_dfma(iters=20000):
+    """measured fp64 FMA lane-ops per second of the current device"""
+    init()
+    out = C.c_double()
+    ms = C.c_double()
+    check(lib().ngx_peak_dfma(C.c_int(iters), C.byref(out), C.byref(ms)))
+    return out.value, ms.value

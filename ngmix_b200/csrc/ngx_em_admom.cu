@@ -1,0 +1,805 @@
+// ngx_em: EMFitter*.go (ngmix/em/em.py:228-317) = prep_image (:95-120) +
+//         em_run / _fixcen / _fixcov / _fluxonly (em/em_nb.py:15-1257)
+// ngx_admom: admom (ngmix/admom/admom_nb.py:13-243)
+//
+// One CTA per stamp, the whole iteration loop inside the kernel.  The stamp
+// (val + a validity/zero-weight code) stays in shared memory; per iteration
+// the E step runs over the pixels with the per-gaussian sums in registers,
+// a shuffle/shared-memory block reduction (fixed order, no atomics) forms
+// the 6*ngauss+2 (EM) or 37 (admom) sums, and the M step / moment update is
+// done by the first ngauss threads.
+#include "ngx_core.cuh"
+#include "ngx_host.cuh"
+
+namespace ngx {
+
+#define NGX_EM_MAX_CONV 48
+
+// gaussian record used inside the EM kernel
+struct EMGauss {
+    double p, row, col, irr, irc, icc;
+};
+
+struct EMShared {
+    EMGauss gm[10];           // pre-psf mixture being fitted
+    EMGauss psf[16];
+    GaussV conv[NGX_EM_MAX_CONV];
+    double logtd[NGX_EM_MAX_CONV];   // logtau - 0.5 logdet of conv gaussians
+    double tab[16];
+    double psf_irr, psf_irc, psf_icc, psf_row, psf_col, psf_ipsum;
+    double sky, elogL_last, frac_diff, p_last;
+    double red[64];           // reduced sums
+    ngx_jacobian jac;
+    int npix, numiter, status, done, fill_zero, stamp;
+    int warp_i[32];
+};
+
+// convolve gm with psf and set norms; thread k < ngauss*npsf.
+// em_nb.py:343-354 (gmix_convolve_fill + gmix_set_norms) and
+// set_logtau_logdet :658-675
+__device__ __forceinline__ void em_build_conv(EMShared *sh, int ngauss,
+                                              int npsf, double area) {
+    int k = threadIdx.x;
+    if (k >= ngauss * npsf) return;
+    int io = k / npsf, ip = k - io * npsf;
+    const EMGauss &o = sh->gm[io];
+    const EMGauss &q = sh->psf[ip];
+    ngx_gauss g;
+    gauss_set(g, o.p * q.p * sh->psf_ipsum, o.row + (q.row - sh->psf_row),
+              o.col + (q.col - sh->psf_col), o.irr + q.irr, o.irc + q.irc,
+              o.icc + q.icc);
+    if (gauss_set_norm(g) != NGX_ST_OK) {
+        atomicOr(&sh->status, NGX_ST_RANGE_ERROR);
+        return;
+    }
+    sh->conv[k] = make_gaussv(g, area);
+    sh->logtd[k] = log(g.p) - 0.5 * log(g.det);
+}
+
+// VARIANT: NGX_EM_FULL / FIXCEN / FIXCOV / FLUXONLY; NG = object gaussians
+template <int VARIANT, int NG>
+__global__ void __launch_bounds__(128)
+k_em(int n, const double *__restrict__ images,
+     const double *__restrict__ weights, const ngx_jacobian *__restrict__ jac,
+     int nrow, int ncol, const double *__restrict__ guess, int ngauss,
+     const double *__restrict__ psf_pars, int npsf_in, ngx_em_conf conf,
+     int ignore_zero_weight, double *__restrict__ pars_out,
+     ngx_em_result *__restrict__ res) {
+    extern __shared__ double smem_d[];
+    __shared__ EMShared sh;
+    constexpr bool DO_CEN = (VARIANT == NGX_EM_FULL || VARIANT == NGX_EM_FIXCOV);
+    constexpr bool DO_COV = (VARIANT == NGX_EM_FULL || VARIANT == NGX_EM_FIXCEN);
+    constexpr bool DO_LOGL = (VARIANT != NGX_EM_FLUXONLY);
+    constexpr int NS = 6 * NG + 2;      // per gaussian 6, + elogL + skysum
+    const int T = blockDim.x;
+    const int nwarps = T >> 5;
+    const int ntot = nrow * ncol;
+    const int npsf = npsf_in > 0 ? npsf_in : 1;
+    double *val = smem_d;               // ntot
+    double *code = val + ntot;          // ntot: <0 excluded, 0 zero weight
+    double *rowd = code + ntot;
+    double *cold = rowd + nrow;
+    double *scratch = cold + ncol;      // NS * nwarps
+
+    const int stamp = blockIdx.x;
+    if (stamp >= n) return;
+    const double *im = images + (size_t)stamp * ntot;
+    const double *wt = weights + (size_t)stamp * ntot;
+
+    // ---- stage the stamp; min/max for prep_image
+    double mn = INFINITY, mx = -INFINITY;
+    int cnt = 0, nzero = 0;
+    for (int p = threadIdx.x; p < ntot; p += T) {
+        double w = wt[p], v = im[p];
+        bool valid = !(ignore_zero_weight && w <= 0.0);
+        val[p] = v;
+        code[p] = valid ? (w > 0.0 ? 1.0 : 0.0) : -1.0;
+        if (valid) cnt++;
+        if (valid && !(w > 0.0)) nzero++;
+        mn = fmin(mn, v);       // prep_image uses the whole image
+        mx = fmax(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
+    }
+    {
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) {
+            scratch[warp] = mn;
+            scratch[nwarps + warp] = mx;
+            sh.warp_i[warp] = cnt;
+            sh.warp_i[16 + warp] = nzero;
+        }
+    }
+    load_exp_table(sh.tab);
+    if (threadIdx.x == 0) {
+        sh.jac = jac[stamp];
+        sh.status = 0;
+        sh.done = 0;
+        sh.numiter = 0;
+        sh.frac_diff = nan("");
+        sh.elogL_last = -9999.9e9;
+    }
+    if (threadIdx.x < ngauss) {
+        const double *g = guess + ((size_t)stamp * ngauss + threadIdx.x) * 6;
+        EMGauss e = {g[0], g[1], g[2], g[3], g[4], g[5]};
+        sh.gm[threadIdx.x] = e;
+    }
+    if (threadIdx.x < npsf) {
+        EMGauss e = {1.0, 0.0, 0.0, 0.0, 0.0, 0.0};    // delta psf, em.py:256
+        if (npsf_in > 0) {
+            const double *g = psf_pars
+                + ((size_t)stamp * npsf + threadIdx.x) * 6;
+            e.p = g[0]; e.row = g[1]; e.col = g[2];
+            e.irr = g[3]; e.irc = g[4]; e.icc = g[5];
+        }
+        sh.psf[threadIdx.x] = e;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < nrow; p += T) rowd[p] = p - sh.jac.row0;
+    for (int p = threadIdx.x; p < ncol; p += T) cold[p] = p - sh.jac.col0;
+    if (threadIdx.x == 0) {
+        double a = INFINITY, b = -INFINITY;
+        int c = 0, z = 0;
+        for (int w = 0; w < nwarps; w++) {
+            a = fmin(a, scratch[w]);
+            b = fmax(b, scratch[nwarps + w]);
+            c += sh.warp_i[w];
+            z += sh.warp_i[16 + w];
+        }
+        sh.npix = c;
+        sh.fill_zero = z > 0;
+        if (conf.have_sky) {
+            sh.sky = conf.sky;
+            sh.red[0] = 0.0;
+        } else {
+            // prep_image, em.py:109-120
+            double desired_minval = 0.001 * (b - a);
+            sh.sky = desired_minval - a;
+            sh.red[0] = sh.sky;
+        }
+        // psf.set_flux(1.0) (gmix.py:299-311) when a psf was given
+        double psum0 = 0.0;
+        for (int k = 0; k < npsf; k++) psum0 += sh.psf[k].p;
+        if (npsf_in > 0) {
+            double rat = 1.0 / psum0;
+            for (int k = 0; k < npsf; k++) sh.psf[k].p *= rat;
+        }
+        // gmix_get_cen / gmix_get_moms of the psf, em_nb.py:1260-1294
+        double row = 0.0, col = 0.0, psum = 0.0;
+        for (int k = 0; k < npsf; k++) {
+            double p = sh.psf[k].p;
+            row += p * sh.psf[k].row;
+            col += p * sh.psf[k].col;
+            psum += p;
+        }
+        row /= psum;
+        col /= psum;
+        double irr = 0.0, irc = 0.0, icc = 0.0;
+        for (int k = 0; k < npsf; k++) {
+            double rd = sh.psf[k].row - row, cd = sh.psf[k].col - col;
+            double p = sh.psf[k].p;
+            irr += p * (sh.psf[k].irr + rd * rd);
+            irc += p * (sh.psf[k].irc + rd * cd);
+            icc += p * (sh.psf[k].icc + cd * cd);
+        }
+        sh.psf_row = row; sh.psf_col = col; sh.psf_ipsum = 1.0 / psum;
+        sh.psf_irr = irr / psum; sh.psf_irc = irc / psum;
+        sh.psf_icc = icc / psum;
+        double pl = 0.0;
+        for (int k = 0; k < ngauss; k++) pl += sh.gm[k].p;
+        sh.p_last = pl;
+    }
+    __syncthreads();
+    if (!conf.have_sky) {
+        double s = sh.red[0];
+        for (int p = threadIdx.x; p < ntot; p += T) val[p] += s;
+    }
+    const double area = sh.jac.scale * sh.jac.scale;
+    const double dvdrow = sh.jac.dvdrow, dvdcol = sh.jac.dvdcol;
+    const double dudrow = sh.jac.dudrow, dudcol = sh.jac.dudcol;
+    em_build_conv(&sh, ngauss, npsf, area);
+    __syncthreads();
+
+    if (sh.npix == 0 && threadIdx.x == 0) sh.status = NGX_ST_FATAL;
+    __syncthreads();
+
+    // ---- iterations
+    for (int it = 0; it < conf.maxiter && !sh.status && !sh.done; it++) {
+        const double sky = sh.sky;
+        if (sh.fill_zero) {
+            // fill_zero_weight_pixels, em_nb.py:1297-1315 (apodized eval)
+            for (int p = threadIdx.x; p < ntot; p += T) {
+                if (code[p] == 0.0) {
+                    int row = p / ncol, col = p - row * ncol;
+                    double v = dvdrow * rowd[row] + dvdcol * cold[col];
+                    double u = dudrow * rowd[row] + dudcol * cold[col];
+                    double s = 0.0;
+                    for (int k = 0; k < ngauss * npsf; k++)
+                        s += eval_fast(sh.conv[k], v, u, sh.tab);
+                    val[p] = sky + s;
+                }
+            }
+            __syncthreads();
+        }
+        double sums[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) sums[i] = 0.0;
+        int bad = 0;
+        for (int p = threadIdx.x; p < ntot; p += T) {
+            if (code[p] < 0.0) continue;
+            int row = p / ncol, col = p - row * ncol;
+            double v = dvdrow * rowd[row] + dvdcol * cold[col];
+            double u = dudrow * rowd[row] + dudcol * cold[col];
+            double gi[NG], tv[NG], tu[NG], tv2[NG], tuv[NG], tu2[NG];
+            double gsum = 0.0, logL = 0.0;
+#pragma unroll
+            for (int ii = 0; ii < NG; ii++) {
+                gi[ii] = tv[ii] = tu[ii] = tv2[ii] = tuv[ii] = tu2[ii] = 0.0;
+                if (ii < ngauss) {
+                    for (int k = ii * npsf; k < (ii + 1) * npsf; k++) {
+                        GaussV g = sh.conv[k];
+                        double vdiff = v - g.row;
+                        double udiff = u - g.col;
+                        double u2 = udiff * udiff;
+                        double v2 = vdiff * vdiff;
+                        double uv = udiff * vdiff;
+                        // -chi2/2 with the hard chi2 < 25 cut and NO
+                        // apodization, em_nb.py:222-227
+                        double x = fma(g.c, uv, fma(g.b, u2, g.a * v2));
+                        double vl = 0.0;
+                        if (x_in_range(x)) {
+                            int idx;
+                            double f = fexp_reduce(x, &idx);
+                            vl = (sh.tab[idx] * g.pn) * fexp_poly(f);
+                        }
+                        gi[ii] += vl;
+                        gsum += vl;
+                        if (DO_CEN) {
+                            tv[ii] = fma(v, vl, tv[ii]);
+                            tu[ii] = fma(u, vl, tu[ii]);
+                        }
+                        if (DO_COV) {
+                            tv2[ii] = fma(v2, vl, tv2[ii]);
+                            tuv[ii] = fma(uv, vl, tuv[ii]);
+                            tu2[ii] = fma(u2, vl, tu2[ii]);
+                        }
+                        if (DO_LOGL) logL = fma(vl, sh.logtd[k] + x, logL);
+                    }
+                }
+            }
+            if (DO_LOGL) {
+                if (gsum == 0.0) logL = 0.0;
+                else logL *= 1.0 / gsum;
+            }
+            double gtot = gsum + sky;
+            if (gtot == 0.0) { bad = 1; continue; }
+            double pv = val[p];
+            double factor = pv / gtot;
+            sums[6 * NG] += logL;
+            sums[6 * NG + 1] += sky * pv / gtot;
+#pragma unroll
+            for (int ii = 0; ii < NG; ii++) {
+                sums[6 * ii] = fma(gi[ii], factor, sums[6 * ii]);
+                if (DO_CEN) {
+                    sums[6 * ii + 1] = fma(tv[ii], factor, sums[6 * ii + 1]);
+                    sums[6 * ii + 2] = fma(tu[ii], factor, sums[6 * ii + 2]);
+                }
+                if (DO_COV) {
+                    sums[6 * ii + 3] = fma(tv2[ii], factor, sums[6 * ii + 3]);
+                    sums[6 * ii + 4] = fma(tuv[ii], factor, sums[6 * ii + 4]);
+                    sums[6 * ii + 5] = fma(tu2[ii], factor, sums[6 * ii + 5]);
+                }
+            }
+        }
+        if (bad) atomicOr(&sh.status, NGX_ST_RANGE_ERROR);   // gtot == 0
+        block_sum<NS>(sums, scratch);
+        if (sh.status) break;       // uniform: status written before the sync
+
+        // ---- M step: gmix_set_from_sums*, thread i < ngauss
+        if (threadIdx.x < ngauss) {
+            int i = threadIdx.x;
+            EMGauss g = sh.gm[i];
+            double p = 0.0, vs = 0.0, us = 0.0, v2s = 0.0, uvs = 0.0,
+                   u2s = 0.0;
+#pragma unroll
+            for (int ii = 0; ii < NG; ii++)
+                if (ii == i) {
+                    p = sums[6 * ii]; vs = sums[6 * ii + 1];
+                    us = sums[6 * ii + 2]; v2s = sums[6 * ii + 3];
+                    uvs = sums[6 * ii + 4]; u2s = sums[6 * ii + 5];
+                }
+            if (VARIANT != NGX_EM_FLUXONLY && p == 0.0) {
+                // numba raises ZeroDivisionError on pinv = 1.0/p
+                atomicOr(&sh.status, NGX_ST_ZERO_DIV);
+            } else {
+                double pinv = (VARIANT != NGX_EM_FLUXONLY) ? 1.0 / p : 0.0;
+                if (DO_CEN) {
+                    g.row = vs * pinv;
+                    g.col = us * pinv;
+                }
+                if (DO_COV) {
+                    double irr = v2s * pinv, irc = uvs * pinv,
+                           icc = u2s * pinv;
+                    irr = irr - sh.psf_irr;
+                    irc = irc - sh.psf_irc;
+                    icc = icc - sh.psf_icc;
+                    if (irr < 0.0 || icc < 0.0) {
+                        irr = 1.0e-4; irc = 0.0; icc = 1.0e-4;
+                    }
+                    double det = irr * icc - irc * irc;
+                    if (det < NGX_LOW_DETVAL) {
+                        double Tt = irr + icc;
+                        irr = icc = Tt / 2;
+                        irc = 0.0;
+                    }
+                    g.irr = irr; g.irc = irc; g.icc = icc;
+                }
+                g.p = p;
+                sh.gm[i] = g;
+            }
+        }
+        __syncthreads();
+        if (!sh.status) em_build_conv(&sh, ngauss, npsf, area);
+        if (threadIdx.x == 0 && !sh.status) {
+            if (conf.vary_sky) sh.sky = sums[6 * NG + 1] / sh.npix;
+            int numiter = it + 1;
+            sh.numiter = numiter;
+            if (VARIANT == NGX_EM_FLUXONLY) {
+                double psum = 0.0;
+                for (int k = 0; k < ngauss; k++) psum += sh.gm[k].p;
+                if (numiter >= conf.miniter) {
+                    sh.frac_diff = fabs(psum / sh.p_last - 1);
+                    if (sh.frac_diff < conf.tol) sh.done = 1;
+                }
+                sh.p_last = psum;
+            } else {
+                double elogL = sums[6 * NG];
+                if (numiter >= conf.miniter) {
+                    if (elogL == 0.0) {
+                        atomicOr(&sh.status, NGX_ST_RANGE_ERROR);
+                    } else {
+                        sh.frac_diff = fabs((elogL - sh.elogL_last) / elogL);
+                        if (sh.frac_diff < conf.tol) sh.done = 1;
+                    }
+                }
+                sh.elogL_last = elogL;
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ngx_em_result r;
+        r.flags = 0;
+        r.numiter = sh.numiter;
+        r.fdiff = sh.frac_diff;
+        r.sky = sh.sky;
+        if (sh.status) r.flags = NGX_EM_RANGE_ERROR;
+        else if (sh.numiter >= conf.maxiter) r.flags = NGX_EM_MAXITER;
+        res[stamp] = r;
+    }
+    if (threadIdx.x < ngauss) {
+        double *o = pars_out + ((size_t)stamp * ngauss + threadIdx.x) * 6;
+        EMGauss g = sh.gm[threadIdx.x];
+        o[0] = g.p; o[1] = g.row; o[2] = g.col;
+        o[3] = g.irr; o[4] = g.irc; o[5] = g.icc;
+    }
+}
+
+// =====================================================================
+// adaptive moments
+struct AMShared {
+    ngx_gauss wt;
+    GaussV wv;
+    double tab[16];
+    double red[40];
+    ngx_jacobian jac;
+    double roworig, colorig, e1old, e2old, Told;
+    int flags, done, numiter, npix_valid;
+};
+
+__global__ void __launch_bounds__(128)
+k_admom(int n, const double *__restrict__ images,
+        const double *__restrict__ weights,
+        const ngx_jacobian *__restrict__ jac, int nrow, int ncol,
+        const double *__restrict__ guess, ngx_admom_conf conf,
+        ngx_admom_result *__restrict__ res) {
+    extern __shared__ double smem_d[];
+    __shared__ AMShared sh;
+    __shared__ ngx_admom_result out;
+    const int T = blockDim.x;
+    const int ntot = nrow * ncol;
+    double *val = smem_d;            // ntot
+    double *var = val + ntot;        // ntot: 1/ierr^2, < 0 for dropped pixels
+    double *rowd = var + ntot;
+    double *cold = rowd + nrow;
+    double *scratch = cold + ncol;   // 37 * nwarps
+    const int stamp = blockIdx.x;
+    if (stamp >= n) return;
+    const double *im = images + (size_t)stamp * ntot;
+    const double *wt = weights + (size_t)stamp * ntot;
+    int cnt = 0;
+    for (int p = threadIdx.x; p < ntot; p += T) {
+        double w = wt[p];
+        val[p] = im[p];
+        if (w > 0.0) {
+            // var = 1/(ierr*ierr), ierr = sqrt(w): admom_nb.py:147
+            double ie = sqrt(w);
+            var[p] = 1.0 / (ie * ie);
+            cnt++;
+        } else {
+            var[p] = -1.0;           // dropped (Observation default)
+        }
+    }
+    (void)cnt;
+    load_exp_table(sh.tab);
+    if (threadIdx.x == 0) {
+        sh.jac = jac[stamp];
+        const double *g = guess + (size_t)stamp * 6;
+        gauss_set(sh.wt, g[0], g[1], g[2], g[3], g[4], g[5]);
+        sh.roworig = g[1];
+        sh.colorig = g[2];
+        sh.e1old = sh.e2old = sh.Told = nan("");
+        sh.flags = 0;
+        sh.done = 0;
+        sh.numiter = 0;
+        memset(&out, 0, sizeof(out));
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < nrow; p += T) rowd[p] = p - sh.jac.row0;
+    for (int p = threadIdx.x; p < ncol; p += T) cold[p] = p - sh.jac.col0;
+    const double area = sh.jac.scale * sh.jac.scale;
+    const double dvdrow = sh.jac.dvdrow, dvdcol = sh.jac.dvdcol;
+    const double dudrow = sh.jac.dudrow, dudcol = sh.jac.dudcol;
+    __syncthreads();
+
+    int i = 0;
+    for (i = 0; i < conf.maxiter; i++) {
+        if (threadIdx.x == 0) {
+            if (sh.wt.det < NGX_LOW_DETVAL) {
+                sh.flags = NGX_LOW_DET;
+                sh.done = 1;
+            } else {
+                gauss_set_norm(sh.wt);
+                sh.wv = make_gaussv(sh.wt, area);
+            }
+        }
+        __syncthreads();
+        if (sh.done) break;
+        // ---- admom_censums :111-128
+        double cs[4] = {0.0, 0.0, 0.0, 0.0};
+        {
+            GaussV g = sh.wv;
+            for (int p = threadIdx.x; p < ntot; p += T) {
+                if (var[p] < 0.0) continue;
+                int row = p / ncol, col = p - row * ncol;
+                double v = dvdrow * rowd[row] + dvdcol * cold[col];
+                double u = dudrow * rowd[row] + dudcol * cold[col];
+                double weight = eval_fast(g, v, u, sh.tab);
+                double wdata = weight * val[p];
+                cs[0] = fma(wdata, v, cs[0]);
+                cs[1] = fma(wdata, u, cs[1]);
+                cs[2] += wdata;
+                cs[3] += 1.0;
+            }
+        }
+        block_sum<4>(cs, scratch);
+        if (threadIdx.x == 0) {
+            // clear_result + censums bookkeeping
+            out.npix = (int)cs[3];
+            out.wsum = 0.0;
+            for (int k = 0; k < 7; k++) out.sums[k] = 0.0;
+            for (int k = 0; k < 49; k++) out.sums_cov[k] = 0.0;
+            for (int k = 0; k < 6; k++) out.pars[k] = nan("");
+            out.rho4 = nan("");
+            out.sums[0] = cs[0]; out.sums[1] = cs[1]; out.sums[5] = cs[2];
+            if (cs[2] <= 0.0) {
+                sh.flags = NGX_NONPOS_FLUX;
+                sh.done = 1;
+            } else {
+                sh.wt.row = cs[0] / cs[2];
+                sh.wt.col = cs[1] / cs[2];
+                if (fabs(sh.wt.row - sh.roworig) > conf.shiftmax
+                    || fabs(sh.wt.col - sh.colorig) > conf.shiftmax) {
+                    sh.flags = NGX_CEN_SHIFT;
+                    sh.done = 1;
+                } else {
+                    sh.wv.row = sh.wt.row;
+                    sh.wv.col = sh.wt.col;
+                }
+            }
+        }
+        __syncthreads();
+        if (sh.done) break;
+        // ---- admom_momsums :131-175: 7 sums, 28 unique cov sums, wsum, n
+        double ms[37];
+#pragma unroll
+        for (int k = 0; k < 37; k++) ms[k] = 0.0;
+        {
+            GaussV g = sh.wv;
+            double vcen = g.row, ucen = g.col;
+            double dcc = -2.0 * g.a, drr = -2.0 * g.b, drc = g.c;
+            for (int p = threadIdx.x; p < ntot; p += T) {
+                double vr = var[p];
+                if (vr < 0.0) continue;
+                int row = p / ncol, col = p - row * ncol;
+                double v = dvdrow * rowd[row] + dvdcol * cold[col];
+                double u = dudrow * rowd[row] + dudcol * cold[col];
+                double weight = eval_fast(g, v, u, sh.tab);
+                double vmod = v - vcen, umod = u - ucen;
+                double wdata = weight * val[p];
+                double w2 = weight * weight;
+                double chi2 = dcc * vmod * vmod + drr * umod * umod
+                    - 2.0 * drc * vmod * umod;
+                double F[7];
+                F[0] = v;
+                F[1] = u;
+                F[2] = umod * umod - vmod * vmod;
+                F[3] = 2 * vmod * umod;
+                F[4] = umod * umod + vmod * vmod;
+                F[5] = 1.0;
+                F[6] = chi2 * chi2;
+                double w2v = w2 * vr;
+                int q = 7;
+#pragma unroll
+                for (int a = 0; a < 7; a++) {
+                    ms[a] = fma(wdata, F[a], ms[a]);
+                    double t = w2v * F[a];
+#pragma unroll
+                    for (int b = 0; b <= a; b++) {
+                        ms[q] = fma(t, F[b], ms[q]);
+                        q++;
+                    }
+                }
+                ms[35] += weight;
+                ms[36] += 1.0;
+            }
+        }
+        block_sum<37>(ms, scratch);
+        if (threadIdx.x == 0) {
+            out.npix = (int)ms[36];
+            out.wsum = ms[35];
+            for (int k = 0; k < 7; k++) out.sums[k] = ms[k];
+            int q = 7;
+            for (int a = 0; a < 7; a++)
+                for (int b = 0; b <= a; b++) {
+                    out.sums_cov[a * 7 + b] = ms[q];
+                    out.sums_cov[b * 7 + a] = ms[q];
+                    q++;
+                }
+            for (int k = 0; k < 6; k++) out.pars[k] = nan("");
+            out.rho4 = nan("");
+            if (ms[5] <= 0.0) {
+                sh.flags = NGX_NONPOS_FLUX;
+                sh.done = 1;
+            } else {
+                double finv = 1.0 / ms[5];
+                double M1 = ms[2] * finv, M2 = ms[3] * finv;
+                double Tm = ms[4] * finv;
+                double Irr = 0.5 * (Tm - M1), Icc = 0.5 * (Tm + M1);
+                double Irc = 0.5 * M2;
+                if (Tm <= 0.0) {
+                    sh.flags = NGX_NONPOS_SIZE;
+                    sh.done = 1;
+                } else {
+                    double e1 = (Icc - Irr) / Tm, e2 = 2 * Irc / Tm;
+                    if (fabs(e1 - sh.e1old) < conf.etol
+                        && fabs(e2 - sh.e2old) < conf.etol
+                        && fabs(Tm / sh.Told - 1.) < conf.Ttol) {
+                        out.pars[0] = sh.wt.row;
+                        out.pars[1] = sh.wt.col;
+                        out.pars[2] = sh.wt.icc - sh.wt.irr;
+                        out.pars[3] = 2.0 * sh.wt.irc;
+                        out.pars[4] = sh.wt.icc + sh.wt.irr;
+                        out.pars[5] = 1.0;
+                        out.rho4 = ms[6] / ms[5];
+                        sh.done = 1;
+                    } else {
+                        if (!conf.cenonly) {
+                            // deweight_moments :178-226
+                            double detm = Irr * Icc - Irc * Irc;
+                            double Wrr = sh.wt.irr, Wrc = sh.wt.irc,
+                                   Wcc = sh.wt.icc;
+                            double detw = Wrr * Wcc - Wrc * Wrc;
+                            if (detm <= NGX_LOW_DETVAL
+                                || detw <= NGX_LOW_DETVAL) {
+                                sh.flags = NGX_LOW_DET;
+                                sh.done = 1;
+                            } else {
+                                double idetw = 1.0 / detw, idetm = 1.0 / detm;
+                                double Nrr = Icc * idetm - Wcc * idetw;
+                                double Ncc = Irr * idetm - Wrr * idetw;
+                                double Nrc = -Irc * idetm + Wrc * idetw;
+                                double detn = Nrr * Ncc - Nrc * Nrc;
+                                if (detn <= NGX_LOW_DETVAL) {
+                                    sh.flags = NGX_LOW_DET;
+                                    sh.done = 1;
+                                } else {
+                                    double idetn = 1. / detn;
+                                    sh.wt.irr = Ncc * idetn;
+                                    sh.wt.icc = Nrr * idetn;
+                                    sh.wt.irc = -Nrc * idetn;
+                                    sh.wt.det = sh.wt.irr * sh.wt.icc
+                                        - sh.wt.irc * sh.wt.irc;
+                                }
+                            }
+                        }
+                        sh.e1old = e1; sh.e2old = e2; sh.Told = Tm;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (sh.done) break;
+    }
+    if (threadIdx.x == 0) {
+        // python leaves i at maxiter-1 when the loop is exhausted
+        if (i == conf.maxiter) i = conf.maxiter - 1;
+        out.numiter = i + 1;
+        out.flags = sh.flags;
+        if (out.numiter == conf.maxiter) out.flags = NGX_MAXITER;
+        out.wt_norm = sh.wt.norm;
+        res[stamp] = out;
+    }
+}
+
+static int pick_threads(int ntot) {
+    if (ntot <= 400) return 32;
+    if (ntot <= 1600) return 64;
+    return 128;
+}
+
+template <int VARIANT>
+static int launch_em(int n, const double *images, const double *weights,
+                     const ngx_jacobian *jac, int nrow, int ncol,
+                     const double *guess, int ngauss, const double *psf_pars,
+                     int npsf, const ngx_em_conf &conf, int ignore_zero_weight,
+                     double *pars_out, ngx_em_result *res,
+                     cudaStream_t stream) {
+    int ntot = nrow * ncol;
+    int threads = pick_threads(ntot);
+    int nconv = ngauss * (npsf > 0 ? npsf : 1);
+    while (threads < nconv) threads *= 2;
+    if (threads > 128)
+        return fail(NGX_ERR_ARG, "ngx_em: too many convolved gaussians%s%s");
+    int nwarps = threads / 32;
+#define NGX_EM_CASE(NGV)                                                     \
+    {                                                                        \
+        size_t smem = sizeof(double)                                         \
+            * (2 * (size_t)ntot + nrow + ncol                                \
+               + (size_t)(6 * NGV + 2) * nwarps);                            \
+        if (smem > (size_t)smem_optin_bytes())                               \
+            return fail(NGX_ERR_ARG, "ngx_em: stamp too large%s%s");         \
+        NGX_CUDA(cudaFuncSetAttribute(                                       \
+            k_em<VARIANT, NGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            (int)smem));                                                     \
+        k_em<VARIANT, NGV><<<n, threads, smem, stream>>>(                    \
+            n, images, weights, jac, nrow, ncol, guess, ngauss, psf_pars,    \
+            npsf, conf, ignore_zero_weight, pars_out, res);                  \
+    }
+    if (ngauss == 1) NGX_EM_CASE(1)
+    else if (ngauss == 2) NGX_EM_CASE(2)
+    else if (ngauss == 3) NGX_EM_CASE(3)
+    else if (ngauss == 4) NGX_EM_CASE(4)
+    else if (ngauss == 5) NGX_EM_CASE(5)
+    else if (ngauss <= 8) NGX_EM_CASE(8)
+    else NGX_EM_CASE(10)
+#undef NGX_EM_CASE
+    NGX_LAUNCH_CHECK();
+    return NGX_OK;
+}
+
+}  // namespace ngx
+
+using namespace ngx;
+
+extern "C" {
+
+int ngx_em(int n, int variant, const double *images, const double *weights,
+           const ngx_jacobian *jac, int nrow, int ncol, const double *guess,
+           int ngauss, const double *psf_pars, int npsf,
+           const ngx_em_conf *conf, int ignore_zero_weight, double *pars_out,
+           ngx_em_result *res, void *stream) {
+    NGX_REQUIRE(n >= 0 && images && weights && jac && guess && conf);
+    NGX_REQUIRE(pars_out && res && nrow >= 1 && ncol >= 1);
+    NGX_REQUIRE(ngauss >= 1 && ngauss <= 10 && npsf >= 0 && npsf <= 16);
+    NGX_REQUIRE(npsf == 0 || psf_pars);
+    NGX_REQUIRE(ngauss * (npsf > 0 ? npsf : 1) <= NGX_EM_MAX_CONV);
+    if (n == 0) return NGX_OK;
+    cudaStream_t s = as_stream(stream);
+    switch (variant) {
+    case NGX_EM_FULL:
+        return launch_em<NGX_EM_FULL>(n, images, weights, jac, nrow, ncol,
+                                      guess, ngauss, psf_pars, npsf, *conf,
+                                      ignore_zero_weight, pars_out, res, s);
+    case NGX_EM_FIXCEN:
+        return launch_em<NGX_EM_FIXCEN>(n, images, weights, jac, nrow, ncol,
+                                        guess, ngauss, psf_pars, npsf, *conf,
+                                        ignore_zero_weight, pars_out, res, s);
+    case NGX_EM_FIXCOV:
+        return launch_em<NGX_EM_FIXCOV>(n, images, weights, jac, nrow, ncol,
+                                        guess, ngauss, psf_pars, npsf, *conf,
+                                        ignore_zero_weight, pars_out, res, s);
+    case NGX_EM_FLUXONLY:
+        return launch_em<NGX_EM_FLUXONLY>(n, images, weights, jac, nrow, ncol,
+                                          guess, ngauss, psf_pars, npsf,
+                                          *conf, ignore_zero_weight, pars_out,
+                                          res, s);
+    default:
+        return fail(NGX_ERR_ARG, "ngx_em: unknown variant%s%s");
+    }
+}
+
+int ngx_admom(int n, const double *images, const double *weights,
+              const ngx_jacobian *jac, int nrow, int ncol, const double *guess,
+              const ngx_admom_conf *conf, ngx_admom_result *res,
+              void *stream) {
+    NGX_REQUIRE(n >= 0 && images && weights && jac && guess && conf && res);
+    NGX_REQUIRE(nrow >= 1 && ncol >= 1 && conf->maxiter >= 1);
+    if (n == 0) return NGX_OK;
+    int ntot = nrow * ncol;
+    int threads = pick_threads(ntot);
+    int nwarps = threads / 32;
+    size_t smem = sizeof(double)
+        * (2 * (size_t)ntot + nrow + ncol + 37 * (size_t)nwarps);
+    if (smem > (size_t)smem_optin_bytes())
+        return fail(NGX_ERR_ARG, "ngx_admom: stamp too large%s%s");
+    NGX_CUDA(cudaFuncSetAttribute(
+        k_admom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_admom<<<n, threads, smem, as_stream(stream)>>>(
+        n, images, weights, jac, nrow, ncol, guess, *conf, res);
+    NGX_LAUNCH_CHECK();
+    return NGX_OK;
+}
+
+int ngx_em_host(int n, int variant, const double *images,
+                const double *weights, const ngx_jacobian *jac, int nrow,
+                int ncol, const double *guess, int ngauss,
+                const double *psf_pars, int npsf, const ngx_em_conf *conf,
+                int ignore_zero_weight, double *pars_out,
+                ngx_em_result *res) {
+    NGX_REQUIRE(n >= 0 && images && weights && jac && guess && conf);
+    size_t ntot = (size_t)n * nrow * ncol;
+    DevBuf<double> di(ntot, images), dw(ntot, weights);
+    DevBuf<ngx_jacobian> dj(n, jac);
+    DevBuf<double> dg((size_t)n * ngauss * 6, guess);
+    DevBuf<double> dp(npsf > 0 ? (size_t)n * npsf * 6 : 0, psf_pars);
+    DevBuf<double> dout((size_t)n * ngauss * 6);
+    DevBuf<ngx_em_result> dr(n);
+    NGX_CUDA(di.err); NGX_CUDA(dw.err); NGX_CUDA(dj.err); NGX_CUDA(dg.err);
+    NGX_CUDA(dp.err); NGX_CUDA(dout.err); NGX_CUDA(dr.err);
+    NGX_CUDA(dout.zero());
+    int rc = ngx_em(n, variant, di.d, dw.d, dj.d, nrow, ncol, dg.d, ngauss,
+                    npsf > 0 ? dp.d : nullptr, npsf, conf, ignore_zero_weight,
+                    dout.d, dr.d, 0);
+    if (rc) return rc;
+    NGX_CUDA(cudaDeviceSynchronize());
+    NGX_CUDA(dout.to_host(pars_out));
+    NGX_CUDA(dr.to_host(res));
+    return NGX_OK;
+}
+
+int ngx_admom_host(int n, const double *images, const double *weights,
+                   const ngx_jacobian *jac, int nrow, int ncol,
+                   const double *guess, const ngx_admom_conf *conf,
+                   ngx_admom_result *res) {
+    NGX_REQUIRE(n >= 0 && images && weights && jac && guess && conf && res);
+    size_t ntot = (size_t)n * nrow * ncol;
+    DevBuf<double> di(ntot, images), dw(ntot, weights);
+    DevBuf<ngx_jacobian> dj(n, jac);
+    DevBuf<double> dg((size_t)n * 6, guess);
+    DevBuf<ngx_admom_result> dr(n);
+    NGX_CUDA(di.err); NGX_CUDA(dw.err); NGX_CUDA(dj.err); NGX_CUDA(dg.err);
+    NGX_CUDA(dr.err);
+    int rc = ngx_admom(n, di.d, dw.d, dj.d, nrow, ncol, dg.d, conf, dr.d, 0);
+    if (rc) return rc;
+    NGX_CUDA(cudaDeviceSynchronize());
+    NGX_CUDA(dr.to_host(res));
+    return NGX_OK;
+}
+
+}  // extern "C"

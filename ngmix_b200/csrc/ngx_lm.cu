@@ -1,0 +1,976 @@
+// ngx_lm_fit: the batched Levenberg-Marquardt fit, one CTA per stamp.
+//
+// Replaces Fitter.go (ngmix/fitting/fitters.py:64-112) = FitModel.calc_fdiff
+// / calc_jacobian (fitting/results.py:439-625) + deriv_images
+// (fitting/derivs_nb.py:40-127) + scipy's MINPACK lmder/lmdif
+// (fitting/leastsqbound.py:445-447) + run_leastsq's epilogue (:70-126) +
+// FitModel.set_fit_result (results.py:45-72).
+//
+// Data movement: the stamp (val, ierr = sqrt(weight); 16 B/pixel) is read
+// from HBM once, lives in shared memory for the whole fit and is never
+// written back; per fit only the ~1.2 KB result record goes out.  The
+// reference's 48 B/pixel AoS and the m x n Jacobian never exist.
+//
+// Work per fit: nfev value passes (16 fp64 instr per gaussian-pixel) and
+// njev derivative passes (30 per gaussian-pixel) over pixels kept in
+// registers C at a time with the gaussians in the outer loop; every
+// derivative pass also accumulates J^T J (21) and J^T f (6) per thread and
+// block-reduces them with warp shuffles.  One thread then advances the
+// MINPACK state machine (ngx_lm_solve.cuh) while the other CTAs resident on
+// the SM keep the fp64 pipe busy.
+#include "ngx_core.cuh"
+#include "ngx_host.cuh"
+#include "ngx_lm_solve.cuh"
+#include "ngx_prior.cuh"
+
+namespace ngx {
+
+#define NGX_PDEF (-9.999e9)
+#define NGX_CDEF (9.999e9)
+#define NGX_BIGVAL (9999.0e47)
+
+// per-gaussian constants in shared memory (8 doubles) + 16-entry table
+//   0 row, 1 col, 2 a=-dcc/2, 3 b=-drr/2, 4 c2=drc/2, 5 h=Tk/2
+#define GC_STRIDE 8
+
+struct LMArgs {
+    int n, model, np, ngauss0, npsf, ngauss, nrow, ncol, ntot;
+    int ignore_zero_weight, analytic, padded;
+    ngx_prior prior;
+    ngx_lm_pars lm;
+    const double *images, *weights;
+    const ngx_jacobian *jac;
+    const double *psf, *guess;
+    ngx_lm_result *res;
+    int *counter;
+};
+
+struct LMShared {
+    LMState st;
+    double xeval[LM_MAXP];
+    double psf[16 * 6];
+    double psf_row, psf_col, psf_ipsum;
+    double cur_ssq, cur_rfirst2, cur_num, cur_den;   // at the accepted x
+    ngx_jacobian jac;
+    int stamp, npix, first_idx, status, action;
+    int warp_i[32], warp_j[32];
+};
+
+// ---------------------------------------------------------------------
+// build the convolved mixture for parameters x: thread k < ngauss owns
+// composed gaussian k = iobj*npsf + ipsf (gmix_convolve_fill's order).
+// Returns nothing; sh->status is OR-ed with range errors.
+__device__ __forceinline__ void build_mixture(const LMArgs &a, LMShared *sh,
+                                              const double *x, double *gc,
+                                              double *ptab, double area,
+                                              int with_table) {
+    int k = threadIdx.x;
+    if (k >= a.ngauss) return;
+    ModelHead h = model_head(a.model, x);
+    if (h.status != NGX_ST_OK) {
+        atomicOr(&sh->status, 1);
+        return;
+    }
+    int npsf = a.npsf > 0 ? a.npsf : 1;
+    int iobj = k / npsf, ipsf = k - iobj * npsf;
+    double p, irr0, irc0, icc0;
+    model_component(a.model, h, iobj, &p, &irr0, &irc0, &icc0);
+    double row = h.row, col = h.col, irr = irr0, irc = irc0, icc = icc0;
+    if (a.npsf > 0) {
+        const double *q = sh->psf + 6 * ipsf;
+        p = p * q[0] * sh->psf_ipsum;
+        row = h.row + (q[1] - sh->psf_row);
+        col = h.col + (q[2] - sh->psf_col);
+        irr = irr0 + q[3];
+        irc = irc0 + q[4];
+        icc = icc0 + q[5];
+    }
+    double det = irr * icc - irc * irc;
+    // gauss2d_set_norm :203-208
+    if (det < NGX_LOW_DETVAL || (irr + icc) <= NGX_LOW_DETVAL
+        || !(det == det)) {
+        atomicOr(&sh->status, 1);
+        return;
+    }
+    double idet = 1.0 / det;
+    double drr = irr * idet, drc = irc * idet, dcc = icc * idet;
+    double norm = 1.0 / (2 * 3.141592653589793 * sqrt(det));
+    double pn = (p * norm) * area;
+    double *g = gc + GC_STRIDE * k;
+    g[0] = row; g[1] = col;
+    g[2] = -0.5 * dcc; g[3] = -0.5 * drr; g[4] = 0.5 * drc;
+    g[5] = 0.5 * (irr0 + icc0);
+    if (with_table) {
+#pragma unroll
+        for (int t = 0; t < 16; t++) ptab[16 * k + t] = c_exp_lookup[t] * pn;
+    }
+}
+
+// pixel coordinates of pixel p from the row/col offset tables
+__device__ __forceinline__ void coords_of(const LMArgs &a, const LMShared *sh,
+                                          const double *rowd,
+                                          const double *cold, int p,
+                                          double *v, double *u) {
+    if (p < a.ntot) {
+        int row = p / a.ncol, col = p - row * a.ncol;
+        double rd = rowd[row], cd = cold[col];
+        *v = sh->jac.dvdrow * rd + sh->jac.dvdcol * cd;
+        *u = sh->jac.dudrow * rd + sh->jac.dudcol * cd;
+    } else {
+        *v = 1.0e300; *u = 1.0e300;
+    }
+}
+
+// ---------------------------------------------------------------------
+// value pass: sums = {sum r^2, s2n_numer, s2n_denom, r_first^2}
+template <int CV>
+__device__ __forceinline__ void value_pass(const LMArgs &a,
+                                           const LMShared *sh,
+                                           const double *gc,
+                                           const double *ptab,
+                                           const double *val,
+                                           const double *ierr,
+                                           const double *rowd,
+                                           const double *cold,
+                                           double (&sums)[4]) {
+    const int T = blockDim.x;
+    sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+    for (int base = 0; base < a.ntot; base += T * CV) {
+        double v[CV], u[CV], acc[CV];
+#pragma unroll
+        for (int c = 0; c < CV; c++) {
+            coords_of(a, sh, rowd, cold, base + c * T + threadIdx.x, &v[c],
+                      &u[c]);
+            acc[c] = 0.0;
+        }
+        for (int k = 0; k < a.ngauss; k++) {
+            const double *g = gc + GC_STRIDE * k;
+            const double *tab = ptab + 16 * k;
+            double row = g[0], col = g[1], ga = g[2], gb = g[3];
+            double gcx = 2.0 * g[4];
+#pragma unroll
+            for (int c = 0; c < CV; c++) {
+                double dv = v[c] - row;
+                double du = u[c] - col;
+                double t = fma(gcx, du, ga * dv);
+                double x = fma(gb * du, du, dv * t);
+                if (x_in_range(x)) {
+                    int idx;
+                    double f = fexp_reduce(x, &idx);
+                    double pv = fexp_poly(f);
+                    if (x_in_apod(x)) pv *= apod_window_x(x);
+                    acc[c] = fma(tab[idx], pv, acc[c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CV; c++) {
+            int p = base + c * T + threadIdx.x;
+            if (p < a.ntot) {
+                double ie = ierr[p], d = val[p];
+                double ivar = ie * ie;
+                double diff = acc[c] - d;
+                double r = diff * ie;
+                sums[0] = fma(r, r, sums[0]);
+                sums[1] = fma(d * acc[c], ivar, sums[1]);
+                sums[2] = fma(acc[c] * acc[c], ivar, sums[2]);
+                if (p == sh->first_idx) sums[3] = r * r;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------
+// derivative pass for the simple models (gauss/exp/dev): per pixel the six
+// images of deriv_images, restructured so that the three covariance
+// derivatives share the moment sums MA, MB, MS.  sums =
+// {A (21, packed lower triangle row by row), b (6), sum r^2}
+template <int CD>
+__device__ __forceinline__ void deriv_pass(const LMArgs &a,
+                                           const LMShared *sh,
+                                           const double *x, const double *gc,
+                                           const double *ptab,
+                                           const double *val,
+                                           const double *ierr,
+                                           const double *rowd,
+                                           const double *cold,
+                                           double (&sums)[28]) {
+    const int T = blockDim.x;
+#pragma unroll
+    for (int i = 0; i < 28; i++) sums[i] = 0.0;
+    // d(e1,e2)/d(g1,g2), results.py:988-995
+    double g1 = x[2], g2 = x[3], Tpar = x[4], flux = x[5];
+    double gsq = g1 * g1 + g2 * g2;
+    double ff = 2.0 / (1.0 + gsq);
+    double dfac = -ff / (1.0 + gsq);
+    double de1dg1 = ff + 2.0 * g1 * g1 * dfac;
+    double de1dg2 = 2.0 * g1 * g2 * dfac;
+    double de2dg1 = de1dg2;
+    double de2dg2 = ff + 2.0 * g2 * g2 * dfac;
+    double e1, e2;
+    g1g2_to_e1e2(g1, g2, &e1, &e2);
+    double iT = 1.0 / Tpar, iflux = 1.0 / flux;
+
+    for (int base = 0; base < a.ntot; base += T * CD) {
+        double v[CD], u[CD];
+        double S0[CD], S1[CD], S2[CD], MA[CD], MB[CD], MS[CD];
+#pragma unroll
+        for (int c = 0; c < CD; c++) {
+            coords_of(a, sh, rowd, cold, base + c * T + threadIdx.x, &v[c],
+                      &u[c]);
+            S0[c] = S1[c] = S2[c] = MA[c] = MB[c] = MS[c] = 0.0;
+        }
+        for (int k = 0; k < a.ngauss; k++) {
+            const double *g = gc + GC_STRIDE * k;
+            const double *tab = ptab + 16 * k;
+            double row = g[0], col = g[1], ga = g[2], gb = g[3], c2 = g[4];
+            double h = g[5];
+            double ha = 0.5 * ga, hb = 0.5 * gb, qc = 0.5 * c2;
+#pragma unroll
+            for (int c = 0; c < CD; c++) {
+                double dv = v[c] - row;
+                double du = u[c] - col;
+                double hqv = fma(c2, du, ga * dv);     // -qv/2
+                double hqu = fma(gb, du, c2 * dv);     // -qu/2
+                double xx = fma(du, hqu, dv * hqv);    // -chi2/2
+                if (x_in_range(xx)) {
+                    int idx;
+                    double f = fexp_reduce(xx, &idx);
+                    double vl = tab[idx] * fexp_poly(f);
+                    if (!x_in_apod(xx)) {
+                        S0[c] += vl;
+                        S1[c] = fma(vl, hqv, S1[c]);
+                        S2[c] = fma(vl, hqu, S2[c]);
+                        double cv = vl * h;
+                        double ea = fma(hqu, hqu, hb);
+                        double eb = fma(hqv, hqv, ha);
+                        MA[c] = fma(cv, ea - eb, MA[c]);
+                        MS[c] = fma(cv, ea + eb, MS[c]);
+                        MB[c] = fma(cv, fma(hqv, hqu, qc), MB[c]);
+                    } else {
+                        // apodization band: the window slope enters the
+                        // terms that flow through chi^2, derivs_nb.py:104-114
+                        double w = apod_window_x(xx);
+                        double vc = vl * (w - 2.0 * apod_window_deriv_x(xx));
+                        double vw = vl * w;
+                        S0[c] += vw;
+                        S1[c] = fma(vc, hqv, S1[c]);
+                        S2[c] = fma(vc, hqu, S2[c]);
+                        double cv = vc * h, cw = vw * h;
+                        double qu2 = hqu * hqu, qv2 = hqv * hqv;
+                        MA[c] += cv * (qu2 - qv2) + cw * (hb - ha);
+                        MS[c] += cv * (qu2 + qv2) + cw * (hb + ha);
+                        MB[c] += cv * (hqv * hqu) + cw * qc;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CD; c++) {
+            int p = base + c * T + threadIdx.x;
+            if (p < a.ntot) {
+                double ie = ierr[p];
+                // undo the factors folded into the accumulators:
+                // qv = -2 hqv; (q q^T - W) terms carry 4, the cross term 8
+                double ma = 4.0 * MA[c], ms = 4.0 * MS[c], mb = 8.0 * MB[c];
+                double j[6];
+                j[0] = (-2.0 * S1[c]) * ie;
+                j[1] = (-2.0 * S2[c]) * ie;
+                j[2] = (0.5 * (de1dg1 * ma + de2dg1 * mb)) * ie;
+                j[3] = (0.5 * (de1dg2 * ma + de2dg2 * mb)) * ie;
+                j[4] = (0.5 * iT * (ms + e1 * ma + e2 * mb)) * ie;
+                j[5] = S0[c] * (ie * iflux);
+                double r = (S0[c] - val[p]) * ie;
+                int q = 0;
+#pragma unroll
+                for (int aa = 0; aa < 6; aa++)
+#pragma unroll
+                    for (int bb = 0; bb <= aa; bb++) {
+                        sums[q] = fma(j[aa], j[bb], sums[q]);
+                        q++;
+                    }
+#pragma unroll
+                for (int aa = 0; aa < 6; aa++)
+                    sums[21 + aa] = fma(j[aa], r, sums[21 + aa]);
+                sums[27] = fma(r, r, sums[27]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------
+// forward-difference Jacobian (MINPACK fdjac2) for the models without
+// analytic derivatives (bdf, bd) or analytic_jacobian = 0: evaluates the
+// base mixture and the np perturbed mixtures per pixel.  The mixtures are
+// built by build_mixture into gcs[(np+1)][ngauss][GC_STRIDE] with their own
+// tables.  sums = {A packed (np(np+1)/2), b (np), sum r^2}
+template <int NPMAX>
+__device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
+                                        const double *hs, const double *gcs,
+                                        const double *ptabs,
+                                        const double *val, const double *ierr,
+                                        const double *rowd,
+                                        const double *cold, double *sums,
+                                        int nsums) {
+    const int T = blockDim.x;
+    const int np = a.np;
+    for (int i = 0; i < nsums; i++) sums[i] = 0.0;
+    for (int base = 0; base < a.ntot; base += T) {
+        int p = base + threadIdx.x;
+        double v, u;
+        coords_of(a, sh, rowd, cold, p, &v, &u);
+        double m[NPMAX + 1];
+        for (int s = 0; s <= np; s++) {
+            const double *gc = gcs + (size_t)s * a.ngauss * GC_STRIDE;
+            const double *ptab = ptabs + (size_t)s * a.ngauss * 16;
+            double acc = 0.0;
+            for (int k = 0; k < a.ngauss; k++) {
+                const double *g = gc + GC_STRIDE * k;
+                double dv = v - g[0];
+                double du = u - g[1];
+                double t = fma(2.0 * g[4], du, g[2] * dv);
+                double x = fma(g[3] * du, du, dv * t);
+                if (x_in_range(x)) {
+                    int idx;
+                    double f = fexp_reduce(x, &idx);
+                    double pv = fexp_poly(f);
+                    if (x_in_apod(x)) pv *= apod_window_x(x);
+                    acc = fma(ptab[16 * k + idx], pv, acc);
+                }
+            }
+            m[s] = acc;
+        }
+        if (p < a.ntot) {
+            double ie = ierr[p];
+            double r = (m[0] - val[p]) * ie;
+            double j[NPMAX];
+            for (int s = 0; s < np; s++) {
+                double rs = (m[s + 1] - val[p]) * ie;
+                j[s] = (rs - r) / hs[s];
+            }
+            int q = 0;
+            for (int aa = 0; aa < np; aa++)
+                for (int bb = 0; bb <= aa; bb++) {
+                    sums[q] = fma(j[aa], j[bb], sums[q]);
+                    q++;
+                }
+            for (int aa = 0; aa < np; aa++)
+                sums[q + aa] = fma(j[aa], r, sums[q + aa]);
+            sums[q + np] = fma(r, r, sums[q + np]);
+        }
+    }
+}
+
+// generic block reduction of nsums values held in a local array
+__device__ __forceinline__ void block_sum_n(double *v, int nv,
+                                            double *scratch) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int nwarps = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nv; i++) {
+        double s = warp_sum(v[i]);
+        if (lane == 0) scratch[i * nwarps + warp] = s;
+    }
+    __syncthreads();
+    for (int i = 0; i < nv; i++) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; w++) s += scratch[i * nwarps + w];
+        v[i] = s;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------
+// prior contributions, thread 0
+__device__ inline double prior_fnorm2(const LMArgs &a, const double *x,
+                                      int *status, int *ninf) {
+    *ninf = 0;
+    if (!a.prior.present) return 0.0;
+    double f[NGX_MAX_PRIOR_ROWS];
+    if (prior_fill_fdiff(a.model, a.prior, x, f)) {
+        *status = 1;
+        return 0.0;
+    }
+    int nr = prior_nrows(a.model, a.prior);
+    double s = 0.0;
+    for (int r = 0; r < nr; r++) {
+        if (isinf(f[r])) *ninf += 1;
+        else s += f[r] * f[r];
+    }
+    return s;
+}
+
+// the epilogue: run_leastsq (leastsqbound.py:70-126) + set_fit_result
+__device__ inline void lm_finish(const LMArgs &a, LMShared *sh,
+                                 ngx_lm_result *out) {
+    LMState *s = &sh->st;
+    int np = a.np;
+    ngx_lm_result r;
+    r.nfev = s->nfev;
+    r.njev = s->njev;
+    r.ier = s->info;
+    r.npix = 0;
+    r.dof = 0;
+    double qnan = nan("");
+    r.lnprob = r.s2n_numer = r.s2n_denom = r.chi2per = r.s2n = qnan;
+    r.T = r.T_err = r.flux = r.flux_err = qnan;
+    for (int i = 0; i < 8; i++) { r.pars[i] = 0.0; r.pars_err[i] = 0.0; }
+    for (int i = 0; i < 64; i++) { r.pars_cov0[i] = 0.0; r.pars_cov[i] = 0.0; }
+    for (int i = 0; i < np; i++) r.pars[i] = s->x[i];
+    for (int i = 0; i < np * np; i++) r.pars_cov0[i] = qnan;
+    int flags = 0;
+    if (s->info > 4) {
+        flags |= 1 << (s->info - 5);
+        for (int i = 0; i < np; i++) {
+            r.pars[i] = NGX_PDEF;
+            r.pars_err[i] = NGX_CDEF;
+        }
+        for (int i = 0; i < np * np; i++) r.pars_cov[i] = NGX_CDEF;
+    } else {
+        double cov0[LM_MAXP * LM_MAXP];
+        int have = lm_cov0(s, cov0);
+        if (!have) {
+            flags |= NGX_LM_SINGULAR_MATRIX;
+            for (int i = 0; i < np; i++) r.pars_err[i] = NGX_CDEF;
+            for (int i = 0; i < np * np; i++) r.pars_cov[i] = NGX_CDEF;
+        } else {
+            for (int i = 0; i < np * np; i++) r.pars_cov0[i] = cov0[i];
+            int dof = sh->npix - np;
+            if (dof == 0) {
+                flags |= NGX_ZERO_DOF;
+                for (int i = 0; i < np; i++) r.pars_err[i] = NGX_CDEF;
+                for (int i = 0; i < np * np; i++) r.pars_cov[i] = NGX_CDEF;
+            } else {
+                // fdiff[n_prior_pars:]: the simple priors fill one row fewer
+                // than they reserve, which drops the first pixel row
+                double ssq = sh->cur_ssq;
+                int nslots = prior_nslots(a.model, a.prior);
+                int nrows = prior_nrows(a.model, a.prior);
+                if (nslots > nrows) ssq -= sh->cur_rfirst2;
+                double s_sq = ssq / dof;
+                for (int i = 0; i < np * np; i++)
+                    r.pars_cov[i] = cov0[i] * s_sq;
+                int cflags = lm_test_cov(np, r.pars_cov);
+                if (cflags) {
+                    flags |= cflags;
+                    for (int i = 0; i < np; i++) r.pars_err[i] = NGX_CDEF;
+                } else {
+                    for (int i = 0; i < np; i++)
+                        r.pars_err[i] = sqrt(r.pars_cov[i * np + i]);
+                }
+            }
+        }
+    }
+    r.flags = flags;
+    if (flags == 0) {
+        double lnp_prior = 0.0;
+        int bad = prior_lnprob(a.model, a.prior, r.pars, &lnp_prior);
+        if (bad) {
+            r.lnprob = -INFINITY;
+            r.s2n_numer = 0.0;
+            r.s2n_denom = NGX_BIGVAL;
+            r.npix = 0;
+        } else {
+            r.lnprob = -0.5 * sh->cur_ssq + lnp_prior;
+            r.s2n_numer = sh->cur_num;
+            r.s2n_denom = sh->cur_den;
+            r.npix = sh->npix;
+        }
+        double s2n = 0.0;
+        if (r.s2n_denom > 0) s2n = r.s2n_numer / sqrt(r.s2n_denom);
+        double chi2 = r.lnprob / (-0.5);
+        int dof = r.npix - np;
+        r.chi2per = chi2 / dof;
+        r.dof = dof;
+        r.s2n = s2n;
+        r.T = r.pars[4];
+        r.T_err = sqrt(r.pars_cov[4 * np + 4]);
+        r.flux = r.pars[np - 1];
+        r.flux_err = sqrt(r.pars_cov[(np - 1) * np + (np - 1)]);
+    }
+    *out = r;
+}
+
+// ---------------------------------------------------------------------
+// MODE 0: analytic Jacobian (gauss/exp/dev), np = 6
+// MODE 1: forward differences (any model), np <= 8
+template <int MODE, int CV, int CD>
+__global__ void __launch_bounds__(256)
+k_lm_fit(LMArgs a) {
+    extern __shared__ double smem_d[];
+    __shared__ LMShared sh;
+    const int T = blockDim.x;
+    const int nwarps = T >> 5;
+    const int nmix = (MODE == 0) ? 1 : (a.np + 1);
+    // dynamic shared memory carve-up
+    double *ptab = smem_d;                                   // nmix*ngauss*16
+    double *gc = ptab + (size_t)nmix * a.ngauss * 16;        // nmix*ngauss*8
+    double *val = gc + (size_t)nmix * a.ngauss * GC_STRIDE;  // padded
+    double *ierr = val + a.padded;
+    double *rowd = ierr + a.padded;
+    double *cold = rowd + a.nrow;
+    double *scratch = cold + a.ncol;                         // 48 * nwarps
+    double *hs = scratch + 48 * nwarps;                      // 8
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh.stamp = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int stamp = sh.stamp;
+        if (stamp >= a.n) break;
+
+        // ---- stage the stamp
+        const double *im = a.images + (size_t)stamp * a.ntot;
+        const double *wt = a.weights + (size_t)stamp * a.ntot;
+        int cnt = 0, first = a.ntot;
+        for (int p = threadIdx.x; p < a.padded; p += T) {
+            double vv = 0.0, ie = 0.0;
+            if (p < a.ntot) {
+                double w = wt[p];
+                bool valid = !(a.ignore_zero_weight && w <= 0.0);
+                if (valid) {
+                    vv = im[p];
+                    ie = sqrt(w < 0.0 ? 0.0 : w);
+                    cnt++;
+                    if (p < first) first = p;
+                }
+            }
+            val[p] = vv;
+            ierr[p] = ie;
+        }
+        if (threadIdx.x == 0) {
+            sh.jac = a.jac[stamp];
+            sh.status = 0;
+        }
+        if (threadIdx.x < 6 * a.npsf)
+            sh.psf[threadIdx.x] = a.psf[(size_t)stamp * 6 * a.npsf
+                                        + threadIdx.x];
+        {
+            int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            for (int o = 16; o > 0; o >>= 1) {
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            }
+            if (lane == 0) { sh.warp_i[warp] = cnt; sh.warp_j[warp] = first; }
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < a.nrow; p += T)
+            rowd[p] = p - sh.jac.row0;
+        for (int p = threadIdx.x; p < a.ncol; p += T)
+            cold[p] = p - sh.jac.col0;
+        if (threadIdx.x == 0) {
+            int c = 0, f = a.ntot;
+            for (int w = 0; w < nwarps; w++) {
+                c += sh.warp_i[w];
+                f = min(f, sh.warp_j[w]);
+            }
+            sh.npix = c;
+            sh.first_idx = f;
+            // psf centroid and flux, gmix_get_cen :108-130
+            double prow = 0.0, pcol = 0.0, psum = 0.0;
+            for (int k = 0; k < a.npsf; k++) {
+                double p = sh.psf[6 * k];
+                prow += p * sh.psf[6 * k + 1];
+                pcol += p * sh.psf[6 * k + 2];
+                psum += p;
+            }
+            if (a.npsf > 0) {
+                sh.psf_row = prow / psum;
+                sh.psf_col = pcol / psum;
+                sh.psf_ipsum = 1.0 / psum;
+            }
+            lm_init(&sh.st, a.np, a.guess + (size_t)stamp * a.np,
+                    a.lm.maxfev, a.lm.ftol, a.lm.xtol);
+            sh.action = sh.st.action;
+            for (int i = 0; i < a.np; i++) sh.xeval[i] = sh.st.xtrial[i];
+            sh.cur_ssq = sh.cur_rfirst2 = sh.cur_num = sh.cur_den = 0.0;
+        }
+        __syncthreads();
+        const double area = sh.jac.scale * sh.jac.scale;
+
+        if (sh.npix == 0) {
+            // GMixFatalError("no weights > 0") at Observation construction
+            if (threadIdx.x == 0) {
+                ngx_lm_result r;
+                memset(&r, 0, sizeof(r));
+                r.flags = NGX_NO_ATTEMPT;
+                for (int i = 0; i < a.np; i++) {
+                    r.pars[i] = NGX_PDEF;
+                    r.pars_err[i] = NGX_CDEF;
+                }
+                a.res[stamp] = r;
+            }
+            continue;
+        }
+
+        // ---- the fit
+        while (sh.action != LM_ACT_DONE) {
+            const int action = sh.action;
+            if (threadIdx.x == 0) sh.status = 0;
+            __syncthreads();
+            if (action == LM_ACT_EVAL_F) {
+                build_mixture(a, &sh, sh.xeval, gc, ptab, area, 1);
+                __syncthreads();
+                double sums[4] = {0, 0, 0, 0};
+                if (!sh.status)
+                    value_pass<CV>(a, &sh, gc, ptab, val, ierr, rowd, cold,
+                                   sums);
+                block_sum<4>(sums, scratch);
+                if (threadIdx.x == 0) {
+                    int status = sh.status, ninf = 0;
+                    double ps = prior_fnorm2(a, sh.xeval, &status, &ninf);
+                    double fnorm;
+                    if (status) fnorm = nan("");
+                    else if (ninf == 1) fnorm = INFINITY;
+                    else if (ninf > 1) fnorm = nan("");
+                    else fnorm = sqrt(sums[0] + ps);
+                    int acc = lm_feed_f(&sh.st, fnorm);
+                    if (acc) {
+                        sh.cur_ssq = sums[0];
+                        sh.cur_num = sums[1];
+                        sh.cur_den = sums[2];
+                        sh.cur_rfirst2 = sums[3];
+                    }
+                }
+            } else if (MODE == 0) {
+                // analytic Jacobian at the accepted point
+                if (threadIdx.x == 0) {
+                    // calc_jacobian raises for T == 0 or flux == 0
+                    if (sh.st.x[4] == 0.0 || sh.st.x[5] == 0.0) sh.status = 1;
+                }
+                build_mixture(a, &sh, sh.st.x, gc, ptab, area, 1);
+                __syncthreads();
+                double sums[28];
+#pragma unroll
+                for (int i = 0; i < 28; i++) sums[i] = 0.0;
+                if (!sh.status)
+                    deriv_pass<CD>(a, &sh, sh.st.x, gc, ptab, val, ierr, rowd,
+                                   cold, sums);
+                block_sum<28>(sums, scratch);
+                if (threadIdx.x == 0) {
+                    double A[LM_MAXP * LM_MAXP], b[LM_MAXP];
+                    int np = a.np;
+                    int status = sh.status;
+                    double f0[NGX_MAX_PRIOR_ROWS];
+                    double jp[NGX_MAX_PRIOR_ROWS * LM_MAXP];
+                    int nr = prior_nrows(a.model, a.prior);
+                    if (!status && nr > 0) {
+                        if (prior_fill_fdiff(a.model, a.prior, sh.st.x, f0))
+                            status = 1;
+                        else if (prior_jacobian(a.model, a.prior, sh.st.x, np,
+                                                f0, jp))
+                            status = 1;
+                    }
+                    int q = 0;
+                    for (int aa = 0; aa < np; aa++)
+                        for (int bb = 0; bb <= aa; bb++) {
+                            double sv = status ? 0.0 : sums[q];
+                            if (!status)
+                                for (int r = 0; r < nr; r++)
+                                    sv += jp[r * np + aa] * jp[r * np + bb];
+                            A[aa + LM_MAXP * bb] = sv;
+                            A[bb + LM_MAXP * aa] = sv;
+                            q++;
+                        }
+                    for (int aa = 0; aa < np; aa++) {
+                        double sv = status ? 0.0 : sums[21 + aa];
+                        if (!status)
+                            for (int r = 0; r < nr; r++)
+                                if (isfinite(f0[r]))
+                                    sv += jp[r * np + aa] * f0[r];
+                        b[aa] = sv;
+                    }
+                    lm_feed_j(&sh.st, A, b, 0);
+                }
+            } else {
+                // forward differences: base + np perturbed mixtures
+                const int np = a.np;
+                if (threadIdx.x == 0) {
+                    const double eps = 1.4901161193847656e-08;  // sqrt(epsmch)
+                    for (int s = 0; s < np; s++) {
+                        double h = eps * fabs(sh.st.x[s]);
+                        if (h == 0.0) h = eps;
+                        hs[s] = h;
+                    }
+                }
+                __syncthreads();
+                int bad_any = 0;
+                for (int s = 0; s <= np; s++) {
+                    if (threadIdx.x == 0) {
+                        for (int i = 0; i < np; i++) sh.xeval[i] = sh.st.x[i];
+                        if (s > 0) {
+                            // x[j] = temp + h (fdjac2); h is then the
+                            // REPRESENTED difference only through hs
+                            sh.xeval[s - 1] = sh.st.x[s - 1] + hs[s - 1];
+                        }
+                        sh.status = 0;
+                    }
+                    __syncthreads();
+                    build_mixture(a, &sh, sh.xeval,
+                                  gc + (size_t)s * a.ngauss * GC_STRIDE,
+                                  ptab + (size_t)s * a.ngauss * 16, area, 1);
+                    __syncthreads();
+                    bad_any |= sh.status;
+                    __syncthreads();
+                }
+                const int nsums = np * (np + 1) / 2 + np + 1;
+                double sums[45];
+                for (int i = 0; i < 45; i++) sums[i] = 0.0;
+                if (!bad_any)
+                    fd_pass<LM_MAXP>(a, &sh, hs, gc, ptab, val, ierr, rowd,
+                                     cold, sums, nsums);
+                block_sum_n(sums, nsums, scratch);
+                if (threadIdx.x == 0) {
+                    double A[LM_MAXP * LM_MAXP], b[LM_MAXP];
+                    int status = bad_any;
+                    int nr = prior_nrows(a.model, a.prior);
+                    double f0[NGX_MAX_PRIOR_ROWS];
+                    double jp[NGX_MAX_PRIOR_ROWS * LM_MAXP];
+                    if (!status && nr > 0) {
+                        // the prior rows are part of fvec: same forward
+                        // difference with the MINPACK step
+                        if (prior_fill_fdiff(a.model, a.prior, sh.st.x, f0))
+                            status = 1;
+                        double xp[LM_MAXP], fs[NGX_MAX_PRIOR_ROWS];
+                        for (int s = 0; s < np && !status; s++) {
+                            for (int i = 0; i < np; i++) xp[i] = sh.st.x[i];
+                            xp[s] = sh.st.x[s] + hs[s];
+                            if (prior_fill_fdiff(a.model, a.prior, xp, fs)) {
+                                status = 1;
+                                break;
+                            }
+                            for (int r = 0; r < nr; r++)
+                                jp[r * np + s] = (fs[r] - f0[r]) / hs[s];
+                        }
+                    }
+                    int q = 0;
+                    for (int aa = 0; aa < np; aa++)
+                        for (int bb = 0; bb <= aa; bb++) {
+                            double sv = status ? 0.0 : sums[q];
+                            if (!status)
+                                for (int r = 0; r < nr; r++)
+                                    sv += jp[r * np + aa] * jp[r * np + bb];
+                            A[aa + LM_MAXP * bb] = sv;
+                            A[bb + LM_MAXP * aa] = sv;
+                            q++;
+                        }
+                    for (int aa = 0; aa < np; aa++) {
+                        double sv = status ? 0.0 : sums[q + aa];
+                        if (!status)
+                            for (int r = 0; r < nr; r++)
+                                sv += jp[r * np + aa] * f0[r];
+                        b[aa] = sv;
+                    }
+                    lm_feed_j(&sh.st, A, b, np);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                sh.action = sh.st.action;
+                for (int i = 0; i < a.np; i++) sh.xeval[i] = sh.st.xtrial[i];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) lm_finish(a, &sh, &a.res[stamp]);
+    }
+}
+
+// ---------------------------------------------------------------------
+static int *g_counter = nullptr;       // work-queue counter, one per process
+static int g_counter_dev = -1;
+
+static int get_counter(int **out) {
+    int dev = 0;
+    NGX_CUDA(cudaGetDevice(&dev));
+    if (!g_counter || g_counter_dev != dev) {
+        NGX_CUDA(cudaMalloc((void **)&g_counter, 64 * sizeof(int)));
+        g_counter_dev = dev;
+    }
+    *out = g_counter;
+    return NGX_OK;
+}
+
+struct LMLaunch {
+    int threads, blocks;
+    size_t smem;
+};
+
+template <typename K>
+static int config_and_launch(K kernel, const LMArgs &a, int threads,
+                             size_t smem, cudaStream_t stream) {
+    if (smem > (size_t)smem_optin_bytes())
+        return fail(NGX_ERR_ARG,
+                    "ngx_lm_fit: stamp + mixture do not fit shared memory%s%s");
+    NGX_CUDA(cudaFuncSetAttribute(kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    int per_sm = 0;
+    NGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,
+                                                           threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    int blocks = sm_count() * per_sm;
+    if (blocks > a.n) blocks = a.n;
+    NGX_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), stream));
+    kernel<<<blocks, threads, smem, stream>>>(a);
+    NGX_LAUNCH_CHECK();
+    return NGX_OK;
+}
+
+}  // namespace ngx
+
+using namespace ngx;
+
+extern "C" {
+
+int ngx_lm_fit(int n, int model, const double *images, const double *weights,
+               const ngx_jacobian *jac, int nrow, int ncol,
+               const double *psf_pars, int npsf, const double *guess,
+               const ngx_prior *prior, const ngx_lm_pars *lm_pars,
+               int ignore_zero_weight, ngx_lm_result *res, void *stream) {
+    NGX_REQUIRE(n >= 0 && images && weights && jac && guess && res);
+    NGX_REQUIRE(nrow >= 1 && ncol >= 1 && npsf >= 0 && npsf <= 16);
+    NGX_REQUIRE(npsf == 0 || psf_pars);
+    NGX_REQUIRE(lm_pars && lm_pars->maxfev > 0);
+    int np = model_npars(model), ng0 = model_ngauss(model);
+    NGX_REQUIRE(np > 0 && ng0 > 0 && model != NGX_CM);
+    if (n == 0) return NGX_OK;
+
+    LMArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.model = model; a.np = np; a.ngauss0 = ng0; a.npsf = npsf;
+    a.ngauss = ng0 * (npsf > 0 ? npsf : 1);
+    a.nrow = nrow; a.ncol = ncol; a.ntot = nrow * ncol;
+    a.ignore_zero_weight = ignore_zero_weight;
+    if (prior) a.prior = *prior;
+    a.lm = *lm_pars;
+    a.images = images; a.weights = weights; a.jac = jac;
+    a.psf = psf_pars; a.guess = guess; a.res = res;
+    NGX_REQUIRE(a.ngauss <= NGX_MAX_GAUSS);
+    if (a.prior.present) {
+        NGX_REQUIRE(a.prior.g_kind == 1);
+        NGX_REQUIRE(model != NGX_BD);   // PriorBDSep rows not built yet
+    }
+    int rc = get_counter(&a.counter);
+    if (rc) return rc;
+
+    bool analytic = lm_pars->analytic_jacobian
+        && (model == NGX_GAUSS || model == NGX_EXP || model == NGX_DEV);
+    a.analytic = analytic;
+    int threads = 128;
+    if (a.ntot <= 1024) threads = 64;
+    NGX_REQUIRE(threads >= a.ngauss && threads >= 6 * npsf);
+    const int CV = 3, CD = 3;
+    int tile = threads * CV * CD;      // padded to both chunk sizes
+    a.padded = ((a.ntot + tile - 1) / tile) * tile;
+    int nmix = analytic ? 1 : np + 1;
+    int nwarps = threads / 32;
+    size_t smem = sizeof(double)
+        * ((size_t)nmix * a.ngauss * (16 + GC_STRIDE) + 2 * (size_t)a.padded
+           + nrow + ncol + 48 * nwarps + 8);
+    if (analytic)
+        return config_and_launch(k_lm_fit<0, CV, CD>, a, threads, smem,
+                                 as_stream(stream));
+    return config_and_launch(k_lm_fit<1, CV, CD>, a, threads, smem,
+                             as_stream(stream));
+}
+
+int ngx_lm_fit_host(int n, int model, const double *images,
+                    const double *weights, const ngx_jacobian *jac, int nrow,
+                    int ncol, const double *psf_pars, int npsf,
+                    const double *guess, const ngx_prior *prior,
+                    const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                    ngx_lm_result *res) {
+    NGX_REQUIRE(n >= 0 && images && weights && jac && guess && res);
+    if (n == 0) return NGX_OK;
+    int np = model_npars(model);
+    NGX_REQUIRE(np > 0);
+    // chunked, double-buffered pipeline: H2D of chunk i+1 overlaps the fit
+    // of chunk i when the host arrays are pinned
+    const size_t ntot = (size_t)nrow * ncol;
+    int chunk = 2048;
+    if (chunk > n) chunk = n;
+    static thread_local double *d_im[2] = {nullptr, nullptr};
+    static thread_local double *d_wt[2] = {nullptr, nullptr};
+    static thread_local ngx_jacobian *d_jac[2] = {nullptr, nullptr};
+    static thread_local double *d_psf[2] = {nullptr, nullptr};
+    static thread_local double *d_guess[2] = {nullptr, nullptr};
+    static thread_local ngx_lm_result *d_res[2] = {nullptr, nullptr};
+    static thread_local size_t cap_pix = 0, cap_obj = 0, cap_psf = 0;
+    static thread_local cudaStream_t streams[2] = {nullptr, nullptr};
+    if (!streams[0]) {
+        NGX_CUDA(cudaStreamCreate(&streams[0]));
+        NGX_CUDA(cudaStreamCreate(&streams[1]));
+    }
+    size_t need_pix = (size_t)chunk * ntot, need_obj = chunk;
+    size_t need_psf = (size_t)chunk * 6 * (npsf > 0 ? npsf : 1);
+    if (need_pix > cap_pix || need_obj > cap_obj || need_psf > cap_psf) {
+        NGX_CUDA(cudaDeviceSynchronize());
+        for (int b = 0; b < 2; b++) {
+            cudaFree(d_im[b]); cudaFree(d_wt[b]); cudaFree(d_jac[b]);
+            cudaFree(d_psf[b]); cudaFree(d_guess[b]); cudaFree(d_res[b]);
+            NGX_CUDA(cudaMalloc((void **)&d_im[b], need_pix * sizeof(double)));
+            NGX_CUDA(cudaMalloc((void **)&d_wt[b], need_pix * sizeof(double)));
+            NGX_CUDA(cudaMalloc((void **)&d_jac[b],
+                                need_obj * sizeof(ngx_jacobian)));
+            NGX_CUDA(cudaMalloc((void **)&d_psf[b],
+                                need_psf * sizeof(double)));
+            NGX_CUDA(cudaMalloc((void **)&d_guess[b],
+                                need_obj * 8 * sizeof(double)));
+            NGX_CUDA(cudaMalloc((void **)&d_res[b],
+                                need_obj * sizeof(ngx_lm_result)));
+        }
+        cap_pix = need_pix; cap_obj = need_obj; cap_psf = need_psf;
+    }
+    // the work-queue counter is shared by launches: serialise the kernels on
+    // one stream (streams[0]) and use streams[1] only for copies
+    cudaEvent_t up[2], done[2];
+    for (int b = 0; b < 2; b++) {
+        NGX_CUDA(cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming));
+        NGX_CUDA(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+    }
+    int nchunks = (n + chunk - 1) / chunk;
+    for (int c = 0; c < nchunks; c++) {
+        int b = c & 1;
+        int lo = c * chunk;
+        int cn = n - lo < chunk ? n - lo : chunk;
+        // buffer b is free once the kernel of chunk c-2 has finished and its
+        // results were copied out (both on streams[0])
+        NGX_CUDA(cudaStreamWaitEvent(streams[1], done[b], 0));
+        NGX_CUDA(cudaMemcpyAsync(d_im[b], images + lo * ntot,
+                                 cn * ntot * sizeof(double),
+                                 cudaMemcpyHostToDevice, streams[1]));
+        NGX_CUDA(cudaMemcpyAsync(d_wt[b], weights + lo * ntot,
+                                 cn * ntot * sizeof(double),
+                                 cudaMemcpyHostToDevice, streams[1]));
+        NGX_CUDA(cudaMemcpyAsync(d_jac[b], jac + lo,
+                                 cn * sizeof(ngx_jacobian),
+                                 cudaMemcpyHostToDevice, streams[1]));
+        if (npsf > 0)
+            NGX_CUDA(cudaMemcpyAsync(d_psf[b],
+                                     psf_pars + (size_t)lo * 6 * npsf,
+                                     (size_t)cn * 6 * npsf * sizeof(double),
+                                     cudaMemcpyHostToDevice, streams[1]));
+        NGX_CUDA(cudaMemcpyAsync(d_guess[b], guess + (size_t)lo * np,
+                                 (size_t)cn * np * sizeof(double),
+                                 cudaMemcpyHostToDevice, streams[1]));
+        NGX_CUDA(cudaEventRecord(up[b], streams[1]));
+        NGX_CUDA(cudaStreamWaitEvent(streams[0], up[b], 0));
+        int rc = ngx_lm_fit(cn, model, d_im[b], d_wt[b], d_jac[b], nrow, ncol,
+                            npsf > 0 ? d_psf[b] : nullptr, npsf, d_guess[b],
+                            prior, lm_pars, ignore_zero_weight, d_res[b],
+                            streams[0]);
+        if (rc) return rc;
+        NGX_CUDA(cudaMemcpyAsync(res + lo, d_res[b],
+                                 cn * sizeof(ngx_lm_result),
+                                 cudaMemcpyDeviceToHost, streams[0]));
+        NGX_CUDA(cudaEventRecord(done[b], streams[0]));
+    }
+    NGX_CUDA(cudaStreamSynchronize(streams[0]));
+    NGX_CUDA(cudaStreamSynchronize(streams[1]));
+    for (int b = 0; b < 2; b++) {
+        cudaEventDestroy(up[b]);
+        cudaEventDestroy(done[b]);
+    }
+    return NGX_OK;
+}
+
+}  // extern "C"

@@ -445,7 +445,6 @@ __global__ void k_deriv_images(int ngauss, const double *__restrict__ gpars,
             for (int a = 0; a < 3; a++) {
                 o[6 + a] = w11 * dc[3 * a] + 2.0 * w12 * dc[3 * a + 1]
                     + w22 * dc[3 * a + 2];
-                // dcov rows kept in global: read through gc + 9..14? no:
             }
         }
     }
