@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""
+bench.py - the headline benchmark of BASELINE.json:
+
+    galaxy LM fits/sec (+ model-pixel evals/sec) on N B200s, beside the
+    reference algorithm timed on the host's own cores.
+
+Workload (BASELINE.json configs[1]): 10 000 exp-model LM fits per GPU, 48x48
+stamps, 3-gaussian ('turb') PSF convolution -> 18 composed gaussians, default
+fit_pars (maxfev 4000, ftol = xtol = 1e-5), analytic Jacobian, no prior.
+A "step" is one pass of the hot path (ngx_lm_fit) over the whole batch.
+Objects shard by index over ranks with no collective: weak scaling, each rank
+fits its own 10 000 stamps (seeded by global index).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement
+of the reference algorithm (oracle/, kind "port": the reference is Python +
+numba + scipy and cannot travel to the GPU box) with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NOBJ = 10000
+DIMS = (48, 48)
+NGAUSS = 18
+# algorithmic work per gaussian-pixel evaluation, SURVEY.md section 8(d):
+FLOPS_VALUE, FLOPS_DERIV = 28.0, 74.0      # source flops (reference code)
+INSTR_VALUE, INSTR_DERIV = 16.0, 30.0      # fused fp64 instructions, ours
+
+
+def make_inputs(nobj, seed0, dims=DIMS, noise=0.01):
+    """config-2 stamps: parameters on the host (seeded per object), truth
+    rendered by the engine itself (exact exp), gaussian noise added"""
+    from ngmix_b200 import sims, _lib
+    b = sims.make_lm_batch(nobj, seed0=seed0, dims=dims, noise=noise,
+                           truth_images=False)
+    gm0, st = _lib.gmix_fill("exp", b["truth"])
+    assert not st.any()
+    gp, _ = _lib.gmix_fill("full", b["psf"].reshape(nobj, -1))
+    gm = _lib.gmix_convolve(gm0, gp)
+    images, st = _lib.render(gm, b["jac"], dims, fast_exp=False)
+    assert not st.any()
+    rng = np.random.RandomState(seed0 + 987654321 % (2 ** 31))
+    images += rng.normal(0.0, noise, size=images.shape)
+    b["images"] = images
+    return b
+
+
+def make_inputs_host(nobj, seed0, dims=DIMS, noise=0.01):
+    """same stamps without a GPU (numpy render) for the reference arm"""
+    from ngmix_b200 import sims
+    return sims.make_lm_batch(nobj, seed0=seed0, dims=dims, noise=noise)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,"
+         "clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(", "))
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def time_cpu_port(b, nthreads, target_s=12.0):
+    """the oracle port on the host cores, on a bounded sample of the same
+    workload; returns (fits/s, nsample, seconds)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    oracle.build()
+    n = b["images"].shape[0]
+    # calibrate on a few fits per thread
+    ncal = min(n, 4 * nthreads)
+    t0 = time.perf_counter()
+    oracle.lm_fit_batch("exp", b["images"][:ncal], b["weights"][:ncal],
+                        b["jac"][:ncal], b["psf"][:ncal], b["guess"][:ncal],
+                        nthreads=nthreads)
+    tcal = time.perf_counter() - t0
+    rate = ncal / tcal
+    ns = int(min(n, max(ncal, rate * target_s)))
+    t0 = time.perf_counter()
+    res = oracle.lm_fit_batch("exp", b["images"][:ns], b["weights"][:ns],
+                              b["jac"][:ns], b["psf"][:ns], b["guess"][:ns],
+                              nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return ns / dt, ns, dt, res
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port, all
+    host threads) on a bounded sample of the same workload per step"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    nsample = min(NOBJ, 64 * cores)
+    b = make_inputs_host(nsample, seed0=0)
+    times = []
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    oracle.build()
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        oracle.lm_fit_batch("exp", b["images"], b["weights"], b["jac"],
+                            b["psf"], b["guess"], nthreads=cores)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt)
+        # keep the whole run within a few minutes
+        if sum(times) > 120 and len(times) >= 1:
+            break
+    ms = 1e3 * float(np.mean(times))
+    value = nsample / (ms * 1e-3)
+    out = {
+        "impl": "reference",
+        "metric": "galaxy LM fits/sec",
+        "value": value, "unit": "fits/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "exp-model LM fits, 48x48 stamps, 3-gaussian "
+                               "PSF (18 gaussians), analytic Jacobian, "
+                               "no prior; CPU sample of %d stamps per step"
+                               % nsample},
+        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": cores,
+                         "kind": "port",
+                         "sample": "%d stamps per step, %d threads over "
+                                   "objects" % (nsample, cores)},
+        "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nobj", type=int, default=NOBJ)
+    ap.add_argument("--no-cpu", action="store_true",
+                    help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ngmix_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: no CPU fallback")
+    torch.cuda.set_device(local)
+    _lib.init(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    nobj = args.nobj
+    W = max(args.warmup, 3)
+
+    # roofline denominator: MEASURED_PEAKS.json has no fp64 entry, so the
+    # fp64 FMA issue peak is measured here, on this box, before the run
+    dfma_per_s, _ = _lib.peak_dfma(60000)
+
+    # ---- inputs: objects [rank*nobj, (rank+1)*nobj)
+    b = make_inputs(nobj, seed0=rank * nobj)
+    H, Wd = DIMS
+    npars = 6
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+
+    h_images, h_weights = pinned(b["images"]), pinned(b["weights"])
+    h_jac, h_psf, h_guess = pinned(b["jac"]), pinned(b["psf"]), \
+        pinned(b["guess"])
+    h_res = torch.zeros(nobj * _lib.LM_RESULT_DTYPE.itemsize,
+                        dtype=torch.uint8).pin_memory()
+    d_images = h_images.to(dev)
+    d_weights = h_weights.to(dev)
+    d_jac, d_psf, d_guess = h_jac.to(dev), h_psf.to(dev), h_guess.to(dev)
+    d_res = torch.zeros(nobj * _lib.LM_RESULT_DTYPE.itemsize,
+                        dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        _lib.lm_fit_device("exp", nobj, d_images.data_ptr(),
+                           d_weights.data_ptr(), d_jac.data_ptr(), H, Wd,
+                           d_psf.data_ptr(), 3, d_guess.data_ptr(),
+                           d_res.data_ptr(), stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (inputs in HBM; 369 MB per step >> L2)
+    for _ in range(W):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record(stream)
+    for k in range(args.steps):
+        kev[k][0].record(stream)
+        step_device()
+        kev[k][1].record(stream)
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    kernel_ms = float(np.mean([a.elapsed_time(c) for a, c in kev]))
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(),
+                        dtype=_lib.LM_RESULT_DTYPE)
+    nfev = res["nfev"].astype("f8")
+    njev = res["njev"].astype("f8")
+    npix = float(H * Wd)
+    value_evals = float((nfev * npix).sum())        # model-pixel evals
+    deriv_evals = float((njev * npix).sum())
+    nflag = int((res["flags"] != 0).sum())
+
+    # ---- end to end through the public host-buffer call: pinned host
+    # inputs -> device -> fit -> results back on the host, every step
+    def step_e2e():
+        return _lib.lm_fit("exp", h_images.numpy(), h_weights.numpy(),
+                           h_jac.numpy(), h_psf.numpy(), h_guess.numpy())
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r_e2e = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    assert np.array_equal(r_e2e["flags"], res["flags"])
+    h2d = int(h_images.numel() * 8 * 2 + h_jac.numel() * 8
+              + h_psf.numel() * 8 + h_guess.numel() * 8)
+    d2h = int(nobj * _lib.LM_RESULT_DTYPE.itemsize)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fits_per_s = world * nobj / (ms_per_step * 1e-3)
+    # roofline of the dominant (only) kernel, k_lm_fit: fp64 FMA pipe
+    flops = NGAUSS * (value_evals * FLOPS_VALUE + deriv_evals * FLOPS_DERIV)
+    instr = NGAUSS * (value_evals * INSTR_VALUE + deriv_evals * INSTR_DERIV)
+    peak_flops = 2.0 * dfma_per_s
+    achieved = flops / (kernel_ms * 1e-3)
+    alg_bytes = nobj * (2 * npix * 8 + 64 + 3 * 48 + 48
+                        + _lib.LM_RESULT_DTYPE.itemsize)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    out = {
+        "metric": "galaxy LM fits/sec",
+        "value": fits_per_s, "unit": "fits/s", "n_gpus": world,
+        "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": "configs[1]: %d exp-model LM fits per GPU, 48x48 "
+                        "stamps, 3-gaussian PSF (18 gaussians), analytic "
+                        "Jacobian, no prior, noise 0.01" % nobj,
+            "timing": "inputs resident in HBM; %.0f MB of stamps per step, "
+                      "larger than L2" % (alg_bytes / 1e6),
+            "parallelism": "objects sharded by index over %d rank(s), no "
+                           "collective" % world,
+        },
+        "model_pixel_evals_per_s": world * (value_evals + deriv_evals)
+        / (ms_per_step * 1e-3),
+        "gaussian_pixel_evals_per_s": world * NGAUSS
+        * (value_evals + deriv_evals) / (ms_per_step * 1e-3),
+        "fit_stats": {"median_nfev": float(np.median(nfev)),
+                      "median_njev": float(np.median(njev)),
+                      "nonzero_flags": nflag},
+        "e2e": {"value": world * nobj * args.steps / e2e_s,
+                "unit": "fits/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
+                "api": "ngmix_b200._lib.lm_fit -> ngx_lm_fit_host (pinned "
+                       "host buffers, chunked H2D overlapped with the fit)"},
+        "gpu_launches": args.steps,
+        "roofline": {
+            "bound": "fp64", "achieved": achieved / 1e9,
+            "peak": peak_flops / 1e9, "unit": "GFLOP/s",
+            "frac": achieved / peak_flops,
+            "peak_source": "measured in this run by ngx_peak_dfma (dense "
+                           "DFMA issue, x2 flops); MEASURED_PEAKS.json has "
+                           "no fp64 entry",
+            "algorithmic": "28 flops per value and 74 per derivative "
+                           "gaussian-pixel evaluation (SURVEY.md 8d) x 18 "
+                           "gaussians x 2304 px x (nfev + njev) passes",
+            "frac_fp64_instr": instr / (kernel_ms * 1e-3) / dfma_per_s,
+            "kernel": "k_lm_fit", "kernel_ms": kernel_ms,
+            "hbm_achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9,
+            "hbm_frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+            "traffic": None,
+        },
+        "clocks": clocks,
+    }
+    if not args.no_cpu:
+        cores = os.cpu_count()
+        cpu_rate, ns, dt, ores = time_cpu_port(b, cores)
+        out["cpu_baseline"] = {
+            "value": cpu_rate, "unit": "fits/s", "cores": cores,
+            "kind": "port",
+            "sample": "first %d stamps of the same batch, %d threads over "
+                      "objects, %.1f s" % (ns, cores, dt)}
+        # parity on the sample, reported beside the throughput
+        same = (ores["flags"] == res["flags"][:ns])
+        perr = np.abs(res["pars"][:ns, :6] - ores["pars"][:, :6])
+        tol = np.maximum(1e-5 * np.abs(ores["pars"][:, :6]),
+                         1e-3 * ores["pars_err"][:, :6])
+        out["parity_on_sample"] = {
+            "n": int(ns), "flags_equal": int(same.sum()),
+            "nfev_ier_equal": int(((ores["nfev"] == res["nfev"][:ns])
+                                   & (ores["ier"] == res["ier"][:ns])).sum()),
+            "pars_within_1e-5": int(np.all(perr <= tol, axis=1).sum())}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

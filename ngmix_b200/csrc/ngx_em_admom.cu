@@ -2,43 +2,55 @@
 //         em_run / _fixcen / _fixcov / _fluxonly (em/em_nb.py:15-1257)
 // ngx_admom: admom (ngmix/admom/admom_nb.py:13-243)
 //
-// One CTA per stamp, the whole iteration loop inside the kernel.  The stamp
-// (val + a validity/zero-weight code) stays in shared memory; per iteration
-// the E step runs over the pixels with the per-gaussian sums in registers,
-// a shuffle/shared-memory block reduction (fixed order, no atomics) forms
-// the 6*ngauss+2 (EM) or 37 (admom) sums, and the M step / moment update is
-// done by the first ngauss threads.
+// One CTA per stamp, the whole iteration loop inside the kernel, the stamp
+// resident in shared memory.
+//
+// EM is REFERENCE-ORDER by construction.  On noisy PSF stamps the EM
+// iteration count is chaotic: letting a compiler contract the reference's
+// own loops into FMAs changes numiter on 14 of 64 golden stamps by up to 240
+// iterations (measured with the oracle).  Bit-exact iteration counts
+// therefore need the reference's exact arithmetic: every per-pixel quantity
+// is computed unfused in the reference's operation order, and the pixel sums
+// are accumulated in pixel order - by 6*ngauss+2 threads, one per sum, each
+// walking a 64-pixel tile of per-pixel contributions that all 64 threads
+// produced in parallel.  Only the convergence scalar (log of p and det) can
+// differ from the reference, by an ulp of libm's log.
+//
+// admom converges in ~8 well-conditioned iterations, so it uses the fast
+// path (fused evaluation, shuffle-tree reductions).
 #include "ngx_core.cuh"
 #include "ngx_host.cuh"
 
 namespace ngx {
 
 #define NGX_EM_MAX_CONV 48
+#define NGX_EM_TILE 64          // pixels per tile == threads per CTA
+#define NGX_EM_MAX_SLOTS 64     // 6*ngauss + 2 <= 62
 
-// gaussian record used inside the EM kernel
 struct EMGauss {
     double p, row, col, irr, irc, icc;
 };
 
 struct EMShared {
-    EMGauss gm[10];           // pre-psf mixture being fitted
+    EMGauss gm[10];              // pre-psf mixture being fitted
     EMGauss psf[16];
-    GaussV conv[NGX_EM_MAX_CONV];
-    double logtd[NGX_EM_MAX_CONV];   // logtau - 0.5 logdet of conv gaussians
+    ngx_gauss conv[NGX_EM_MAX_CONV];   // normalised convolved mixture
+    double logtau[NGX_EM_MAX_CONV], logdet[NGX_EM_MAX_CONV];
     double tab[16];
     double psf_irr, psf_irc, psf_icc, psf_row, psf_col, psf_ipsum;
-    double sky, elogL_last, frac_diff, p_last;
-    double red[64];           // reduced sums
+    double sky, elogL_last, frac_diff, p_last, shift;
+    double red[NGX_EM_MAX_SLOTS];      // the accumulated sums
+    double mn[2], mx[2];
     ngx_jacobian jac;
-    int npix, numiter, status, done, fill_zero, stamp;
-    int warp_i[32];
+    unsigned valid_mask[2];
+    int npix, numiter, status, done, fill_zero;
+    int cnt[2], nzero[2];
 };
 
-// convolve gm with psf and set norms; thread k < ngauss*npsf.
-// em_nb.py:343-354 (gmix_convolve_fill + gmix_set_norms) and
-// set_logtau_logdet :658-675
+// gmix_convolve_fill + gmix_set_norms (em_nb.py:343-354) and
+// set_logtau_logdet (:658-675); thread k < ngauss*npsf
 __device__ __forceinline__ void em_build_conv(EMShared *sh, int ngauss,
-                                              int npsf, double area) {
+                                              int npsf, bool want_log) {
     int k = threadIdx.x;
     if (k >= ngauss * npsf) return;
     int io = k / npsf, ip = k - io * npsf;
@@ -52,13 +64,17 @@ __device__ __forceinline__ void em_build_conv(EMShared *sh, int ngauss,
         atomicOr(&sh->status, NGX_ST_RANGE_ERROR);
         return;
     }
-    sh->conv[k] = make_gaussv(g, area);
-    sh->logtd[k] = log(g.p) - 0.5 * log(g.det);
+    sh->conv[k] = g;
+    if (want_log) {
+        sh->logtau[k] = log(g.p);
+        sh->logdet[k] = log(g.det);
+    }
 }
 
-// VARIANT: NGX_EM_FULL / FIXCEN / FIXCOV / FLUXONLY; NG = object gaussians
-template <int VARIANT, int NG>
-__global__ void __launch_bounds__(128)
+// slot layout per object gaussian ii: 6*ii + {0 pnew, 1 vsum, 2 usum,
+// 3 v2sum, 4 uvsum, 5 u2sum}; then 6*ngauss: elogL, 6*ngauss+1: skysum
+template <int VARIANT>
+__global__ void __launch_bounds__(NGX_EM_TILE)
 k_em(int n, const double *__restrict__ images,
      const double *__restrict__ weights, const ngx_jacobian *__restrict__ jac,
      int nrow, int ncol, const double *__restrict__ guess, int ngauss,
@@ -70,21 +86,21 @@ k_em(int n, const double *__restrict__ images,
     constexpr bool DO_CEN = (VARIANT == NGX_EM_FULL || VARIANT == NGX_EM_FIXCOV);
     constexpr bool DO_COV = (VARIANT == NGX_EM_FULL || VARIANT == NGX_EM_FIXCEN);
     constexpr bool DO_LOGL = (VARIANT != NGX_EM_FLUXONLY);
-    constexpr int NS = 6 * NG + 2;      // per gaussian 6, + elogL + skysum
-    const int T = blockDim.x;
-    const int nwarps = T >> 5;
+    const int T = NGX_EM_TILE;
     const int ntot = nrow * ncol;
     const int npsf = npsf_in > 0 ? npsf_in : 1;
+    const int nslots = 6 * ngauss + 2;
     double *val = smem_d;               // ntot
     double *code = val + ntot;          // ntot: <0 excluded, 0 zero weight
     double *rowd = code + ntot;
     double *cold = rowd + nrow;
-    double *scratch = cold + ncol;      // NS * nwarps
+    double *contrib = cold + ncol;      // nslots * T, slot major
 
     const int stamp = blockIdx.x;
     if (stamp >= n) return;
     const double *im = images + (size_t)stamp * ntot;
     const double *wt = weights + (size_t)stamp * ntot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // ---- stage the stamp; min/max for prep_image
     double mn = INFINITY, mx = -INFINITY;
@@ -105,14 +121,9 @@ k_em(int n, const double *__restrict__ images,
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
     }
-    {
-        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (lane == 0) {
-            scratch[warp] = mn;
-            scratch[nwarps + warp] = mx;
-            sh.warp_i[warp] = cnt;
-            sh.warp_i[16 + warp] = nzero;
-        }
+    if (lane == 0) {
+        sh.mn[warp] = mn; sh.mx[warp] = mx;
+        sh.cnt[warp] = cnt; sh.nzero[warp] = nzero;
     }
     load_exp_table(sh.tab);
     if (threadIdx.x == 0) {
@@ -142,29 +153,22 @@ k_em(int n, const double *__restrict__ images,
     for (int p = threadIdx.x; p < nrow; p += T) rowd[p] = p - sh.jac.row0;
     for (int p = threadIdx.x; p < ncol; p += T) cold[p] = p - sh.jac.col0;
     if (threadIdx.x == 0) {
-        double a = INFINITY, b = -INFINITY;
-        int c = 0, z = 0;
-        for (int w = 0; w < nwarps; w++) {
-            a = fmin(a, scratch[w]);
-            b = fmax(b, scratch[nwarps + w]);
-            c += sh.warp_i[w];
-            z += sh.warp_i[16 + w];
-        }
-        sh.npix = c;
-        sh.fill_zero = z > 0;
+        double a = fmin(sh.mn[0], sh.mn[1]), b = fmax(sh.mx[0], sh.mx[1]);
+        sh.npix = sh.cnt[0] + sh.cnt[1];
+        sh.fill_zero = (sh.nzero[0] + sh.nzero[1]) > 0;
         if (conf.have_sky) {
             sh.sky = conf.sky;
-            sh.red[0] = 0.0;
+            sh.shift = 0.0;
         } else {
             // prep_image, em.py:109-120
             double desired_minval = 0.001 * (b - a);
             sh.sky = desired_minval - a;
-            sh.red[0] = sh.sky;
+            sh.shift = sh.sky;
         }
         // psf.set_flux(1.0) (gmix.py:299-311) when a psf was given
-        double psum0 = 0.0;
-        for (int k = 0; k < npsf; k++) psum0 += sh.psf[k].p;
         if (npsf_in > 0) {
+            double psum0 = 0.0;
+            for (int k = 0; k < npsf; k++) psum0 += sh.psf[k].p;
             double rat = 1.0 / psum0;
             for (int k = 0; k < npsf; k++) sh.psf[k].p *= rat;
         }
@@ -192,19 +196,17 @@ k_em(int n, const double *__restrict__ images,
         double pl = 0.0;
         for (int k = 0; k < ngauss; k++) pl += sh.gm[k].p;
         sh.p_last = pl;
+        if (sh.npix == 0) sh.status = NGX_ST_FATAL;
     }
     __syncthreads();
     if (!conf.have_sky) {
-        double s = sh.red[0];
+        double s = sh.shift;
         for (int p = threadIdx.x; p < ntot; p += T) val[p] += s;
     }
     const double area = sh.jac.scale * sh.jac.scale;
     const double dvdrow = sh.jac.dvdrow, dvdcol = sh.jac.dvdcol;
     const double dudrow = sh.jac.dudrow, dudcol = sh.jac.dudcol;
-    em_build_conv(&sh, ngauss, npsf, area);
-    __syncthreads();
-
-    if (sh.npix == 0 && threadIdx.x == 0) sh.status = NGX_ST_FATAL;
+    em_build_conv(&sh, ngauss, npsf, DO_LOGL);
     __syncthreads();
 
     // ---- iterations
@@ -218,112 +220,132 @@ k_em(int n, const double *__restrict__ images,
                     double v = dvdrow * rowd[row] + dvdcol * cold[col];
                     double u = dudrow * rowd[row] + dudcol * cold[col];
                     double s = 0.0;
-                    for (int k = 0; k < ngauss * npsf; k++)
-                        s += eval_fast(sh.conv[k], v, u, sh.tab);
+                    for (int k = 0; k < ngauss * npsf; k++) {
+                        const ngx_gauss &g = sh.conv[k];
+                        double vdiff = v - g.row, udiff = u - g.col;
+                        double chi2 = g.dcc * vdiff * vdiff
+                            + g.drr * udiff * udiff
+                            - 2.0 * g.drc * vdiff * udiff;
+                        double mv = 0.0;
+                        if (chi2 < 25.0 && chi2 >= 0.0) {
+                            double x = -0.5 * chi2;
+                            mv = g.pnorm * fexp_ref(x) * area;
+                            if (chi2 > 20.0) mv *= apod_window_x(x);
+                        }
+                        s += mv;
+                    }
                     val[p] = sky + s;
                 }
             }
-            __syncthreads();
         }
-        double sums[NS];
-#pragma unroll
-        for (int i = 0; i < NS; i++) sums[i] = 0.0;
-        int bad = 0;
-        for (int p = threadIdx.x; p < ntot; p += T) {
-            if (code[p] < 0.0) continue;
-            int row = p / ncol, col = p - row * ncol;
-            double v = dvdrow * rowd[row] + dvdcol * cold[col];
-            double u = dudrow * rowd[row] + dudcol * cold[col];
-            double gi[NG], tv[NG], tu[NG], tv2[NG], tuv[NG], tu2[NG];
-            double gsum = 0.0, logL = 0.0;
-#pragma unroll
-            for (int ii = 0; ii < NG; ii++) {
-                gi[ii] = tv[ii] = tu[ii] = tv2[ii] = tuv[ii] = tu2[ii] = 0.0;
-                if (ii < ngauss) {
+        if (threadIdx.x < nslots) sh.red[threadIdx.x] = 0.0;
+        double acc = 0.0;          // thread s accumulates slot s
+        __syncthreads();
+
+        for (int base = 0; base < ntot; base += T) {
+            // ---- phase A: one pixel per thread, reference operation order
+            int p = base + threadIdx.x;
+            bool valid = (p < ntot) && (code[p] >= 0.0);
+            int bad = 0;
+            if (valid) {
+                int row = p / ncol, col = p - row * ncol;
+                double v = dvdrow * rowd[row] + dvdcol * cold[col];
+                double u = dudrow * rowd[row] + dudcol * cold[col];
+                double gsum = 0.0, logL = 0.0;
+                for (int ii = 0; ii < ngauss; ii++) {
+                    double gi = 0.0, tv = 0.0, tu = 0.0, tv2 = 0.0, tuv = 0.0,
+                           tu2 = 0.0;
                     for (int k = ii * npsf; k < (ii + 1) * npsf; k++) {
-                        GaussV g = sh.conv[k];
+                        const ngx_gauss &g = sh.conv[k];
                         double vdiff = v - g.row;
                         double udiff = u - g.col;
                         double u2 = udiff * udiff;
                         double v2 = vdiff * vdiff;
                         double uv = udiff * vdiff;
-                        // -chi2/2 with the hard chi2 < 25 cut and NO
-                        // apodization, em_nb.py:222-227
-                        double x = fma(g.c, uv, fma(g.b, u2, g.a * v2));
-                        double vl = 0.0;
-                        if (x_in_range(x)) {
-                            int idx;
-                            double f = fexp_reduce(x, &idx);
-                            vl = (sh.tab[idx] * g.pn) * fexp_poly(f);
-                        }
-                        gi[ii] += vl;
+                        double chi2 = g.dcc * v2 + g.drr * u2
+                            - 2.0 * g.drc * uv;
+                        double vl;
+                        // hard cut, NO apodization: em_nb.py:222-227
+                        if (chi2 < 25.0 && chi2 >= 0.0)
+                            vl = g.pnorm * fexp_ref(-0.5 * chi2) * area;
+                        else
+                            vl = 0.0;
+                        gi += vl;
                         gsum += vl;
                         if (DO_CEN) {
-                            tv[ii] = fma(v, vl, tv[ii]);
-                            tu[ii] = fma(u, vl, tu[ii]);
+                            tv += v * vl;
+                            tu += u * vl;
                         }
                         if (DO_COV) {
-                            tv2[ii] = fma(v2, vl, tv2[ii]);
-                            tuv[ii] = fma(uv, vl, tuv[ii]);
-                            tu2[ii] = fma(u2, vl, tu2[ii]);
+                            tv2 += v2 * vl;
+                            tuv += uv * vl;
+                            tu2 += u2 * vl;
                         }
-                        if (DO_LOGL) logL = fma(vl, sh.logtd[k] + x, logL);
+                        if (DO_LOGL)
+                            logL += vl * (sh.logtau[k] - 0.5 * sh.logdet[k]
+                                          - 0.5 * chi2);
                     }
+                    double *c = contrib + (size_t)(6 * ii) * T + threadIdx.x;
+                    c[0] = gi; c[T] = tv; c[2 * T] = tu;
+                    c[3 * T] = tv2; c[4 * T] = tuv; c[5 * T] = tu2;
+                }
+                if (DO_LOGL) {
+                    if (gsum == 0.0) logL = 0.0;
+                    else logL *= 1.0 / gsum;
+                }
+                double gtot = gsum + sky;
+                if (gtot == 0.0) {
+                    bad = 1;
+                } else {
+                    double pv = val[p];
+                    contrib[(size_t)(6 * ngauss) * T + threadIdx.x] = logL;
+                    contrib[(size_t)(6 * ngauss + 1) * T + threadIdx.x] =
+                        sky * pv / gtot;
+                    double factor = pv / gtot;
+                    for (int s = 0; s < 6 * ngauss; s++)
+                        contrib[(size_t)s * T + threadIdx.x] *= factor;
                 }
             }
-            if (DO_LOGL) {
-                if (gsum == 0.0) logL = 0.0;
-                else logL *= 1.0 / gsum;
+            unsigned bal = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) sh.valid_mask[warp] = bal;
+            if (bad) atomicOr(&sh.status, NGX_ST_RANGE_ERROR);   // gtot == 0
+            __syncthreads();
+            if (sh.status) break;
+            // ---- phase B: thread s adds its slot in pixel order
+            if (threadIdx.x < nslots) {
+                const double *c = contrib + (size_t)threadIdx.x * T;
+                unsigned m0 = sh.valid_mask[0], m1 = sh.valid_mask[1];
+#pragma unroll 8
+                for (int t = 0; t < 32; t++)
+                    if ((m0 >> t) & 1u) acc += c[t];
+#pragma unroll 8
+                for (int t = 0; t < 32; t++)
+                    if ((m1 >> t) & 1u) acc += c[32 + t];
             }
-            double gtot = gsum + sky;
-            if (gtot == 0.0) { bad = 1; continue; }
-            double pv = val[p];
-            double factor = pv / gtot;
-            sums[6 * NG] += logL;
-            sums[6 * NG + 1] += sky * pv / gtot;
-#pragma unroll
-            for (int ii = 0; ii < NG; ii++) {
-                sums[6 * ii] = fma(gi[ii], factor, sums[6 * ii]);
-                if (DO_CEN) {
-                    sums[6 * ii + 1] = fma(tv[ii], factor, sums[6 * ii + 1]);
-                    sums[6 * ii + 2] = fma(tu[ii], factor, sums[6 * ii + 2]);
-                }
-                if (DO_COV) {
-                    sums[6 * ii + 3] = fma(tv2[ii], factor, sums[6 * ii + 3]);
-                    sums[6 * ii + 4] = fma(tuv[ii], factor, sums[6 * ii + 4]);
-                    sums[6 * ii + 5] = fma(tu2[ii], factor, sums[6 * ii + 5]);
-                }
-            }
+            __syncthreads();
         }
-        if (bad) atomicOr(&sh.status, NGX_ST_RANGE_ERROR);   // gtot == 0
-        block_sum<NS>(sums, scratch);
-        if (sh.status) break;       // uniform: status written before the sync
+        if (sh.status) break;       // uniform
+        if (threadIdx.x < nslots) sh.red[threadIdx.x] = acc;
+        __syncthreads();
 
         // ---- M step: gmix_set_from_sums*, thread i < ngauss
         if (threadIdx.x < ngauss) {
             int i = threadIdx.x;
             EMGauss g = sh.gm[i];
-            double p = 0.0, vs = 0.0, us = 0.0, v2s = 0.0, uvs = 0.0,
-                   u2s = 0.0;
-#pragma unroll
-            for (int ii = 0; ii < NG; ii++)
-                if (ii == i) {
-                    p = sums[6 * ii]; vs = sums[6 * ii + 1];
-                    us = sums[6 * ii + 2]; v2s = sums[6 * ii + 3];
-                    uvs = sums[6 * ii + 4]; u2s = sums[6 * ii + 5];
-                }
+            double p = sh.red[6 * i];
             if (VARIANT != NGX_EM_FLUXONLY && p == 0.0) {
                 // numba raises ZeroDivisionError on pinv = 1.0/p
                 atomicOr(&sh.status, NGX_ST_ZERO_DIV);
             } else {
                 double pinv = (VARIANT != NGX_EM_FLUXONLY) ? 1.0 / p : 0.0;
                 if (DO_CEN) {
-                    g.row = vs * pinv;
-                    g.col = us * pinv;
+                    g.row = sh.red[6 * i + 1] * pinv;
+                    g.col = sh.red[6 * i + 2] * pinv;
                 }
                 if (DO_COV) {
-                    double irr = v2s * pinv, irc = uvs * pinv,
-                           icc = u2s * pinv;
+                    double irr = sh.red[6 * i + 3] * pinv;
+                    double irc = sh.red[6 * i + 4] * pinv;
+                    double icc = sh.red[6 * i + 5] * pinv;
                     irr = irr - sh.psf_irr;
                     irc = irc - sh.psf_irc;
                     icc = icc - sh.psf_icc;
@@ -343,9 +365,9 @@ k_em(int n, const double *__restrict__ images,
             }
         }
         __syncthreads();
-        if (!sh.status) em_build_conv(&sh, ngauss, npsf, area);
+        if (!sh.status) em_build_conv(&sh, ngauss, npsf, DO_LOGL);
         if (threadIdx.x == 0 && !sh.status) {
-            if (conf.vary_sky) sh.sky = sums[6 * NG + 1] / sh.npix;
+            if (conf.vary_sky) sh.sky = sh.red[6 * ngauss + 1] / sh.npix;
             int numiter = it + 1;
             sh.numiter = numiter;
             if (VARIANT == NGX_EM_FLUXONLY) {
@@ -357,7 +379,7 @@ k_em(int n, const double *__restrict__ images,
                 }
                 sh.p_last = psum;
             } else {
-                double elogL = sums[6 * NG];
+                double elogL = sh.red[6 * ngauss];
                 if (numiter >= conf.miniter) {
                     if (elogL == 0.0) {
                         atomicOr(&sh.status, NGX_ST_RANGE_ERROR);
@@ -661,34 +683,17 @@ static int launch_em(int n, const double *images, const double *weights,
                      double *pars_out, ngx_em_result *res,
                      cudaStream_t stream) {
     int ntot = nrow * ncol;
-    int threads = pick_threads(ntot);
-    int nconv = ngauss * (npsf > 0 ? npsf : 1);
-    while (threads < nconv) threads *= 2;
-    if (threads > 128)
-        return fail(NGX_ERR_ARG, "ngx_em: too many convolved gaussians%s%s");
-    int nwarps = threads / 32;
-#define NGX_EM_CASE(NGV)                                                     \
-    {                                                                        \
-        size_t smem = sizeof(double)                                         \
-            * (2 * (size_t)ntot + nrow + ncol                                \
-               + (size_t)(6 * NGV + 2) * nwarps);                            \
-        if (smem > (size_t)smem_optin_bytes())                               \
-            return fail(NGX_ERR_ARG, "ngx_em: stamp too large%s%s");         \
-        NGX_CUDA(cudaFuncSetAttribute(                                       \
-            k_em<VARIANT, NGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-            (int)smem));                                                     \
-        k_em<VARIANT, NGV><<<n, threads, smem, stream>>>(                    \
-            n, images, weights, jac, nrow, ncol, guess, ngauss, psf_pars,    \
-            npsf, conf, ignore_zero_weight, pars_out, res);                  \
-    }
-    if (ngauss == 1) NGX_EM_CASE(1)
-    else if (ngauss == 2) NGX_EM_CASE(2)
-    else if (ngauss == 3) NGX_EM_CASE(3)
-    else if (ngauss == 4) NGX_EM_CASE(4)
-    else if (ngauss == 5) NGX_EM_CASE(5)
-    else if (ngauss <= 8) NGX_EM_CASE(8)
-    else NGX_EM_CASE(10)
-#undef NGX_EM_CASE
+    int nslots = 6 * ngauss + 2;
+    size_t smem = sizeof(double)
+        * (2 * (size_t)ntot + nrow + ncol + (size_t)nslots * NGX_EM_TILE);
+    if (smem > (size_t)smem_optin_bytes())
+        return fail(NGX_ERR_ARG, "ngx_em: stamp too large%s%s");
+    NGX_CUDA(cudaFuncSetAttribute(k_em<VARIANT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    k_em<VARIANT><<<n, NGX_EM_TILE, smem, stream>>>(
+        n, images, weights, jac, nrow, ncol, guess, ngauss, psf_pars, npsf,
+        conf, ignore_zero_weight, pars_out, res);
     NGX_LAUNCH_CHECK();
     return NGX_OK;
 }
