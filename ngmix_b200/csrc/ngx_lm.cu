@@ -8,8 +8,14 @@
 //
 // Data movement: the stamp (val, ierr = sqrt(weight); 16 B/pixel) is read
 // from HBM once, lives in shared memory for the whole fit and is never
-// written back; per fit only the ~1.2 KB result record goes out.  The
+// written back; per fit only the 1.2 KB result record goes out.  The
 // reference's 48 B/pixel AoS and the m x n Jacobian never exist.
+//
+// Pixel order: the stamp is held in TILED order, 4 rows x 8 columns per
+// 32-pixel tile, so a warp always owns compact 2-d tiles.  A gaussian whose
+// chi^2 < 25 footprint misses a tile is skipped for the whole warp with one
+// vote; the narrow components of the exp/dev mixtures touch only a few
+// tiles.
 //
 // Work per fit: nfev value passes (16 fp64 instr per gaussian-pixel) and
 // njev derivative passes (30 per gaussian-pixel) over pixels kept in
@@ -29,13 +35,14 @@ namespace ngx {
 #define NGX_CDEF (9.999e9)
 #define NGX_BIGVAL (9999.0e47)
 
-// per-gaussian constants in shared memory (8 doubles) + 16-entry table
-//   0 row, 1 col, 2 a=-dcc/2, 3 b=-drr/2, 4 c2=drc/2, 5 h=Tk/2
-#define GC_STRIDE 8
+// per-gaussian constants in shared memory + 16-entry table pn*exp(i)
+//   0 row, 1 col, 2 a=-dcc/2, 3 b=-drr/2, 4 c2=drc/2, 5 h=Tk/2,
+//   6 c=drc, 7 ha=a/2, 8 hb=b/2, 9 qc=c2/2
+#define GC_STRIDE 10
 
 struct LMArgs {
     int n, model, np, ngauss0, npsf, ngauss, nrow, ncol, ntot;
-    int ignore_zero_weight, analytic, padded;
+    int ignore_zero_weight, analytic, nq, tpr;
     ngx_prior prior;
     ngx_lm_pars lm;
     const double *images, *weights;
@@ -52,18 +59,26 @@ struct LMShared {
     double psf_row, psf_col, psf_ipsum;
     double cur_ssq, cur_rfirst2, cur_num, cur_den;   // at the accepted x
     ngx_jacobian jac;
-    int stamp, npix, first_idx, status, action;
-    int warp_i[32], warp_j[32];
+    int stamp, npix, first_q, status, action, first_eval;
+    int warp_i[32], warp_j[32], warp_k[32];
 };
+
+// tiled index q -> (row, col); tiles are 4 rows x 8 cols, row-band major
+__device__ __forceinline__ void q_to_rowcol(int q, int tpr, int *row,
+                                            int *col) {
+    int tile = q >> 5, w = q & 31;
+    int trow = tile / tpr, tcol = tile - trow * tpr;
+    *row = (trow << 2) + (w >> 3);
+    *col = (tcol << 3) + (w & 7);
+}
 
 // ---------------------------------------------------------------------
 // build the convolved mixture for parameters x: thread k < ngauss owns
 // composed gaussian k = iobj*npsf + ipsf (gmix_convolve_fill's order).
-// Returns nothing; sh->status is OR-ed with range errors.
+// sh->status is OR-ed with range errors.
 __device__ __forceinline__ void build_mixture(const LMArgs &a, LMShared *sh,
                                               const double *x, double *gc,
-                                              double *ptab, double area,
-                                              int with_table) {
+                                              double *ptab, double area) {
     int k = threadIdx.x;
     if (k >= a.ngauss) return;
     ModelHead h = model_head(a.model, x);
@@ -100,25 +115,35 @@ __device__ __forceinline__ void build_mixture(const LMArgs &a, LMShared *sh,
     g[0] = row; g[1] = col;
     g[2] = -0.5 * dcc; g[3] = -0.5 * drr; g[4] = 0.5 * drc;
     g[5] = 0.5 * (irr0 + icc0);
-    if (with_table) {
+    g[6] = drc; g[7] = -0.25 * dcc; g[8] = -0.25 * drr; g[9] = 0.25 * drc;
 #pragma unroll
-        for (int t = 0; t < 16; t++) ptab[16 * k + t] = c_exp_lookup[t] * pn;
-    }
+    for (int t = 0; t < 16; t++) ptab[16 * k + t] = c_exp_lookup[t] * pn;
 }
 
-// pixel coordinates of pixel p from the row/col offset tables
+// pixel coordinates of tiled index q from the row/col offset tables
 __device__ __forceinline__ void coords_of(const LMArgs &a, const LMShared *sh,
                                           const double *rowd,
-                                          const double *cold, int p,
+                                          const double *cold, int q,
                                           double *v, double *u) {
-    if (p < a.ntot) {
-        int row = p / a.ncol, col = p - row * a.ncol;
+    int row, col;
+    q_to_rowcol(q, a.tpr, &row, &col);
+    if (q < a.nq && row < a.nrow && col < a.ncol) {
         double rd = rowd[row], cd = cold[col];
         *v = sh->jac.dvdrow * rd + sh->jac.dvdcol * cd;
         *u = sh->jac.dudrow * rd + sh->jac.dudcol * cd;
     } else {
-        *v = 1.0e300; *u = 1.0e300;
+        *v = 1.0e10; *u = 1.0e10;     // padding: far outside any footprint
     }
+}
+
+// exp part of one evaluation for a lane that may be out of range: the table
+// index is clamped so the shared-memory read stays in bounds and the result
+// is only used under the in-range predicate.
+__device__ __forceinline__ double fexp_tab(double x, const double *tab) {
+    int idx;
+    double f = fexp_reduce(x, &idx);
+    idx = min((unsigned)idx, 15u);
+    return tab[idx] * fexp_poly(f);
 }
 
 // ---------------------------------------------------------------------
@@ -135,7 +160,7 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
                                            double (&sums)[4]) {
     const int T = blockDim.x;
     sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
-    for (int base = 0; base < a.ntot; base += T * CV) {
+    for (int base = 0; base < a.nq; base += T * CV) {
         double v[CV], u[CV], acc[CV];
 #pragma unroll
         for (int c = 0; c < CV; c++) {
@@ -146,35 +171,44 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
         for (int k = 0; k < a.ngauss; k++) {
             const double *g = gc + GC_STRIDE * k;
             const double *tab = ptab + 16 * k;
-            double row = g[0], col = g[1], ga = g[2], gb = g[3];
-            double gcx = 2.0 * g[4];
+            double row = g[0], col = g[1], ga = g[2], gb = g[3], gcx = g[6];
+            double x[CV];
+            bool inr[CV], any = false, anyapod = false;
 #pragma unroll
             for (int c = 0; c < CV; c++) {
                 double dv = v[c] - row;
                 double du = u[c] - col;
                 double t = fma(gcx, du, ga * dv);
-                double x = fma(gb * du, du, dv * t);
-                if (x_in_range(x)) {
-                    int idx;
-                    double f = fexp_reduce(x, &idx);
-                    double pv = fexp_poly(f);
-                    if (x_in_apod(x)) pv *= apod_window_x(x);
-                    acc[c] = fma(tab[idx], pv, acc[c]);
-                }
+                x[c] = fma(gb * du, du, dv * t);
+                inr[c] = x_in_range(x[c]);
+                any |= inr[c];
+                anyapod |= inr[c] && x_in_apod(x[c]);
             }
+            if (!__any_sync(0xffffffffu, any)) continue;   // warp-uniform
+            double e[CV];
+#pragma unroll
+            for (int c = 0; c < CV; c++) e[c] = fexp_tab(x[c], tab);
+            if (__any_sync(0xffffffffu, anyapod)) {
+#pragma unroll
+                for (int c = 0; c < CV; c++)
+                    if (x_in_apod(x[c])) e[c] *= apod_window_x(x[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < CV; c++)
+                if (inr[c]) acc[c] += e[c];
         }
 #pragma unroll
         for (int c = 0; c < CV; c++) {
-            int p = base + c * T + threadIdx.x;
-            if (p < a.ntot) {
-                double ie = ierr[p], d = val[p];
+            int q = base + c * T + threadIdx.x;
+            if (q < a.nq) {
+                double ie = ierr[q], d = val[q];
                 double ivar = ie * ie;
                 double diff = acc[c] - d;
                 double r = diff * ie;
                 sums[0] = fma(r, r, sums[0]);
                 sums[1] = fma(d * acc[c], ivar, sums[1]);
                 sums[2] = fma(acc[c] * acc[c], ivar, sums[2]);
-                if (p == sh->first_idx) sums[3] = r * r;
+                if (q == sh->first_q) sums[3] = r * r;
             }
         }
     }
@@ -183,8 +217,15 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
 // ---------------------------------------------------------------------
 // derivative pass for the simple models (gauss/exp/dev): per pixel the six
 // images of deriv_images, restructured so that the three covariance
-// derivatives share the moment sums MA, MB, MS.  sums =
-// {A (21, packed lower triangle row by row), b (6), sum r^2}
+// derivatives share the moment sums MA, MB, MS.  With
+// hq = -Q delta / 2 the per-gaussian work is
+//   S0 += val            S1 += valc hqv        S2 += valc hqu
+//   MA += h valc ((hqu^2 + b/2) - (hqv^2 + a/2))
+//   MS += h valc ((hqu^2 + b/2) + (hqv^2 + a/2))
+//   MB += h valc (hqv hqu + c/4)
+// sums = {A (21, packed lower triangle row by row), b (6), sum r^2,
+//         s2n_numer, s2n_denom, r_first^2}
+#define NDSUM 31
 template <int CD>
 __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                                            const LMShared *sh,
@@ -194,10 +235,10 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                                            const double *ierr,
                                            const double *rowd,
                                            const double *cold,
-                                           double (&sums)[28]) {
+                                           double (&sums)[NDSUM]) {
     const int T = blockDim.x;
 #pragma unroll
-    for (int i = 0; i < 28; i++) sums[i] = 0.0;
+    for (int i = 0; i < NDSUM; i++) sums[i] = 0.0;
     // d(e1,e2)/d(g1,g2), results.py:988-995
     double g1 = x[2], g2 = x[3], Tpar = x[4], flux = x[5];
     double gsq = g1 * g1 + g2 * g2;
@@ -211,7 +252,7 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
     g1g2_to_e1e2(g1, g2, &e1, &e2);
     double iT = 1.0 / Tpar, iflux = 1.0 / flux;
 
-    for (int base = 0; base < a.ntot; base += T * CD) {
+    for (int base = 0; base < a.nq; base += T * CD) {
         double v[CD], u[CD];
         double S0[CD], S1[CD], S2[CD], MA[CD], MB[CD], MS[CD];
 #pragma unroll
@@ -224,52 +265,72 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
             const double *g = gc + GC_STRIDE * k;
             const double *tab = ptab + 16 * k;
             double row = g[0], col = g[1], ga = g[2], gb = g[3], c2 = g[4];
-            double h = g[5];
-            double ha = 0.5 * ga, hb = 0.5 * gb, qc = 0.5 * c2;
+            double xx[CD], hqv[CD], hqu[CD];
+            bool inr[CD], any = false, anyapod = false;
 #pragma unroll
             for (int c = 0; c < CD; c++) {
                 double dv = v[c] - row;
                 double du = u[c] - col;
-                double hqv = fma(c2, du, ga * dv);     // -qv/2
-                double hqu = fma(gb, du, c2 * dv);     // -qu/2
-                double xx = fma(du, hqu, dv * hqv);    // -chi2/2
-                if (x_in_range(xx)) {
-                    int idx;
-                    double f = fexp_reduce(xx, &idx);
-                    double vl = tab[idx] * fexp_poly(f);
-                    if (!x_in_apod(xx)) {
-                        S0[c] += vl;
-                        S1[c] = fma(vl, hqv, S1[c]);
-                        S2[c] = fma(vl, hqu, S2[c]);
-                        double cv = vl * h;
-                        double ea = fma(hqu, hqu, hb);
-                        double eb = fma(hqv, hqv, ha);
-                        MA[c] = fma(cv, ea - eb, MA[c]);
-                        MS[c] = fma(cv, ea + eb, MS[c]);
-                        MB[c] = fma(cv, fma(hqv, hqu, qc), MB[c]);
-                    } else {
-                        // apodization band: the window slope enters the
-                        // terms that flow through chi^2, derivs_nb.py:104-114
-                        double w = apod_window_x(xx);
-                        double vc = vl * (w - 2.0 * apod_window_deriv_x(xx));
-                        double vw = vl * w;
-                        S0[c] += vw;
-                        S1[c] = fma(vc, hqv, S1[c]);
-                        S2[c] = fma(vc, hqu, S2[c]);
-                        double cv = vc * h, cw = vw * h;
-                        double qu2 = hqu * hqu, qv2 = hqv * hqv;
-                        MA[c] += cv * (qu2 - qv2) + cw * (hb - ha);
-                        MS[c] += cv * (qu2 + qv2) + cw * (hb + ha);
-                        MB[c] += cv * (hqv * hqu) + cw * qc;
+                hqv[c] = fma(c2, du, ga * dv);     // -qv/2
+                hqu[c] = fma(gb, du, c2 * dv);     // -qu/2
+                xx[c] = fma(du, hqu[c], dv * hqv[c]);    // -chi2/2
+                inr[c] = x_in_range(xx[c]);
+                any |= inr[c];
+                anyapod |= inr[c] && x_in_apod(xx[c]);
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;   // warp-uniform
+            double h = g[5], ha = g[7], hb = g[8], qc = g[9];
+            // lanes outside the footprint contribute exact zeros: their
+            // (possibly huge) chi^2 terms must not meet 0 * inf
+#pragma unroll
+            for (int c = 0; c < CD; c++)
+                if (!inr[c]) { hqv[c] = 0.0; hqu[c] = 0.0; }
+            if (!__any_sync(0xffffffffu, anyapod)) {
+#pragma unroll
+                for (int c = 0; c < CD; c++) {
+                    double vl = fexp_tab(xx[c], tab);
+                    if (!inr[c]) vl = 0.0;
+                    S0[c] += vl;
+                    S1[c] = fma(vl, hqv[c], S1[c]);
+                    S2[c] = fma(vl, hqu[c], S2[c]);
+                    double cv = vl * h;
+                    double ea = fma(hqu[c], hqu[c], hb);
+                    double eb = fma(hqv[c], hqv[c], ha);
+                    MA[c] = fma(cv, ea - eb, MA[c]);
+                    MS[c] = fma(cv, ea + eb, MS[c]);
+                    MB[c] = fma(cv, fma(hqv[c], hqu[c], qc), MB[c]);
+                }
+            } else {
+                // some lane sits in the apodization band: the window slope
+                // enters the terms that flow through chi^2,
+                // derivs_nb.py:104-114
+#pragma unroll
+                for (int c = 0; c < CD; c++) {
+                    double vl = fexp_tab(xx[c], tab);
+                    if (!inr[c]) vl = 0.0;
+                    double w = 1.0, wd = 0.0;
+                    if (inr[c] && x_in_apod(xx[c])) {
+                        w = apod_window_x(xx[c]);
+                        wd = apod_window_deriv_x(xx[c]);
                     }
+                    double vc = vl * (w - 2.0 * wd);
+                    double vw = vl * w;
+                    S0[c] += vw;
+                    S1[c] = fma(vc, hqv[c], S1[c]);
+                    S2[c] = fma(vc, hqu[c], S2[c]);
+                    double cv = vc * h, cw = vw * h;
+                    double qu2 = hqu[c] * hqu[c], qv2 = hqv[c] * hqv[c];
+                    MA[c] += cv * (qu2 - qv2) + cw * (hb - ha);
+                    MS[c] += cv * (qu2 + qv2) + cw * (hb + ha);
+                    MB[c] += cv * (hqv[c] * hqu[c]) + cw * qc;
                 }
             }
         }
 #pragma unroll
         for (int c = 0; c < CD; c++) {
-            int p = base + c * T + threadIdx.x;
-            if (p < a.ntot) {
-                double ie = ierr[p];
+            int q = base + c * T + threadIdx.x;
+            if (q < a.nq) {
+                double ie = ierr[q], d = val[q];
                 // undo the factors folded into the accumulators:
                 // qv = -2 hqv; (q q^T - W) terms carry 4, the cross term 8
                 double ma = 4.0 * MA[c], ms = 4.0 * MS[c], mb = 8.0 * MB[c];
@@ -280,19 +341,23 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                 j[3] = (0.5 * (de1dg2 * ma + de2dg2 * mb)) * ie;
                 j[4] = (0.5 * iT * (ms + e1 * ma + e2 * mb)) * ie;
                 j[5] = S0[c] * (ie * iflux);
-                double r = (S0[c] - val[p]) * ie;
-                int q = 0;
+                double r = (S0[c] - d) * ie;
+                int qq = 0;
 #pragma unroll
                 for (int aa = 0; aa < 6; aa++)
 #pragma unroll
                     for (int bb = 0; bb <= aa; bb++) {
-                        sums[q] = fma(j[aa], j[bb], sums[q]);
-                        q++;
+                        sums[qq] = fma(j[aa], j[bb], sums[qq]);
+                        qq++;
                     }
 #pragma unroll
                 for (int aa = 0; aa < 6; aa++)
                     sums[21 + aa] = fma(j[aa], r, sums[21 + aa]);
                 sums[27] = fma(r, r, sums[27]);
+                double ivar = ie * ie;
+                sums[28] = fma(d * S0[c], ivar, sums[28]);
+                sums[29] = fma(S0[c] * S0[c], ivar, sums[29]);
+                if (q == sh->first_q) sums[30] = r * r;
             }
         }
     }
@@ -315,10 +380,10 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
     const int T = blockDim.x;
     const int np = a.np;
     for (int i = 0; i < nsums; i++) sums[i] = 0.0;
-    for (int base = 0; base < a.ntot; base += T) {
-        int p = base + threadIdx.x;
+    for (int base = 0; base < a.nq; base += T) {
+        int q = base + threadIdx.x;
         double v, u;
-        coords_of(a, sh, rowd, cold, p, &v, &u);
+        coords_of(a, sh, rowd, cold, q, &v, &u);
         double m[NPMAX + 1];
         for (int s = 0; s <= np; s++) {
             const double *gc = gcs + (size_t)s * a.ngauss * GC_STRIDE;
@@ -328,35 +393,33 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
                 const double *g = gc + GC_STRIDE * k;
                 double dv = v - g[0];
                 double du = u - g[1];
-                double t = fma(2.0 * g[4], du, g[2] * dv);
+                double t = fma(g[6], du, g[2] * dv);
                 double x = fma(g[3] * du, du, dv * t);
-                if (x_in_range(x)) {
-                    int idx;
-                    double f = fexp_reduce(x, &idx);
-                    double pv = fexp_poly(f);
-                    if (x_in_apod(x)) pv *= apod_window_x(x);
-                    acc = fma(ptab[16 * k + idx], pv, acc);
-                }
+                bool inr = x_in_range(x);
+                if (!__any_sync(0xffffffffu, inr)) continue;
+                double e = fexp_tab(x, ptab + 16 * k);
+                if (inr && x_in_apod(x)) e *= apod_window_x(x);
+                if (inr) acc += e;
             }
             m[s] = acc;
         }
-        if (p < a.ntot) {
-            double ie = ierr[p];
-            double r = (m[0] - val[p]) * ie;
+        if (q < a.nq) {
+            double ie = ierr[q];
+            double r = (m[0] - val[q]) * ie;
             double j[NPMAX];
             for (int s = 0; s < np; s++) {
-                double rs = (m[s + 1] - val[p]) * ie;
+                double rs = (m[s + 1] - val[q]) * ie;
                 j[s] = (rs - r) / hs[s];
             }
-            int q = 0;
+            int qq = 0;
             for (int aa = 0; aa < np; aa++)
                 for (int bb = 0; bb <= aa; bb++) {
-                    sums[q] = fma(j[aa], j[bb], sums[q]);
-                    q++;
+                    sums[qq] = fma(j[aa], j[bb], sums[qq]);
+                    qq++;
                 }
             for (int aa = 0; aa < np; aa++)
-                sums[q + aa] = fma(j[aa], r, sums[q + aa]);
-            sums[q + np] = fma(r, r, sums[q + np]);
+                sums[qq + aa] = fma(j[aa], r, sums[qq + aa]);
+            sums[qq + np] = fma(r, r, sums[qq + np]);
         }
     }
 }
@@ -381,7 +444,7 @@ __device__ __forceinline__ void block_sum_n(double *v, int nv,
 
 // ---------------------------------------------------------------------
 // prior contributions, thread 0
-__device__ inline double prior_fnorm2(const LMArgs &a, const double *x,
+__device__ __noinline__ double prior_fnorm2(const LMArgs &a, const double *x,
                                       int *status, int *ninf) {
     *ninf = 0;
     if (!a.prior.present) return 0.0;
@@ -400,7 +463,7 @@ __device__ inline double prior_fnorm2(const LMArgs &a, const double *x,
 }
 
 // the epilogue: run_leastsq (leastsqbound.py:70-126) + set_fit_result
-__device__ inline void lm_finish(const LMArgs &a, LMShared *sh,
+__device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
                                  ngx_lm_result *out) {
     LMState *s = &sh->st;
     int np = a.np;
@@ -491,10 +554,79 @@ __device__ inline void lm_finish(const LMArgs &a, LMShared *sh,
 }
 
 // ---------------------------------------------------------------------
+// ---------------------------------------------------------------------
+// assemble J^T J, J^T f from the pixel sums and the prior rows and feed the
+// state machine (thread 0).  packed = lower triangle row by row, then b.
+__device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
+                                           const double *sums, int status,
+                                           int analytic, const double *hs) {
+    double A[LM_MAXP * LM_MAXP], b[LM_MAXP];
+    const int np = a.np;
+    const double *x = sh->st.x;
+    int nr = prior_nrows(a.model, a.prior);
+    double f0[NGX_MAX_PRIOR_ROWS];
+    double jp[NGX_MAX_PRIOR_ROWS * LM_MAXP];
+    if (!status && nr > 0) {
+        if (prior_fill_fdiff(a.model, a.prior, x, f0)) {
+            status = 1;
+        } else if (analytic) {
+            if (prior_jacobian(a.model, a.prior, x, np, f0, jp)) status = 1;
+        } else {
+            // the prior rows are part of fvec: MINPACK's own forward
+            // difference with its step hs
+            double xp[LM_MAXP], fs[NGX_MAX_PRIOR_ROWS];
+            for (int s = 0; s < np && !status; s++) {
+                for (int i = 0; i < np; i++) xp[i] = x[i];
+                xp[s] = x[s] + hs[s];
+                if (prior_fill_fdiff(a.model, a.prior, xp, fs)) {
+                    status = 1;
+                    break;
+                }
+                for (int r = 0; r < nr; r++)
+                    jp[r * np + s] = (fs[r] - f0[r]) / hs[s];
+            }
+        }
+    }
+    int q = 0;
+    for (int aa = 0; aa < np; aa++)
+        for (int bb = 0; bb <= aa; bb++) {
+            double sv = status ? 0.0 : sums[q];
+            if (!status)
+                for (int r = 0; r < nr; r++)
+                    sv += jp[r * np + aa] * jp[r * np + bb];
+            A[aa + LM_MAXP * bb] = sv;
+            A[bb + LM_MAXP * aa] = sv;
+            q++;
+        }
+    for (int aa = 0; aa < np; aa++) {
+        double sv = status ? 0.0 : sums[q + aa];
+        if (!status)
+            for (int r = 0; r < nr; r++)
+                if (isfinite(f0[r])) sv += jp[r * np + aa] * f0[r];
+        b[aa] = sv;
+    }
+    lm_feed_j(&sh->st, A, b, analytic ? 0 : np);
+}
+
+// feed |f| of a residual pass (thread 0); returns 1 if the point is adopted
+__device__ __noinline__ int feed_residual(const LMArgs &a, LMShared *sh,
+                                          const double *xeval, double ssq,
+                                          int status) {
+    int ninf = 0;
+    double ps = prior_fnorm2(a, xeval, &status, &ninf);
+    double fnorm;
+    if (status) fnorm = nan("");
+    else if (ninf == 1) fnorm = INFINITY;
+    else if (ninf > 1) fnorm = nan("");
+    else fnorm = sqrt(ssq + ps);
+    return lm_feed_f(&sh->st, fnorm);
+}
+
+// ---------------------------------------------------------------------
 // MODE 0: analytic Jacobian (gauss/exp/dev), np = 6
 // MODE 1: forward differences (any model), np <= 8
 template <int MODE, int CV, int CD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 4)
 k_lm_fit(LMArgs a) {
     extern __shared__ double smem_d[];
     __shared__ LMShared sh;
@@ -503,10 +635,10 @@ k_lm_fit(LMArgs a) {
     const int nmix = (MODE == 0) ? 1 : (a.np + 1);
     // dynamic shared memory carve-up
     double *ptab = smem_d;                                   // nmix*ngauss*16
-    double *gc = ptab + (size_t)nmix * a.ngauss * 16;        // nmix*ngauss*8
-    double *val = gc + (size_t)nmix * a.ngauss * GC_STRIDE;  // padded
-    double *ierr = val + a.padded;
-    double *rowd = ierr + a.padded;
+    double *gc = ptab + (size_t)nmix * a.ngauss * 16;        // nmix*ngauss*GC
+    double *val = gc + (size_t)nmix * a.ngauss * GC_STRIDE;  // nq
+    double *ierr = val + a.nq;
+    double *rowd = ierr + a.nq;
     double *cold = rowd + a.nrow;
     double *scratch = cold + a.ncol;                         // 48 * nwarps
     double *hs = scratch + 48 * nwarps;                      // 8
@@ -518,24 +650,27 @@ k_lm_fit(LMArgs a) {
         const int stamp = sh.stamp;
         if (stamp >= a.n) break;
 
-        // ---- stage the stamp
+        // ---- stage the stamp in tiled order
         const double *im = a.images + (size_t)stamp * a.ntot;
         const double *wt = a.weights + (size_t)stamp * a.ntot;
-        int cnt = 0, first = a.ntot;
-        for (int p = threadIdx.x; p < a.padded; p += T) {
+        int cnt = 0, first = a.ntot, firstq = 0;
+        for (int q = threadIdx.x; q < a.nq; q += T) {
+            int row, col;
+            q_to_rowcol(q, a.tpr, &row, &col);
             double vv = 0.0, ie = 0.0;
-            if (p < a.ntot) {
+            if (row < a.nrow && col < a.ncol) {
+                int p = row * a.ncol + col;
                 double w = wt[p];
                 bool valid = !(a.ignore_zero_weight && w <= 0.0);
                 if (valid) {
                     vv = im[p];
                     ie = sqrt(w < 0.0 ? 0.0 : w);
                     cnt++;
-                    if (p < first) first = p;
+                    if (p < first) { first = p; firstq = q; }
                 }
             }
-            val[p] = vv;
-            ierr[p] = ie;
+            val[q] = vv;
+            ierr[q] = ie;
         }
         if (threadIdx.x == 0) {
             sh.jac = a.jac[stamp];
@@ -548,9 +683,15 @@ k_lm_fit(LMArgs a) {
             int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             for (int o = 16; o > 0; o >>= 1) {
                 cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-                first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+                int of = __shfl_xor_sync(0xffffffffu, first, o);
+                int oq = __shfl_xor_sync(0xffffffffu, firstq, o);
+                if (of < first) { first = of; firstq = oq; }
             }
-            if (lane == 0) { sh.warp_i[warp] = cnt; sh.warp_j[warp] = first; }
+            if (lane == 0) {
+                sh.warp_i[warp] = cnt;
+                sh.warp_j[warp] = first;
+                sh.warp_k[warp] = firstq;
+            }
         }
         __syncthreads();
         for (int p = threadIdx.x; p < a.nrow; p += T)
@@ -558,13 +699,13 @@ k_lm_fit(LMArgs a) {
         for (int p = threadIdx.x; p < a.ncol; p += T)
             cold[p] = p - sh.jac.col0;
         if (threadIdx.x == 0) {
-            int c = 0, f = a.ntot;
+            int c = 0, f = a.ntot, fq = -1;
             for (int w = 0; w < nwarps; w++) {
                 c += sh.warp_i[w];
-                f = min(f, sh.warp_j[w]);
+                if (sh.warp_j[w] < f) { f = sh.warp_j[w]; fq = sh.warp_k[w]; }
             }
             sh.npix = c;
-            sh.first_idx = f;
+            sh.first_q = fq;
             // psf centroid and flux, gmix_get_cen :108-130
             double prow = 0.0, pcol = 0.0, psum = 0.0;
             for (int k = 0; k < a.npsf; k++) {
@@ -581,6 +722,7 @@ k_lm_fit(LMArgs a) {
             lm_init(&sh.st, a.np, a.guess + (size_t)stamp * a.np,
                     a.lm.maxfev, a.lm.ftol, a.lm.xtol);
             sh.action = sh.st.action;
+            sh.first_eval = 1;
             for (int i = 0; i < a.np; i++) sh.xeval[i] = sh.st.xtrial[i];
             sh.cur_ssq = sh.cur_rfirst2 = sh.cur_num = sh.cur_den = 0.0;
         }
@@ -605,10 +747,49 @@ k_lm_fit(LMArgs a) {
         // ---- the fit
         while (sh.action != LM_ACT_DONE) {
             const int action = sh.action;
+            const int first_eval = sh.first_eval;
+            __syncthreads();
             if (threadIdx.x == 0) sh.status = 0;
             __syncthreads();
-            if (action == LM_ACT_EVAL_F) {
-                build_mixture(a, &sh, sh.xeval, gc, ptab, area, 1);
+            if (MODE == 0 && (first_eval || action == LM_ACT_EVAL_J)) {
+                // derivative pass at the accepted point.  The very first
+                // evaluation is fused: the same pass yields f(x0) and J(x0)
+                // (the reference evaluates them separately; nfev and njev
+                // count as the reference's do).
+                build_mixture(a, &sh, sh.st.x, gc, ptab, area);
+                __syncthreads();
+                const int mix_status = sh.status;
+                double sums[NDSUM];
+#pragma unroll
+                for (int i = 0; i < NDSUM; i++) sums[i] = 0.0;
+                // calc_jacobian raises for T == 0 or flux == 0
+                int jstatus = mix_status
+                    || sh.st.x[4] == 0.0 || sh.st.x[5] == 0.0;
+                if (!jstatus)
+                    deriv_pass<CD>(a, &sh, sh.st.x, gc, ptab, val, ierr, rowd,
+                                   cold, sums);
+                else if (first_eval && !mix_status) {
+                    // f(x0) is evaluable although the Jacobian is not
+                    double s4[4];
+                    value_pass<CV>(a, &sh, gc, ptab, val, ierr, rowd, cold,
+                                   s4);
+                    sums[27] = s4[0]; sums[28] = s4[1]; sums[29] = s4[2];
+                    sums[30] = s4[3];
+                }
+                block_sum<NDSUM>(sums, scratch);
+                if (threadIdx.x == 0) {
+                    if (first_eval) {
+                        feed_residual(a, &sh, sh.st.x, sums[27], mix_status);
+                        sh.cur_ssq = sums[27];
+                        sh.cur_num = sums[28];
+                        sh.cur_den = sums[29];
+                        sh.cur_rfirst2 = sums[30];
+                        sh.first_eval = 0;
+                    }
+                    feed_jacobian(a, &sh, sums, jstatus, 1, hs);
+                }
+            } else if (action == LM_ACT_EVAL_F) {
+                build_mixture(a, &sh, sh.xeval, gc, ptab, area);
                 __syncthreads();
                 double sums[4] = {0, 0, 0, 0};
                 if (!sh.status)
@@ -616,70 +797,15 @@ k_lm_fit(LMArgs a) {
                                    sums);
                 block_sum<4>(sums, scratch);
                 if (threadIdx.x == 0) {
-                    int status = sh.status, ninf = 0;
-                    double ps = prior_fnorm2(a, sh.xeval, &status, &ninf);
-                    double fnorm;
-                    if (status) fnorm = nan("");
-                    else if (ninf == 1) fnorm = INFINITY;
-                    else if (ninf > 1) fnorm = nan("");
-                    else fnorm = sqrt(sums[0] + ps);
-                    int acc = lm_feed_f(&sh.st, fnorm);
+                    int acc = feed_residual(a, &sh, sh.xeval, sums[0],
+                                            sh.status);
                     if (acc) {
                         sh.cur_ssq = sums[0];
                         sh.cur_num = sums[1];
                         sh.cur_den = sums[2];
                         sh.cur_rfirst2 = sums[3];
                     }
-                }
-            } else if (MODE == 0) {
-                // analytic Jacobian at the accepted point
-                if (threadIdx.x == 0) {
-                    // calc_jacobian raises for T == 0 or flux == 0
-                    if (sh.st.x[4] == 0.0 || sh.st.x[5] == 0.0) sh.status = 1;
-                }
-                build_mixture(a, &sh, sh.st.x, gc, ptab, area, 1);
-                __syncthreads();
-                double sums[28];
-#pragma unroll
-                for (int i = 0; i < 28; i++) sums[i] = 0.0;
-                if (!sh.status)
-                    deriv_pass<CD>(a, &sh, sh.st.x, gc, ptab, val, ierr, rowd,
-                                   cold, sums);
-                block_sum<28>(sums, scratch);
-                if (threadIdx.x == 0) {
-                    double A[LM_MAXP * LM_MAXP], b[LM_MAXP];
-                    int np = a.np;
-                    int status = sh.status;
-                    double f0[NGX_MAX_PRIOR_ROWS];
-                    double jp[NGX_MAX_PRIOR_ROWS * LM_MAXP];
-                    int nr = prior_nrows(a.model, a.prior);
-                    if (!status && nr > 0) {
-                        if (prior_fill_fdiff(a.model, a.prior, sh.st.x, f0))
-                            status = 1;
-                        else if (prior_jacobian(a.model, a.prior, sh.st.x, np,
-                                                f0, jp))
-                            status = 1;
-                    }
-                    int q = 0;
-                    for (int aa = 0; aa < np; aa++)
-                        for (int bb = 0; bb <= aa; bb++) {
-                            double sv = status ? 0.0 : sums[q];
-                            if (!status)
-                                for (int r = 0; r < nr; r++)
-                                    sv += jp[r * np + aa] * jp[r * np + bb];
-                            A[aa + LM_MAXP * bb] = sv;
-                            A[bb + LM_MAXP * aa] = sv;
-                            q++;
-                        }
-                    for (int aa = 0; aa < np; aa++) {
-                        double sv = status ? 0.0 : sums[21 + aa];
-                        if (!status)
-                            for (int r = 0; r < nr; r++)
-                                if (isfinite(f0[r]))
-                                    sv += jp[r * np + aa] * f0[r];
-                        b[aa] = sv;
-                    }
-                    lm_feed_j(&sh.st, A, b, 0);
+                    sh.first_eval = 0;
                 }
             } else {
                 // forward differences: base + np perturbed mixtures
@@ -697,17 +823,14 @@ k_lm_fit(LMArgs a) {
                 for (int s = 0; s <= np; s++) {
                     if (threadIdx.x == 0) {
                         for (int i = 0; i < np; i++) sh.xeval[i] = sh.st.x[i];
-                        if (s > 0) {
-                            // x[j] = temp + h (fdjac2); h is then the
-                            // REPRESENTED difference only through hs
+                        if (s > 0)
                             sh.xeval[s - 1] = sh.st.x[s - 1] + hs[s - 1];
-                        }
                         sh.status = 0;
                     }
                     __syncthreads();
                     build_mixture(a, &sh, sh.xeval,
                                   gc + (size_t)s * a.ngauss * GC_STRIDE,
-                                  ptab + (size_t)s * a.ngauss * 16, area, 1);
+                                  ptab + (size_t)s * a.ngauss * 16, area);
                     __syncthreads();
                     bad_any |= sh.status;
                     __syncthreads();
@@ -719,49 +842,8 @@ k_lm_fit(LMArgs a) {
                     fd_pass<LM_MAXP>(a, &sh, hs, gc, ptab, val, ierr, rowd,
                                      cold, sums, nsums);
                 block_sum_n(sums, nsums, scratch);
-                if (threadIdx.x == 0) {
-                    double A[LM_MAXP * LM_MAXP], b[LM_MAXP];
-                    int status = bad_any;
-                    int nr = prior_nrows(a.model, a.prior);
-                    double f0[NGX_MAX_PRIOR_ROWS];
-                    double jp[NGX_MAX_PRIOR_ROWS * LM_MAXP];
-                    if (!status && nr > 0) {
-                        // the prior rows are part of fvec: same forward
-                        // difference with the MINPACK step
-                        if (prior_fill_fdiff(a.model, a.prior, sh.st.x, f0))
-                            status = 1;
-                        double xp[LM_MAXP], fs[NGX_MAX_PRIOR_ROWS];
-                        for (int s = 0; s < np && !status; s++) {
-                            for (int i = 0; i < np; i++) xp[i] = sh.st.x[i];
-                            xp[s] = sh.st.x[s] + hs[s];
-                            if (prior_fill_fdiff(a.model, a.prior, xp, fs)) {
-                                status = 1;
-                                break;
-                            }
-                            for (int r = 0; r < nr; r++)
-                                jp[r * np + s] = (fs[r] - f0[r]) / hs[s];
-                        }
-                    }
-                    int q = 0;
-                    for (int aa = 0; aa < np; aa++)
-                        for (int bb = 0; bb <= aa; bb++) {
-                            double sv = status ? 0.0 : sums[q];
-                            if (!status)
-                                for (int r = 0; r < nr; r++)
-                                    sv += jp[r * np + aa] * jp[r * np + bb];
-                            A[aa + LM_MAXP * bb] = sv;
-                            A[bb + LM_MAXP * aa] = sv;
-                            q++;
-                        }
-                    for (int aa = 0; aa < np; aa++) {
-                        double sv = status ? 0.0 : sums[q + aa];
-                        if (!status)
-                            for (int r = 0; r < nr; r++)
-                                sv += jp[r * np + aa] * f0[r];
-                        b[aa] = sv;
-                    }
-                    lm_feed_j(&sh.st, A, b, np);
-                }
+                if (threadIdx.x == 0)
+                    feed_jacobian(a, &sh, sums, bad_any, 0, hs);
             }
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -858,13 +940,14 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     int threads = 128;
     if (a.ntot <= 1024) threads = 64;
     NGX_REQUIRE(threads >= a.ngauss && threads >= 6 * npsf);
-    const int CV = 3, CD = 3;
-    int tile = threads * CV * CD;      // padded to both chunk sizes
-    a.padded = ((a.ntot + tile - 1) / tile) * tile;
+    const int CV = 3, CD = 2;
+    // tiled pixel order: 4 x 8 tiles, one per warp
+    a.tpr = (ncol + 7) / 8;
+    a.nq = 32 * a.tpr * ((nrow + 3) / 4);
     int nmix = analytic ? 1 : np + 1;
     int nwarps = threads / 32;
     size_t smem = sizeof(double)
-        * ((size_t)nmix * a.ngauss * (16 + GC_STRIDE) + 2 * (size_t)a.padded
+        * ((size_t)nmix * a.ngauss * (16 + GC_STRIDE) + 2 * (size_t)a.nq
            + nrow + ncol + 48 * nwarps + 8);
     if (analytic)
         return config_and_launch(k_lm_fit<0, CV, CD>, a, threads, smem,
