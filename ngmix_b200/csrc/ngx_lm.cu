@@ -76,9 +76,9 @@ __device__ __forceinline__ void q_to_rowcol(int q, int tpr, int *row,
 // build the convolved mixture for parameters x: thread k < ngauss owns
 // composed gaussian k = iobj*npsf + ipsf (gmix_convolve_fill's order).
 // sh->status is OR-ed with range errors.
-__device__ __forceinline__ void build_mixture(const LMArgs &a, LMShared *sh,
-                                              const double *x, double *gc,
-                                              double *ptab, double area) {
+__device__ __noinline__ void build_mixture(const LMArgs &a, LMShared *sh,
+                                           const double *x, double *gc,
+                                           double *ptab, double area) {
     int k = threadIdx.x;
     if (k >= a.ngauss) return;
     ModelHead h = model_head(a.model, x);
@@ -168,6 +168,7 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
                       &u[c]);
             acc[c] = 0.0;
         }
+#pragma unroll 1
         for (int k = 0; k < a.ngauss; k++) {
             const double *g = gc + GC_STRIDE * k;
             const double *tab = ptab + 16 * k;
@@ -261,6 +262,7 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                       &u[c]);
             S0[c] = S1[c] = S2[c] = MA[c] = MB[c] = MS[c] = 0.0;
         }
+#pragma unroll 1
         for (int k = 0; k < a.ngauss; k++) {
             const double *g = gc + GC_STRIDE * k;
             const double *tab = ptab + 16 * k;
@@ -751,7 +753,11 @@ k_lm_fit(LMArgs a) {
             __syncthreads();
             if (threadIdx.x == 0) sh.status = 0;
             __syncthreads();
-            if (MODE == 0 && (first_eval || action == LM_ACT_EVAL_J)) {
+            // fuse f(x0) into the first derivative pass unless the Jacobian
+            // is not evaluable there (T == 0 or flux == 0)
+            const bool fuse = first_eval && sh.st.x[4] != 0.0
+                && sh.st.x[5] != 0.0;
+            if (MODE == 0 && (fuse || action == LM_ACT_EVAL_J)) {
                 // derivative pass at the accepted point.  The very first
                 // evaluation is fused: the same pass yields f(x0) and J(x0)
                 // (the reference evaluates them separately; nfev and njev
@@ -768,17 +774,9 @@ k_lm_fit(LMArgs a) {
                 if (!jstatus)
                     deriv_pass<CD>(a, &sh, sh.st.x, gc, ptab, val, ierr, rowd,
                                    cold, sums);
-                else if (first_eval && !mix_status) {
-                    // f(x0) is evaluable although the Jacobian is not
-                    double s4[4];
-                    value_pass<CV>(a, &sh, gc, ptab, val, ierr, rowd, cold,
-                                   s4);
-                    sums[27] = s4[0]; sums[28] = s4[1]; sums[29] = s4[2];
-                    sums[30] = s4[3];
-                }
                 block_sum<NDSUM>(sums, scratch);
                 if (threadIdx.x == 0) {
-                    if (first_eval) {
+                    if (fuse) {
                         feed_residual(a, &sh, sh.st.x, sums[27], mix_status);
                         sh.cur_ssq = sums[27];
                         sh.cur_num = sums[28];

@@ -17,8 +17,13 @@
 
 #ifdef __CUDACC__
 #define NGX_HD __host__ __device__
+// the solver runs on one thread per CTA: keep ONE compact, non-unrolled copy
+// of every routine so it does not evict the pixel loops from the 32 KB
+// instruction cache (ncu: 50% of its stall samples were no_instruction)
+#define NGX_NI __noinline__
 #else
 #define NGX_HD
+#define NGX_NI
 #endif
 
 namespace ngx {
@@ -54,6 +59,7 @@ NGX_HD inline double lm_min(double a, double b) { return a <= b ? a : b; }
 // plain sum of squares rounds within an ulp or two of it.
 NGX_HD inline double lm_enorm(int n, const double *x) {
     double s = 0.0;
+#pragma unroll 1
     for (int i = 0; i < n; i++) s += x[i] * x[i];
     return sqrt(s);
 }
@@ -62,21 +68,26 @@ NGX_HD inline double lm_enorm(int n, const double *x) {
 // LM_MAXP).  Pivot rule of qrfac: at step j take the first column k >= j with
 // the largest remaining norm.  A non-positive pivot leaves a zero row (rank
 // deficiency), as qrfac leaves a zero diagonal.
-NGX_HD inline void lm_pchol(int n, const double *A, double *R, int *ipvt,
+NGX_HD NGX_NI static void lm_pchol(int n, const double *A, double *R, int *ipvt,
                             double *acnorm) {
     double d[LM_MAXP];
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         ipvt[j] = j;
         d[j] = A[j + LM_MAXP * j];
         acnorm[j] = sqrt(d[j] > 0.0 ? d[j] : 0.0);
+#pragma unroll 1
         for (int i = 0; i < n; i++) R[i + LM_MAXP * j] = 0.0;
     }
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         int kmax = j;
+#pragma unroll 1
         for (int k = j; k < n; k++)
             if (d[k] > d[kmax]) kmax = k;
         if (kmax != j) {
             // swap columns j and kmax of R (rows < j), d and ipvt
+#pragma unroll 1
             for (int i = 0; i < j; i++) {
                 double t = R[i + LM_MAXP * j];
                 R[i + LM_MAXP * j] = R[i + LM_MAXP * kmax];
@@ -88,17 +99,22 @@ NGX_HD inline void lm_pchol(int n, const double *A, double *R, int *ipvt,
         double piv = d[j];
         if (!(piv > 0.0)) {
             // remaining columns are numerically dependent
+#pragma unroll 1
             for (int k = j; k < n; k++) R[j + LM_MAXP * k] = 0.0;
+#pragma unroll 1
             for (int jj = j; jj < n; jj++)
+#pragma unroll 1
                 for (int k = jj; k < n; k++) R[jj + LM_MAXP * k] = 0.0;
             return;
         }
         double rjj = sqrt(piv);
         R[j + LM_MAXP * j] = rjj;
         int pj = ipvt[j];
+#pragma unroll 1
         for (int k = j + 1; k < n; k++) {
             int pk = ipvt[k];
             double s = A[pj + LM_MAXP * pk];
+#pragma unroll 1
             for (int i = 0; i < j; i++)
                 s -= R[i + LM_MAXP * j] * R[i + LM_MAXP * k];
             double rjk = s / rjj;
@@ -109,21 +125,26 @@ NGX_HD inline void lm_pchol(int n, const double *A, double *R, int *ipvt,
 }
 
 // MINPACK qrsolv on an n x n R (column major, ld LM_MAXP)
-NGX_HD inline void lm_qrsolv(int n, double *r, const int *ipvt,
+NGX_HD NGX_NI static void lm_qrsolv(int n, double *r, const int *ipvt,
                              const double *diag, const double *qtb, double *x,
                              double *sdiag, double *wa) {
     const int ld = LM_MAXP;
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
+#pragma unroll 1
         for (int i = j; i < n; i++) r[i + ld * j] = r[j + ld * i];
         x[j] = r[j + ld * j];
         wa[j] = qtb[j];
     }
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         int l = ipvt[j];
         if (diag[l] != 0.0) {
+#pragma unroll 1
             for (int k = j; k < n; k++) sdiag[k] = 0.0;
             sdiag[j] = diag[l];
             double qtbpj = 0.0;
+#pragma unroll 1
             for (int k = j; k < n; k++) {
                 if (sdiag[k] == 0.0) continue;
                 double c, s;
@@ -141,6 +162,7 @@ NGX_HD inline void lm_qrsolv(int n, double *r, const int *ipvt,
                 double temp = c * wa[k] + s * qtbpj;
                 qtbpj = -s * wa[k] + c * qtbpj;
                 wa[k] = temp;
+#pragma unroll 1
                 for (int i = k + 1; i < n; i++) {
                     temp = c * r[i + ld * k] + s * sdiag[i];
                     sdiag[i] = -s * r[i + ld * k] + c * sdiag[i];
@@ -152,40 +174,49 @@ NGX_HD inline void lm_qrsolv(int n, double *r, const int *ipvt,
         r[j + ld * j] = x[j];
     }
     int nsing = n;
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         if (sdiag[j] == 0.0 && nsing == n) nsing = j;
         if (nsing < n) wa[j] = 0.0;
     }
+#pragma unroll 1
     for (int k = 1; k <= nsing; k++) {
         int j = nsing - k;
         double sum = 0.0;
+#pragma unroll 1
         for (int i = j + 1; i < nsing; i++) sum += r[i + ld * j] * wa[i];
         wa[j] = (wa[j] - sum) / sdiag[j];
     }
+#pragma unroll 1
     for (int j = 0; j < n; j++) x[ipvt[j]] = wa[j];
 }
 
 // MINPACK lmpar
-NGX_HD inline void lm_lmpar(int n, double *r, const int *ipvt,
+NGX_HD NGX_NI static void lm_lmpar(int n, double *r, const int *ipvt,
                             const double *diag, const double *qtb,
                             double delta, double *par, double *x) {
     const int ld = LM_MAXP;
     double sdiag[LM_MAXP], wa1[LM_MAXP], wa2[LM_MAXP];
     int nsing = n;
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         wa1[j] = qtb[j];
         if (r[j + ld * j] == 0.0 && nsing == n) nsing = j;
         if (nsing < n) wa1[j] = 0.0;
     }
+#pragma unroll 1
     for (int k = 1; k <= nsing; k++) {
         int j = nsing - k;
         wa1[j] /= r[j + ld * j];
         double temp = wa1[j];
+#pragma unroll 1
         for (int i = 0; i < j; i++) wa1[i] -= r[i + ld * j] * temp;
     }
+#pragma unroll 1
     for (int j = 0; j < n; j++) x[ipvt[j]] = wa1[j];
 
     int iter = 0;
+#pragma unroll 1
     for (int j = 0; j < n; j++) wa2[j] = diag[j] * x[j];
     double dxnorm = lm_enorm(n, wa2);
     double fp = dxnorm - delta;
@@ -195,20 +226,25 @@ NGX_HD inline void lm_lmpar(int n, double *r, const int *ipvt,
     }
     double parl = 0.0;
     if (nsing >= n) {
+#pragma unroll 1
         for (int j = 0; j < n; j++) {
             int l = ipvt[j];
             wa1[j] = diag[l] * (wa2[l] / dxnorm);
         }
+#pragma unroll 1
         for (int j = 0; j < n; j++) {
             double sum = 0.0;
+#pragma unroll 1
             for (int i = 0; i < j; i++) sum += r[i + ld * j] * wa1[i];
             wa1[j] = (wa1[j] - sum) / r[j + ld * j];
         }
         double temp = lm_enorm(n, wa1);
         parl = ((fp / delta) / temp) / temp;
     }
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         double sum = 0.0;
+#pragma unroll 1
         for (int i = 0; i <= j; i++) sum += r[i + ld * j] * qtb[i];
         wa1[j] = sum / diag[ipvt[j]];
     }
@@ -218,12 +254,15 @@ NGX_HD inline void lm_lmpar(int n, double *r, const int *ipvt,
     *par = lm_max(*par, parl);
     *par = lm_min(*par, paru);
     if (*par == 0.0) *par = gnorm / dxnorm;
+#pragma unroll 1
     for (;;) {
         iter++;
         if (*par == 0.0) *par = lm_max(LM_DWARF, 0.001 * paru);
         double temp = sqrt(*par);
+#pragma unroll 1
         for (int j = 0; j < n; j++) wa1[j] = temp * diag[j];
         lm_qrsolv(n, r, ipvt, wa1, qtb, x, sdiag, wa2);
+#pragma unroll 1
         for (int j = 0; j < n; j++) wa2[j] = diag[j] * x[j];
         dxnorm = lm_enorm(n, wa2);
         temp = fp;
@@ -231,13 +270,16 @@ NGX_HD inline void lm_lmpar(int n, double *r, const int *ipvt,
         if (fabs(fp) <= 0.1 * delta
             || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10)
             break;
+#pragma unroll 1
         for (int j = 0; j < n; j++) {
             int l = ipvt[j];
             wa1[j] = diag[l] * (wa2[l] / dxnorm);
         }
+#pragma unroll 1
         for (int j = 0; j < n; j++) {
             wa1[j] /= sdiag[j];
             temp = wa1[j];
+#pragma unroll 1
             for (int i = j + 1; i < n; i++) wa1[i] -= r[i + ld * j] * temp;
         }
         temp = lm_enorm(n, wa1);
@@ -249,7 +291,7 @@ NGX_HD inline void lm_lmpar(int n, double *r, const int *ipvt,
 }
 
 // ---------------------------------------------------------------------
-NGX_HD inline void lm_init(LMState *s, int n, const double *x0, int maxfev,
+NGX_HD NGX_NI static void lm_init(LMState *s, int n, const double *x0, int maxfev,
                            double ftol, double xtol) {
     s->n = n;
     s->maxfev = maxfev;
@@ -268,6 +310,7 @@ NGX_HD inline void lm_init(LMState *s, int n, const double *x0, int maxfev,
     s->gnorm = 0.0;
     s->pnorm = 0.0;
     s->fnorm = 0.0;
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
         s->x[i] = x0[i];
         s->xtrial[i] = x0[i];
@@ -277,10 +320,11 @@ NGX_HD inline void lm_init(LMState *s, int n, const double *x0, int maxfev,
 }
 
 // compute the next trial point from the current factorisation (lmpar)
-NGX_HD inline void lm_propose(LMState *s) {
+NGX_HD NGX_NI static void lm_propose(LMState *s) {
     int n = s->n;
     double p[LM_MAXP], wa3[LM_MAXP];
     lm_lmpar(n, s->R, s->ipvt, s->diag, s->qtf, s->delta, &s->par, p);
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         s->step[j] = -p[j];
         s->xtrial[j] = s->x[j] + s->step[j];
@@ -295,7 +339,7 @@ NGX_HD inline void lm_propose(LMState *s) {
 // model or prior was out of range: the reference's -inf residual vector has
 // a NaN MINPACK norm).  Returns 1 when the trial point was accepted (or was
 // the initial point), i.e. when the caller must adopt the pass's statistics.
-NGX_HD inline int lm_feed_f(LMState *s, double fnorm_new) {
+NGX_HD NGX_NI static int lm_feed_f(LMState *s, double fnorm_new) {
     int n = s->n;
     s->nfev += 1;
     if (s->nfev == 1) {
@@ -312,9 +356,12 @@ NGX_HD inline int lm_feed_f(LMState *s, double fnorm_new) {
     }
     // |R P^T p|
     double wa3[LM_MAXP];
+#pragma unroll 1
     for (int j = 0; j < n; j++) wa3[j] = 0.0;
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         double temp = s->step[s->ipvt[j]];
+#pragma unroll 1
         for (int i = 0; i <= j; i++) wa3[i] += s->R[i + LM_MAXP * j] * temp;
     }
     double temp1 = lm_enorm(n, wa3) / s->fnorm;
@@ -336,6 +383,7 @@ NGX_HD inline int lm_feed_f(LMState *s, double fnorm_new) {
     int accepted = 0;
     if (ratio >= 1.0e-4) {
         double wa2[LM_MAXP];
+#pragma unroll 1
         for (int j = 0; j < n; j++) {
             s->x[j] = s->xtrial[j];
             wa2[j] = s->diag[j] * s->x[j];
@@ -375,7 +423,7 @@ NGX_HD inline int lm_feed_f(LMState *s, double fnorm_new) {
 // Feed the result of an EVAL_J pass at s->x: A = J^T J (column major, ld
 // LM_MAXP), b = J^T f.  extra_nfev is the number of residual evaluations the
 // Jacobian cost (n for forward differences, 0 for the analytic one).
-NGX_HD inline void lm_feed_j(LMState *s, const double *A, const double *b,
+NGX_HD NGX_NI static void lm_feed_j(LMState *s, const double *A, const double *b,
                              int extra_nfev) {
     int n = s->n;
     s->njev += 1;
@@ -383,6 +431,7 @@ NGX_HD inline void lm_feed_j(LMState *s, const double *A, const double *b,
     lm_pchol(n, A, s->R, s->ipvt, s->acnorm);
     if (s->iter == 1) {
         double wa3[LM_MAXP];
+#pragma unroll 1
         for (int j = 0; j < n; j++) {
             s->diag[j] = s->acnorm[j];
             if (s->acnorm[j] == 0.0) s->diag[j] = 1.0;
@@ -393,19 +442,23 @@ NGX_HD inline void lm_feed_j(LMState *s, const double *A, const double *b,
         if (s->delta == 0.0) s->delta = s->factor;
     }
     // qtf = R^-T P^T b
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         double rjj = s->R[j + LM_MAXP * j];
         double v = b[s->ipvt[j]];
+#pragma unroll 1
         for (int i = 0; i < j; i++) v -= s->R[i + LM_MAXP * j] * s->qtf[i];
         s->qtf[j] = (rjj != 0.0) ? v / rjj : 0.0;
     }
     // gnorm = max_j |(J^T f)_j| / (acnorm_j |f|)
     double gnorm = 0.0;
     if (s->fnorm != 0.0) {
+#pragma unroll 1
         for (int j = 0; j < n; j++) {
             int l = s->ipvt[j];
             if (s->acnorm[l] != 0.0) {
                 double sum = 0.0;
+#pragma unroll 1
                 for (int i = 0; i <= j; i++)
                     sum += s->R[i + LM_MAXP * j] * (s->qtf[i] / s->fnorm);
                 gnorm = lm_max(gnorm, fabs(sum / s->acnorm[l]));
@@ -418,32 +471,41 @@ NGX_HD inline void lm_feed_j(LMState *s, const double *A, const double *b,
         s->action = LM_ACT_DONE;
         return;
     }
+#pragma unroll 1
     for (int j = 0; j < n; j++) s->diag[j] = lm_max(s->diag[j], s->acnorm[j]);
     lm_propose(s);
 }
 
 // cov0 = (J^T J)^-1 = P R^-1 R^-T P^T from the last factorisation (row
 // major n x n out).  Returns 0 when R is singular (scipy: cov_x None).
-NGX_HD inline int lm_cov0(const LMState *s, double *cov) {
+NGX_HD NGX_NI static int lm_cov0(const LMState *s, double *cov) {
     int n = s->n;
     const int ld = LM_MAXP;
     double rinv[LM_MAXP * LM_MAXP];
+#pragma unroll 1
     for (int j = 0; j < n; j++)
         if (s->R[j + ld * j] == 0.0) return 0;
+#pragma unroll 1
     for (int i = 0; i < n * LM_MAXP; i++) rinv[i] = 0.0;
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         rinv[j + ld * j] = 1.0 / s->R[j + ld * j];
+#pragma unroll 1
         for (int i = j - 1; i >= 0; i--) {
             double sum = 0.0;
+#pragma unroll 1
             for (int k = i + 1; k <= j; k++)
                 sum += s->R[i + ld * k] * rinv[k + ld * j];
             rinv[i + ld * j] = -sum / s->R[i + ld * i];
         }
     }
     // row ipvt[j] of P R^-1 is row j of R^-1
+#pragma unroll 1
     for (int a = 0; a < n; a++)
+#pragma unroll 1
         for (int b = 0; b <= a; b++) {
             double sum = 0.0;
+#pragma unroll 1
             for (int k = 0; k < n; k++)
                 sum += rinv[a + ld * k] * rinv[b + ld * k];
             cov[s->ipvt[a] * n + s->ipvt[b]] = sum;
@@ -456,25 +518,32 @@ NGX_HD inline int lm_cov0(const LMState *s, double *cov) {
 // construction: a negative eigenvalue exists iff the matrix is not positive
 // semi-definite, decided by a Cholesky sweep with a rounding-level floor.
 // Returns flag bits (NEG_COV_EIG 1024, NEG_COV_DIAG 2048, EIG_NOTFINITE 8192)
-NGX_HD inline int lm_test_cov(int n, const double *cov) {
+NGX_HD NGX_NI static int lm_test_cov(int n, const double *cov) {
     int flags = 0;
+#pragma unroll 1
     for (int i = 0; i < n * n; i++)
         if (!(fabs(cov[i]) <= DBL_MAX)) return 8192;
+#pragma unroll 1
     for (int i = 0; i < n; i++)
         if (cov[i * n + i] < 0.0) flags |= 2048;
     double L[LM_MAXP * LM_MAXP];
     double scale = 0.0;
+#pragma unroll 1
     for (int i = 0; i < n; i++) scale = lm_max(scale, fabs(cov[i * n + i]));
     double tol = 64.0 * LM_EPSMCH * scale;
     int neg = 0;
+#pragma unroll 1
     for (int j = 0; j < n && !neg; j++) {
         double dsum = cov[j * n + j];
+#pragma unroll 1
         for (int k = 0; k < j; k++) dsum -= L[j * n + k] * L[j * n + k];
         if (dsum < -tol) { neg = 1; break; }
         double ljj = sqrt(dsum > 0.0 ? dsum : 0.0);
         L[j * n + j] = ljj;
+#pragma unroll 1
         for (int i = j + 1; i < n; i++) {
             double sum = cov[i * n + j];
+#pragma unroll 1
             for (int k = 0; k < j; k++) sum -= L[i * n + k] * L[j * n + k];
             L[i * n + j] = ljj > 0.0 ? sum / ljj : 0.0;
         }
