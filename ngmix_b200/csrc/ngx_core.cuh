@@ -117,6 +117,13 @@ __device__ __forceinline__ double apod_window_x(double x) {
     double u = fma(2.0, x, 25.0) * 0.2;
     return u * u * u * (10.0 + u * (-15.0 + 6.0 * u));
 }
+// the same window with fused multiply-adds (hot loops; within an ulp or two
+// of apod_window_x)
+__device__ __forceinline__ double apod_window_fast(double x) {
+    double u = fma(0.4, x, 5.0);
+    double t = fma(fma(6.0, u, -15.0), u, 10.0);
+    return (u * u) * (u * t);
+}
 // apod_window_deriv (fastexp_nb.py:120-135)
 __device__ __forceinline__ double apod_window_deriv_x(double x) {
     double u = fma(2.0, x, 25.0) * 0.2;

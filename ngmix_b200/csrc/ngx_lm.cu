@@ -59,7 +59,7 @@ struct LMShared {
     double psf_row, psf_col, psf_ipsum;
     double cur_ssq, cur_rfirst2, cur_num, cur_den;   // at the accepted x
     ngx_jacobian jac;
-    int stamp, npix, first_q, status, action, first_eval;
+    int stamp, npix, first_q, status, action, spec;
     int warp_i[32], warp_j[32], warp_k[32];
 };
 
@@ -190,9 +190,15 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
 #pragma unroll
             for (int c = 0; c < CV; c++) e[c] = fexp_tab(x[c], tab);
             if (__any_sync(0xffffffffu, anyapod)) {
+                // some lane of some pixel sits in the apodization band
 #pragma unroll
-                for (int c = 0; c < CV; c++)
-                    if (x_in_apod(x[c])) e[c] *= apod_window_x(x[c]);
+                for (int c = 0; c < CV; c++) {
+                    bool ap = inr[c] && x_in_apod(x[c]);
+                    if (__any_sync(0xffffffffu, ap)) {
+                        double w = apod_window_fast(x[c]);
+                        if (ap) e[c] *= w;
+                    }
+                }
             }
 #pragma unroll
             for (int c = 0; c < CV; c++)
@@ -287,11 +293,13 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
 #pragma unroll
             for (int c = 0; c < CD; c++)
                 if (!inr[c]) { hqv[c] = 0.0; hqu[c] = 0.0; }
-            if (!__any_sync(0xffffffffu, anyapod)) {
+            const bool warp_apod = __any_sync(0xffffffffu, anyapod);
 #pragma unroll
-                for (int c = 0; c < CD; c++) {
-                    double vl = fexp_tab(xx[c], tab);
-                    if (!inr[c]) vl = 0.0;
+            for (int c = 0; c < CD; c++) {
+                double vl = fexp_tab(xx[c], tab);
+                if (!inr[c]) vl = 0.0;
+                bool ap = inr[c] && x_in_apod(xx[c]);
+                if (!(warp_apod && __any_sync(0xffffffffu, ap))) {
                     S0[c] += vl;
                     S1[c] = fma(vl, hqv[c], S1[c]);
                     S2[c] = fma(vl, hqu[c], S2[c]);
@@ -301,18 +309,13 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                     MA[c] = fma(cv, ea - eb, MA[c]);
                     MS[c] = fma(cv, ea + eb, MS[c]);
                     MB[c] = fma(cv, fma(hqv[c], hqu[c], qc), MB[c]);
-                }
-            } else {
-                // some lane sits in the apodization band: the window slope
-                // enters the terms that flow through chi^2,
-                // derivs_nb.py:104-114
-#pragma unroll
-                for (int c = 0; c < CD; c++) {
-                    double vl = fexp_tab(xx[c], tab);
-                    if (!inr[c]) vl = 0.0;
+                } else {
+                    // a lane of this pixel group sits in the apodization
+                    // band: the window slope enters the terms that flow
+                    // through chi^2, derivs_nb.py:104-114
                     double w = 1.0, wd = 0.0;
-                    if (inr[c] && x_in_apod(xx[c])) {
-                        w = apod_window_x(xx[c]);
+                    if (ap) {
+                        w = apod_window_fast(xx[c]);
                         wd = apod_window_deriv_x(xx[c]);
                     }
                     double vc = vl * (w - 2.0 * wd);
@@ -322,9 +325,9 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                     S2[c] = fma(vc, hqu[c], S2[c]);
                     double cv = vc * h, cw = vw * h;
                     double qu2 = hqu[c] * hqu[c], qv2 = hqv[c] * hqv[c];
-                    MA[c] += cv * (qu2 - qv2) + cw * (hb - ha);
-                    MS[c] += cv * (qu2 + qv2) + cw * (hb + ha);
-                    MB[c] += cv * (hqv[c] * hqu[c]) + cw * qc;
+                    MA[c] = fma(cv, qu2 - qv2, fma(cw, hb - ha, MA[c]));
+                    MS[c] = fma(cv, qu2 + qv2, fma(cw, hb + ha, MS[c]));
+                    MB[c] = fma(cv, hqv[c] * hqu[c], fma(cw, qc, MB[c]));
                 }
             }
         }
@@ -724,7 +727,7 @@ k_lm_fit(LMArgs a) {
             lm_init(&sh.st, a.np, a.guess + (size_t)stamp * a.np,
                     a.lm.maxfev, a.lm.ftol, a.lm.xtol);
             sh.action = sh.st.action;
-            sh.first_eval = 1;
+            sh.spec = 1;
             for (int i = 0; i < a.np; i++) sh.xeval[i] = sh.st.xtrial[i];
             sh.cur_ssq = sh.cur_rfirst2 = sh.cur_num = sh.cur_den = 0.0;
         }
@@ -749,42 +752,51 @@ k_lm_fit(LMArgs a) {
         // ---- the fit
         while (sh.action != LM_ACT_DONE) {
             const int action = sh.action;
-            const int first_eval = sh.first_eval;
+            const int spec = sh.spec;
             __syncthreads();
             if (threadIdx.x == 0) sh.status = 0;
             __syncthreads();
-            // fuse f(x0) into the first derivative pass unless the Jacobian
-            // is not evaluable there (T == 0 or flux == 0)
-            const bool fuse = first_eval && sh.st.x[4] != 0.0
-                && sh.st.x[5] != 0.0;
-            if (MODE == 0 && (fuse || action == LM_ACT_EVAL_J)) {
-                // derivative pass at the accepted point.  The very first
-                // evaluation is fused: the same pass yields f(x0) and J(x0)
-                // (the reference evaluates them separately; nfev and njev
-                // count as the reference's do).
-                build_mixture(a, &sh, sh.st.x, gc, ptab, area);
+            // the point this pass evaluates: the trial point for a residual
+            // evaluation, the accepted point for a Jacobian
+            const bool want_f = (action == LM_ACT_EVAL_F);
+            const double *xp = want_f ? sh.xeval : sh.st.x;
+            // Speculation: when the previous trial was accepted (and at the
+            // very first evaluation) the residual pass also produces the
+            // Jacobian at the trial point, which MINPACK asks for next if the
+            // step is accepted.  One fused pass costs 30 fp64 instr per
+            // gaussian-pixel instead of 16 + 30, halves the serial sections
+            // per iteration, and leaves nfev/njev/iterates unchanged; a
+            // rejected step just discards the extra sums.
+            const bool fused = want_f && spec && xp[4] != 0.0 && xp[5] != 0.0;
+            if (MODE == 0 && (fused || action == LM_ACT_EVAL_J)) {
+                build_mixture(a, &sh, xp, gc, ptab, area);
                 __syncthreads();
                 const int mix_status = sh.status;
                 double sums[NDSUM];
 #pragma unroll
                 for (int i = 0; i < NDSUM; i++) sums[i] = 0.0;
                 // calc_jacobian raises for T == 0 or flux == 0
-                int jstatus = mix_status
-                    || sh.st.x[4] == 0.0 || sh.st.x[5] == 0.0;
+                int jstatus = mix_status || xp[4] == 0.0 || xp[5] == 0.0;
                 if (!jstatus)
-                    deriv_pass<CD>(a, &sh, sh.st.x, gc, ptab, val, ierr, rowd,
-                                   cold, sums);
+                    deriv_pass<CD>(a, &sh, xp, gc, ptab, val, ierr, rowd, cold,
+                                   sums);
                 block_sum<NDSUM>(sums, scratch);
                 if (threadIdx.x == 0) {
-                    if (fuse) {
-                        feed_residual(a, &sh, sh.st.x, sums[27], mix_status);
-                        sh.cur_ssq = sums[27];
-                        sh.cur_num = sums[28];
-                        sh.cur_den = sums[29];
-                        sh.cur_rfirst2 = sums[30];
-                        sh.first_eval = 0;
+                    if (want_f) {
+                        int acc = feed_residual(a, &sh, xp, sums[27],
+                                                mix_status);
+                        if (acc) {
+                            sh.cur_ssq = sums[27];
+                            sh.cur_num = sums[28];
+                            sh.cur_den = sums[29];
+                            sh.cur_rfirst2 = sums[30];
+                            if (sh.st.action == LM_ACT_EVAL_J)
+                                feed_jacobian(a, &sh, sums, jstatus, 1, hs);
+                        }
+                        sh.spec = acc;
+                    } else {
+                        feed_jacobian(a, &sh, sums, jstatus, 1, hs);
                     }
-                    feed_jacobian(a, &sh, sums, jstatus, 1, hs);
                 }
             } else if (action == LM_ACT_EVAL_F) {
                 build_mixture(a, &sh, sh.xeval, gc, ptab, area);
@@ -803,7 +815,7 @@ k_lm_fit(LMArgs a) {
                         sh.cur_den = sums[2];
                         sh.cur_rfirst2 = sums[3];
                     }
-                    sh.first_eval = 0;
+                    sh.spec = acc;
                 }
             } else {
                 // forward differences: base + np perturbed mixtures
