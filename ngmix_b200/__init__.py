@@ -1,5 +1,26 @@
 """
 ngmix_b200: B200-native batched Gaussian-mixture image fitting, a drop-in for
-the fitting hot path of esheldon/ngmix (see DESIGN.md).
+the fitting hot path of esheldon/ngmix (see DESIGN.md, INTEGRATION.md).
+
+The public names mirror ngmix: GMix/GMixModel, Observation/Jacobian/
+make_pixels, fitting.Fitter (Levenberg-Marquardt), em and admom runners.
+Every numerical operation goes through the C ABI (include/ngx.h) to
+hand-written sm_100a CUDA kernels; there is no CPU fallback.
 """
 __version__ = "0.1.0"
+
+from . import flags, defaults, gexceptions, priors, shape  # noqa: F401
+from .gexceptions import GMixRangeError, GMixFatalError  # noqa: F401
+from .jacobian import Jacobian, DiagonalJacobian, UnitJacobian  # noqa: F401
+from .pixels import make_pixels, make_coords  # noqa: F401
+from .gmix import (  # noqa: F401
+    GMix, GMixModel, GMixCM, GMixCoellip, make_gmix_model, gmix_concat,
+)
+from .observation import (  # noqa: F401
+    Observation, ObsList, MultiBandObsList, get_mb_obs,
+)
+from . import fitting, em, admom  # noqa: F401
+from .fitting import Fitter, fit_batch  # noqa: F401
+from .em import EMFitter, run_em, em_batch  # noqa: F401
+from .admom import AdmomFitter, run_admom, admom_batch  # noqa: F401
+from . import joint_prior  # noqa: F401

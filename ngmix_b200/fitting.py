@@ -1,0 +1,213 @@
+"""
+ngmix.fitting.Fitter on the B200: same constructor and `go(obs, guess)` as
+ngmix/fitting/fitters.py:20-117, same result keys as run_leastsq
+(fitting/leastsqbound.py:118-126) + FitModel.set_fit_result
+(fitting/results.py:45-72).  The whole fit - residuals, analytic or
+forward-difference Jacobian, MINPACK iteration, covariance and fit statistics
+- runs in one kernel launch (ngx_lm_fit); `go` is the n = 1 case of
+`fit_batch`, which takes stacked arrays and is the fast path.
+"""
+import numpy as np
+
+from . import _lib
+from .defaults import DEFAULT_LM_PARS
+from .gexceptions import GMixFatalError, GMixRangeError
+from .gmix import (GMix, get_model_name, get_model_npars, get_model_num,
+                   make_gmix_model)
+from .observation import Observation, get_mb_obs
+
+__all__ = ['Fitter', 'FitResult', 'fit_batch', 'SIMPLE_ANALYTIC_MODELS']
+
+# models with an analytic Jacobian (fitting/results.py:921)
+SIMPLE_ANALYTIC_MODELS = ('gauss', 'exp', 'dev')
+_LM_MODELS = ('gauss', 'exp', 'dev', 'turb', 'bdf', 'bd')
+
+
+def _prior_record(prior):
+    if prior is None:
+        return None
+    if isinstance(prior, _lib.Prior):
+        return prior
+    if hasattr(prior, "to_ngx"):
+        return prior.to_ngx()
+    raise TypeError("unsupported prior %s" % type(prior))
+
+
+def fit_batch(model, images, weights, jacobians, psf_pars, guesses,
+              prior=None, fit_pars=None, analytic_jacobian=True,
+              ignore_zero_weight=True):
+    """
+    Levenberg-Marquardt fits of n stamps in one launch.
+
+    Parameters
+    ----------
+    model: str
+        gauss, exp, dev, turb, bdf or bd
+    images, weights: [n, H, W] arrays
+    jacobians: [n, 8] array (or Jacobian records)
+        row0, col0, dvdrow, dvdcol, dudrow, dudcol, det, scale per stamp
+    psf_pars: [n, npsf, 6] array or None
+        full gaussian parameters of each stamp's psf mixture
+    guesses: [n, npars] array
+    prior: PriorSimpleSep / PriorBDFSep, optional
+    fit_pars: dict with maxfev, ftol, xtol, optional
+
+    Returns
+    -------
+    structured array [n] with fields flags, nfev, ier, npix, dof, lnprob,
+    s2n_numer, s2n_denom, chi2per, s2n, T, T_err, flux, flux_err, pars,
+    pars_err, pars_cov0, pars_cov (matrices flattened row major, 8x8 slots)
+    """
+    model = get_model_name(get_model_num(model))
+    if model not in _LM_MODELS:
+        raise ValueError("model '%s' cannot be fit with ngx_lm_fit" % model)
+    fp = dict(DEFAULT_LM_PARS)
+    if fit_pars is not None:
+        fp.update(fit_pars)
+    return _lib.lm_fit(model, images, weights, jacobians, psf_pars, guesses,
+                       prior=_prior_record(prior), maxfev=fp["maxfev"],
+                       ftol=fp["ftol"], xtol=fp["xtol"],
+                       analytic_jacobian=analytic_jacobian,
+                       ignore_zero_weight=ignore_zero_weight)
+
+
+_ERRMSG = {
+    1: "Both actual and predicted relative reductions in the sum of squares "
+       "are at most ftol",
+    2: "The relative error between two consecutive iterates is at most xtol",
+    3: "Both ftol and xtol termination conditions are satisfied",
+    4: "The cosine of the angle between func(x) and any column of the "
+       "Jacobian is at most gtol in absolute value",
+    5: "Number of calls to function has reached maxfev",
+    6: "ftol is too small, no further reduction in the sum of squares is "
+       "possible",
+    7: "xtol is too small, no further improvement in the approximate "
+       "solution is possible",
+    8: "gtol is too small, func(x) is orthogonal to the columns of the "
+       "Jacobian to machine precision",
+}
+
+
+def record_to_result(rec, model, npars):
+    """one record of fit_batch -> the reference's result dict"""
+    n = npars
+    res = {
+        "model": model,
+        "flags": int(rec["flags"]),
+        "nfev": int(rec["nfev"]),
+        "ier": int(rec["ier"]),
+        "errmsg": _ERRMSG.get(int(rec["ier"]), ""),
+        "pars": rec["pars"][:n].copy(),
+        "pars_err": rec["pars_err"][:n].copy(),
+        "pars_cov": rec["pars_cov"][:n * n].reshape(n, n).copy(),
+    }
+    cov0 = rec["pars_cov0"][:n * n].reshape(n, n).copy()
+    res["pars_cov0"] = None if np.isnan(cov0).all() else cov0
+    if res["flags"] & _lib_flags("LM_SINGULAR_MATRIX"):
+        res["errmsg"] = "singular covariance"
+    if res["flags"] == 0:
+        for k in ("lnprob", "s2n_numer", "s2n_denom", "chi2per", "s2n",
+                  "T", "T_err", "flux", "flux_err"):
+            res[k] = float(rec[k])
+        res["npix"] = int(rec["npix"])
+        res["dof"] = int(rec["dof"])
+        res["s2n_w"] = res["s2n"]
+        res["g"] = res["pars"][2:4].copy()
+        res["g_cov"] = res["pars_cov"][2:4, 2:4].copy()
+        res["g_err"] = res["pars_err"][2:4].copy()
+    return res
+
+
+def _lib_flags(name):
+    from . import flags
+    return getattr(flags, name)
+
+
+class FitResult(dict):
+    """
+    The result of Fitter.go: a dict with the reference's keys plus the
+    mixture helpers of FitModel (results.py:74-123).
+    """
+
+    def __init__(self, obs, model, result):
+        super().__init__(result)
+        self.obs = get_mb_obs(obs)
+        self.model_name = model
+        self.npars = get_model_npars(model)
+        self.nband = 1
+
+    def get_gmix(self, band=0):
+        return make_gmix_model(self["pars"], self.model_name)
+
+    def get_convolved_gmix(self, band=0, obsnum=0):
+        gm = self.get_gmix(band)
+        obs = self.obs[band][obsnum]
+        if obs.has_psf_gmix():
+            gm = gm.convolve(obs.psf.gmix)
+        return gm
+
+    def make_image(self, band=0, obsnum=0):
+        gm = self.get_convolved_gmix(band=band, obsnum=obsnum)
+        obs = self.obs[band][obsnum]
+        return gm.make_image(obs.image.shape, jacobian=obs.jacobian)
+
+
+class Fitter(object):
+    """
+    Levenberg-Marquardt fit of a PSF-convolved model to an observation.
+
+    Parameters
+    ----------
+    model: str
+        The model to fit
+    prior: PriorSimpleSep or PriorBDFSep, optional
+    fit_pars: dict, optional
+        maxfev, ftol, xtol (defaults 4000, 1e-5, 1e-5)
+    use_noise_image: bool, optional
+        the noise-power sandwich covariance is out of scope (SURVEY.md row
+        21); True raises NotImplementedError
+    analytic_jacobian: bool, optional
+        analytic Jacobian for gauss/exp/dev, forward differences otherwise
+        (MINPACK lmder / lmdif, as in the reference).  Default True.
+    """
+
+    def __init__(self, model, prior=None, fit_pars=None,
+                 use_noise_image=False, analytic_jacobian=True):
+        self.prior = prior
+        self.model = get_model_num(model)
+        self.model_name = get_model_name(self.model)
+        if use_noise_image:
+            raise NotImplementedError("use_noise_image is out of scope")
+        self.use_noise_image = use_noise_image
+        self.analytic_jacobian = analytic_jacobian
+        self.fit_pars = dict(fit_pars) if fit_pars is not None \
+            else dict(DEFAULT_LM_PARS)
+
+    def go(self, obs, guess):
+        """run the fit; returns a dict-like FitResult"""
+        mb = get_mb_obs(obs)
+        if len(mb) != 1 or len(mb[0]) != 1:
+            raise NotImplementedError(
+                "multi-epoch / multi-band fits are a 'next' row of the scope "
+                "table; send one Observation")
+        o = mb[0][0]
+        npars = get_model_npars(self.model_name)
+        guess = np.array(guess, dtype="f8")
+        assert guess.size == npars, \
+            "guess has npars=%d, expected %d" % (guess.size, npars)
+        psf_pars = None
+        if o.has_psf_gmix():
+            psf_pars = o.psf.gmix.get_full_pars().reshape(1, -1, 6)
+        # FitModel._setup_fit fills the mixtures at the guess and lets a
+        # GMixRangeError propagate (results.py:359-375)
+        gm0 = make_gmix_model(guess, self.model_name)
+        del gm0
+        rec = fit_batch(self.model_name, o.image[None], o.weight[None],
+                        o._jacobian._data, psf_pars, guess[None],
+                        prior=self.prior, fit_pars=self.fit_pars,
+                        analytic_jacobian=self.analytic_jacobian,
+                        ignore_zero_weight=o.ignore_zero_weight)[0]
+        if rec["flags"] == 1 and rec["nfev"] == 0:
+            raise GMixFatalError("no weights > 0")
+        res = record_to_result(rec, self.model_name, npars)
+        return FitResult(o, self.model_name, res)
