@@ -210,6 +210,8 @@ def main():
     torch.cuda.set_device(local)
     _lib.init(local)
     if world > 1:
+        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
+        os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     nobj = args.nobj
@@ -289,9 +291,12 @@ def main():
 
     # ---- end to end through the public host-buffer call: pinned host
     # inputs -> device -> fit -> results back on the host, every step
+    e2e_out = np.frombuffer(h_res.numpy(), dtype=_lib.LM_RESULT_DTYPE)
+
     def step_e2e():
         return _lib.lm_fit("exp", h_images.numpy(), h_weights.numpy(),
-                           h_jac.numpy(), h_psf.numpy(), h_guess.numpy())
+                           h_jac.numpy(), h_psf.numpy(), h_guess.numpy(),
+                           out=e2e_out)
 
     for _ in range(2):
         step_e2e()

@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""
+Secondary measurements (BASELINE.json configs[2]): EM 3-gaussian fits and
+adaptive moments on 25x25 PSF stamps, device-resident, beside the CPU oracle
+port on the host threads.  Prints one JSON line; not the headline bench.
+
+    python bench_extra.py [--nobj 20000] [--steps 3]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nobj", type=int, default=20000)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    import torch
+    from ngmix_b200 import _lib, sims
+    _lib.init(0)
+    dev = torch.device("cuda", 0)
+    n = args.nobj
+    b = sims.make_psf_batch(n, seed0=424242)
+    t = {k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev)
+         for k in ("images", "weights", "jac", "em_guess", "am_guess")}
+    d_pars = torch.zeros(n * 18, dtype=torch.float64, device=dev)
+    d_em = torch.zeros(n * _lib.EM_RESULT_DTYPE.itemsize, dtype=torch.uint8,
+                       device=dev)
+    d_am = torch.zeros(n * _lib.ADMOM_RESULT_DTYPE.itemsize,
+                       dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+
+    def em():
+        _lib.em_device(n, t["images"].data_ptr(), t["weights"].data_ptr(),
+                       t["jac"].data_ptr(), 25, 25, t["em_guess"].data_ptr(),
+                       3, d_pars.data_ptr(), d_em.data_ptr(), stream=s)
+
+    def am():
+        _lib.admom_device(n, t["images"].data_ptr(), t["weights"].data_ptr(),
+                          t["jac"].data_ptr(), 25, 25,
+                          t["am_guess"].data_ptr(), d_am.data_ptr(), stream=s)
+
+    out = {"config": "configs[2]: %d PSF stamps 25x25, EM 3-gaussian "
+                     "(tol 1e-5, miniter 40, maxiter 500) + admom" % n}
+    for name, fn in (("em", em), ("admom", am)):
+        fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out[name] = {"fits_per_s": n / (ms * 1e-3), "ms_per_step": ms}
+    rem = np.frombuffer(d_em.cpu().numpy().tobytes(),
+                        dtype=_lib.EM_RESULT_DTYPE)
+    ram = np.frombuffer(d_am.cpu().numpy().tobytes(),
+                        dtype=_lib.ADMOM_RESULT_DTYPE)
+    out["em"]["median_numiter"] = float(np.median(rem["numiter"]))
+    out["em"]["frac_maxiter"] = float(np.mean(rem["flags"] == 32))
+    # gaussian-pixel E+M evaluations per second (3 gaussians x 625 px x iters)
+    out["em"]["gauss_pixel_evals_per_s"] = float(
+        rem["numiter"].sum() * 3.0 * 625 / (out["em"]["ms_per_step"] * 1e-3))
+    out["admom"]["median_numiter"] = float(np.median(ram["numiter"]))
+    if not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        oracle.build()
+        cores = os.cpu_count()
+        ns = min(n, 40 * cores)
+        t0 = time.perf_counter()
+        ores, _ = oracle.em_go_batch(b["images"][:ns], b["weights"][:ns],
+                                     b["jac"][:ns], b["em_guess"][:ns],
+                                     nthreads=cores)
+        dt = time.perf_counter() - t0
+        out["em"]["cpu_port_fits_per_s"] = ns / dt
+        out["em"]["cpu_cores"] = cores
+        out["em"]["numiter_equal_on_sample"] = int(
+            (ores["numiter"] == rem["numiter"][:ns]).sum())
+        out["em"]["flags_equal_on_sample"] = int(
+            (ores["flags"] == rem["flags"][:ns]).sum())
+        out["em"]["sample"] = ns
+        na = min(n, 2000 * cores)
+        t0 = time.perf_counter()
+        oam = oracle.admom_go_batch(b["images"][:na], b["weights"][:na],
+                                    b["jac"][:na], b["am_guess"][:na],
+                                    nthreads=cores)
+        dt = time.perf_counter() - t0
+        out["admom"]["cpu_port_fits_per_s"] = na / dt
+        out["admom"]["numiter_equal_on_sample"] = int(
+            (oam["numiter"] == ram["numiter"][:na]).sum())
+        out["admom"]["flags_equal_on_sample"] = int(
+            (oam["flags"] == ram["flags"][:na]).sum())
+        out["admom"]["sample"] = na
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -330,11 +330,12 @@ def deriv_images(gpars, dcov, jac, dims):
 # ---------------------------------------------------------------- LM
 def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
            maxfev=4000, ftol=1.0e-5, xtol=1.0e-5, analytic_jacobian=True,
-           ignore_zero_weight=True):
+           ignore_zero_weight=True, out=None):
     """
     batched Fitter.go through the host-buffer entry point.
     images/weights [n,H,W]; psf_pars [n,npsf,6] or None; guess [n,npars].
-    Returns LM_RESULT_DTYPE [n].
+    Returns LM_RESULT_DTYPE [n] (written into `out` when given, e.g. a view
+    of pinned host memory, which lets the D2H copy run asynchronously).
     """
     init()
     images = _f8(images)
@@ -351,7 +352,12 @@ def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
         npsf = psf_pars.shape[1]
     pr = prior if prior is not None else Prior()
     lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)
-    res = np.zeros(n, dtype=LM_RESULT_DTYPE)
+    if out is None:
+        res = np.empty(n, dtype=LM_RESULT_DTYPE)
+    else:
+        res = out
+        assert res.dtype == LM_RESULT_DTYPE and res.shape == (n,) \
+            and res.flags.c_contiguous
     check(lib().ngx_lm_fit_host(
         C.c_int(n), C.c_int(MODELS[model]), _p(images), _p(weights), _p(jac),
         C.c_int(H), C.c_int(W), _p(psf_pars), C.c_int(npsf), _p(guess),
@@ -437,3 +443,30 @@ def peak_dfma(iters=20000):
     ms = C.c_double()
     check(lib().ngx_peak_dfma(C.c_int(iters), C.byref(out), C.byref(ms)))
     return out.value, ms.value
+
+
+def em_device(n, d_images, d_weights, d_jac, nrow, ncol, d_guess, ngauss,
+              d_pars_out, d_res, d_psf=0, npsf=0, variant="full", tol=1.0e-5,
+              miniter=40, maxiter=500, vary_sky=False, sky=None,
+              ignore_zero_weight=True, stream=0):
+    """device-pointer EM entry point (asynchronous on `stream`)"""
+    conf = EMConf(tol, maxiter, miniter, 0.0 if sky is None else sky,
+                  int(vary_sky), int(sky is not None))
+    check(lib().ngx_em(
+        C.c_int(n), C.c_int(EM_VARIANTS[variant]), C.c_void_p(d_images),
+        C.c_void_p(d_weights), C.c_void_p(d_jac), C.c_int(nrow),
+        C.c_int(ncol), C.c_void_p(d_guess), C.c_int(ngauss),
+        C.c_void_p(d_psf) if npsf else None, C.c_int(npsf), C.byref(conf),
+        C.c_int(int(ignore_zero_weight)), C.c_void_p(d_pars_out),
+        C.c_void_p(d_res), C.c_void_p(stream)))
+
+
+def admom_device(n, d_images, d_weights, d_jac, nrow, ncol, d_guess, d_res,
+                 maxiter=200, shiftmax=5.0, etol=1.0e-5, Ttol=1.0e-3,
+                 cenonly=False, stream=0):
+    """device-pointer admom entry point (asynchronous on `stream`)"""
+    conf = AdmomConf(maxiter, int(cenonly), shiftmax, etol, Ttol)
+    check(lib().ngx_admom(
+        C.c_int(n), C.c_void_p(d_images), C.c_void_p(d_weights),
+        C.c_void_p(d_jac), C.c_int(nrow), C.c_int(ncol), C.c_void_p(d_guess),
+        C.byref(conf), C.c_void_p(d_res), C.c_void_p(stream)))

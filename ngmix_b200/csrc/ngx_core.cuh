@@ -111,6 +111,15 @@ __device__ __forceinline__ double fexp_ref(double x) {
     return c_exp_lookup[idx] * p;
 }
 
+// the same with the exp(i) table in shared memory (per-lane index)
+__device__ __forceinline__ double fexp_ref_tab(double x, const double *tab) {
+    int idx;
+    double f = fexp_reduce(x, &idx);
+    double p = NGX_C0 + f * (NGX_C1 + f * (NGX_C2 + f * (NGX_C3 + f * (
+        NGX_C4 + f * NGX_C5))));
+    return tab[idx] * p;
+}
+
 // apod_window (fastexp_nb.py:97-117) in terms of x = -chi2/2;
 // 25 - chi2 == fma(2, x, 25) exactly as the reference rounds it
 __device__ __forceinline__ double apod_window_x(double x) {

@@ -26,6 +26,9 @@ namespace ngx {
 #define NGX_EM_MAX_CONV 48
 #define NGX_EM_TILE 64          // pixels per tile == threads per CTA
 #define NGX_EM_MAX_SLOTS 64     // 6*ngauss + 2 <= 62
+// contributions are stored slot-major with a padded stride so that phase B
+// (thread s walks slot s) hits different banks
+#define NGX_EM_STRIDE (NGX_EM_TILE + 1)
 
 struct EMGauss {
     double p, row, col, irr, irc, icc;
@@ -94,7 +97,7 @@ k_em(int n, const double *__restrict__ images,
     double *code = val + ntot;          // ntot: <0 excluded, 0 zero weight
     double *rowd = code + ntot;
     double *cold = rowd + nrow;
-    double *contrib = cold + ncol;      // nslots * T, slot major
+    double *contrib = cold + ncol;      // nslots * NGX_EM_STRIDE
 
     const int stamp = blockIdx.x;
     if (stamp >= n) return;
@@ -229,7 +232,7 @@ k_em(int n, const double *__restrict__ images,
                         double mv = 0.0;
                         if (chi2 < 25.0 && chi2 >= 0.0) {
                             double x = -0.5 * chi2;
-                            mv = g.pnorm * fexp_ref(x) * area;
+                            mv = g.pnorm * fexp_ref_tab(x, sh.tab) * area;
                             if (chi2 > 20.0) mv *= apod_window_x(x);
                         }
                         s += mv;
@@ -267,7 +270,7 @@ k_em(int n, const double *__restrict__ images,
                         double vl;
                         // hard cut, NO apodization: em_nb.py:222-227
                         if (chi2 < 25.0 && chi2 >= 0.0)
-                            vl = g.pnorm * fexp_ref(-0.5 * chi2) * area;
+                            vl = g.pnorm * fexp_ref_tab(-0.5 * chi2, sh.tab) * area;
                         else
                             vl = 0.0;
                         gi += vl;
@@ -285,9 +288,11 @@ k_em(int n, const double *__restrict__ images,
                             logL += vl * (sh.logtau[k] - 0.5 * sh.logdet[k]
                                           - 0.5 * chi2);
                     }
-                    double *c = contrib + (size_t)(6 * ii) * T + threadIdx.x;
-                    c[0] = gi; c[T] = tv; c[2 * T] = tu;
-                    c[3 * T] = tv2; c[4 * T] = tuv; c[5 * T] = tu2;
+                    double *c = contrib + (size_t)(6 * ii) * NGX_EM_STRIDE
+                        + threadIdx.x;
+                    c[0] = gi; c[NGX_EM_STRIDE] = tv;
+                    c[2 * NGX_EM_STRIDE] = tu; c[3 * NGX_EM_STRIDE] = tv2;
+                    c[4 * NGX_EM_STRIDE] = tuv; c[5 * NGX_EM_STRIDE] = tu2;
                 }
                 if (DO_LOGL) {
                     if (gsum == 0.0) logL = 0.0;
@@ -298,12 +303,14 @@ k_em(int n, const double *__restrict__ images,
                     bad = 1;
                 } else {
                     double pv = val[p];
-                    contrib[(size_t)(6 * ngauss) * T + threadIdx.x] = logL;
-                    contrib[(size_t)(6 * ngauss + 1) * T + threadIdx.x] =
-                        sky * pv / gtot;
+                    contrib[(size_t)(6 * ngauss) * NGX_EM_STRIDE
+                            + threadIdx.x] = logL;
+                    contrib[(size_t)(6 * ngauss + 1) * NGX_EM_STRIDE
+                            + threadIdx.x] = sky * pv / gtot;
                     double factor = pv / gtot;
                     for (int s = 0; s < 6 * ngauss; s++)
-                        contrib[(size_t)s * T + threadIdx.x] *= factor;
+                        contrib[(size_t)s * NGX_EM_STRIDE + threadIdx.x]
+                            *= factor;
                 }
             }
             unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -313,7 +320,8 @@ k_em(int n, const double *__restrict__ images,
             if (sh.status) break;
             // ---- phase B: thread s adds its slot in pixel order
             if (threadIdx.x < nslots) {
-                const double *c = contrib + (size_t)threadIdx.x * T;
+                const double *c = contrib
+                    + (size_t)threadIdx.x * NGX_EM_STRIDE;
                 unsigned m0 = sh.valid_mask[0], m1 = sh.valid_mask[1];
 #pragma unroll 8
                 for (int t = 0; t < 32; t++)
@@ -685,7 +693,7 @@ static int launch_em(int n, const double *images, const double *weights,
     int ntot = nrow * ncol;
     int nslots = 6 * ngauss + 2;
     size_t smem = sizeof(double)
-        * (2 * (size_t)ntot + nrow + ncol + (size_t)nslots * NGX_EM_TILE);
+        * (2 * (size_t)ntot + nrow + ncol + (size_t)nslots * NGX_EM_STRIDE);
     if (smem > (size_t)smem_optin_bytes())
         return fail(NGX_ERR_ARG, "ngx_em: stamp too large%s%s");
     NGX_CUDA(cudaFuncSetAttribute(k_em<VARIANT>,

@@ -467,95 +467,102 @@ __device__ __noinline__ double prior_fnorm2(const LMArgs &a, const double *x,
     return s;
 }
 
-// the epilogue: run_leastsq (leastsqbound.py:70-126) + set_fit_result
+// the epilogue: run_leastsq (leastsqbound.py:70-126) + set_fit_result.
+// Writes straight into the global result record; matrices are staged in the
+// shared-memory workspace of the state (no per-thread local arrays).
 __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
-                                 ngx_lm_result *out) {
+                                       ngx_lm_result *out) {
     LMState *s = &sh->st;
-    int np = a.np;
-    ngx_lm_result r;
-    r.nfev = s->nfev;
-    r.njev = s->njev;
-    r.ier = s->info;
-    r.npix = 0;
-    r.dof = 0;
-    double qnan = nan("");
-    r.lnprob = r.s2n_numer = r.s2n_denom = r.chi2per = r.s2n = qnan;
-    r.T = r.T_err = r.flux = r.flux_err = qnan;
-    for (int i = 0; i < 8; i++) { r.pars[i] = 0.0; r.pars_err[i] = 0.0; }
-    for (int i = 0; i < 64; i++) { r.pars_cov0[i] = 0.0; r.pars_cov[i] = 0.0; }
-    for (int i = 0; i < np; i++) r.pars[i] = s->x[i];
-    for (int i = 0; i < np * np; i++) r.pars_cov0[i] = qnan;
+    const int np = a.np;
+    ngx_lm_result &r = *out;
+    const double qnan = nan("");
+    double *cov0 = s->A;        // J^T J is no longer needed
+    double *pcov = s->T1;       // after lm_cov0 is done with it
     int flags = 0;
+    int have_cov = 0, have_pcov = 0, have_err = 0;
     if (s->info > 4) {
         flags |= 1 << (s->info - 5);
-        for (int i = 0; i < np; i++) {
-            r.pars[i] = NGX_PDEF;
-            r.pars_err[i] = NGX_CDEF;
-        }
-        for (int i = 0; i < np * np; i++) r.pars_cov[i] = NGX_CDEF;
     } else {
-        double cov0[LM_MAXP * LM_MAXP];
-        int have = lm_cov0(s, cov0);
-        if (!have) {
+        have_cov = lm_cov0(s, cov0);
+        if (!have_cov) {
             flags |= NGX_LM_SINGULAR_MATRIX;
-            for (int i = 0; i < np; i++) r.pars_err[i] = NGX_CDEF;
-            for (int i = 0; i < np * np; i++) r.pars_cov[i] = NGX_CDEF;
         } else {
-            for (int i = 0; i < np * np; i++) r.pars_cov0[i] = cov0[i];
             int dof = sh->npix - np;
             if (dof == 0) {
                 flags |= NGX_ZERO_DOF;
-                for (int i = 0; i < np; i++) r.pars_err[i] = NGX_CDEF;
-                for (int i = 0; i < np * np; i++) r.pars_cov[i] = NGX_CDEF;
             } else {
                 // fdiff[n_prior_pars:]: the simple priors fill one row fewer
                 // than they reserve, which drops the first pixel row
                 double ssq = sh->cur_ssq;
-                int nslots = prior_nslots(a.model, a.prior);
-                int nrows = prior_nrows(a.model, a.prior);
-                if (nslots > nrows) ssq -= sh->cur_rfirst2;
+                if (prior_nslots(a.model, a.prior)
+                    > prior_nrows(a.model, a.prior))
+                    ssq -= sh->cur_rfirst2;
                 double s_sq = ssq / dof;
-                for (int i = 0; i < np * np; i++)
-                    r.pars_cov[i] = cov0[i] * s_sq;
-                int cflags = lm_test_cov(np, r.pars_cov);
-                if (cflags) {
-                    flags |= cflags;
-                    for (int i = 0; i < np; i++) r.pars_err[i] = NGX_CDEF;
-                } else {
-                    for (int i = 0; i < np; i++)
-                        r.pars_err[i] = sqrt(r.pars_cov[i * np + i]);
-                }
+#pragma unroll 1
+                for (int i = 0; i < np * np; i++) pcov[i] = cov0[i] * s_sq;
+                have_pcov = 1;
+                int cflags = lm_test_cov(np, pcov, s->T2);
+                if (cflags) flags |= cflags;
+                else have_err = 1;
             }
         }
     }
     r.flags = flags;
+    r.nfev = s->nfev;
+    r.njev = s->njev;
+    r.ier = s->info;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        double pv = 0.0, pe = 0.0;
+        if (i < np) {
+            pv = (s->info > 4) ? NGX_PDEF : s->x[i];
+            pe = have_err ? sqrt(pcov[i * np + i]) : NGX_CDEF;
+        }
+        r.pars[i] = pv;
+        r.pars_err[i] = pe;
+    }
+#pragma unroll 1
+    for (int i = 0; i < 64; i++) {
+        double c0 = 0.0, c1 = 0.0;
+        if (i < np * np) {
+            c0 = have_cov ? cov0[i] : qnan;
+            c1 = have_pcov ? pcov[i] : NGX_CDEF;
+        }
+        r.pars_cov0[i] = c0;
+        r.pars_cov[i] = c1;
+    }
+    int npix = 0, dof = 0;
+    double lnprob = qnan, num = qnan, den = qnan, chi2per = qnan, s2n = qnan;
+    double Tv = qnan, Terr = qnan, flux = qnan, fluxerr = qnan;
     if (flags == 0) {
         double lnp_prior = 0.0;
-        int bad = prior_lnprob(a.model, a.prior, r.pars, &lnp_prior);
+        int bad = prior_lnprob(a.model, a.prior, s->x, &lnp_prior);
         if (bad) {
-            r.lnprob = -INFINITY;
-            r.s2n_numer = 0.0;
-            r.s2n_denom = NGX_BIGVAL;
-            r.npix = 0;
+            lnprob = -INFINITY;
+            num = 0.0;
+            den = NGX_BIGVAL;
+            npix = 0;
         } else {
-            r.lnprob = -0.5 * sh->cur_ssq + lnp_prior;
-            r.s2n_numer = sh->cur_num;
-            r.s2n_denom = sh->cur_den;
-            r.npix = sh->npix;
+            lnprob = -0.5 * sh->cur_ssq + lnp_prior;
+            num = sh->cur_num;
+            den = sh->cur_den;
+            npix = sh->npix;
         }
-        double s2n = 0.0;
-        if (r.s2n_denom > 0) s2n = r.s2n_numer / sqrt(r.s2n_denom);
-        double chi2 = r.lnprob / (-0.5);
-        int dof = r.npix - np;
-        r.chi2per = chi2 / dof;
-        r.dof = dof;
-        r.s2n = s2n;
-        r.T = r.pars[4];
-        r.T_err = sqrt(r.pars_cov[4 * np + 4]);
-        r.flux = r.pars[np - 1];
-        r.flux_err = sqrt(r.pars_cov[(np - 1) * np + (np - 1)]);
+        s2n = 0.0;
+        if (den > 0) s2n = num / sqrt(den);
+        double chi2 = lnprob / (-0.5);
+        dof = npix - np;
+        chi2per = chi2 / dof;
+        Tv = s->x[4];
+        Terr = sqrt(pcov[4 * np + 4]);
+        flux = s->x[np - 1];
+        fluxerr = sqrt(pcov[(np - 1) * np + (np - 1)]);
     }
-    *out = r;
+    r.npix = npix;
+    r.dof = dof;
+    r.lnprob = lnprob; r.s2n_numer = num; r.s2n_denom = den;
+    r.chi2per = chi2per; r.s2n = s2n;
+    r.T = Tv; r.T_err = Terr; r.flux = flux; r.flux_err = fluxerr;
 }
 
 // ---------------------------------------------------------------------
@@ -565,12 +572,12 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
 __device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
                                            const double *sums, int status,
                                            int analytic, const double *hs) {
-    double A[LM_MAXP * LM_MAXP], b[LM_MAXP];
+    double *A = sh->st.A, *b = sh->st.b;
     const int np = a.np;
     const double *x = sh->st.x;
     int nr = prior_nrows(a.model, a.prior);
-    double f0[NGX_MAX_PRIOR_ROWS];
-    double jp[NGX_MAX_PRIOR_ROWS * LM_MAXP];
+    double *f0 = sh->st.v[7];
+    double *jp = sh->st.T1;
     if (!status && nr > 0) {
         if (prior_fill_fdiff(a.model, a.prior, x, f0)) {
             status = 1;
@@ -579,7 +586,7 @@ __device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
         } else {
             // the prior rows are part of fvec: MINPACK's own forward
             // difference with its step hs
-            double xp[LM_MAXP], fs[NGX_MAX_PRIOR_ROWS];
+            double *xp = sh->st.v[8], *fs = sh->st.v[9];
             for (int s = 0; s < np && !status; s++) {
                 for (int i = 0; i < np; i++) xp[i] = x[i];
                 xp[s] = x[s] + hs[s];
@@ -630,8 +637,8 @@ __device__ __noinline__ int feed_residual(const LMArgs &a, LMShared *sh,
 // ---------------------------------------------------------------------
 // MODE 0: analytic Jacobian (gauss/exp/dev), np = 6
 // MODE 1: forward differences (any model), np <= 8
-template <int MODE, int CV, int CD>
-__global__ void __launch_bounds__(128, 4)
+template <int MODE, int CV, int CD, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_lm_fit(LMArgs a) {
     extern __shared__ double smem_d[];
     __shared__ LMShared sh;
@@ -655,6 +662,13 @@ k_lm_fit(LMArgs a) {
         const int stamp = sh.stamp;
         if (stamp >= a.n) break;
 
+#ifdef NGX_PROF
+        long long pt0 = clock64(), pt_mix = 0, pt_pass = 0, pt_solve = 0,
+                  pt_stage = 0, pt_fin = 0, ptx;
+#define PROF_T(x) do { ptx = clock64(); x += ptx - pt0; pt0 = ptx; } while (0)
+#else
+#define PROF_T(x)
+#endif
         // ---- stage the stamp in tiled order
         const double *im = a.images + (size_t)stamp * a.ntot;
         const double *wt = a.weights + (size_t)stamp * a.ntot;
@@ -737,18 +751,18 @@ k_lm_fit(LMArgs a) {
         if (sh.npix == 0) {
             // GMixFatalError("no weights > 0") at Observation construction
             if (threadIdx.x == 0) {
-                ngx_lm_result r;
-                memset(&r, 0, sizeof(r));
-                r.flags = NGX_NO_ATTEMPT;
+                ngx_lm_result *r = &a.res[stamp];
+                memset(r, 0, sizeof(*r));
+                r->flags = NGX_NO_ATTEMPT;
                 for (int i = 0; i < a.np; i++) {
-                    r.pars[i] = NGX_PDEF;
-                    r.pars_err[i] = NGX_CDEF;
+                    r->pars[i] = NGX_PDEF;
+                    r->pars_err[i] = NGX_CDEF;
                 }
-                a.res[stamp] = r;
             }
             continue;
         }
 
+        PROF_T(pt_stage);
         // ---- the fit
         while (sh.action != LM_ACT_DONE) {
             const int action = sh.action;
@@ -771,6 +785,7 @@ k_lm_fit(LMArgs a) {
             if (MODE == 0 && (fused || action == LM_ACT_EVAL_J)) {
                 build_mixture(a, &sh, xp, gc, ptab, area);
                 __syncthreads();
+                PROF_T(pt_mix);
                 const int mix_status = sh.status;
                 double sums[NDSUM];
 #pragma unroll
@@ -781,6 +796,7 @@ k_lm_fit(LMArgs a) {
                     deriv_pass<CD>(a, &sh, xp, gc, ptab, val, ierr, rowd, cold,
                                    sums);
                 block_sum<NDSUM>(sums, scratch);
+                PROF_T(pt_pass);
                 if (threadIdx.x == 0) {
                     if (want_f) {
                         int acc = feed_residual(a, &sh, xp, sums[27],
@@ -801,11 +817,13 @@ k_lm_fit(LMArgs a) {
             } else if (action == LM_ACT_EVAL_F) {
                 build_mixture(a, &sh, sh.xeval, gc, ptab, area);
                 __syncthreads();
+                PROF_T(pt_mix);
                 double sums[4] = {0, 0, 0, 0};
                 if (!sh.status)
                     value_pass<CV>(a, &sh, gc, ptab, val, ierr, rowd, cold,
                                    sums);
                 block_sum<4>(sums, scratch);
+                PROF_T(pt_pass);
                 if (threadIdx.x == 0) {
                     int acc = feed_residual(a, &sh, sh.xeval, sums[0],
                                             sh.status);
@@ -861,8 +879,19 @@ k_lm_fit(LMArgs a) {
                 for (int i = 0; i < a.np; i++) sh.xeval[i] = sh.st.xtrial[i];
             }
             __syncthreads();
+            PROF_T(pt_solve);
         }
+        PROF_T(pt_solve);
         if (threadIdx.x == 0) lm_finish(a, &sh, &a.res[stamp]);
+#ifdef NGX_PROF
+        PROF_T(pt_fin);
+        if (threadIdx.x == 0) {
+            double *o = a.res[stamp].pars_cov0 + 56;
+            o[0] = (double)pt_stage; o[1] = (double)pt_mix;
+            o[2] = (double)pt_pass; o[3] = (double)pt_solve;
+            o[4] = (double)pt_fin;
+        }
+#endif
     }
 }
 
@@ -950,7 +979,6 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     int threads = 128;
     if (a.ntot <= 1024) threads = 64;
     NGX_REQUIRE(threads >= a.ngauss && threads >= 6 * npsf);
-    const int CV = 3, CD = 2;
     // tiled pixel order: 4 x 8 tiles, one per warp
     a.tpr = (ncol + 7) / 8;
     a.nq = 32 * a.tpr * ((nrow + 3) / 4);
@@ -959,10 +987,27 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     size_t smem = sizeof(double)
         * ((size_t)nmix * a.ngauss * (16 + GC_STRIDE) + 2 * (size_t)a.nq
            + nrow + ncol + 48 * nwarps + 8);
-    if (analytic)
-        return config_and_launch(k_lm_fit<0, CV, CD>, a, threads, smem,
+    // tuning knob (experiments only): NGX_LM_VARIANT selects the register
+    // blocking / occupancy trade-off of the analytic kernel
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("NGX_LM_VARIANT");
+        variant = e ? atoi(e) : 0;
+    }
+    if (analytic) {
+        if (variant == 1)
+            return config_and_launch(k_lm_fit<0, 3, 3, 3>, a, threads, smem,
+                                     as_stream(stream));
+        if (variant == 2)
+            return config_and_launch(k_lm_fit<0, 4, 2, 3>, a, threads, smem,
+                                     as_stream(stream));
+        if (variant == 3)
+            return config_and_launch(k_lm_fit<0, 2, 1, 4>, a, threads, smem,
+                                     as_stream(stream));
+        return config_and_launch(k_lm_fit<0, 3, 2, 4>, a, threads, smem,
                                  as_stream(stream));
-    return config_and_launch(k_lm_fit<1, CV, CD>, a, threads, smem,
+    }
+    return config_and_launch(k_lm_fit<1, 3, 2, 4>, a, threads, smem,
                              as_stream(stream));
 }
 
@@ -988,6 +1033,8 @@ int ngx_lm_fit_host(int n, int model, const double *images,
     static thread_local double *d_guess[2] = {nullptr, nullptr};
     static thread_local ngx_lm_result *d_res[2] = {nullptr, nullptr};
     static thread_local size_t cap_pix = 0, cap_obj = 0, cap_psf = 0;
+    static thread_local ngx_lm_result *h_stage = nullptr;   // pinned
+    static thread_local size_t cap_stage = 0;
     static thread_local cudaStream_t streams[2] = {nullptr, nullptr};
     if (!streams[0]) {
         NGX_CUDA(cudaStreamCreate(&streams[0]));
@@ -1013,6 +1060,20 @@ int ngx_lm_fit_host(int n, int model, const double *images,
         }
         cap_pix = need_pix; cap_obj = need_obj; cap_psf = need_psf;
     }
+    // results: device -> pinned memory asynchronously.  If the caller's
+    // array is itself pinned it is the target, else a pinned staging buffer
+    // is copied out by the host while the next chunk runs.
+    cudaPointerAttributes attr;
+    bool res_pinned = cudaPointerGetAttributes(&attr, res) == cudaSuccess
+        && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!res_pinned && (size_t)n > cap_stage) {
+        if (h_stage) cudaFreeHost(h_stage);
+        NGX_CUDA(cudaMallocHost((void **)&h_stage,
+                                (size_t)n * sizeof(ngx_lm_result)));
+        cap_stage = n;
+    }
+    ngx_lm_result *res_dst = res_pinned ? res : h_stage;
     // the work-queue counter is shared by launches: serialise the kernels on
     // one stream (streams[0]) and use streams[1] only for copies
     cudaEvent_t up[2], done[2];
@@ -1052,13 +1113,23 @@ int ngx_lm_fit_host(int n, int model, const double *images,
                             prior, lm_pars, ignore_zero_weight, d_res[b],
                             streams[0]);
         if (rc) return rc;
-        NGX_CUDA(cudaMemcpyAsync(res + lo, d_res[b],
+        NGX_CUDA(cudaMemcpyAsync(res_dst + lo, d_res[b],
                                  cn * sizeof(ngx_lm_result),
                                  cudaMemcpyDeviceToHost, streams[0]));
         NGX_CUDA(cudaEventRecord(done[b], streams[0]));
+        if (!res_pinned && c > 0) {
+            // chunk c-1 is complete once its event fires; chunk c is queued
+            int pb = (c - 1) & 1, plo = (c - 1) * chunk;
+            NGX_CUDA(cudaEventSynchronize(done[pb]));
+            memcpy(res + plo, h_stage + plo, (size_t)chunk * sizeof(*res));
+        }
     }
     NGX_CUDA(cudaStreamSynchronize(streams[0]));
     NGX_CUDA(cudaStreamSynchronize(streams[1]));
+    if (!res_pinned) {
+        int plo = (nchunks - 1) * chunk;
+        memcpy(res + plo, h_stage + plo, (size_t)(n - plo) * sizeof(*res));
+    }
     for (int b = 0; b < 2; b++) {
         cudaEventDestroy(up[b]);
         cudaEventDestroy(done[b]);

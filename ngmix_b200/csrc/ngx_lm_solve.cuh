@@ -49,6 +49,14 @@ struct LMState {
     double R[LM_MAXP * LM_MAXP];   // column major, upper triangle = R
     int ipvt[LM_MAXP];
     double fnorm, xnorm, delta, par, gnorm, pnorm;
+    // workspace.  The state lives in shared memory on the device; keeping the
+    // temporaries here (not in per-thread local arrays) matters: local memory
+    // is interleaved by lane, so one thread walking a local array touches a
+    // new 128-byte line per element (ncu: 42% of the solver's stalls were
+    // long-scoreboard, 1.1 GB of DRAM traffic per launch).
+    double A[LM_MAXP * LM_MAXP], b[LM_MAXP];     // J^T J, J^T f
+    double T1[LM_MAXP * LM_MAXP], T2[LM_MAXP * LM_MAXP];
+    double v[10][LM_MAXP];
 };
 
 NGX_HD inline double lm_max(double a, double b) { return a >= b ? a : b; }
@@ -69,8 +77,7 @@ NGX_HD inline double lm_enorm(int n, const double *x) {
 // the largest remaining norm.  A non-positive pivot leaves a zero row (rank
 // deficiency), as qrfac leaves a zero diagonal.
 NGX_HD NGX_NI static void lm_pchol(int n, const double *A, double *R, int *ipvt,
-                            double *acnorm) {
-    double d[LM_MAXP];
+                            double *acnorm, double *d) {
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
         ipvt[j] = j;
@@ -194,9 +201,9 @@ NGX_HD NGX_NI static void lm_qrsolv(int n, double *r, const int *ipvt,
 // MINPACK lmpar
 NGX_HD NGX_NI static void lm_lmpar(int n, double *r, const int *ipvt,
                             const double *diag, const double *qtb,
-                            double delta, double *par, double *x) {
+                            double delta, double *par, double *x,
+                            double *sdiag, double *wa1, double *wa2) {
     const int ld = LM_MAXP;
-    double sdiag[LM_MAXP], wa1[LM_MAXP], wa2[LM_MAXP];
     int nsing = n;
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
@@ -322,8 +329,9 @@ NGX_HD NGX_NI static void lm_init(LMState *s, int n, const double *x0, int maxfe
 // compute the next trial point from the current factorisation (lmpar)
 NGX_HD NGX_NI static void lm_propose(LMState *s) {
     int n = s->n;
-    double p[LM_MAXP], wa3[LM_MAXP];
-    lm_lmpar(n, s->R, s->ipvt, s->diag, s->qtf, s->delta, &s->par, p);
+    double *p = s->v[4], *wa3 = s->v[5];
+    lm_lmpar(n, s->R, s->ipvt, s->diag, s->qtf, s->delta, &s->par, p,
+             s->v[1], s->v[2], s->v[3]);
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
         s->step[j] = -p[j];
@@ -355,7 +363,7 @@ NGX_HD NGX_NI static int lm_feed_f(LMState *s, double fnorm_new) {
         actred = 1.0 - r * r;
     }
     // |R P^T p|
-    double wa3[LM_MAXP];
+    double *wa3 = s->v[5];
 #pragma unroll 1
     for (int j = 0; j < n; j++) wa3[j] = 0.0;
 #pragma unroll 1
@@ -382,7 +390,7 @@ NGX_HD NGX_NI static int lm_feed_f(LMState *s, double fnorm_new) {
     }
     int accepted = 0;
     if (ratio >= 1.0e-4) {
-        double wa2[LM_MAXP];
+        double *wa2 = s->v[6];
 #pragma unroll 1
         for (int j = 0; j < n; j++) {
             s->x[j] = s->xtrial[j];
@@ -428,9 +436,9 @@ NGX_HD NGX_NI static void lm_feed_j(LMState *s, const double *A, const double *b
     int n = s->n;
     s->njev += 1;
     s->nfev += extra_nfev;
-    lm_pchol(n, A, s->R, s->ipvt, s->acnorm);
+    lm_pchol(n, A, s->R, s->ipvt, s->acnorm, s->v[0]);
     if (s->iter == 1) {
-        double wa3[LM_MAXP];
+        double *wa3 = s->v[5];
 #pragma unroll 1
         for (int j = 0; j < n; j++) {
             s->diag[j] = s->acnorm[j];
@@ -478,10 +486,10 @@ NGX_HD NGX_NI static void lm_feed_j(LMState *s, const double *A, const double *b
 
 // cov0 = (J^T J)^-1 = P R^-1 R^-T P^T from the last factorisation (row
 // major n x n out).  Returns 0 when R is singular (scipy: cov_x None).
-NGX_HD NGX_NI static int lm_cov0(const LMState *s, double *cov) {
+NGX_HD NGX_NI static int lm_cov0(LMState *s, double *cov) {
     int n = s->n;
     const int ld = LM_MAXP;
-    double rinv[LM_MAXP * LM_MAXP];
+    double *rinv = s->T1;
 #pragma unroll 1
     for (int j = 0; j < n; j++)
         if (s->R[j + ld * j] == 0.0) return 0;
@@ -518,7 +526,7 @@ NGX_HD NGX_NI static int lm_cov0(const LMState *s, double *cov) {
 // construction: a negative eigenvalue exists iff the matrix is not positive
 // semi-definite, decided by a Cholesky sweep with a rounding-level floor.
 // Returns flag bits (NEG_COV_EIG 1024, NEG_COV_DIAG 2048, EIG_NOTFINITE 8192)
-NGX_HD NGX_NI static int lm_test_cov(int n, const double *cov) {
+NGX_HD NGX_NI static int lm_test_cov(int n, const double *cov, double *L) {
     int flags = 0;
 #pragma unroll 1
     for (int i = 0; i < n * n; i++)
@@ -526,7 +534,6 @@ NGX_HD NGX_NI static int lm_test_cov(int n, const double *cov) {
 #pragma unroll 1
     for (int i = 0; i < n; i++)
         if (cov[i * n + i] < 0.0) flags |= 2048;
-    double L[LM_MAXP * LM_MAXP];
     double scale = 0.0;
 #pragma unroll 1
     for (int i = 0; i < n; i++) scale = lm_max(scale, fabs(cov[i * n + i]));

@@ -70,5 +70,6 @@ extern "C" int harness_lm_fit(int model, const ora_pixel *pixels, int npix,
 }
 
 extern "C" int harness_test_cov(int n, const double *cov) {
-    return ngx::lm_test_cov(n, cov);
+    double L[64];
+    return ngx::lm_test_cov(n, cov, L);
 }
