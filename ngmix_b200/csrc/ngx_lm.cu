@@ -24,6 +24,7 @@
 // block-reduces them with warp shuffles.  One thread then advances the
 // MINPACK state machine (ngx_lm_solve.cuh) while the other CTAs resident on
 // the SM keep the fp64 pipe busy.
+#include <cuda_pipeline.h>
 #include "ngx_core.cuh"
 #include "ngx_host.cuh"
 #include "ngx_lm_solve.cuh"
@@ -673,16 +674,31 @@ k_lm_fit(LMArgs a) {
         const double *im = a.images + (size_t)stamp * a.ntot;
         const double *wt = a.weights + (size_t)stamp * a.ntot;
         int cnt = 0, first = a.ntot, firstq = 0;
+        // all global loads of the stamp are issued as asynchronous 8-byte
+        // copies (LDGSTS) straight into their tiled shared-memory slots, so
+        // the ~36 loads per thread overlap instead of each waiting on DRAM
+        for (int q = threadIdx.x; q < a.nq; q += T) {
+            int row, col;
+            q_to_rowcol(q, a.tpr, &row, &col);
+            if (row < a.nrow && col < a.ncol) {
+                int p = row * a.ncol + col;
+                __pipeline_memcpy_async(&val[q], &im[p], sizeof(double));
+                __pipeline_memcpy_async(&ierr[q], &wt[p], sizeof(double));
+            }
+        }
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
+        // each thread converts the entries it fetched itself
         for (int q = threadIdx.x; q < a.nq; q += T) {
             int row, col;
             q_to_rowcol(q, a.tpr, &row, &col);
             double vv = 0.0, ie = 0.0;
             if (row < a.nrow && col < a.ncol) {
                 int p = row * a.ncol + col;
-                double w = wt[p];
+                double w = ierr[q];
                 bool valid = !(a.ignore_zero_weight && w <= 0.0);
                 if (valid) {
-                    vv = im[p];
+                    vv = val[q];
                     ie = sqrt(w < 0.0 ? 0.0 : w);
                     cnt++;
                     if (p < first) { first = p; firstq = q; }

@@ -116,6 +116,9 @@ NGX_HD NGX_NI static void lm_pchol(int n, const double *A, double *R, int *ipvt,
         }
         double rjj = sqrt(piv);
         R[j + LM_MAXP * j] = rjj;
+        // one reciprocal per row instead of a division per element: a double
+        // division is a ~30-instruction dependent sequence on this thread
+        double irjj = 1.0 / rjj;
         int pj = ipvt[j];
 #pragma unroll 1
         for (int k = j + 1; k < n; k++) {
@@ -124,7 +127,7 @@ NGX_HD NGX_NI static void lm_pchol(int n, const double *A, double *R, int *ipvt,
 #pragma unroll 1
             for (int i = 0; i < j; i++)
                 s -= R[i + LM_MAXP * j] * R[i + LM_MAXP * k];
-            double rjk = s / rjj;
+            double rjk = s * irjj;
             R[j + LM_MAXP * k] = rjk;
             d[k] -= rjk * rjk;
         }
@@ -458,19 +461,17 @@ NGX_HD NGX_NI static void lm_feed_j(LMState *s, const double *A, const double *b
         for (int i = 0; i < j; i++) v -= s->R[i + LM_MAXP * j] * s->qtf[i];
         s->qtf[j] = (rjj != 0.0) ? v / rjj : 0.0;
     }
-    // gnorm = max_j |(J^T f)_j| / (acnorm_j |f|)
+    // gnorm = max_j |(J^T f)_j| / (acnorm_j |f|).  MINPACK forms (J^T f)_j as
+    // sum_i R[i,j] qtf[i]/|f|; that is b[ipvt_j]/|f| exactly, and gnorm only
+    // feeds the gnorm <= gtol (= 0) and gnorm <= eps tests
     double gnorm = 0.0;
     if (s->fnorm != 0.0) {
+        double ifnorm = 1.0 / s->fnorm;
 #pragma unroll 1
         for (int j = 0; j < n; j++) {
             int l = s->ipvt[j];
-            if (s->acnorm[l] != 0.0) {
-                double sum = 0.0;
-#pragma unroll 1
-                for (int i = 0; i <= j; i++)
-                    sum += s->R[i + LM_MAXP * j] * (s->qtf[i] / s->fnorm);
-                gnorm = lm_max(gnorm, fabs(sum / s->acnorm[l]));
-            }
+            if (s->acnorm[l] != 0.0)
+                gnorm = lm_max(gnorm, fabs((b[l] * ifnorm) / s->acnorm[l]));
         }
     }
     s->gnorm = gnorm;
