@@ -315,6 +315,36 @@ def main():
               + h_psf.numel() * 8 + h_guess.numel() * 8)
     d2h = int(nobj * _lib.LM_RESULT_DTYPE.itemsize)
 
+    # ---- the stand-alone fdiff kernel (fill_fdiff + get_loglike fused,
+    # ngx_loglike) on the same stamps, at the guess mixtures
+    gm0, _ = _lib.gmix_fill("exp", b["guess"])
+    gp, _ = _lib.gmix_fill("full", b["psf"].reshape(nobj, -1))
+    gmc = _lib.gmix_convolve(gm0, gp)
+    _lib.gmix_set_norms(gmc)
+    d_gm = torch.from_numpy(
+        np.frombuffer(gmc.tobytes(), dtype=np.uint8).copy()).to(dev)
+    d_out4 = torch.zeros(nobj * 4, dtype=torch.float64, device=dev)
+    d_fd = torch.zeros(nobj * H * Wd, dtype=torch.float64, device=dev)
+
+    def step_fdiff():
+        _lib.loglike_device(nobj, NGAUSS, d_gm.data_ptr(),
+                            d_images.data_ptr(), d_weights.data_ptr(),
+                            d_jac.data_ptr(), H, Wd, d_out4.data_ptr(),
+                            d_fdiff=d_fd.data_ptr(),
+                            stream=stream.cuda_stream)
+
+    for _ in range(W):
+        step_fdiff()
+    torch.cuda.synchronize()
+    f0 = torch.cuda.Event(enable_timing=True)
+    f1 = torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(args.steps):
+        step_fdiff()
+    f1.record(stream)
+    torch.cuda.synchronize()
+    fdiff_ms = f0.elapsed_time(f1) / args.steps
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -361,7 +391,7 @@ def main():
                 "d2h_bytes_per_step": d2h,
                 "api": "ngmix_b200._lib.lm_fit -> ngx_lm_fit_host (pinned "
                        "host buffers, chunked H2D overlapped with the fit)"},
-        "gpu_launches": args.steps,
+        "gpu_launches": args.steps,   # k_lm_fit launches in the timed region
         "roofline": {
             "bound": "fp64", "achieved": achieved / 1e9,
             "peak": peak_flops / 1e9, "unit": "GFLOP/s",
@@ -377,6 +407,18 @@ def main():
             "hbm_achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9,
             "hbm_frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
             "traffic": None,
+        },
+        "fdiff_kernel": {
+            "kernel": "k_loglike_tiled (ngx_loglike: fill_fdiff + "
+                      "get_loglike + get_model_s2n_sum in one pass)",
+            "ms": fdiff_ms,
+            "model_pixel_evals_per_s": nobj * npix / (fdiff_ms * 1e-3),
+            "gaussian_pixel_evals_per_s": nobj * npix * NGAUSS
+            / (fdiff_ms * 1e-3),
+            "frac_fp64_flops": nobj * npix * NGAUSS * FLOPS_VALUE
+            / (fdiff_ms * 1e-3) / peak_flops,
+            "frac_fp64_instr": nobj * npix * NGAUSS * INSTR_VALUE
+            / (fdiff_ms * 1e-3) / dfma_per_s,
         },
         "clocks": clocks,
     }

@@ -470,3 +470,15 @@ def admom_device(n, d_images, d_weights, d_jac, nrow, ncol, d_guess, d_res,
         C.c_int(n), C.c_void_p(d_images), C.c_void_p(d_weights),
         C.c_void_p(d_jac), C.c_int(nrow), C.c_int(ncol), C.c_void_p(d_guess),
         C.byref(conf), C.c_void_p(d_res), C.c_void_p(stream)))
+
+
+def loglike_device(n, ngauss, d_gmix, d_images, d_weights, d_jac, nrow, ncol,
+                   d_out4, d_fdiff=0, d_status=0, ignore_zero_weight=True,
+                   stream=0):
+    """device-pointer fused fdiff/loglike/s2n pass (asynchronous)"""
+    check(lib().ngx_loglike(
+        C.c_int(n), C.c_int(ngauss), C.c_void_p(d_gmix),
+        C.c_void_p(d_images), C.c_void_p(d_weights), C.c_void_p(d_jac),
+        C.c_int(nrow), C.c_int(ncol), C.c_int(int(ignore_zero_weight)),
+        C.c_void_p(d_out4), C.c_void_p(d_fdiff) if d_fdiff else None,
+        C.c_void_p(d_status) if d_status else None, C.c_void_p(stream)))

@@ -204,6 +204,25 @@ __device__ __forceinline__ double eval_exact(const ngx_gauss &g, double v,
     return g.pnorm * exp(-0.5 * chi2) * area;
 }
 
+// tiled index q -> (row, col); tiles are 4 rows x 8 cols, row-band major
+__device__ __forceinline__ void q_to_rowcol(int q, int tpr, int *row,
+                                            int *col) {
+    int tile = q >> 5, w = q & 31;
+    int trow = tile / tpr, tcol = tile - trow * tpr;
+    *row = (trow << 2) + (w >> 3);
+    *col = (tcol << 3) + (w & 7);
+}
+
+// exp part of one evaluation for a lane that may be out of range: the table
+// index is clamped so the shared-memory read stays in bounds and the result
+// is only used under the in-range predicate.
+__device__ __forceinline__ double fexp_tab(double x, const double *tab) {
+    int idx;
+    double f = fexp_reduce(x, &idx);
+    idx = min((unsigned)idx, 15u);
+    return tab[idx] * fexp_poly(f);
+}
+
 // ---------------------------------------------------------------------
 // gauss2d_set (gmix_nb.py:221-240)
 __device__ __forceinline__ void gauss_set(ngx_gauss &g, double p, double row,

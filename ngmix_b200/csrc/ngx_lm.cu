@@ -64,15 +64,6 @@ struct LMShared {
     int warp_i[32], warp_j[32], warp_k[32];
 };
 
-// tiled index q -> (row, col); tiles are 4 rows x 8 cols, row-band major
-__device__ __forceinline__ void q_to_rowcol(int q, int tpr, int *row,
-                                            int *col) {
-    int tile = q >> 5, w = q & 31;
-    int trow = tile / tpr, tcol = tile - trow * tpr;
-    *row = (trow << 2) + (w >> 3);
-    *col = (tcol << 3) + (w & 7);
-}
-
 // ---------------------------------------------------------------------
 // build the convolved mixture for parameters x: thread k < ngauss owns
 // composed gaussian k = iobj*npsf + ipsf (gmix_convolve_fill's order).
@@ -135,16 +126,6 @@ __device__ __forceinline__ void coords_of(const LMArgs &a, const LMShared *sh,
     } else {
         *v = 1.0e10; *u = 1.0e10;     // padding: far outside any footprint
     }
-}
-
-// exp part of one evaluation for a lane that may be out of range: the table
-// index is clamped so the shared-memory read stays in bounds and the result
-// is only used under the in-range predicate.
-__device__ __forceinline__ double fexp_tab(double x, const double *tab) {
-    int idx;
-    double f = fexp_reduce(x, &idx);
-    idx = min((unsigned)idx, 15u);
-    return tab[idx] * fexp_poly(f);
 }
 
 // ---------------------------------------------------------------------
@@ -638,8 +619,8 @@ __device__ __noinline__ int feed_residual(const LMArgs &a, LMShared *sh,
 // ---------------------------------------------------------------------
 // MODE 0: analytic Jacobian (gauss/exp/dev), np = 6
 // MODE 1: forward differences (any model), np <= 8
-template <int MODE, int CV, int CD, int MINB>
-__global__ void __launch_bounds__(128, MINB)
+template <int MODE, int CV, int CD, int MINB, int NT = 128>
+__global__ void __launch_bounds__(NT, MINB)
 k_lm_fit(LMArgs a) {
     extern __shared__ double smem_d[];
     __shared__ LMShared sh;
@@ -1020,6 +1001,19 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
         if (variant == 3)
             return config_and_launch(k_lm_fit<0, 2, 1, 4>, a, threads, smem,
                                      as_stream(stream));
+        if (variant == 4 || variant == 5) {
+            // 6 warps per CTA at <= 85 registers
+            threads = 192;
+            nwarps = 6;
+            smem = sizeof(double)
+                * ((size_t)nmix * a.ngauss * (16 + GC_STRIDE)
+                   + 2 * (size_t)a.nq + nrow + ncol + 48 * nwarps + 8);
+            if (variant == 4)
+                return config_and_launch(k_lm_fit<0, 3, 2, 4, 192>, a,
+                                         threads, smem, as_stream(stream));
+            return config_and_launch(k_lm_fit<0, 2, 1, 4, 192>, a, threads,
+                                     smem, as_stream(stream));
+        }
         return config_and_launch(k_lm_fit<0, 3, 2, 4>, a, threads, smem,
                                  as_stream(stream));
     }

@@ -415,6 +415,188 @@ __global__ void k_loglike(int ngauss, const ngx_gauss *__restrict__ gmix,
 }
 
 // ---------------------------------------------------------------------
+// The same fused pass for image/weight/jacobian input, organised like the
+// value pass of the LM kernel: pixels in TILED order (4 rows x 8 columns per
+// warp tile) so that a gaussian whose chi^2 < 25 footprint misses the tile is
+// skipped with one vote, gaussians in the outer loop with their constants and
+// a pn*exp(i) table in shared memory, C pixels per thread in registers.
+// fdiff keeps the reference's order (row-major over the positive-weight
+// pixels): a ballot pre-pass counts the valid pixels of every 8-pixel row
+// segment, prefix sums give each segment's offset.
+#define LLT_C 3
+__global__ void __launch_bounds__(256, 3)
+k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
+                const double *__restrict__ images,
+                const double *__restrict__ weights,
+                const ngx_jacobian *__restrict__ jac, int nrow, int ncol,
+                int tpr, int nq, int ignore_zero_weight,
+                double *__restrict__ out4, double *__restrict__ fdiff,
+                int32_t *__restrict__ status) {
+    extern __shared__ double smem_d[];
+    double *scratch = smem_d;                   // 4 * 32
+    double *gc = scratch + 4 * 32;              // ngauss * 6
+    double *ptab = gc + 6 * ngauss;             // ngauss * 16
+    int *segoff = (int *)(ptab + 16 * ngauss);  // nrow * tpr
+    int *rowoff = segoff + nrow * tpr;          // nrow
+    __shared__ int bad;
+    const int T = blockDim.x;
+    const int obj = blockIdx.x;
+    const int ntot = nrow * ncol;
+    const int lane = threadIdx.x & 31;
+    const ngx_jacobian j = jac[obj];
+    const double area = j.scale * j.scale;
+    const double *im = images + (size_t)obj * ntot;
+    const double *wt = weights + (size_t)obj * ntot;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < ngauss; k += T) {
+        ngx_gauss g = gmix[(size_t)obj * ngauss + k];
+        if (gauss_set_norm(g) != NGX_ST_OK) bad = 1;
+        double *c = gc + 6 * k;
+        c[0] = g.row; c[1] = g.col;
+        c[2] = -0.5 * g.dcc; c[3] = -0.5 * g.drr; c[4] = g.drc;
+        double pn = g.pnorm * area;
+        for (int t = 0; t < 16; t++) ptab[16 * k + t] = c_exp_lookup[t] * pn;
+    }
+    if (fdiff) {
+        // valid pixels per 8-pixel row segment
+        for (int base = 0; base < nq; base += T) {
+            int q = base + threadIdx.x;
+            int row, col;
+            q_to_rowcol(q, tpr, &row, &col);
+            bool valid = false;
+            if (q < nq && row < nrow && col < ncol) {
+                double w = wt[row * ncol + col];
+                valid = !(ignore_zero_weight && w <= 0.0);
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, valid);
+            if ((lane & 7) == 0 && q < nq && row < nrow)
+                segoff[row * tpr + (col >> 3)] =
+                    __popc((bal >> (lane & 24)) & 0xffu);
+        }
+    }
+    __syncthreads();
+    if (bad) {
+        if (threadIdx.x == 0) {
+            if (status) status[obj] = NGX_ST_RANGE_ERROR;
+            for (int q = 0; q < 4; q++) out4[4 * (size_t)obj + q] = nan("");
+        }
+        return;
+    }
+    if (fdiff) {
+        for (int r = threadIdx.x; r < nrow; r += T) {
+            int run = 0;
+            for (int t = 0; t < tpr; t++) {
+                int c = segoff[r * tpr + t];
+                segoff[r * tpr + t] = run;
+                run += c;
+            }
+            rowoff[r] = run;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int run = 0;
+            for (int r = 0; r < nrow; r++) {
+                int c = rowoff[r];
+                rowoff[r] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+    }
+    double sums[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int base = 0; base < nq; base += T * LLT_C) {
+        double v[LLT_C], u[LLT_C], acc[LLT_C];
+#pragma unroll
+        for (int c = 0; c < LLT_C; c++) {
+            int q = base + c * T + threadIdx.x;
+            int row, col;
+            q_to_rowcol(q, tpr, &row, &col);
+            acc[c] = 0.0;
+            if (q < nq && row < nrow && col < ncol)
+                pixel_vu(j, row, col, &v[c], &u[c]);
+            else
+                v[c] = u[c] = 1.0e10;
+        }
+#pragma unroll 1
+        for (int k = 0; k < ngauss; k++) {
+            const double *g = gc + 6 * k;
+            const double *tab = ptab + 16 * k;
+            double grow = g[0], gcol = g[1], ga = g[2], gb = g[3], gcx = g[4];
+            double x[LLT_C];
+            bool inr[LLT_C], any = false, anyapod = false;
+#pragma unroll
+            for (int c = 0; c < LLT_C; c++) {
+                double dv = v[c] - grow;
+                double du = u[c] - gcol;
+                double t = fma(gcx, du, ga * dv);
+                x[c] = fma(gb * du, du, dv * t);
+                inr[c] = x_in_range(x[c]);
+                any |= inr[c];
+                anyapod |= inr[c] && x_in_apod(x[c]);
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;   // warp-uniform
+            double e[LLT_C];
+#pragma unroll
+            for (int c = 0; c < LLT_C; c++) e[c] = fexp_tab(x[c], tab);
+            if (__any_sync(0xffffffffu, anyapod)) {
+#pragma unroll
+                for (int c = 0; c < LLT_C; c++) {
+                    bool ap = inr[c] && x_in_apod(x[c]);
+                    if (__any_sync(0xffffffffu, ap)) {
+                        double w = apod_window_fast(x[c]);
+                        if (ap) e[c] *= w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < LLT_C; c++)
+                if (inr[c]) acc[c] += e[c];
+        }
+#pragma unroll
+        for (int c = 0; c < LLT_C; c++) {
+            int q = base + c * T + threadIdx.x;
+            int row, col;
+            q_to_rowcol(q, tpr, &row, &col);
+            bool valid = false;
+            double d = 0.0, ie = 0.0;
+            if (q < nq && row < nrow && col < ncol) {
+                int p = row * ncol + col;
+                double w = wt[p];
+                valid = !(ignore_zero_weight && w <= 0.0);
+                if (valid) {
+                    d = im[p];
+                    ie = sqrt(w < 0.0 ? 0.0 : w);
+                }
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                double ivar = ie * ie;
+                double diff = acc[c] - d;
+                sums[0] += diff * diff * ivar;
+                sums[1] += d * acc[c] * ivar;
+                sums[2] += acc[c] * acc[c] * ivar;
+                sums[3] += 1.0;
+                if (fdiff) {
+                    unsigned seg = (bal >> (lane & 24)) & 0xffu;
+                    int pos = rowoff[row] + segoff[row * tpr + (col >> 3)]
+                        + __popc(seg & ((1u << (lane & 7)) - 1u));
+                    fdiff[(size_t)obj * ntot + pos] = diff * ie;
+                }
+            }
+        }
+    }
+    block_sum<4>(sums, scratch);
+    if (threadIdx.x == 0) {
+        out4[4 * (size_t)obj + 0] = -0.5 * sums[0];
+        out4[4 * (size_t)obj + 1] = sums[1];
+        out4[4 * (size_t)obj + 2] = sums[2];
+        out4[4 * (size_t)obj + 3] = sums[3];
+        if (status) status[obj] = NGX_ST_OK;
+    }
+}
+
+// ---------------------------------------------------------------------
 // deriv_images, derivs_nb.py:40-127, in the reference's own operation
 // order (this entry point exists for parity of the derivative math; the LM
 // kernel uses the restructured form in ngx_lm.cu).
@@ -646,11 +828,16 @@ static int launch_loglike(int src, int n, int ngauss, const ngx_gauss *gmix,
     int ntot = src == 0 ? nrow * ncol : maxpix;
     int threads = 256;
     if (ntot <= 1024) threads = 128;
-    if (src == 0)
-        k_loglike<0><<<n, threads, smem, as_stream(stream)>>>(
-            ngauss, gmix, images, weights, jac, nrow, ncol,
-            ignore_zero_weight, nullptr, 0, nullptr, out4, fdiff, status);
-    else
+    if (src == 0) {
+        int tpr = (ncol + 7) / 8;
+        int nq = 32 * tpr * ((nrow + 3) / 4);
+        size_t smt = sizeof(double) * (4 * 32 + 22 * (size_t)ngauss)
+            + sizeof(int) * ((size_t)nrow * tpr + nrow);
+        NGX_REQUIRE(smt <= 48 * 1024);
+        k_loglike_tiled<<<n, 256, smt, as_stream(stream)>>>(
+            ngauss, gmix, images, weights, jac, nrow, ncol, tpr, nq,
+            ignore_zero_weight, out4, fdiff, status);
+    } else
         k_loglike<1><<<n, threads, smem, as_stream(stream)>>>(
             ngauss, gmix, nullptr, nullptr, nullptr, 0, 0, 0, pixels, maxpix,
             npix, out4, fdiff, status);
