@@ -348,8 +348,10 @@ def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
     if psf_pars is None:
         npsf = 0
     else:
-        psf_pars = _f8(psf_pars).reshape(n, -1, 6)
-        npsf = psf_pars.shape[1]
+        psf_pars = _f8(psf_pars)
+        npsf = psf_pars.shape[1] if psf_pars.ndim == 3 \
+            else psf_pars.size // max(6 * n, 1)
+        psf_pars = psf_pars.reshape(n, npsf, 6)
     pr = prior if prior is not None else Prior()
     lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)
     if out is None:
@@ -396,13 +398,17 @@ def em(images, weights, jac, guess, psf_pars=None, variant="full",
         images, weights = images[None], weights[None]
     n, H, W = images.shape
     jac = as_jac(jac, n)
-    guess = _f8(guess).reshape(n, -1, 6)
-    ngauss = guess.shape[1]
+    guess = _f8(guess)
+    ngauss = guess.shape[1] if guess.ndim == 3 \
+        else guess.size // max(6 * n, 1)
+    guess = guess.reshape(n, ngauss, 6)
     if psf_pars is None:
         npsf = 0
     else:
-        psf_pars = _f8(psf_pars).reshape(n, -1, 6)
-        npsf = psf_pars.shape[1]
+        psf_pars = _f8(psf_pars)
+        npsf = psf_pars.shape[1] if psf_pars.ndim == 3 \
+            else psf_pars.size // max(6 * n, 1)
+        psf_pars = psf_pars.reshape(n, npsf, 6)
     if miniter is None:
         miniter = 20 if variant == "fluxonly" else 40
     conf = EMConf(tol, maxiter, miniter, 0.0 if sky is None else sky,

@@ -1034,8 +1034,13 @@ int ngx_lm_fit_host(int n, int model, const double *images,
     // chunked, double-buffered pipeline: H2D of chunk i+1 overlaps the fit
     // of chunk i when the host arrays are pinned
     const size_t ntot = (size_t)nrow * ncol;
-    int chunk = 2048;
+    // chunk schedule: a short first chunk (one wave of CTAs) so the first
+    // kernel starts after ~20 MB of H2D instead of a full chunk, then chunks
+    // of four waves
+    const int wave = 4 * sm_count();
+    int chunk = 4 * wave;
     if (chunk > n) chunk = n;
+    int first_chunk = wave < chunk ? wave : chunk;
     static thread_local double *d_im[2] = {nullptr, nullptr};
     static thread_local double *d_wt[2] = {nullptr, nullptr};
     static thread_local ngx_jacobian *d_jac[2] = {nullptr, nullptr};
@@ -1091,11 +1096,11 @@ int ngx_lm_fit_host(int n, int model, const double *images,
         NGX_CUDA(cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming));
         NGX_CUDA(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
     }
-    int nchunks = (n + chunk - 1) / chunk;
+    int nchunks = 1 + (n - first_chunk + chunk - 1) / chunk;
     for (int c = 0; c < nchunks; c++) {
         int b = c & 1;
-        int lo = c * chunk;
-        int cn = n - lo < chunk ? n - lo : chunk;
+        int lo = c == 0 ? 0 : first_chunk + (c - 1) * chunk;
+        int cn = c == 0 ? first_chunk : (n - lo < chunk ? n - lo : chunk);
         // buffer b is free once the kernel of chunk c-2 has finished and its
         // results were copied out (both on streams[0])
         NGX_CUDA(cudaStreamWaitEvent(streams[1], done[b], 0));
@@ -1129,15 +1134,16 @@ int ngx_lm_fit_host(int n, int model, const double *images,
         NGX_CUDA(cudaEventRecord(done[b], streams[0]));
         if (!res_pinned && c > 0) {
             // chunk c-1 is complete once its event fires; chunk c is queued
-            int pb = (c - 1) & 1, plo = (c - 1) * chunk;
+            int pb = (c - 1) & 1;
+            int plo = c == 1 ? 0 : first_chunk + (c - 2) * chunk;
             NGX_CUDA(cudaEventSynchronize(done[pb]));
-            memcpy(res + plo, h_stage + plo, (size_t)chunk * sizeof(*res));
+            memcpy(res + plo, h_stage + plo, (size_t)(lo - plo) * sizeof(*res));
         }
     }
     NGX_CUDA(cudaStreamSynchronize(streams[0]));
     NGX_CUDA(cudaStreamSynchronize(streams[1]));
     if (!res_pinned) {
-        int plo = (nchunks - 1) * chunk;
+        int plo = nchunks == 1 ? 0 : first_chunk + (nchunks - 2) * chunk;
         memcpy(res + plo, h_stage + plo, (size_t)(n - plo) * sizeof(*res));
     }
     for (int b = 0; b < 2; b++) {

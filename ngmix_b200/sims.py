@@ -293,3 +293,62 @@ def make_bdf_batch(n, seed0=0, dims=(64, 64), noise=0.01, scale=0.263,
             images[i] = im + rng.normal(0.0, noise, size=im.shape)
     return dict(images=images, weights=weights, jac=jac, psf=psf,
                 truth=truth, guess=guess, model="bdf", noise=noise)
+
+
+def _shear_full_pars(full, s1, s2):
+    """apply reduced shear (s1, s2) to every gaussian of [n,6] full pars, as
+    GMix.get_sheared does (ngmix/gmix/gmix.py:478-516)"""
+    from .shape import get_sheared_moments
+    out = full.copy()
+    for k in range(full.shape[0]):
+        out[k, 3], out[k, 4], out[k, 5] = get_sheared_moments(
+            full[k, 3], full[k, 4], full[k, 5], s1, s2)
+    return out
+
+
+METACAL_TYPES = (("noshear", 0.0, 0.0), ("1p", 0.01, 0.0), ("1m", -0.01, 0.0),
+                 ("2p", 0.0, 0.01), ("2m", 0.0, -0.01))
+
+
+def make_metacal_batch(nobj, seed0=0, dims=(48, 48), noise=0.01, scale=0.263,
+                       guess_frac=0.05):
+    """
+    Config 5 batch: per object 5 stamps (noshear, 1p, 1m, 2p,
+    2m) - the exp truth sheared by +-0.01, convolved with a round 1-gaussian
+    reconvolution PSF (T = 0.35), the SAME noise field on all five - to be
+    fit as 5*nobj independent exp LM fits.  Stamp order is object-major.
+    """
+    H, W = dims
+    n = 5 * nobj
+    images = np.zeros((n, H, W))
+    weights = np.zeros((n, H, W)) + 1.0 / noise ** 2
+    jac = np.zeros((n, 8))
+    psf = np.zeros((n, 1, 6))
+    guess = np.zeros((n, 6))
+    truth = np.zeros((nobj, 6))
+    for i in range(nobj):
+        rng = np.random.RandomState(seed0 + i)
+        dy, dx = rng.uniform(-0.5, 0.5, size=2)
+        j = diag_jacobian((H - 1) / 2 + dy, (W - 1) / 2 + dx, scale)
+        while True:
+            g1, g2 = rng.normal(0.0, 0.15, size=2)
+            if np.hypot(g1, g2) < 0.6:
+                break
+        truth[i] = (0.0, 0.0, g1, g2, rng.uniform(0.15, 1.0),
+                    rng.uniform(50.0, 200.0))
+        ppars = simple_full_pars([0.0, 0.0, 0.0, 0.0, 0.35, 1.0], "gauss")
+        g0 = np.zeros(6)
+        g0[0:2] = rng.uniform(-0.01, 0.01, size=2)
+        g0[2:] = truth[i, 2:] * (1.0 + rng.uniform(-guess_frac, guess_frac,
+                                                   size=4))
+        noise_im = rng.normal(0.0, noise, size=(H, W))
+        full0 = simple_full_pars(truth[i], "exp")
+        for k, (_, s1, s2) in enumerate(METACAL_TYPES):
+            full = convolve_full_pars(_shear_full_pars(full0, s1, s2), ppars)
+            m = 5 * i + k
+            images[m] = render_full_pars(full, dims, j) + noise_im
+            jac[m] = j
+            psf[m] = ppars
+            guess[m] = g0
+    return dict(images=images, weights=weights, jac=jac, psf=psf,
+                guess=guess, truth=truth, model="exp", noise=noise)
