@@ -154,6 +154,101 @@ __device__ __forceinline__ bool x_in_apod(double x) {
 }
 
 // ---------------------------------------------------------------------
+// The hot-loop form of fexp.  Everything that is not fp64 arithmetic is
+// squeezed out of the per-evaluation path:
+//  * the quintic's coefficients are constant-bank operands of the DFMAs
+//    (a literal costs two 32-bit moves per use once registers run short);
+//  * the range tests work on the high word of y = x - 1/2, which the range
+//    reduction needs anyway: with hy = hi(y) - hi(-1/2) (unsigned)
+//        0 <= chi2 < 25  <=>  -13 < y <= -1/2  <=>  hy < NGX_HY_RANGE
+//        chi2 >= 20      <=>  y <= -10.5       <=>  hy >= NGX_HY_APOD
+//    (x - 1/2 is exact on these boundaries; chi2 == 20 has window 1 and slope
+//    0 exactly, so including it in the band changes nothing), and x <= 0 is
+//    one signed compare of hi(x);
+//  * the per-gaussian table pn*exp(i) is stored ROTATED, slot = ival & 15
+//    (ival in [-12, 0] uses slots 0 and 4..15), and slot 1 holds 0.0: a lane
+//    outside the footprint reads slot 1, so its value is an exact zero without
+//    selects on the 64-bit result.
+__constant__ double c_fexp_c[6] = {NGX_C0, NGX_C1, NGX_C2,
+                                   NGX_C3, NGX_C4, NGX_C5};
+#define NGX_HY_BASE 0xBFE00000u
+#define NGX_HY_RANGE 0x004A0000u      // hi(-13) - hi(-1/2)
+#define NGX_HY_APOD 0x00450000u       // hi(-10.5) - hi(-1/2)
+#define NGX_TAB_ZERO 1u
+
+__device__ __forceinline__ double fexp_poly_c(double f) {
+    double p = fma(f, c_fexp_c[5], c_fexp_c[4]);
+    p = fma(f, p, c_fexp_c[3]);
+    p = fma(f, p, c_fexp_c[2]);
+    p = fma(f, p, c_fexp_c[1]);
+    p = fma(f, p, c_fexp_c[0]);
+    return p;
+}
+
+// range reduction + range tests; returns f, the table slot, and the
+// in-range / in-apodization-band predicates
+__device__ __forceinline__ double fexp_split(double x, unsigned *slot,
+                                             bool *inr, bool *ap) {
+    double y = __dadd_rn(x, -0.5);
+    unsigned hy = (unsigned)__double2hiint(y) - NGX_HY_BASE;
+    bool in = (hy < NGX_HY_RANGE) && (__double2hiint(x) <= 0);
+    *inr = in;
+    *ap = in && (hy >= NGX_HY_APOD);
+    double t = __dadd_ru(y, NGX_MAGIC);
+    *slot = in ? ((unsigned)__double2loint(t) & 15u) : NGX_TAB_ZERO;
+    double r = __dadd_rn(t, -NGX_MAGIC);
+    return __dadd_rn(x, -r);
+}
+
+// fill one gaussian's rotated table (16 doubles)
+__device__ __forceinline__ void fill_rot_table(double *tab, double pn) {
+#pragma unroll
+    for (int t = 0; t < 16; t++)
+        tab[(t + 1) & 15] = (t >= 3) ? c_exp_lookup[t] * pn : 0.0;
+}
+
+// apodization window and the combination w - 2 w' the derivative images
+// need (derivs_nb.py:104-108), sharing u = (25 - chi2) / 5:
+//   w = u^3 (10 - 15 u + 6 u^2),  w' = -6 (u (1 - u))^2
+__device__ __forceinline__ void apod_pair(double x, double *w, double *wc) {
+    double u = fma(0.4, x, 5.0);
+    double t = fma(fma(6.0, u, -15.0), u, 10.0);
+    double ww = (u * u) * (u * t);
+    double umu = fma(-u, u, u);
+    *w = ww;
+    *wc = fma(12.0 * umu, umu, ww);
+}
+
+// 4 x 8 pixel tile -> centre and half extents in (v, u)
+__device__ __forceinline__ void tile_extent(const ngx_jacobian &j, int tile,
+                                            int tpr, int nrow, int ncol,
+                                            double *vc, double *uc,
+                                            double *hv, double *hu) {
+    int trow = tile / tpr, tcol = tile - trow * tpr;
+    int r0 = trow << 2, c0 = tcol << 3;
+    int r1 = min(r0 + 3, nrow - 1), c1 = min(c0 + 7, ncol - 1);
+    double rc = 0.5 * (r0 + r1) - j.row0, cc = 0.5 * (c0 + c1) - j.col0;
+    double hr = 0.5 * (r1 - r0), hc = 0.5 * (c1 - c0);
+    *vc = j.dvdrow * rc + j.dvdcol * cc;
+    *uc = j.dudrow * rc + j.dudcol * cc;
+    *hv = fabs(j.dvdrow) * hr + fabs(j.dvdcol) * hc;
+    *hu = fabs(j.dudrow) * hr + fabs(j.dudcol) * hc;
+}
+
+// does the chi2 < 25 footprint of a gaussian at (row, col) with
+// rv = 5 sqrt(irr), ru = 5 sqrt(icc) possibly meet the tile?  chi2 < 25
+// implies |dv| < rv and |du| < ru; the margins cover rounding, and anything
+// not finite counts as a hit.
+__device__ __forceinline__ bool tile_hit(double vc, double uc, double hv,
+                                         double hu, double row, double col,
+                                         double rv, double ru) {
+    double dv = fabs(vc - row), du = fabs(uc - col);
+    double tv = (rv + hv) * (1.0 + 1.0e-9) + 1.0e-9 * (fabs(vc) + fabs(row));
+    double tu = (ru + hu) * (1.0 + 1.0e-9) + 1.0e-9 * (fabs(uc) + fabs(col));
+    return !(dv > tv) && !(du > tu);
+}
+
+// ---------------------------------------------------------------------
 // per-gaussian constants for the value pass:
 //   x = -chi2/2 = a dv^2 + b du^2 + c dv du,  value = pn * fexp(x)
 struct GaussV {

@@ -776,6 +776,7 @@ int ngx_em_host(int n, int variant, const double *images,
                 int ignore_zero_weight, double *pars_out,
                 ngx_em_result *res) {
     NGX_REQUIRE(n >= 0 && images && weights && jac && guess && conf);
+    if (n == 0) return NGX_OK;
     size_t ntot = (size_t)n * nrow * ncol;
     DevBuf<double> di(ntot, images), dw(ntot, weights);
     DevBuf<ngx_jacobian> dj(n, jac);
@@ -801,6 +802,7 @@ int ngx_admom_host(int n, const double *images, const double *weights,
                    const double *guess, const ngx_admom_conf *conf,
                    ngx_admom_result *res) {
     NGX_REQUIRE(n >= 0 && images && weights && jac && guess && conf && res);
+    if (n == 0) return NGX_OK;
     size_t ntot = (size_t)n * nrow * ncol;
     DevBuf<double> di(ntot, images), dw(ntot, weights);
     DevBuf<ngx_jacobian> dj(n, jac);

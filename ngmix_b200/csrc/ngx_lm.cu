@@ -37,9 +37,13 @@ namespace ngx {
 #define NGX_BIGVAL (9999.0e47)
 
 // per-gaussian constants in shared memory + 16-entry table pn*exp(i)
-//   0 row, 1 col, 2 a=-dcc/2, 3 b=-drr/2, 4 c2=drc/2, 5 h=Tk/2,
-//   6 c=drc, 7 ha=a/2, 8 hb=b/2, 9 qc=c2/2
-#define GC_STRIDE 10
+//   0 row, 1 col, 2 a=-dcc/2, 3 b=-drr/2, 4 c2=drc/2, 5 c=drc, 6 h=Tk/2,
+//   7 qc=c2/2, 8 ha=a/2, 9 hb=b/2, 10 hb-ha, 11 hb+ha,
+//   12 rv=5 sqrt(irr), 13 ru=5 sqrt(icc)
+// (pairs are read as 16-byte shared-memory loads).  One record per gaussian:
+// the 16-entry rotated pn*exp(i) table followed by the constants.
+#define GC_STRIDE 14
+#define REC (16 + GC_STRIDE)
 
 struct LMArgs {
     int n, model, np, ngauss0, npsf, ngauss, nrow, ncol, ntot;
@@ -69,8 +73,8 @@ struct LMShared {
 // composed gaussian k = iobj*npsf + ipsf (gmix_convolve_fill's order).
 // sh->status is OR-ed with range errors.
 __device__ __noinline__ void build_mixture(const LMArgs &a, LMShared *sh,
-                                           const double *x, double *gc,
-                                           double *ptab, double area) {
+                                           const double *x, double *mix,
+                                           double area) {
     int k = threadIdx.x;
     if (k >= a.ngauss) return;
     ModelHead h = model_head(a.model, x);
@@ -103,92 +107,141 @@ __device__ __noinline__ void build_mixture(const LMArgs &a, LMShared *sh,
     double drr = irr * idet, drc = irc * idet, dcc = icc * idet;
     double norm = 1.0 / (2 * 3.141592653589793 * sqrt(det));
     double pn = (p * norm) * area;
-    double *g = gc + GC_STRIDE * k;
+    double *g = mix + REC * k + 16;
+    double ha = -0.25 * dcc, hb = -0.25 * drr;
     g[0] = row; g[1] = col;
-    g[2] = -0.5 * dcc; g[3] = -0.5 * drr; g[4] = 0.5 * drc;
-    g[5] = 0.5 * (irr0 + icc0);
-    g[6] = drc; g[7] = -0.25 * dcc; g[8] = -0.25 * drr; g[9] = 0.25 * drc;
-#pragma unroll
-    for (int t = 0; t < 16; t++) ptab[16 * k + t] = c_exp_lookup[t] * pn;
+    g[2] = -0.5 * dcc; g[3] = -0.5 * drr;
+    g[4] = 0.5 * drc; g[5] = drc;
+    g[6] = 0.5 * (irr0 + icc0); g[7] = 0.25 * drc;
+    g[8] = ha; g[9] = hb;
+    g[10] = hb - ha; g[11] = hb + ha;
+    // chi^2 < 25 implies |dv| < 5 sqrt(irr), |du| < 5 sqrt(icc)
+    g[12] = 5.0 * sqrt(irr); g[13] = 5.0 * sqrt(icc);
+    fill_rot_table(mix + REC * k, pn);
 }
 
-// pixel coordinates of tiled index q from the row/col offset tables
+// per tile, the bit mask of the gaussians of mixture gc whose footprint can
+// reach it (slack widens the test when one mask also serves the
+// forward-difference mixtures)
+__device__ __forceinline__ void build_tile_masks(const LMArgs &a,
+                                                 const LMShared *sh,
+                                                 const double *mix,
+                                                 unsigned *tmask,
+                                                 double slack) {
+    const int ntile = a.nq >> 5;
+    const int nwords = (a.ngauss + 31) >> 5;
+    for (int t = threadIdx.x; t < ntile; t += blockDim.x) {
+        double vc, uc, hv, hu;
+        tile_extent(sh->jac, t, a.tpr, a.nrow, a.ncol, &vc, &uc, &hv, &hu);
+        hv += slack * (fabs(vc) + hv);
+        hu += slack * (fabs(uc) + hu);
+        for (int w = 0; w < nwords; w++) {
+            unsigned m = 0;
+            int kend = min(32, a.ngauss - 32 * w);
+            for (int kk = 0; kk < kend; kk++) {
+                const double *g = mix + REC * (32 * w + kk) + 16;
+                double rv = g[12], ru = g[13];
+                rv += slack * (rv + fabs(g[0]));
+                ru += slack * (ru + fabs(g[1]));
+                if (tile_hit(vc, uc, hv, hu, g[0], g[1], rv, ru))
+                    m |= 1u << kk;
+            }
+            tmask[(size_t)t * nwords + w] = m;
+        }
+    }
+}
+
+// pixel coordinates of tiled index q from the row/col offset tables.
+// Padding slots (beyond the stamp's edge) take the coordinates of the
+// nearest real pixel; their val/ierr are zero, so they add exact zeros.
 __device__ __forceinline__ void coords_of(const LMArgs &a, const LMShared *sh,
                                           const double *rowd,
                                           const double *cold, int q,
                                           double *v, double *u) {
     int row, col;
     q_to_rowcol(q, a.tpr, &row, &col);
-    if (q < a.nq && row < a.nrow && col < a.ncol) {
-        double rd = rowd[row], cd = cold[col];
-        *v = sh->jac.dvdrow * rd + sh->jac.dvdcol * cd;
-        *u = sh->jac.dudrow * rd + sh->jac.dudcol * cd;
-    } else {
-        *v = 1.0e10; *u = 1.0e10;     // padding: far outside any footprint
-    }
+    double rd = rowd[min(row, a.nrow - 1)], cd = cold[min(col, a.ncol - 1)];
+    *v = sh->jac.dvdrow * rd + sh->jac.dvdcol * cd;
+    *u = sh->jac.dudrow * rd + sh->jac.dudcol * cd;
+}
+
+// union of the masks of the C consecutive tiles starting at tile t0
+template <int C>
+__device__ __forceinline__ unsigned tiles_mask(const unsigned *tmask, int t0,
+                                               int ntile, int nwords, int w) {
+    unsigned m = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++)
+        if (t0 + c < ntile) m |= tmask[(size_t)(t0 + c) * nwords + w];
+    return m;
 }
 
 // ---------------------------------------------------------------------
-// value pass: sums = {sum r^2, s2n_numer, s2n_denom, r_first^2}
+// value pass: sums = {sum r^2, s2n_numer, s2n_denom, r_first^2}.
+// Each warp takes CV consecutive tiles per chunk.
 template <int CV>
 __device__ __forceinline__ void value_pass(const LMArgs &a,
                                            const LMShared *sh,
-                                           const double *gc,
-                                           const double *ptab,
+                                           const double *mix,
+                                           const unsigned *tmask,
                                            const double *val,
                                            const double *ierr,
                                            const double *rowd,
                                            const double *cold,
                                            double (&sums)[4]) {
     const int T = blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ntile = a.nq >> 5;
+    const int nwords = (a.ngauss + 31) >> 5;
     sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
     for (int base = 0; base < a.nq; base += T * CV) {
+        const int q0 = base + warp * CV * 32 + lane;
         double v[CV], u[CV], acc[CV];
 #pragma unroll
         for (int c = 0; c < CV; c++) {
-            coords_of(a, sh, rowd, cold, base + c * T + threadIdx.x, &v[c],
-                      &u[c]);
+            coords_of(a, sh, rowd, cold, q0 + 32 * c, &v[c], &u[c]);
             acc[c] = 0.0;
         }
+        for (int w = 0; w < nwords; w++) {
+            unsigned m = tiles_mask<CV>(tmask, q0 >> 5, ntile, nwords, w);
 #pragma unroll 1
-        for (int k = 0; k < a.ngauss; k++) {
-            const double *g = gc + GC_STRIDE * k;
-            const double *tab = ptab + 16 * k;
-            double row = g[0], col = g[1], ga = g[2], gb = g[3], gcx = g[6];
-            double x[CV];
-            bool inr[CV], any = false, anyapod = false;
-#pragma unroll
-            for (int c = 0; c < CV; c++) {
-                double dv = v[c] - row;
-                double du = u[c] - col;
-                double t = fma(gcx, du, ga * dv);
-                x[c] = fma(gb * du, du, dv * t);
-                inr[c] = x_in_range(x[c]);
-                any |= inr[c];
-                anyapod |= inr[c] && x_in_apod(x[c]);
-            }
-            if (!__any_sync(0xffffffffu, any)) continue;   // warp-uniform
-            double e[CV];
-#pragma unroll
-            for (int c = 0; c < CV; c++) e[c] = fexp_tab(x[c], tab);
-            if (__any_sync(0xffffffffu, anyapod)) {
-                // some lane of some pixel sits in the apodization band
+            while (m) {
+                const int k = 32 * w + __ffs((int)m) - 1;
+                m &= m - 1;
+                const double *tab = mix + REC * k;
+                const double2 *g2 = (const double2 *)(tab + 16);
+                const double2 rc = g2[0], ab = g2[1], cc = g2[2];
+                double x[CV], e[CV];
+                bool ap[CV], anyap = false;
 #pragma unroll
                 for (int c = 0; c < CV; c++) {
-                    bool ap = inr[c] && x_in_apod(x[c]);
-                    if (__any_sync(0xffffffffu, ap)) {
-                        double w = apod_window_fast(x[c]);
-                        if (ap) e[c] *= w;
+                    double dv = v[c] - rc.x;
+                    double du = u[c] - rc.y;
+                    double t = fma(cc.y, du, ab.x * dv);
+                    x[c] = fma(ab.y * du, du, dv * t);
+                    unsigned slot;
+                    bool inr;
+                    double f = fexp_split(x[c], &slot, &inr, &ap[c]);
+                    e[c] = tab[slot] * fexp_poly_c(f);
+                    anyap |= ap[c];
+                }
+                if (__any_sync(0xffffffffu, anyap)) {
+                    // some lane of some pixel sits in the apodization band
+#pragma unroll
+                    for (int c = 0; c < CV; c++) {
+                        if (__any_sync(0xffffffffu, ap[c])) {
+                            double w = apod_window_fast(x[c]);
+                            if (ap[c]) e[c] *= w;
+                        }
                     }
                 }
-            }
 #pragma unroll
-            for (int c = 0; c < CV; c++)
-                if (inr[c]) acc[c] += e[c];
+                for (int c = 0; c < CV; c++) acc[c] += e[c];
+            }
         }
 #pragma unroll
         for (int c = 0; c < CV; c++) {
-            int q = base + c * T + threadIdx.x;
+            int q = q0 + 32 * c;
             if (q < a.nq) {
                 double ie = ierr[q], d = val[q];
                 double ivar = ie * ie;
@@ -218,14 +271,18 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
 template <int CD>
 __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                                            const LMShared *sh,
-                                           const double *x, const double *gc,
-                                           const double *ptab,
+                                           const double *x,
+                                           const double *mix,
+                                           const unsigned *tmask,
                                            const double *val,
                                            const double *ierr,
                                            const double *rowd,
                                            const double *cold,
                                            double (&sums)[NDSUM]) {
     const int T = blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ntile = a.nq >> 5;
+    const int nwords = (a.ngauss + 31) >> 5;
 #pragma unroll
     for (int i = 0; i < NDSUM; i++) sums[i] = 0.0;
     // d(e1,e2)/d(g1,g2), results.py:988-995
@@ -242,80 +299,79 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
     double iT = 1.0 / Tpar, iflux = 1.0 / flux;
 
     for (int base = 0; base < a.nq; base += T * CD) {
+        const int q0 = base + warp * CD * 32 + lane;
         double v[CD], u[CD];
         double S0[CD], S1[CD], S2[CD], MA[CD], MB[CD], MS[CD];
 #pragma unroll
         for (int c = 0; c < CD; c++) {
-            coords_of(a, sh, rowd, cold, base + c * T + threadIdx.x, &v[c],
-                      &u[c]);
+            coords_of(a, sh, rowd, cold, q0 + 32 * c, &v[c], &u[c]);
             S0[c] = S1[c] = S2[c] = MA[c] = MB[c] = MS[c] = 0.0;
         }
+        for (int w = 0; w < nwords; w++) {
+            unsigned m = tiles_mask<CD>(tmask, q0 >> 5, ntile, nwords, w);
 #pragma unroll 1
-        for (int k = 0; k < a.ngauss; k++) {
-            const double *g = gc + GC_STRIDE * k;
-            const double *tab = ptab + 16 * k;
-            double row = g[0], col = g[1], ga = g[2], gb = g[3], c2 = g[4];
-            double xx[CD], hqv[CD], hqu[CD];
-            bool inr[CD], any = false, anyapod = false;
+            while (m) {
+                const int k = 32 * w + __ffs((int)m) - 1;
+                m &= m - 1;
+                const double *tab = mix + REC * k;
+                const double2 *gg = (const double2 *)(tab + 16);
+                const double2 rc = gg[0], ab = gg[1], cc = gg[2];
+                double xx[CD], hqv[CD], hqu[CD], vl[CD];
+                bool ap[CD], anyap = false;
 #pragma unroll
-            for (int c = 0; c < CD; c++) {
-                double dv = v[c] - row;
-                double du = u[c] - col;
-                hqv[c] = fma(c2, du, ga * dv);     // -qv/2
-                hqu[c] = fma(gb, du, c2 * dv);     // -qu/2
-                xx[c] = fma(du, hqu[c], dv * hqv[c]);    // -chi2/2
-                inr[c] = x_in_range(xx[c]);
-                any |= inr[c];
-                anyapod |= inr[c] && x_in_apod(xx[c]);
-            }
-            if (!__any_sync(0xffffffffu, any)) continue;   // warp-uniform
-            double h = g[5], ha = g[7], hb = g[8], qc = g[9];
-            // lanes outside the footprint contribute exact zeros: their
-            // (possibly huge) chi^2 terms must not meet 0 * inf
+                for (int c = 0; c < CD; c++) {
+                    double dv = v[c] - rc.x;
+                    double du = u[c] - rc.y;
+                    hqv[c] = fma(cc.x, du, ab.x * dv);     // -qv/2
+                    hqu[c] = fma(ab.y, du, cc.x * dv);     // -qu/2
+                    xx[c] = fma(du, hqu[c], dv * hqv[c]);  // -chi2/2
+                    unsigned slot;
+                    bool inr;
+                    double f = fexp_split(xx[c], &slot, &inr, &ap[c]);
+                    // exact zero outside the footprint (table slot 1)
+                    vl[c] = tab[slot] * fexp_poly_c(f);
+                    anyap |= ap[c];
+                }
+                const double2 hq = gg[3];           // h, qc
+                const bool warp_apod = __any_sync(0xffffffffu, anyap);
 #pragma unroll
-            for (int c = 0; c < CD; c++)
-                if (!inr[c]) { hqv[c] = 0.0; hqu[c] = 0.0; }
-            const bool warp_apod = __any_sync(0xffffffffu, anyapod);
-#pragma unroll
-            for (int c = 0; c < CD; c++) {
-                double vl = fexp_tab(xx[c], tab);
-                if (!inr[c]) vl = 0.0;
-                bool ap = inr[c] && x_in_apod(xx[c]);
-                if (!(warp_apod && __any_sync(0xffffffffu, ap))) {
-                    S0[c] += vl;
-                    S1[c] = fma(vl, hqv[c], S1[c]);
-                    S2[c] = fma(vl, hqu[c], S2[c]);
-                    double cv = vl * h;
-                    double ea = fma(hqu[c], hqu[c], hb);
-                    double eb = fma(hqv[c], hqv[c], ha);
-                    MA[c] = fma(cv, ea - eb, MA[c]);
-                    MS[c] = fma(cv, ea + eb, MS[c]);
-                    MB[c] = fma(cv, fma(hqv[c], hqu[c], qc), MB[c]);
-                } else {
-                    // a lane of this pixel group sits in the apodization
-                    // band: the window slope enters the terms that flow
-                    // through chi^2, derivs_nb.py:104-114
-                    double w = 1.0, wd = 0.0;
-                    if (ap) {
-                        w = apod_window_fast(xx[c]);
-                        wd = apod_window_deriv_x(xx[c]);
+                for (int c = 0; c < CD; c++) {
+                    if (!(warp_apod && __any_sync(0xffffffffu, ap[c]))) {
+                        const double2 hab = gg[4];  // ha, hb
+                        S0[c] += vl[c];
+                        S1[c] = fma(vl[c], hqv[c], S1[c]);
+                        S2[c] = fma(vl[c], hqu[c], S2[c]);
+                        double cv = vl[c] * hq.x;
+                        double ea = fma(hqu[c], hqu[c], hab.y);
+                        double eb = fma(hqv[c], hqv[c], hab.x);
+                        MA[c] = fma(cv, ea - eb, MA[c]);
+                        MS[c] = fma(cv, ea + eb, MS[c]);
+                        MB[c] = fma(cv, fma(hqv[c], hqu[c], hq.y), MB[c]);
+                    } else {
+                        // a lane of this tile sits in the apodization
+                        // band: the window slope enters the terms that flow
+                        // through chi^2, derivs_nb.py:104-114
+                        const double2 hpm = gg[5];  // hb - ha, hb + ha
+                        double wv = 1.0, wc = 1.0;
+                        if (ap[c]) apod_pair(xx[c], &wv, &wc);
+                        double vc = vl[c] * wc;
+                        double vw = vl[c] * wv;
+                        S0[c] += vw;
+                        S1[c] = fma(vc, hqv[c], S1[c]);
+                        S2[c] = fma(vc, hqu[c], S2[c]);
+                        double cv = vc * hq.x, cw = vw * hq.x;
+                        double qu2 = hqu[c] * hqu[c], qv2 = hqv[c] * hqv[c];
+                        MA[c] = fma(cv, qu2 - qv2, fma(cw, hpm.x, MA[c]));
+                        MS[c] = fma(cv, qu2 + qv2, fma(cw, hpm.y, MS[c]));
+                        MB[c] = fma(cv, hqv[c] * hqu[c],
+                                    fma(cw, hq.y, MB[c]));
                     }
-                    double vc = vl * (w - 2.0 * wd);
-                    double vw = vl * w;
-                    S0[c] += vw;
-                    S1[c] = fma(vc, hqv[c], S1[c]);
-                    S2[c] = fma(vc, hqu[c], S2[c]);
-                    double cv = vc * h, cw = vw * h;
-                    double qu2 = hqu[c] * hqu[c], qv2 = hqv[c] * hqv[c];
-                    MA[c] = fma(cv, qu2 - qv2, fma(cw, hb - ha, MA[c]));
-                    MS[c] = fma(cv, qu2 + qv2, fma(cw, hb + ha, MS[c]));
-                    MB[c] = fma(cv, hqv[c] * hqu[c], fma(cw, qc, MB[c]));
                 }
             }
         }
 #pragma unroll
         for (int c = 0; c < CD; c++) {
-            int q = base + c * T + threadIdx.x;
+            int q = q0 + 32 * c;
             if (q < a.nq) {
                 double ie = ierr[q], d = val[q];
                 // undo the factors folded into the accumulators:
@@ -355,58 +411,98 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
 // analytic derivatives (bdf, bd) or analytic_jacobian = 0: evaluates the
 // base mixture and the np perturbed mixtures per pixel.  The mixtures are
 // built by build_mixture into gcs[(np+1)][ngauss][GC_STRIDE] with their own
-// tables.  sums = {A packed (np(np+1)/2), b (np), sum r^2}
+// tables; the tile masks come from the base mixture (with slack for the
+// 1.5e-8 relative perturbations).
+// sums = {A packed (np(np+1)/2), b (np), sum r^2}
+#define CF 2
+#define FD_B0 (LM_MAXP * (LM_MAXP + 1) / 2)
+#define FD_NSUM (FD_B0 + LM_MAXP + 1)
 template <int NPMAX>
 __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
-                                        const double *hs, const double *gcs,
-                                        const double *ptabs,
+                                        const double *hs, const double *mixes,
+                                        const unsigned *tmask,
                                         const double *val, const double *ierr,
                                         const double *rowd,
-                                        const double *cold, double *sums,
-                                        int nsums) {
+                                        const double *cold,
+                                        double (&sums)[FD_NSUM]) {
     const int T = blockDim.x;
     const int np = a.np;
-    for (int i = 0; i < nsums; i++) sums[i] = 0.0;
-    for (int base = 0; base < a.nq; base += T) {
-        int q = base + threadIdx.x;
-        double v, u;
-        coords_of(a, sh, rowd, cold, q, &v, &u);
-        double m[NPMAX + 1];
-        for (int s = 0; s <= np; s++) {
-            const double *gc = gcs + (size_t)s * a.ngauss * GC_STRIDE;
-            const double *ptab = ptabs + (size_t)s * a.ngauss * 16;
-            double acc = 0.0;
-            for (int k = 0; k < a.ngauss; k++) {
-                const double *g = gc + GC_STRIDE * k;
-                double dv = v - g[0];
-                double du = u - g[1];
-                double t = fma(g[6], du, g[2] * dv);
-                double x = fma(g[3] * du, du, dv * t);
-                bool inr = x_in_range(x);
-                if (!__any_sync(0xffffffffu, inr)) continue;
-                double e = fexp_tab(x, ptab + 16 * k);
-                if (inr && x_in_apod(x)) e *= apod_window_x(x);
-                if (inr) acc += e;
-            }
-            m[s] = acc;
-        }
-        if (q < a.nq) {
-            double ie = ierr[q];
-            double r = (m[0] - val[q]) * ie;
-            double j[NPMAX];
-            for (int s = 0; s < np; s++) {
-                double rs = (m[s + 1] - val[q]) * ie;
-                j[s] = (rs - r) / hs[s];
-            }
-            int qq = 0;
-            for (int aa = 0; aa < np; aa++)
-                for (int bb = 0; bb <= aa; bb++) {
-                    sums[qq] = fma(j[aa], j[bb], sums[qq]);
-                    qq++;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ntile = a.nq >> 5;
+    const int nwords = (a.ngauss + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < FD_NSUM; i++) sums[i] = 0.0;
+    double hstep[NPMAX];
+#pragma unroll
+    for (int s = 0; s < NPMAX; s++) hstep[s] = s < np ? hs[s] : 1.0;
+    for (int base = 0; base < a.nq; base += T * CF) {
+        const int q0 = base + warp * CF * 32 + lane;
+        double v[CF], u[CF];
+#pragma unroll
+        for (int c = 0; c < CF; c++)
+            coords_of(a, sh, rowd, cold, q0 + 32 * c, &v[c], &u[c]);
+        double mod[NPMAX + 1][CF];
+#pragma unroll
+        for (int s = 0; s <= NPMAX; s++) {
+#pragma unroll
+            for (int c = 0; c < CF; c++) mod[s][c] = 0.0;
+            if (s > np) continue;
+            const double *mix = mixes + (size_t)s * a.ngauss * REC;
+            for (int w = 0; w < nwords; w++) {
+                unsigned m = tiles_mask<CF>(tmask, q0 >> 5, ntile, nwords, w);
+#pragma unroll 1
+                while (m) {
+                    const int k = 32 * w + __ffs((int)m) - 1;
+                    m &= m - 1;
+                    const double *tab = mix + REC * k;
+                    const double2 *g2 = (const double2 *)(tab + 16);
+                    const double2 rc = g2[0], ab = g2[1], cc = g2[2];
+#pragma unroll
+                    for (int c = 0; c < CF; c++) {
+                        double dv = v[c] - rc.x;
+                        double du = u[c] - rc.y;
+                        double t = fma(cc.y, du, ab.x * dv);
+                        double x = fma(ab.y * du, du, dv * t);
+                        unsigned slot;
+                        bool inr, ap;
+                        double f = fexp_split(x, &slot, &inr, &ap);
+                        double e = tab[slot] * fexp_poly_c(f);
+                        if (__any_sync(0xffffffffu, ap)) {
+                            double wv = apod_window_x(x);
+                            if (ap) e *= wv;
+                        }
+                        mod[s][c] += e;
+                    }
                 }
-            for (int aa = 0; aa < np; aa++)
-                sums[qq + aa] = fma(j[aa], r, sums[qq + aa]);
-            sums[qq + np] = fma(r, r, sums[qq + np]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CF; c++) {
+            int q = q0 + 32 * c;
+            if (q < a.nq) {
+                double ie = ierr[q], d = val[q];
+                double r = (mod[0][c] - d) * ie;
+                double j[NPMAX];
+#pragma unroll
+                for (int s = 0; s < NPMAX; s++) {
+                    double rs = (mod[s + 1][c] - d) * ie;
+                    j[s] = s < np ? (rs - r) / hstep[s] : 0.0;
+                }
+                // static layout: packed triangle of NPMAX, then b, then r^2
+                // (the first np rows of the triangle are those of np)
+                int qq = 0;
+#pragma unroll
+                for (int aa = 0; aa < NPMAX; aa++)
+#pragma unroll
+                    for (int bb = 0; bb <= aa; bb++) {
+                        sums[qq] = fma(j[aa], j[bb], sums[qq]);
+                        qq++;
+                    }
+#pragma unroll
+                for (int aa = 0; aa < NPMAX; aa++)
+                    sums[FD_B0 + aa] = fma(j[aa], r, sums[FD_B0 + aa]);
+                sums[FD_B0 + NPMAX] = fma(r, r, sums[FD_B0 + NPMAX]);
+            }
         }
     }
 }
@@ -628,14 +724,14 @@ k_lm_fit(LMArgs a) {
     const int nwarps = T >> 5;
     const int nmix = (MODE == 0) ? 1 : (a.np + 1);
     // dynamic shared memory carve-up
-    double *ptab = smem_d;                                   // nmix*ngauss*16
-    double *gc = ptab + (size_t)nmix * a.ngauss * 16;        // nmix*ngauss*GC
-    double *val = gc + (size_t)nmix * a.ngauss * GC_STRIDE;  // nq
+    double *mix = smem_d;                                    // nmix*ngauss*REC
+    double *val = mix + (size_t)nmix * a.ngauss * REC;       // nq
     double *ierr = val + a.nq;
     double *rowd = ierr + a.nq;
     double *cold = rowd + a.nrow;
     double *scratch = cold + a.ncol;                         // 48 * nwarps
     double *hs = scratch + 48 * nwarps;                      // 8
+    unsigned *tmask = (unsigned *)(hs + 8);                  // ntile*nwords
 
     for (;;) {
         __syncthreads();
@@ -780,18 +876,20 @@ k_lm_fit(LMArgs a) {
             // rejected step just discards the extra sums.
             const bool fused = want_f && spec && xp[4] != 0.0 && xp[5] != 0.0;
             if (MODE == 0 && (fused || action == LM_ACT_EVAL_J)) {
-                build_mixture(a, &sh, xp, gc, ptab, area);
+                build_mixture(a, &sh, xp, mix, area);
+                __syncthreads();
+                const int mix_status = sh.status;
+                if (!mix_status) build_tile_masks(a, &sh, mix, tmask, 1.0e-9);
                 __syncthreads();
                 PROF_T(pt_mix);
-                const int mix_status = sh.status;
                 double sums[NDSUM];
 #pragma unroll
                 for (int i = 0; i < NDSUM; i++) sums[i] = 0.0;
                 // calc_jacobian raises for T == 0 or flux == 0
                 int jstatus = mix_status || xp[4] == 0.0 || xp[5] == 0.0;
                 if (!jstatus)
-                    deriv_pass<CD>(a, &sh, xp, gc, ptab, val, ierr, rowd, cold,
-                                   sums);
+                    deriv_pass<CD>(a, &sh, xp, mix, tmask, val, ierr, rowd,
+                                   cold, sums);
                 block_sum<NDSUM>(sums, scratch);
                 PROF_T(pt_pass);
                 if (threadIdx.x == 0) {
@@ -812,13 +910,15 @@ k_lm_fit(LMArgs a) {
                     }
                 }
             } else if (action == LM_ACT_EVAL_F) {
-                build_mixture(a, &sh, sh.xeval, gc, ptab, area);
+                build_mixture(a, &sh, sh.xeval, mix, area);
+                __syncthreads();
+                if (!sh.status) build_tile_masks(a, &sh, mix, tmask, 1.0e-9);
                 __syncthreads();
                 PROF_T(pt_mix);
                 double sums[4] = {0, 0, 0, 0};
                 if (!sh.status)
-                    value_pass<CV>(a, &sh, gc, ptab, val, ierr, rowd, cold,
-                                   sums);
+                    value_pass<CV>(a, &sh, mix, tmask, val, ierr, rowd,
+                                   cold, sums);
                 block_sum<4>(sums, scratch);
                 PROF_T(pt_pass);
                 if (threadIdx.x == 0) {
@@ -854,21 +954,28 @@ k_lm_fit(LMArgs a) {
                     }
                     __syncthreads();
                     build_mixture(a, &sh, sh.xeval,
-                                  gc + (size_t)s * a.ngauss * GC_STRIDE,
-                                  ptab + (size_t)s * a.ngauss * 16, area);
+                                  mix + (size_t)s * a.ngauss * REC, area);
                     __syncthreads();
                     bad_any |= sh.status;
                     __syncthreads();
                 }
-                const int nsums = np * (np + 1) / 2 + np + 1;
-                double sums[45];
-                for (int i = 0; i < 45; i++) sums[i] = 0.0;
+                if (!bad_any) build_tile_masks(a, &sh, mix, tmask, 1.0e-6);
+                __syncthreads();
+                double sums[FD_NSUM];
+#pragma unroll
+                for (int i = 0; i < FD_NSUM; i++) sums[i] = 0.0;
                 if (!bad_any)
-                    fd_pass<LM_MAXP>(a, &sh, hs, gc, ptab, val, ierr, rowd,
-                                     cold, sums, nsums);
-                block_sum_n(sums, nsums, scratch);
-                if (threadIdx.x == 0)
-                    feed_jacobian(a, &sh, sums, bad_any, 0, hs);
+                    fd_pass<LM_MAXP>(a, &sh, hs, mix, tmask, val, ierr,
+                                     rowd, cold, sums);
+                block_sum<FD_NSUM>(sums, scratch);
+                if (threadIdx.x == 0) {
+                    // feed_jacobian wants {triangle of np, b, r^2} contiguous
+                    double *pk = sh.st.T2;
+                    const int tri = np * (np + 1) / 2;
+                    for (int i = 0; i < tri; i++) pk[i] = sums[i];
+                    for (int i = 0; i <= np; i++) pk[tri + i] = sums[FD_B0 + i];
+                    feed_jacobian(a, &sh, pk, bad_any, 0, hs);
+                }
             }
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -982,41 +1089,12 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     int nmix = analytic ? 1 : np + 1;
     int nwarps = threads / 32;
     size_t smem = sizeof(double)
-        * ((size_t)nmix * a.ngauss * (16 + GC_STRIDE) + 2 * (size_t)a.nq
-           + nrow + ncol + 48 * nwarps + 8);
-    // tuning knob (experiments only): NGX_LM_VARIANT selects the register
-    // blocking / occupancy trade-off of the analytic kernel
-    static int variant = -1;
-    if (variant < 0) {
-        const char *e = getenv("NGX_LM_VARIANT");
-        variant = e ? atoi(e) : 0;
-    }
-    if (analytic) {
-        if (variant == 1)
-            return config_and_launch(k_lm_fit<0, 3, 3, 3>, a, threads, smem,
-                                     as_stream(stream));
-        if (variant == 2)
-            return config_and_launch(k_lm_fit<0, 4, 2, 3>, a, threads, smem,
-                                     as_stream(stream));
-        if (variant == 3)
-            return config_and_launch(k_lm_fit<0, 2, 1, 4>, a, threads, smem,
-                                     as_stream(stream));
-        if (variant == 4 || variant == 5) {
-            // 6 warps per CTA at <= 85 registers
-            threads = 192;
-            nwarps = 6;
-            smem = sizeof(double)
-                * ((size_t)nmix * a.ngauss * (16 + GC_STRIDE)
-                   + 2 * (size_t)a.nq + nrow + ncol + 48 * nwarps + 8);
-            if (variant == 4)
-                return config_and_launch(k_lm_fit<0, 3, 2, 4, 192>, a,
-                                         threads, smem, as_stream(stream));
-            return config_and_launch(k_lm_fit<0, 2, 1, 4, 192>, a, threads,
-                                     smem, as_stream(stream));
-        }
+        * ((size_t)nmix * a.ngauss * REC + 2 * (size_t)a.nq
+           + nrow + ncol + 48 * nwarps + 8
+           + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
+    if (analytic)
         return config_and_launch(k_lm_fit<0, 3, 2, 4>, a, threads, smem,
                                  as_stream(stream));
-    }
     return config_and_launch(k_lm_fit<1, 3, 2, 4>, a, threads, smem,
                              as_stream(stream));
 }

@@ -416,14 +416,16 @@ __global__ void k_loglike(int ngauss, const ngx_gauss *__restrict__ gmix,
 
 // ---------------------------------------------------------------------
 // The same fused pass for image/weight/jacobian input, organised like the
-// value pass of the LM kernel: pixels in TILED order (4 rows x 8 columns per
-// warp tile) so that a gaussian whose chi^2 < 25 footprint misses the tile is
-// skipped with one vote, gaussians in the outer loop with their constants and
-// a pn*exp(i) table in shared memory, C pixels per thread in registers.
+// value pass of the LM kernel.  Pixels are taken in TILED order (4 rows x 8
+// columns per warp tile, C consecutive tiles per warp and chunk).  Before the
+// pixel loop every tile gets a bit mask of the gaussians whose chi^2 < 25
+// bounding box meets it, so a warp only visits gaussians that can contribute;
+// their constants and rotated pn*exp(i) tables sit in shared memory.
 // fdiff keeps the reference's order (row-major over the positive-weight
 // pixels): a ballot pre-pass counts the valid pixels of every 8-pixel row
 // segment, prefix sums give each segment's offset.
 #define LLT_C 3
+#define LLT_REC 24      // 16-entry table, then row, col, a, b, c, -, rv, ru
 __global__ void __launch_bounds__(256, 3)
 k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
                 const double *__restrict__ images,
@@ -433,16 +435,18 @@ k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
                 double *__restrict__ out4, double *__restrict__ fdiff,
                 int32_t *__restrict__ status) {
     extern __shared__ double smem_d[];
+    const int ntile = nq >> 5;
+    const int nwords = (ngauss + 31) >> 5;
     double *scratch = smem_d;                   // 4 * 32
-    double *gc = scratch + 4 * 32;              // ngauss * 6
-    double *ptab = gc + 6 * ngauss;             // ngauss * 16
-    int *segoff = (int *)(ptab + 16 * ngauss);  // nrow * tpr
+    double *mix = scratch + 4 * 32;             // ngauss * LLT_REC
+    unsigned *tmask = (unsigned *)(mix + LLT_REC * ngauss);  // ntile * nwords
+    int *segoff = (int *)(tmask + (size_t)ntile * nwords);  // nrow * tpr
     int *rowoff = segoff + nrow * tpr;          // nrow
     __shared__ int bad;
     const int T = blockDim.x;
     const int obj = blockIdx.x;
     const int ntot = nrow * ncol;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ngx_jacobian j = jac[obj];
     const double area = j.scale * j.scale;
     const double *im = images + (size_t)obj * ntot;
@@ -452,11 +456,12 @@ k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
     for (int k = threadIdx.x; k < ngauss; k += T) {
         ngx_gauss g = gmix[(size_t)obj * ngauss + k];
         if (gauss_set_norm(g) != NGX_ST_OK) bad = 1;
-        double *c = gc + 6 * k;
+        double *c = mix + LLT_REC * k + 16;
         c[0] = g.row; c[1] = g.col;
         c[2] = -0.5 * g.dcc; c[3] = -0.5 * g.drr; c[4] = g.drc;
-        double pn = g.pnorm * area;
-        for (int t = 0; t < 16; t++) ptab[16 * k + t] = c_exp_lookup[t] * pn;
+        c[5] = 0.0;
+        c[6] = 5.0 * sqrt(g.irr); c[7] = 5.0 * sqrt(g.icc);
+        fill_rot_table(mix + LLT_REC * k, g.pnorm * area);
     }
     if (fdiff) {
         // valid pixels per 8-pixel row segment
@@ -483,6 +488,21 @@ k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
         }
         return;
     }
+    // gaussians that can reach each tile
+    for (int t = threadIdx.x; t < ntile; t += T) {
+        double vc, uc, hv, hu;
+        tile_extent(j, t, tpr, nrow, ncol, &vc, &uc, &hv, &hu);
+        for (int w = 0; w < nwords; w++) {
+            unsigned m = 0;
+            int kend = min(32, ngauss - 32 * w);
+            for (int kk = 0; kk < kend; kk++) {
+                const double *g = mix + LLT_REC * (32 * w + kk) + 16;
+                if (tile_hit(vc, uc, hv, hu, g[0], g[1], g[6], g[7]))
+                    m |= 1u << kk;
+            }
+            tmask[(size_t)t * nwords + w] = m;
+        }
+    }
     if (fdiff) {
         for (int r = threadIdx.x; r < nrow; r += T) {
             int run = 0;
@@ -502,60 +522,67 @@ k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
                 run += c;
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
     double sums[4] = {0.0, 0.0, 0.0, 0.0};
     for (int base = 0; base < nq; base += T * LLT_C) {
+        // this warp's LLT_C consecutive tiles
+        const int q0 = base + (warp * LLT_C) * 32 + lane;
         double v[LLT_C], u[LLT_C], acc[LLT_C];
 #pragma unroll
         for (int c = 0; c < LLT_C; c++) {
-            int q = base + c * T + threadIdx.x;
             int row, col;
-            q_to_rowcol(q, tpr, &row, &col);
+            q_to_rowcol(q0 + 32 * c, tpr, &row, &col);
             acc[c] = 0.0;
-            if (q < nq && row < nrow && col < ncol)
-                pixel_vu(j, row, col, &v[c], &u[c]);
-            else
-                v[c] = u[c] = 1.0e10;
+            // padding lanes evaluate a real pixel and are dropped below
+            pixel_vu(j, min(row, nrow - 1), min(col, ncol - 1), &v[c], &u[c]);
         }
-#pragma unroll 1
-        for (int k = 0; k < ngauss; k++) {
-            const double *g = gc + 6 * k;
-            const double *tab = ptab + 16 * k;
-            double grow = g[0], gcol = g[1], ga = g[2], gb = g[3], gcx = g[4];
-            double x[LLT_C];
-            bool inr[LLT_C], any = false, anyapod = false;
+        for (int w = 0; w < nwords; w++) {
+            unsigned m = 0;
 #pragma unroll
             for (int c = 0; c < LLT_C; c++) {
-                double dv = v[c] - grow;
-                double du = u[c] - gcol;
-                double t = fma(gcx, du, ga * dv);
-                x[c] = fma(gb * du, du, dv * t);
-                inr[c] = x_in_range(x[c]);
-                any |= inr[c];
-                anyapod |= inr[c] && x_in_apod(x[c]);
+                int t = (q0 >> 5) + c;
+                if (t < ntile) m |= tmask[(size_t)t * nwords + w];
             }
-            if (!__any_sync(0xffffffffu, any)) continue;   // warp-uniform
-            double e[LLT_C];
-#pragma unroll
-            for (int c = 0; c < LLT_C; c++) e[c] = fexp_tab(x[c], tab);
-            if (__any_sync(0xffffffffu, anyapod)) {
+#pragma unroll 1
+            while (m) {
+                const int k = 32 * w + __ffs((int)m) - 1;
+                m &= m - 1;
+                const double *tab = mix + LLT_REC * k;
+                const double2 *g2 = (const double2 *)(tab + 16);
+                const double2 rc = g2[0], ab = g2[1];
+                const double grow = rc.x, gcol = rc.y, ga = ab.x, gb = ab.y,
+                             gcx = tab[20];
+                double x[LLT_C], e[LLT_C];
+                bool ap[LLT_C], anyap = false;
 #pragma unroll
                 for (int c = 0; c < LLT_C; c++) {
-                    bool ap = inr[c] && x_in_apod(x[c]);
-                    if (__any_sync(0xffffffffu, ap)) {
-                        double w = apod_window_fast(x[c]);
-                        if (ap) e[c] *= w;
+                    double dv = v[c] - grow;
+                    double du = u[c] - gcol;
+                    double t = fma(gcx, du, ga * dv);
+                    x[c] = fma(gb * du, du, dv * t);
+                    unsigned slot;
+                    bool inr;
+                    double f = fexp_split(x[c], &slot, &inr, &ap[c]);
+                    e[c] = tab[slot] * fexp_poly_c(f);
+                    anyap |= ap[c];
+                }
+                if (__any_sync(0xffffffffu, anyap)) {
+#pragma unroll
+                    for (int c = 0; c < LLT_C; c++) {
+                        if (__any_sync(0xffffffffu, ap[c])) {
+                            double w = apod_window_fast(x[c]);
+                            if (ap[c]) e[c] *= w;
+                        }
                     }
                 }
-            }
 #pragma unroll
-            for (int c = 0; c < LLT_C; c++)
-                if (inr[c]) acc[c] += e[c];
+                for (int c = 0; c < LLT_C; c++) acc[c] += e[c];
+            }
         }
 #pragma unroll
         for (int c = 0; c < LLT_C; c++) {
-            int q = base + c * T + threadIdx.x;
+            int q = q0 + 32 * c;
             int row, col;
             q_to_rowcol(q, tpr, &row, &col);
             bool valid = false;
@@ -831,7 +858,9 @@ static int launch_loglike(int src, int n, int ngauss, const ngx_gauss *gmix,
     if (src == 0) {
         int tpr = (ncol + 7) / 8;
         int nq = 32 * tpr * ((nrow + 3) / 4);
-        size_t smt = sizeof(double) * (4 * 32 + 22 * (size_t)ngauss)
+        size_t smt = sizeof(double)
+            * (4 * 32 + LLT_REC * (size_t)ngauss
+               + ((size_t)(nq / 32) * ((ngauss + 31) / 32) + 1) / 2)
             + sizeof(int) * ((size_t)nrow * tpr + nrow);
         NGX_REQUIRE(smt <= 48 * 1024);
         k_loglike_tiled<<<n, 256, smt, as_stream(stream)>>>(
@@ -913,6 +942,7 @@ int ngx_peak_dfma(int iters, double *dfma_per_s, double *ms_out) {
 int ngx_gmix_fill_host(int n, int model, int ngauss, const double *pars,
                        int npars, ngx_gauss *gmix, int32_t *status) {
     NGX_REQUIRE(n >= 0 && pars && gmix);
+    if (n == 0) return NGX_OK;
     DevBuf<double> dp((size_t)n * npars, pars);
     DevBuf<ngx_gauss> dg((size_t)n * ngauss);
     DevBuf<int32_t> ds(n);
@@ -929,6 +959,7 @@ int ngx_gmix_fill_host(int n, int model, int ngauss, const double *pars,
 int ngx_gmix_fill_cm_host(int n, const double *cm, const double *pars,
                           ngx_gauss *gmix, int32_t *status) {
     NGX_REQUIRE(n >= 0 && cm && pars && gmix);
+    if (n == 0) return NGX_OK;
     DevBuf<double> dc((size_t)n * 3, cm), dp((size_t)n * 6, pars);
     DevBuf<ngx_gauss> dg((size_t)n * 16);
     DevBuf<int32_t> ds(n);
@@ -945,6 +976,7 @@ int ngx_gmix_fill_cm_host(int n, const double *cm, const double *pars,
 int ngx_gmix_set_norms_host(int n, int ngauss, ngx_gauss *gmix,
                             int32_t *status) {
     NGX_REQUIRE(n >= 0 && gmix);
+    if (n == 0) return NGX_OK;
     DevBuf<ngx_gauss> dg((size_t)n * ngauss, gmix);
     DevBuf<int32_t> ds(n);
     NGX_BUF(dg); NGX_BUF(ds);
@@ -959,6 +991,7 @@ int ngx_gmix_set_norms_host(int n, int ngauss, ngx_gauss *gmix,
 int ngx_gmix_convolve_host(int n, int nobj, int npsf, const ngx_gauss *obj,
                            const ngx_gauss *psf, ngx_gauss *out) {
     NGX_REQUIRE(n >= 0 && obj && psf && out);
+    if (n == 0) return NGX_OK;
     DevBuf<ngx_gauss> dobj((size_t)n * nobj, obj), dpsf((size_t)n * npsf, psf);
     DevBuf<ngx_gauss> dout((size_t)n * nobj * npsf);
     NGX_BUF(dobj); NGX_BUF(dpsf); NGX_BUF(dout);
@@ -974,6 +1007,7 @@ int ngx_make_pixels_host(int n, int nrow, int ncol, const double *images,
                          int ignore_zero_weight, ngx_pixel *pixels,
                          int32_t *npix) {
     NGX_REQUIRE(n >= 0 && images && weights && jac && pixels && npix);
+    if (n == 0) return NGX_OK;
     size_t ntot = (size_t)n * nrow * ncol;
     DevBuf<double> di(ntot, images), dw(ntot, weights);
     DevBuf<ngx_jacobian> dj(n, jac);
@@ -993,6 +1027,7 @@ int ngx_make_pixels_host(int n, int nrow, int ncol, const double *images,
 int ngx_make_coords_host(int n, int nrow, int ncol, const ngx_jacobian *jac,
                          ngx_coord *coords) {
     NGX_REQUIRE(n >= 0 && jac && coords);
+    if (n == 0) return NGX_OK;
     DevBuf<ngx_jacobian> dj(n, jac);
     DevBuf<ngx_coord> dc((size_t)n * nrow * ncol);
     NGX_BUF(dj); NGX_BUF(dc);
@@ -1007,6 +1042,7 @@ int ngx_render_host(int n, int ngauss, const ngx_gauss *gmix,
                     const ngx_jacobian *jac, int nrow, int ncol, int fast_exp,
                     double *images, int32_t *status) {
     NGX_REQUIRE(n >= 0 && gmix && jac && images);
+    if (n == 0) return NGX_OK;
     DevBuf<ngx_gauss> dg((size_t)n * ngauss, gmix);
     DevBuf<ngx_jacobian> dj(n, jac);
     DevBuf<double> di((size_t)n * nrow * ncol, images);
@@ -1027,6 +1063,7 @@ int ngx_loglike_host(int n, int ngauss, const ngx_gauss *gmix,
                      int ignore_zero_weight, double *out4, double *fdiff,
                      int32_t *status) {
     NGX_REQUIRE(n >= 0 && gmix && images && weights && jac && out4);
+    if (n == 0) return NGX_OK;
     size_t ntot = (size_t)n * nrow * ncol;
     DevBuf<ngx_gauss> dg((size_t)n * ngauss, gmix);
     DevBuf<double> di(ntot, images), dw(ntot, weights);
@@ -1053,6 +1090,7 @@ int ngx_loglike_pixels_host(int n, int ngauss, const ngx_gauss *gmix,
                             const int32_t *npix, double *out4, double *fdiff,
                             int32_t *status) {
     NGX_REQUIRE(n >= 0 && gmix && pixels && npix && out4);
+    if (n == 0) return NGX_OK;
     size_t ntot = (size_t)n * maxpix;
     DevBuf<ngx_gauss> dg((size_t)n * ngauss, gmix);
     DevBuf<ngx_pixel> dp(ntot, pixels);
@@ -1077,6 +1115,7 @@ int ngx_deriv_images_host(int n, int ngauss, const double *gpars,
                           const double *dcov, const ngx_jacobian *jac,
                           int nrow, int ncol, double *out) {
     NGX_REQUIRE(n >= 0 && gpars && dcov && jac && out);
+    if (n == 0) return NGX_OK;
     DevBuf<double> dgp((size_t)n * ngauss * 6, gpars);
     DevBuf<double> ddc((size_t)n * ngauss * 9, dcov);
     DevBuf<ngx_jacobian> dj(n, jac);
