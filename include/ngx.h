@@ -319,6 +319,9 @@ int ngx_admom_host(int n, const double *images, const double *weights,
  * full grid and returns the measured fp64 FMA instructions (lane ops) per
  * second in *dfma_per_s.  Device pointers are not needed. */
 int ngx_peak_dfma(int iters, double *dfma_per_s, double *ms);
+/* FP64 tensor-core probe: warp-level m8n8k4 DMMA instructions per second;
+ * mode 1 interleaves 8 DFMA chains per thread (pipe-sharing check). */
+int ngx_peak_dmma(int iters, int mode, double *dmma_per_s, double *ms);
 
 #ifdef __cplusplus
 }

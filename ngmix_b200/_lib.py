@@ -97,7 +97,7 @@ SYMBOLS = [
     "ngx_gmix_convolve_host", "ngx_make_pixels_host", "ngx_make_coords_host",
     "ngx_render_host", "ngx_loglike_host", "ngx_loglike_pixels_host",
     "ngx_deriv_images_host", "ngx_lm_fit_host", "ngx_em_host",
-    "ngx_admom_host", "ngx_peak_dfma",
+    "ngx_admom_host", "ngx_peak_dfma", "ngx_peak_dmma",
 ]
 
 _lib = None
@@ -448,6 +448,16 @@ def peak_dfma(iters=20000):
     out = C.c_double()
     ms = C.c_double()
     check(lib().ngx_peak_dfma(C.c_int(iters), C.byref(out), C.byref(ms)))
+    return out.value, ms.value
+
+
+def peak_dmma(iters=20000, mode=0):
+    """measured warp-level fp64 m8n8k4 MMA instructions per second"""
+    init()
+    out = C.c_double()
+    ms = C.c_double()
+    check(lib().ngx_peak_dmma(C.c_int(iters), C.c_int(mode), C.byref(out),
+                              C.byref(ms)))
     return out.value, ms.value
 
 

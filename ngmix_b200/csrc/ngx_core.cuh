@@ -460,4 +460,51 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch) {
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------
+// Warp reduction of up to 32 values per lane with a halving butterfly: at
+// each of the five steps a lane hands half of its values to its partner and
+// adds the partner's half of the others, so all NV sums cost NV-1 shuffles
+// in total instead of 5 NV.  On return lane L holds the warp total of v[L]
+// (L < NV) in v[0].  Fixed order, deterministic.
+template <int NV>
+__device__ __forceinline__ void warp_sum_multi(double (&v)[NV]) {
+    static_assert(NV <= 32, "at most one value per lane");
+    const int lane = threadIdx.x & 31;
+    double w[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) w[i] = i < NV ? v[i] : 0.0;
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; i++) {
+            // values that are structurally zero on both sides stay zero
+            if (i >= NV && i + h >= NV) continue;
+            double send = up ? w[i] : w[i + h];
+            double keep = up ? w[i + h] : w[i];
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    v[0] = w[0];
+}
+
+// Block totals of NV <= 32 per-thread values, left in shared memory:
+// out[i] = sum over the block of v[i].  scratch holds 32 doubles per warp.
+// Contains two __syncthreads.
+template <int NV>
+__device__ __forceinline__ void block_sum_to(double (&v)[NV], double *scratch,
+                                             double *out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    warp_sum_multi<NV>(v);
+    if (lane < NV) scratch[warp * 32 + lane] = v[0];
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; w++) s += scratch[w * 32 + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
 }  // namespace ngx

@@ -64,6 +64,7 @@ struct LMShared {
     double psf_row, psf_col, psf_ipsum;
     double cur_ssq, cur_rfirst2, cur_num, cur_den;   // at the accepted x
     ngx_jacobian jac;
+    double tot[48];            // block totals of the pass sums
     int stamp, npix, first_q, status, action, spec;
     int warp_i[32], warp_j[32], warp_k[32];
 };
@@ -890,23 +891,24 @@ k_lm_fit(LMArgs a) {
                 if (!jstatus)
                     deriv_pass<CD>(a, &sh, xp, mix, tmask, val, ierr, rowd,
                                    cold, sums);
-                block_sum<NDSUM>(sums, scratch);
+                block_sum_to<NDSUM>(sums, scratch, sh.tot);
                 PROF_T(pt_pass);
                 if (threadIdx.x == 0) {
+                    const double *tot = sh.tot;
                     if (want_f) {
-                        int acc = feed_residual(a, &sh, xp, sums[27],
+                        int acc = feed_residual(a, &sh, xp, tot[27],
                                                 mix_status);
                         if (acc) {
-                            sh.cur_ssq = sums[27];
-                            sh.cur_num = sums[28];
-                            sh.cur_den = sums[29];
-                            sh.cur_rfirst2 = sums[30];
+                            sh.cur_ssq = tot[27];
+                            sh.cur_num = tot[28];
+                            sh.cur_den = tot[29];
+                            sh.cur_rfirst2 = tot[30];
                             if (sh.st.action == LM_ACT_EVAL_J)
-                                feed_jacobian(a, &sh, sums, jstatus, 1, hs);
+                                feed_jacobian(a, &sh, tot, jstatus, 1, hs);
                         }
                         sh.spec = acc;
                     } else {
-                        feed_jacobian(a, &sh, sums, jstatus, 1, hs);
+                        feed_jacobian(a, &sh, tot, jstatus, 1, hs);
                     }
                 }
             } else if (action == LM_ACT_EVAL_F) {
@@ -919,16 +921,17 @@ k_lm_fit(LMArgs a) {
                 if (!sh.status)
                     value_pass<CV>(a, &sh, mix, tmask, val, ierr, rowd,
                                    cold, sums);
-                block_sum<4>(sums, scratch);
+                block_sum_to<4>(sums, scratch, sh.tot);
                 PROF_T(pt_pass);
                 if (threadIdx.x == 0) {
-                    int acc = feed_residual(a, &sh, sh.xeval, sums[0],
+                    const double *tot = sh.tot;
+                    int acc = feed_residual(a, &sh, sh.xeval, tot[0],
                                             sh.status);
                     if (acc) {
-                        sh.cur_ssq = sums[0];
-                        sh.cur_num = sums[1];
-                        sh.cur_den = sums[2];
-                        sh.cur_rfirst2 = sums[3];
+                        sh.cur_ssq = tot[0];
+                        sh.cur_num = tot[1];
+                        sh.cur_den = tot[2];
+                        sh.cur_rfirst2 = tot[3];
                     }
                     sh.spec = acc;
                 }
@@ -967,13 +970,22 @@ k_lm_fit(LMArgs a) {
                 if (!bad_any)
                     fd_pass<LM_MAXP>(a, &sh, hs, mix, tmask, val, ierr,
                                      rowd, cold, sums);
-                block_sum<FD_NSUM>(sums, scratch);
+                {
+                    double s1[32], s2[FD_NSUM - 32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) s1[i] = sums[i];
+#pragma unroll
+                    for (int i = 32; i < FD_NSUM; i++) s2[i - 32] = sums[i];
+                    block_sum_to<32>(s1, scratch, sh.tot);
+                    block_sum_to<FD_NSUM - 32>(s2, scratch, sh.tot + 32);
+                }
                 if (threadIdx.x == 0) {
                     // feed_jacobian wants {triangle of np, b, r^2} contiguous
                     double *pk = sh.st.T2;
                     const int tri = np * (np + 1) / 2;
-                    for (int i = 0; i < tri; i++) pk[i] = sums[i];
-                    for (int i = 0; i <= np; i++) pk[tri + i] = sums[FD_B0 + i];
+                    for (int i = 0; i < tri; i++) pk[i] = sh.tot[i];
+                    for (int i = 0; i <= np; i++)
+                        pk[tri + i] = sh.tot[FD_B0 + i];
                     feed_jacobian(a, &sh, pk, bad_any, 0, hs);
                 }
             }

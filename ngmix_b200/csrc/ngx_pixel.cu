@@ -713,6 +713,38 @@ __global__ void k_peak_dfma(int iters, double *sink) {
     if (s == 123.456) sink[0] = s;
 }
 
+// FP64 tensor-core probe: mode 0 = 4 independent m8n8k4 DMMA chains per warp,
+// mode 1 = the same interleaved with 8 DFMA chains (do they share a pipe?)
+__device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a,
+                                          double b) {
+    asm volatile(
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, "
+        "{%0,%1};\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+__global__ void k_peak_dmma(int iters, int mode, double *sink) {
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0e-3;
+    double c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double f0 = a, f1 = a + 1, f2 = a + 2, f3 = a + 3, f4 = a + 4, f5 = a + 5,
+           f6 = a + 6, f7 = a + 7;
+    const double m = 1.0000001, k = 1.0e-9;
+    for (int i = 0; i < iters; i++) {
+        dmma8x8x4(c[0], c[1], a, b);
+        dmma8x8x4(c[2], c[3], a, b);
+        dmma8x8x4(c[4], c[5], a, b);
+        dmma8x8x4(c[6], c[7], a, b);
+        if (mode == 1) {
+            f0 = fma(f0, m, k); f1 = fma(f1, m, k); f2 = fma(f2, m, k);
+            f3 = fma(f3, m, k); f4 = fma(f4, m, k); f5 = fma(f5, m, k);
+            f6 = fma(f6, m, k); f7 = fma(f7, m, k);
+        }
+    }
+    double s = c[0] + c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7]
+        + f0 + f1 + f2 + f3 + f4 + f5 + f6 + f7;
+    if (s == 123.456) sink[0] = s;
+}
+
 }  // namespace ngx
 
 using namespace ngx;
@@ -932,6 +964,30 @@ int ngx_peak_dfma(int iters, double *dfma_per_s, double *ms_out) {
     cudaEventDestroy(e1);
     double ops = (double)blocks * threads * 8.0 * iters;
     *dfma_per_s = ops / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return NGX_OK;
+}
+
+int ngx_peak_dmma(int iters, int mode, double *dmma_per_s, double *ms_out) {
+    NGX_REQUIRE(iters > 0 && dmma_per_s);
+    DevBuf<double> sink(1);
+    NGX_CUDA(sink.err);
+    int blocks = sm_count() * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    NGX_CUDA(cudaEventCreate(&e0));
+    NGX_CUDA(cudaEventCreate(&e1));
+    k_peak_dmma<<<blocks, threads>>>(iters / 10 + 1, mode, sink.d);
+    NGX_CUDA(cudaEventRecord(e0));
+    k_peak_dmma<<<blocks, threads>>>(iters, mode, sink.d);
+    NGX_CUDA(cudaEventRecord(e1));
+    NGX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    NGX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // warp-level DMMA instructions per second
+    double ops = (double)blocks * (threads / 32) * 4.0 * iters;
+    *dmma_per_s = ops / (ms * 1e-3);
     if (ms_out) *ms_out = ms;
     return NGX_OK;
 }
