@@ -18,11 +18,85 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def bdf_prior(_lib):
+    """PriorBDFSep of examples/fitting/fitting_bd_empsf.py:101-142"""
+    pr = _lib.Prior()
+    pr.present = 1
+    pr.g_kind = 1
+    pr.cen1, pr.cen2, pr.sigma1, pr.sigma2 = 0.0, 0.0, 0.263, 0.263
+    pr.g_sigma = 0.3
+    pr.T = _lib.Prior1D(1, 0, -1.0, 1.0e3, 0, 0)
+    pr.fracdev = _lib.Prior1D(3, 0, 0.5, 0.1, 0, 0)
+    pr.F = _lib.Prior1D(1, 0, -100.0, 1.0e9, 0, 0)
+    return pr
+
+
+def bench_bdf(args, torch, _lib, sims, dev):
+    """configs[3]: bdf fits (7 pars, 16 x 3 = 48 gaussians, 64x64 stamps,
+    PriorBDFSep, forward-difference Jacobian as the reference's lmdif path)"""
+    n = args.nbdf
+    b = sims.make_bdf_batch(n, seed0=777000, dims=(64, 64), noise=0.02)
+    t = {k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev)
+         for k in ("images", "weights", "jac", "psf", "guess")}
+    d_res = torch.zeros(n * _lib.LM_RESULT_DTYPE.itemsize, dtype=torch.uint8,
+                        device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    pr = bdf_prior(_lib)
+
+    def fit():
+        _lib.lm_fit_device("bdf", n, t["images"].data_ptr(),
+                           t["weights"].data_ptr(), t["jac"].data_ptr(), 64,
+                           64, t["psf"].data_ptr(), 3, t["guess"].data_ptr(),
+                           d_res.data_ptr(), prior=pr, stream=s)
+
+    fit()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fit()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(),
+                        dtype=_lib.LM_RESULT_DTYPE)
+    nfev = res["nfev"].astype(float)
+    o = {"config": "configs[3]: %d bdf fits, 64x64 stamps, 48 gaussians, "
+                   "PriorBDFSep, forward-difference Jacobian" % n,
+         "fits_per_s": n / (ms * 1e-3), "ms_per_step": ms,
+         "median_nfev": float(np.median(nfev)),
+         "nonzero_flags": int((res["flags"] != 0).sum()),
+         # every nfev is one full-mixture evaluation of the stamp
+         "model_pixel_evals_per_s": float(nfev.sum() * 4096 / (ms * 1e-3)),
+         "gaussian_pixel_evals_per_s": float(nfev.sum() * 4096 * 48
+                                             / (ms * 1e-3))}
+    if not args.no_cpu:
+        import oracle
+        cores = os.cpu_count()
+        ns = min(n, 4 * cores)
+        t0 = time.perf_counter()
+        ref = oracle.lm_fit_batch("bdf", b["images"][:ns], b["weights"][:ns],
+                                  b["jac"][:ns], b["psf"][:ns],
+                                  b["guess"][:ns],
+                                  prior=oracle.make_prior("bdf"),
+                                  nthreads=cores)
+        dt = time.perf_counter() - t0
+        o["cpu_port_fits_per_s"] = ns / dt
+        o["cpu_cores"] = cores
+        o["sample"] = ns
+        o["flags_equal_on_sample"] = int((ref["flags"] == res["flags"][:ns]).sum())
+        o["nfev_equal_on_sample"] = int((ref["nfev"] == res["nfev"][:ns]).sum())
+    return o
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nobj", type=int, default=20000)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nbdf", type=int, default=2000,
+                    help="configs[3] sample: bdf fits on 64x64 stamps")
     args = ap.parse_args()
     import torch
     from ngmix_b200 import _lib, sims
@@ -103,6 +177,8 @@ def main():
         out["admom"]["flags_equal_on_sample"] = int(
             (oam["flags"] == ram["flags"][:na]).sum())
         out["admom"]["sample"] = na
+    if args.nbdf > 0:
+        out["bdf"] = bench_bdf(args, torch, _lib, sims, dev)
     print(json.dumps(out))
 
 

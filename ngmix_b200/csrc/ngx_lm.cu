@@ -6,24 +6,28 @@
 // (fitting/leastsqbound.py:445-447) + run_leastsq's epilogue (:70-126) +
 // FitModel.set_fit_result (results.py:45-72).
 //
-// Data movement: the stamp (val, ierr = sqrt(weight); 16 B/pixel) is read
-// from HBM once, lives in shared memory for the whole fit and is never
-// written back; per fit only the 1.2 KB result record goes out.  The
-// reference's 48 B/pixel AoS and the m x n Jacobian never exist.
+// Data movement: the stamp (pixel values and weights, 16 B/pixel) is read
+// from HBM once.  The pixel values live in shared memory (tiled order) for
+// the whole fit; the weights stay in L2 and each pass re-reads them there
+// (ierr = sqrt(w) is recomputed where it is used), which keeps a stamp's
+// shared-memory footprint at 8 B/pixel.  The next stamp of the CTA is
+// prefetched into L2 while the current one is fitted.  Per fit only the
+// 1.2 KB result record goes out; the reference's 48 B/pixel AoS and the
+// m x n Jacobian never exist.
 //
-// Pixel order: the stamp is held in TILED order, 4 rows x 8 columns per
-// 32-pixel tile, so a warp always owns compact 2-d tiles.  A gaussian whose
-// chi^2 < 25 footprint misses a tile is skipped for the whole warp with one
-// vote; the narrow components of the exp/dev mixtures touch only a few
-// tiles.
+// Pixel order: 4 rows x 8 columns per 32-pixel tile, C consecutive tiles per
+// warp and chunk.  Before every pass each tile gets a bit mask of the
+// gaussians whose chi^2 < 25 bounding box can reach it, so a warp only
+// visits gaussians that may contribute; the narrow components of the
+// exp/dev mixtures touch only a few tiles.
 //
-// Work per fit: nfev value passes (16 fp64 instr per gaussian-pixel) and
+// Work per fit: nfev value passes (18 fp64 instr per gaussian-pixel) and
 // njev derivative passes (30 per gaussian-pixel) over pixels kept in
 // registers C at a time with the gaussians in the outer loop; every
-// derivative pass also accumulates J^T J (21) and J^T f (6) per thread and
-// block-reduces them with warp shuffles.  One thread then advances the
-// MINPACK state machine (ngx_lm_solve.cuh) while the other CTAs resident on
-// the SM keep the fp64 pipe busy.
+// derivative pass also accumulates J^T J (21) and J^T f (6) per thread; the
+// 31 sums are reduced with a halving butterfly (31 shuffles per warp).  One
+// thread then advances the MINPACK state machine (ngx_lm_solve.cuh) while
+// the other CTAs resident on the SM keep the fp64 pipe busy.
 #include <cuda_pipeline.h>
 #include "ngx_core.cuh"
 #include "ngx_host.cuh"
@@ -44,6 +48,9 @@ namespace ngx {
 // the 16-entry rotated pn*exp(i) table followed by the constants.
 #define GC_STRIDE 14
 #define REC (16 + GC_STRIDE)
+// The forward-difference pass keeps np + 1 mixtures resident; they use a
+// compact record (row, col, a, b, c, pn) and one shared rotated exp(i) table.
+#define FDREC 6
 
 struct LMArgs {
     int n, model, np, ngauss0, npsf, ngauss, nrow, ncol, ntot;
@@ -65,7 +72,7 @@ struct LMShared {
     double cur_ssq, cur_rfirst2, cur_num, cur_den;   // at the accepted x
     ngx_jacobian jac;
     double tot[48];            // block totals of the pass sums
-    int stamp, npix, first_q, status, action, spec;
+    int stamp, next, npix, first_q, status, action, spec;
     int warp_i[32], warp_j[32], warp_k[32];
 };
 
@@ -75,7 +82,8 @@ struct LMShared {
 // sh->status is OR-ed with range errors.
 __device__ __noinline__ void build_mixture(const LMArgs &a, LMShared *sh,
                                            const double *x, double *mix,
-                                           double area) {
+                                           double area,
+                                           double *compact = nullptr) {
     int k = threadIdx.x;
     if (k >= a.ngauss) return;
     ModelHead h = model_head(a.model, x);
@@ -108,6 +116,14 @@ __device__ __noinline__ void build_mixture(const LMArgs &a, LMShared *sh,
     double drr = irr * idet, drc = irc * idet, dcc = icc * idet;
     double norm = 1.0 / (2 * 3.141592653589793 * sqrt(det));
     double pn = (p * norm) * area;
+    if (compact) {
+        // forward-difference record: row, col, a, b, c, pn
+        double *c = compact + FDREC * k;
+        c[0] = row; c[1] = col;
+        c[2] = -0.5 * dcc; c[3] = -0.5 * drr;
+        c[4] = drc; c[5] = pn;
+    }
+    if (!mix) return;
     double *g = mix + REC * k + 16;
     double ha = -0.25 * dcc, hb = -0.25 * drr;
     g[0] = row; g[1] = col;
@@ -166,6 +182,24 @@ __device__ __forceinline__ void coords_of(const LMArgs &a, const LMShared *sh,
     *u = sh->jac.dudrow * rd + sh->jac.dudcol * cd;
 }
 
+// weight of tiled slot q straight from the caller's weight map (L2-resident:
+// the stamp was prefetched and read once when it was staged); 0 for padding.
+// Only the pixel values live in shared memory: ierr = sqrt(weight) is
+// recomputed where it is used, which halves the footprint of a stamp and
+// lets a fifth CTA fit on the SM.
+__device__ __forceinline__ double weight_of(const LMArgs &a, const double *wt,
+                                            int q) {
+    int row, col;
+    q_to_rowcol(q, a.tpr, &row, &col);
+    double w = 0.0;
+    if (q < a.nq && row < a.nrow && col < a.ncol)
+        w = __ldg(&wt[row * a.ncol + col]);
+    return w;
+}
+__device__ __forceinline__ double ierr_of(double w) {
+    return w > 0.0 ? sqrt(w) : 0.0;
+}
+
 // union of the masks of the C consecutive tiles starting at tile t0
 template <int C>
 __device__ __forceinline__ unsigned tiles_mask(const unsigned *tmask, int t0,
@@ -180,13 +214,14 @@ __device__ __forceinline__ unsigned tiles_mask(const unsigned *tmask, int t0,
 // ---------------------------------------------------------------------
 // value pass: sums = {sum r^2, s2n_numer, s2n_denom, r_first^2}.
 // Each warp takes CV consecutive tiles per chunk.
-template <int CV>
+template <int CV, bool WG>
 __device__ __forceinline__ void value_pass(const LMArgs &a,
                                            const LMShared *sh,
                                            const double *mix,
                                            const unsigned *tmask,
                                            const double *val,
                                            const double *ierr,
+                                           const double *wt,
                                            const double *rowd,
                                            const double *cold,
                                            double (&sums)[4]) {
@@ -197,10 +232,11 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
     sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
     for (int base = 0; base < a.nq; base += T * CV) {
         const int q0 = base + warp * CV * 32 + lane;
-        double v[CV], u[CV], acc[CV];
+        double v[CV], u[CV], acc[CV], wgt[CV];
 #pragma unroll
         for (int c = 0; c < CV; c++) {
             coords_of(a, sh, rowd, cold, q0 + 32 * c, &v[c], &u[c]);
+            wgt[c] = WG ? weight_of(a, wt, q0 + 32 * c) : 0.0;
             acc[c] = 0.0;
         }
         for (int w = 0; w < nwords; w++) {
@@ -244,7 +280,7 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
         for (int c = 0; c < CV; c++) {
             int q = q0 + 32 * c;
             if (q < a.nq) {
-                double ie = ierr[q], d = val[q];
+                double ie = WG ? ierr_of(wgt[c]) : ierr[q], d = val[q];
                 double ivar = ie * ie;
                 double diff = acc[c] - d;
                 double r = diff * ie;
@@ -269,7 +305,7 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
 // sums = {A (21, packed lower triangle row by row), b (6), sum r^2,
 //         s2n_numer, s2n_denom, r_first^2}
 #define NDSUM 31
-template <int CD>
+template <int CD, bool WG>
 __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                                            const LMShared *sh,
                                            const double *x,
@@ -277,6 +313,7 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                                            const unsigned *tmask,
                                            const double *val,
                                            const double *ierr,
+                                           const double *wt,
                                            const double *rowd,
                                            const double *cold,
                                            double (&sums)[NDSUM]) {
@@ -301,11 +338,12 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
 
     for (int base = 0; base < a.nq; base += T * CD) {
         const int q0 = base + warp * CD * 32 + lane;
-        double v[CD], u[CD];
+        double v[CD], u[CD], wgt[CD];
         double S0[CD], S1[CD], S2[CD], MA[CD], MB[CD], MS[CD];
 #pragma unroll
         for (int c = 0; c < CD; c++) {
             coords_of(a, sh, rowd, cold, q0 + 32 * c, &v[c], &u[c]);
+            wgt[c] = WG ? weight_of(a, wt, q0 + 32 * c) : 0.0;
             S0[c] = S1[c] = S2[c] = MA[c] = MB[c] = MS[c] = 0.0;
         }
         for (int w = 0; w < nwords; w++) {
@@ -374,7 +412,7 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
         for (int c = 0; c < CD; c++) {
             int q = q0 + 32 * c;
             if (q < a.nq) {
-                double ie = ierr[q], d = val[q];
+                double ie = WG ? ierr_of(wgt[c]) : ierr[q], d = val[q];
                 // undo the factors folded into the accumulators:
                 // qv = -2 hqv; (q q^T - W) terms carry 4, the cross term 8
                 double ma = 4.0 * MA[c], ms = 4.0 * MS[c], mb = 8.0 * MB[c];
@@ -411,18 +449,20 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
 // forward-difference Jacobian (MINPACK fdjac2) for the models without
 // analytic derivatives (bdf, bd) or analytic_jacobian = 0: evaluates the
 // base mixture and the np perturbed mixtures per pixel.  The mixtures are
-// built by build_mixture into gcs[(np+1)][ngauss][GC_STRIDE] with their own
-// tables; the tile masks come from the base mixture (with slack for the
-// 1.5e-8 relative perturbations).
+// built by build_mixture as compact records fdm[(np+1)][ngauss][FDREC]; the
+// tile masks come from the base mixture (with slack for the 1.5e-8 relative
+// perturbations).
 // sums = {A packed (np(np+1)/2), b (np), sum r^2}
 #define CF 2
 #define FD_B0 (LM_MAXP * (LM_MAXP + 1) / 2)
 #define FD_NSUM (FD_B0 + LM_MAXP + 1)
-template <int NPMAX>
+template <int NPMAX, bool WG>
 __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
-                                        const double *hs, const double *mixes,
+                                        const double *hs, const double *fdm,
+                                        const double *etab,
                                         const unsigned *tmask,
                                         const double *val, const double *ierr,
+                                        const double *wt,
                                         const double *rowd,
                                         const double *cold,
                                         double (&sums)[FD_NSUM]) {
@@ -438,36 +478,40 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
     for (int s = 0; s < NPMAX; s++) hstep[s] = s < np ? hs[s] : 1.0;
     for (int base = 0; base < a.nq; base += T * CF) {
         const int q0 = base + warp * CF * 32 + lane;
-        double v[CF], u[CF];
+        double v[CF], u[CF], wgt[CF];
 #pragma unroll
-        for (int c = 0; c < CF; c++)
+        for (int c = 0; c < CF; c++) {
             coords_of(a, sh, rowd, cold, q0 + 32 * c, &v[c], &u[c]);
+            wgt[c] = WG ? weight_of(a, wt, q0 + 32 * c) : 0.0;
+        }
         double mod[NPMAX + 1][CF];
 #pragma unroll
         for (int s = 0; s <= NPMAX; s++) {
 #pragma unroll
             for (int c = 0; c < CF; c++) mod[s][c] = 0.0;
             if (s > np) continue;
-            const double *mix = mixes + (size_t)s * a.ngauss * REC;
+            const double *recs = fdm + (size_t)s * a.ngauss * FDREC;
             for (int w = 0; w < nwords; w++) {
                 unsigned m = tiles_mask<CF>(tmask, q0 >> 5, ntile, nwords, w);
 #pragma unroll 1
                 while (m) {
                     const int k = 32 * w + __ffs((int)m) - 1;
                     m &= m - 1;
-                    const double *tab = mix + REC * k;
-                    const double2 *g2 = (const double2 *)(tab + 16);
-                    const double2 rc = g2[0], ab = g2[1], cc = g2[2];
+                    const double2 *g2 =
+                        (const double2 *)(recs + FDREC * k);
+                    const double2 rc = g2[0], ab = g2[1], cp = g2[2];
 #pragma unroll
                     for (int c = 0; c < CF; c++) {
                         double dv = v[c] - rc.x;
                         double du = u[c] - rc.y;
-                        double t = fma(cc.y, du, ab.x * dv);
+                        double t = fma(cp.x, du, ab.x * dv);
                         double x = fma(ab.y * du, du, dv * t);
                         unsigned slot;
                         bool inr, ap;
                         double f = fexp_split(x, &slot, &inr, &ap);
-                        double e = tab[slot] * fexp_poly_c(f);
+                        // (exp(i) pn) P(f): the product the per-gaussian
+                        // tables of the other passes hold precomputed
+                        double e = (etab[slot] * cp.y) * fexp_poly_c(f);
                         if (__any_sync(0xffffffffu, ap)) {
                             double wv = apod_window_x(x);
                             if (ap) e *= wv;
@@ -481,7 +525,7 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
         for (int c = 0; c < CF; c++) {
             int q = q0 + 32 * c;
             if (q < a.nq) {
-                double ie = ierr[q], d = val[q];
+                double ie = WG ? ierr_of(wgt[c]) : ierr[q], d = val[q];
                 double r = (mod[0][c] - d) * ie;
                 double j[NPMAX];
 #pragma unroll
@@ -716,31 +760,41 @@ __device__ __noinline__ int feed_residual(const LMArgs &a, LMShared *sh,
 // ---------------------------------------------------------------------
 // MODE 0: analytic Jacobian (gauss/exp/dev), np = 6
 // MODE 1: forward differences (any model), np <= 8
-template <int MODE, int CV, int CD, int MINB, int NT = 128>
+// WG: the weights stay in global memory / L2 (stamps too large to keep both
+// planes in shared memory at four CTAs per SM); otherwise ierr = sqrt(w) is
+// staged next to the pixel values.
+template <int MODE, int CV, int CD, int MINB, bool WG, int NT = 128>
 __global__ void __launch_bounds__(NT, MINB)
 k_lm_fit(LMArgs a) {
     extern __shared__ double smem_d[];
     __shared__ LMShared sh;
     const int T = blockDim.x;
     const int nwarps = T >> 5;
-    const int nmix = (MODE == 0) ? 1 : (a.np + 1);
+    const int nfd = (MODE == 0) ? 0 : (a.np + 1);
     // dynamic shared memory carve-up
-    double *mix = smem_d;                                    // nmix*ngauss*REC
-    double *val = mix + (size_t)nmix * a.ngauss * REC;       // nq
-    double *ierr = val + a.nq;
-    double *rowd = ierr + a.nq;
+    double *mix = smem_d;                                    // ngauss*REC
+    double *fdm = mix + (size_t)a.ngauss * REC;              // nfd*ngauss*FDREC
+    double *etab = fdm + (size_t)nfd * a.ngauss * FDREC;     // 16 (MODE 1)
+    double *val = etab + (nfd ? 16 : 0);                     // nq
+    double *ierr = val + a.nq;                               // nq (!WG)
+    double *rowd = ierr + (WG ? 0 : a.nq);
     double *cold = rowd + a.nrow;
     double *scratch = cold + a.ncol;                         // 48 * nwarps
     double *hs = scratch + 48 * nwarps;                      // 8
     unsigned *tmask = (unsigned *)(hs + 8);                  // ntile*nwords
 
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) sh.stamp = atomicAdd(a.counter, 1);
-        __syncthreads();
-        const int stamp = sh.stamp;
-        if (stamp >= a.n) break;
+    if (nfd) fill_rot_table(etab, 1.0);     // every thread, same values
+    // Work queue: stamps are handed out by an atomic counter, one ahead, so
+    // the stamp after the current one is known early and can be pulled into
+    // L2 while this one is being fitted.
+    if (threadIdx.x == 0) sh.stamp = atomicAdd(a.counter, 1);
+    __syncthreads();
+    int stamp = sh.stamp;
+    int pending = -1;       // stamp whose epilogue (lm_finish) is still owed
+    const int warp_id = threadIdx.x >> 5;
 
+    for (;;) {
+        const bool have = stamp < a.n;
 #ifdef NGX_PROF
         long long pt0 = clock64(), pt_mix = 0, pt_pass = 0, pt_solve = 0,
                   pt_stage = 0, pt_fin = 0, ptx;
@@ -748,52 +802,110 @@ k_lm_fit(LMArgs a) {
 #else
 #define PROF_T(x)
 #endif
-        // ---- stage the stamp in tiled order
-        const double *im = a.images + (size_t)stamp * a.ntot;
-        const double *wt = a.weights + (size_t)stamp * a.ntot;
+        // ---- warp 0: the epilogue of the previous stamp (one thread);
+        //      the other warps meanwhile stage the next stamp, which only
+        //      touches val/ierr and a few words the epilogue does not read
         int cnt = 0, first = a.ntot, firstq = 0;
-        // all global loads of the stamp are issued as asynchronous 8-byte
-        // copies (LDGSTS) straight into their tiled shared-memory slots, so
-        // the ~36 loads per thread overlap instead of each waiting on DRAM
-        for (int q = threadIdx.x; q < a.nq; q += T) {
-            int row, col;
-            q_to_rowcol(q, a.tpr, &row, &col);
-            if (row < a.nrow && col < a.ncol) {
-                int p = row * a.ncol + col;
-                __pipeline_memcpy_async(&val[q], &im[p], sizeof(double));
-                __pipeline_memcpy_async(&ierr[q], &wt[p], sizeof(double));
-            }
-        }
-        __pipeline_commit();
-        __pipeline_wait_prior(0);
-        // each thread converts the entries it fetched itself
-        for (int q = threadIdx.x; q < a.nq; q += T) {
-            int row, col;
-            q_to_rowcol(q, a.tpr, &row, &col);
-            double vv = 0.0, ie = 0.0;
-            if (row < a.nrow && col < a.ncol) {
-                int p = row * a.ncol + col;
-                double w = ierr[q];
-                bool valid = !(a.ignore_zero_weight && w <= 0.0);
-                if (valid) {
-                    vv = val[q];
-                    ie = sqrt(w < 0.0 ? 0.0 : w);
-                    cnt++;
-                    if (p < first) { first = p; firstq = q; }
+        if (warp_id == 0) {
+            if (threadIdx.x == 0) {
+                if (pending >= 0) lm_finish(a, &sh, &a.res[pending]);
+                if (have) {
+                    sh.next = atomicAdd(a.counter, 1);
+                    sh.jac = a.jac[stamp];
+                    sh.status = 0;
                 }
             }
-            val[q] = vv;
-            ierr[q] = ie;
-        }
-        if (threadIdx.x == 0) {
-            sh.jac = a.jac[stamp];
-            sh.status = 0;
-        }
-        if (threadIdx.x < 6 * a.npsf)
-            sh.psf[threadIdx.x] = a.psf[(size_t)stamp * 6 * a.npsf
-                                        + threadIdx.x];
-        {
-            int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        } else if (have) {
+            const double *im = a.images + (size_t)stamp * a.ntot;
+            const double *wt = a.weights + (size_t)stamp * a.ntot;
+            const int t0 = threadIdx.x - 32, TS = T - 32;
+            if (WG) {
+                // the pixel values go straight into their tiled shared-memory
+                // slots as asynchronous 8-byte copies (LDGSTS); the weights are
+                // only inspected here (valid-pixel count, first valid pixel)
+                for (int q = t0; q < a.nq; q += TS) {
+                    int row, col;
+                    q_to_rowcol(q, a.tpr, &row, &col);
+                    if (row < a.nrow && col < a.ncol)
+                        __pipeline_memcpy_async(&val[q], &im[row * a.ncol + col],
+                                                sizeof(double));
+                }
+                __pipeline_commit();
+                if (t0 < 6 * a.npsf)
+                    sh.psf[t0] = a.psf[(size_t)stamp * 6 * a.npsf + t0];
+                unsigned long long invalid = 0;     // per-thread slots, <= 64
+                int slot = 0;
+    #pragma unroll 4
+                for (int q = t0; q < a.nq; q += TS, slot++) {
+                    int row, col;
+                    q_to_rowcol(q, a.tpr, &row, &col);
+                    bool valid = false;
+                    if (row < a.nrow && col < a.ncol) {
+                        int p = row * a.ncol + col;
+                        double w = __ldg(&wt[p]);
+                        valid = !(a.ignore_zero_weight && w <= 0.0);
+                        if (valid) {
+                            cnt++;
+                            if (p < first) { first = p; firstq = q; }
+                        }
+                    }
+                    if (!valid && slot < 64) invalid |= 1ull << slot;
+                }
+                __pipeline_wait_prior(0);
+                // pixels that do not take part hold an exact zero
+                slot = 0;
+                for (int q = t0; q < a.nq; q += TS, slot++) {
+                    if (slot >= 64 || ((invalid >> slot) & 1ull)) {
+                        int row, col;
+                        q_to_rowcol(q, a.tpr, &row, &col);
+                        bool valid = false;
+                        if (slot >= 64 && row < a.nrow && col < a.ncol) {
+                            double w = __ldg(&wt[row * a.ncol + col]);
+                            valid = !(a.ignore_zero_weight && w <= 0.0);
+                        }
+                        if (!valid) val[q] = 0.0;
+                    }
+                }
+            } else {
+                // both planes as asynchronous 8-byte copies (LDGSTS) straight
+                // into their tiled shared-memory slots, so the loads of a
+                // thread overlap instead of each waiting on DRAM
+                for (int q = t0; q < a.nq; q += TS) {
+                    int row, col;
+                    q_to_rowcol(q, a.tpr, &row, &col);
+                    if (row < a.nrow && col < a.ncol) {
+                        int p = row * a.ncol + col;
+                        __pipeline_memcpy_async(&val[q], &im[p],
+                                                sizeof(double));
+                        __pipeline_memcpy_async(&ierr[q], &wt[p],
+                                                sizeof(double));
+                    }
+                }
+                __pipeline_commit();
+                if (t0 < 6 * a.npsf)
+                    sh.psf[t0] = a.psf[(size_t)stamp * 6 * a.npsf + t0];
+                __pipeline_wait_prior(0);
+                // each thread converts the entries it fetched itself
+                for (int q = t0; q < a.nq; q += TS) {
+                    int row, col;
+                    q_to_rowcol(q, a.tpr, &row, &col);
+                    double vv = 0.0, ie = 0.0;
+                    if (row < a.nrow && col < a.ncol) {
+                        int p = row * a.ncol + col;
+                        double w = ierr[q];
+                        bool valid = !(a.ignore_zero_weight && w <= 0.0);
+                        if (valid) {
+                            vv = val[q];
+                            ie = sqrt(w < 0.0 ? 0.0 : w);
+                            cnt++;
+                            if (p < first) { first = p; firstq = q; }
+                        }
+                    }
+                    val[q] = vv;
+                    ierr[q] = ie;
+                }
+            }
+            const int lane = threadIdx.x & 31;
             for (int o = 16; o > 0; o >>= 1) {
                 cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
                 int of = __shfl_xor_sync(0xffffffffu, first, o);
@@ -801,19 +913,33 @@ k_lm_fit(LMArgs a) {
                 if (of < first) { first = of; firstq = oq; }
             }
             if (lane == 0) {
-                sh.warp_i[warp] = cnt;
-                sh.warp_j[warp] = first;
-                sh.warp_k[warp] = firstq;
+                sh.warp_i[warp_id] = cnt;
+                sh.warp_j[warp_id] = first;
+                sh.warp_k[warp_id] = firstq;
             }
         }
+        if (!have) break;
+        pending = -1;
         __syncthreads();
+        const int next = sh.next;
+        if (next < a.n) {
+            // pull the next stamp into L2 while this one is fitted
+            const char *pi = (const char *)(a.images + (size_t)next * a.ntot);
+            const char *pw = (const char *)(a.weights + (size_t)next * a.ntot);
+            const size_t bytes = (size_t)a.ntot * sizeof(double);
+            for (size_t off = (size_t)threadIdx.x * 128; off < bytes;
+                 off += (size_t)T * 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + off));
+            }
+        }
         for (int p = threadIdx.x; p < a.nrow; p += T)
             rowd[p] = p - sh.jac.row0;
         for (int p = threadIdx.x; p < a.ncol; p += T)
             cold[p] = p - sh.jac.col0;
         if (threadIdx.x == 0) {
             int c = 0, f = a.ntot, fq = -1;
-            for (int w = 0; w < nwarps; w++) {
+            for (int w = 1; w < nwarps; w++) {
                 c += sh.warp_i[w];
                 if (sh.warp_j[w] < f) { f = sh.warp_j[w]; fq = sh.warp_k[w]; }
             }
@@ -841,6 +967,7 @@ k_lm_fit(LMArgs a) {
         }
         __syncthreads();
         const double area = sh.jac.scale * sh.jac.scale;
+        const double *wts = a.weights + (size_t)stamp * a.ntot;
 
         if (sh.npix == 0) {
             // GMixFatalError("no weights > 0") at Observation construction
@@ -853,6 +980,8 @@ k_lm_fit(LMArgs a) {
                     r->pars_err[i] = NGX_CDEF;
                 }
             }
+            __syncthreads();
+            stamp = next;
             continue;
         }
 
@@ -889,7 +1018,7 @@ k_lm_fit(LMArgs a) {
                 // calc_jacobian raises for T == 0 or flux == 0
                 int jstatus = mix_status || xp[4] == 0.0 || xp[5] == 0.0;
                 if (!jstatus)
-                    deriv_pass<CD>(a, &sh, xp, mix, tmask, val, ierr, rowd,
+                    deriv_pass<CD, WG>(a, &sh, xp, mix, tmask, val, ierr, wts, rowd,
                                    cold, sums);
                 block_sum_to<NDSUM>(sums, scratch, sh.tot);
                 PROF_T(pt_pass);
@@ -919,7 +1048,7 @@ k_lm_fit(LMArgs a) {
                 PROF_T(pt_mix);
                 double sums[4] = {0, 0, 0, 0};
                 if (!sh.status)
-                    value_pass<CV>(a, &sh, mix, tmask, val, ierr, rowd,
+                    value_pass<CV, WG>(a, &sh, mix, tmask, val, ierr, wts, rowd,
                                    cold, sums);
                 block_sum_to<4>(sums, scratch, sh.tot);
                 PROF_T(pt_pass);
@@ -956,8 +1085,8 @@ k_lm_fit(LMArgs a) {
                         sh.status = 0;
                     }
                     __syncthreads();
-                    build_mixture(a, &sh, sh.xeval,
-                                  mix + (size_t)s * a.ngauss * REC, area);
+                    build_mixture(a, &sh, sh.xeval, s == 0 ? mix : nullptr,
+                                  area, fdm + (size_t)s * a.ngauss * FDREC);
                     __syncthreads();
                     bad_any |= sh.status;
                     __syncthreads();
@@ -968,7 +1097,7 @@ k_lm_fit(LMArgs a) {
 #pragma unroll
                 for (int i = 0; i < FD_NSUM; i++) sums[i] = 0.0;
                 if (!bad_any)
-                    fd_pass<LM_MAXP>(a, &sh, hs, mix, tmask, val, ierr,
+                    fd_pass<LM_MAXP, WG>(a, &sh, hs, fdm, etab, tmask, val, ierr, wts,
                                      rowd, cold, sums);
                 {
                     double s1[32], s2[FD_NSUM - 32];
@@ -998,16 +1127,21 @@ k_lm_fit(LMArgs a) {
             PROF_T(pt_solve);
         }
         PROF_T(pt_solve);
-        if (threadIdx.x == 0) lm_finish(a, &sh, &a.res[stamp]);
 #ifdef NGX_PROF
-        PROF_T(pt_fin);
+        // the epilogue is timed with the next stamp's staging
         if (threadIdx.x == 0) {
+            lm_finish(a, &sh, &a.res[stamp]);
+            PROF_T(pt_fin);
             double *o = a.res[stamp].pars_cov0 + 56;
             o[0] = (double)pt_stage; o[1] = (double)pt_mix;
             o[2] = (double)pt_pass; o[3] = (double)pt_solve;
             o[4] = (double)pt_fin;
         }
+        __syncthreads();
+#else
+        pending = stamp;
 #endif
+        stamp = next;
     }
 }
 
@@ -1098,17 +1232,31 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     // tiled pixel order: 4 x 8 tiles, one per warp
     a.tpr = (ncol + 7) / 8;
     a.nq = 32 * a.tpr * ((nrow + 3) / 4);
-    int nmix = analytic ? 1 : np + 1;
+    int nfd = analytic ? 0 : np + 1;
     int nwarps = threads / 32;
+    // shared memory without the ierr plane
     size_t smem = sizeof(double)
-        * ((size_t)nmix * a.ngauss * REC + 2 * (size_t)a.nq
-           + nrow + ncol + 48 * nwarps + 8
+        * ((size_t)a.ngauss * REC + (size_t)nfd * a.ngauss * FDREC
+           + (nfd ? 16 : 0) + (size_t)a.nq + nrow + ncol + 48 * nwarps + 8
            + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
-    if (analytic)
-        return config_and_launch(k_lm_fit<0, 3, 2, 4>, a, threads, smem,
-                                 as_stream(stream));
-    return config_and_launch(k_lm_fit<1, 3, 2, 4>, a, threads, smem,
-                             as_stream(stream));
+    // keep ierr = sqrt(w) in shared memory too when four CTAs (the register
+    // limit) still fit on an SM; larger stamps leave the weights in L2
+    size_t smem_both = smem + sizeof(double) * (size_t)a.nq;
+    size_t per_cta = smem_both + sizeof(LMShared) + 1024;
+    bool wg = 4 * per_cta > (size_t)smem_optin_bytes() + 1024;
+    cudaStream_t st = as_stream(stream);
+    if (analytic) {
+        if (wg)
+            return config_and_launch(k_lm_fit<0, 3, 2, 4, true>, a, threads,
+                                     smem, st);
+        return config_and_launch(k_lm_fit<0, 3, 2, 4, false>, a, threads,
+                                 smem_both, st);
+    }
+    if (wg)
+        return config_and_launch(k_lm_fit<1, 3, 2, 4, true>, a, threads, smem,
+                                 st);
+    return config_and_launch(k_lm_fit<1, 3, 2, 4, false>, a, threads,
+                             smem_both, st);
 }
 
 int ngx_lm_fit_host(int n, int model, const double *images,
