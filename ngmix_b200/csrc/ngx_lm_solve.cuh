@@ -49,6 +49,11 @@ struct LMState {
     double R[LM_MAXP * LM_MAXP];   // column major, upper triangle = R
     int ipvt[LM_MAXP];
     double fnorm, xnorm, delta, par, gnorm, pnorm;
+    // predicted reduction and directional derivative of the proposed step
+    // (lmder's prered / dirder): they depend only on the factorisation and
+    // the step, so lm_propose computes them and the caller can tell a likely
+    // final evaluation (prered <= ftol) before running it
+    double prered, dirder;
     // workspace.  The state lives in shared memory on the device; keeping the
     // temporaries here (not in per-thread local arrays) matters: local memory
     // is interleaved by lane, so one thread walking a local array touches a
@@ -320,6 +325,8 @@ NGX_HD NGX_NI static void lm_init(LMState *s, int n, const double *x0, int maxfe
     s->gnorm = 0.0;
     s->pnorm = 0.0;
     s->fnorm = 0.0;
+    s->prered = 1.0;
+    s->dirder = 0.0;
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
         s->x[i] = x0[i];
@@ -343,6 +350,19 @@ NGX_HD NGX_NI static void lm_propose(LMState *s) {
     }
     s->pnorm = lm_enorm(n, wa3);
     if (s->iter == 1) s->delta = lm_min(s->delta, s->pnorm);
+    // |R P^T p|
+#pragma unroll 1
+    for (int j = 0; j < n; j++) wa3[j] = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+        double temp = s->step[s->ipvt[j]];
+#pragma unroll 1
+        for (int i = 0; i <= j; i++) wa3[i] += s->R[i + LM_MAXP * j] * temp;
+    }
+    double temp1 = lm_enorm(n, wa3) / s->fnorm;
+    double temp2 = (sqrt(s->par) * s->pnorm) / s->fnorm;
+    s->prered = temp1 * temp1 + temp2 * temp2 / 0.5;
+    s->dirder = -(temp1 * temp1 + temp2 * temp2);
     s->action = LM_ACT_EVAL_F;
 }
 
@@ -365,20 +385,7 @@ NGX_HD NGX_NI static int lm_feed_f(LMState *s, double fnorm_new) {
         double r = fnorm1 / s->fnorm;
         actred = 1.0 - r * r;
     }
-    // |R P^T p|
-    double *wa3 = s->v[5];
-#pragma unroll 1
-    for (int j = 0; j < n; j++) wa3[j] = 0.0;
-#pragma unroll 1
-    for (int j = 0; j < n; j++) {
-        double temp = s->step[s->ipvt[j]];
-#pragma unroll 1
-        for (int i = 0; i <= j; i++) wa3[i] += s->R[i + LM_MAXP * j] * temp;
-    }
-    double temp1 = lm_enorm(n, wa3) / s->fnorm;
-    double temp2 = (sqrt(s->par) * s->pnorm) / s->fnorm;
-    double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
-    double dirder = -(temp1 * temp1 + temp2 * temp2);
+    const double prered = s->prered, dirder = s->dirder;
     double ratio = 0.0;
     if (prered != 0.0) ratio = actred / prered;
     if (ratio <= 0.25) {
