@@ -1276,11 +1276,12 @@ int ngx_lm_fit_host(int n, int model, const double *images,
     // chunked, double-buffered pipeline: H2D of chunk i+1 overlaps the fit
     // of chunk i when the host arrays are pinned
     const size_t ntot = (size_t)nrow * ncol;
-    // chunk schedule: a short first chunk (one wave of CTAs) so the first
-    // kernel starts after ~20 MB of H2D instead of a full chunk, then chunks
-    // of four waves
+    // chunk schedule: the pipeline is bound by the H2D copy (PCIe), so what
+    // is exposed is the first chunk's copy and the last chunk's fit: a short
+    // first chunk (one wave of CTAs, ~20 MB) and then chunks of two waves,
+    // whose fit (~0.6 ms) hides behind the next chunk's copy (~0.8 ms)
     const int wave = 4 * sm_count();
-    int chunk = 4 * wave;
+    int chunk = 2 * wave;
     if (chunk > n) chunk = n;
     int first_chunk = wave < chunk ? wave : chunk;
     static thread_local double *d_im[2] = {nullptr, nullptr};
