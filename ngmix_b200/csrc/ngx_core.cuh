@@ -219,12 +219,23 @@ __device__ __forceinline__ void apod_pair(double x, double *w, double *wc) {
     *wc = fma(12.0 * umu, umu, ww);
 }
 
+// tile -> (tile row, tile column) without the ~20-instruction integer
+// division: (tile + 1/2) / tpr in fp32 truncates to the exact quotient for
+// any tile count below 2^20
+__device__ __forceinline__ void tile_rowcol(int tile, int tpr, int *trow,
+                                            int *tcol) {
+    int r = __float2int_rz(__fdividef((float)tile + 0.5f, (float)tpr));
+    *trow = r;
+    *tcol = tile - r * tpr;
+}
+
 // 4 x 8 pixel tile -> centre and half extents in (v, u)
 __device__ __forceinline__ void tile_extent(const ngx_jacobian &j, int tile,
                                             int tpr, int nrow, int ncol,
                                             double *vc, double *uc,
                                             double *hv, double *hu) {
-    int trow = tile / tpr, tcol = tile - trow * tpr;
+    int trow, tcol;
+    tile_rowcol(tile, tpr, &trow, &tcol);
     int r0 = trow << 2, c0 = tcol << 3;
     int r1 = min(r0 + 3, nrow - 1), c1 = min(c0 + 7, ncol - 1);
     double rc = 0.5 * (r0 + r1) - j.row0, cc = 0.5 * (c0 + c1) - j.col0;
@@ -303,7 +314,8 @@ __device__ __forceinline__ double eval_exact(const ngx_gauss &g, double v,
 __device__ __forceinline__ void q_to_rowcol(int q, int tpr, int *row,
                                             int *col) {
     int tile = q >> 5, w = q & 31;
-    int trow = tile / tpr, tcol = tile - trow * tpr;
+    int trow, tcol;
+    tile_rowcol(tile, tpr, &trow, &tcol);
     *row = (trow << 2) + (w >> 3);
     *col = (tcol << 3) + (w & 7);
 }

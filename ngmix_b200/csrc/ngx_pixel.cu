@@ -5,6 +5,7 @@
 //   ngx_loglike / ngx_loglike_pixels   (gmix_nb.py:824-937, one fused pass)
 //   ngx_deriv_images                   (fitting/derivs_nb.py:40-127)
 // plus library management and the *_host staging variants.
+#include <cuda_pipeline.h>
 #include "ngx_core.cuh"
 #include "ngx_host.cuh"
 
@@ -437,11 +438,14 @@ k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
     extern __shared__ double smem_d[];
     const int ntile = nq >> 5;
     const int nwords = (ngauss + 31) >> 5;
-    double *scratch = smem_d;                   // 4 * 32
-    double *mix = scratch + 4 * 32;             // ngauss * LLT_REC
+    double *scratch = smem_d;                   // 32 + 32 * 8 (warps)
+    double *mix = scratch + 32 * 9;             // ngauss * LLT_REC
     unsigned *tmask = (unsigned *)(mix + LLT_REC * ngauss);  // ntile * nwords
     int *segoff = (int *)(tmask + (size_t)ntile * nwords);  // nrow * tpr
     int *rowoff = segoff + nrow * tpr;          // nrow
+    // the stamp itself, tiled order (8-byte aligned after the int tables)
+    double *val_s = (double *)(((uintptr_t)(rowoff + nrow) + 7) & ~(uintptr_t)7);
+    double *wt_s = val_s + nq;
     __shared__ int bad;
     const int T = blockDim.x;
     const int obj = blockIdx.x;
@@ -452,6 +456,19 @@ k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
     const double *im = images + (size_t)obj * ntot;
     const double *wt = weights + (size_t)obj * ntot;
     if (threadIdx.x == 0) bad = 0;
+    // start the stamp's trip from HBM now (asynchronous 8-byte copies into
+    // the tiled slots); it is first needed after the mixture set-up
+    for (int q = threadIdx.x; q < nq; q += T) {
+        int row, col;
+        q_to_rowcol(q, tpr, &row, &col);
+        if (row < nrow && col < ncol) {
+            __pipeline_memcpy_async(&val_s[q], &im[row * ncol + col],
+                                    sizeof(double));
+            __pipeline_memcpy_async(&wt_s[q], &wt[row * ncol + col],
+                                    sizeof(double));
+        }
+    }
+    __pipeline_commit();
     __syncthreads();
     for (int k = threadIdx.x; k < ngauss; k += T) {
         ngx_gauss g = gmix[(size_t)obj * ngauss + k];
@@ -463,6 +480,8 @@ k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
         c[6] = 5.0 * sqrt(g.irr); c[7] = 5.0 * sqrt(g.icc);
         fill_rot_table(mix + LLT_REC * k, g.pnorm * area);
     }
+    __pipeline_wait_prior(0);
+    __syncthreads();
     if (fdiff) {
         // valid pixels per 8-pixel row segment
         for (int base = 0; base < nq; base += T) {
@@ -470,10 +489,8 @@ k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
             int row, col;
             q_to_rowcol(q, tpr, &row, &col);
             bool valid = false;
-            if (q < nq && row < nrow && col < ncol) {
-                double w = wt[row * ncol + col];
-                valid = !(ignore_zero_weight && w <= 0.0);
-            }
+            if (q < nq && row < nrow && col < ncol)
+                valid = !(ignore_zero_weight && wt_s[q] <= 0.0);
             unsigned bal = __ballot_sync(0xffffffffu, valid);
             if ((lane & 7) == 0 && q < nq && row < nrow)
                 segoff[row * tpr + (col >> 3)] =
@@ -588,11 +605,10 @@ k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
             bool valid = false;
             double d = 0.0, ie = 0.0;
             if (q < nq && row < nrow && col < ncol) {
-                int p = row * ncol + col;
-                double w = wt[p];
+                double w = wt_s[q];
                 valid = !(ignore_zero_weight && w <= 0.0);
                 if (valid) {
-                    d = im[p];
+                    d = val_s[q];
                     ie = sqrt(w < 0.0 ? 0.0 : w);
                 }
             }
@@ -613,12 +629,12 @@ k_loglike_tiled(int ngauss, const ngx_gauss *__restrict__ gmix,
             }
         }
     }
-    block_sum<4>(sums, scratch);
+    block_sum_to<4>(sums, scratch + 32, scratch);
     if (threadIdx.x == 0) {
-        out4[4 * (size_t)obj + 0] = -0.5 * sums[0];
-        out4[4 * (size_t)obj + 1] = sums[1];
-        out4[4 * (size_t)obj + 2] = sums[2];
-        out4[4 * (size_t)obj + 3] = sums[3];
+        out4[4 * (size_t)obj + 0] = -0.5 * scratch[0];
+        out4[4 * (size_t)obj + 1] = scratch[1];
+        out4[4 * (size_t)obj + 2] = scratch[2];
+        out4[4 * (size_t)obj + 3] = scratch[3];
         if (status) status[obj] = NGX_ST_OK;
     }
 }
@@ -891,10 +907,15 @@ static int launch_loglike(int src, int n, int ngauss, const ngx_gauss *gmix,
         int tpr = (ncol + 7) / 8;
         int nq = 32 * tpr * ((nrow + 3) / 4);
         size_t smt = sizeof(double)
-            * (4 * 32 + LLT_REC * (size_t)ngauss
-               + ((size_t)(nq / 32) * ((ngauss + 31) / 32) + 1) / 2)
+            * (32 * 9 + LLT_REC * (size_t)ngauss
+               + ((size_t)(nq / 32) * ((ngauss + 31) / 32) + 1) / 2
+               + 2 * (size_t)nq + 1)
             + sizeof(int) * ((size_t)nrow * tpr + nrow);
-        NGX_REQUIRE(smt <= 48 * 1024);
+        if (smt > (size_t)smem_optin_bytes())
+            return fail(NGX_ERR_ARG, "ngx_loglike: stamp too large%s%s");
+        NGX_CUDA(cudaFuncSetAttribute(
+            k_loglike_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int)smt));
         k_loglike_tiled<<<n, 256, smt, as_stream(stream)>>>(
             ngauss, gmix, images, weights, jac, nrow, ncol, tpr, nq,
             ignore_zero_weight, out4, fdiff, status);
