@@ -1,0 +1,224 @@
+"""
+ObservationBatch: N same-size stamps resident on the GPU.
+
+The reference builds one Observation per stamp on the host and recomputes its
+pixel array at every mutation (ngmix/observation.py:814-830,
+ngmix/pixels/pixels.py:6-52); at the kernel rates of this engine that host
+work, and the host->device copy of the stamps, is what bounds a pipeline
+(SURVEY.md 8f rank 1).  An ObservationBatch uploads the stacked arrays once
+and every fitter then runs on the resident copy: PSF EM -> PSF mixture ->
+galaxy LM fit chain without the stamps or the PSF mixtures leaving the
+device.  Pixel construction (v, u, ierr, zero-weight handling; pixels_nb.py)
+happens inside the kernels from (image, weight, jacobian).
+
+Device memory is held in torch tensors (plumbing only); all arithmetic goes
+through the C ABI's device-pointer entry points (include/ngx.h).
+"""
+import numpy as np
+
+from . import _lib
+from .defaults import DEFAULT_LM_PARS
+from .gmix import get_model_name, get_model_num, get_model_npars
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class ObservationBatch(object):
+    """
+    N stamps [n, H, W] with weights, jacobians and (optionally) psf mixtures
+    on one device.
+
+    Use from_arrays or from_observations to construct.
+    """
+
+    def __init__(self, images, weights, jac, psf_pars=None, device=0,
+                 ignore_zero_weight=True):
+        torch = _torch()
+        _lib.init(device)
+        self.device = torch.device("cuda", device)
+        self.ignore_zero_weight = bool(ignore_zero_weight)
+        self.images = self._up(images)
+        self.weights = self._up(weights)
+        if self.images.dim() != 3 or self.images.shape != self.weights.shape:
+            raise ValueError("images and weights must both be [n, H, W]")
+        self.n, self.nrow, self.ncol = (int(x) for x in self.images.shape)
+        self.jac = self._up(_lib.as_jac(jac, self.n) if not self._is_tensor(jac)
+                            else jac)
+        self.psf_pars = None
+        self.npsf = 0
+        if psf_pars is not None:
+            self.set_psf(psf_pars)
+
+    # ------------------------------------------------------------ building
+    @classmethod
+    def from_arrays(cls, images, weights, jacobians, psf_pars=None, device=0,
+                    ignore_zero_weight=True):
+        """
+        images, weights: [n, H, W] (numpy, pinned or pageable, or torch)
+        jacobians: [n, 8] rows (row0, col0, dvdrow, dvdcol, dudrow, dudcol,
+            det, scale) or Jacobian records
+        psf_pars: [n, npsf, 6] full gaussian parameters, optional
+        """
+        return cls(images, weights, jacobians, psf_pars=psf_pars,
+                   device=device, ignore_zero_weight=ignore_zero_weight)
+
+    @classmethod
+    def from_observations(cls, obslist, device=0):
+        """stack same-size Observations; psf mixtures are taken from
+        obs.psf.gmix when every observation has one"""
+        if len(obslist) == 0:
+            raise ValueError("empty observation list")
+        images = np.stack([o.image for o in obslist])
+        weights = np.stack([o.weight for o in obslist])
+        jac = np.stack([np.asarray(o.jacobian._data.view("f8")).reshape(8)
+                        for o in obslist])
+        psf = None
+        if all(o.has_psf_gmix() for o in obslist):
+            psf = np.stack([o.psf.gmix.get_full_pars().reshape(-1, 6)
+                            for o in obslist])
+        izw = all(getattr(o, "_ignore_zero_weight", True) for o in obslist)
+        return cls(images, weights, jac, psf_pars=psf, device=device,
+                   ignore_zero_weight=izw)
+
+    def _is_tensor(self, a):
+        return _torch().is_tensor(a)
+
+    def _up(self, a):
+        torch = _torch()
+        if torch.is_tensor(a):
+            return a.to(device=self.device, dtype=torch.float64).contiguous()
+        a = np.ascontiguousarray(a, dtype="f8")
+        return torch.from_numpy(a).to(self.device, non_blocking=True)
+
+    def set_psf(self, psf_pars):
+        """psf mixtures as full parameters [n, npsf, 6]; a device tensor (for
+        example the output of em()) is adopted without a copy"""
+        t = self._up(psf_pars).reshape(self.n, -1, 6)
+        self.psf_pars = t
+        self.npsf = int(t.shape[1])
+
+    def __len__(self):
+        return self.n
+
+    @property
+    def dims(self):
+        return self.nrow, self.ncol
+
+    def _stream(self):
+        return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def _empty_records(self, dtype):
+        torch = _torch()
+        return torch.zeros(max(self.n, 1) * dtype.itemsize, dtype=torch.uint8,
+                           device=self.device)
+
+    def _records(self, t, dtype):
+        return np.frombuffer(t.cpu().numpy().tobytes(),
+                             dtype=dtype)[:self.n].copy()
+
+    # ------------------------------------------------------------- fitters
+    def fit(self, model, guesses, prior=None, fit_pars=None,
+            analytic_jacobian=True, return_device=False):
+        """
+        Levenberg-Marquardt fit of every stamp (Fitter.go,
+        fitting/fitters.py:64-112) on the resident data.  guesses [n, npars].
+        Returns the LM_RESULT_DTYPE records (numpy), or the raw device buffer
+        with return_device=True.
+        """
+        from .fitting import _prior_record, _LM_MODELS
+        model = get_model_name(get_model_num(model))
+        if model not in _LM_MODELS:
+            raise ValueError("model '%s' cannot be fit with ngx_lm_fit" % model)
+        np_ = get_model_npars(model)
+        g = self._up(guesses).reshape(self.n, np_)
+        fp = dict(DEFAULT_LM_PARS)
+        if fit_pars is not None:
+            fp.update(fit_pars)
+        out = self._empty_records(_lib.LM_RESULT_DTYPE)
+        if self.n > 0:
+            _lib.lm_fit_device(
+                model, self.n, self.images.data_ptr(), self.weights.data_ptr(),
+                self.jac.data_ptr(), self.nrow, self.ncol,
+                self.psf_pars.data_ptr() if self.npsf else 0, self.npsf,
+                g.data_ptr(), out.data_ptr(), prior=_prior_record(prior),
+                maxfev=fp["maxfev"], ftol=fp["ftol"], xtol=fp["xtol"],
+                analytic_jacobian=analytic_jacobian,
+                ignore_zero_weight=self.ignore_zero_weight,
+                stream=self._stream())
+        if return_device:
+            return out
+        return self._records(out, _lib.LM_RESULT_DTYPE)
+
+    def em(self, guesses, use_psf=False, variant="full", tol=1.0e-5,
+           miniter=None, maxiter=500, vary_sky=False, sky=None,
+           return_device=False):
+        """
+        EM fit of every stamp (EMFitter.go, em/em.py:228-317); guesses
+        [n, ngauss, 6] full parameters.  Returns (records, pars [n,ngauss,6]);
+        with return_device=True pars stays a device tensor, ready for
+        set_psf() of another batch.
+        """
+        torch = _torch()
+        g = self._up(guesses).reshape(self.n, -1, 6)
+        ngauss = int(g.shape[1])
+        if miniter is None:
+            miniter = 20 if variant == "fluxonly" else 40
+        pars = torch.zeros((self.n, ngauss, 6), dtype=torch.float64,
+                           device=self.device)
+        out = self._empty_records(_lib.EM_RESULT_DTYPE)
+        npsf = self.npsf if use_psf else 0
+        if self.n > 0:
+            _lib.em_device(
+                self.n, self.images.data_ptr(), self.weights.data_ptr(),
+                self.jac.data_ptr(), self.nrow, self.ncol, g.data_ptr(),
+                ngauss, pars.data_ptr(), out.data_ptr(),
+                d_psf=self.psf_pars.data_ptr() if npsf else 0, npsf=npsf,
+                variant=variant, tol=tol, miniter=miniter, maxiter=maxiter,
+                vary_sky=vary_sky, sky=sky,
+                ignore_zero_weight=self.ignore_zero_weight,
+                stream=self._stream())
+        res = self._records(out, _lib.EM_RESULT_DTYPE)
+        if return_device:
+            return res, pars
+        return res, pars.cpu().numpy()
+
+    def admom(self, guesses, maxiter=200, shiftmax=5.0, etol=1.0e-5,
+              Ttol=1.0e-3, cenonly=False):
+        """adaptive moments of every stamp (admom/admom.py:325-360); guesses
+        [n, 6] full parameters of the weight gaussian"""
+        g = self._up(guesses).reshape(self.n, 6)
+        out = self._empty_records(_lib.ADMOM_RESULT_DTYPE)
+        if self.n > 0:
+            _lib.admom_device(
+                self.n, self.images.data_ptr(), self.weights.data_ptr(),
+                self.jac.data_ptr(), self.nrow, self.ncol, g.data_ptr(),
+                out.data_ptr(), maxiter=maxiter, shiftmax=shiftmax, etol=etol,
+                Ttol=Ttol, cenonly=cenonly, stream=self._stream())
+        return self._records(out, _lib.ADMOM_RESULT_DTYPE)
+
+    # -------------------------------------------------------------- pixels
+    def make_pixels(self):
+        """the reference's pixel records (pixels/pixels.py:6-52) for every
+        stamp: (pixels [n, H*W], npix [n]); pixels[i, :npix[i]] are valid"""
+        return _lib.make_pixels(self.images.cpu().numpy(),
+                                self.weights.cpu().numpy(),
+                                self.jac.cpu().numpy(),
+                                ignore_zero_weight=self.ignore_zero_weight)
+
+    def shard(self, rank, world_size):
+        """contiguous index range of this batch owned by `rank` (no copy)"""
+        from .shard import shard_range
+        lo, hi = shard_range(self.n, rank, world_size)
+        sub = object.__new__(ObservationBatch)
+        sub.device = self.device
+        sub.ignore_zero_weight = self.ignore_zero_weight
+        sub.images = self.images[lo:hi]
+        sub.weights = self.weights[lo:hi]
+        sub.jac = self.jac[lo:hi]
+        sub.n, sub.nrow, sub.ncol = hi - lo, self.nrow, self.ncol
+        sub.psf_pars = None if self.psf_pars is None else self.psf_pars[lo:hi]
+        sub.npsf = self.npsf
+        return sub
