@@ -31,6 +31,59 @@ def bdf_prior(_lib):
     return pr
 
 
+def bench_gaussmom(args, torch, _lib, b, t, dev):
+    """Gaussian-weighted moments (GaussMom, fwhm 1.2) of the PSF stamps"""
+    import ngmix_b200 as ngmix
+    n = b["images"].shape[0]
+    out = {}
+    for nmom in (6, 17):
+        gm = ngmix.GaussMom(1.2, with_higher_order=(nmom == 17)).weight
+        wt = np.repeat(gm.get_data()[None, :], n, axis=0)
+        d_wt = torch.from_numpy(
+            np.frombuffer(wt.tobytes(), dtype=np.uint8).copy()).to(dev)
+        maxrad = 100.0 * float(np.sqrt(gm.get_T() / 2.0))
+        d_mr = torch.full((n,), maxrad, dtype=torch.float64, device=dev)
+        d_res = torch.zeros(n * _lib.MOM_RESULT_DTYPE.itemsize,
+                            dtype=torch.uint8, device=dev)
+        s = torch.cuda.current_stream().cuda_stream
+
+        def fn():
+            _lib.weighted_sums_device(
+                n, 1, d_wt.data_ptr(), t["images"].data_ptr(),
+                t["weights"].data_ptr(), t["jac"].data_ptr(), 25, 25,
+                d_mr.data_ptr(), nmom, d_res.data_ptr(), stream=s)
+
+        fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        o = {"stamps_per_s": n / (ms * 1e-3), "ms_per_step": ms}
+        if not args.no_cpu:
+            import oracle
+            ns = min(n, 2000)
+            wpars = gm.get_full_pars()
+            t0 = time.perf_counter()
+            refs = [oracle.weighted_sums(b["images"][i], b["weights"][i],
+                                         b["jac"][i], wpars, maxrad, nmom)
+                    for i in range(ns)]
+            dt = time.perf_counter() - t0
+            rec = np.frombuffer(d_res.cpu().numpy().tobytes(),
+                                dtype=_lib.MOM_RESULT_DTYPE)
+            worst = max(np.abs(rec["sums"][i][:nmom] - refs[i]["sums"]).max()
+                        / np.abs(refs[i]["sums"]).max() for i in range(ns))
+            o["cpu_port_stamps_per_s_1core"] = ns / dt
+            o["max_rel_diff_sums_on_sample"] = float(worst)
+            o["sample"] = ns
+        out["nmom%d" % nmom] = o
+    return out
+
+
 def bench_bdf(args, torch, _lib, sims, dev):
     """configs[3]: bdf fits (7 pars, 16 x 3 = 48 gaussians, 64x64 stamps,
     PriorBDFSep, forward-difference Jacobian as the reference's lmdif path)"""
@@ -177,6 +230,7 @@ def main():
         out["admom"]["flags_equal_on_sample"] = int(
             (oam["flags"] == ram["flags"][:na]).sum())
         out["admom"]["sample"] = na
+    out["gaussmom"] = bench_gaussmom(args, torch, _lib, b, t, dev)
     if args.nbdf > 0:
         out["bdf"] = bench_bdf(args, torch, _lib, sims, dev)
     print(json.dumps(out))

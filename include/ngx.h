@@ -267,6 +267,26 @@ int ngx_admom(int n, const double *images, const double *weights,
               const ngx_jacobian *jac, int nrow, int ncol, const double *guess,
               const ngx_admom_conf *conf, ngx_admom_result *res, void *stream);
 
+/* weighted moments: get_weighted_sums / get_higher_order_weighted_sums
+ * (gmix/gmix_nb.py:681-821), the pass behind GMix.get_weighted_sums
+ * (gmix/gmix.py:706-754) and GaussMom.go (gaussmom.py:49-73).
+ * gmix [n,ngauss] is the weight mixture (norms are set on a private copy; a
+ * range error sets flags = NGX_GMIX_RANGE_ERROR), maxrad [n] the radius cut
+ * in (v,u) units, nmom 6 or 17.  sums_cov holds [nmom][nmom] row major in its
+ * leading nmom*nmom entries (the layout of get_moments_result_dtype). */
+#define NGX_NMOM_MAX 17
+typedef struct {
+    int32_t flags, npix;
+    double wsum;
+    double sums[NGX_NMOM_MAX];
+    double sums_cov[NGX_NMOM_MAX * NGX_NMOM_MAX];
+} ngx_mom_result;
+int ngx_weighted_sums(int n, int ngauss, const ngx_gauss *gmix,
+                      const double *images, const double *weights,
+                      const ngx_jacobian *jac, int nrow, int ncol,
+                      const double *maxrad, int nmom, int ignore_zero_weight,
+                      ngx_mom_result *res, void *stream);
+
 /* ------------------------------------------------------------------ */
 /* host-buffer variants (synchronous; H2D/D2H inside) */
 int ngx_gmix_fill_host(int n, int model, int ngauss, const double *pars,
@@ -313,6 +333,11 @@ int ngx_admom_host(int n, const double *images, const double *weights,
                    const ngx_jacobian *jac, int nrow, int ncol,
                    const double *guess, const ngx_admom_conf *conf,
                    ngx_admom_result *res);
+int ngx_weighted_sums_host(int n, int ngauss, const ngx_gauss *gmix,
+                           const double *images, const double *weights,
+                           const ngx_jacobian *jac, int nrow, int ncol,
+                           const double *maxrad, int nmom,
+                           int ignore_zero_weight, ngx_mom_result *res);
 
 /* FP64 pipe micro-benchmark used for the roofline denominator: runs a
  * register-resident chain of `iters` x 8 independent DFMAs per thread on a

@@ -23,5 +23,6 @@ from . import fitting, em, admom  # noqa: F401
 from .fitting import Fitter, fit_batch  # noqa: F401
 from .em import EMFitter, run_em, em_batch  # noqa: F401
 from .admom import AdmomFitter, run_admom, admom_batch  # noqa: F401
-from . import joint_prior  # noqa: F401
+from . import joint_prior, moments, gaussmom  # noqa: F401
+from .gaussmom import GaussMom, gaussmom_batch  # noqa: F401
 from .batch import ObservationBatch  # noqa: F401

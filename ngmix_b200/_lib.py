@@ -98,6 +98,7 @@ SYMBOLS = [
     "ngx_render_host", "ngx_loglike_host", "ngx_loglike_pixels_host",
     "ngx_deriv_images_host", "ngx_lm_fit_host", "ngx_em_host",
     "ngx_admom_host", "ngx_peak_dfma", "ngx_peak_dmma",
+    "ngx_weighted_sums", "ngx_weighted_sums_host",
 ]
 
 _lib = None
@@ -440,6 +441,46 @@ def admom(images, weights, jac, guess, maxiter=200, shiftmax=5.0,
                                C.c_int(H), C.c_int(W), _p(guess),
                                C.byref(conf), _p(res)))
     return res
+
+
+MOM_RESULT_DTYPE = np.dtype([
+    ("flags", "i4"), ("npix", "i4"), ("wsum", "f8"), ("sums", "f8", 17),
+    ("sums_cov", "f8", 17 * 17)], align=True)
+assert MOM_RESULT_DTYPE.itemsize == 2464
+
+
+def weighted_sums(gm, images, weights, jac, maxrad, nmom=6,
+                  ignore_zero_weight=True):
+    """batched get_weighted_sums / get_higher_order_weighted_sums: gm
+    [n, ngauss] weight mixtures (GAUSS_DTYPE), maxrad [n]; returns
+    MOM_RESULT_DTYPE [n] (sums_cov is [nmom, nmom] in its leading entries)"""
+    init()
+    images = _f8(images)
+    weights = _f8(weights)
+    if images.ndim == 2:
+        images, weights = images[None], weights[None]
+    n, H, W = images.shape
+    jac = as_jac(jac, n)
+    gm = np.ascontiguousarray(gm, dtype=GAUSS_DTYPE).reshape(n, -1)
+    maxrad = np.ascontiguousarray(np.broadcast_to(_f8(maxrad), (n,)))
+    res = np.zeros(n, dtype=MOM_RESULT_DTYPE)
+    check(lib().ngx_weighted_sums_host(
+        C.c_int(n), C.c_int(gm.shape[1]), _p(gm), _p(images), _p(weights),
+        _p(jac), C.c_int(H), C.c_int(W), _p(maxrad), C.c_int(nmom),
+        C.c_int(int(ignore_zero_weight)), _p(res)))
+    return res
+
+
+def weighted_sums_device(n, ngauss, d_gmix, d_images, d_weights, d_jac, nrow,
+                         ncol, d_maxrad, nmom, d_res, ignore_zero_weight=True,
+                         stream=0):
+    """device-pointer weighted-moment pass (asynchronous on `stream`)"""
+    check(lib().ngx_weighted_sums(
+        C.c_int(n), C.c_int(ngauss), C.c_void_p(d_gmix),
+        C.c_void_p(d_images), C.c_void_p(d_weights), C.c_void_p(d_jac),
+        C.c_int(nrow), C.c_int(ncol), C.c_void_p(d_maxrad), C.c_int(nmom),
+        C.c_int(int(ignore_zero_weight)), C.c_void_p(d_res),
+        C.c_void_p(stream)))
 
 
 def peak_dfma(iters=20000):

@@ -199,6 +199,43 @@ class ObservationBatch(object):
                 Ttol=Ttol, cenonly=cenonly, stream=self._stream())
         return self._records(out, _lib.ADMOM_RESULT_DTYPE)
 
+    def gaussmom(self, fwhm, with_higher_order=False, return_records=False):
+        """
+        Gaussian-weighted moments of every stamp (GaussMom.go,
+        gaussmom.py:49-73) on the resident data: a list of result dicts, or
+        the raw MOM_RESULT_DTYPE records with return_records=True.
+        """
+        torch = _torch()
+        from .gaussmom import GaussMom, _to_flux_units
+        from .gmix import get_weighted_moments_stats, moments_record
+        gm = GaussMom(fwhm, with_higher_order).weight
+        nmom = 17 if with_higher_order else 6
+        wt = np.repeat(gm.get_data()[None, :], max(self.n, 1), axis=0)
+        d_wt = torch.from_numpy(
+            np.frombuffer(wt.tobytes(), dtype=np.uint8).copy()).to(self.device)
+        d_maxrad = torch.full((max(self.n, 1),),
+                              100.0 * float(np.sqrt(gm.get_T() / 2.0)),
+                              dtype=torch.float64, device=self.device)
+        out = self._empty_records(_lib.MOM_RESULT_DTYPE)
+        if self.n > 0:
+            _lib.weighted_sums_device(
+                self.n, 1, d_wt.data_ptr(), self.images.data_ptr(),
+                self.weights.data_ptr(), self.jac.data_ptr(), self.nrow,
+                self.ncol, d_maxrad.data_ptr(), nmom, out.data_ptr(),
+                ignore_zero_weight=self.ignore_zero_weight,
+                stream=self._stream())
+        recs = self._records(out, _lib.MOM_RESULT_DTYPE)
+        if return_records:
+            return recs
+        scale = self.jac[:, 7].cpu().numpy()
+        res = []
+        for i in range(self.n):
+            r = get_weighted_moments_stats(moments_record(recs[i], nmom))
+            if r["flags"] == 0:
+                _to_flux_units(r, 1.0 / scale[i] ** 2)
+            res.append(r)
+        return res
+
     # -------------------------------------------------------------- pixels
     def make_pixels(self):
         """the reference's pixel records (pixels/pixels.py:6-52) for every

@@ -1,0 +1,264 @@
+// ngx_weighted_sums: gaussian-mixture weighted moments of a stamp.
+//
+// Replaces get_weighted_sums / get_higher_order_weighted_sums
+// (ngmix/gmix/gmix_nb.py:681-821), the single pixel pass behind
+// GMix.get_weighted_sums / get_weighted_moments (gmix/gmix.py:674-754) and
+// GaussMom.go (gaussmom.py:49-73).  One CTA per stamp; pixels are built on
+// the fly from (image, weight, jacobian) exactly as fill_pixels does
+// (pixels_nb.py:6-58), the weight mixture is evaluated with the exact
+// exponential (gmix_eval_pixel, gmix_nb.py:95-105).
+//
+// Sums: nmom first moments F_i weighted by w * val, their covariance
+// sum w^2 var F_i F_j (upper triangle, mirrored on output), wsum and npix.
+// 6 moments need 29 accumulators and one pixel pass; 17 moments need 172,
+// taken in seven row groups of at most 32 accumulators so that they stay in
+// registers (the single weight gaussian is cheap to re-evaluate).  Reductions
+// are halving butterflies in a fixed order: deterministic.
+#include "ngx_core.cuh"
+#include "ngx_host.cuh"
+
+namespace ngx {
+
+// the moment basis (gmix_nb.py:713-718, 784-807); v, u are offsets from the
+// weight centre except in F[0], F[1], which are the pixel's own coordinates
+template <int NMOM>
+__device__ __forceinline__ void mom_basis(double pv, double pu, double v,
+                                          double u, double r2,
+                                          double (&F)[NMOM]) {
+    F[0] = pv;
+    F[1] = pu;
+    if (NMOM == 6) {
+        F[2] = u * u - v * v;
+        F[3] = 2 * v * u;
+        F[4] = r2;
+        F[5] = 1.0;
+    } else {
+        double u2 = u * u, v2 = v * v, vu = v * u;
+        double u4 = u2 * u2, v4 = v2 * v2;
+        double r4 = r2 * r2, r6 = r4 * r2, r8 = r6 * r2;
+        F[2] = u2 - v2;
+        F[3] = 2 * vu;
+        F[4] = r2;
+        F[5] = 1.0;
+        F[6] = u * r2;
+        F[7] = v * r2;
+        F[8] = u * (u2 - 3 * v2);
+        F[9] = v * (3 * u2 - v2);
+        F[10] = r4;
+        F[11] = r2 * (u2 - v2);
+        F[12] = r2 * 2 * u * v;
+        F[13] = u4 - 6 * u2 * v2 + v4;
+        F[14] = (u2 - v2) * 4 * u * v;
+        F[15] = r6;
+        F[16] = r8;
+    }
+}
+
+// number of upper-triangle entries of covariance rows [I0, I1)
+__host__ __device__ constexpr int tri_rows(int nmom, int i0, int i1) {
+    int c = 0;
+    for (int i = i0; i < i1; i++) c += nmom - i;
+    return c;
+}
+
+struct MomArgs {
+    int ngauss, nrow, ncol, ignore_zero_weight;
+    const ngx_gauss *gmix;      // normalised copy in shared memory
+    const double *im, *wt;
+    ngx_jacobian jac;
+    double maxrad2;
+};
+
+// One pixel pass accumulating covariance rows [I0, I1) (upper triangle)
+// and, with FIRST, the nmom sums, wsum and npix.  Results go to shared
+// memory: out[0 .. NACC).
+template <int NMOM, int I0, int I1, bool FIRST>
+__device__ __forceinline__ void mom_pass(const MomArgs &a, double *scratch,
+                                         double *out) {
+    constexpr int NCOV = tri_rows(NMOM, I0, I1);
+    constexpr int NACC = NCOV + (FIRST ? NMOM + 2 : 0);
+    static_assert(NACC <= 32, "row group too large");
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+    const int ntot = a.nrow * a.ncol;
+    const double area = a.jac.scale * a.jac.scale;
+    const double vcen = a.gmix[0].row, ucen = a.gmix[0].col;
+    for (int p = threadIdx.x; p < ntot; p += blockDim.x) {
+        double ivar = a.wt[p];
+        if (a.ignore_zero_weight && ivar <= 0.0) continue;   // fill_pixels
+        if (ivar < 0.0) ivar = 0.0;
+        double ierr = sqrt(ivar);
+        int row = p / a.ncol, col = p - row * a.ncol;
+        double rowdiff = row - a.jac.row0, coldiff = col - a.jac.col0;
+        double pv = a.jac.dvdrow * rowdiff + a.jac.dvdcol * coldiff;
+        double pu = a.jac.dudrow * rowdiff + a.jac.dudcol * coldiff;
+        double v = pv - vcen, u = pu - ucen;
+        double r2 = u * u + v * v;
+        if (!(r2 < a.maxrad2)) continue;
+        // get_weighted_sums also requires ierr > 0 (:708); the higher-order
+        // version does not (:773)
+        if (NMOM == 6 && !(ierr > 0.0)) continue;
+        double weight = 0.0;
+        for (int k = 0; k < a.ngauss; k++)
+            weight += eval_exact(a.gmix[k], pv, pu, area);
+        double var = 1.0 / (ierr * ierr);
+        double F[NMOM];
+        mom_basis<NMOM>(pv, pu, v, u, r2, F);
+        double w2v = (weight * weight) * var;
+        int q = 0;
+#pragma unroll
+        for (int i = I0; i < I1; i++) {
+            double wf = w2v * F[i];
+#pragma unroll
+            for (int j = i; j < NMOM; j++) {
+                acc[q] += wf * F[j];
+                q++;
+            }
+        }
+        if (FIRST) {
+            double wdata = weight * a.im[p];
+#pragma unroll
+            for (int i = 0; i < NMOM; i++) acc[NCOV + i] += wdata * F[i];
+            acc[NCOV + NMOM] += weight;
+            acc[NCOV + NMOM + 1] += 1.0;
+        }
+    }
+    block_sum_to<NACC>(acc, scratch, out);
+}
+
+// copy a reduced row group into the result record (thread 0)
+template <int NMOM, int I0, int I1, bool FIRST>
+__device__ __forceinline__ void mom_store(const double *tot,
+                                          ngx_mom_result *r) {
+    constexpr int NCOV = tri_rows(NMOM, I0, I1);
+    int q = 0;
+    for (int i = I0; i < I1; i++)
+        for (int j = i; j < NMOM; j++) {
+            r->sums_cov[i * NMOM + j] = tot[q];
+            r->sums_cov[j * NMOM + i] = tot[q];
+            q++;
+        }
+    if (FIRST) {
+        for (int i = 0; i < NMOM; i++) r->sums[i] = tot[NCOV + i];
+        r->wsum = tot[NCOV + NMOM];
+        r->npix = (int)(tot[NCOV + NMOM + 1] + 0.5);
+    }
+}
+
+template <int NMOM, int I0, int I1, bool FIRST>
+__device__ __forceinline__ void mom_group(const MomArgs &a, double *scratch,
+                                          double *tot, ngx_mom_result *r) {
+    mom_pass<NMOM, I0, I1, FIRST>(a, scratch, tot);
+    if (threadIdx.x == 0) mom_store<NMOM, I0, I1, FIRST>(tot, r);
+    __syncthreads();
+}
+
+template <int NMOM>
+__global__ void __launch_bounds__(128)
+k_weighted_sums(int ngauss, const ngx_gauss *__restrict__ gmix,
+                const double *__restrict__ images,
+                const double *__restrict__ weights,
+                const ngx_jacobian *__restrict__ jac, int nrow, int ncol,
+                const double *__restrict__ maxrad, int ignore_zero_weight,
+                ngx_mom_result *__restrict__ res) {
+    extern __shared__ double smem_d[];
+    double *scratch = smem_d;                       // 32 * nwarps
+    double *tot = scratch + 32 * (blockDim.x >> 5); // 32
+    ngx_gauss *gm = (ngx_gauss *)(tot + 32);        // ngauss
+    __shared__ int bad;
+    const int obj = blockIdx.x;
+    const size_t ntot = (size_t)nrow * ncol;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < ngauss; k += blockDim.x) {
+        ngx_gauss g = gmix[(size_t)obj * ngauss + k];
+        if (gauss_set_norm(g) != NGX_ST_OK) bad = 1;
+        gm[k] = g;
+    }
+    __syncthreads();
+    ngx_mom_result *r = &res[obj];
+    if (threadIdx.x == 0) {
+        r->flags = bad ? NGX_GMIX_RANGE_ERROR : 0;
+        r->npix = 0;
+        r->wsum = 0.0;
+        for (int i = 0; i < NGX_NMOM_MAX; i++) r->sums[i] = 0.0;
+        for (int i = 0; i < NGX_NMOM_MAX * NGX_NMOM_MAX; i++)
+            r->sums_cov[i] = 0.0;
+    }
+    if (bad) return;
+    MomArgs a;
+    a.ngauss = ngauss; a.nrow = nrow; a.ncol = ncol;
+    a.ignore_zero_weight = ignore_zero_weight;
+    a.gmix = gm;
+    a.im = images + obj * ntot;
+    a.wt = weights + obj * ntot;
+    a.jac = jac[obj];
+    a.maxrad2 = maxrad[obj] * maxrad[obj];
+    __syncthreads();
+    if (NMOM == 6) {
+        mom_group<6, 0, 6, true>(a, scratch, tot, r);      // 21 + 8
+    } else {
+        mom_group<17, 0, 1, false>(a, scratch, tot, r);    // 17
+        mom_group<17, 1, 2, false>(a, scratch, tot, r);    // 16
+        mom_group<17, 2, 4, false>(a, scratch, tot, r);    // 29
+        mom_group<17, 4, 6, false>(a, scratch, tot, r);    // 25
+        mom_group<17, 6, 9, false>(a, scratch, tot, r);    // 30
+        mom_group<17, 9, 13, false>(a, scratch, tot, r);   // 26
+        mom_group<17, 13, 17, true>(a, scratch, tot, r);   // 10 + 19
+    }
+}
+
+}  // namespace ngx
+
+using namespace ngx;
+
+extern "C" {
+
+int ngx_weighted_sums(int n, int ngauss, const ngx_gauss *gmix,
+                      const double *images, const double *weights,
+                      const ngx_jacobian *jac, int nrow, int ncol,
+                      const double *maxrad, int nmom, int ignore_zero_weight,
+                      ngx_mom_result *res, void *stream) {
+    NGX_REQUIRE(n >= 0 && ngauss >= 1 && ngauss <= NGX_MAX_GAUSS);
+    NGX_REQUIRE(nrow >= 1 && ncol >= 1 && (nmom == 6 || nmom == 17));
+    NGX_REQUIRE(gmix && images && weights && jac && maxrad && res);
+    if (n == 0) return NGX_OK;
+    const int threads = 128;
+    size_t smem = sizeof(double) * (32 * (threads / 32) + 32)
+        + sizeof(ngx_gauss) * (size_t)ngauss;
+    if (nmom == 6)
+        k_weighted_sums<6><<<n, threads, smem, as_stream(stream)>>>(
+            ngauss, gmix, images, weights, jac, nrow, ncol, maxrad,
+            ignore_zero_weight, res);
+    else
+        k_weighted_sums<17><<<n, threads, smem, as_stream(stream)>>>(
+            ngauss, gmix, images, weights, jac, nrow, ncol, maxrad,
+            ignore_zero_weight, res);
+    NGX_LAUNCH_CHECK();
+    return NGX_OK;
+}
+
+int ngx_weighted_sums_host(int n, int ngauss, const ngx_gauss *gmix,
+                           const double *images, const double *weights,
+                           const ngx_jacobian *jac, int nrow, int ncol,
+                           const double *maxrad, int nmom,
+                           int ignore_zero_weight, ngx_mom_result *res) {
+    NGX_REQUIRE(n >= 0 && gmix && images && weights && jac && maxrad && res);
+    if (n == 0) return NGX_OK;
+    size_t ntot = (size_t)n * nrow * ncol;
+    DevBuf<ngx_gauss> dg((size_t)n * ngauss, gmix);
+    DevBuf<double> di(ntot, images), dw(ntot, weights), dm(n, maxrad);
+    DevBuf<ngx_jacobian> dj(n, jac);
+    DevBuf<ngx_mom_result> dr(n);
+    NGX_CUDA(dg.err); NGX_CUDA(di.err); NGX_CUDA(dw.err); NGX_CUDA(dm.err);
+    NGX_CUDA(dj.err); NGX_CUDA(dr.err);
+    int rc = ngx_weighted_sums(n, ngauss, dg.d, di.d, dw.d, dj.d, nrow, ncol,
+                               dm.d, nmom, ignore_zero_weight, dr.d, 0);
+    if (rc) return rc;
+    NGX_CUDA(cudaDeviceSynchronize());
+    NGX_CUDA(dr.to_host(res));
+    return NGX_OK;
+}
+
+}  // extern "C"

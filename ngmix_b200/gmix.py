@@ -304,6 +304,38 @@ class GMix(object):
     def get_model_s2n(self, obs):
         return np.sqrt(self.get_model_s2n_sum(obs))
 
+    def get_weighted_sums(self, obs, maxrad=None, with_higher_order=False,
+                          res=None):
+        """
+        Weighted moment sums with this mixture as the weight
+        (gmix/gmix.py:706-754 -> gmix_nb.py:681-821) through
+        ngx_weighted_sums.  Returns a record with flags, npix, wsum, sums,
+        sums_cov, pars, F; when `res` is sent the sums are added to it.
+        """
+        self.set_norms_if_needed()
+        if maxrad is None:
+            maxrad = 100 * np.sqrt(self.get_T() / 2)
+        nmom = 17 if with_higher_order else 6
+        rec = _lib.weighted_sums(
+            self._data[None], obs.image, obs.weight, obs.jacobian._data,
+            maxrad, nmom,
+            ignore_zero_weight=getattr(obs, "_ignore_zero_weight", True))[0]
+        if rec["flags"] & 128:      # NGX_GMIX_RANGE_ERROR
+            raise GMixRangeError("det or T too low")
+        new = moments_record(rec, nmom)
+        if res is None:
+            return new
+        for name in ("npix", "wsum", "sums", "sums_cov"):
+            res[name] += new[name]
+        return res
+
+    def get_weighted_moments(self, obs, maxrad=None, with_higher_order=False):
+        """weighted moments with e1, e2, T, s2n etc.
+        (gmix/gmix.py:674-704)"""
+        res = self.get_weighted_sums(obs, maxrad=maxrad,
+                                     with_higher_order=with_higher_order)
+        return get_weighted_moments_stats(res)
+
     # ---- pure host helpers -------------------------------------------
     def get_sheared(self, s1, s2=None):
         from .shape import Shape, get_sheared_moments
@@ -447,6 +479,41 @@ class GMixCoellip(GMixModel):
 
     def copy(self):
         return GMixCoellip(self._pars)
+
+
+def get_moments_result_dtype(with_higher_order=False):
+    """gmix/gmix.py:1314-1330"""
+    nmom = 17 if with_higher_order else 6
+    return [("flags", "i4"), ("npix", "i4"), ("wsum", "f8"),
+            ("sums", "f8", nmom), ("sums_cov", "f8", (nmom, nmom)),
+            ("pars", "f8", nmom), ("F", "f8", nmom)]
+
+
+def moments_record(rec, nmom):
+    """one ngx_mom_result -> a record of the reference's moments dtype"""
+    out = np.zeros(1, dtype=np.dtype(
+        get_moments_result_dtype(with_higher_order=(nmom == 17)),
+        align=True))[0]
+    out["flags"] = 0
+    out["npix"] = rec["npix"]
+    out["wsum"] = rec["wsum"]
+    out["sums"] = rec["sums"][:nmom]
+    out["sums_cov"] = rec["sums_cov"][:nmom * nmom].reshape(nmom, nmom)
+    return out
+
+
+def get_weighted_moments_stats(ares):
+    """summary statistics of a moments record (gmix/gmix.py:1295-1311)"""
+    from . import moments
+    res = {}
+    for name in ares.dtype.names:
+        if name in ("sums", "sums_cov"):
+            res[name] = ares[name].copy()
+        else:
+            res[name] = ares[name]
+    res.update(moments.make_mom_result(res["sums"].copy(),
+                                       res["sums_cov"].copy(), res["wsum"]))
+    return res
 
 
 def gmix_concat(gmixes):

@@ -608,6 +608,68 @@ def gen_lm_bdf():
     save("lm_bdf", **out)
 
 
+def gen_moments():
+    """GaussMom (6 and 17 moments) on galaxy stamps, and get_weighted_sums
+    with a two-gaussian off-centre weight and a maxrad"""
+    from ngmix.gaussmom import GaussMom
+    b = sims.make_lm_batch(12, seed0=9100, noise=0.05)
+    n = b["images"].shape[0]
+    # a masked stamp and a low-S/N stamp
+    rng = np.random.RandomState(91)
+    b["weights"][3][rng.uniform(size=b["weights"][3].shape) < 0.15] = 0.0
+    b["images"][5] = rng.normal(0.0, 0.05, size=b["images"][5].shape)
+    out = {k: b[k] for k in ("images", "weights", "jac")}
+    out["fwhm"] = np.array(1.2)
+    stat_keys = ("flags", "flux_flags", "T_flags", "flux", "flux_err", "T",
+                 "T_err", "s2n", "e1", "e2", "sums_norm", "wsum")
+    for nmom, tag in ((6, "m6"), (17, "m17")):
+        fitter = GaussMom(fwhm=1.2, with_higher_order=(nmom == 17))
+        res = {k: np.zeros(n) for k in stat_keys}
+        res["npix"] = np.zeros(n, "i4")
+        res["sums"] = np.zeros((n, nmom))
+        res["sums_cov"] = np.zeros((n, nmom, nmom))
+        res["sums_err"] = np.zeros((n, 6))
+        res["e_err"] = np.zeros((n, 2))
+        res["pars"] = np.zeros((n, 6)) + np.nan
+        for i in range(n):
+            obs = ngmix.Observation(b["images"][i], weight=b["weights"][i],
+                                    jacobian=jac_from_record(b["jac"][i]))
+            r = fitter.go(obs)
+            for k in stat_keys:
+                res[k][i] = r[k]
+            res["npix"][i] = r["npix"]
+            res["sums"][i] = r["sums"]
+            res["sums_cov"][i] = r["sums_cov"]
+            res["sums_err"][i] = r["sums_err"][:6]
+            res["e_err"][i] = r["e_err"]
+            if "pars" in r and r["flags"] == 0:
+                res["pars"][i] = r["pars"][:6]
+        print(tag, "flags", res["flags"], "T", res["T"][:4])
+        for k, v in res.items():
+            out[tag + "_" + k] = v
+    # raw sums with a general weight mixture and a radius cut
+    wt_pars = np.array([0.6, 0.05, -0.03, 0.20, 0.02, 0.25,
+                        0.4, -0.04, 0.06, 0.45, -0.05, 0.38])
+    wt = ngmix.GMix(pars=wt_pars)
+    out["wt_pars"] = wt_pars
+    out["maxrad"] = np.array(2.5)
+    for nmom, tag in ((6, "w6"), (17, "w17")):
+        sums = np.zeros((n, nmom))
+        cov = np.zeros((n, nmom, nmom))
+        wsum = np.zeros(n)
+        npix = np.zeros(n, "i4")
+        for i in range(n):
+            obs = ngmix.Observation(b["images"][i], weight=b["weights"][i],
+                                    jacobian=jac_from_record(b["jac"][i]))
+            r = wt.get_weighted_sums(obs, maxrad=2.5,
+                                     with_higher_order=(nmom == 17))
+            sums[i], cov[i] = r["sums"], r["sums_cov"]
+            wsum[i], npix[i] = r["wsum"], r["npix"]
+        out[tag + "_sums"], out[tag + "_sums_cov"] = sums, cov
+        out[tag + "_wsum"], out[tag + "_npix"] = wsum, npix
+    save("moments", **out)
+
+
 GENERATORS = {
     "fastexp": gen_fastexp,
     "gmix": gen_gmix,
@@ -617,6 +679,7 @@ GENERATORS = {
     "lm_other": gen_lm_other,
     "em_admom": gen_em_admom,
     "lm_bdf": gen_lm_bdf,
+    "moments": gen_moments,
 }
 
 if __name__ == "__main__":

@@ -9,6 +9,7 @@
  */
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include "oracle.h"
 
 #define GMIX_LOW_DETVAL 1.0e-200     /* gmix_nb.py:11 */
@@ -506,4 +507,89 @@ void ora_deriv_images(const double *gpars, const double *dcov, int ngauss,
             }
         }
     }
+}
+
+/* ------------------------------------------------------------------ */
+/* weighted moments, gmix_nb.py:681-821.  The weight is the mixture evaluated
+ * with the exact exponential (gmix_eval_pixel, gmix_nb.py:95-105). */
+static double gmix_eval_exact(const ora_gauss *gmix, int n, double v,
+                              double u, double area) {
+    double s = 0.0;
+    for (int k = 0; k < n; k++) s += gauss_eval_exact(&gmix[k], v, u, area);
+    return s;
+}
+
+int ora_weighted_sums(ora_gauss *wt, int ngauss, const ora_pixel *pixels,
+                      int npix, double maxrad, int nmom, ora_mom_result *res) {
+    if (wt[0].norm_set == 0)
+        if (ora_gmix_set_norms(wt, ngauss)) return ORA_RANGE_ERROR;
+    double maxrad2 = maxrad * maxrad;
+    double vcen = wt[0].row, ucen = wt[0].col;
+    double F[ORA_NMOM_MAX];
+    for (int ip = 0; ip < npix; ip++) {
+        const ora_pixel *px = &pixels[ip];
+        double v = px->v - vcen, u = px->u - ucen;
+        double r2 = u * u + v * v;
+        /* :708 requires ierr > 0 as well; the higher-order version :773 does
+         * not */
+        if (!(r2 < maxrad2)) continue;
+        if (nmom == 6 && !(px->ierr > 0.0)) continue;
+        double weight = gmix_eval_exact(wt, ngauss, px->v, px->u, px->area);
+        double var = 1.0 / (px->ierr * px->ierr);
+        double wdata = weight * px->val;
+        double w2 = weight * weight;
+        F[0] = px->v;
+        F[1] = px->u;
+        if (nmom == 6) {
+            F[2] = u * u - v * v;
+            F[3] = 2 * v * u;
+            F[4] = r2;
+            F[5] = 1.0;
+        } else {
+            double u2 = u * u, v2 = v * v, vu = v * u;
+            double u4 = u2 * u2, v4 = v2 * v2;
+            double r4 = r2 * r2, r6 = r4 * r2, r8 = r6 * r2;
+            F[2] = u2 - v2;
+            F[3] = 2 * vu;
+            F[4] = r2;
+            F[5] = 1.0;
+            F[6] = u * r2;
+            F[7] = v * r2;
+            F[8] = u * (u2 - 3 * v2);
+            F[9] = v * (3 * u2 - v2);
+            F[10] = r4;
+            F[11] = r2 * (u2 - v2);
+            F[12] = r2 * 2 * u * v;
+            F[13] = u4 - 6 * u2 * v2 + v4;
+            F[14] = (u2 - v2) * 4 * u * v;
+            F[15] = r6;
+            F[16] = r8;
+        }
+        res->wsum += weight;
+        res->npix += 1;
+        for (int i = 0; i < nmom; i++) {
+            res->sums[i] += wdata * F[i];
+            for (int j = 0; j < nmom; j++)
+                res->sums_cov[i * nmom + j] += w2 * var * F[i] * F[j];
+        }
+    }
+    return ORA_OK;
+}
+
+int ora_weighted_sums_go(const double *image, const double *weight, int nrow,
+                         int ncol, const ora_jac *jac, const double *wt_pars,
+                         int ngauss, double maxrad, int nmom,
+                         int ignore_zero_weight, ora_mom_result *res) {
+    int ntot = nrow * ncol;
+    ora_pixel *pixels = (ora_pixel *)malloc(sizeof(ora_pixel) * (size_t)ntot);
+    ora_gauss *wt = (ora_gauss *)malloc(sizeof(ora_gauss) * (size_t)ngauss);
+    int npix = ora_fill_pixels(pixels, ntot, image, weight, nrow, ncol, jac,
+                               ignore_zero_weight);
+    memset(res, 0, sizeof(*res));
+    int st = ora_gmix_fill(ORA_FULL, wt_pars, 6 * ngauss, wt, ngauss);
+    if (st == ORA_OK)
+        st = ora_weighted_sums(wt, ngauss, pixels, npix, maxrad, nmom, res);
+    free(pixels);
+    free(wt);
+    return st;
 }

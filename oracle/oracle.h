@@ -211,4 +211,23 @@ int ora_admom_go_batch(int n, int nthreads, const double *images,
                        const double *jacs, const double *guess_pars,
                        const ora_admom_conf *conf, ora_admom_result *res);
 
+/* ---- weighted moments (ngmix/gmix/gmix_nb.py:681-821) ---- */
+#define ORA_NMOM_MAX 17
+typedef struct {
+    int32_t flags, npix;
+    double wsum;
+    double sums[ORA_NMOM_MAX];
+    double sums_cov[ORA_NMOM_MAX * ORA_NMOM_MAX];   /* [nmom][nmom] in the
+                                                       leading nmom*nmom */
+} ora_mom_result;
+/* adds to res (the reference accumulates into the caller's record);
+ * nmom = 6 (get_weighted_sums) or 17 (get_higher_order_weighted_sums) */
+int ora_weighted_sums(ora_gauss *wt, int ngauss, const ora_pixel *pixels,
+                      int npix, double maxrad, int nmom, ora_mom_result *res);
+/* from image/weight/jacobian: fill_pixels + the sums, fresh record */
+int ora_weighted_sums_go(const double *image, const double *weight, int nrow,
+                         int ncol, const ora_jac *jac, const double *wt_pars,
+                         int ngauss, double maxrad, int nmom,
+                         int ignore_zero_weight, ora_mom_result *res);
+
 #endif

@@ -419,3 +419,29 @@ def admom_go_batch(images, weights, jacs, guess_pars, nthreads=1, **kw):
                              _p(weights), C.c_int(H), C.c_int(W), _p(jacs),
                              _p(guess_pars), _p(conf), _p(res))
     return res
+
+
+# ------------------------------------------------------------ weighted moments
+MOM_RESULT_DTYPE = np.dtype([
+    ("flags", "i4"), ("npix", "i4"), ("wsum", "f8"), ("sums", "f8", 17),
+    ("sums_cov", "f8", 17 * 17)], align=True)
+
+
+def weighted_sums(image, weight, jac, wt_pars, maxrad, nmom=6,
+                  ignore_zero_weight=True):
+    """get_weighted_sums / get_higher_order_weighted_sums
+    (gmix_nb.py:681-821) from image/weight/jacobian with the weight mixture
+    given as full parameters; returns dict(sums, sums_cov, wsum, npix)"""
+    image, weight, jac = _f8(image), _f8(weight), _f8(jac)
+    wt_pars = _f8(wt_pars).ravel()
+    res = np.zeros(1, dtype=MOM_RESULT_DTYPE)
+    st = lib().ora_weighted_sums_go(
+        _p(image), _p(weight), C.c_int(image.shape[0]),
+        C.c_int(image.shape[1]), _p(jac), _p(wt_pars),
+        C.c_int(wt_pars.size // 6), C.c_double(maxrad), C.c_int(nmom),
+        C.c_int(int(ignore_zero_weight)), _p(res))
+    assert st == 0
+    r = res[0]
+    return dict(sums=r["sums"][:nmom].copy(),
+                sums_cov=r["sums_cov"][:nmom * nmom].reshape(nmom, nmom).copy(),
+                wsum=float(r["wsum"]), npix=int(r["npix"]))

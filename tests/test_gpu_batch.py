@@ -87,6 +87,23 @@ def test_psf_em_to_galaxy_fit_chain_on_device(ngx):
     assert np.all(got["flags"][res["flags"] == 0] >= 0)
 
 
+def test_batch_gaussmom_equals_host_call(ngx):
+    import ngmix_b200 as ngmix
+    from ngmix_b200 import sims
+    b = sims.make_lm_batch(16, seed0=8500, noise=0.05)
+    ob = ngmix.ObservationBatch.from_arrays(b["images"], b["weights"],
+                                            b["jac"])
+    for higher in (False, True):
+        got = ob.gaussmom(1.2, with_higher_order=higher)
+        ref = ngmix.gaussmom_batch(b["images"], b["weights"], b["jac"], 1.2,
+                                   with_higher_order=higher)
+        for a, r in zip(got, ref):
+            assert a["flags"] == r["flags"]
+            assert np.array_equal(a["sums"], r["sums"])
+            assert np.array_equal(a["sums_cov"], r["sums_cov"])
+            assert a["T"] == r["T"] and a["e1"] == r["e1"]
+
+
 def test_from_observations(ngx):
     import ngmix_b200 as ngmix
     from ngmix_b200 import sims
