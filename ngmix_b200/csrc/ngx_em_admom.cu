@@ -26,9 +26,9 @@ namespace ngx {
 #define NGX_EM_MAX_CONV 48
 #define NGX_EM_TILE 64          // pixels per tile == threads per CTA
 #define NGX_EM_MAX_SLOTS 64     // 6*ngauss + 2 <= 62
-// contributions are stored slot-major with a padded stride so that phase B
-// (thread s walks slot s) hits different banks
-#define NGX_EM_STRIDE (NGX_EM_TILE + 1)
+// contributions are stored slot-major with a padded, 16-byte aligned stride:
+// phase B (thread s walks slot s with 16-byte loads) spreads over the banks
+#define NGX_EM_STRIDE (NGX_EM_TILE + 2)
 
 struct EMGauss {
     double p, row, col, irr, irc, icc;
@@ -45,7 +45,6 @@ struct EMShared {
     double red[NGX_EM_MAX_SLOTS];      // the accumulated sums
     double mn[2], mx[2];
     ngx_jacobian jac;
-    unsigned valid_mask[2];
     int npix, numiter, status, done, fill_zero;
     int cnt[2], nzero[2];
 };
@@ -76,11 +75,15 @@ __device__ __forceinline__ void em_build_conv(EMShared *sh, int ngauss,
 
 // slot layout per object gaussian ii: 6*ii + {0 pnew, 1 vsum, 2 usum,
 // 3 v2sum, 4 uvsum, 5 u2sum}; then 6*ngauss: elogL, 6*ngauss+1: skysum
-template <int VARIANT>
+// NG > 0 fixes ngauss at compile time: the per-gaussian sums of a pixel then
+// stay in registers until the pixel's total is known and are written to
+// shared memory once, already scaled (NG = 0: runtime ngauss, scaled in
+// place).  Same operations in the same order either way.
+template <int VARIANT, int NG>
 __global__ void __launch_bounds__(NGX_EM_TILE)
 k_em(int n, const double *__restrict__ images,
      const double *__restrict__ weights, const ngx_jacobian *__restrict__ jac,
-     int nrow, int ncol, const double *__restrict__ guess, int ngauss,
+     int nrow, int ncol, const double *__restrict__ guess, int ngauss_in,
      const double *__restrict__ psf_pars, int npsf_in, ngx_em_conf conf,
      int ignore_zero_weight, double *__restrict__ pars_out,
      ngx_em_result *__restrict__ res) {
@@ -91,13 +94,15 @@ k_em(int n, const double *__restrict__ images,
     constexpr bool DO_LOGL = (VARIANT != NGX_EM_FLUXONLY);
     const int T = NGX_EM_TILE;
     const int ntot = nrow * ncol;
+    const int ngauss = NG > 0 ? NG : ngauss_in;
     const int npsf = npsf_in > 0 ? npsf_in : 1;
     const int nslots = 6 * ngauss + 2;
     double *val = smem_d;               // ntot
     double *code = val + ntot;          // ntot: <0 excluded, 0 zero weight
-    double *rowd = code + ntot;
-    double *cold = rowd + nrow;
-    double *contrib = cold + ncol;      // nslots * NGX_EM_STRIDE
+    double *pv = code + ntot;           // ntot: pixel v (fixed for the fit)
+    double *pu = pv + ntot;             // ntot: pixel u
+    // nslots * NGX_EM_STRIDE, 16-byte aligned
+    double *contrib = pu + ntot;        // 4 * ntot doubles: 16-byte aligned
 
     const int stamp = blockIdx.x;
     if (stamp >= n) return;
@@ -153,8 +158,14 @@ k_em(int n, const double *__restrict__ images,
         sh.psf[threadIdx.x] = e;
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < nrow; p += T) rowd[p] = p - sh.jac.row0;
-    for (int p = threadIdx.x; p < ncol; p += T) cold[p] = p - sh.jac.col0;
+    // pixel coordinates, jacobian_nb.py:4-16 (they do not change during the
+    // iterations)
+    for (int p = threadIdx.x; p < ntot; p += T) {
+        int row = p / ncol, col = p - row * ncol;
+        double rowdiff = row - sh.jac.row0, coldiff = col - sh.jac.col0;
+        pv[p] = sh.jac.dvdrow * rowdiff + sh.jac.dvdcol * coldiff;
+        pu[p] = sh.jac.dudrow * rowdiff + sh.jac.dudcol * coldiff;
+    }
     if (threadIdx.x == 0) {
         double a = fmin(sh.mn[0], sh.mn[1]), b = fmax(sh.mx[0], sh.mx[1]);
         sh.npix = sh.cnt[0] + sh.cnt[1];
@@ -207,8 +218,6 @@ k_em(int n, const double *__restrict__ images,
         for (int p = threadIdx.x; p < ntot; p += T) val[p] += s;
     }
     const double area = sh.jac.scale * sh.jac.scale;
-    const double dvdrow = sh.jac.dvdrow, dvdcol = sh.jac.dvdcol;
-    const double dudrow = sh.jac.dudrow, dudcol = sh.jac.dudcol;
     em_build_conv(&sh, ngauss, npsf, DO_LOGL);
     __syncthreads();
 
@@ -219,9 +228,7 @@ k_em(int n, const double *__restrict__ images,
             // fill_zero_weight_pixels, em_nb.py:1297-1315 (apodized eval)
             for (int p = threadIdx.x; p < ntot; p += T) {
                 if (code[p] == 0.0) {
-                    int row = p / ncol, col = p - row * ncol;
-                    double v = dvdrow * rowd[row] + dvdcol * cold[col];
-                    double u = dudrow * rowd[row] + dudcol * cold[col];
+                    double v = pv[p], u = pu[p];
                     double s = 0.0;
                     for (int k = 0; k < ngauss * npsf; k++) {
                         const ngx_gauss &g = sh.conv[k];
@@ -250,12 +257,13 @@ k_em(int n, const double *__restrict__ images,
             int p = base + threadIdx.x;
             bool valid = (p < ntot) && (code[p] >= 0.0);
             int bad = 0;
+            double *cme = contrib + threadIdx.x;
             if (valid) {
-                int row = p / ncol, col = p - row * ncol;
-                double v = dvdrow * rowd[row] + dvdcol * cold[col];
-                double u = dudrow * rowd[row] + dudcol * cold[col];
+                double v = pv[p], u = pu[p];
                 double gsum = 0.0, logL = 0.0;
-                for (int ii = 0; ii < ngauss; ii++) {
+                double cg[NG > 0 ? NG : 1][6];
+#pragma unroll
+                for (int ii = 0; ii < (NG > 0 ? NG : ngauss); ii++) {
                     double gi = 0.0, tv = 0.0, tu = 0.0, tv2 = 0.0, tuv = 0.0,
                            tu2 = 0.0;
                     for (int k = ii * npsf; k < (ii + 1) * npsf; k++) {
@@ -288,11 +296,15 @@ k_em(int n, const double *__restrict__ images,
                             logL += vl * (sh.logtau[k] - 0.5 * sh.logdet[k]
                                           - 0.5 * chi2);
                     }
-                    double *c = contrib + (size_t)(6 * ii) * NGX_EM_STRIDE
-                        + threadIdx.x;
-                    c[0] = gi; c[NGX_EM_STRIDE] = tv;
-                    c[2 * NGX_EM_STRIDE] = tu; c[3 * NGX_EM_STRIDE] = tv2;
-                    c[4 * NGX_EM_STRIDE] = tuv; c[5 * NGX_EM_STRIDE] = tu2;
+                    if (NG > 0) {
+                        cg[ii][0] = gi; cg[ii][1] = tv; cg[ii][2] = tu;
+                        cg[ii][3] = tv2; cg[ii][4] = tuv; cg[ii][5] = tu2;
+                    } else {
+                        double *c = cme + (size_t)(6 * ii) * NGX_EM_STRIDE;
+                        c[0] = gi; c[NGX_EM_STRIDE] = tv;
+                        c[2 * NGX_EM_STRIDE] = tu; c[3 * NGX_EM_STRIDE] = tv2;
+                        c[4 * NGX_EM_STRIDE] = tuv; c[5 * NGX_EM_STRIDE] = tu2;
+                    }
                 }
                 if (DO_LOGL) {
                     if (gsum == 0.0) logL = 0.0;
@@ -302,33 +314,41 @@ k_em(int n, const double *__restrict__ images,
                 if (gtot == 0.0) {
                     bad = 1;
                 } else {
-                    double pv = val[p];
-                    contrib[(size_t)(6 * ngauss) * NGX_EM_STRIDE
-                            + threadIdx.x] = logL;
-                    contrib[(size_t)(6 * ngauss + 1) * NGX_EM_STRIDE
-                            + threadIdx.x] = sky * pv / gtot;
-                    double factor = pv / gtot;
-                    for (int s = 0; s < 6 * ngauss; s++)
-                        contrib[(size_t)s * NGX_EM_STRIDE + threadIdx.x]
-                            *= factor;
+                    double pval = val[p];
+                    cme[(size_t)(6 * ngauss) * NGX_EM_STRIDE] = logL;
+                    cme[(size_t)(6 * ngauss + 1) * NGX_EM_STRIDE]
+                        = sky * pval / gtot;
+                    double factor = pval / gtot;
+                    if (NG > 0) {
+#pragma unroll
+                        for (int ii = 0; ii < (NG > 0 ? NG : 1); ii++)
+#pragma unroll
+                            for (int m = 0; m < 6; m++)
+                                cme[(size_t)(6 * ii + m) * NGX_EM_STRIDE]
+                                    = cg[ii][m] * factor;
+                    } else {
+                        for (int s = 0; s < 6 * ngauss; s++)
+                            cme[(size_t)s * NGX_EM_STRIDE] *= factor;
+                    }
                 }
+            } else {
+                // a pixel that does not take part adds exact zeros (x + 0 = x)
+                for (int s = 0; s < nslots; s++)
+                    cme[(size_t)s * NGX_EM_STRIDE] = 0.0;
             }
-            unsigned bal = __ballot_sync(0xffffffffu, valid);
-            if (lane == 0) sh.valid_mask[warp] = bal;
             if (bad) atomicOr(&sh.status, NGX_ST_RANGE_ERROR);   // gtot == 0
             __syncthreads();
             if (sh.status) break;
             // ---- phase B: thread s adds its slot in pixel order
             if (threadIdx.x < nslots) {
-                const double *c = contrib
-                    + (size_t)threadIdx.x * NGX_EM_STRIDE;
-                unsigned m0 = sh.valid_mask[0], m1 = sh.valid_mask[1];
+                const double2 *c = (const double2 *)(
+                    contrib + (size_t)threadIdx.x * NGX_EM_STRIDE);
 #pragma unroll 8
-                for (int t = 0; t < 32; t++)
-                    if ((m0 >> t) & 1u) acc += c[t];
-#pragma unroll 8
-                for (int t = 0; t < 32; t++)
-                    if ((m1 >> t) & 1u) acc += c[32 + t];
+                for (int t = 0; t < NGX_EM_TILE / 2; t++) {
+                    double2 x = c[t];
+                    acc += x.x;
+                    acc += x.y;
+                }
             }
             __syncthreads();
         }
@@ -693,15 +713,24 @@ static int launch_em(int n, const double *images, const double *weights,
     int ntot = nrow * ncol;
     int nslots = 6 * ngauss + 2;
     size_t smem = sizeof(double)
-        * (2 * (size_t)ntot + nrow + ncol + (size_t)nslots * NGX_EM_STRIDE);
+        * (4 * (size_t)ntot + 1 + (size_t)nslots * NGX_EM_STRIDE);
     if (smem > (size_t)smem_optin_bytes())
         return fail(NGX_ERR_ARG, "ngx_em: stamp too large%s%s");
-    NGX_CUDA(cudaFuncSetAttribute(k_em<VARIANT>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    k_em<VARIANT><<<n, NGX_EM_TILE, smem, stream>>>(
-        n, images, weights, jac, nrow, ncol, guess, ngauss, psf_pars, npsf,
-        conf, ignore_zero_weight, pars_out, res);
+#define NGX_EM_LAUNCH(NG_)                                                   \
+    do {                                                                     \
+        NGX_CUDA(cudaFuncSetAttribute(                                       \
+            k_em<VARIANT, NG_>,                                              \
+            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        k_em<VARIANT, NG_><<<n, NGX_EM_TILE, smem, stream>>>(                \
+            n, images, weights, jac, nrow, ncol, guess, ngauss, psf_pars,    \
+            npsf, conf, ignore_zero_weight, pars_out, res);                  \
+    } while (0)
+    // the common mixture sizes get the register-resident variant
+    if (ngauss == 1) NGX_EM_LAUNCH(1);
+    else if (ngauss == 2) NGX_EM_LAUNCH(2);
+    else if (ngauss == 3) NGX_EM_LAUNCH(3);
+    else NGX_EM_LAUNCH(0);
+#undef NGX_EM_LAUNCH
     NGX_LAUNCH_CHECK();
     return NGX_OK;
 }
