@@ -37,8 +37,10 @@ struct EMGauss {
 struct EMShared {
     EMGauss gm[10];              // pre-psf mixture being fitted
     EMGauss psf[16];
-    ngx_gauss conv[NGX_EM_MAX_CONV];   // normalised convolved mixture
-    double logtau[NGX_EM_MAX_CONV], logdet[NGX_EM_MAX_CONV];
+    // normalised convolved mixture and its log terms: ngauss*npsf entries in
+    // dynamic shared memory (a fixed 48-entry array cost two resident CTAs)
+    ngx_gauss *conv;
+    double *logtau, *logdet;
     double tab[16];
     double psf_irr, psf_irc, psf_icc, psf_row, psf_col, psf_ipsum;
     double sky, elogL_last, frac_diff, p_last, shift;
@@ -97,12 +99,17 @@ k_em(int n, const double *__restrict__ images,
     const int ngauss = NG > 0 ? NG : ngauss_in;
     const int npsf = npsf_in > 0 ? npsf_in : 1;
     const int nslots = 6 * ngauss + 2;
-    double *val = smem_d;               // ntot
-    double *code = val + ntot;          // ntot: <0 excluded, 0 zero weight
-    double *pv = code + ntot;           // ntot: pixel v (fixed for the fit)
+    const int nconv = ngauss * npsf;
+    // nslots * NGX_EM_STRIDE first (16-byte aligned for the phase-B loads)
+    double *contrib = smem_d;
+    double *val = contrib + (size_t)nslots * NGX_EM_STRIDE;   // ntot
+    double *pv = val + ntot;            // ntot: pixel v (fixed for the fit)
     double *pu = pv + ntot;             // ntot: pixel u
-    // nslots * NGX_EM_STRIDE, 16-byte aligned
-    double *contrib = pu + ntot;        // 4 * ntot doubles: 16-byte aligned
+    ngx_gauss *conv_d = (ngx_gauss *)(pu + ntot);             // nconv
+    double *logtau_d = (double *)(conv_d + nconv);            // nconv
+    double *logdet_d = logtau_d + nconv;                      // nconv
+    // per pixel: 255 excluded, 0 zero weight (filled each iteration), 1 normal
+    unsigned char *code = (unsigned char *)(logdet_d + nconv);
 
     const int stamp = blockIdx.x;
     if (stamp >= n) return;
@@ -117,7 +124,7 @@ k_em(int n, const double *__restrict__ images,
         double w = wt[p], v = im[p];
         bool valid = !(ignore_zero_weight && w <= 0.0);
         val[p] = v;
-        code[p] = valid ? (w > 0.0 ? 1.0 : 0.0) : -1.0;
+        code[p] = valid ? (w > 0.0 ? 1 : 0) : 255;
         if (valid) cnt++;
         if (valid && !(w > 0.0)) nzero++;
         mn = fmin(mn, v);       // prep_image uses the whole image
@@ -141,6 +148,9 @@ k_em(int n, const double *__restrict__ images,
         sh.numiter = 0;
         sh.frac_diff = nan("");
         sh.elogL_last = -9999.9e9;
+        sh.conv = conv_d;
+        sh.logtau = logtau_d;
+        sh.logdet = logdet_d;
     }
     if (threadIdx.x < ngauss) {
         const double *g = guess + ((size_t)stamp * ngauss + threadIdx.x) * 6;
@@ -227,7 +237,7 @@ k_em(int n, const double *__restrict__ images,
         if (sh.fill_zero) {
             // fill_zero_weight_pixels, em_nb.py:1297-1315 (apodized eval)
             for (int p = threadIdx.x; p < ntot; p += T) {
-                if (code[p] == 0.0) {
+                if (code[p] == 0) {
                     double v = pv[p], u = pu[p];
                     double s = 0.0;
                     for (int k = 0; k < ngauss * npsf; k++) {
@@ -255,7 +265,7 @@ k_em(int n, const double *__restrict__ images,
         for (int base = 0; base < ntot; base += T) {
             // ---- phase A: one pixel per thread, reference operation order
             int p = base + threadIdx.x;
-            bool valid = (p < ntot) && (code[p] >= 0.0);
+            bool valid = (p < ntot) && (code[p] != 255);
             int bad = 0;
             double *cme = contrib + threadIdx.x;
             if (valid) {
@@ -712,8 +722,10 @@ static int launch_em(int n, const double *images, const double *weights,
                      cudaStream_t stream) {
     int ntot = nrow * ncol;
     int nslots = 6 * ngauss + 2;
+    int nconv = ngauss * (npsf > 0 ? npsf : 1);
     size_t smem = sizeof(double)
-        * (4 * (size_t)ntot + 1 + (size_t)nslots * NGX_EM_STRIDE);
+        * (3 * (size_t)ntot + (size_t)nslots * NGX_EM_STRIDE + 2 * nconv)
+        + sizeof(ngx_gauss) * (size_t)nconv + (size_t)ntot + 16;
     if (smem > (size_t)smem_optin_bytes())
         return fail(NGX_ERR_ARG, "ngx_em: stamp too large%s%s");
 #define NGX_EM_LAUNCH(NG_)                                                   \
