@@ -84,6 +84,76 @@ def bench_gaussmom(args, torch, _lib, b, t, dev):
     return out
 
 
+def bench_multi(args, _lib, sims, torch, dev):
+    """multi-epoch / multi-band exp fits: 2 bands x 2 epochs of 48x48 stamps
+    per object (Fitter.go on a MultiBandObsList), host-buffer call"""
+    import ngmix_b200 as ngmix
+    nobj = 2000
+    b = sims.make_lm_batch(4 * nobj, seed0=31000, noise=0.02)
+    starts = np.arange(0, 4 * nobj + 1, 4)
+    bands = np.tile(np.array([0, 0, 1, 1], dtype="i4"), nobj)
+    g = b["guess"][::4]
+    guesses = np.column_stack([g, g[:, 5]])
+    # the four stamps of an object share the truth of its first stamp only
+    # approximately (independent sims): the fit is a throughput workload
+    t0 = time.perf_counter()
+    recs = ngmix.fit_batch_multi("exp", starts, bands, 2, b["images"],
+                                 b["weights"], b["jac"], b["psf"], guesses)
+    t1 = time.perf_counter()
+    recs = ngmix.fit_batch_multi("exp", starts, bands, 2, b["images"],
+                                 b["weights"], b["jac"], b["psf"], guesses)
+    dt = time.perf_counter() - t1
+    # device-resident timing of the same workload
+    tt = {k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev)
+          for k in ("images", "weights", "jac", "psf")}
+    d_ss = torch.from_numpy(starts.astype("i4")).to(dev)
+    d_sb = torch.from_numpy(bands).to(dev)
+    d_g = torch.from_numpy(np.ascontiguousarray(guesses)).to(dev)
+    d_res = torch.zeros(nobj * _lib.LM_RESULT_DTYPE.itemsize,
+                        dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def fn():
+        _lib.lm_fit_multi_device(
+            "exp", nobj, d_ss.data_ptr(), d_sb.data_ptr(), 2,
+            tt["images"].data_ptr(), tt["weights"].data_ptr(),
+            tt["jac"].data_ptr(), 48, 48, tt["psf"].data_ptr(), 3,
+            d_g.data_ptr(), d_res.data_ptr(), stream=st)
+
+    fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    o = {"config": "%d objects x (2 bands x 2 epochs) 48x48, exp, 7 "
+                   "parameters" % nobj,
+         "objects_per_s": nobj / (ms * 1e-3),
+         "stamps_per_s": 4 * nobj / (ms * 1e-3), "ms_per_step": ms,
+         "host_call_objects_per_s": nobj / dt,
+         "median_nfev": float(np.median(recs["nfev"]))}
+    if not args.no_cpu:
+        import oracle
+        ns = 32
+        t0 = time.perf_counter()
+        same = 0
+        for i in range(ns):
+            sl = slice(4 * i, 4 * i + 4)
+            r = oracle.lm_fit_multi("exp", b["images"][sl], b["weights"][sl],
+                                    b["jac"][sl], b["psf"][sl], bands[sl], 2,
+                                    guesses[i])
+            same += int(r["flags"] == recs["flags"][i]
+                        and r["nfev"] == recs["nfev"][i])
+        o["cpu_port_objects_per_s_1core"] = ns / (time.perf_counter() - t0)
+        o["flags_nfev_equal_on_sample"] = same
+        o["sample"] = ns
+    return o
+
+
 def bench_bdf(args, torch, _lib, sims, dev):
     """configs[3]: bdf fits (7 pars, 16 x 3 = 48 gaussians, 64x64 stamps,
     PriorBDFSep, forward-difference Jacobian as the reference's lmdif path)"""
@@ -231,6 +301,7 @@ def main():
             (oam["flags"] == ram["flags"][:na]).sum())
         out["admom"]["sample"] = na
     out["gaussmom"] = bench_gaussmom(args, torch, _lib, b, t, dev)
+    out["multi"] = bench_multi(args, _lib, sims, torch, dev)
     if args.nbdf > 0:
         out["bdf"] = bench_bdf(args, torch, _lib, sims, dev)
     print(json.dumps(out))

@@ -183,7 +183,10 @@ typedef struct {
     double g_sigma;
     ngx_prior1d T;
     ngx_prior1d fracdev;  /* bdf only */
-    ngx_prior1d F;
+    ngx_prior1d F;        /* flux prior (band 0) */
+    int32_t nband;        /* 0 or 1: single band; 2, 3: ngx_lm_fit_multi */
+    int32_t pad;
+    ngx_prior1d F_more[2];    /* flux priors of bands 1 and 2 */
 } ngx_prior;
 
 /* DEFAULT_LM_PARS, ngmix/defaults.py:17 */
@@ -217,6 +220,23 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
                int ignore_zero_weight, ngx_lm_result *res, void *stream);
 
 /* ------------------------------------------------------------------ */
+/* Fitter.go on ObsList / MultiBandObsList input (fitting/results.py:212-347,
+ * 439-570: every epoch of every band is a stamp of the object; the residual
+ * vector stacks the prior rows and the stamps' pixel rows, the parameters are
+ * (cen1, cen2, g1, g2, T, F_band0 .. F_band{nband-1})).  Object i owns stamps
+ * stamp_start[i] .. stamp_start[i+1]-1 of the stamp arrays, ordered band by
+ * band; stamp_band[s] is the band of stamp s; guess is [nobj, 5 + nband].
+ * Simple models (gauss, exp, dev) with the analytic Jacobian, nband <= 3.
+ * The result record is the single-stamp one: pars / pars_cov carry 5 + nband
+ * entries, flux / flux_err are those of band 0. */
+int ngx_lm_fit_multi(int nobj, int model, const int32_t *stamp_start,
+                     const int32_t *stamp_band, int nband,
+                     const double *images, const double *weights,
+                     const ngx_jacobian *jac, int nrow, int ncol,
+                     const double *psf_pars, int npsf, const double *guess,
+                     const ngx_prior *prior, const ngx_lm_pars *lm_pars,
+                     int ignore_zero_weight, ngx_lm_result *res, void *stream);
+
 /* EM: EMFitter*.go (em/em.py:228-317) = prep_image (:95-120) + em_run /
  * em_run_fixcen / em_run_fixcov / em_run_fluxonly (em/em_nb.py:15-1257) */
 #define NGX_EM_FULL 0
@@ -338,6 +358,14 @@ int ngx_weighted_sums_host(int n, int ngauss, const ngx_gauss *gmix,
                            const ngx_jacobian *jac, int nrow, int ncol,
                            const double *maxrad, int nmom,
                            int ignore_zero_weight, ngx_mom_result *res);
+int ngx_lm_fit_multi_host(int nobj, int model, const int32_t *stamp_start,
+                          const int32_t *stamp_band, int nband,
+                          const double *images, const double *weights,
+                          const ngx_jacobian *jac, int nrow, int ncol,
+                          const double *psf_pars, int npsf,
+                          const double *guess, const ngx_prior *prior,
+                          const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                          ngx_lm_result *res);
 
 /* FP64 pipe micro-benchmark used for the roofline denominator: runs a
  * register-resident chain of `iters` x 8 independent DFMAs per thread on a

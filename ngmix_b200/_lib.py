@@ -66,7 +66,9 @@ class Prior(C.Structure):
                 ("cen1", C.c_double), ("cen2", C.c_double),
                 ("sigma1", C.c_double), ("sigma2", C.c_double),
                 ("g_sigma", C.c_double), ("T", Prior1D),
-                ("fracdev", Prior1D), ("F", Prior1D)]
+                ("fracdev", Prior1D), ("F", Prior1D),
+                ("nband", C.c_int32), ("pad", C.c_int32),
+                ("F_more", Prior1D * 2)]
 
 
 class LMPars(C.Structure):
@@ -99,6 +101,7 @@ SYMBOLS = [
     "ngx_deriv_images_host", "ngx_lm_fit_host", "ngx_em_host",
     "ngx_admom_host", "ngx_peak_dfma", "ngx_peak_dmma",
     "ngx_weighted_sums", "ngx_weighted_sums_host",
+    "ngx_lm_fit_multi", "ngx_lm_fit_multi_host",
 ]
 
 _lib = None
@@ -366,6 +369,59 @@ def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
         C.c_int(H), C.c_int(W), _p(psf_pars), C.c_int(npsf), _p(guess),
         C.byref(pr), C.byref(lmp), C.c_int(int(ignore_zero_weight)), _p(res)))
     return res
+
+
+def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
+                 psf_pars, guess, prior=None, maxfev=4000, ftol=1.0e-5,
+                 xtol=1.0e-5, ignore_zero_weight=True):
+    """
+    Fitter.go on ObsList / MultiBandObsList input for a batch of objects:
+    object i owns stamps stamp_start[i]:stamp_start[i+1] of images/weights
+    [ns,H,W] (ordered band by band), stamp_band [ns]; guess [nobj, 5+nband].
+    Returns LM_RESULT_DTYPE [nobj].
+    """
+    init()
+    images = _f8(images)
+    weights = _f8(weights)
+    ns, H, W = images.shape
+    jac = as_jac(jac, ns)
+    stamp_start = np.ascontiguousarray(stamp_start, dtype="i4")
+    stamp_band = np.ascontiguousarray(stamp_band, dtype="i4")
+    nobj = stamp_start.size - 1
+    assert stamp_start[0] == 0 and stamp_start[-1] == ns
+    assert stamp_band.size == ns
+    guess = _f8(guess).reshape(nobj, 5 + nband)
+    if psf_pars is None:
+        npsf = 0
+    else:
+        psf_pars = _f8(psf_pars).reshape(ns, -1, 6)
+        npsf = psf_pars.shape[1]
+    pr = prior if prior is not None else Prior()
+    lmp = LMPars(maxfev, 1, ftol, xtol)
+    res = np.zeros(nobj, dtype=LM_RESULT_DTYPE)
+    check(lib().ngx_lm_fit_multi_host(
+        C.c_int(nobj), C.c_int(MODELS[model]), _p(stamp_start),
+        _p(stamp_band), C.c_int(nband), _p(images), _p(weights), _p(jac),
+        C.c_int(H), C.c_int(W), _p(psf_pars), C.c_int(npsf), _p(guess),
+        C.byref(pr), C.byref(lmp), C.c_int(int(ignore_zero_weight)), _p(res)))
+    return res
+
+
+def lm_fit_multi_device(model, nobj, d_stamp_start, d_stamp_band, nband,
+                        d_images, d_weights, d_jac, nrow, ncol, d_psf, npsf,
+                        d_guess, d_res, prior=None, maxfev=4000, ftol=1.0e-5,
+                        xtol=1.0e-5, ignore_zero_weight=True, stream=0):
+    """device-pointer multi-epoch / multi-band fit (asynchronous)"""
+    pr = prior if prior is not None else Prior()
+    lmp = LMPars(maxfev, 1, ftol, xtol)
+    check(lib().ngx_lm_fit_multi(
+        C.c_int(nobj), C.c_int(MODELS[model]), C.c_void_p(d_stamp_start),
+        C.c_void_p(d_stamp_band), C.c_int(nband), C.c_void_p(d_images),
+        C.c_void_p(d_weights), C.c_void_p(d_jac), C.c_int(nrow),
+        C.c_int(ncol), C.c_void_p(d_psf) if npsf else None, C.c_int(npsf),
+        C.c_void_p(d_guess), C.byref(pr), C.byref(lmp),
+        C.c_int(int(ignore_zero_weight)), C.c_void_p(d_res),
+        C.c_void_p(stream)))
 
 
 def lm_fit_device(model, n, d_images, d_weights, d_jac, nrow, ncol, d_psf,

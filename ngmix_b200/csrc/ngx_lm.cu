@@ -62,6 +62,9 @@ struct LMArgs {
     const double *psf, *guess;
     ngx_lm_result *res;
     int *counter;
+    // objects with several stamps (ngx_lm_fit_multi)
+    int nband;
+    const int32_t *stamp_start, *stamp_band;
 };
 
 struct LMShared {
@@ -199,6 +202,19 @@ __device__ __forceinline__ double weight_of(const LMArgs &a, const double *wt,
 __device__ __forceinline__ double ierr_of(double w) {
     return w > 0.0 ? sqrt(w) : 0.0;
 }
+// pixel value of tiled slot q from the caller's image (objects with several
+// stamps keep nothing resident); excluded pixels read as exact zeros, like
+// the staged copy
+__device__ __forceinline__ double pixel_of(const LMArgs &a, const double *im,
+                                           int q, double w) {
+    int row, col;
+    q_to_rowcol(q, a.tpr, &row, &col);
+    double d = 0.0;
+    if (q < a.nq && row < a.nrow && col < a.ncol
+        && !(a.ignore_zero_weight && w <= 0.0))
+        d = __ldg(&im[row * a.ncol + col]);
+    return d;
+}
 
 // union of the masks of the C consecutive tiles starting at tile t0
 template <int C>
@@ -214,7 +230,7 @@ __device__ __forceinline__ unsigned tiles_mask(const unsigned *tmask, int t0,
 // ---------------------------------------------------------------------
 // value pass: sums = {sum r^2, s2n_numer, s2n_denom, r_first^2}.
 // Each warp takes CV consecutive tiles per chunk.
-template <int CV, bool WG>
+template <int CV, int SRC>
 __device__ __forceinline__ void value_pass(const LMArgs &a,
                                            const LMShared *sh,
                                            const double *mix,
@@ -222,6 +238,7 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
                                            const double *val,
                                            const double *ierr,
                                            const double *wt,
+                                           const double *im,
                                            const double *rowd,
                                            const double *cold,
                                            double (&sums)[4]) {
@@ -232,11 +249,12 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
     sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
     for (int base = 0; base < a.nq; base += T * CV) {
         const int q0 = base + warp * CV * 32 + lane;
-        double v[CV], u[CV], acc[CV], wgt[CV];
+        double v[CV], u[CV], acc[CV], wgt[CV], dval[CV];
 #pragma unroll
         for (int c = 0; c < CV; c++) {
             coords_of(a, sh, rowd, cold, q0 + 32 * c, &v[c], &u[c]);
-            wgt[c] = WG ? weight_of(a, wt, q0 + 32 * c) : 0.0;
+            wgt[c] = SRC >= 1 ? weight_of(a, wt, q0 + 32 * c) : 0.0;
+            dval[c] = SRC == 2 ? pixel_of(a, im, q0 + 32 * c, wgt[c]) : 0.0;
             acc[c] = 0.0;
         }
         for (int w = 0; w < nwords; w++) {
@@ -280,7 +298,8 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
         for (int c = 0; c < CV; c++) {
             int q = q0 + 32 * c;
             if (q < a.nq) {
-                double ie = WG ? ierr_of(wgt[c]) : ierr[q], d = val[q];
+                double ie = SRC >= 1 ? ierr_of(wgt[c]) : ierr[q];
+                double d = SRC == 2 ? dval[c] : val[q];
                 double ivar = ie * ie;
                 double diff = acc[c] - d;
                 double r = diff * ie;
@@ -305,7 +324,7 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
 // sums = {A (21, packed lower triangle row by row), b (6), sum r^2,
 //         s2n_numer, s2n_denom, r_first^2}
 #define NDSUM 31
-template <int CD, bool WG>
+template <int CD, int SRC>
 __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                                            const LMShared *sh,
                                            const double *x,
@@ -314,6 +333,7 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                                            const double *val,
                                            const double *ierr,
                                            const double *wt,
+                                           const double *im,
                                            const double *rowd,
                                            const double *cold,
                                            double (&sums)[NDSUM]) {
@@ -338,12 +358,13 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
 
     for (int base = 0; base < a.nq; base += T * CD) {
         const int q0 = base + warp * CD * 32 + lane;
-        double v[CD], u[CD], wgt[CD];
+        double v[CD], u[CD], wgt[CD], dval[CD];
         double S0[CD], S1[CD], S2[CD], MA[CD], MB[CD], MS[CD];
 #pragma unroll
         for (int c = 0; c < CD; c++) {
             coords_of(a, sh, rowd, cold, q0 + 32 * c, &v[c], &u[c]);
-            wgt[c] = WG ? weight_of(a, wt, q0 + 32 * c) : 0.0;
+            wgt[c] = SRC >= 1 ? weight_of(a, wt, q0 + 32 * c) : 0.0;
+            dval[c] = SRC == 2 ? pixel_of(a, im, q0 + 32 * c, wgt[c]) : 0.0;
             S0[c] = S1[c] = S2[c] = MA[c] = MB[c] = MS[c] = 0.0;
         }
         for (int w = 0; w < nwords; w++) {
@@ -412,7 +433,8 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
         for (int c = 0; c < CD; c++) {
             int q = q0 + 32 * c;
             if (q < a.nq) {
-                double ie = WG ? ierr_of(wgt[c]) : ierr[q], d = val[q];
+                double ie = SRC >= 1 ? ierr_of(wgt[c]) : ierr[q];
+                double d = SRC == 2 ? dval[c] : val[q];
                 // undo the factors folded into the accumulators:
                 // qv = -2 hqv; (q q^T - W) terms carry 4, the cross term 8
                 double ma = 4.0 * MA[c], ms = 4.0 * MS[c], mb = 8.0 * MB[c];
@@ -456,13 +478,13 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
 #define CF 2
 #define FD_B0 (LM_MAXP * (LM_MAXP + 1) / 2)
 #define FD_NSUM (FD_B0 + LM_MAXP + 1)
-template <int NPMAX, bool WG>
+template <int NPMAX, int SRC>
 __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
                                         const double *hs, const double *fdm,
                                         const double *etab,
                                         const unsigned *tmask,
                                         const double *val, const double *ierr,
-                                        const double *wt,
+                                        const double *wt, const double *im,
                                         const double *rowd,
                                         const double *cold,
                                         double (&sums)[FD_NSUM]) {
@@ -478,11 +500,12 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
     for (int s = 0; s < NPMAX; s++) hstep[s] = s < np ? hs[s] : 1.0;
     for (int base = 0; base < a.nq; base += T * CF) {
         const int q0 = base + warp * CF * 32 + lane;
-        double v[CF], u[CF], wgt[CF];
+        double v[CF], u[CF], wgt[CF], dval[CF];
 #pragma unroll
         for (int c = 0; c < CF; c++) {
             coords_of(a, sh, rowd, cold, q0 + 32 * c, &v[c], &u[c]);
-            wgt[c] = WG ? weight_of(a, wt, q0 + 32 * c) : 0.0;
+            wgt[c] = SRC >= 1 ? weight_of(a, wt, q0 + 32 * c) : 0.0;
+            dval[c] = SRC == 2 ? pixel_of(a, im, q0 + 32 * c, wgt[c]) : 0.0;
         }
         double mod[NPMAX + 1][CF];
 #pragma unroll
@@ -525,7 +548,8 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
         for (int c = 0; c < CF; c++) {
             int q = q0 + 32 * c;
             if (q < a.nq) {
-                double ie = WG ? ierr_of(wgt[c]) : ierr[q], d = val[q];
+                double ie = SRC >= 1 ? ierr_of(wgt[c]) : ierr[q];
+                double d = SRC == 2 ? dval[c] : val[q];
                 double r = (mod[0][c] - d) * ie;
                 double j[NPMAX];
 #pragma unroll
@@ -678,8 +702,10 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
         chi2per = chi2 / dof;
         Tv = s->x[4];
         Terr = sqrt(pcov[4 * np + 4]);
-        flux = s->x[np - 1];
-        fluxerr = sqrt(pcov[(np - 1) * np + (np - 1)]);
+        // band 0 of a multi-band fit; the last parameter otherwise
+        const int fi = a.nband > 1 ? 5 : np - 1;
+        flux = s->x[fi];
+        fluxerr = sqrt(pcov[fi * np + fi]);
     }
     r.npix = npix;
     r.dof = dof;
@@ -1022,7 +1048,8 @@ k_lm_fit(LMArgs a) {
                 // calc_jacobian raises for T == 0 or flux == 0
                 int jstatus = mix_status || xp[4] == 0.0 || xp[5] == 0.0;
                 if (!jstatus)
-                    deriv_pass<CD, WG>(a, &sh, xp, mix, tmask, val, ierr, wts, rowd,
+                    deriv_pass<CD, WG ? 1 : 0>(a, &sh, xp, mix, tmask, val, ierr, wts,
+                                               nullptr, rowd,
                                    cold, sums);
                 block_sum_to<NDSUM>(sums, scratch, sh.tot);
                 PROF_T(pt_pass);
@@ -1052,7 +1079,8 @@ k_lm_fit(LMArgs a) {
                 PROF_T(pt_mix);
                 double sums[4] = {0, 0, 0, 0};
                 if (!sh.status)
-                    value_pass<CV, WG>(a, &sh, mix, tmask, val, ierr, wts, rowd,
+                    value_pass<CV, WG ? 1 : 0>(a, &sh, mix, tmask, val, ierr, wts,
+                                               nullptr, rowd,
                                    cold, sums);
                 block_sum_to<4>(sums, scratch, sh.tot);
                 PROF_T(pt_pass);
@@ -1101,7 +1129,8 @@ k_lm_fit(LMArgs a) {
 #pragma unroll
                 for (int i = 0; i < FD_NSUM; i++) sums[i] = 0.0;
                 if (!bad_any)
-                    fd_pass<LM_MAXP, WG>(a, &sh, hs, fdm, etab, tmask, val, ierr, wts,
+                    fd_pass<LM_MAXP, WG ? 1 : 0>(a, &sh, hs, fdm, etab, tmask, val,
+                                                 ierr, wts, nullptr,
                                      rowd, cold, sums);
                 {
                     double s1[32], s2[FD_NSUM - 32];
@@ -1146,6 +1175,242 @@ k_lm_fit(LMArgs a) {
         pending = stamp;
 #endif
         stamp = next;
+    }
+}
+
+// ---------------------------------------------------------------------
+// Objects with several stamps: Fitter.go on an ObsList / MultiBandObsList
+// (fitting/results.py:212-347, 439-570).  One CTA per object; the parameters
+// are (cen1, cen2, g1, g2, T, F_0 .. F_{nband-1}).  Every pass walks the
+// object's stamps: per stamp the band's mixture is composed with that stamp's
+// psf and jacobian, the stamp's pixels come straight from global memory / L2
+// (nothing is resident: an object may have many epochs), and the per-thread
+// sums of the stamp are reduced and scattered into the object's J^T J
+// (flux column 5 + band).  Solver, priors, speculation and epilogue are the
+// single-stamp ones.
+struct LMMulti {
+    double macc[48];        // object sums: packed J^T J, J^T f, then
+                            // [44] sum r^2, [45] s2n numer, [46] denom,
+                            // [47] r_first^2
+    double bp[6];           // band parameters of the current stamp
+    int first_q_obj, mstatus;
+};
+
+__device__ __forceinline__ bool multi_pars_nonzero(const double *x, int nband) {
+    bool ok = x[4] != 0.0;
+    for (int b = 0; b < nband; b++) ok = ok && x[5 + b] != 0.0;
+    return ok;
+}
+
+template <int CV, int CD>
+__global__ void __launch_bounds__(128, 4)
+k_lm_fit_multi(LMArgs a) {
+    extern __shared__ double smem_d[];
+    __shared__ LMShared sh;
+    __shared__ LMMulti mu;
+    const int T = blockDim.x;
+    const int nwarps = T >> 5;
+    constexpr int NP = 0;
+    double *mix = smem_d;                                    // ngauss*REC
+    double *rowd = mix + (size_t)a.ngauss * REC;
+    double *cold = rowd + a.nrow;
+    double *scratch = cold + a.ncol;                         // 48 * nwarps
+    double *hs = scratch + 48 * nwarps;                      // 8
+    unsigned *tmask = (unsigned *)(hs + 8);
+    const int np = a.np, nband = a.nband;
+    const int tri = np * (np + 1) / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh.stamp = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int obj = sh.stamp;
+        if (obj >= a.n) break;
+        const int s0 = a.stamp_start[obj], s1 = a.stamp_start[obj + 1];
+
+        // ---- valid pixels of the object, first valid pixel of its first
+        //      stamp (the row run_leastsq drops when a prior is present)
+        int cnt = 0, first = a.ntot, firstq = 0;
+        for (int e = s0; e < s1; e++) {
+            const double *wt = a.weights + (size_t)e * a.ntot;
+            for (int q = threadIdx.x; q < a.nq; q += T) {
+                int row, col;
+                q_to_rowcol(q, a.tpr, &row, &col);
+                if (row < a.nrow && col < a.ncol) {
+                    int p = row * a.ncol + col;
+                    double w = __ldg(&wt[p]);
+                    if (!(a.ignore_zero_weight && w <= 0.0)) {
+                        cnt++;
+                        if (e == s0 && p < first) { first = p; firstq = q; }
+                    }
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            int of = __shfl_xor_sync(0xffffffffu, first, o);
+            int oq = __shfl_xor_sync(0xffffffffu, firstq, o);
+            if (of < first) { first = of; firstq = oq; }
+        }
+        if (lane == 0) {
+            sh.warp_i[warp] = cnt;
+            sh.warp_j[warp] = first;
+            sh.warp_k[warp] = firstq;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int c = 0, f = a.ntot, fq = -1;
+            for (int w = 0; w < nwarps; w++) {
+                c += sh.warp_i[w];
+                if (sh.warp_j[w] < f) { f = sh.warp_j[w]; fq = sh.warp_k[w]; }
+            }
+            sh.npix = c;
+            mu.first_q_obj = fq;
+            lm_init(&sh.st, np, a.guess + (size_t)obj * np, a.lm.maxfev,
+                    a.lm.ftol, a.lm.xtol);
+            sh.action = sh.st.action;
+            sh.spec = 1;
+            for (int i = 0; i < np; i++) sh.xeval[i] = sh.st.xtrial[i];
+            sh.cur_ssq = sh.cur_rfirst2 = sh.cur_num = sh.cur_den = 0.0;
+        }
+        __syncthreads();
+        if (sh.npix == 0 || s1 <= s0) {
+            if (threadIdx.x == 0) {
+                ngx_lm_result *r = &a.res[obj];
+                memset(r, 0, sizeof(*r));
+                r->flags = NGX_NO_ATTEMPT;
+                for (int i = 0; i < np; i++) {
+                    r->pars[i] = NGX_PDEF;
+                    r->pars_err[i] = NGX_CDEF;
+                }
+            }
+            continue;
+        }
+
+        while (sh.action != LM_ACT_DONE) {
+            const int action = sh.action;
+            const int spec = sh.spec;
+            __syncthreads();
+            const bool want_f = (action == LM_ACT_EVAL_F);
+            const double *xp = want_f ? sh.xeval : sh.st.x;
+            const bool nonzero = multi_pars_nonzero(xp, nband);
+            const bool fused = want_f && spec && nonzero
+                && !(sh.st.prered <= sh.st.ftol);
+            const bool do_deriv = fused || action == LM_ACT_EVAL_J;
+            if (threadIdx.x < 48) mu.macc[threadIdx.x] = 0.0;
+            if (threadIdx.x == 0) mu.mstatus = 0;
+            __syncthreads();
+            // calc_jacobian raises for T == 0 or a zero flux
+            const int jstatus0 = do_deriv && !nonzero;
+            for (int e = s0; e < s1; e++) {
+                const int band = a.stamp_band[e];
+                if (threadIdx.x == 0) {
+                    sh.jac = a.jac[e];
+                    sh.status = 0;
+                    for (int i = 0; i < 5; i++) mu.bp[i] = xp[i];
+                    mu.bp[5] = xp[5 + band];
+                    sh.first_q = (e == s0) ? mu.first_q_obj : -1;
+                }
+                if (threadIdx.x < 6 * a.npsf)
+                    sh.psf[threadIdx.x] = a.psf[(size_t)e * 6 * a.npsf
+                                                + threadIdx.x];
+                __syncthreads();
+                for (int p = threadIdx.x; p < a.nrow; p += T)
+                    rowd[p] = p - sh.jac.row0;
+                for (int p = threadIdx.x; p < a.ncol; p += T)
+                    cold[p] = p - sh.jac.col0;
+                if (threadIdx.x == 0 && a.npsf > 0) {
+                    // psf centroid and flux, gmix_get_cen :108-130
+                    double prow = 0.0, pcol = 0.0, psum = 0.0;
+                    for (int k = 0; k < a.npsf; k++) {
+                        double p = sh.psf[6 * k];
+                        prow += p * sh.psf[6 * k + 1];
+                        pcol += p * sh.psf[6 * k + 2];
+                        psum += p;
+                    }
+                    sh.psf_row = prow / psum;
+                    sh.psf_col = pcol / psum;
+                    sh.psf_ipsum = 1.0 / psum;
+                }
+                __syncthreads();
+                const double area = sh.jac.scale * sh.jac.scale;
+                build_mixture(a, &sh, mu.bp, mix, area);
+                __syncthreads();
+                if (sh.status) {            // uniform: read after the barrier
+                    if (threadIdx.x == 0) mu.mstatus = 1;
+                    break;
+                }
+                build_tile_masks(a, &sh, mix, tmask, 1.0e-9);
+                __syncthreads();
+                const double *im = a.images + (size_t)e * a.ntot;
+                const double *wt = a.weights + (size_t)e * a.ntot;
+                if (do_deriv) {
+                    double sums[NDSUM];
+#pragma unroll
+                    for (int i = 0; i < NDSUM; i++) sums[i] = 0.0;
+                    if (!jstatus0)
+                        deriv_pass<CD, 2>(a, &sh, mu.bp, mix, tmask, nullptr,
+                                          nullptr, wt, im, rowd, cold, sums);
+                    block_sum_to<NDSUM>(sums, scratch, sh.tot);
+                    if (threadIdx.x == 0) {
+                        // scatter the stamp's 6 x 6 block: local parameter
+                        // l < 5 is global l, local 5 is the band's flux
+                        const double *t = sh.tot;
+                        int q = 0;
+                        for (int la = 0; la < 6; la++) {
+                            int ga = la < 5 ? la : 5 + band;
+                            for (int lb = 0; lb <= la; lb++) {
+                                int gb = lb < 5 ? lb : 5 + band;
+                                mu.macc[ga * (ga + 1) / 2 + gb] += t[q];
+                                q++;
+                            }
+                            mu.macc[tri + ga] += t[21 + la];
+                        }
+                        mu.macc[44] += t[27];
+                        mu.macc[45] += t[28];
+                        mu.macc[46] += t[29];
+                        if (e == s0) mu.macc[47] = t[30];
+                    }
+                } else {
+                    double sums[4] = {0, 0, 0, 0};
+                    value_pass<CV, 2>(a, &sh, mix, tmask, nullptr, nullptr, wt,
+                                      im, rowd, cold, sums);
+                    block_sum_to<4>(sums, scratch, sh.tot);
+                    if (threadIdx.x == 0) {
+                        mu.macc[44] += sh.tot[0];
+                        mu.macc[45] += sh.tot[1];
+                        mu.macc[46] += sh.tot[2];
+                        if (e == s0) mu.macc[47] = sh.tot[3];
+                    }
+                }
+                __syncthreads();
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int mstatus = mu.mstatus;
+                const int jstatus = mstatus || jstatus0;
+                if (want_f) {
+                    int acc = feed_residual(a, &sh, xp, mu.macc[44],
+                                                mstatus);
+                    if (acc) {
+                        sh.cur_ssq = mu.macc[44];
+                        sh.cur_num = mu.macc[45];
+                        sh.cur_den = mu.macc[46];
+                        sh.cur_rfirst2 = mu.macc[47];
+                        if (fused && sh.st.action == LM_ACT_EVAL_J)
+                            feed_jacobian(a, &sh, mu.macc, jstatus, 1, hs);
+                    }
+                    sh.spec = acc;
+                } else {
+                    feed_jacobian(a, &sh, mu.macc, jstatus, 1, hs);
+                }
+                sh.action = sh.st.action;
+                for (int i = 0; i < np; i++) sh.xeval[i] = sh.st.xtrial[i];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) lm_finish(a, &sh, &a.res[obj]);
     }
 }
 
@@ -1261,6 +1526,86 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
                                  st);
     return config_and_launch(k_lm_fit<1, 3, 2, 4, false>, a, threads,
                              smem_both, st);
+}
+
+int ngx_lm_fit_multi(int nobj, int model, const int32_t *stamp_start,
+                     const int32_t *stamp_band, int nband,
+                     const double *images, const double *weights,
+                     const ngx_jacobian *jac, int nrow, int ncol,
+                     const double *psf_pars, int npsf, const double *guess,
+                     const ngx_prior *prior, const ngx_lm_pars *lm_pars,
+                     int ignore_zero_weight, ngx_lm_result *res,
+                     void *stream) {
+    NGX_REQUIRE(nobj >= 0 && stamp_start && stamp_band && images && weights);
+    NGX_REQUIRE(jac && guess && res && lm_pars && lm_pars->maxfev > 0);
+    NGX_REQUIRE(nrow >= 1 && ncol >= 1 && npsf >= 0 && npsf <= 16);
+    NGX_REQUIRE(npsf == 0 || psf_pars);
+    NGX_REQUIRE(nband >= 1 && nband <= 3);
+    NGX_REQUIRE(model == NGX_GAUSS || model == NGX_EXP || model == NGX_DEV);
+    NGX_REQUIRE(lm_pars->analytic_jacobian);
+    if (nobj == 0) return NGX_OK;
+    LMArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = nobj; a.model = model; a.np = 5 + nband; a.nband = nband;
+    a.ngauss0 = model_ngauss(model); a.npsf = npsf;
+    a.ngauss = a.ngauss0 * (npsf > 0 ? npsf : 1);
+    a.nrow = nrow; a.ncol = ncol; a.ntot = nrow * ncol;
+    a.ignore_zero_weight = ignore_zero_weight;
+    a.analytic = 1;
+    if (prior) a.prior = *prior;
+    if (a.prior.present) {
+        NGX_REQUIRE(a.prior.g_kind == 1);
+        a.prior.nband = nband;
+    }
+    a.lm = *lm_pars;
+    a.images = images; a.weights = weights; a.jac = jac;
+    a.psf = psf_pars; a.guess = guess; a.res = res;
+    a.stamp_start = stamp_start; a.stamp_band = stamp_band;
+    NGX_REQUIRE(a.ngauss <= NGX_MAX_GAUSS);
+    int rc = get_counter(&a.counter);
+    if (rc) return rc;
+    int threads = 128;
+    NGX_REQUIRE(threads >= a.ngauss && threads >= 6 * npsf);
+    a.tpr = (ncol + 7) / 8;
+    a.nq = 32 * a.tpr * ((nrow + 3) / 4);
+    int nwarps = threads / 32;
+    size_t smem = sizeof(double)
+        * ((size_t)a.ngauss * REC + nrow + ncol + 48 * nwarps + 8
+           + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
+    return config_and_launch(k_lm_fit_multi<3, 2>, a, threads, smem,
+                             as_stream(stream));
+}
+
+int ngx_lm_fit_multi_host(int nobj, int model, const int32_t *stamp_start,
+                          const int32_t *stamp_band, int nband,
+                          const double *images, const double *weights,
+                          const ngx_jacobian *jac, int nrow, int ncol,
+                          const double *psf_pars, int npsf,
+                          const double *guess, const ngx_prior *prior,
+                          const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                          ngx_lm_result *res) {
+    NGX_REQUIRE(nobj >= 0 && stamp_start && stamp_band && images && weights);
+    NGX_REQUIRE(jac && guess && res && nband >= 1 && nband <= 3);
+    if (nobj == 0) return NGX_OK;
+    const int ns = stamp_start[nobj];
+    NGX_REQUIRE(ns >= 0 && stamp_start[0] == 0);
+    const size_t ntot = (size_t)nrow * ncol;
+    DevBuf<int32_t> dss(nobj + 1, stamp_start), dsb(ns, stamp_band);
+    DevBuf<double> di(ns * ntot, images), dw(ns * ntot, weights);
+    DevBuf<ngx_jacobian> dj(ns, jac);
+    DevBuf<double> dp(npsf > 0 ? (size_t)ns * npsf * 6 : 0, psf_pars);
+    DevBuf<double> dg((size_t)nobj * (5 + nband), guess);
+    DevBuf<ngx_lm_result> dr(nobj);
+    NGX_CUDA(dss.err); NGX_CUDA(dsb.err); NGX_CUDA(di.err); NGX_CUDA(dw.err);
+    NGX_CUDA(dj.err); NGX_CUDA(dp.err); NGX_CUDA(dg.err); NGX_CUDA(dr.err);
+    int rc = ngx_lm_fit_multi(nobj, model, dss.d, dsb.d, nband, di.d, dw.d,
+                              dj.d, nrow, ncol, npsf > 0 ? dp.d : nullptr,
+                              npsf, dg.d, prior, lm_pars, ignore_zero_weight,
+                              dr.d, 0);
+    if (rc) return rc;
+    NGX_CUDA(cudaDeviceSynchronize());
+    NGX_CUDA(dr.to_host(res));
+    return NGX_OK;
 }
 
 int ngx_lm_fit_host(int n, int model, const double *images,

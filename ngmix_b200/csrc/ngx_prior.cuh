@@ -75,20 +75,27 @@ __device__ inline double clip_sqrt(double lnp) {
     return sqrt(c);
 }
 
+__host__ __device__ inline int prior_nband(const ngx_prior &pr) {
+    return pr.nband > 1 ? pr.nband : 1;
+}
+// flux prior of a band
+__device__ inline const ngx_prior1d &prior_F(const ngx_prior &pr, int band) {
+    return band == 0 ? pr.F : pr.F_more[band - 1];
+}
 // number of residual slots reserved for the prior (results.py:1050-1076)
 __host__ __device__ inline int prior_nslots(int model, const ngx_prior &pr) {
     if (!pr.present) return 0;
-    return model == NGX_BD ? 7 : 6;
+    return (model == NGX_BD ? 6 : 5) + prior_nband(pr);
 }
 // number of rows the prior actually fills
 __host__ __device__ inline int prior_nrows(int model, const ngx_prior &pr) {
     if (!pr.present) return 0;
     if (model == NGX_BDF) return 6;
-    return 5;
+    return 4 + prior_nband(pr);
 }
 
 // one row of prior.fill_fdiff; row index in the reference's order.
-// simple: 0 cen1, 1 cen2, 2 g, 3 T, 4 F        (sqrt(clip(-2 lnp)))
+// simple: 0 cen1, 1 cen2, 2 g, 3 T, 4.. F per band   (sqrt(clip(-2 lnp)))
 // bdf   : 0 cen1, 1 cen2, 2 g, 3 T, 4 fracdev, 5 F   (signed get_fdiff)
 __device__ __noinline__ int prior_row(int model, const ngx_prior &pr,
                                 const double *p, int row, double *out) {
@@ -128,7 +135,7 @@ __device__ __noinline__ int prior_row(int model, const ngx_prior &pr,
         if (st) return st;
         break;
     default:
-        st = prior1d_lnprob(pr.F, p[5], &lnp);
+        st = prior1d_lnprob(prior_F(pr, row - 4), p[5 + (row - 4)], &lnp);
         if (st) return st;
     }
     *out = clip_sqrt(lnp);
@@ -174,8 +181,11 @@ __device__ __noinline__ int prior_lnprob(int model, const ngx_prior &pr,
         lnp += t;
         fi = 6;
     }
-    if (prior1d_lnprob(pr.F, p[fi], &t)) return NGX_ST_RANGE_ERROR;
-    lnp += t;
+    for (int b = 0; b < prior_nband(pr); b++) {
+        if (prior1d_lnprob(prior_F(pr, b), p[fi + b], &t))
+            return NGX_ST_RANGE_ERROR;
+        lnp += t;
+    }
     *out = lnp;
     return NGX_ST_OK;
 }

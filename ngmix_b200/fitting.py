@@ -71,6 +71,36 @@ def fit_batch(model, images, weights, jacobians, psf_pars, guesses,
                        ignore_zero_weight=ignore_zero_weight)
 
 
+def fit_batch_multi(model, stamp_start, stamp_band, nband, images, weights,
+                    jacobians, psf_pars, guesses, prior=None, fit_pars=None,
+                    ignore_zero_weight=True):
+    """
+    Levenberg-Marquardt fits of objects observed in several epochs and/or
+    bands (Fitter.go on ObsList / MultiBandObsList, fitting/results.py:
+    212-570) in one launch.  Object i owns stamps
+    stamp_start[i]:stamp_start[i+1] of the [ns, H, W] stamp arrays, ordered
+    band by band; stamp_band [ns] gives each stamp's band; guesses
+    [nobj, 5 + nband] = (cen1, cen2, g1, g2, T, F_0 .. F_{nband-1}).
+    gauss / exp / dev with the analytic Jacobian, nband <= 3.
+    """
+    model = get_model_name(get_model_num(model))
+    if model not in SIMPLE_ANALYTIC_MODELS:
+        raise ValueError("multi-epoch fits need a model with an analytic "
+                         "jacobian: %s" % str(SIMPLE_ANALYTIC_MODELS))
+    fp = dict(DEFAULT_LM_PARS)
+    if fit_pars is not None:
+        fp.update(fit_pars)
+    pr = _prior_record(prior)
+    if pr is not None and getattr(prior, "nband", nband) != nband:
+        raise ValueError("prior has %d flux priors, data has %d bands"
+                         % (prior.nband, nband))
+    return _lib.lm_fit_multi(model, stamp_start, stamp_band, nband, images,
+                             weights, jacobians, psf_pars, guesses, prior=pr,
+                             maxfev=fp["maxfev"], ftol=fp["ftol"],
+                             xtol=fp["xtol"],
+                             ignore_zero_weight=ignore_zero_weight)
+
+
 _ERRMSG = {
     1: "Both actual and predicted relative reductions in the sum of squares "
        "are at most ftol",
@@ -115,6 +145,13 @@ def record_to_result(rec, model, npars):
         res["g"] = res["pars"][2:4].copy()
         res["g_cov"] = res["pars_cov"][2:4, 2:4].copy()
         res["g_err"] = res["pars_err"][2:4].copy()
+        nband = n - get_model_npars(model) + 1
+        if nband > 1:
+            # _set_flux, results.py:1079-1109
+            start = n - nband
+            res["flux"] = res["pars"][start:].copy()
+            res["flux_cov"] = res["pars_cov"][start:, start:].copy()
+            res["flux_err"] = np.sqrt(np.diag(res["flux_cov"]))
     return res
 
 
@@ -133,11 +170,19 @@ class FitResult(dict):
         super().__init__(result)
         self.obs = get_mb_obs(obs)
         self.model_name = model
-        self.npars = get_model_npars(model)
-        self.nband = 1
+        self.nband = len(self.obs)
+        self.npars = get_model_npars(model) + self.nband - 1
+
+    def get_band_pars(self, pars, band):
+        """results.py:1025-1047 (simple models: 5 shared + the band's flux)"""
+        n0 = get_model_npars(self.model_name)
+        out = np.array(pars[:n0], dtype="f8")
+        out[n0 - 1] = pars[n0 - 1 + band]
+        return out
 
     def get_gmix(self, band=0):
-        return make_gmix_model(self["pars"], self.model_name)
+        return make_gmix_model(self.get_band_pars(self["pars"], band),
+                               self.model_name)
 
     def get_convolved_gmix(self, band=0, obsnum=0):
         gm = self.get_gmix(band)
@@ -187,9 +232,7 @@ class Fitter(object):
         """run the fit; returns a dict-like FitResult"""
         mb = get_mb_obs(obs)
         if len(mb) != 1 or len(mb[0]) != 1:
-            raise NotImplementedError(
-                "multi-epoch / multi-band fits are a 'next' row of the scope "
-                "table; send one Observation")
+            return self._go_multi(mb, guess)
         o = mb[0][0]
         npars = get_model_npars(self.model_name)
         guess = np.array(guess, dtype="f8")
@@ -211,3 +254,48 @@ class Fitter(object):
             raise GMixFatalError("no weights > 0")
         res = record_to_result(rec, self.model_name, npars)
         return FitResult(o, self.model_name, res)
+
+    def _go_multi(self, mb, guess):
+        """ObsList / MultiBandObsList: every epoch of every band is a stamp
+        of one object (same stamp size and psf mixture size throughout)"""
+        nband = len(mb)
+        npars = get_model_npars(self.model_name) + nband - 1
+        guess = np.array(guess, dtype="f8")
+        assert guess.size == npars, \
+            "guess has npars=%d, expected %d" % (guess.size, npars)
+        if self.model_name not in SIMPLE_ANALYTIC_MODELS \
+                or not self.analytic_jacobian:
+            raise NotImplementedError(
+                "multi-epoch / multi-band fits: gauss, exp, dev with the "
+                "analytic jacobian")
+        if nband > 3:
+            raise NotImplementedError("at most 3 bands (8 parameters)")
+        stamps = [(b, o) for b, ol in enumerate(mb) for o in ol]
+        shape = stamps[0][1].image.shape
+        has_psf = stamps[0][1].has_psf_gmix()
+        for _, o in stamps:
+            if o.image.shape != shape or o.has_psf_gmix() != has_psf:
+                raise NotImplementedError(
+                    "all stamps of an object must share their size and all "
+                    "or none carry a psf mixture")
+        images = np.stack([o.image for _, o in stamps])
+        weights = np.stack([o.weight for _, o in stamps])
+        jac = np.stack([np.asarray(o._jacobian._data.view("f8")).reshape(8)
+                        for _, o in stamps])
+        bands = np.array([b for b, _ in stamps], dtype="i4")
+        psf_pars = None
+        if has_psf:
+            psf_pars = np.stack([o.psf.gmix.get_full_pars().reshape(-1, 6)
+                                 for _, o in stamps])
+        for b in range(nband):
+            make_gmix_model(np.append(guess[:5], guess[5 + b]),
+                            self.model_name)
+        izw = all(o.ignore_zero_weight for _, o in stamps)
+        rec = fit_batch_multi(self.model_name, [0, len(stamps)], bands, nband,
+                              images, weights, jac, psf_pars, guess[None],
+                              prior=self.prior, fit_pars=self.fit_pars,
+                              ignore_zero_weight=izw)[0]
+        if rec["flags"] == 1 and rec["nfev"] == 0:
+            raise GMixFatalError("no weights > 0")
+        res = record_to_result(rec, self.model_name, npars)
+        return FitResult(mb, self.model_name, res)

@@ -206,8 +206,8 @@ class PriorSimpleSep(object):
         return n
 
     def to_ngx(self):
-        if self.nband != 1:
-            raise NotImplementedError("multi-band priors are not built yet")
+        if self.nband > 3:
+            raise NotImplementedError("at most 3 bands (8 parameters)")
         if not isinstance(self.g_prior, GPriorBA):
             raise NotImplementedError("g prior must be GPriorBA")
         pr = _lib.Prior()
@@ -219,6 +219,9 @@ class PriorSimpleSep(object):
         pr.g_sigma = self.g_prior.sigma
         pr.T = self.T_prior._ngx()
         pr.F = self.F_priors[0]._ngx()
+        pr.nband = self.nband
+        for b in range(1, self.nband):
+            pr.F_more[b - 1] = self.F_priors[b]._ngx()
         return pr
 
 

@@ -670,6 +670,113 @@ def gen_moments():
     save("moments", **out)
 
 
+def _multi_case(rng, nband, nepoch, model, noise, with_prior):
+    """one object observed nepoch[b] times in band b: stamps, truth, guess"""
+    from ngmix_b200.sims import (diag_jacobian, simple_full_pars,
+                                 convolve_full_pars, render_full_pars)
+    H = W = 32
+    g1, g2 = rng.normal(0.0, 0.12, size=2)
+    T = rng.uniform(0.2, 0.8)
+    fluxes = rng.uniform(60.0, 180.0, size=nband)
+    images, weights, jacs, psfs, bands = [], [], [], [], []
+    for b in range(nband):
+        for _ in range(nepoch[b]):
+            dy, dx = rng.uniform(-0.5, 0.5, size=2)
+            jac = diag_jacobian((H - 1) / 2 + dy, (W - 1) / 2 + dx, 0.263)
+            ppars = [0.0, 0.0, rng.normal(0, 0.01), rng.normal(0, 0.01),
+                     rng.uniform(0.22, 0.32), 1.0]
+            psf = simple_full_pars(ppars, "turb")
+            pars = [0.0, 0.0, g1, g2, T, fluxes[b]]
+            full = convolve_full_pars(simple_full_pars(pars, model), psf)
+            im = render_full_pars(full, (H, W), jac)
+            images.append(im + rng.normal(0.0, noise, size=im.shape))
+            wt = np.zeros((H, W)) + 1.0 / noise ** 2
+            if rng.uniform() < 0.3:
+                wt[rng.uniform(size=wt.shape) < 0.05] = 0.0
+            weights.append(wt)
+            jacs.append(jac)
+            psfs.append(psf)
+            bands.append(b)
+    truth = np.array([0.0, 0.0, g1, g2, T] + list(fluxes))
+    guess = truth.copy()
+    guess[0:2] = rng.uniform(-0.01, 0.01, size=2)
+    guess[2:] *= 1.0 + rng.uniform(-0.05, 0.05, size=guess.size - 2)
+    return (np.array(images), np.array(weights), np.array(jacs),
+            np.array(psfs), np.array(bands, dtype="i4"), truth, guess)
+
+
+def gen_lm_multi():
+    """Fitter.go on ObsList and MultiBandObsList inputs (multi-epoch,
+    1-3 bands), with and without PriorSimpleSep (a flux prior per band)"""
+    from ngmix.fitting import Fitter
+    from ngmix import priors, joint_prior
+    rng = np.random.RandomState(31415)
+    configs = [
+        # (nband, epochs per band, model, with_prior)
+        (1, [3], "exp", False), (1, [3], "exp", True),
+        (2, [2, 2], "exp", True), (2, [1, 3], "gauss", False),
+        (3, [1, 1, 1], "exp", True), (3, [2, 1, 2], "dev", True),
+        (3, [1, 2, 1], "gauss", False), (1, [4], "dev", False),
+    ]
+    out = {"ncases": np.array(0)}
+    icase = 0
+    for nband, nep, model, with_prior in configs:
+        for rep in range(3):
+            noise = [0.02, 0.05, 0.3][rep]
+            (images, weights, jacs, psfs, bands, truth,
+             guess) = _multi_case(rng, nband, nep, model, noise, with_prior)
+            mbobs = ngmix.MultiBandObsList()
+            k = 0
+            for b in range(nband):
+                ol = ngmix.ObsList()
+                for _ in range(nep[b]):
+                    psf_obs = ngmix.Observation(
+                        np.zeros((5, 5)) + 1.0,
+                        gmix=ngmix.GMix(pars=psfs[k].ravel()))
+                    ol.append(ngmix.Observation(
+                        images[k], weight=weights[k],
+                        jacobian=jac_from_record(jacs[k]), psf=psf_obs))
+                    k += 1
+                mbobs.append(ol)
+            prior = None
+            if with_prior:
+                prior = joint_prior.PriorSimpleSep(
+                    priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng),
+                    priors.GPriorBA(0.3, rng=rng),
+                    priors.TwoSidedErf(-1.0, 0.1, 1.0e3, 1.0, rng=rng),
+                    [priors.TwoSidedErf(-1.0e2, 1.0, 1.0e9, 1.0e8, rng=rng)
+                     for _ in range(nband)])
+            fitter = Fitter(model=model, prior=prior)
+            obs_in = mbobs if nband > 1 else mbobs[0]
+            r = fitter.go(obs=obs_in, guess=guess)
+            np_ = 5 + nband
+            p = "c%d_" % icase
+            out[p + "images"], out[p + "weights"] = images, weights
+            out[p + "jac"], out[p + "psf"], out[p + "bands"] = jacs, psfs, bands
+            out[p + "guess"] = guess
+            out[p + "model"] = np.array(model)
+            out[p + "nband"] = np.array(nband)
+            out[p + "prior"] = np.array(int(with_prior))
+            out[p + "flags"] = np.array(r["flags"])
+            out[p + "nfev"] = np.array(r["nfev"])
+            out[p + "ier"] = np.array(r["ier"])
+            out[p + "pars"] = np.array(r["pars"])
+            out[p + "pars_cov"] = np.array(r["pars_cov"])
+            out[p + "pars_err"] = np.array(r["pars_err"])
+            if r["flags"] == 0:
+                for key in ("lnprob", "s2n", "chi2per", "dof", "npix",
+                            "s2n_numer", "s2n_denom", "T", "T_err"):
+                    out[p + key] = np.array(r[key])
+                out[p + "flux"] = np.atleast_1d(r["flux"])
+                out[p + "flux_err"] = np.atleast_1d(r["flux_err"])
+            print(icase, model, nband, nep, "flags", r["flags"], "nfev",
+                  r["nfev"], "ier", r["ier"])
+            assert len(r["pars"]) == np_
+            icase += 1
+    out["ncases"] = np.array(icase)
+    save("lm_multi", **out)
+
+
 GENERATORS = {
     "fastexp": gen_fastexp,
     "gmix": gen_gmix,
@@ -680,6 +787,7 @@ GENERATORS = {
     "em_admom": gen_em_admom,
     "lm_bdf": gen_lm_bdf,
     "moments": gen_moments,
+    "lm_multi": gen_lm_multi,
 }
 
 if __name__ == "__main__":

@@ -10,7 +10,8 @@
  *   PriorBDFSep.fill_fdiff     ngmix/joint_prior.py:565-599
  *   run_leastsq / _test_cov    ngmix/fitting/leastsqbound.py:33-180
  *   FitModel.set_fit_result    ngmix/fitting/results.py:45-72,142-210
- * Single band, single epoch (nband = 1), no bounds.
+ * ora_lm_fit: single band, single epoch; ora_lm_fit_multi: ObsList /
+ * MultiBandObsList (simple models).  No bounds.
  */
 #include <math.h>
 #include <pthread.h>
@@ -580,6 +581,371 @@ int ora_lm_fit(int model, const double *image, const double *weight,
     ctx_free(&c);
     free(pixels);
     return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* Multi-epoch / multi-band fit: Fitter.go on an ObsList or MultiBandObsList
+ * (results.py:212-347 _set_obs / _fill_gmix_all, :439-466 calc_fdiff,
+ * :487-570 calc_jacobian, :142-200 calc_lnprob; get_band_pars :1025-1047;
+ * PriorSimpleSep with a list of flux priors, joint_prior.py:20-150).
+ * Simple models with the analytic jacobian.  Stamps are ordered band by band,
+ * as the reference walks them. */
+typedef struct {
+    int model, npars, nband, nstamp, n_prior_pars, fdiff_size, totpix;
+    fitctx *c;                      /* one per stamp */
+    const int32_t *band;            /* band of each stamp */
+    const ora_prior *prior;         /* cen, g, T (F unused) */
+    const ora_prior1d *Fp;          /* flux prior of each band */
+} mfitctx;
+
+static void m_band_pars(const double *pars, int band, double *bp) {
+    for (int i = 0; i < 5; i++) bp[i] = pars[i];
+    bp[5] = pars[5 + band];
+}
+
+static int m_fill_gmix_all(mfitctx *m, const double *pars) {
+    for (int i = 0; i < m->nstamp; i++) {
+        double bp[6];
+        m_band_pars(pars, m->band[i], bp);
+        if (ctx_fill_gmix(&m->c[i], bp)) return ORA_RANGE_ERROR;
+    }
+    return ORA_OK;
+}
+
+/* PriorSimpleSep.fill_fdiff with nband flux priors; rows filled or -1 */
+static int m_prior_fill_fdiff(const mfitctx *m, const double *pars,
+                              double *fdiff) {
+    const ora_prior *pr = m->prior;
+    if (!pr || !pr->present) return 0;
+    int index = 0;
+    double s2inv1 = 1.0 / (pr->sigma1 * pr->sigma1);
+    double s2inv2 = 1.0 / (pr->sigma2 * pr->sigma2);
+    double d1 = pr->cen1 - pars[0];
+    double d2 = pr->cen2 - pars[1];
+    fdiff[index++] = -0.5 * d1 * d1 * s2inv1;
+    fdiff[index++] = -0.5 * d2 * d2 * s2inv2;
+    double lnp;
+    if (gprior_lnprob(pr, pars[2], pars[3], &lnp)) return -1;
+    fdiff[index++] = lnp;
+    if (prior1d_lnprob(&pr->T, pars[4], &lnp)) return -1;
+    fdiff[index++] = lnp;
+    for (int b = 0; b < m->nband; b++) {
+        if (prior1d_lnprob(&m->Fp[b], pars[5 + b], &lnp)) return -1;
+        fdiff[index++] = lnp;
+    }
+    for (int i = 0; i < index; i++) {
+        double c = -2 * fdiff[i];
+        if (c < 0.0) c = 0.0;
+        fdiff[i] = sqrt(c);
+    }
+    return index;
+}
+
+static int m_prior_lnprob(const mfitctx *m, const double *pars, double *out) {
+    const ora_prior *pr = m->prior;
+    if (!pr || !pr->present) { *out = 0.0; return ORA_OK; }
+    double s2inv1 = 1.0 / (pr->sigma1 * pr->sigma1);
+    double s2inv2 = 1.0 / (pr->sigma2 * pr->sigma2);
+    double d1 = pr->cen1 - pars[0];
+    double d2 = pr->cen2 - pars[1];
+    double lnp = -0.5 * d1 * d1 * s2inv1 - 0.5 * d2 * d2 * s2inv2;
+    double t;
+    if (gprior_lnprob(pr, pars[2], pars[3], &t)) return ORA_RANGE_ERROR;
+    lnp += t;
+    if (prior1d_lnprob(&pr->T, pars[4], &t)) return ORA_RANGE_ERROR;
+    lnp += t;
+    for (int b = 0; b < m->nband; b++) {
+        if (prior1d_lnprob(&m->Fp[b], pars[5 + b], &t)) return ORA_RANGE_ERROR;
+        lnp += t;
+    }
+    *out = lnp;
+    return ORA_OK;
+}
+
+static int m_calc_fdiff(mfitctx *m, const double *pars, double *fdiff) {
+    int n = m->fdiff_size;
+    for (int i = 0; i < n; i++) fdiff[i] = 0.0;
+    int bad = 0;
+    if (m_fill_gmix_all(m, pars)) bad = 1;
+    int start = 0;
+    if (!bad) {
+        start = m_prior_fill_fdiff(m, pars, fdiff);
+        if (start < 0) bad = 1;
+    }
+    for (int i = 0; i < m->nstamp && !bad; i++) {
+        fitctx *c = &m->c[i];
+        if (ora_fill_fdiff(c->gm, c->ngauss, c->pixels, c->npix, fdiff, start))
+            bad = 1;
+        start += c->npix;
+    }
+    if (bad) {
+        for (int i = 0; i < n; i++) fdiff[i] = -INFINITY;
+        return ORA_RANGE_ERROR;
+    }
+    return ORA_OK;
+}
+
+static int m_prior_jacobian(mfitctx *m, const double *pars, double *jac,
+                            int *nrows) {
+    *nrows = 0;
+    if (!m->prior || !m->prior->present) return ORA_OK;
+    int mm = m->fdiff_size, np = m->npars;
+    double f0[8] = {0}, fs[8] = {0}, p[8];
+    int n = m_prior_fill_fdiff(m, pars, f0);
+    if (n < 0) return ORA_RANGE_ERROR;
+    for (int ipar = 0; ipar < np; ipar++) {
+        double step = STEP_PRIOR * fmax(1.0, fabs(pars[ipar]));
+        for (int k = 0; k < np; k++) p[k] = pars[k];
+        p[ipar] = pars[ipar] + step;
+        if (m_prior_fill_fdiff(m, p, fs) < 0) {
+            step = -step;
+            p[ipar] = pars[ipar] + step;
+            if (m_prior_fill_fdiff(m, p, fs) < 0) return ORA_RANGE_ERROR;
+        }
+        for (int k = 0; k < n; k++) {
+            double d = 0.0;
+            if (isfinite(f0[k]) && isfinite(fs[k])) d = (fs[k] - f0[k]) / step;
+            jac[k + (size_t)ipar * mm] = d;
+        }
+    }
+    *nrows = n;
+    return ORA_OK;
+}
+
+static int m_calc_jacobian(mfitctx *m, const double *pars, double *jac) {
+    int mm = m->fdiff_size, np = m->npars;
+    memset(jac, 0, sizeof(double) * (size_t)mm * np);
+    int start = 0, bad = 0;
+    if (m_prior_jacobian(m, pars, jac, &start)) bad = 1;
+    if (!bad && m_fill_gmix_all(m, pars)) bad = 1;
+    /* the reference walks the bands and raises at the first zero T / flux */
+    for (int b = 0; b < m->nband && !bad; b++)
+        if (pars[4] == 0.0 || pars[5 + b] == 0.0) bad = 1;
+    for (int is = 0; is < m->nstamp && !bad; is++) {
+        fitctx *c = &m->c[is];
+        double bp[6];
+        m_band_pars(pars, m->band[is], bp);
+        /* the single-stamp jacobian of this stamp in band parameters */
+        int mloc = c->npix;
+        double *jl = (double *)calloc((size_t)mloc * 6, sizeof(double));
+        fitctx tmp = *c;
+        tmp.prior = NULL;
+        tmp.n_prior_pars = 0;
+        tmp.fdiff_size = mloc;
+        tmp.npars = 6;
+        if (ctx_calc_jacobian(&tmp, bp, jl)) bad = 1;
+        if (!bad) {
+            int fluxcol = 5 + m->band[is];
+            for (int i = 0; i < mloc; i++) {
+                for (int k = 0; k < 5; k++)
+                    jac[start + i + (size_t)k * mm] = jl[i + (size_t)k * mloc];
+                jac[start + i + (size_t)fluxcol * mm]
+                    = jl[i + (size_t)5 * mloc];
+            }
+        }
+        free(jl);
+        start += mloc;
+    }
+    if (bad) {
+        memset(jac, 0, sizeof(double) * (size_t)mm * np);
+        return ORA_RANGE_ERROR;
+    }
+    return ORA_OK;
+}
+
+static int mcb_fdiff(void *ctx, int mm, int n, const double *x, double *fvec) {
+    (void)mm; (void)n;
+    m_calc_fdiff((mfitctx *)ctx, x, fvec);
+    return 0;
+}
+static int mcb_jac(void *ctx, int mm, int n, const double *x, double *fjac) {
+    (void)mm; (void)n;
+    m_calc_jacobian((mfitctx *)ctx, x, fjac);
+    return 0;
+}
+
+/* Fitter.go on nstamp stamps of one object.  bands[nstamp] non-decreasing,
+ * guess/pars have 5 + nband entries, Fp[nband] flux priors (NULL without a
+ * prior).  Returns -2 when a stamp has no usable pixel (GMixFatalError). */
+int ora_lm_fit_multi(int model, int nstamp, const double *images,
+                     const double *weights, int nrow, int ncol,
+                     const ora_jac *jacs, const double *psf_pars, int npsf,
+                     const int32_t *bands, int nband, const double *guess,
+                     const ora_prior *prior, const ora_prior1d *Fp, int maxfev,
+                     double ftol, double xtol, int ignore_zero_weight,
+                     ora_lm_result *res) {
+    memset(res, 0, sizeof(*res));
+    if (!(model == ORA_GAUSS || model == ORA_EXP || model == ORA_DEV))
+        return -1;
+    if (nband < 1 || 5 + nband > 8 || nstamp < 1) return -1;
+    int ntot = nrow * ncol;
+    mfitctx m;
+    memset(&m, 0, sizeof(m));
+    m.model = model; m.nband = nband; m.nstamp = nstamp;
+    m.npars = 5 + nband;
+    m.band = bands; m.prior = prior; m.Fp = Fp;
+    m.n_prior_pars = (prior && prior->present) ? 5 + nband : 0;
+    m.c = (fitctx *)calloc((size_t)nstamp, sizeof(fitctx));
+    ora_pixel **pix = (ora_pixel **)calloc((size_t)nstamp, sizeof(*pix));
+    int rc = 0;
+    for (int is = 0; is < nstamp; is++) {
+        const double *im = images + (size_t)is * ntot;
+        const double *wt = weights + (size_t)is * ntot;
+        int npixv = ntot;
+        if (ignore_zero_weight) {
+            npixv = 0;
+            for (int i = 0; i < ntot; i++) if (wt[i] > 0.0) npixv++;
+        }
+        if (npixv == 0) rc = -2;
+        pix[is] = (ora_pixel *)malloc(sizeof(ora_pixel) * (size_t)(npixv + 1));
+        ora_fill_pixels(pix[is], npixv, im, wt, nrow, ncol, &jacs[is],
+                        ignore_zero_weight);
+        ctx_init(&m.c[is], model, pix[is], npixv,
+                 psf_pars ? psf_pars + (size_t)is * 6 * npsf : NULL, npsf,
+                 NULL);
+        m.totpix += npixv;
+    }
+    m.fdiff_size = m.totpix + m.n_prior_pars;
+    int np = m.npars, mm = m.fdiff_size;
+    if (rc == 0) {
+        double x[8];
+        for (int i = 0; i < np; i++) x[i] = guess[i];
+        double *fvec = (double *)malloc(sizeof(double) * (size_t)mm * (np + 1));
+        double *fjac = fvec + mm;
+        int ipvt[8];
+        double qtf[8];
+        int nfev = 0, njev = 0;
+        int ier = ora_lmder(mcb_fdiff, mcb_jac, &m, mm, np, x, fvec, fjac,
+                            ftol, xtol, 0.0, maxfev, 100.0, &nfev, &njev,
+                            ipvt, qtf);
+        int flags = 0;
+        res->nfev = nfev; res->njev = njev; res->ier = ier;
+        for (int i = 0; i < np; i++) res->pars[i] = x[i];
+        for (int i = 0; i < np * np; i++) res->pars_cov0[i] = NAN;
+        int have_cov0 = 0;
+        if (ier >= 1 && ier <= 4) {
+            double rinv[64];
+            int sing = 0;
+            for (int j = 0; j < np; j++)
+                if (fjac[j + (size_t)j * mm] == 0.0) sing = 1;
+            if (!sing) {
+                memset(rinv, 0, sizeof(rinv));
+                for (int j = 0; j < np; j++) {
+                    rinv[j * np + j] = 1.0 / fjac[j + (size_t)j * mm];
+                    for (int i = j - 1; i >= 0; i--) {
+                        double s = 0.0;
+                        for (int k = i + 1; k <= j; k++)
+                            s += fjac[i + (size_t)k * mm] * rinv[k * np + j];
+                        rinv[i * np + j] = -s / fjac[i + (size_t)i * mm];
+                    }
+                }
+                double prinv[64];
+                for (int j = 0; j < np; j++)
+                    for (int k = 0; k < np; k++)
+                        prinv[ipvt[j] * np + k] = rinv[j * np + k];
+                for (int a = 0; a < np; a++)
+                    for (int b = 0; b < np; b++) {
+                        double s = 0.0;
+                        for (int k = 0; k < np; k++)
+                            s += prinv[a * np + k] * prinv[b * np + k];
+                        res->pars_cov0[a * np + b] = s;
+                    }
+                have_cov0 = 1;
+            }
+        }
+        if (ier > 4) {
+            flags |= 1 << (ier - 5);
+            set_defaults(res, np);
+        } else if (!have_cov0) {
+            flags |= ORA_LM_SINGULAR_MATRIX;
+            for (int i = 0; i < np; i++) res->pars_err[i] = CDEF;
+            for (int i = 0; i < np * np; i++) res->pars_cov[i] = CDEF;
+        } else {
+            m_calc_fdiff(&m, res->pars, fvec);
+            int dof = mm - m.n_prior_pars - np;
+            if (dof == 0) {
+                for (int i = 0; i < np; i++) res->pars_err[i] = CDEF;
+                for (int i = 0; i < np * np; i++) res->pars_cov[i] = CDEF;
+                flags |= ORA_ZERO_DOF;
+            } else {
+                double ssum = 0.0;
+                for (int i = m.n_prior_pars; i < mm; i++)
+                    ssum += fvec[i] * fvec[i];
+                double s_sq = ssum / dof;
+                for (int i = 0; i < np * np; i++)
+                    res->pars_cov[i] = res->pars_cov0[i] * s_sq;
+                int cflags = 0;
+                double ev[8];
+                if (sym_eigvals(np, res->pars_cov, ev)) {
+                    cflags |= ORA_EIG_NOTFINITE;
+                } else {
+                    for (int i = 0; i < np; i++)
+                        if (ev[i] < 0) cflags |= ORA_LM_NEG_COV_EIG;
+                    for (int i = 0; i < np; i++)
+                        if (res->pars_cov[i * np + i] < 0)
+                            cflags |= ORA_LM_NEG_COV_DIAG;
+                }
+                if (cflags) {
+                    flags |= cflags;
+                    for (int i = 0; i < np; i++) res->pars_err[i] = CDEF;
+                } else {
+                    for (int i = 0; i < np; i++)
+                        res->pars_err[i] = sqrt(res->pars_cov[i * np + i]);
+                }
+            }
+        }
+        res->flags = flags;
+        res->lnprob = NAN; res->s2n_numer = NAN; res->s2n_denom = NAN;
+        res->chi2per = NAN; res->s2n = NAN; res->T = NAN; res->T_err = NAN;
+        res->flux = NAN; res->flux_err = NAN;
+        if (flags == 0) {
+            double lnp_prior = 0.0;
+            int bad = 0;
+            /* calc_lnprob: priors first, then the mixtures */
+            if (m_prior_lnprob(&m, res->pars, &lnp_prior)) bad = 1;
+            if (!bad && m_fill_gmix_all(&m, res->pars)) bad = 1;
+            double lnprob = 0.0, num = 0.0, den = 0.0;
+            int npix = 0;
+            for (int is = 0; is < nstamp && !bad; is++) {
+                double out4[4];
+                fitctx *c = &m.c[is];
+                if (ora_get_loglike(c->gm, c->ngauss, c->pixels, c->npix,
+                                    out4)) {
+                    bad = 1;
+                    break;
+                }
+                lnprob += out4[0]; num += out4[1]; den += out4[2];
+                npix += (int)out4[3];
+            }
+            if (bad) {
+                res->lnprob = -INFINITY; res->s2n_numer = 0.0;
+                res->s2n_denom = BIGVAL; res->npix = 0;
+            } else {
+                res->lnprob = lnprob + lnp_prior;
+                res->s2n_numer = num; res->s2n_denom = den; res->npix = npix;
+            }
+            double s2n = 0.0;
+            if (res->s2n_denom > 0)
+                s2n = res->s2n_numer / sqrt(res->s2n_denom);
+            int dof = res->npix - np;
+            res->chi2per = (res->lnprob / (-0.5)) / dof;
+            res->dof = dof;
+            res->s2n = s2n;
+            res->T = res->pars[4];
+            res->T_err = sqrt(res->pars_cov[4 * np + 4]);
+            /* band 0; the caller slices pars / pars_cov for more bands */
+            res->flux = res->pars[5];
+            res->flux_err = sqrt(res->pars_cov[5 * np + 5]);
+        }
+        free(fvec);
+    }
+    for (int is = 0; is < nstamp; is++) {
+        ctx_free(&m.c[is]);
+        free(pix[is]);
+    }
+    free(pix);
+    free(m.c);
+    return rc;
 }
 
 /* ---------------- threaded batch driver (cpu_baseline) ---------------- */

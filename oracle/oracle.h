@@ -123,6 +123,17 @@ int ora_lm_fit(int model, const double *image, const double *weight,
                int maxfev, double ftol, double xtol, int analytic_jacobian,
                int ignore_zero_weight, ora_lm_result *res);
 
+/* Fitter.go on an ObsList / MultiBandObsList: nstamp stamps of one object,
+ * ordered band by band (bands[] non-decreasing), 5 + nband parameters,
+ * Fp[nband] flux priors (used when prior->present) */
+int ora_lm_fit_multi(int model, int nstamp, const double *images,
+                     const double *weights, int nrow, int ncol,
+                     const ora_jac *jacs, const double *psf_pars, int npsf,
+                     const int32_t *bands, int nband, const double *guess,
+                     const ora_prior *prior, const ora_prior1d *Fp, int maxfev,
+                     double ftol, double xtol, int ignore_zero_weight,
+                     ora_lm_result *res);
+
 /* residual vector and jacobian of FitModel (results.py:439-570) */
 int ora_lm_calc_fdiff(int model, const ora_pixel *pixels, int npix,
                       const double *psf_pars, int npsf, const ora_prior *prior,

@@ -445,3 +445,34 @@ def weighted_sums(image, weight, jac, wt_pars, maxrad, nmom=6,
     return dict(sums=r["sums"][:nmom].copy(),
                 sums_cov=r["sums_cov"][:nmom * nmom].reshape(nmom, nmom).copy(),
                 wsum=float(r["wsum"]), npix=int(r["npix"]))
+
+
+# ------------------------------------------------- multi-epoch / multi-band LM
+def lm_fit_multi(model, images, weights, jacs, psf_pars, bands, nband, guess,
+                 prior=None, Fpriors=None, maxfev=4000, ftol=1.0e-5,
+                 xtol=1.0e-5, ignore_zero_weight=True):
+    """Fitter.go on the stamps of ONE object (ObsList / MultiBandObsList):
+    images [ns,H,W] ordered band by band, bands [ns] int, guess [5+nband],
+    Fpriors a list of nband Prior1D (used with `prior`)"""
+    images, weights, jacs = _f8(images), _f8(weights), _f8(jacs)
+    guess = _f8(guess)
+    ns, H, W = images.shape
+    bands = np.ascontiguousarray(bands, dtype="i4")
+    if psf_pars is None:
+        npsf, psf_ptr = 0, None
+    else:
+        psf_pars = _f8(psf_pars).reshape(ns, -1, 6)
+        npsf, psf_ptr = psf_pars.shape[1], _p(psf_pars)
+    pr = prior if prior is not None else make_prior("none")
+    fp = (Prior1D * nband)()
+    for b in range(nband):
+        fp[b] = Fpriors[b] if Fpriors is not None else pr.F
+    res = np.zeros(1, dtype=LM_RESULT_DTYPE)
+    st = lib().ora_lm_fit_multi(
+        C.c_int(MODELS[model]), C.c_int(ns), _p(images), _p(weights),
+        C.c_int(H), C.c_int(W), _p(jacs), psf_ptr, C.c_int(npsf), _p(bands),
+        C.c_int(nband), _p(guess), C.byref(pr), fp, C.c_int(maxfev),
+        C.c_double(ftol), C.c_double(xtol), C.c_int(int(ignore_zero_weight)),
+        _p(res))
+    assert st == 0, st
+    return res[0]

@@ -1,0 +1,183 @@
+"""
+Multi-epoch / multi-band LM fits (Fitter.go on ObsList / MultiBandObsList,
+SURVEY.md 8f rank 4): the oracle against golden vectors from the reference
+(CPU), the CUDA path against the same vectors and the oracle (GPU).
+"""
+import os
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+PAR_TOL = 1e-5
+
+
+def _golden():
+    return np.load(os.path.join(GOLDEN, "lm_multi.npz"))
+
+
+def _case(g, k):
+    p = "c%d_" % k
+    d = {key[len(p):]: g[key] for key in g.files if key.startswith(p)}
+    d["model"] = str(d["model"])
+    d["nband"] = int(d["nband"])
+    d["prior"] = int(d["prior"])
+    return d
+
+
+def _ora_priors(ora, c):
+    if not c["prior"]:
+        return None, None
+    pr = ora.make_prior("erf")
+    fps = [ora.Prior1D(2, 0, -1.0e2, 1.0, 1.0e9, 1.0e8)
+           for _ in range(c["nband"])]
+    return pr, fps
+
+
+def _check(r, c, np_, exact_counts=True):
+    assert int(r["flags"]) == int(c["flags"])
+    if exact_counts:
+        assert int(r["nfev"]) == int(c["nfev"])
+        assert int(r["ier"]) == int(c["ier"])
+    err = c["pars_err"]
+    tol = np.maximum(PAR_TOL * np.abs(c["pars"]), 1e-3 * err)
+    assert np.all(np.abs(r["pars"][:np_] - c["pars"]) <= tol)
+    cov = np.asarray(r["pars_cov"][:np_ * np_]).reshape(np_, np_)
+    scale = np.sqrt(np.outer(np.diag(c["pars_cov"]), np.diag(c["pars_cov"])))
+    assert np.abs(cov - c["pars_cov"]).max() <= 1e-3 * scale.max()
+    if int(c["flags"]) == 0:
+        assert int(r["npix"]) == int(c["npix"])
+        assert int(r["dof"]) == int(c["dof"])
+        for key in ("lnprob", "s2n", "chi2per", "T", "T_err"):
+            assert abs(float(r[key]) - float(c[key])) \
+                <= 1e-5 * max(abs(float(c[key])), 1.0), key
+
+
+def test_oracle_multi_matches_reference(ora):
+    g = _golden()
+    for k in range(int(g["ncases"])):
+        c = _case(g, k)
+        pr, fps = _ora_priors(ora, c)
+        r = ora.lm_fit_multi(c["model"], c["images"], c["weights"], c["jac"],
+                             c["psf"], c["bands"], c["nband"], c["guess"],
+                             prior=pr, Fpriors=fps)
+        _check(r, c, 5 + c["nband"])
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.fixture(scope="module")
+def ngx():
+    from ngmix_b200 import _lib
+    _lib.init(0)
+    return _lib
+
+
+def _ngx_prior(c):
+    import ngmix_b200 as ngmix
+    if not c["prior"]:
+        return None
+    return ngmix.joint_prior.PriorSimpleSep(
+        ngmix.priors.CenPrior(0.0, 0.0, 0.263, 0.263),
+        ngmix.priors.GPriorBA(0.3),
+        ngmix.priors.TwoSidedErf(-1.0, 0.1, 1.0e3, 1.0),
+        [ngmix.priors.TwoSidedErf(-1.0e2, 1.0, 1.0e9, 1.0e8)
+         for _ in range(c["nband"])])
+
+
+@pytest.mark.gpu
+def test_gpu_multi_matches_reference(ngx):
+    import ngmix_b200 as ngmix
+    g = _golden()
+    for k in range(int(g["ncases"])):
+        c = _case(g, k)
+        ns = c["images"].shape[0]
+        rec = ngmix.fit_batch_multi(
+            c["model"], [0, ns], c["bands"], c["nband"], c["images"],
+            c["weights"], c["jac"], c["psf"], c["guess"][None],
+            prior=_ngx_prior(c))[0]
+        _check(rec, c, 5 + c["nband"])
+
+
+@pytest.mark.gpu
+def test_gpu_fitter_go_obslist_and_mbobs(ngx):
+    """the reference-facing call: Fitter.go(ObsList / MultiBandObsList)"""
+    import ngmix_b200 as ngmix
+    g = _golden()
+    for k in (1, 7, 13, 16):
+        c = _case(g, k)
+        mbobs = ngmix.MultiBandObsList()
+        i = 0
+        for b in range(c["nband"]):
+            ol = ngmix.ObsList()
+            while i < c["bands"].size and c["bands"][i] == b:
+                j = c["jac"][i]
+                jac = ngmix.Jacobian(row=j[0], col=j[1], dvdrow=j[2],
+                                     dvdcol=j[3], dudrow=j[4], dudcol=j[5])
+                psf_obs = ngmix.Observation(
+                    np.zeros((5, 5)) + 1.0,
+                    gmix=ngmix.GMix(pars=c["psf"][i].ravel()))
+                ol.append(ngmix.Observation(c["images"][i],
+                                            weight=c["weights"][i],
+                                            jacobian=jac, psf=psf_obs))
+                i += 1
+            mbobs.append(ol)
+        fitter = ngmix.Fitter(model=c["model"], prior=_ngx_prior(c))
+        obs_in = mbobs if c["nband"] > 1 else mbobs[0]
+        res = fitter.go(obs=obs_in, guess=c["guess"])
+        np_ = 5 + c["nband"]
+        assert res["flags"] == int(c["flags"])
+        assert res["nfev"] == int(c["nfev"]) and res["ier"] == int(c["ier"])
+        assert np.allclose(res["pars"], c["pars"], rtol=1e-5,
+                           atol=1e-3 * c["pars_err"].max())
+        assert res["pars_cov"].shape == (np_, np_)
+        assert np.allclose(np.atleast_1d(res["flux"]), c["flux"], rtol=1e-5)
+        assert np.allclose(np.atleast_1d(res["flux_err"]), c["flux_err"],
+                           rtol=1e-3)
+        assert abs(res["s2n"] - float(c["s2n"])) < 1e-5 * float(c["s2n"])
+        gm = res.get_convolved_gmix(band=c["nband"] - 1, obsnum=0)
+        assert gm.get_data().size == c["psf"].shape[1] * \
+            {"gauss": 1, "exp": 6, "dev": 10}[c["model"]]
+
+
+@pytest.mark.gpu
+def test_gpu_multi_batch_vs_oracle(ngx, ora):
+    """a batch of objects with ragged epoch counts, two bands, masked pixels"""
+    import ngmix_b200 as ngmix
+    from ngmix_b200 import sims
+    rng = np.random.RandomState(77)
+    nobj, nband = 12, 2
+    b = sims.make_lm_batch(60, seed0=77000, dims=(24, 24), noise=0.05)
+    starts, bands, guesses = [0], [], []
+    k = 0
+    for i in range(nobj):
+        ne = [int(rng.randint(1, 4)), int(rng.randint(1, 3))]
+        for band in range(nband):
+            bands += [band] * ne[band]
+        k += sum(ne)
+        starts.append(k)
+        gs = b["guess"][starts[i]].copy()
+        guesses.append(np.append(gs, gs[5] * 1.02))
+    ns = starts[-1]
+    images, weights = b["images"][:ns].copy(), b["weights"][:ns].copy()
+    weights[3][5:9, :] = 0.0
+    jac, psf = b["jac"][:ns], b["psf"][:ns]
+    guesses = np.array(guesses)
+    recs = ngmix.fit_batch_multi("exp", starts, bands, nband, images, weights,
+                                 jac, psf, guesses)
+    assert recs.shape == (nobj,)
+    for i in range(nobj):
+        sl = slice(starts[i], starts[i + 1])
+        r = ora.lm_fit_multi("exp", images[sl], weights[sl], jac[sl], psf[sl],
+                             np.array(bands[sl]), nband, guesses[i])
+        assert recs["flags"][i] == r["flags"]
+        assert recs["npix"][i] == r["npix"]
+        if r["flags"] == 0:
+            tol = np.maximum(PAR_TOL * np.abs(r["pars"][:7]),
+                             1e-3 * r["pars_err"][:7])
+            assert np.all(np.abs(recs["pars"][i][:7] - r["pars"][:7]) <= tol)
+            assert abs(recs["lnprob"][i] - r["lnprob"]) \
+                <= 1e-6 * abs(r["lnprob"])
+    # an object without usable pixels is reported, not fitted
+    weights[starts[2]:starts[3]] = 0.0
+    recs = ngmix.fit_batch_multi("exp", starts, bands, nband, images, weights,
+                                 jac, psf, guesses)
+    assert recs["flags"][2] == 1 and recs["nfev"][2] == 0
