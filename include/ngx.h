@@ -307,6 +307,23 @@ int ngx_weighted_sums(int n, int ngauss, const ngx_gauss *gmix,
                       const double *maxrad, int nmom, int ignore_zero_weight,
                       ngx_mom_result *res, void *stream);
 
+/* template (psf) flux: PSFFluxFitModel.go (fitting/results.py:676-805),
+ * zero-lag cross-correlation of the exact-exp render of each stamp's template
+ * mixture with the image, chi^2 at the fitted flux.  Object i owns stamps
+ * stamp_start[i] .. stamp_start[i+1]-1; gm_pars [nstamps, ngauss, 6] are the
+ * full parameters of each stamp's template (the psf mixture for a psf flux);
+ * normalize != 0 sets each template's flux to 1 first. */
+typedef struct {
+    int32_t flags, pad;    /* DIV_ZERO 2^14, BAD_VAR 2^6, GMIX_RANGE_ERROR */
+    double flux, flux_err, chi2per, dof;
+} ngx_flux_result;
+int ngx_template_flux(int nobj, const int32_t *stamp_start,
+                      const double *images, const double *weights,
+                      const ngx_jacobian *jac, int nrow, int ncol,
+                      const double *gm_pars, int ngauss, int normalize,
+                      int ignore_zero_weight, ngx_flux_result *res,
+                      void *stream);
+
 /* ------------------------------------------------------------------ */
 /* host-buffer variants (synchronous; H2D/D2H inside) */
 int ngx_gmix_fill_host(int n, int model, int ngauss, const double *pars,
@@ -358,6 +375,11 @@ int ngx_weighted_sums_host(int n, int ngauss, const ngx_gauss *gmix,
                            const ngx_jacobian *jac, int nrow, int ncol,
                            const double *maxrad, int nmom,
                            int ignore_zero_weight, ngx_mom_result *res);
+int ngx_template_flux_host(int nobj, const int32_t *stamp_start,
+                           const double *images, const double *weights,
+                           const ngx_jacobian *jac, int nrow, int ncol,
+                           const double *gm_pars, int ngauss, int normalize,
+                           int ignore_zero_weight, ngx_flux_result *res);
 int ngx_lm_fit_multi_host(int nobj, int model, const int32_t *stamp_start,
                           const int32_t *stamp_band, int nband,
                           const double *images, const double *weights,

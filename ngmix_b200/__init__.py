@@ -20,7 +20,10 @@ from .observation import (  # noqa: F401
     Observation, ObsList, MultiBandObsList, get_mb_obs,
 )
 from . import fitting, em, admom  # noqa: F401
-from .fitting import Fitter, fit_batch, fit_batch_multi  # noqa: F401
+from .fitting import (  # noqa: F401
+    Fitter, PSFFluxFitter, fit_batch, fit_batch_multi,
+)
+from . import guessers, runners, bootstrap  # noqa: F401
 from .em import EMFitter, run_em, em_batch  # noqa: F401
 from .admom import AdmomFitter, run_admom, admom_batch  # noqa: F401
 from . import joint_prior, moments, gaussmom  # noqa: F401

@@ -102,6 +102,7 @@ SYMBOLS = [
     "ngx_admom_host", "ngx_peak_dfma", "ngx_peak_dmma",
     "ngx_weighted_sums", "ngx_weighted_sums_host",
     "ngx_lm_fit_multi", "ngx_lm_fit_multi_host",
+    "ngx_template_flux", "ngx_template_flux_host",
 ]
 
 _lib = None
@@ -537,6 +538,33 @@ def weighted_sums_device(n, ngauss, d_gmix, d_images, d_weights, d_jac, nrow,
         C.c_int(nrow), C.c_int(ncol), C.c_void_p(d_maxrad), C.c_int(nmom),
         C.c_int(int(ignore_zero_weight)), C.c_void_p(d_res),
         C.c_void_p(stream)))
+
+
+FLUX_RESULT_DTYPE = np.dtype([("flags", "i4"), ("pad", "i4"), ("flux", "f8"),
+                              ("flux_err", "f8"), ("chi2per", "f8"),
+                              ("dof", "f8")])
+
+
+def template_flux(stamp_start, images, weights, jac, gm_pars, normalize=True,
+                  ignore_zero_weight=True):
+    """batched PSFFluxFitModel.go: object i owns stamps
+    stamp_start[i]:stamp_start[i+1]; gm_pars [ns, ngauss, 6] template
+    mixtures; returns FLUX_RESULT_DTYPE [nobj]"""
+    init()
+    images = _f8(images)
+    weights = _f8(weights)
+    ns, H, W = images.shape
+    jac = as_jac(jac, ns)
+    stamp_start = np.ascontiguousarray(stamp_start, dtype="i4")
+    nobj = stamp_start.size - 1
+    assert stamp_start[0] == 0 and stamp_start[-1] == ns
+    gm_pars = _f8(gm_pars).reshape(ns, -1, 6)
+    res = np.zeros(nobj, dtype=FLUX_RESULT_DTYPE)
+    check(lib().ngx_template_flux_host(
+        C.c_int(nobj), _p(stamp_start), _p(images), _p(weights), _p(jac),
+        C.c_int(H), C.c_int(W), _p(gm_pars), C.c_int(gm_pars.shape[1]),
+        C.c_int(int(normalize)), C.c_int(int(ignore_zero_weight)), _p(res)))
+    return res
 
 
 def peak_dfma(iters=20000):

@@ -209,6 +209,137 @@ k_weighted_sums(int ngauss, const ngx_gauss *__restrict__ gmix,
     }
 }
 
+// ---------------------------------------------------------------------
+// ngx_template_flux: PSFFluxFitModel.go (fitting/results.py:702-770).  One
+// CTA per object; the object's stamps are walked twice: zero-lag
+// cross-correlation of the exact-exp render of each stamp's template mixture
+// with the image (all pixels; zero weights drop out), then chi^2 at the
+// fitted flux.
+struct FluxShared {
+    ngx_gauss gm[16];
+    double tot[8];
+    double flux, norm;
+    int bad;
+};
+
+__device__ __forceinline__ void flux_set_mixture(FluxShared *sh,
+                                                 const double *pars, int ngauss,
+                                                 int normalize, int ipass,
+                                                 double flux) {
+    // one thread: GMix(pars=...), set_flux(1.0) (gmix.py:299-311), and for
+    // the second pass set_flux(flux * norm)
+    double p[16], psum = 0.0;
+    for (int k = 0; k < ngauss; k++) { p[k] = pars[6 * k]; psum += p[k]; }
+    if (normalize) {
+        double rat = 1.0 / psum;
+        for (int k = 0; k < ngauss; k++) p[k] *= rat;
+    }
+    double nsum = 0.0;
+    for (int k = 0; k < ngauss; k++) nsum += p[k];
+    if (ipass == 1) {
+        sh->norm = nsum;
+    } else {
+        double rat = (flux * nsum) / nsum;
+        for (int k = 0; k < ngauss; k++) p[k] *= rat;
+    }
+    sh->bad = 0;
+    for (int k = 0; k < ngauss; k++) {
+        ngx_gauss g;
+        const double *q = pars + 6 * k;
+        gauss_set(g, p[k], q[1], q[2], q[3], q[4], q[5]);
+        if (gauss_set_norm(g) != NGX_ST_OK) sh->bad = 1;
+        sh->gm[k] = g;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_template_flux(const int32_t *__restrict__ stamp_start,
+                const double *__restrict__ images,
+                const double *__restrict__ weights,
+                const ngx_jacobian *__restrict__ jac, int nrow, int ncol,
+                const double *__restrict__ gm_pars, int ngauss, int normalize,
+                int ignore_zero_weight, ngx_flux_result *__restrict__ res) {
+    __shared__ FluxShared sh;
+    __shared__ double scratch[32 * 4];
+    const int obj = blockIdx.x;
+    const int s0 = stamp_start[obj], s1 = stamp_start[obj + 1];
+    const int ntot = nrow * ncol;
+    double xcorr = 0.0, msq = 0.0, chi2 = 0.0, totpix = 0.0, effpix = 0.0;
+    int bad = 0;
+    for (int ipass = 1; ipass <= 2 && !bad; ipass++) {
+        for (int e = s0; e < s1; e++) {
+            __syncthreads();
+            if (threadIdx.x == 0)
+                flux_set_mixture(&sh, gm_pars + (size_t)e * 6 * ngauss, ngauss,
+                                 normalize, ipass, sh.flux);
+            __syncthreads();
+            if (sh.bad) { bad = 1; break; }
+            const ngx_jacobian j = jac[e];
+            const double area = j.scale * j.scale;
+            const double *im = images + (size_t)e * ntot;
+            const double *wt = weights + (size_t)e * ntot;
+            double acc[5] = {0, 0, 0, 0, 0};
+            for (int p = threadIdx.x; p < ntot; p += blockDim.x) {
+                int row = p / ncol, col = p - row * ncol;
+                double rowdiff = row - j.row0, coldiff = col - j.col0;
+                double v = j.dvdrow * rowdiff + j.dvdcol * coldiff;
+                double u = j.dudrow * rowdiff + j.dudcol * coldiff;
+                double model = 0.0;
+                for (int k = 0; k < ngauss; k++)
+                    model += eval_exact(sh.gm[k], v, u, area);
+                double d = im[p], w = wt[p];
+                if (ipass == 1) {
+                    acc[0] += model * d * w;
+                    acc[1] += model * model * w;
+                    if (!(ignore_zero_weight && w <= 0.0)) acc[2] += 1.0;
+                    if (w > 0) acc[3] += 1.0;
+                } else {
+                    double diff = model - d;
+                    acc[4] += diff * diff * w;
+                }
+            }
+            block_sum_to<5>(acc, scratch, sh.tot);
+            xcorr += sh.tot[0]; msq += sh.tot[1];
+            totpix += sh.tot[2]; effpix += sh.tot[3];
+            chi2 += sh.tot[4];
+        }
+        if (ipass == 1) {
+            if (msq == 0) break;
+            __syncthreads();
+            if (threadIdx.x == 0) sh.flux = xcorr / msq;
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        ngx_flux_result r;
+        r.pad = 0;
+        int flags = 0;
+        double flux = -9.999e9, flux_err = 9.999e9;
+        if (bad) {
+            flags = NGX_GMIX_RANGE_ERROR;
+            r.chi2per = 9999.0;
+            r.dof = 0.0;
+        } else {
+            if (msq != 0) flux = xcorr / msq;
+            double dof = effpix - 1;
+            if (dof <= 0) dof = 1.0e-6;
+            r.chi2per = chi2 / dof;
+            r.dof = dof;
+            if (msq == 0 || totpix == 1) {
+                flags |= 1 << 14;               // DIV_ZERO
+            } else {
+                double arg = chi2 / msq / (totpix - 1);
+                if (arg >= 0.0) flux_err = sqrt(arg);
+                else flags |= 1 << 6;           // BAD_VAR
+            }
+        }
+        r.flags = flags;
+        r.flux = flux;
+        r.flux_err = flux_err;
+        res[obj] = r;
+    }
+}
+
 }  // namespace ngx
 
 using namespace ngx;
@@ -255,6 +386,49 @@ int ngx_weighted_sums_host(int n, int ngauss, const ngx_gauss *gmix,
     NGX_CUDA(dj.err); NGX_CUDA(dr.err);
     int rc = ngx_weighted_sums(n, ngauss, dg.d, di.d, dw.d, dj.d, nrow, ncol,
                                dm.d, nmom, ignore_zero_weight, dr.d, 0);
+    if (rc) return rc;
+    NGX_CUDA(cudaDeviceSynchronize());
+    NGX_CUDA(dr.to_host(res));
+    return NGX_OK;
+}
+
+int ngx_template_flux(int nobj, const int32_t *stamp_start,
+                      const double *images, const double *weights,
+                      const ngx_jacobian *jac, int nrow, int ncol,
+                      const double *gm_pars, int ngauss, int normalize,
+                      int ignore_zero_weight, ngx_flux_result *res,
+                      void *stream) {
+    NGX_REQUIRE(nobj >= 0 && stamp_start && images && weights && jac);
+    NGX_REQUIRE(gm_pars && res && ngauss >= 1 && ngauss <= 16);
+    NGX_REQUIRE(nrow >= 1 && ncol >= 1);
+    if (nobj == 0) return NGX_OK;
+    k_template_flux<<<nobj, 128, 0, as_stream(stream)>>>(
+        stamp_start, images, weights, jac, nrow, ncol, gm_pars, ngauss,
+        normalize, ignore_zero_weight, res);
+    NGX_LAUNCH_CHECK();
+    return NGX_OK;
+}
+
+int ngx_template_flux_host(int nobj, const int32_t *stamp_start,
+                           const double *images, const double *weights,
+                           const ngx_jacobian *jac, int nrow, int ncol,
+                           const double *gm_pars, int ngauss, int normalize,
+                           int ignore_zero_weight, ngx_flux_result *res) {
+    NGX_REQUIRE(nobj >= 0 && stamp_start && images && weights && jac);
+    NGX_REQUIRE(gm_pars && res);
+    if (nobj == 0) return NGX_OK;
+    const int ns = stamp_start[nobj];
+    const size_t ntot = (size_t)nrow * ncol;
+    DevBuf<int32_t> dss(nobj + 1, stamp_start);
+    DevBuf<double> di(ns * ntot, images), dw(ns * ntot, weights);
+    DevBuf<ngx_jacobian> dj(ns, jac);
+    DevBuf<double> dg((size_t)ns * ngauss * 6, gm_pars);
+    DevBuf<ngx_flux_result> dr(nobj);
+    NGX_CUDA(dss.err); NGX_CUDA(di.err); NGX_CUDA(dw.err); NGX_CUDA(dj.err);
+    NGX_CUDA(dg.err); NGX_CUDA(dr.err);
+    int rc = ngx_template_flux(nobj, dss.d, di.d, dw.d, dj.d, nrow, ncol,
+                               dg.d, ngauss, normalize, ignore_zero_weight,
+                               dr.d, 0);
     if (rc) return rc;
     NGX_CUDA(cudaDeviceSynchronize());
     NGX_CUDA(dr.to_host(res));

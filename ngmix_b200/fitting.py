@@ -197,6 +197,54 @@ class FitResult(dict):
         return gm.make_image(obs.image.shape, jacobian=obs.jacobian)
 
 
+class PSFFluxFitter(object):
+    """
+    Template flux by zero-lag cross-correlation (fitting/fitters.py:144-181,
+    results.py:676-805) through ngx_template_flux: with do_psf the psf
+    mixtures of the observation(s) are the templates ("psf flux"), otherwise
+    the observations' own mixtures.  Pixel templates are not supported.
+    """
+
+    def __init__(self, do_psf=True, normalize_psf=True):
+        self.do_psf = do_psf
+        self.normalize_psf = normalize_psf
+
+    def go(self, obs):
+        from .observation import Observation, ObsList
+        if isinstance(obs, Observation):
+            obslist = [obs]
+        elif isinstance(obs, ObsList):
+            obslist = list(obs)
+        else:
+            raise ValueError("obs should be Observation or ObsList")
+        gms = []
+        for o in obslist:
+            src = o.psf if self.do_psf else o
+            if not src.has_gmix():
+                raise ValueError("neither gmix or template image are set")
+            gms.append(src.gmix.get_full_pars().reshape(-1, 6))
+        shape = obslist[0].image.shape
+        if any(o.image.shape != shape for o in obslist) \
+                or any(g.shape != gms[0].shape for g in gms):
+            raise NotImplementedError(
+                "all stamps must share their size and mixture size")
+        # without do_psf the template is always normalised (results.py:853)
+        normalize = self.normalize_psf if self.do_psf else True
+        rec = _lib.template_flux(
+            [0, len(obslist)], np.stack([o.image for o in obslist]),
+            np.stack([o.weight for o in obslist]),
+            np.stack([np.asarray(o._jacobian._data.view("f8")).reshape(8)
+                      for o in obslist]),
+            np.stack(gms), normalize=normalize,
+            ignore_zero_weight=all(o.ignore_zero_weight for o in obslist))[0]
+        if rec["flags"] & 128:
+            raise GMixRangeError("det or T too low")
+        return {"model": "template", "flags": int(rec["flags"]),
+                "chi2per": float(rec["chi2per"]), "dof": float(rec["dof"]),
+                "flux": float(rec["flux"]),
+                "flux_err": float(rec["flux_err"])}
+
+
 class Fitter(object):
     """
     Levenberg-Marquardt fit of a PSF-convolved model to an observation.

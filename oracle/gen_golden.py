@@ -777,6 +777,126 @@ def gen_lm_multi():
     save("lm_multi", **out)
 
 
+def gen_psfflux():
+    """PSFFluxFitter.go (template flux by cross-correlation) on single
+    observations and ObsLists"""
+    from ngmix.fitting import PSFFluxFitter
+    b = sims.make_lm_batch(12, seed0=9400, noise=0.05)
+    rng = np.random.RandomState(94)
+    b["weights"][2][rng.uniform(size=b["weights"][2].shape) < 0.2] = 0.0
+    out = {k: b[k] for k in ("images", "weights", "jac", "psf")}
+    groups = [[0], [1], [2], [3, 4, 5], [6, 7], [8, 9, 10, 11]]
+    out["ngroups"] = np.array(len(groups))
+    for normalize in (True, False):
+        tag = "n%d_" % int(normalize)
+        res = {k: np.zeros(len(groups)) for k in
+               ("flags", "flux", "flux_err", "chi2per", "dof")}
+        for ig, grp in enumerate(groups):
+            ol = ngmix.ObsList()
+            for i in grp:
+                ppars = b["psf"][i].copy()
+                if not normalize:
+                    ppars[:, 0] *= 1.7      # unnormalised psf mixture
+                psf_obs = ngmix.Observation(
+                    np.zeros((5, 5)) + 1.0, gmix=ngmix.GMix(pars=ppars.ravel()))
+                ol.append(ngmix.Observation(
+                    b["images"][i], weight=b["weights"][i],
+                    jacobian=jac_from_record(b["jac"][i]), psf=psf_obs))
+            obs_in = ol if len(grp) > 1 else ol[0]
+            r = PSFFluxFitter(normalize_psf=normalize).go(obs=obs_in)
+            for k in res:
+                res[k][ig] = r[k]
+        for k, v in res.items():
+            out[tag + k] = v
+        print(tag, res["flux"], res["flags"])
+    for ig, grp in enumerate(groups):
+        out["g%d" % ig] = np.array(grp)
+    save("psfflux", **out)
+
+
+def _boot_obs(i, b, p):
+    psf_obs = ngmix.Observation(
+        p["images"][i], weight=p["weights"][i],
+        jacobian=jac_from_record(p["jac"][i]))
+    return ngmix.Observation(
+        b["images"][i], weight=b["weights"][i],
+        jacobian=jac_from_record(b["jac"][i]), psf=psf_obs)
+
+
+def gen_boot():
+    """guessers with fixed seeds, and the PSF-EM -> psf-flux guess -> LM
+    chain through PSFRunner / Runner / Bootstrapper"""
+    from ngmix import guessers
+    from ngmix.em import EMFitter
+    from ngmix.fitting import Fitter
+    from ngmix.runners import Runner, PSFRunner
+    from ngmix.bootstrap import Bootstrapper
+    n = 8
+    b = sims.make_lm_batch(n, seed0=9600, noise=0.03)
+    # psf images rendered from the same psf mixtures as the galaxy stamps
+    p = dict(images=np.zeros((n, 25, 25)), weights=np.zeros((n, 25, 25)),
+             jac=np.zeros((n, 8)))
+    for i in range(n):
+        rng = np.random.RandomState(9700 + i)
+        p["jac"][i] = sims.diag_jacobian(12.0 + rng.uniform(-0.3, 0.3),
+                                         12.0 + rng.uniform(-0.3, 0.3), 0.263)
+        im = sims.render_full_pars(b["psf"][i], (25, 25), p["jac"][i])
+        p["images"][i] = im + rng.normal(0.0, 1.0e-4, size=im.shape)
+        p["weights"][i] = 1.0 / 1.0e-4 ** 2
+    out = {"images": b["images"], "weights": b["weights"], "jac": b["jac"],
+           "psf_images": p["images"], "psf_weights": p["weights"],
+           "psf_jac": p["jac"], "n": np.array(n)}
+    # ---- stand-alone guessers, fixed seeds
+    obs0 = _boot_obs(0, b, p)
+    for ng in (1, 2, 3, 4, 5):
+        for moms in (0, 1):
+            g = guessers.GMixPSFGuesser(np.random.RandomState(100 + ng), ng,
+                                        guess_from_moms=bool(moms))
+            out["gpsf_%d_%d" % (ng, moms)] = g(obs0.psf).get_full_pars()
+    out["gsimple"] = guessers.SimplePSFGuesser(
+        np.random.RandomState(7))(obs0.psf)
+    out["gsimple_moms"] = guessers.SimplePSFGuesser(
+        np.random.RandomState(7), guess_from_moms=True)(obs0.psf)
+    out["gtflux1"] = guessers.TFluxGuesser(
+        np.random.RandomState(8), 0.4, 100.0)()
+    out["gtflux3"] = guessers.TFluxGuesser(
+        np.random.RandomState(8), 0.4, [100.0, 50.0, 20.0])(nrand=3)
+    out["gpars"] = guessers.ParsGuesser(
+        np.random.RandomState(9), [0.1, -0.1, 0.2, 0.7, 0.5, 80.0])()
+    out["gpars4"] = guessers.ParsGuesser(
+        np.random.RandomState(9), [0.1, -0.1, 0.2, 0.85, 0.5, 80.0],
+        widths=[0.01, 0.01, 0.05, 0.05, 0.2, 0.2])(nrand=4)
+    # ---- the chain
+    res = dict(flags=np.zeros(n, "i4"), nfev=np.zeros(n, "i4"),
+               pars=np.zeros((n, 6)), pars_err=np.zeros((n, 6)),
+               psf_flags=np.zeros(n, "i4"), psf_numiter=np.zeros(n, "i4"),
+               psf_pars=np.zeros((n, 12)), psf_flux=np.zeros(n),
+               s2n=np.zeros(n))
+    for i in range(n):
+        rng = np.random.RandomState(9800 + i)
+        obs = _boot_obs(i, b, p)
+        psf_runner = PSFRunner(
+            fitter=EMFitter(tol=1.0e-5),
+            guesser=guessers.GMixPSFGuesser(rng=rng, ngauss=2), ntry=2)
+        runner = Runner(
+            fitter=Fitter(model="exp"),
+            guesser=guessers.TPSFFluxGuesser(rng=rng, T=0.25), ntry=2)
+        r = Bootstrapper(runner=runner, psf_runner=psf_runner).go(obs)
+        pres = obs.psf.meta["result"]
+        res["flags"][i], res["nfev"][i] = r["flags"], r["nfev"]
+        res["pars"][i], res["pars_err"][i] = r["pars"], r["pars_err"]
+        res["s2n"][i] = r["s2n"]
+        res["psf_flags"][i] = pres["flags"]
+        res["psf_numiter"][i] = pres["numiter"]
+        res["psf_pars"][i] = obs.psf.gmix.get_full_pars()
+        res["psf_flux"][i] = ngmix.fitting.PSFFluxFitter().go(obs)["flux"]
+    print("boot flags", res["flags"], "nfev", res["nfev"], "psf numiter",
+          res["psf_numiter"])
+    for k, v in res.items():
+        out["boot_" + k] = v
+    save("boot", **out)
+
+
 GENERATORS = {
     "fastexp": gen_fastexp,
     "gmix": gen_gmix,
@@ -788,6 +908,8 @@ GENERATORS = {
     "lm_bdf": gen_lm_bdf,
     "moments": gen_moments,
     "lm_multi": gen_lm_multi,
+    "psfflux": gen_psfflux,
+    "boot": gen_boot,
 }
 
 if __name__ == "__main__":

@@ -593,3 +593,98 @@ int ora_weighted_sums_go(const double *image, const double *weight, int nrow,
     free(wt);
     return st;
 }
+
+/* ------------------------------------------------------------------ */
+/* PSFFluxFitModel.go (fitting/results.py:702-770): zero-lag
+ * cross-correlation of the exact-exp render of the template mixture with the
+ * image, over ALL pixels (zero weights drop out through wt), then chi^2 at
+ * the fitted flux.  totpix counts obs.pixels (after the zero-weight cut),
+ * the dof counts weight > 0 (get_effective_npix). */
+int ora_template_flux(int nstamp, const double *images, const double *weights,
+                      int nrow, int ncol, const ora_jac *jacs,
+                      const double *gm_pars, int ngauss, int normalize,
+                      int ignore_zero_weight, ora_flux_result *res) {
+    int ntot = nrow * ncol;
+    ora_gauss *gm = (ora_gauss *)malloc(sizeof(ora_gauss) * (size_t)ngauss);
+    double *norms = (double *)malloc(sizeof(double) * (size_t)nstamp);
+    double xcorr = 0.0, msq = 0.0, chi2 = 0.0;
+    int totpix = 0, effpix = 0, flags = 0;
+    double flux = -9.999e9, flux_err = 9.999e9;
+    memset(res, 0, sizeof(*res));
+    for (int ipass = 1; ipass <= 2; ipass++) {
+        for (int is = 0; is < nstamp; is++) {
+            const double *im = images + (size_t)is * ntot;
+            const double *wt = weights + (size_t)is * ntot;
+            const ora_jac *jac = &jacs[is];
+            double pars[6 * 16];
+            for (int i = 0; i < 6 * ngauss; i++)
+                pars[i] = gm_pars[(size_t)is * 6 * ngauss + i];
+            double psum = 0.0;
+            for (int k = 0; k < ngauss; k++) psum += pars[6 * k];
+            if (normalize) {
+                /* GMix.set_flux(1.0), gmix.py:299-311 */
+                double rat = 1.0 / psum;
+                for (int k = 0; k < ngauss; k++) pars[6 * k] *= rat;
+            }
+            if (ipass == 1) {
+                double nsum = 0.0;
+                for (int k = 0; k < ngauss; k++) nsum += pars[6 * k];
+                norms[is] = nsum;
+            } else {
+                double cur = 0.0;
+                for (int k = 0; k < ngauss; k++) cur += pars[6 * k];
+                double rat = (flux * norms[is]) / cur;
+                for (int k = 0; k < ngauss; k++) pars[6 * k] *= rat;
+            }
+            if (ora_gmix_fill(ORA_FULL, pars, 6 * ngauss, gm, ngauss)
+                || ora_gmix_set_norms(gm, ngauss)) {
+                free(gm); free(norms);
+                return ORA_RANGE_ERROR;
+            }
+            double area = jac->scale * jac->scale;
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int row = 0; row < nrow; row++)
+                for (int col = 0; col < ncol; col++) {
+                    double rowdiff = row - jac->row0, coldiff = col - jac->col0;
+                    double v = jac->dvdrow * rowdiff + jac->dvdcol * coldiff;
+                    double u = jac->dudrow * rowdiff + jac->dudcol * coldiff;
+                    double model = 0.0;
+                    for (int k = 0; k < ngauss; k++)
+                        model += gauss_eval_exact(&gm[k], v, u, area);
+                    double d = im[row * ncol + col], w = wt[row * ncol + col];
+                    if (ipass == 1) {
+                        s1 += model * d * w;
+                        s2 += model * model * w;
+                        if (!(ignore_zero_weight && w <= 0.0)) totpix++;
+                        if (w > 0) effpix++;
+                    } else {
+                        double diff = model - d;
+                        s3 += diff * diff * w;
+                    }
+                }
+            if (ipass == 1) { xcorr += s1; msq += s2; }
+            else chi2 += s3;
+        }
+        if (ipass == 1) {
+            if (msq == 0) break;
+            flux = xcorr / msq;
+        }
+    }
+    double dof = effpix - 1;
+    if (dof <= 0) dof = 1.0e-6;
+    double chi2per = 9999.0;
+    if (dof > 0) chi2per = chi2 / dof;
+    else flags |= (1 << 15);
+    if (msq == 0 || totpix == 1) {
+        flags |= (1 << 14);                     /* DIV_ZERO */
+    } else {
+        double arg = chi2 / msq / (totpix - 1);
+        if (arg >= 0.0) flux_err = sqrt(arg);
+        else flags |= (1 << 6);                 /* BAD_VAR */
+    }
+    res->flags = flags;
+    res->flux = flux; res->flux_err = flux_err;
+    res->chi2per = chi2per; res->dof = dof;
+    free(gm); free(norms);
+    return ORA_OK;
+}

@@ -222,6 +222,18 @@ int ora_admom_go_batch(int n, int nthreads, const double *images,
                        const double *jacs, const double *guess_pars,
                        const ora_admom_conf *conf, ora_admom_result *res);
 
+/* ---- template (psf) flux: PSFFluxFitModel.go, fitting/results.py:676-805 ----
+ * nstamp stamps of one object; gm_pars [nstamp, ngauss, 6] full parameters of
+ * the template mixture of each stamp (the psf mixture for a psf flux) */
+typedef struct {
+    int32_t flags, pad;
+    double flux, flux_err, chi2per, dof;
+} ora_flux_result;
+int ora_template_flux(int nstamp, const double *images, const double *weights,
+                      int nrow, int ncol, const ora_jac *jacs,
+                      const double *gm_pars, int ngauss, int normalize,
+                      int ignore_zero_weight, ora_flux_result *res);
+
 /* ---- weighted moments (ngmix/gmix/gmix_nb.py:681-821) ---- */
 #define ORA_NMOM_MAX 17
 typedef struct {

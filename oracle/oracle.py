@@ -476,3 +476,27 @@ def lm_fit_multi(model, images, weights, jacs, psf_pars, bands, nband, guess,
         _p(res))
     assert st == 0, st
     return res[0]
+
+
+# ------------------------------------------------------------ template flux
+FLUX_RESULT_DTYPE = np.dtype([("flags", "i4"), ("pad", "i4"), ("flux", "f8"),
+                              ("flux_err", "f8"), ("chi2per", "f8"),
+                              ("dof", "f8")])
+
+
+def template_flux(images, weights, jacs, gm_pars, normalize=True,
+                  ignore_zero_weight=True):
+    """PSFFluxFitModel.go on the stamps of one object; gm_pars
+    [ns, ngauss, 6]"""
+    images, weights, jacs = _f8(images), _f8(weights), _f8(jacs)
+    if images.ndim == 2:
+        images, weights = images[None], weights[None]
+    ns, H, W = images.shape
+    gm_pars = _f8(gm_pars).reshape(ns, -1, 6)
+    res = np.zeros(1, dtype=FLUX_RESULT_DTYPE)
+    st = lib().ora_template_flux(
+        C.c_int(ns), _p(images), _p(weights), C.c_int(H), C.c_int(W),
+        _p(jacs), _p(gm_pars), C.c_int(gm_pars.shape[1]),
+        C.c_int(int(normalize)), C.c_int(int(ignore_zero_weight)), _p(res))
+    assert st == 0, st
+    return res[0]
