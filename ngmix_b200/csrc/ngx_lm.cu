@@ -1521,9 +1521,18 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
         return config_and_launch(k_lm_fit<0, 3, 2, 4, false>, a, threads,
                                  smem_both, st);
     }
-    if (wg)
+    if (wg) {
+        // large stamps with the np + 1 forward-difference mixtures resident
+        // leave room for few CTAs: give each one eight warps
+        if (threads == 128 && 4 * (smem + sizeof(LMShared) + 1024)
+                > (size_t)smem_optin_bytes() + 1024) {
+            size_t smem8 = smem + sizeof(double) * 48 * 4;
+            return config_and_launch(k_lm_fit<1, 3, 2, 2, true, 256>, a, 256,
+                                     smem8, st);
+        }
         return config_and_launch(k_lm_fit<1, 3, 2, 4, true>, a, threads, smem,
                                  st);
+    }
     return config_and_launch(k_lm_fit<1, 3, 2, 4, false>, a, threads,
                              smem_both, st);
 }
