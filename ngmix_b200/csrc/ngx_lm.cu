@@ -241,7 +241,8 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
                                            const double *im,
                                            const double *rowd,
                                            const double *cold,
-                                           double (&sums)[4]) {
+                                           double (&sums)[4],
+                                           double *mstore = nullptr) {
     const int T = blockDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ntile = a.nq >> 5;
@@ -298,6 +299,9 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
         for (int c = 0; c < CV; c++) {
             int q = q0 + 32 * c;
             if (q < a.nq) {
+                // forward-difference mode keeps the model of the last
+                // evaluated point: MINPACK differences against it
+                if (mstore) mstore[q] = acc[c];
                 double ie = SRC >= 1 ? ierr_of(wgt[c]) : ierr[q];
                 double d = SRC == 2 ? dval[c] : val[q];
                 double ivar = ie * ie;
@@ -487,7 +491,8 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
                                         const double *wt, const double *im,
                                         const double *rowd,
                                         const double *cold,
-                                        double (&sums)[FD_NSUM]) {
+                                        double (&sums)[FD_NSUM],
+                                        const double *mbase) {
     const int T = blockDim.x;
     const int np = a.np;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -513,6 +518,16 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
 #pragma unroll
             for (int c = 0; c < CF; c++) mod[s][c] = 0.0;
             if (s > np) continue;
+            if (s == 0) {
+                // the base model is the last value pass's (the accepted
+                // point: lmdif calls fdjac2 with its fvec)
+#pragma unroll
+                for (int c = 0; c < CF; c++) {
+                    int q = q0 + 32 * c;
+                    if (q < a.nq) mod[0][c] = mbase[q];
+                }
+                continue;
+            }
             const double *recs = fdm + (size_t)s * a.ngauss * FDREC;
             for (int w = 0; w < nwords; w++) {
                 unsigned m = tiles_mask<CF>(tmask, q0 >> 5, ntile, nwords, w);
@@ -801,7 +816,8 @@ k_lm_fit(LMArgs a) {
     double *mix = smem_d;                                    // ngauss*REC
     double *fdm = mix + (size_t)a.ngauss * REC;              // nfd*ngauss*FDREC
     double *etab = fdm + (size_t)nfd * a.ngauss * FDREC;     // 16 (MODE 1)
-    double *val = etab + (nfd ? 16 : 0);                     // nq
+    double *mplane = etab + (nfd ? 16 : 0);                  // nq (MODE 1)
+    double *val = mplane + (nfd ? a.nq : 0);                 // nq
     double *ierr = val + a.nq;                               // nq (!WG)
     double *rowd = ierr + (WG ? 0 : a.nq);
     double *cold = rowd + a.nrow;
@@ -1080,8 +1096,8 @@ k_lm_fit(LMArgs a) {
                 double sums[4] = {0, 0, 0, 0};
                 if (!sh.status)
                     value_pass<CV, WG ? 1 : 0>(a, &sh, mix, tmask, val, ierr, wts,
-                                               nullptr, rowd,
-                                   cold, sums);
+                                               nullptr, rowd, cold, sums,
+                                               MODE == 1 ? mplane : nullptr);
                 block_sum_to<4>(sums, scratch, sh.tot);
                 PROF_T(pt_pass);
                 if (threadIdx.x == 0) {
@@ -1131,7 +1147,7 @@ k_lm_fit(LMArgs a) {
                 if (!bad_any)
                     fd_pass<LM_MAXP, WG ? 1 : 0>(a, &sh, hs, fdm, etab, tmask, val,
                                                  ierr, wts, nullptr,
-                                     rowd, cold, sums);
+                                     rowd, cold, sums, mplane);
                 {
                     double s1[32], s2[FD_NSUM - 32];
 #pragma unroll
@@ -1506,7 +1522,8 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     // shared memory without the ierr plane
     size_t smem = sizeof(double)
         * ((size_t)a.ngauss * REC + (size_t)nfd * a.ngauss * FDREC
-           + (nfd ? 16 : 0) + (size_t)a.nq + nrow + ncol + 48 * nwarps + 8
+           + (nfd ? 16 + (size_t)a.nq : 0) + (size_t)a.nq + nrow + ncol
+           + 48 * nwarps + 8
            + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
     // keep ierr = sqrt(w) in shared memory too when four CTAs (the register
     // limit) still fit on an SM; larger stamps leave the weights in L2
