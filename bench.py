@@ -39,6 +39,12 @@ FLOPS_VALUE, FLOPS_DERIV = 28.0, 74.0      # source flops (reference code)
 INSTR_VALUE, INSTR_DERIV = 16.0, 30.0      # fused fp64 instructions, ours
 
 
+# DRAM traffic of one k_lm_fit launch over NCU_LAUNCH_STAMPS stamps, from the
+# committed ncu capture (profiles/ncu_lm_fit_r1i.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = 371877120 + 42902272
+NCU_LAUNCH_STAMPS = 10000
+
+
 def make_inputs(nobj, seed0, dims=DIMS, noise=0.01):
     """config-2 stamps: parameters on the host (seeded per object), truth
     rendered by the engine itself (exact exp), gaussian noise added"""
@@ -406,7 +412,14 @@ def main():
             "kernel": "k_lm_fit", "kernel_ms": kernel_ms,
             "hbm_achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9,
             "hbm_frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one k_lm_fit
+            # launch of this workload (10 000 stamps per rank) from the
+            # ncu --set full capture in profiles/ncu_lm_fit_r1i.txt:
+            # 371.9 MB read + 42.9 MB written; algorithmic 384 MB + records
+            "traffic": (NCU_DRAM_BYTES_PER_LAUNCH
+                        if nobj == NCU_LAUNCH_STAMPS else None),
+            "traffic_source": "ncu capture profiles/ncu_lm_fit_r1i.txt "
+                              "(not measured in this run)",
         },
         "fdiff_kernel": {
             "kernel": "k_loglike_tiled (ngx_loglike: fill_fdiff + "
