@@ -150,3 +150,39 @@ def test_full_size_properties(ngx):
     assert np.allclose(r2["pars"][:, 2:5], res["pars"][sub, 2:5], rtol=1e-7,
                        atol=1e-10)
     assert np.array_equal(r2["nfev"], res["nfev"][sub])
+
+
+@pytest.mark.parametrize("noise,prior_kind", [(1.0, None), (1.0, "flat"),
+                                              (0.3, "erf")])
+def test_config2_low_s2n_and_priors(ngx, ora, noise, prior_kind):
+    """config 2's second pass: sigma = 1.0 (S/N 10-20, fits that take up to
+    ~40 evaluations) with and without the reference tests' prior sets; flags,
+    nfev and ier bit-exact, parameters to 1e-5"""
+    from ngmix_b200 import sims
+    n = 400
+    b = sims.make_lm_batch(n, seed0=123000, noise=noise)
+    pr = opr = None
+    if prior_kind:
+        opr = ora.make_prior(prior_kind)
+        pr = ngx.Prior()
+        pr.present, pr.g_kind = 1, 1
+        pr.cen1 = pr.cen2 = 0.0
+        pr.sigma1 = pr.sigma2 = 0.263
+        pr.g_sigma = 0.3
+        for name in ("T", "F"):
+            src = getattr(opr, name)
+            setattr(pr, name, ngx.Prior1D(src.kind, 0, src.a, src.b, src.c,
+                                          src.d))
+    res = ngx.lm_fit("exp", b["images"], b["weights"], b["jac"], b["psf"],
+                     b["guess"], prior=pr)
+    ref = ora.lm_fit_batch("exp", b["images"], b["weights"], b["jac"],
+                           b["psf"], b["guess"], prior=opr, nthreads=8)
+    assert np.array_equal(res["flags"], ref["flags"])
+    assert np.array_equal(res["nfev"], ref["nfev"])
+    assert np.array_equal(res["ier"], ref["ier"])
+    assert ref["nfev"].max() > 6 or noise < 1.0     # the slow fits are there
+    ok = ref["flags"] == 0
+    tol = np.maximum(PAR_TOL * np.abs(ref["pars"][:, :6]),
+                     1e-3 * ref["pars_err"][:, :6])
+    assert np.all(np.abs(res["pars"][:, :6] - ref["pars"][:, :6])[ok]
+                  <= tol[ok])
