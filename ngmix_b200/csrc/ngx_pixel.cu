@@ -299,38 +299,26 @@ __device__ __forceinline__ void value_chunk(const GaussV *gv, int ngauss,
 
 #define LL_C 4
 
-// SRC = 0: images/weights/jacobian (pixels built on the fly, ordered
-// compaction for fdiff); SRC = 1: pre-built ngx_pixel records.
-template <int SRC>
-__global__ void k_loglike(int ngauss, const ngx_gauss *__restrict__ gmix,
-                          const double *__restrict__ images,
-                          const double *__restrict__ weights,
-                          const ngx_jacobian *__restrict__ jac, int nrow,
-                          int ncol, int ignore_zero_weight,
-                          const ngx_pixel *__restrict__ pixels, int maxpix,
-                          const int32_t *__restrict__ npix_in,
-                          double *__restrict__ out4,
-                          double *__restrict__ fdiff,
-                          int32_t *__restrict__ status) {
+// Pre-built pixel records (GMix.fill_fdiff / get_loglike on obs.pixels):
+// every record takes part, fdiff[i] belongs to pixel i.
+__global__ void k_loglike_pixels(int ngauss,
+                                 const ngx_gauss *__restrict__ gmix,
+                                 const ngx_pixel *__restrict__ pixels,
+                                 int maxpix,
+                                 const int32_t *__restrict__ npix_in,
+                                 double *__restrict__ out4,
+                                 double *__restrict__ fdiff,
+                                 int32_t *__restrict__ status) {
     extern __shared__ double smem_d[];
     double *tab = smem_d;                       // 16
-    double *scratch = smem_d + 16;              // 4 * 32
-    GaussV *gv = (GaussV *)(scratch + 4 * 32);  // ngauss
+    double *scratch = smem_d + 16;              // 32 * nwarps + 32
+    GaussV *gv = (GaussV *)(scratch + 32 * 9);  // ngauss
     __shared__ int bad;
-    __shared__ int warp_counts[32];
-    __shared__ int running;
-    int obj = blockIdx.x;
-    int ntot = (SRC == 0) ? nrow * ncol : npix_in[obj];
-    int stride = (SRC == 0) ? nrow * ncol : maxpix;
-    ngx_jacobian j;
-    double area = 0.0;
-    if (SRC == 0) {
-        j = jac[obj];
-        area = j.scale * j.scale;
-    } else if (ntot > 0) {
-        area = pixels[(size_t)obj * stride].area;
-    }
-    if (threadIdx.x == 0) { bad = 0; running = 0; }
+    const int obj = blockIdx.x;
+    const int ntot = npix_in[obj];
+    const ngx_pixel *px0 = pixels + (size_t)obj * maxpix;
+    const double area = ntot > 0 ? px0[0].area : 0.0;
+    if (threadIdx.x == 0) bad = 0;
     load_exp_table(tab);
     __syncthreads();
     for (int k = threadIdx.x; k < ngauss; k += blockDim.x) {
@@ -347,70 +335,37 @@ __global__ void k_loglike(int ngauss, const ngx_gauss *__restrict__ gmix,
         return;
     }
     double sums[4] = {0.0, 0.0, 0.0, 0.0};   // chi2, s2n_numer, s2n_denom, n
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int nwarps = blockDim.x >> 5;
     for (int base = 0; base < ntot; base += blockDim.x * LL_C) {
         double v[LL_C], u[LL_C], acc[LL_C], val[LL_C], ierr[LL_C];
-        bool valid[LL_C];
 #pragma unroll
         for (int c = 0; c < LL_C; c++) {
             int p = base + c * blockDim.x + threadIdx.x;
             acc[c] = 0.0;
-            valid[c] = false;
-            v[c] = 1.0e300; u[c] = 1.0e300; val[c] = 0.0; ierr[c] = 0.0;
-            if (p < ntot) {
-                if (SRC == 0) {
-                    double ivar = weights[(size_t)obj * stride + p];
-                    valid[c] = !(ignore_zero_weight && ivar <= 0.0);
-                    if (valid[c]) {
-                        int row = p / ncol, col = p - row * ncol;
-                        pixel_vu(j, row, col, &v[c], &u[c]);
-                        val[c] = images[(size_t)obj * stride + p];
-                        if (ivar < 0.0) ivar = 0.0;
-                        ierr[c] = sqrt(ivar);
-                    }
-                } else {
-                    ngx_pixel px = pixels[(size_t)obj * stride + p];
-                    valid[c] = true;
-                    v[c] = px.v; u[c] = px.u; val[c] = px.val;
-                    ierr[c] = px.ierr;
-                }
-            }
+            // lanes past the end sit at the first pixel and are dropped below
+            ngx_pixel px = px0[p < ntot ? p : 0];
+            v[c] = px.v; u[c] = px.u; val[c] = px.val; ierr[c] = px.ierr;
         }
         value_chunk<LL_C>(gv, ngauss, tab, v, u, acc);
 #pragma unroll
         for (int c = 0; c < LL_C; c++) {
-            // ordered compaction of the fdiff output (uniform control flow)
-            unsigned bal = __ballot_sync(0xffffffffu, valid[c]);
-            if (lane == 0) warp_counts[warp] = __popc(bal);
-            __syncthreads();
-            int off = running;
-            for (int w = 0; w < warp; w++) off += warp_counts[w];
-            int pos = off + __popc(bal & ((1u << lane) - 1u));
-            if (valid[c]) {
+            int p = base + c * blockDim.x + threadIdx.x;
+            if (p < ntot) {
                 double ivar = ierr[c] * ierr[c];
                 double diff = acc[c] - val[c];
                 sums[0] += diff * diff * ivar;
                 sums[1] += val[c] * acc[c] * ivar;
                 sums[2] += acc[c] * acc[c] * ivar;
                 sums[3] += 1.0;
-                if (fdiff) fdiff[(size_t)obj * stride + pos] = diff * ierr[c];
+                if (fdiff) fdiff[(size_t)obj * maxpix + p] = diff * ierr[c];
             }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int tot = 0;
-                for (int w = 0; w < nwarps; w++) tot += warp_counts[w];
-                running += tot;
-            }
-            __syncthreads();
         }
     }
-    block_sum<4>(sums, scratch);
+    block_sum_to<4>(sums, scratch + 32, scratch);
     if (threadIdx.x == 0) {
-        out4[4 * (size_t)obj + 0] = -0.5 * sums[0];
-        out4[4 * (size_t)obj + 1] = sums[1];
-        out4[4 * (size_t)obj + 2] = sums[2];
-        out4[4 * (size_t)obj + 3] = sums[3];
+        out4[4 * (size_t)obj + 0] = -0.5 * scratch[0];
+        out4[4 * (size_t)obj + 1] = scratch[1];
+        out4[4 * (size_t)obj + 2] = scratch[2];
+        out4[4 * (size_t)obj + 3] = scratch[3];
         if (status) status[obj] = NGX_ST_OK;
     }
 }
@@ -897,7 +852,7 @@ static int launch_loglike(int src, int n, int ngauss, const ngx_gauss *gmix,
                           int ignore_zero_weight, const ngx_pixel *pixels,
                           int maxpix, const int32_t *npix, double *out4,
                           double *fdiff, int32_t *status, void *stream) {
-    size_t smem = (16 + 4 * 32) * sizeof(double)
+    size_t smem = (16 + 32 * 9) * sizeof(double)
         + (size_t)ngauss * sizeof(GaussV);
     NGX_REQUIRE(smem <= 48 * 1024);
     int ntot = src == 0 ? nrow * ncol : maxpix;
@@ -920,9 +875,8 @@ static int launch_loglike(int src, int n, int ngauss, const ngx_gauss *gmix,
             ngauss, gmix, images, weights, jac, nrow, ncol, tpr, nq,
             ignore_zero_weight, out4, fdiff, status);
     } else
-        k_loglike<1><<<n, threads, smem, as_stream(stream)>>>(
-            ngauss, gmix, nullptr, nullptr, nullptr, 0, 0, 0, pixels, maxpix,
-            npix, out4, fdiff, status);
+        k_loglike_pixels<<<n, threads, smem, as_stream(stream)>>>(
+            ngauss, gmix, pixels, maxpix, npix, out4, fdiff, status);
     NGX_LAUNCH_CHECK();
     return NGX_OK;
 }
