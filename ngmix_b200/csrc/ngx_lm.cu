@@ -733,13 +733,17 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
 // ---------------------------------------------------------------------
 // assemble J^T J, J^T f from the pixel sums and the prior rows and feed the
 // state machine (thread 0).  packed = lower triangle row by row, then b.
+// pre: A and b already hold the pixel sums (assemble_normal_eq, run by the
+// whole CTA); only the prior rows are added here.
 __device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
                                            const double *sums, int status,
-                                           int analytic, const double *hs) {
+                                           int analytic, const double *hs,
+                                           int pre = 0) {
     double *A = sh->st.A, *b = sh->st.b;
     const int np = a.np;
     const double *x = sh->st.x;
     int nr = prior_nrows(a.model, a.prior);
+    const int status_in = status;
     double *f0 = sh->st.v[7];
     double *jp = sh->st.T1;
     if (!status && nr > 0) {
@@ -763,25 +767,48 @@ __device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
             }
         }
     }
-    int q = 0;
-    for (int aa = 0; aa < np; aa++)
-        for (int bb = 0; bb <= aa; bb++) {
-            double sv = status ? 0.0 : sums[q];
+    // with the sums in place and nothing to add (no prior, or a status that
+    // was already known when they were placed) the assembly is done
+    if (!(pre && status == status_in && (nr == 0 || status))) {
+        int q = 0;
+        for (int aa = 0; aa < np; aa++)
+            for (int bb = 0; bb <= aa; bb++) {
+                double sv = status ? 0.0 : sums[q];
+                if (!status)
+                    for (int r = 0; r < nr; r++)
+                        sv += jp[r * np + aa] * jp[r * np + bb];
+                A[aa + LM_MAXP * bb] = sv;
+                A[bb + LM_MAXP * aa] = sv;
+                q++;
+            }
+        for (int aa = 0; aa < np; aa++) {
+            double sv = status ? 0.0 : sums[q + aa];
             if (!status)
                 for (int r = 0; r < nr; r++)
-                    sv += jp[r * np + aa] * jp[r * np + bb];
-            A[aa + LM_MAXP * bb] = sv;
-            A[bb + LM_MAXP * aa] = sv;
-            q++;
+                    if (isfinite(f0[r])) sv += jp[r * np + aa] * f0[r];
+            b[aa] = sv;
         }
-    for (int aa = 0; aa < np; aa++) {
-        double sv = status ? 0.0 : sums[q + aa];
-        if (!status)
-            for (int r = 0; r < nr; r++)
-                if (isfinite(f0[r])) sv += jp[r * np + aa] * f0[r];
-        b[aa] = sv;
     }
     lm_feed_j(&sh->st, A, b, analytic ? 0 : np);
+}
+
+// J^T J (symmetric, ld LM_MAXP) and J^T f of a six-parameter fit from the
+// packed block totals, one entry per thread; zeros when the Jacobian is
+// undefined.  The solver thread then only adds the prior rows.
+__device__ __forceinline__ void assemble_normal_eq(LMShared *sh,
+                                                   const double *tot,
+                                                   int jstatus) {
+    const int t = threadIdx.x;
+    if (t < 21) {
+        const int aa = t >= 15 ? 5 : t >= 10 ? 4 : t >= 6 ? 3 : t >= 3 ? 2
+            : t >= 1 ? 1 : 0;
+        const int bb = t - aa * (aa + 1) / 2;
+        const double sv = jstatus ? 0.0 : tot[t];
+        sh->st.A[aa + LM_MAXP * bb] = sv;
+        sh->st.A[bb + LM_MAXP * aa] = sv;
+    } else if (t < 27) {
+        sh->st.b[t - 21] = jstatus ? 0.0 : tot[t];
+    }
 }
 
 // feed |f| of a residual pass (thread 0); returns 1 if the point is adopted
@@ -1068,6 +1095,11 @@ k_lm_fit(LMArgs a) {
                                                nullptr, rowd,
                                    cold, sums);
                 block_sum_to<NDSUM>(sums, scratch, sh.tot);
+                // J^T J of the previous Jacobian is dead by now (its
+                // factor R is what the solver keeps), so the new sums can
+                // go in place before the step is known to be accepted
+                assemble_normal_eq(&sh, sh.tot, jstatus);
+                __syncthreads();
                 PROF_T(pt_pass);
                 if (threadIdx.x == 0) {
                     const double *tot = sh.tot;
@@ -1080,11 +1112,11 @@ k_lm_fit(LMArgs a) {
                             sh.cur_den = tot[29];
                             sh.cur_rfirst2 = tot[30];
                             if (sh.st.action == LM_ACT_EVAL_J)
-                                feed_jacobian(a, &sh, tot, jstatus, 1, hs);
+                                feed_jacobian(a, &sh, tot, jstatus, 1, hs, 1);
                         }
                         sh.spec = acc;
                     } else {
-                        feed_jacobian(a, &sh, tot, jstatus, 1, hs);
+                        feed_jacobian(a, &sh, tot, jstatus, 1, hs, 1);
                     }
                 }
             } else if (action == LM_ACT_EVAL_F) {
