@@ -128,9 +128,10 @@ __device__ __forceinline__ double apod_window_x(double x) {
 }
 // the same window with fused multiply-adds (hot loops; within an ulp or two
 // of apod_window_x)
+__constant__ double c_apod[5] = {0.4, 5.0, 6.0, -15.0, 10.0};
 __device__ __forceinline__ double apod_window_fast(double x) {
-    double u = fma(0.4, x, 5.0);
-    double t = fma(fma(6.0, u, -15.0), u, 10.0);
+    double u = fma(c_apod[0], x, c_apod[1]);
+    double t = fma(fma(c_apod[2], u, c_apod[3]), u, c_apod[4]);
     return (u * u) * (u * t);
 }
 // apod_window_deriv (fastexp_nb.py:120-135)

@@ -285,10 +285,8 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
                     // some lane of some pixel sits in the apodization band
 #pragma unroll
                     for (int c = 0; c < CV; c++) {
-                        if (__any_sync(0xffffffffu, ap[c])) {
-                            double w = apod_window_fast(x[c]);
-                            if (ap[c]) e[c] *= w;
-                        }
+                        double w = apod_window_fast(x[c]);
+                        if (ap[c]) e[c] *= w;
                     }
                 }
 #pragma unroll

@@ -186,6 +186,54 @@ def test_render_vs_oracle_random(ngx, ora):
                 assert np.abs(im[i] - oim).max() / sc < IMG_TOL
 
 
+@pytest.mark.parametrize("dims", [(48, 48), (31, 47), (5, 3), (64, 64)])
+@pytest.mark.parametrize("mask", ["none", "some", "negative_kept"])
+def test_loglike_fdiff_vs_oracle_masks(ngx, ora, dims, mask):
+    """fdiff order and values with no masked pixels (direct row-major
+    positions), with several masked pixels (compaction tables) and with
+    ignore_zero_weight=False, on stamp sizes with padding tiles"""
+    rng = np.random.RandomState(5 + dims[0])
+    n = 4
+    pars = np.zeros((n, 6))
+    pars[:, 0:2] = rng.uniform(-0.3, 0.3, (n, 2))
+    pars[:, 2:4] = rng.uniform(-0.3, 0.3, (n, 2))
+    pars[:, 4] = rng.uniform(0.2, 2.0, n)
+    pars[:, 5] = rng.uniform(10, 100, n)
+    jac = np.zeros((n, 8))
+    for i in range(n):
+        jac[i] = [(dims[0] - 1) / 2 + rng.uniform(-0.5, 0.5),
+                  (dims[1] - 1) / 2 + rng.uniform(-0.5, 0.5),
+                  0.263, 0.0, 0.0, 0.263, 0.263 ** 2, 0.263]
+    gm, _ = ngx.gmix_fill("exp", pars)
+    ngx.gmix_set_norms(gm)
+    images = rng.normal(0.0, 0.1, (n,) + dims)
+    weights = np.full((n,) + dims, 100.0)
+    izw = True
+    if mask != "none":
+        nbad = max(1, dims[0] * dims[1] // 7)
+        for i in range(n):
+            idx = rng.choice(dims[0] * dims[1], nbad, replace=False)
+            weights[i].reshape(-1)[idx] = 0.0
+            weights[i].reshape(-1)[idx[: nbad // 2]] = -1.0
+        izw = mask == "some"
+    out4, fdiff, st = ngx.loglike(gm, images, weights, jac,
+                                  ignore_zero_weight=izw, want_fdiff=True)
+    assert not st.any()
+    for i in range(n):
+        og, _ = ora.gmix_fill("exp", pars[i])
+        ora.gmix_set_norms(og)
+        pix = ora.make_pixels(images[i], weights[i], jac[i],
+                              ignore_zero_weight=izw)
+        want = np.zeros(pix.size)
+        ora.fill_fdiff(og, pix, want)
+        o4, _ = ora.get_loglike(og, pix)
+        assert out4[i][3] == pix.size == o4[3]
+        assert relerr(out4[i][:3], o4[:3]) < IMG_TOL
+        assert np.abs(fdiff[i][:pix.size] - want).max() \
+            / np.abs(want).max() < IMG_TOL
+        assert not fdiff[i][pix.size:].any()
+
+
 # ------------------------------------------------------------------ LM
 def _prior(ngx, kind):
     pr = ngx.Prior()
