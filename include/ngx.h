@@ -187,6 +187,7 @@ typedef struct {
     int32_t nband;        /* 0 or 1: single band; 2, 3: ngx_lm_fit_multi */
     int32_t pad;
     ngx_prior1d F_more[2];    /* flux priors of bands 1 and 2 */
+    ngx_prior1d logTratio;    /* bd only: PriorBDSep, joint_prior.py:267-399 */
 } ngx_prior;
 
 /* DEFAULT_LM_PARS, ngmix/defaults.py:17 */

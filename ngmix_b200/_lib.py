@@ -68,7 +68,7 @@ class Prior(C.Structure):
                 ("g_sigma", C.c_double), ("T", Prior1D),
                 ("fracdev", Prior1D), ("F", Prior1D),
                 ("nband", C.c_int32), ("pad", C.c_int32),
-                ("F_more", Prior1D * 2)]
+                ("F_more", Prior1D * 2), ("logTratio", Prior1D)]
 
 
 class LMPars(C.Structure):

@@ -536,24 +536,31 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
                     const double2 *g2 =
                         (const double2 *)(recs + FDREC * k);
                     const double2 rc = g2[0], ab = g2[1], cp = g2[2];
+                    double x[CF], e[CF];
+                    bool ap[CF], anyap = false;
 #pragma unroll
                     for (int c = 0; c < CF; c++) {
                         double dv = v[c] - rc.x;
                         double du = u[c] - rc.y;
                         double t = fma(cp.x, du, ab.x * dv);
-                        double x = fma(ab.y * du, du, dv * t);
+                        x[c] = fma(ab.y * du, du, dv * t);
                         unsigned slot;
-                        bool inr, ap;
-                        double f = fexp_split(x, &slot, &inr, &ap);
+                        bool inr;
+                        double f = fexp_split(x[c], &slot, &inr, &ap[c]);
                         // (exp(i) pn) P(f): the product the per-gaussian
                         // tables of the other passes hold precomputed
-                        double e = (etab[slot] * cp.y) * fexp_poly_c(f);
-                        if (__any_sync(0xffffffffu, ap)) {
-                            double wv = apod_window_x(x);
-                            if (ap) e *= wv;
-                        }
-                        mod[s][c] += e;
+                        e[c] = (etab[slot] * cp.y) * fexp_poly_c(f);
+                        anyap |= ap[c];
                     }
+                    if (__any_sync(0xffffffffu, anyap)) {
+#pragma unroll
+                        for (int c = 0; c < CF; c++) {
+                            double wv = apod_window_x(x[c]);
+                            if (ap[c]) e[c] *= wv;
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < CF; c++) mod[s][c] += e[c];
                 }
             }
         }
@@ -1533,7 +1540,6 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     NGX_REQUIRE(a.ngauss <= NGX_MAX_GAUSS);
     if (a.prior.present) {
         NGX_REQUIRE(a.prior.g_kind == 1);
-        NGX_REQUIRE(model != NGX_BD);   // PriorBDSep rows not built yet
     }
     int rc = get_counter(&a.counter);
     if (rc) return rc;

@@ -2,6 +2,7 @@
 // Jacobian, evaluated by one thread per object:
 //   PriorSimpleSep.fill_fdiff      ngmix/joint_prior.py:86-120
 //   PriorBDFSep.fill_fdiff         ngmix/joint_prior.py:565-599
+//   PriorBDSep.fill_fdiff          ngmix/joint_prior.py:364-399
 //   get_lnprob_scalar              ngmix/joint_prior.py:136-150, 543-563
 //   FitModel._fill_prior_jacobian  ngmix/fitting/results.py:572-625
 // over CenPrior (priors/multivariate.py:48-71), GPriorBA (priors/shape.py:
@@ -91,16 +92,33 @@ __host__ __device__ inline int prior_nslots(int model, const ngx_prior &pr) {
 __host__ __device__ inline int prior_nrows(int model, const ngx_prior &pr) {
     if (!pr.present) return 0;
     if (model == NGX_BDF) return 6;
+    if (model == NGX_BD) return 7;
     return 4 + prior_nband(pr);
 }
 
 // one row of prior.fill_fdiff; row index in the reference's order.
 // simple: 0 cen1, 1 cen2, 2 g, 3 T, 4.. F per band   (sqrt(clip(-2 lnp)))
 // bdf   : 0 cen1, 1 cen2, 2 g, 3 T, 4 fracdev, 5 F   (signed get_fdiff)
+// bd    : 0 cen1, 1 cen2, 2 g, 3 T, 4 logTratio, 5 fracdev, 6 F  (signed)
 __device__ __noinline__ int prior_row(int model, const ngx_prior &pr,
                                 const double *p, int row, double *out) {
     double lnp;
     int st;
+    if (model == NGX_BD) {
+        switch (row) {
+        case 0: *out = (p[0] - pr.cen1) * (1.0 / pr.sigma1); return 0;
+        case 1: *out = (p[1] - pr.cen2) * (1.0 / pr.sigma2); return 0;
+        case 2:
+            st = gprior_lnprob(pr, p[2], p[3], &lnp);
+            if (st) return st;
+            *out = clip_sqrt(lnp);
+            return 0;
+        case 3: return prior1d_fdiff(pr.T, p[4], out);
+        case 4: return prior1d_fdiff(pr.logTratio, p[5], out);
+        case 5: return prior1d_fdiff(pr.fracdev, p[6], out);
+        default: return prior1d_fdiff(pr.F, p[7], out);
+        }
+    }
     if (model == NGX_BDF) {
         switch (row) {
         case 0: *out = (p[0] - pr.cen1) * (1.0 / pr.sigma1); return 0;
@@ -146,8 +164,9 @@ __device__ __noinline__ int prior_row(int model, const ngx_prior &pr,
 __device__ inline int prior_row_of_par(int model, int ipar) {
     if (ipar < 2) return ipar;
     if (ipar < 4) return 2;
-    if (model == NGX_BDF) return ipar - 1;      // 4->3 (T), 5->4, 6->5
-    return ipar - 1;                            // 4->3 (T), 5->4 (F)
+    // bdf: 4->3 (T), 5->4, 6->5; bd: 4->3, 5->4, 6->5, 7->6; simple: 4->3 (T),
+    // 5.. -> 4.. (F per band)
+    return ipar - 1;
 }
 
 // all rows; returns NGX_ST_*
@@ -176,6 +195,13 @@ __device__ __noinline__ int prior_lnprob(int model, const ngx_prior &pr,
     if (prior1d_lnprob(pr.T, p[4], &t)) return NGX_ST_RANGE_ERROR;
     lnp += t;
     int fi = 5;
+    if (model == NGX_BD) {
+        if (prior1d_lnprob(pr.logTratio, p[5], &t)) return NGX_ST_RANGE_ERROR;
+        lnp += t;
+        if (prior1d_lnprob(pr.fracdev, p[6], &t)) return NGX_ST_RANGE_ERROR;
+        lnp += t;
+        fi = 7;
+    }
     if (model == NGX_BDF) {
         if (prior1d_lnprob(pr.fracdev, p[5], &t)) return NGX_ST_RANGE_ERROR;
         lnp += t;

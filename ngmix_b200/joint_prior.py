@@ -1,2 +1,2 @@
 """joint priors under the reference's module name (ngmix/joint_prior.py)"""
-from .priors import PriorSimpleSep, PriorBDFSep  # noqa: F401
+from .priors import PriorSimpleSep, PriorBDFSep, PriorBDSep  # noqa: F401

@@ -256,3 +256,44 @@ class PriorBDFSep(PriorSimpleSep):
         pr = super().to_ngx()
         pr.fracdev = self.fracdev_prior._ngx()
         return pr
+
+
+class PriorBDSep(PriorSimpleSep):
+    """separate priors for the bd model, pars [cen1, cen2, g1, g2, T,
+    logTratio, fracdev, F] (joint_prior.py:267-481)"""
+
+    def __init__(self, cen_prior, g_prior, T_prior, logTratio_prior,
+                 fracdev_prior, F_prior):
+        self.logTratio_prior = logTratio_prior
+        self.fracdev_prior = fracdev_prior
+        super().__init__(cen_prior, g_prior, T_prior, F_prior)
+        if logTratio_prior.has_bounds() or fracdev_prior.has_bounds():
+            raise NotImplementedError("bounded fits are not in scope")
+
+    def get_lnprob_scalar(self, pars):
+        lnp = self.cen_prior.get_lnprob_scalar(pars[0], pars[1])
+        lnp += self.g_prior.get_lnprob_scalar2d(pars[2], pars[3])
+        lnp += self.T_prior.get_lnprob_scalar(pars[4])
+        lnp += self.logTratio_prior.get_lnprob_scalar(pars[5])
+        lnp += self.fracdev_prior.get_lnprob_scalar(pars[6])
+        for i, F_prior in enumerate(self.F_priors):
+            lnp += F_prior.get_lnprob_scalar(pars[7 + i])
+        return lnp
+
+    def fill_fdiff(self, pars, fdiff):
+        f1, f2 = self.cen_prior.get_fdiff(pars[0], pars[1])
+        rows = [f1, f2, self.g_prior.get_fdiff(pars[2], pars[3]),
+                self.T_prior.get_fdiff(pars[4]),
+                self.logTratio_prior.get_fdiff(pars[5]),
+                self.fracdev_prior.get_fdiff(pars[6])]
+        rows += [F.get_fdiff(pars[7 + i]) for i, F in enumerate(self.F_priors)]
+        fdiff[0:len(rows)] = rows
+        return len(rows)
+
+    def to_ngx(self):
+        if self.nband != 1:
+            raise NotImplementedError("bd fits are single band")
+        pr = super().to_ngx()
+        pr.logTratio = self.logTratio_prior._ngx()
+        pr.fracdev = self.fracdev_prior._ngx()
+        return pr

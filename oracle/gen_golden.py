@@ -608,6 +608,61 @@ def gen_lm_bdf():
     save("lm_bdf", **out)
 
 
+def gen_lm_bd():
+    """bd model (8 parameters, lmdif) with and without PriorBDSep"""
+    from ngmix import priors, joint_prior
+    from ngmix.fitting import Fitter
+    b = sims.make_bdf_batch(6, seed0=9100, dims=(40, 40), noise=0.02)
+    n = b["images"].shape[0]
+    rng = np.random.RandomState(8)
+    guess = np.zeros((n, 8))
+    guess[:, :5] = b["guess"][:, :5]
+    guess[:, 5] = rng.uniform(-0.2, 0.2, n)          # log10(Td/Te)
+    guess[:, 6:] = b["guess"][:, 5:]
+    prior = joint_prior.PriorBDSep(
+        cen_prior=priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng),
+        g_prior=priors.GPriorBA(0.3, rng=rng),
+        T_prior=priors.FlatPrior(-1.0, 1.0e3, rng=rng),
+        logTratio_prior=priors.Normal(0.0, 0.5, rng=rng),
+        fracdev_prior=priors.Normal(0.5, 0.1, rng=rng),
+        F_prior=priors.FlatPrior(-100.0, 1.0e9, rng=rng))
+    out = {k: b[k] for k in ("images", "weights", "jac", "psf")}
+    out["guess"] = guess
+    for pk, pr in (("none", None), ("bd", prior)):
+        res = dict(flags=np.zeros(n, "i4"), nfev=np.zeros(n, "i4"),
+                   ier=np.zeros(n, "i4"), pars=np.zeros((n, 8)),
+                   pars_err=np.zeros((n, 8)), pars_cov=np.zeros((n, 8, 8)),
+                   lnprob=np.zeros(n), s2n=np.zeros(n), chi2per=np.zeros(n),
+                   dof=np.zeros(n, "i4"))
+        fitter = Fitter(model="bd", prior=pr)
+        for i in range(n):
+            psf_obs = ngmix.Observation(
+                np.ones((5, 5)),
+                jacobian=ngmix.DiagonalJacobian(row=2, col=2, scale=0.263),
+                gmix=ngmix.GMix(pars=b["psf"][i].ravel()))
+            obs = ngmix.Observation(b["images"][i], weight=b["weights"][i],
+                                    jacobian=jac_from_record(b["jac"][i]),
+                                    psf=psf_obs)
+            r = fitter.go(obs, guess[i].copy())
+            res["flags"][i] = r["flags"]
+            res["nfev"][i] = r["nfev"]
+            res["ier"][i] = r["ier"]
+            res["pars"][i] = r["pars"]
+            if "pars_err" in r:
+                res["pars_err"][i] = r["pars_err"]
+                res["pars_cov"][i] = r["pars_cov"]
+            if r["flags"] == 0:
+                res["lnprob"][i] = r["lnprob"]
+                res["s2n"][i] = r["s2n"]
+                res["chi2per"][i] = r["chi2per"]
+                res["dof"][i] = r["dof"]
+        print("bd", pk, "flags", res["flags"], "nfev", res["nfev"], "ier",
+              res["ier"])
+        for k, v in res.items():
+            out["%s_%s" % (pk, k)] = v
+    save("lm_bd", **out)
+
+
 def gen_moments():
     """GaussMom (6 and 17 moments) on galaxy stamps, and get_weighted_sums
     with a two-gaussian off-centre weight and a maxrad"""
@@ -906,6 +961,7 @@ GENERATORS = {
     "lm_other": gen_lm_other,
     "em_admom": gen_em_admom,
     "lm_bdf": gen_lm_bdf,
+    "lm_bd": gen_lm_bd,
     "moments": gen_moments,
     "lm_multi": gen_lm_multi,
     "psfflux": gen_psfflux,

@@ -102,6 +102,27 @@ static int prior_fill_fdiff(int model, const ora_prior *pr, const double *pars,
                             double *fdiff) {
     if (!pr || !pr->present) return 0;
     int index = 0;
+    if (model == ORA_BD) {
+        /* PriorBDSep.fill_fdiff, joint_prior.py:364-399, signed rows */
+        double sinv1 = 1.0 / pr->sigma1, sinv2 = 1.0 / pr->sigma2;
+        fdiff[index++] = (pars[0] - pr->cen1) * sinv1;
+        fdiff[index++] = (pars[1] - pr->cen2) * sinv2;
+        double lnp;
+        if (gprior_lnprob(pr, pars[2], pars[3], &lnp)) return -1;
+        double c = -2 * lnp;
+        if (c < 0.0) c = 0.0;
+        fdiff[index++] = sqrt(c);
+        double fd;
+        if (prior1d_fdiff(&pr->T, pars[4], &fd)) return -1;
+        fdiff[index++] = fd;
+        if (prior1d_fdiff(&pr->logTratio, pars[5], &fd)) return -1;
+        fdiff[index++] = fd;
+        if (prior1d_fdiff(&pr->fracdev, pars[6], &fd)) return -1;
+        fdiff[index++] = fd;
+        if (prior1d_fdiff(&pr->F, pars[7], &fd)) return -1;
+        fdiff[index++] = fd;
+        return index;
+    }
     if (model == ORA_BDF) {
         /* joint_prior.py:565-599, signed rows */
         double sinv1 = 1.0 / pr->sigma1, sinv2 = 1.0 / pr->sigma2;
@@ -158,6 +179,14 @@ static int prior_lnprob(int model, const ora_prior *pr, const double *pars,
     if (prior1d_lnprob(&pr->T, pars[4], &t)) return ORA_RANGE_ERROR;
     lnp += t;
     int fi = 5;
+    if (model == ORA_BD) {
+        /* PriorBDSep.get_lnprob_scalar, joint_prior.py:343-362 */
+        if (prior1d_lnprob(&pr->logTratio, pars[5], &t)) return ORA_RANGE_ERROR;
+        lnp += t;
+        if (prior1d_lnprob(&pr->fracdev, pars[6], &t)) return ORA_RANGE_ERROR;
+        lnp += t;
+        fi = 7;
+    }
     if (model == ORA_BDF) {
         if (prior1d_lnprob(&pr->fracdev, pars[5], &t)) return ORA_RANGE_ERROR;
         lnp += t;

@@ -105,8 +105,9 @@ typedef struct {
     double cen1, cen2, sigma1, sigma2;
     double g_sigma;
     ora_prior1d T;
-    ora_prior1d fracdev;   /* bdf only */
+    ora_prior1d fracdev;   /* bdf, bd */
     ora_prior1d F;
+    ora_prior1d logTratio; /* bd only */
 } ora_prior;
 
 /* ---- LM fit = Fitter.go (fitting/fitters.py:64-112) ---- */

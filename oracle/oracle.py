@@ -42,7 +42,8 @@ class Prior(C.Structure):
                 ("cen1", C.c_double), ("cen2", C.c_double),
                 ("sigma1", C.c_double), ("sigma2", C.c_double),
                 ("g_sigma", C.c_double), ("T", Prior1D),
-                ("fracdev", Prior1D), ("F", Prior1D)]
+                ("fracdev", Prior1D), ("F", Prior1D),
+                ("logTratio", Prior1D)]
 
 
 class LMResult(C.Structure):
@@ -258,6 +259,11 @@ def make_prior(kind, model="exp"):
         pr.F = Prior1D(2, 0, -1.0e2, 1.0, 1.0e9, 1.0e8)
     elif kind == "bdf":
         pr.T = Prior1D(1, 0, -1.0, 1.0e3, 0, 0)
+        pr.fracdev = Prior1D(3, 0, 0.5, 0.1, 0, 0)
+        pr.F = Prior1D(1, 0, -100.0, 1.0e9, 0, 0)
+    elif kind == "bd":
+        pr.T = Prior1D(1, 0, -1.0, 1.0e3, 0, 0)
+        pr.logTratio = Prior1D(3, 0, 0.0, 0.5, 0, 0)
         pr.fracdev = Prior1D(3, 0, 0.5, 0.1, 0, 0)
         pr.F = Prior1D(1, 0, -100.0, 1.0e9, 0, 0)
     else:

@@ -202,6 +202,36 @@ def test_fitter_with_prior_and_determinism(ng):
         assert np.array_equal(r1["pars_cov"], r2["pars_cov"])
 
 
+def test_fitter_bd_with_joint_prior(ng):
+    """Fitter(model='bd', prior=PriorBDSep(...)) against the reference"""
+    g = load_golden("lm_bd")
+    pr = ng.priors
+    prior = ng.joint_prior.PriorBDSep(
+        pr.CenPrior(0.0, 0.0, 0.263, 0.263), pr.GPriorBA(0.3),
+        pr.FlatPrior(-1.0, 1.0e3), pr.Normal(0.0, 0.5), pr.Normal(0.5, 0.1),
+        pr.FlatPrior(-100.0, 1.0e9))
+    fitter = ng.Fitter(model="bd", prior=prior)
+    for i in range(2):
+        rec = g["jac"][i]
+        jac = ng.Jacobian(row=rec[0], col=rec[1], dvdrow=rec[2],
+                          dvdcol=rec[3], dudrow=rec[4], dudcol=rec[5])
+        psf_obs = ng.Observation(np.ones((5, 5)),
+                                 gmix=ng.GMix(pars=g["psf"][i].ravel()))
+        obs = ng.Observation(g["images"][i], weight=g["weights"][i],
+                             jacobian=jac, psf=psf_obs)
+        r = fitter.go(obs, g["guess"][i])
+        assert r["flags"] == g["bd_flags"][i]
+        assert r["nfev"] == g["bd_nfev"][i]
+        err = g["bd_pars_err"][i]
+        assert np.all(np.abs(r["pars"] - g["bd_pars"][i])
+                      <= np.maximum(1e-5 * np.abs(g["bd_pars"][i]),
+                                    1e-2 * err))
+        assert abs(r["lnprob"] / g["bd_lnprob"][i] - 1) < 1e-6
+        # the prior object's own rows equal what the kernel used
+        fd = np.zeros(8)
+        assert prior.fill_fdiff(r["pars"], fd) == 7
+
+
 def test_em_appendix_b(ng):
     jac = ng.DiagonalJacobian(row=12, col=12, scale=0.263)
     truth = ng.GMix(pars=[60, -0.3, 0.2, 0.12, 0.01, 0.15,

@@ -253,6 +253,11 @@ def _prior(ngx, kind):
         pr.T = ngx.Prior1D(1, 0, -1.0, 1.0e3, 0, 0)
         pr.fracdev = ngx.Prior1D(3, 0, 0.5, 0.1, 0, 0)
         pr.F = ngx.Prior1D(1, 0, -100.0, 1.0e9, 0, 0)
+    elif kind == "bd":
+        pr.T = ngx.Prior1D(1, 0, -1.0, 1.0e3, 0, 0)
+        pr.logTratio = ngx.Prior1D(3, 0, 0.0, 0.5, 0, 0)
+        pr.fracdev = ngx.Prior1D(3, 0, 0.5, 0.1, 0, 0)
+        pr.F = ngx.Prior1D(1, 0, -100.0, 1.0e9, 0, 0)
     return pr
 
 
@@ -319,6 +324,24 @@ def test_lm_bdf_golden(ngx):
         err = g["res_pars_err"][i]
         tol = np.maximum(PAR_TOL * np.abs(ref), 1e-2 * err)
         assert np.all(np.abs(res["pars"][i][:7] - ref) <= tol), i
+
+
+@pytest.mark.parametrize("pk", ["none", "bd"])
+def test_lm_bd_golden(ngx, pk):
+    """bd model (8 parameters, forward differences), PriorBDSep rows"""
+    g = load_golden("lm_bd")
+    res = ngx.lm_fit("bd", g["images"], g["weights"], g["jac"], g["psf"],
+                     g["guess"], prior=_prior(ngx, pk))
+    assert np.array_equal(res["flags"], g[pk + "_flags"])
+    assert np.array_equal(res["nfev"], g[pk + "_nfev"])
+    assert np.array_equal(res["ier"], g[pk + "_ier"])
+    for i in range(res.size):
+        ref = g[pk + "_pars"][i]
+        err = g[pk + "_pars_err"][i]
+        tol = np.maximum(PAR_TOL * np.abs(ref), 1e-2 * err)
+        assert np.all(np.abs(res["pars"][i][:8] - ref) <= tol), i
+        assert relerr(res["lnprob"][i], g[pk + "_lnprob"][i]) < 1e-6
+        assert res["dof"][i] == g[pk + "_dof"][i]
 
 
 def test_lm_vs_oracle_batch(ngx, ora):

@@ -242,6 +242,25 @@ def test_lm_bdf(ora):
         assert relerr(r["lnprob"], g["res_lnprob"][i]) < 1e-8
 
 
+@pytest.mark.parametrize("pk", ["none", "bd"])
+def test_lm_bd(ora, pk):
+    """bd model (8 parameters, lmdif), without prior and with PriorBDSep"""
+    g = load_golden("lm_bd")
+    prior = ora.make_prior(pk)
+    n = g["images"].shape[0]
+    for i in range(n):
+        r = ora.lm_fit("bd", g["images"][i], g["weights"][i], g["jac"][i],
+                       g["psf"][i], g["guess"][i], prior=prior)
+        assert r["flags"] == g[pk + "_flags"][i]
+        assert r["ier"] == g[pk + "_ier"][i]
+        assert r["nfev"] == g[pk + "_nfev"][i]
+        err = g[pk + "_pars_err"][i]
+        assert np.all(np.abs(r["pars"][:8] - g[pk + "_pars"][i])
+                      <= 1e-5 * err + 1e-8 * np.abs(g[pk + "_pars"][i]))
+        assert relerr(r["lnprob"], g[pk + "_lnprob"][i]) < 1e-7
+        assert r["dof"] == g[pk + "_dof"][i]
+
+
 # ------------------------------------------------------------------ EM
 def test_em(ora):
     g = load_golden("em_admom")
