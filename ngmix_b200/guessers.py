@@ -5,14 +5,16 @@ caller's RandomState in the reference's order, so a pipeline seeded the same
 way starts its fits from the same points.  The psf fluxes behind
 TPSFFluxGuesser come from the device (ngx_template_flux).
 
-Built: TFluxGuesser, TPSFFluxGuesser, ParsGuesser (without prior),
-GMixPSFGuesser, SimplePSFGuesser.  The *AndPrior guessers need the priors'
-sampling code, which is not part of this engine.
+Built: TFluxGuesser, TPSFFluxGuesser, ParsGuesser (each with the optional
+prior fix-up), TFluxAndPriorGuesser, TPSFFluxAndPriorGuesser, BDFGuesser,
+BDFPSFFluxGuesser, BDGuesser, PriorGuesser, GMixPSFGuesser, SimplePSFGuesser.
+Not built: the galsim-model guessers (R50*) and CoellipPSFGuesser.
 """
 import numpy as np
 
 from . import moments
-from .gexceptions import PSFFluxFailure
+from .defaults import LOWVAL
+from .gexceptions import GMixRangeError, PSFFluxFailure
 from .gmix import GMix, GMixModel
 from .observation import get_mb_obs
 
@@ -32,11 +34,32 @@ def _fluxes(rng, fluxes, nrand, guess):
         guess[:, 5 + band] = flux * rng.uniform(low=0.9, high=1.1, size=nrand)
 
 
-def _check_prior(prior):
-    if prior is not None:
-        raise NotImplementedError(
-            "fixing guesses against a prior needs the priors' sampling code, "
-            "which is out of scope; send prior=None")
+def _allowed(prior, pars):
+    """does the prior accept this parameter vector"""
+    try:
+        return prior.get_lnprob_scalar(pars) > LOWVAL
+    except GMixRangeError:
+        return False
+
+
+def _fix_guess(guess, prior, ntry=4):
+    """rows the prior rejects are replaced by draws from the prior, up to
+    ntry times each (guessers.py:1275-1299)"""
+    for row in guess:
+        for _ in range(ntry):
+            if _allowed(prior, row):
+                break
+            row[:] = prior.sample()
+
+
+def _fix_guess_TFlux(guess, prior, ntry=4):
+    """the same, replacing only T and what follows it
+    (guessers.py:1245-1272)"""
+    for row in guess:
+        for _ in range(ntry):
+            if _allowed(prior, row):
+                break
+            row[4:] = prior.sample()[4:]
 
 
 class TFluxGuesser(object):
@@ -44,15 +67,17 @@ class TFluxGuesser(object):
     T and fluxes within 10% (guessers.py:14-75)"""
 
     def __init__(self, rng, T, flux, prior=None):
-        _check_prior(prior)
         self.rng = rng
         self.T = T
         self.fluxes = np.array(flux, dtype="f8", ndmin=1)
+        self.prior = prior
 
     def __call__(self, nrand=1, obs=None):
         guess = np.zeros((nrand, 5 + self.fluxes.size))
         _cen_shape_T(self.rng, self.T, nrand, guess)
         _fluxes(self.rng, self.fluxes, nrand, guess)
+        if self.prior is not None:
+            _fix_guess(guess, self.prior)
         return guess[0] if nrand == 1 else guess
 
 
@@ -61,9 +86,9 @@ class TPSFFluxGuesser(object):
     observations (guessers.py:78-144); the fluxes are cached per obs"""
 
     def __init__(self, rng, T, prior=None):
-        _check_prior(prior)
         self.rng = rng
         self.T = T
+        self.prior = prior
         self._id_last = None
         self._psf_fluxes = None
 
@@ -78,7 +103,115 @@ class TPSFFluxGuesser(object):
         guess = np.zeros((nrand, 5 + fluxes.size))
         _cen_shape_T(self.rng, self.T, nrand, guess)
         _fluxes(self.rng, fluxes, nrand, guess)
+        if self.prior is not None:
+            _fix_guess(guess, self.prior)
         return guess[0] if nrand == 1 else guess
+
+
+def _prior_start(prior, rng, T, nrand):
+    """a draw of every parameter from the prior with T replaced by the
+    caller's T within 10%: the common start of the *AndPrior / BDF / BD
+    guessers (guessers.py:183-190, 311-314)"""
+    guess = prior.sample(nrand)
+    guess[:, 4] = T * (1.0 + rng.uniform(low=-0.1, high=0.1, size=nrand))
+    return guess
+
+
+class TPSFFluxAndPriorGuesser(TPSFFluxGuesser):
+    """centre and shape from the prior, T within 10% of the input, fluxes
+    within 10% of the psf fluxes (guessers.py:147-202)"""
+
+    def __init__(self, rng, T, prior):
+        super().__init__(rng, T, prior=prior)
+
+    def __call__(self, obs, nrand=1):
+        fluxes = self._get_psf_fluxes(obs)
+        guess = _prior_start(self.prior, self.rng, self.T, nrand)
+        _fluxes(self.rng, fluxes, nrand, guess)
+        _fix_guess_TFlux(guess, self.prior)
+        return guess[0] if nrand == 1 else guess
+
+
+def _scatter_fluxes(rng, fluxes, nrand, guess, first):
+    for band, flux in enumerate(fluxes):
+        r = rng.uniform(low=-0.1, high=0.1, size=nrand)
+        guess[:, first + band] = flux * (1.0 + r)
+
+
+class TFluxAndPriorGuesser(object):
+    """centre and shape from the prior, T and fluxes within 10% of the
+    inputs; draws come from the centre prior's rng (guessers.py:264-322)"""
+
+    def __init__(self, rng, T, flux, prior):
+        self.T = T
+        self.fluxes = np.array(flux, dtype="f8", ndmin=1)
+        self.prior = prior
+
+    def __call__(self, nrand=1, obs=None):
+        rng = self.prior.cen_prior.rng
+        guess = _prior_start(self.prior, rng, self.T, nrand)
+        _scatter_fluxes(rng, self.fluxes, nrand, guess, 5)
+        _fix_guess_TFlux(guess, self.prior)
+        return guess[0] if nrand == 1 else guess
+
+
+class BDFGuesser(object):
+    """bdf guesses: the prior's draw with T and fluxes within 10% of the
+    inputs and fracdev in [0.4, 0.6] (guessers.py:379-429)"""
+    _first_flux = 6
+
+    def __init__(self, T, flux, prior):
+        self.T = T
+        self.fluxes = np.array(flux, ndmin=1)
+        self.prior = prior
+
+    def _get_fluxes(self, obs):
+        return self.fluxes
+
+    def __call__(self, nrand=1, obs=None):
+        rng = self.prior.cen_prior.rng
+        fluxes = self._get_fluxes(obs)
+        guess = _prior_start(self.prior, rng, self.T, nrand)
+        # the reference writes this draw into column 5 for bd as well (where
+        # column 5 is log10(Td/Te)); kept as is
+        guess[:, 5] = rng.uniform(low=0.4, high=0.6, size=nrand)
+        _scatter_fluxes(rng, fluxes, nrand, guess, self._first_flux)
+        _fix_guess(guess, self.prior)
+        return guess[0] if nrand == 1 else guess
+
+
+class BDGuesser(BDFGuesser):
+    """bd guesses, fluxes from column 7 (guessers.py:432-486)"""
+    _first_flux = 7
+
+
+class BDFPSFFluxGuesser(BDFGuesser, TPSFFluxGuesser):
+    """bdf guesses with the fluxes from psf template fits
+    (guessers.py:325-376)"""
+
+    def __init__(self, T, prior):
+        self.T = T
+        self.prior = prior
+        self.rng = prior.cen_prior.rng
+        self._id_last = None
+        self._psf_fluxes = None
+
+    def _get_fluxes(self, obs):
+        return self._get_psf_fluxes(obs)
+
+    def __call__(self, obs, nrand=1):
+        return BDFGuesser.__call__(self, nrand=nrand, obs=obs)
+
+
+class PriorGuesser(object):
+    """guesses that are plain draws from a joint prior
+    (guessers.py:667-686)"""
+
+    def __init__(self, prior):
+        self.prior = prior
+
+    def __call__(self, obs=None, nrand=None):
+        return self.prior.sample(nrand)
 
 
 def get_psf_fluxes(rng, obs):
@@ -110,8 +243,8 @@ class ParsGuesser(object):
     centres and shapes by absolute widths, the rest by fractional widths"""
 
     def __init__(self, rng, pars, prior=None, widths=None):
-        _check_prior(prior)
         self.rng = rng
+        self.prior = prior
         self.pars = np.array(pars, dtype="f8")
         self.np = self.pars.size
         if widths is None:
@@ -132,6 +265,8 @@ class ParsGuesser(object):
         guess[:, 2], guess[:, 3] = g1, g2
         for i in range(4, self.np):
             guess[:, i] = pars[i] * (1.0 + widths[i] * _srandu(rng, n))
+        if self.prior is not None:
+            _fix_guess(guess, self.prior)
         return guess[0] if is_scalar else guess
 
 

@@ -6,8 +6,9 @@ Normal and the joint PriorSimpleSep / PriorBDFSep.
 
 Each class also evaluates ln(prob) on the host for user code (scalar
 bookkeeping), and `to_ngx()` turns a joint prior into the ngx_prior record the
-kernels consume.  Sampling helpers and the MCMC-oriented priors are out of
-scope.
+kernels consume.  `sample()` draws from the caller's RandomState in the
+reference's order (the guessers that start a fit from the prior depend on it);
+the MCMC-oriented priors are out of scope.
 """
 from math import erf
 
@@ -49,7 +50,10 @@ class FlatPrior(PriorBase):
         return self.get_lnprob_scalar(val)
 
     def sample(self, nrand=None):
-        return self.rng.uniform(self.minval, self.maxval, size=nrand)
+        """uniform on the interval (priors/priors.py:159-187)"""
+        u = self.rng.uniform(size=1 if nrand is None else nrand)
+        vals = self.minval + (self.maxval - self.minval) * u
+        return vals[0] if nrand is None else vals
 
     def _ngx(self):
         return _lib.Prior1D(1, 0, self.minval, self.maxval, 0.0, 0.0)
@@ -77,6 +81,29 @@ class TwoSidedErf(PriorBase):
     def get_fdiff(self, val):
         p = -2 * self.get_lnprob_scalar(val)
         return np.sqrt(max(p, 0.0))
+
+    def get_prob_array(self, vals):
+        vals = np.atleast_1d(np.asarray(vals, dtype="f8"))
+        return np.array([self.get_prob_scalar(v) for v in vals])
+
+    def sample(self, nrand=None):
+        """rejection sampling between 5 widths either side
+        (priors/priors.py:339-388): candidates and heights are drawn in
+        rounds of the number still missing"""
+        n = 1 if nrand is None else nrand
+        lo = self.minval - 5.0 * self.width_at_min
+        hi = self.maxval + 5.0 * self.width_at_max
+        out = np.zeros(n)
+        have = 0
+        while have < n:
+            need = n - have
+            x = self.rng.uniform(low=lo, high=hi, size=need)
+            p = self.get_prob_array(x)
+            h = self.rng.uniform(size=need)
+            keep = x[h < p]
+            out[have:have + keep.size] = keep
+            have += keep.size
+        return out[0] if nrand is None else out
 
     def _ngx(self):
         return _lib.Prior1D(2, 0, self.minval, self.width_at_min, self.maxval,
@@ -163,6 +190,74 @@ class GPriorBA(PriorBase):
         chi2 = -2 * self.get_lnprob_scalar2d(g1, g2)
         return np.sqrt(max(chi2, 0.0))
 
+    def get_prob_array1d(self, g):
+        """p(|g|) = A 2 pi g (1-g^2)^2 exp(-g^2/2 sigma^2), 0 for g >= 1
+        (priors/shape.py:608-640)"""
+        g = np.atleast_1d(np.asarray(g, dtype="f8"))
+        out = np.zeros(g.size)
+        gsq = g * g
+        omgsq = 1.0 - gsq
+        w, = np.where(omgsq > 0.0)
+        if w.size > 0:
+            omgsq *= omgsq
+            out[w] = omgsq[w] * np.exp(-0.5 * gsq[w] * self.sig2inv)
+            out[w] *= self.A * 2 * np.pi * g[w]
+        return out
+
+    def get_prob_scalar1d(self, g):
+        return float(self.get_prob_array1d(g)[0])
+
+    def _set_maxval1d(self):
+        """peak of p(|g|).  The reference finds it with a numerical minimiser
+        started at sigma (shape.py:294-311); the stationary point of
+        log p = log g + 2 log(1-g^2) - g^2/2 sigma^2 is the root in (0,1) of
+        1/g - 4g/(1-g^2) - g/sigma^2, bracketed and bisected here."""
+        f = lambda g: 1.0 / g - 4.0 * g / (1.0 - g * g) - g * self.sig2inv
+        lo, hi = 1.0e-12, 1.0 - 1.0e-12
+        for _ in range(200):
+            mid = 0.5 * (lo + hi)
+            if f(mid) > 0.0:
+                lo = mid
+            else:
+                hi = mid
+        self.maxval1d_loc = 0.5 * (lo + hi)
+        self.maxval1d = self.get_prob_scalar1d(self.maxval1d_loc)
+
+    def sample1d(self, nrand, maxguess=None):
+        """|g| by rejection under 1.1 x the peak, candidates in [0, gmax-1e-4)
+        (priors/shape.py:160-209,471-491).  The reference draws one number
+        for its minimiser's starting point on every call; that draw is kept
+        so the caller's random stream stays aligned."""
+        rng = self.rng
+        if maxguess is None:
+            rng.uniform(low=-1.0, high=1.0)
+        if not hasattr(self, "maxval1d"):
+            self._set_maxval1d()
+        top = self.maxval1d * 1.1
+        gmax = self.gmax - 1.0e-4
+        out = np.zeros(nrand)
+        have = 0
+        while have < nrand:
+            need = nrand - have
+            g = gmax * rng.uniform(size=need)
+            h = top * rng.uniform(size=need)
+            keep = g[h < self.get_prob_array1d(g)]
+            out[have:have + keep.size] = keep
+            have += keep.size
+        return out
+
+    def sample2d(self, nrand=None, maxguess=0.1):
+        """(g1, g2): |g| from sample1d and a uniform position angle
+        (priors/shape.py:211-248; its default maxguess is a number, so no
+        starting-point draw is made on this path)"""
+        n = 1 if nrand is None else nrand
+        g = self.sample1d(n, maxguess=maxguess)
+        twotheta = 2 * (self.rng.uniform(size=n) * 2 * np.pi)
+        g1, g2 = g * np.cos(twotheta), g * np.sin(twotheta)
+        if nrand is None:
+            return g1[0], g2[0]
+        return g1, g2
+
 
 class PriorSimpleSep(object):
     """separate priors on centre, shape, T and flux (joint_prior.py:5-236)"""
@@ -171,7 +266,7 @@ class PriorSimpleSep(object):
         self.cen_prior = cen_prior
         self.g_prior = g_prior
         self.T_prior = T_prior
-        if isinstance(F_prior, list):
+        if isinstance(F_prior, (list, tuple)):
             self.nband = len(F_prior)
         else:
             self.nband = 1
@@ -191,6 +286,23 @@ class PriorSimpleSep(object):
         for i, F_prior in enumerate(self.F_priors):
             lnp += F_prior.get_lnprob_scalar(pars[5 + i])
         return lnp
+
+    # the 1-d priors between T and the fluxes, in parameter order
+    def _middle_priors(self):
+        return []
+
+    def sample(self, nrand=None):
+        """one draw per component in parameter order: centre, shape, T, the
+        model's extra parameters, one flux per band (joint_prior.py:191-226,
+        425-461, 621-655); [npars] or [nrand, npars]"""
+        n = 1 if nrand is None else nrand
+        cols = list(self.cen_prior.sample(n))
+        cols += list(self.g_prior.sample2d(n))
+        cols.append(self.T_prior.sample(n))
+        cols += [p.sample(n) for p in self._middle_priors()]
+        cols += [F.sample(n) for F in self.F_priors]
+        samples = np.stack(cols, axis=1)
+        return samples[0] if nrand is None else samples
 
     def fill_fdiff(self, pars, fdiff):
         lnp1, lnp2 = self.cen_prior.get_lnprob_scalar_sep(pars[0], pars[1])
@@ -243,6 +355,9 @@ class PriorBDFSep(PriorSimpleSep):
             lnp += F_prior.get_lnprob_scalar(pars[6 + i])
         return lnp
 
+    def _middle_priors(self):
+        return [self.fracdev_prior]
+
     def fill_fdiff(self, pars, fdiff):
         f1, f2 = self.cen_prior.get_fdiff(pars[0], pars[1])
         rows = [f1, f2, self.g_prior.get_fdiff(pars[2], pars[3]),
@@ -279,6 +394,9 @@ class PriorBDSep(PriorSimpleSep):
         for i, F_prior in enumerate(self.F_priors):
             lnp += F_prior.get_lnprob_scalar(pars[7 + i])
         return lnp
+
+    def _middle_priors(self):
+        return [self.logTratio_prior, self.fracdev_prior]
 
     def fill_fdiff(self, pars, fdiff):
         f1, f2 = self.cen_prior.get_fdiff(pars[0], pars[1])

@@ -952,6 +952,15 @@ def gen_boot():
     save("boot", **out)
 
 
+def gen_guessers():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from guesser_cases import guesser_cases
+    out = guesser_cases(ngmix, lambda seed: np.random.RandomState(seed))
+    for k, v in out.items():
+        print(k, np.asarray(v).shape)
+    save("guessers", **{k: np.asarray(v) for k, v in out.items()})
+
+
 GENERATORS = {
     "fastexp": gen_fastexp,
     "gmix": gen_gmix,
@@ -962,6 +971,7 @@ GENERATORS = {
     "em_admom": gen_em_admom,
     "lm_bdf": gen_lm_bdf,
     "lm_bd": gen_lm_bd,
+    "guessers": gen_guessers,
     "moments": gen_moments,
     "lm_multi": gen_lm_multi,
     "psfflux": gen_psfflux,

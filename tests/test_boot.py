@@ -71,9 +71,7 @@ def test_guessers_without_device():
                                widths=[0.01, 0.01, 0.05, 0.05, 0.2, 0.2])(
         nrand=4)
     assert np.allclose(got, g["gpars4"], rtol=1e-14, atol=0)
-    with pytest.raises(NotImplementedError):
-        guessers.TFluxGuesser(np.random.RandomState(1), 0.4, 1.0,
-                              prior=object())
+    # guessers with a prior: tests/test_guessers.py
 
 
 # ------------------------------------------------------------------ GPU
