@@ -167,6 +167,19 @@ int ngx_deriv_images(int n, int ngauss, const double *gpars,
                      const double *dcov, const ngx_jacobian *jac, int nrow,
                      int ncol, double *out, void *stream);
 
+/* calc_noise_cov (fitting/noise_cov.py:90-137), the matrix B of the sandwich
+ * covariance pars_cov0 B pars_cov0 of a fit under stationary correlated noise:
+ * B_ab = sum_q conj(G_a) G_b |fft2(noise)|^2 / N^2 with G_a = fft2(weight *
+ * dmodel/dp_a), evaluated in real space (Parseval) as the Gram matrix of the
+ * circular cross-correlations of weight * dmodel/dp_a with the noise image.
+ * dimages [n,nd,nrow*ncol] holds the derivative images, parameter a uses
+ * image rows[a] (NULL: a) times scale[n,nk] (NULL: 1); work [n,nk,nrow*ncol]
+ * is scratch; B [n,nk,nk]; nk <= 8. */
+int ngx_noise_b(int n, int nk, const int32_t *rows, const double *dimages,
+                int nd, const double *scale, const double *weights,
+                const double *noise, int nrow, int ncol, double *work,
+                double *B, void *stream);
+
 /* ------------------------------------------------------------------ */
 /* priors of the LM residual vector (PriorSimpleSep joint_prior.py:5-236,
  * PriorBDFSep :484-676) over CenPrior, GPriorBA, FlatPrior, TwoSidedErf,
@@ -356,6 +369,19 @@ int ngx_loglike_pixels_host(int n, int ngauss, const ngx_gauss *gmix,
 int ngx_deriv_images_host(int n, int ngauss, const double *gpars,
                           const double *dcov, const ngx_jacobian *jac,
                           int nrow, int ncol, double *out);
+/* B from caller-supplied derivative images [n,nk,nrow*ncol] (the
+ * central-difference images of models without analytic derivatives,
+ * noise_cov.py:203-226) */
+int ngx_noise_b_host(int n, int nk, const double *dimages,
+                     const double *weights, const double *noise, int nrow,
+                     int ncol, double *B);
+/* B [n,6,6] in parameter order (cen1, cen2, g1, g2, T, flux) for the models
+ * with analytic derivative images (noise_cov.py:160-201): gpars / dcov as for
+ * ngx_deriv_images, flux [n] */
+int ngx_noise_cov_host(int n, int ngauss, const double *gpars,
+                       const double *dcov, const double *flux,
+                       const ngx_jacobian *jac, const double *weights,
+                       const double *noise, int nrow, int ncol, double *B);
 int ngx_lm_fit_host(int n, int model, const double *images,
                     const double *weights, const ngx_jacobian *jac, int nrow,
                     int ncol, const double *psf_pars, int npsf,

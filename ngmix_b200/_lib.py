@@ -103,6 +103,7 @@ SYMBOLS = [
     "ngx_weighted_sums", "ngx_weighted_sums_host",
     "ngx_lm_fit_multi", "ngx_lm_fit_multi_host",
     "ngx_template_flux", "ngx_template_flux_host",
+    "ngx_noise_b", "ngx_noise_b_host", "ngx_noise_cov_host",
 ]
 
 _lib = None
@@ -330,6 +331,42 @@ def deriv_images(gpars, dcov, jac, dims):
                                       _p(dcov), _p(jac), C.c_int(dims[0]),
                                       C.c_int(dims[1]), _p(out)))
     return out
+
+
+def noise_b(dimages, weights, noise):
+    """B [n,nk,nk] of the noise-power sandwich covariance from caller-made
+    derivative images [n,nk,H*W] (ngx_noise_b_host)"""
+    init()
+    dimages = _f8(dimages)
+    n, nk = dimages.shape[:2]
+    weights = _f8(weights).reshape(n, *np.shape(weights)[-2:])
+    noise = _f8(noise).reshape(weights.shape)
+    H, W = weights.shape[1:]
+    assert dimages.shape[2] == H * W
+    B = np.zeros((n, nk, nk))
+    check(lib().ngx_noise_b_host(C.c_int(n), C.c_int(nk), _p(dimages),
+                                 _p(weights), _p(noise), C.c_int(H),
+                                 C.c_int(W), _p(B)))
+    return B
+
+
+def noise_cov_b(gpars, dcov, flux, jac, weights, noise):
+    """B [n,6,6] for the models with analytic derivative images
+    (ngx_noise_cov_host); gpars [n,ngauss,6], dcov [n,ngauss,3,3]"""
+    init()
+    gpars = _f8(gpars)
+    n, ngauss = gpars.shape[:2]
+    dcov = _f8(dcov).reshape(n, ngauss, 3, 3)
+    flux = _f8(flux).reshape(n)
+    jac = as_jac(jac, n)
+    weights = _f8(weights).reshape(n, *np.shape(weights)[-2:])
+    noise = _f8(noise).reshape(weights.shape)
+    H, W = weights.shape[1:]
+    B = np.zeros((n, 6, 6))
+    check(lib().ngx_noise_cov_host(C.c_int(n), C.c_int(ngauss), _p(gpars),
+                                   _p(dcov), _p(flux), _p(jac), _p(weights),
+                                   _p(noise), C.c_int(H), C.c_int(W), _p(B)))
+    return B
 
 
 # ---------------------------------------------------------------- LM

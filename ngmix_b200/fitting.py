@@ -35,7 +35,7 @@ def _prior_record(prior):
 
 def fit_batch(model, images, weights, jacobians, psf_pars, guesses,
               prior=None, fit_pars=None, analytic_jacobian=True,
-              ignore_zero_weight=True):
+              ignore_zero_weight=True, noise_images=None):
     """
     Levenberg-Marquardt fits of n stamps in one launch.
 
@@ -51,6 +51,10 @@ def fit_batch(model, images, weights, jacobians, psf_pars, guesses,
     guesses: [n, npars] array
     prior: PriorSimpleSep / PriorBDFSep, optional
     fit_pars: dict with maxfev, ftol, xtol, optional
+    noise_images: [n, H, W] array, optional
+        independent noise realisations; if sent, pars_cov / pars_err become
+        the noise-power sandwich covariance (Fitter(use_noise_image=True),
+        fitting/noise_cov.py)
 
     Returns
     -------
@@ -64,11 +68,24 @@ def fit_batch(model, images, weights, jacobians, psf_pars, guesses,
     fp = dict(DEFAULT_LM_PARS)
     if fit_pars is not None:
         fp.update(fit_pars)
-    return _lib.lm_fit(model, images, weights, jacobians, psf_pars, guesses,
+    recs = _lib.lm_fit(model, images, weights, jacobians, psf_pars, guesses,
                        prior=_prior_record(prior), maxfev=fp["maxfev"],
                        ftol=fp["ftol"], xtol=fp["xtol"],
                        analytic_jacobian=analytic_jacobian,
                        ignore_zero_weight=ignore_zero_weight)
+    if noise_images is not None:
+        from . import noise_cov
+        npars = get_model_npars(model)
+        ok = np.flatnonzero(recs["flags"] == 0)
+        if ok.size > 0:
+            psf_ok = None if psf_pars is None else np.asarray(psf_pars)[ok]
+            B = np.zeros((recs.size, npars, npars))
+            B[ok] = noise_cov.calc_noise_b(
+                model, recs["pars"][ok, :npars], psf_ok,
+                _lib.as_jac(jacobians)[ok], np.asarray(weights)[ok],
+                np.asarray(noise_images)[ok])
+            noise_cov.apply_noise_cov_batch(recs, B, npars)
+    return recs
 
 
 def fit_batch_multi(model, stamp_start, stamp_band, nband, images, weights,
@@ -257,8 +274,10 @@ class Fitter(object):
     fit_pars: dict, optional
         maxfev, ftol, xtol (defaults 4000, 1e-5, 1e-5)
     use_noise_image: bool, optional
-        the noise-power sandwich covariance is out of scope (SURVEY.md row
-        21); True raises NotImplementedError
+        replace the chi^2-scaled covariance by the noise-power sandwich
+        covariance measured from the noise images attached to the
+        observations (fitting/noise_cov.py); every observation must then
+        carry a noise image.  Default False.
     analytic_jacobian: bool, optional
         analytic Jacobian for gauss/exp/dev, forward differences otherwise
         (MINPACK lmder / lmdif, as in the reference).  Default True.
@@ -269,8 +288,6 @@ class Fitter(object):
         self.prior = prior
         self.model = get_model_num(model)
         self.model_name = get_model_name(self.model)
-        if use_noise_image:
-            raise NotImplementedError("use_noise_image is out of scope")
         self.use_noise_image = use_noise_image
         self.analytic_jacobian = analytic_jacobian
         self.fit_pars = dict(fit_pars) if fit_pars is not None \
@@ -279,6 +296,12 @@ class Fitter(object):
     def go(self, obs, guess):
         """run the fit; returns a dict-like FitResult"""
         mb = get_mb_obs(obs)
+        if self.use_noise_image:
+            for obslist in mb:
+                for tobs in obslist:
+                    if not tobs.has_noise():
+                        raise ValueError("obs.noise must be set when "
+                                         "use_noise_image=True")
         if len(mb) != 1 or len(mb[0]) != 1:
             return self._go_multi(mb, guess)
         o = mb[0][0]
@@ -301,6 +324,8 @@ class Fitter(object):
         if rec["flags"] == 1 and rec["nfev"] == 0:
             raise GMixFatalError("no weights > 0")
         res = record_to_result(rec, self.model_name, npars)
+        if self.use_noise_image:
+            self._apply_noise_cov(mb, res)
         return FitResult(o, self.model_name, res)
 
     def _go_multi(self, mb, guess):
@@ -346,4 +371,32 @@ class Fitter(object):
         if rec["flags"] == 1 and rec["nfev"] == 0:
             raise GMixFatalError("no weights > 0")
         res = record_to_result(rec, self.model_name, npars)
+        if self.use_noise_image:
+            self._apply_noise_cov(mb, res)
         return FitResult(mb, self.model_name, res)
+
+    def _apply_noise_cov(self, mb, res):
+        """calc_noise_cov + apply_noise_cov (fitting/noise_cov.py:38-137): B
+        is accumulated over the epochs of every band, each epoch's block
+        landing on the shape parameters and its band's flux"""
+        from . import noise_cov
+        if res["flags"] != 0:
+            return
+        pars = res["pars"]
+        npars, nband = pars.size, len(mb)
+        nshape = npars - nband
+        B = np.zeros((npars, npars))
+        for band, obslist in enumerate(mb):
+            kp = list(range(nshape)) + [nshape + band]
+            for o in obslist:
+                psf_pars = None
+                if o.has_psf_gmix():
+                    psf_pars = o.psf.gmix.get_full_pars().reshape(1, -1, 6)
+                try:
+                    Bk = noise_cov.calc_noise_b(
+                        self.model_name, pars[kp][None], psf_pars,
+                        o._jacobian._data, o.weight[None], o.noise[None])[0]
+                except ValueError:
+                    Bk = np.full((len(kp), len(kp)), np.nan)
+                B[np.ix_(kp, kp)] += Bk
+        noise_cov.apply_noise_cov(res, B)

@@ -663,6 +663,79 @@ def gen_lm_bd():
     save("lm_bd", **out)
 
 
+def gen_noise_cov():
+    """Fitter(use_noise_image=True): sandwich covariance under correlated
+    noise (fitting/noise_cov.py); exp with the analytic derivative images,
+    bdf with the central-difference ones"""
+    from ngmix import priors, joint_prior
+    from ngmix.fitting import Fitter
+    out = {}
+    for tag, model in (("exp", "exp"), ("bdf", "bdf")):
+        if model == "exp":
+            b = sims.make_lm_batch(5, seed0=15000, noise=0.05, dims=(32, 30))
+            prior = None
+        else:
+            b = sims.make_bdf_batch(3, seed0=15100, dims=(36, 36), noise=0.02)
+            rng = np.random.RandomState(7)
+            prior = joint_prior.PriorBDFSep(
+                cen_prior=priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng),
+                g_prior=priors.GPriorBA(0.3, rng=rng),
+                T_prior=priors.FlatPrior(-1.0, 1.0e3, rng=rng),
+                fracdev_prior=priors.Normal(0.5, 0.1, rng=rng),
+                F_prior=priors.FlatPrior(-100.0, 1.0e9, rng=rng))
+        n = b["images"].shape[0]
+        npars = b["guess"].shape[1]
+        sig = b["noise"]
+        rng = np.random.RandomState(77)
+        # correlated noise: white noise smoothed by a small kernel, scaled
+        # back to the nominal per-pixel variance; the same recipe for the
+        # noise added to the image (on top of the sims' white noise it
+        # replaces) and for the independent noise image
+        def corr_noise(shape):
+            w = rng.normal(size=shape)
+            sm = (w + 0.6 * np.roll(w, 1, 0) + 0.6 * np.roll(w, 1, 1)
+                  + 0.3 * np.roll(w, (1, 1), (0, 1)))
+            return sm * (sig / sm.std())
+        images = b["images"].copy()
+        noise = np.zeros_like(images)
+        for i in range(n):
+            images[i] += corr_noise(images[i].shape)
+            noise[i] = corr_noise(images[i].shape)
+        for k in ("weights", "jac", "psf", "guess"):
+            out["%s_%s" % (tag, k)] = b[k]
+        out[tag + "_images"] = images
+        out[tag + "_noise"] = noise
+        res = dict(flags=np.zeros(n, "i4"), nfev=np.zeros(n, "i4"),
+                   pars=np.zeros((n, npars)), pars_err=np.zeros((n, npars)),
+                   pars_cov=np.zeros((n, npars, npars)),
+                   pars_cov0=np.zeros((n, npars, npars)),
+                   pars_err_plain=np.zeros((n, npars)))
+        for i in range(n):
+            psf_obs = ngmix.Observation(
+                np.ones((5, 5)),
+                jacobian=ngmix.DiagonalJacobian(row=2, col=2, scale=0.263),
+                gmix=ngmix.GMix(pars=b["psf"][i].ravel()))
+            obs = ngmix.Observation(images[i], weight=b["weights"][i],
+                                    noise=noise[i],
+                                    jacobian=jac_from_record(b["jac"][i]),
+                                    psf=psf_obs)
+            r = Fitter(model=model, prior=prior, use_noise_image=True).go(
+                obs, b["guess"][i].copy())
+            r0 = Fitter(model=model, prior=prior).go(obs, b["guess"][i].copy())
+            res["flags"][i] = r["flags"]
+            res["nfev"][i] = r["nfev"]
+            res["pars"][i] = r["pars"]
+            res["pars_err"][i] = r["pars_err"]
+            res["pars_cov"][i] = r["pars_cov"]
+            res["pars_cov0"][i] = r["pars_cov0"]
+            res["pars_err_plain"][i] = r0["pars_err"]
+        print(tag, "flags", res["flags"], "err ratio",
+              res["pars_err"][:, 2] / res["pars_err_plain"][:, 2])
+        for k, v in res.items():
+            out["%s_res_%s" % (tag, k)] = v
+    save("noise_cov", **out)
+
+
 def gen_moments():
     """GaussMom (6 and 17 moments) on galaxy stamps, and get_weighted_sums
     with a two-gaussian off-centre weight and a maxrad"""
@@ -972,6 +1045,7 @@ GENERATORS = {
     "lm_bdf": gen_lm_bdf,
     "lm_bd": gen_lm_bd,
     "guessers": gen_guessers,
+    "noise_cov": gen_noise_cov,
     "moments": gen_moments,
     "lm_multi": gen_lm_multi,
     "psfflux": gen_psfflux,

@@ -506,3 +506,91 @@ def template_flux(images, weights, jacs, gm_pars, normalize=True,
         C.c_int(int(normalize)), C.c_int(int(ignore_zero_weight)), _p(res))
     assert st == 0, st
     return res[0]
+
+
+# ------------------------------------------------------------------ noise cov
+def _full_pars(gm):
+    return np.array([[gm[k][i] for k in ("p", "row", "col", "irr", "irc",
+                                         "icc")] for i in range(gm.size)])
+
+
+def noise_cov(model, pars, pars_cov0, weight, noise, jac, psf_pars=None):
+    """calc_noise_cov (ngmix/fitting/noise_cov.py:90-137), single epoch and
+    band, restated with numpy's fft exactly as the reference writes it:
+    B_ab = sum_q conj(G_a) G_b |fft2(noise)|^2 / N^2, G_a = fft2(weight *
+    dmodel/dp_a); returns pars_cov0 B pars_cov0 and B.  Derivative images:
+    deriv_images for gauss/exp/dev (:160-201), central differences of fast
+    renders otherwise (:203-226, steps fitting/results.py:927-952)."""
+    pars = _f8(pars)
+    weight = _f8(weight)
+    noise = _f8(noise)
+    jac = _f8(jac)
+    dims = weight.shape
+    npars = pars.size
+    psf = None
+    if psf_pars is not None:
+        psf, _ = gmix_fill("full", _f8(psf_pars).ravel())
+
+    def composed(p):
+        gm0, st = gmix_fill(model, p)
+        assert st == 0
+        return gm0, (gmix_convolve(gm0, psf) if psf is not None else gm0)
+
+    if model in ("gauss", "exp", "dev") and pars[5] != 0.0:
+        gm0, gmc = composed(pars)
+        gpars = _full_pars(gmc)
+        modpars = _full_pars(gm0)
+        npsf = gpars.shape[0] // modpars.shape[0]
+        modcov = np.repeat(modpars[:, 3:6], npsf, axis=0)
+        g1, g2, T, flux = pars[2:6]
+        gsq = g1 * g1 + g2 * g2
+        f = 2.0 / (1.0 + gsq)
+        dfac = -f / (1.0 + gsq)
+        de1dg1 = f + 2.0 * g1 * g1 * dfac
+        de1dg2 = 2.0 * g1 * g2 * dfac
+        de2dg1 = de1dg2
+        de2dg2 = f + 2.0 * g2 * g2 * dfac
+        Tk = modcov[:, 0] + modcov[:, 2]
+        dcov = np.zeros((gpars.shape[0], 3, 3))
+        for i, (de1, de2) in enumerate(((de1dg1, de2dg1), (de1dg2, de2dg2))):
+            dcov[:, i, 0] = -0.5 * Tk * de1
+            dcov[:, i, 1] = 0.5 * Tk * de2
+            dcov[:, i, 2] = 0.5 * Tk * de1
+        dcov[:, 2, :] = modcov / T
+        coords = make_coords(dims, jac)
+        out = deriv_images(gpars, dcov, coords["v"], coords["u"],
+                           coords["area"])
+        images = [out[k].reshape(dims) for k in (1, 2, 3, 4, 5)]
+        images.append(out[0].reshape(dims) / flux)
+    else:
+        images = []
+        for ipar in range(npars):
+            if ipar < 2:
+                step = 1.0e-3
+            elif ipar < 4:
+                step = 1.0e-4
+            elif ipar < npars - 1:
+                step = max(1.0e-4, 1.0e-3 * abs(pars[ipar]))
+            else:
+                step = max(1.0e-6, 1.0e-3 * abs(pars[ipar]))
+            ims = []
+            for sign in (1, -1):
+                p = pars.copy()
+                p[ipar] += sign * step
+                _, gm = composed(p)
+                im, st = render(gm, dims, jac, fast_exp=True)
+                assert st == 0
+                ims.append(im)
+            images.append((ims[0] - ims[1]) / (2 * step))
+    kernels = [np.fft.fft2(weight * dim) for dim in images]
+    power = np.abs(np.fft.fft2(noise)) ** 2
+    n = weight.size
+    B = np.zeros((npars, npars))
+    for ia in range(npars):
+        for ib in range(ia, npars):
+            val = np.sum(np.conj(kernels[ia]) * kernels[ib] * power).real \
+                / n ** 2
+            B[ia, ib] = val
+            B[ib, ia] = val
+    pars_cov0 = _f8(pars_cov0)
+    return pars_cov0 @ B @ pars_cov0, B
