@@ -213,6 +213,50 @@ def bench_bdf(args, torch, _lib, sims, dev):
     return o
 
 
+def bench_metacal(args, torch, _lib, sims, dev):
+    """configs[4]: metacal-style batch, 5 sheared images per object fit as
+    independent exp LM fits (1-gaussian reconvolution psf); R11 / R22 from
+    the +-0.01 pairs as a sanity number"""
+    nobj = args.nmcal
+    b = sims.make_metacal_batch(nobj, seed0=555000, noise=0.01)
+    n = 5 * nobj
+    t = {k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev)
+         for k in ("images", "weights", "jac", "psf", "guess")}
+    d_res = torch.zeros(n * _lib.LM_RESULT_DTYPE.itemsize, dtype=torch.uint8,
+                        device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+
+    def fit():
+        _lib.lm_fit_device("exp", n, t["images"].data_ptr(),
+                           t["weights"].data_ptr(), t["jac"].data_ptr(), 48,
+                           48, t["psf"].data_ptr(), 1, t["guess"].data_ptr(),
+                           d_res.data_ptr(), stream=s)
+
+    fit()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fit()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(),
+                        dtype=_lib.LM_RESULT_DTYPE)
+    g = res["pars"][:, 2:4].reshape(nobj, 5, 2)
+    ok = (res["flags"].reshape(nobj, 5) == 0).all(axis=1)
+    R11 = float(np.mean(g[ok, 1, 0] - g[ok, 2, 0]) / 0.02)
+    R22 = float(np.mean(g[ok, 3, 1] - g[ok, 4, 1]) / 0.02)
+    return {"config": "configs[4]: %d objects x 5 sheared images, exp LM "
+                      "fits, 48x48, 1-gaussian psf (6 gaussians)" % nobj,
+            "fits_per_s": n / (ms * 1e-3),
+            "objects_per_s": nobj / (ms * 1e-3), "ms_per_step": ms,
+            "nonzero_flags": int((res["flags"] != 0).sum()),
+            "median_nfev": float(np.median(res["nfev"])),
+            "R11": R11, "R22": R22}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nobj", type=int, default=20000)
@@ -220,6 +264,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nbdf", type=int, default=2000,
                     help="configs[3] sample: bdf fits on 64x64 stamps")
+    ap.add_argument("--nmcal", type=int, default=2000,
+                    help="configs[4] sample: objects with 5 sheared images")
     args = ap.parse_args()
     import torch
     from ngmix_b200 import _lib, sims
@@ -304,6 +350,8 @@ def main():
     out["multi"] = bench_multi(args, _lib, sims, torch, dev)
     if args.nbdf > 0:
         out["bdf"] = bench_bdf(args, torch, _lib, sims, dev)
+    if args.nmcal > 0:
+        out["metacal"] = bench_metacal(args, torch, _lib, sims, dev)
     print(json.dumps(out))
 
 

@@ -79,3 +79,42 @@ def run_psf_fitter(obs, fitter, guesser=None, ntry=1, set_result=True):
         if res["flags"] == 0 and hasattr(res, "get_gmix"):
             target.gmix = res.get_gmix()
     return res
+
+
+def run_fit_batch(model, images, weights, jacobians, psf_pars, guesser,
+                  ntry=1, **kw):
+    """
+    The Runner's retry loop (run_fitter, ngmix/runners.py:116-147) over a
+    batch: round 0 fits every object, each later round refits only the
+    objects whose flags are still non-zero, from fresh guesses, in one launch.
+
+    guesser: callable(indices, itry) -> [len(indices), npars] guesses for the
+        objects `indices` (int array) in round `itry`
+    other arguments as fit_batch.  Returns (records [n], tries [n]) where
+    tries counts the fits each object went through.
+    """
+    import numpy as np
+    from .fitting import fit_batch
+    images, weights = np.asarray(images), np.asarray(weights)
+    n = images.shape[0]
+    jac = np.asarray(jacobians).reshape(n, -1)
+    psf = None if psf_pars is None else np.asarray(psf_pars)
+    noise = kw.pop("noise_images", None)
+    todo = np.arange(n)
+    recs = None
+    tries = np.zeros(n, dtype="i4")
+    for itry in range(ntry):
+        guess = np.asarray(guesser(todo, itry), dtype="f8")
+        sub = fit_batch(model, images[todo], weights[todo], jac[todo],
+                        None if psf is None else psf[todo], guess,
+                        noise_images=None if noise is None
+                        else np.asarray(noise)[todo], **kw)
+        if recs is None:
+            recs = sub.copy()
+        else:
+            recs[todo] = sub
+        tries[todo] += 1
+        todo = todo[sub["flags"] != 0]
+        if todo.size == 0:
+            break
+    return recs, tries

@@ -122,3 +122,31 @@ def test_from_observations(ngx):
     ref = ngmix.fit_batch("exp", b["images"], b["weights"], b["jac"],
                           b["psf"], b["guess"])
     _same_records(got, ref)
+
+
+def test_run_fit_batch_retries_only_failures(ngx):
+    """batched Runner: the second round refits exactly the objects that
+    failed the first (here: a guess outside the model's domain), and what
+    comes back equals fitting everything from the good guesses"""
+    import ngmix_b200 as ng
+    from ngmix_b200 import sims
+    from ngmix_b200.runners import run_fit_batch
+    b = sims.make_lm_batch(12, seed0=5150, noise=0.05, dims=(32, 32))
+    bad = np.array([1, 4, 7])
+    calls = []
+
+    def guesser(idx, itry):
+        calls.append(idx.copy())
+        g = b["guess"][idx].copy()
+        if itry == 0:
+            g[np.isin(idx, bad), 4] = -1.0          # T < 0: range error
+        return g
+
+    recs, tries = run_fit_batch("exp", b["images"], b["weights"], b["jac"],
+                                b["psf"], guesser, ntry=3)
+    assert len(calls) == 2 and np.array_equal(calls[1], bad)
+    assert np.array_equal(tries, np.where(np.isin(np.arange(12), bad), 2, 1))
+    want = ng.fit_batch("exp", b["images"], b["weights"], b["jac"], b["psf"],
+                        b["guess"])
+    assert not recs["flags"].any()
+    assert np.array_equal(recs["pars"], want["pars"])
