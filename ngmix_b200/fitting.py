@@ -16,7 +16,8 @@ from .gmix import (GMix, get_model_name, get_model_npars, get_model_num,
                    make_gmix_model)
 from .observation import Observation, get_mb_obs
 
-__all__ = ['Fitter', 'FitResult', 'fit_batch', 'SIMPLE_ANALYTIC_MODELS']
+__all__ = ['Fitter', 'FitResult', 'FitModel', 'fit_batch',
+           'SIMPLE_ANALYTIC_MODELS', 'get_band_pars', 'get_lm_n_prior_pars']
 
 # models with an analytic Jacobian (fitting/results.py:921)
 SIMPLE_ANALYTIC_MODELS = ('gauss', 'exp', 'dev')
@@ -212,6 +213,168 @@ class FitResult(dict):
         gm = self.get_convolved_gmix(band=band, obsnum=obsnum)
         obs = self.obs[band][obsnum]
         return gm.make_image(obs.image.shape, jacobian=obs.jacobian)
+
+
+def get_lm_n_prior_pars(model, nband):
+    """residual slots reserved for the prior (fitting/results.py:1050-1076)"""
+    if model == "bd":
+        return 6 + nband
+    if model in ("bdf", "exp", "dev", "gauss", "turb"):
+        return 5 + nband
+    raise ValueError("bad model: %s" % model)
+
+
+def get_band_pars(model, pars, band):
+    """the parameters of one band: everything up to the fluxes plus that
+    band's flux (fitting/results.py:1013-1047)"""
+    nshape = get_model_npars(model) - 1
+    return np.append(np.asarray(pars[:nshape], dtype="f8"),
+                     pars[nshape + band])
+
+
+class FitModel(FitResult):
+    """
+    The fit model of the reference (fitting/results.py:17-625): the residual
+    vector, its Jacobian and ln(prob) at arbitrary parameters, evaluated
+    through the same device passes the fit uses, plus the result dict.
+
+    calc_fdiff    prior rows, then (model - data) * ierr of every epoch, -inf
+                  everywhere on a range error            (results.py:439-485)
+    calc_jacobian prior rows by forward differences, pixel rows from
+                  deriv_images, zero on a range error    (results.py:487-625)
+    calc_lnprob   sum of get_loglike + ln(prior)         (results.py:142-210)
+    """
+
+    def __init__(self, obs, model, guess, prior=None):
+        model = get_model_name(get_model_num(model))
+        super().__init__(obs, model, {})
+        self.prior = prior
+        self.model = get_model_num(model)
+        self.n_prior_pars = 0 if prior is None else \
+            get_lm_n_prior_pars(model, self.nband)
+        self.totpix = sum(o.pixels.size for ol in self.obs for o in ol)
+        self.fdiff_size = self.totpix + self.n_prior_pars
+        guess = np.array(guess, dtype="f8")
+        assert guess.size == self.npars, \
+            "guess has npars=%d, expected %d" % (guess.size, self.npars)
+        # as FitModel._setup_fit: a guess outside the model's domain raises
+        self._convolved(guess)
+
+    def _convolved(self, pars):
+        """[(obs, convolved GMix, pre-psf GMix, band)] at pars"""
+        out = []
+        for band, obslist in enumerate(self.obs):
+            gm0 = make_gmix_model(get_band_pars(self.model_name, pars, band),
+                                  self.model_name)
+            for o in obslist:
+                gm = gm0.convolve(o.psf.gmix) if o.has_psf_gmix() else gm0
+                gm.set_norms()
+                out.append((o, gm, gm0, band))
+        return out
+
+    def set_fit_result(self, result):
+        self.update(result)
+
+    def calc_fdiff(self, pars):
+        from .defaults import LOWVAL
+        pars = np.asarray(pars, dtype="f8")
+        fdiff = np.zeros(self.fdiff_size)
+        try:
+            mix = self._convolved(pars)
+            start = 0
+            if self.prior is not None:
+                start = self.prior.fill_fdiff(pars, fdiff)
+            for o, gm, _, _ in mix:
+                pix = o.pixels
+                _, fd, st = _lib.loglike_pixels(gm._data[None], pix[None],
+                                                want_fdiff=True)
+                if st[0]:
+                    raise GMixRangeError("det or T too low")
+                fdiff[start:start + pix.size] = fd[0]
+                start += pix.size
+        except GMixRangeError:
+            fdiff[:] = LOWVAL
+        return fdiff
+
+    def calc_lnprob(self, pars, more=False):
+        from .defaults import LOWVAL, BIGVAL
+        pars = np.asarray(pars, dtype="f8")
+        tot = {"lnprob": 0.0, "s2n_numer": 0.0, "s2n_denom": 0.0, "npix": 0}
+        try:
+            if self.prior is not None:
+                tot["lnprob"] += self.prior.get_lnprob_scalar(pars)
+            for o, gm, _, _ in self._convolved(pars):
+                r = gm.get_loglike(o, more=True)
+                tot["lnprob"] += r["loglike"]
+                for k in ("s2n_numer", "s2n_denom", "npix"):
+                    tot[k] += r[k]
+        except GMixRangeError:
+            tot = {"lnprob": LOWVAL, "s2n_numer": 0.0, "s2n_denom": BIGVAL,
+                   "npix": 0}
+        return tot if more else tot["lnprob"]
+
+    def calc_jacobian(self, pars):
+        from .noise_cov import model_deriv_data
+        if self.model_name not in SIMPLE_ANALYTIC_MODELS:
+            raise ValueError("analytic jacobian is not available for model "
+                             "%s" % self.model_name)
+        pars = np.asarray(pars, dtype="f8")
+        jac = np.zeros((self.fdiff_size, self.npars))
+        try:
+            start = self._fill_prior_jacobian(pars, jac)
+            mix = self._convolved(pars)
+            for o, _, _, band in mix:
+                bp = get_band_pars(self.model_name, pars, band)
+                if bp[4] == 0.0 or bp[5] == 0.0:
+                    raise GMixRangeError("zero T or flux")
+                psf_pars = None
+                if o.has_psf_gmix():
+                    psf_pars = o.psf.gmix.get_full_pars().reshape(1, -1, 6)
+                gpars, dcov = model_deriv_data(self.model_name, bp[None],
+                                               psf_pars)
+                out = _lib.deriv_images(gpars, dcov, o._jacobian._data,
+                                        o.image.shape)[0]
+                # the reference evaluates on obs.pixels: the valid pixels in
+                # row-major order
+                keep = np.ones(o.image.size, dtype=bool)
+                if o.ignore_zero_weight:
+                    keep = o.weight.ravel() > 0.0
+                out = out[:, keep]
+                ierr = o.pixels["ierr"]
+                sl = slice(start, start + ierr.size)
+                for k in range(5):
+                    jac[sl, k] = out[1 + k] * ierr
+                jac[sl, 5 + band] = out[0] * (ierr / bp[5])
+                start += ierr.size
+        except (GMixRangeError, ValueError):
+            jac[:] = 0.0
+        return jac
+
+    def _fill_prior_jacobian(self, pars, jac):
+        """forward differences of prior.fill_fdiff, backward where the step
+        leaves the prior's domain (results.py:572-625)"""
+        if self.prior is None:
+            return 0
+        step_prior = 1.0e-8
+        f0 = np.zeros(self.n_prior_pars)
+        fs = np.zeros(self.n_prior_pars)
+        n = self.prior.fill_fdiff(pars, f0)
+        good0 = np.isfinite(f0[:n])
+        for ipar in range(self.npars):
+            step = step_prior * max(1.0, abs(pars[ipar]))
+            p = pars.copy()
+            p[ipar] = pars[ipar] + step
+            try:
+                self.prior.fill_fdiff(p, fs)
+            except GMixRangeError:
+                step = -step
+                p[ipar] = pars[ipar] + step
+                self.prior.fill_fdiff(p, fs)
+            good = good0 & np.isfinite(fs[:n])
+            d = np.zeros(n)
+            d[good] = (fs[:n][good] - f0[:n][good]) / step
+            jac[:n, ipar] = d
+        return n
 
 
 class PSFFluxFitter(object):

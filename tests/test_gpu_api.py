@@ -232,6 +232,74 @@ def test_fitter_bd_with_joint_prior(ng):
         assert prior.fill_fdiff(r["pars"], fd) == 7
 
 
+def test_fitmodel_calc_fdiff_and_jacobian(ng):
+    """FitModel.calc_fdiff / calc_jacobian / calc_lnprob at the guess against
+    the reference's vectors (lm_trace.npz: prior rows, pixel rows, J^T J,
+    J^T f), the central-difference check of tests/test_fitting_lm_jacobian.py
+    :44-68, and the zero Jacobian / -inf residuals on range errors (:108-125)"""
+    g = load_golden("lm_exp")
+    t = load_golden("lm_trace")
+    pr = ng.priors
+    priors = {
+        "none": None,
+        "flat": pr.PriorSimpleSep(
+            pr.CenPrior(0.0, 0.0, 0.263, 0.263), pr.GPriorBA(0.3),
+            pr.FlatPrior(-1.0, 1.0e3), pr.FlatPrior(-100.0, 1.0e9)),
+        "erf": pr.PriorSimpleSep(
+            pr.CenPrior(0.0, 0.0, 0.263, 0.263), pr.GPriorBA(0.3),
+            pr.TwoSidedErf(-1.0, 0.1, 1.0e3, 1.0),
+            pr.TwoSidedErf(-1.0e2, 1.0, 1.0e9, 1.0e8)),
+    }
+    for pk, prior in priors.items():
+        for i in range(2):
+            rec = g["lo_jac"][i]
+            jac = ng.Jacobian(row=rec[0], col=rec[1], dvdrow=rec[2],
+                              dvdcol=rec[3], dudrow=rec[4], dudcol=rec[5])
+            psf_obs = ng.Observation(
+                np.ones((5, 5)), gmix=ng.GMix(pars=g["lo_psf"][i].ravel()))
+            obs = ng.Observation(g["lo_images"][i], weight=g["lo_weights"][i],
+                                 jacobian=jac, psf=psf_obs)
+            guess = g["lo_guess"][i]
+            fm = ng.fitting.FitModel(obs, "exp", guess, prior=prior)
+            want = t["%s_%d_fdiff" % (pk, i)]
+            assert fm.fdiff_size == want.size
+            fd = fm.calc_fdiff(guess)
+            assert np.abs(fd - want).max() <= 1e-11 * np.abs(want).max()
+            J = fm.calc_jacobian(guess)
+            assert J.shape == (want.size, 6)
+            jp = t["%s_%d_jac_prior" % (pk, i)]
+            assert np.allclose(J[:jp.shape[0]], jp, rtol=1e-12, atol=1e-14)
+            jtj = t["%s_%d_jtj" % (pk, i)]
+            assert np.abs(J.T @ J - jtj).max() <= 1e-10 * np.abs(jtj).max()
+            assert np.abs(J.T @ fd - t["%s_%d_jtf" % (pk, i)]).max() \
+                <= 1e-9 * np.abs(t["%s_%d_jtf" % (pk, i)]).max()
+            # analytic Jacobian vs central differences of calc_fdiff
+            for k, h in enumerate([1e-4, 1e-4, 1e-5, 1e-5, 1e-4, 1e-2]):
+                p1, p2 = guess.copy(), guess.copy()
+                p1[k] += h
+                p2[k] -= h
+                num = (fm.calc_fdiff(p1) - fm.calc_fdiff(p2)) / (2 * h)
+                scale = np.abs(J[:, k]).max()
+                assert np.abs(num - J[:, k]).max() <= 1e-4 * scale, (pk, k)
+            # ln(prob) = -chi2/2 of the pixel rows + ln(prior)
+            lnp = fm.calc_lnprob(guess)
+            npri = 0 if prior is None else prior.fill_fdiff(guess,
+                                                            np.zeros(8))
+            lnprior = 0.0 if prior is None else \
+                prior.get_lnprob_scalar(guess)
+            assert abs(lnp - (-0.5 * (fd[npri:] ** 2).sum() + lnprior)) \
+                < 1e-9 * abs(lnp)
+            # range errors: -inf residuals, zero Jacobian, LOWVAL ln(prob)
+            bad = guess.copy()
+            bad[2] = 1.5
+            assert np.all(np.isneginf(fm.calc_fdiff(bad)))
+            assert not fm.calc_jacobian(bad).any()
+            assert fm.calc_lnprob(bad) == -np.inf
+            zero = guess.copy()
+            zero[5] = 0.0
+            assert not fm.calc_jacobian(zero).any()
+
+
 def test_em_appendix_b(ng):
     jac = ng.DiagonalJacobian(row=12, col=12, scale=0.263)
     truth = ng.GMix(pars=[60, -0.3, 0.2, 0.12, 0.01, 0.15,
