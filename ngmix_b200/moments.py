@@ -175,3 +175,83 @@ def regularize_mom_shapes(res, fwhm_reg):
     out["flags"] |= res["flags"]
     out["flagstr"] = _flags.get_flags_str(out["flags"])
     return out
+
+
+# ---- gaussian size conversions and second-moment algebra
+# (ngmix/moments.py:94-395); irr = <y^2>, irc = <xy>, icc = <x^2>
+def r50_to_sigma(r50):
+    """half-light radius of a gaussian = fwhm / 2"""
+    return fwhm_to_sigma(2.0 * r50)
+
+
+def sigma_to_r50(sigma):
+    return sigma_to_fwhm(sigma) / 2.0
+
+
+def r50_to_T(r50):
+    return 2 * r50_to_sigma(r50) ** 2
+
+
+def T_to_r50(T):
+    return sigma_to_r50(np.sqrt(T / 2.0))
+
+
+def moms_to_e1e2(M1, M2, T):
+    """(M1, M2) / T; T must be positive"""
+    from .gexceptions import GMixRangeError
+    if np.any(np.asarray(T) <= 0.0):
+        raise GMixRangeError("T <= 0.0")
+    Tinv = 1.0 / T
+    return M1 * Tinv, M2 * Tinv
+
+
+def get_Tround(T, g1, g2):
+    """size of the round object the shape (g1, g2) was sheared from"""
+    gsq = g1 ** 2 + g2 ** 2
+    return T * (1 - gsq) / (1 + gsq)
+
+
+def get_T(Tround, g1, g2):
+    gsq = g1 ** 2 + g2 ** 2
+    return Tround * (1 + gsq) / (1 - gsq)
+
+
+def mom2e(Irr, Irc, Icc):
+    T = Irr + Icc
+    return (Icc - Irr) / T, 2.0 * Irc / T, T
+
+
+def mom2g(Irr, Irc, Icc):
+    from . import shape
+    e1, e2, T = mom2e(Irr, Irc, Icc)
+    g1, g2 = shape.e1e2_to_g1g2(e1, e2)
+    return g1, g2, T
+
+
+def e2mom(e1, e2, T):
+    return (1 - e1) * T / 2.0, e2 * T / 2.0, (1 + e1) * T / 2.0
+
+
+def g2mom(g1, g2, T):
+    from . import shape
+    return e2mom(*shape.g1g2_to_e1e2(g1, g2), T)
+
+
+def get_sheared_g1g2T(g1, g2, T, s1, s2):
+    """shape and size after the shear (s1, s2): the round size is kept"""
+    from . import shape
+    g1s, g2s = shape.shear_reduced(g1, g2, s1, s2)
+    return g1s, g2s, get_T(get_Tround(T, g1, g2), g1s, g2s)
+
+
+def get_sheared_M1M2T(M1, M2, T, s1, s2):
+    from . import shape
+    g1, g2 = shape.e1e2_to_g1g2(*moms_to_e1e2(M1, M2, T))
+    g1s, g2s, Ts = get_sheared_g1g2T(g1, g2, T, s1, s2)
+    e1s, e2s = shape.g1g2_to_e1e2(g1s, g2s)
+    return Ts * e1s, Ts * e2s, Ts
+
+
+def get_sheared_moments(irr, irc, icc, s1, s2):
+    g1, g2, T = mom2g(irr, irc, icc)
+    return g2mom(*get_sheared_g1g2T(g1, g2, T, s1, s2))

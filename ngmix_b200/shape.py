@@ -86,6 +86,20 @@ class Shape(object):
         g1, g2 = shear_reduced(self.g1, self.g2, s1, s2)
         return Shape(g1, g2)
 
+    def set_g1g2(self, g1, g2):
+        if g1 * g1 + g2 * g2 >= 1.0:
+            raise GMixRangeError("g out of range")
+        self.g1, self.g2 = g1, g2
+
+    def get_rotated(self, theta_radians):
+        return Shape(*rotate_shape(self.g1, self.g2, theta_radians))
+
+    def rotate(self, theta_radians):
+        self.set_g1g2(*rotate_shape(self.g1, self.g2, theta_radians))
+
+    def __neg__(self):
+        return Shape(-self.g1, -self.g2)
+
     def copy(self):
         return Shape(self.g1, self.g2)
 
@@ -104,3 +118,61 @@ def fwhm_to_T(fwhm):
 
 def T_to_fwhm(T):
     return 2.3548200450309493 * np.sqrt(T / 2)
+
+
+def rotate_shape(g1, g2, theta):
+    """the shape seen after rotating the axes by theta radians: a spin-2
+    rotation by 2 theta (shape.py:492-519)"""
+    c, sn = np.cos(2.0 * theta), np.sin(2.0 * theta)
+    return g1 * c + g2 * sn, g2 * c - g1 * sn
+
+
+def _scaled(a1, a2, amax_msg, scale_of):
+    """(a1, a2) rescaled so its modulus becomes scale_of(modulus); the
+    modulus must be < 1; zeros stay zeros.  Scalars in, scalars out."""
+    scalar = np.ndim(a1) == 0
+    a1 = np.atleast_1d(np.asarray(a1, dtype="f8"))
+    a2 = np.atleast_1d(np.asarray(a2, dtype="f8"))
+    mod = np.sqrt(a1 * a1 + a2 * a2)
+    if np.any(mod >= 1.0):
+        raise GMixRangeError(amax_msg)
+    fac = np.zeros(mod.size)
+    w = mod > 0.0
+    fac[w] = scale_of(mod[w]) / mod[w]
+    o1, o2 = fac * a1, fac * a2
+    return (o1[0], o2[0]) if scalar else (o1, o2)
+
+
+def g1g2_to_eta1eta2(g1, g2):
+    """eta = 2 atanh(g) along the same position angle (shape.py:296-347)"""
+    return _scaled(g1, g2, "g out of bounds converting to eta",
+                   lambda g: 2 * np.arctanh(g))
+
+
+def e1e2_to_eta1eta2(e1, e2):
+    """eta = atanh(e) (shape.py:350-393)"""
+    return _scaled(e1, e2, "some e were out of bounds", np.arctanh)
+
+
+def eta1eta2_to_g1g2(eta1, eta2):
+    """g = tanh(eta / 2) (shape.py:396-440)"""
+    scalar = np.ndim(eta1) == 0
+    eta1 = np.atleast_1d(np.asarray(eta1, dtype="f8"))
+    eta2 = np.atleast_1d(np.asarray(eta2, dtype="f8"))
+    eta = np.sqrt(eta1 * eta1 + eta2 * eta2)
+    g = np.tanh(0.5 * eta)
+    if np.any(g >= 1.0):
+        raise GMixRangeError("some g were out of bounds")
+    fac = np.zeros(eta.size)
+    w = eta != 0.0
+    fac[w] = g[w] / eta[w]
+    g1, g2 = fac * eta1, fac * eta2
+    return (g1[0], g2[0]) if scalar else (g1, g2)
+
+
+def dgs_by_dgo_jacob(g1, g2, s1, s2):
+    """jacobian determinant of the map g -> g sheared by s
+    (shape.py:443-468)"""
+    ssq = s1 * s1 + s2 * s2
+    den = 1 + 2 * g1 * s1 + 2 * g2 * s2 + g1 ** 2 * ssq + g2 ** 2 * ssq
+    return (ssq - 1) ** 2 / den ** 2

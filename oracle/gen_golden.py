@@ -736,6 +736,47 @@ def gen_noise_cov():
     save("noise_cov", **out)
 
 
+def gen_shape_moments():
+    """known answers of the host-side shape / moment algebra
+    (ngmix/shape.py, ngmix/moments.py)"""
+    from ngmix import shape, moments
+    rng = np.random.RandomState(21)
+    g1 = rng.uniform(-0.6, 0.6, 12)
+    g2 = rng.uniform(-0.6, 0.6, 12)
+    s1 = rng.uniform(-0.1, 0.1, 12)
+    s2 = rng.uniform(-0.1, 0.1, 12)
+    T = rng.uniform(0.1, 4.0, 12)
+    th = rng.uniform(-3, 3, 12)
+    out = dict(g1=g1, g2=g2, s1=s1, s2=s2, T=T, theta=th)
+    out["eta_from_g"] = np.array(shape.g1g2_to_eta1eta2(g1, g2))
+    e1, e2 = np.array([shape.g1g2_to_e1e2(a, b) for a, b in zip(g1, g2)]).T
+    out["eta_from_e"] = np.array(shape.e1e2_to_eta1eta2(e1, e2))
+    out["g_from_eta"] = np.array(shape.eta1eta2_to_g1g2(
+        out["eta_from_g"][0], out["eta_from_g"][1]))
+    out["jacob"] = shape.dgs_by_dgo_jacob(g1, g2, s1, s2)
+    out["rot"] = np.array(shape.rotate_shape(g1, g2, th))
+    irr, irc, icc = moments.g2mom(g1[0], g2[0], T[0])
+    out["g2mom"] = np.array([moments.g2mom(a, b, c)
+                             for a, b, c in zip(g1, g2, T)])
+    out["mom2g"] = np.array([moments.mom2g(*m) for m in out["g2mom"]])
+    out["mom2e"] = np.array([moments.mom2e(*m) for m in out["g2mom"]])
+    out["e2mom"] = np.array([moments.e2mom(a, b, c)
+                             for a, b, c in zip(e1, e2, T)])
+    out["sheared_g1g2T"] = np.array([
+        moments.get_sheared_g1g2T(*v) for v in zip(g1, g2, T, s1, s2)])
+    out["sheared_M1M2T"] = np.array([
+        moments.get_sheared_M1M2T(c * a, c * b, c, d, e)
+        for a, b, c, d, e in zip(e1, e2, T, s1, s2)])
+    out["sheared_moments"] = np.array([
+        moments.get_sheared_moments(m[0], m[1], m[2], d, e)
+        for m, d, e in zip(out["g2mom"], s1, s2)])
+    out["Tround"] = moments.get_Tround(T, g1, g2)
+    out["T_from_round"] = moments.get_T(out["Tround"], g1, g2)
+    out["r50"] = np.array([moments.T_to_r50(T), moments.r50_to_T(T),
+                           moments.r50_to_sigma(T), moments.sigma_to_r50(T)])
+    save("shape_moments", **out)
+
+
 def gen_moments():
     """GaussMom (6 and 17 moments) on galaxy stamps, and get_weighted_sums
     with a two-gaussian off-centre weight and a maxrad"""
@@ -1046,6 +1087,7 @@ GENERATORS = {
     "lm_bd": gen_lm_bd,
     "guessers": gen_guessers,
     "noise_cov": gen_noise_cov,
+    "shape_moments": gen_shape_moments,
     "moments": gen_moments,
     "lm_multi": gen_lm_multi,
     "psfflux": gen_psfflux,
