@@ -81,14 +81,17 @@ __device__ __forceinline__ void em_build_conv(EMShared *sh, int ngauss,
 // stay in registers until the pixel's total is known and are written to
 // shared memory once, already scaled (NG = 0: runtime ngauss, scaled in
 // place).  Same operations in the same order either way.
-template <int VARIANT, int NG>
+// GM: the stamp-sized arrays (shifted image, pixel coordinates, pixel codes)
+// live in a global scratch buffer instead of shared memory, for stamps too
+// large to be resident; the arithmetic is the same.
+template <int VARIANT, int NG, bool GM = false>
 __global__ void __launch_bounds__(NGX_EM_TILE)
 k_em(int n, const double *__restrict__ images,
      const double *__restrict__ weights, const ngx_jacobian *__restrict__ jac,
      int nrow, int ncol, const double *__restrict__ guess, int ngauss_in,
      const double *__restrict__ psf_pars, int npsf_in, ngx_em_conf conf,
      int ignore_zero_weight, double *__restrict__ pars_out,
-     ngx_em_result *__restrict__ res) {
+     ngx_em_result *__restrict__ res, double *gscratch = nullptr) {
     extern __shared__ double smem_d[];
     __shared__ EMShared sh;
     constexpr bool DO_CEN = (VARIANT == NGX_EM_FULL || VARIANT == NGX_EM_FIXCOV);
@@ -102,17 +105,24 @@ k_em(int n, const double *__restrict__ images,
     const int nconv = ngauss * npsf;
     // nslots * NGX_EM_STRIDE first (16-byte aligned for the phase-B loads)
     double *contrib = smem_d;
-    double *val = contrib + (size_t)nslots * NGX_EM_STRIDE;   // ntot
-    double *pv = val + ntot;            // ntot: pixel v (fixed for the fit)
-    double *pu = pv + ntot;             // ntot: pixel u
-    ngx_gauss *conv_d = (ngx_gauss *)(pu + ntot);             // nconv
-    double *logtau_d = (double *)(conv_d + nconv);            // nconv
-    double *logdet_d = logtau_d + nconv;                      // nconv
-    // per pixel: 255 excluded, 0 zero weight (filled each iteration), 1 normal
-    unsigned char *code = (unsigned char *)(logdet_d + nconv);
-
     const int stamp = blockIdx.x;
     if (stamp >= n) return;
+    double *stamp_arrays = contrib + (size_t)nslots * NGX_EM_STRIDE;
+    if (GM)
+        stamp_arrays = gscratch
+            + (size_t)stamp * (3 * (size_t)ntot + ((size_t)ntot + 7) / 8);
+    double *val = stamp_arrays;         // ntot
+    double *pv = val + ntot;            // ntot: pixel v (fixed for the fit)
+    double *pu = pv + ntot;             // ntot: pixel u
+    // per pixel: 255 excluded, 0 zero weight (filled each iteration), 1 normal
+    unsigned char *code_g = (unsigned char *)(pu + ntot);
+    ngx_gauss *conv_d = (ngx_gauss *)(
+        GM ? contrib + (size_t)nslots * NGX_EM_STRIDE : pu + ntot);  // nconv
+    double *logtau_d = (double *)(conv_d + nconv);            // nconv
+    double *logdet_d = logtau_d + nconv;                      // nconv
+    unsigned char *code = GM ? code_g
+                             : (unsigned char *)(logdet_d + nconv);
+
     const double *im = images + (size_t)stamp * ntot;
     const double *wt = weights + (size_t)stamp * ntot;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -462,24 +472,27 @@ struct AMShared {
     int flags, done, numiter, npix_valid;
 };
 
+// GM: pixel values and variances in a global scratch buffer (stamps too large
+// for shared memory)
+template <bool GM>
 __global__ void __launch_bounds__(128)
 k_admom(int n, const double *__restrict__ images,
         const double *__restrict__ weights,
         const ngx_jacobian *__restrict__ jac, int nrow, int ncol,
         const double *__restrict__ guess, ngx_admom_conf conf,
-        ngx_admom_result *__restrict__ res) {
+        ngx_admom_result *__restrict__ res, double *gscratch) {
     extern __shared__ double smem_d[];
     __shared__ AMShared sh;
     __shared__ ngx_admom_result out;
     const int T = blockDim.x;
     const int ntot = nrow * ncol;
-    double *val = smem_d;            // ntot
-    double *var = val + ntot;        // ntot: 1/ierr^2, < 0 for dropped pixels
-    double *rowd = var + ntot;
-    double *cold = rowd + nrow;
-    double *scratch = cold + ncol;   // 37 * nwarps
     const int stamp = blockIdx.x;
     if (stamp >= n) return;
+    double *val = GM ? gscratch + (size_t)stamp * 2 * ntot : smem_d;  // ntot
+    double *var = val + ntot;        // ntot: 1/ierr^2, < 0 for dropped pixels
+    double *rowd = GM ? smem_d : var + ntot;
+    double *cold = rowd + nrow;
+    double *scratch = cold + ncol;   // 37 * nwarps
     const double *im = images + (size_t)stamp * ntot;
     const double *wt = weights + (size_t)stamp * ntot;
     int cnt = 0;
@@ -726,8 +739,39 @@ static int launch_em(int n, const double *images, const double *weights,
     size_t smem = sizeof(double)
         * (3 * (size_t)ntot + (size_t)nslots * NGX_EM_STRIDE + 2 * nconv)
         + sizeof(ngx_gauss) * (size_t)nconv + (size_t)ntot + 16;
-    if (smem > (size_t)smem_optin_bytes())
-        return fail(NGX_ERR_ARG, "ngx_em: stamp too large%s%s");
+    if (smem > (size_t)smem_optin_bytes()) {
+        // stamp-sized arrays in a stream-ordered global scratch buffer,
+        // a bounded number of stamps per launch
+        size_t smem_g = sizeof(double)
+            * ((size_t)nslots * NGX_EM_STRIDE + 2 * nconv)
+            + sizeof(ngx_gauss) * (size_t)nconv + 16;
+        if (smem_g > (size_t)smem_optin_bytes())
+            return fail(NGX_ERR_ARG, "ngx_em: mixture too large%s%s");
+        const size_t per = 3 * (size_t)ntot + ((size_t)ntot + 7) / 8;
+        int chunk = (int)((size_t)(1u << 28) / per);       // 2 GiB of doubles
+        if (chunk < 1) chunk = 1;
+        if (chunk > n) chunk = n;
+        double *scr = nullptr;
+        NGX_CUDA(cudaMallocAsync((void **)&scr, sizeof(double) * per * chunk,
+                                 stream));
+        NGX_CUDA(cudaFuncSetAttribute(
+            k_em<VARIANT, 0, true>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        const int np1 = npsf > 0 ? npsf : 0;
+        for (int i0 = 0; i0 < n; i0 += chunk) {
+            const int m = n - i0 < chunk ? n - i0 : chunk;
+            k_em<VARIANT, 0, true><<<m, NGX_EM_TILE, smem_g, stream>>>(
+                m, images + (size_t)i0 * ntot, weights + (size_t)i0 * ntot,
+                jac + i0, nrow, ncol, guess + (size_t)i0 * ngauss * 6, ngauss,
+                psf_pars ? psf_pars + (size_t)i0 * np1 * 6 : nullptr, npsf,
+                conf, ignore_zero_weight, pars_out + (size_t)i0 * ngauss * 6,
+                res + i0, scr);
+        }
+        cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(scr, stream);
+        NGX_CUDA(e);
+        return NGX_OK;
+    }
 #define NGX_EM_LAUNCH(NG_)                                                   \
     do {                                                                     \
         NGX_CUDA(cudaFuncSetAttribute(                                       \
@@ -800,12 +844,34 @@ int ngx_admom(int n, const double *images, const double *weights,
     int nwarps = threads / 32;
     size_t smem = sizeof(double)
         * (2 * (size_t)ntot + nrow + ncol + 37 * (size_t)nwarps);
-    if (smem > (size_t)smem_optin_bytes())
-        return fail(NGX_ERR_ARG, "ngx_admom: stamp too large%s%s");
+    cudaStream_t st = as_stream(stream);
+    if (smem > (size_t)smem_optin_bytes()) {
+        // pixel values and variances in a stream-ordered scratch buffer
+        size_t smem_g = sizeof(double) * (nrow + ncol + 37 * (size_t)nwarps);
+        const size_t per = 2 * (size_t)ntot;
+        int chunk = (int)((size_t)(1u << 28) / per);       // 2 GiB of doubles
+        if (chunk < 1) chunk = 1;
+        if (chunk > n) chunk = n;
+        double *scr = nullptr;
+        NGX_CUDA(cudaMallocAsync((void **)&scr, sizeof(double) * per * chunk,
+                                 st));
+        for (int i0 = 0; i0 < n; i0 += chunk) {
+            const int m = n - i0 < chunk ? n - i0 : chunk;
+            k_admom<true><<<m, threads, smem_g, st>>>(
+                m, images + (size_t)i0 * ntot, weights + (size_t)i0 * ntot,
+                jac + i0, nrow, ncol, guess + (size_t)i0 * 6, *conf, res + i0,
+                scr);
+        }
+        cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(scr, st);
+        NGX_CUDA(e);
+        return NGX_OK;
+    }
     NGX_CUDA(cudaFuncSetAttribute(
-        k_admom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_admom<<<n, threads, smem, as_stream(stream)>>>(
-        n, images, weights, jac, nrow, ncol, guess, *conf, res);
+        k_admom<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        (int)smem));
+    k_admom<false><<<n, threads, smem, st>>>(
+        n, images, weights, jac, nrow, ncol, guess, *conf, res, nullptr);
     NGX_LAUNCH_CHECK();
     return NGX_OK;
 }

@@ -65,6 +65,8 @@ struct LMArgs {
     // objects with several stamps (ngx_lm_fit_multi)
     int nband;
     const int32_t *stamp_start, *stamp_band;
+    // stamps too large for shared memory (GS kernels): per-CTA planes
+    double *gscratch;
 };
 
 struct LMShared {
@@ -836,9 +838,14 @@ __device__ __noinline__ int feed_residual(const LMArgs &a, LMShared *sh,
 // WG: the weights stay in global memory / L2 (stamps too large to keep both
 // planes in shared memory at four CTAs per SM); otherwise ierr = sqrt(w) is
 // staged next to the pixel values.
-template <int MODE, int CV, int CD, int MINB, bool WG, int NT = 128>
+// GS: the pixel-value plane (and the base-model plane of the forward-
+// difference mode) live in a per-CTA slice of a global scratch buffer
+// instead of shared memory, for stamps too large to be resident (WG only).
+template <int MODE, int CV, int CD, int MINB, bool WG, int NT = 128,
+          bool GS = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_lm_fit(LMArgs a) {
+    static_assert(!GS || WG, "GS keeps the weights in global memory");
     extern __shared__ double smem_d[];
     __shared__ LMShared sh;
     const int T = blockDim.x;
@@ -848,10 +855,13 @@ k_lm_fit(LMArgs a) {
     double *mix = smem_d;                                    // ngauss*REC
     double *fdm = mix + (size_t)a.ngauss * REC;              // nfd*ngauss*FDREC
     double *etab = fdm + (size_t)nfd * a.ngauss * FDREC;     // 16 (MODE 1)
-    double *mplane = etab + (nfd ? 16 : 0);                  // nq (MODE 1)
+    double *planes = etab + (nfd ? 16 : 0);
+    double *gplanes = GS ? a.gscratch
+        + (size_t)blockIdx.x * ((nfd ? 2 : 1) * (size_t)a.nq) : planes;
+    double *mplane = gplanes;                                // nq (MODE 1)
     double *val = mplane + (nfd ? a.nq : 0);                 // nq
     double *ierr = val + a.nq;                               // nq (!WG)
-    double *rowd = ierr + (WG ? 0 : a.nq);
+    double *rowd = GS ? planes : ierr + (WG ? 0 : a.nq);
     double *cold = rowd + a.nrow;
     double *scratch = cold + a.ncol;                         // 48 * nwarps
     double *hs = scratch + 48 * nwarps;                      // 8
@@ -900,9 +910,14 @@ k_lm_fit(LMArgs a) {
                 for (int q = t0; q < a.nq; q += TS) {
                     int row, col;
                     q_to_rowcol(q, a.tpr, &row, &col);
-                    if (row < a.nrow && col < a.ncol)
-                        __pipeline_memcpy_async(&val[q], &im[row * a.ncol + col],
-                                                sizeof(double));
+                    if (row < a.nrow && col < a.ncol) {
+                        if (GS)
+                            val[q] = im[row * a.ncol + col];
+                        else
+                            __pipeline_memcpy_async(
+                                &val[q], &im[row * a.ncol + col],
+                                sizeof(double));
+                    }
                 }
                 __pipeline_commit();
                 if (t0 < 6 * a.npsf)
@@ -1487,6 +1502,13 @@ struct LMLaunch {
     size_t smem;
 };
 
+// stamp_start = 0..n and stamp_band = 0 for n one-stamp objects
+__global__ void k_iota_zero(int n, int32_t *start, int32_t *band) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) start[i] = i;
+    if (i < n) band[i] = 0;
+}
+
 template <typename K>
 static int config_and_launch(K kernel, const LMArgs &a, int threads,
                              size_t smem, cudaStream_t stream) {
@@ -1567,12 +1589,55 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     size_t per_cta = smem_both + sizeof(LMShared) + 1024;
     bool wg = 4 * per_cta > (size_t)smem_optin_bytes() + 1024;
     cudaStream_t st = as_stream(stream);
+    if (analytic && smem + sizeof(LMShared) + 1024
+            > (size_t)smem_optin_bytes()) {
+        // the stamp does not fit shared memory even without the weights:
+        // fit each stamp as a one-epoch object of the multi-epoch kernel,
+        // which reads its pixels from global memory on every pass
+        int32_t *ss = nullptr;
+        NGX_CUDA(cudaMallocAsync((void **)&ss, sizeof(int32_t) * (2 * n + 1),
+                                 st));
+        k_iota_zero<<<(n + 256) / 256, 256, 0, st>>>(n, ss, ss + n + 1);
+        int rc2 = ngx_lm_fit_multi(n, model, ss, ss + n + 1, 1, images,
+                                   weights, jac, nrow, ncol, psf_pars, npsf,
+                                   guess, prior, lm_pars, ignore_zero_weight,
+                                   res, stream);
+        cudaFreeAsync(ss, st);
+        return rc2;
+    }
     if (analytic) {
         if (wg)
             return config_and_launch(k_lm_fit<0, 3, 2, 4, true>, a, threads,
                                      smem, st);
         return config_and_launch(k_lm_fit<0, 3, 2, 4, false>, a, threads,
                                  smem_both, st);
+    }
+    if (smem + sizeof(LMShared) + 1024 > (size_t)smem_optin_bytes()) {
+        // forward-difference fit of a stamp that does not fit shared memory:
+        // the value and base-model planes go to a per-CTA global scratch
+        size_t smem_g = smem - sizeof(double) * (size_t)a.nq * (nfd ? 2 : 1)
+            + sizeof(double) * 48 * 4;
+        if (smem_g > (size_t)smem_optin_bytes())
+            return fail(NGX_ERR_ARG,
+                        "ngx_lm_fit: mixture does not fit shared memory%s%s");
+        auto kern = k_lm_fit<1, 3, 2, 2, true, 256, true>;
+        NGX_CUDA(cudaFuncSetAttribute(
+            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        int per_sm = 0;
+        NGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &per_sm, kern, 256, smem_g));
+        if (per_sm < 1) per_sm = 1;
+        int blocks = sm_count() * per_sm;
+        if (blocks > n) blocks = n;
+        NGX_CUDA(cudaMallocAsync(
+            (void **)&a.gscratch,
+            sizeof(double) * (size_t)blocks * (nfd ? 2 : 1) * a.nq, st));
+        NGX_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), st));
+        kern<<<blocks, 256, smem_g, st>>>(a);
+        cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(a.gscratch, st);
+        NGX_CUDA(e);
+        return NGX_OK;
     }
     if (wg) {
         // large stamps with the np + 1 forward-difference mixtures resident

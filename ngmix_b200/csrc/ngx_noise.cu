@@ -27,18 +27,23 @@ struct NoiseMap {
     int rows[NZ_MAXK];   // which image of D is parameter a's derivative
 };
 
-// grid (nk, n): one CTA correlates one derivative image with the noise image
+// grid (nk, n): one CTA correlates one derivative image with the noise image.
+// GM: the two staged planes live in a per-CTA slice of a global scratch
+// buffer (stamps too large for shared memory).
+template <bool GM>
 __global__ void __launch_bounds__(256)
 k_noise_corr(int nk, NoiseMap map, const double *__restrict__ D, int nd,
              const double *__restrict__ scale,
              const double *__restrict__ weights,
              const double *__restrict__ noise, int nrow, int ncol, int wp,
-             double *__restrict__ C) {
+             double *__restrict__ C, double *gscratch) {
     extern __shared__ double smem_d[];
     const int a = blockIdx.x, obj = blockIdx.y;
     const int ntot = nrow * ncol;
     const int p2 = 2 * wp + 1;                 // odd pitch: rows spread over banks
-    double *k2 = smem_d;                       // nrow * p2: k, columns repeated
+    double *k2 = GM ? gscratch + ((size_t)obj * nk + a)
+        * ((size_t)nrow * p2 + (size_t)nrow * wp) : smem_d;
+    // k2: nrow * p2 (k, columns repeated)
     double *n2 = k2 + (size_t)nrow * p2;       // nrow * wp: noise, zero padded
     const double *d = D + ((size_t)obj * nd + map.rows[a]) * ntot;
     const double *w = weights + (size_t)obj * ntot;
@@ -140,14 +145,38 @@ static int noise_b_launch(int n, int nk, const NoiseMap &map, const double *D,
     const int wp = ((ncol + NZ_JB - 1) / NZ_JB) * NZ_JB;
     size_t smem = sizeof(double)
         * ((size_t)nrow * (2 * wp + 1) + (size_t)nrow * wp);
-    if (smem > (size_t)smem_optin_bytes())
-        return fail(NGX_ERR_ARG, "ngx_noise_b: stamp too large%s%s");
-    NGX_CUDA(cudaFuncSetAttribute(
-        k_noise_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(nk, n);
-    k_noise_corr<<<grid, 256, smem, st>>>(nk, map, D, nd, scale, weights,
-                                          noise, nrow, ncol, wp, C);
-    NGX_LAUNCH_CHECK();
+    if (smem > (size_t)smem_optin_bytes()) {
+        // staged planes in a stream-ordered global scratch, a bounded number
+        // of stamps per launch
+        const size_t per = (size_t)nk * (smem / sizeof(double));
+        int chunk = (int)((size_t)(1u << 28) / per);       // 2 GiB of doubles
+        if (chunk < 1) chunk = 1;
+        if (chunk > n) chunk = n;
+        double *scr = nullptr;
+        NGX_CUDA(cudaMallocAsync((void **)&scr, sizeof(double) * per * chunk,
+                                 st));
+        const size_t ntot = (size_t)nrow * ncol;
+        for (int i0 = 0; i0 < n; i0 += chunk) {
+            const int m = n - i0 < chunk ? n - i0 : chunk;
+            dim3 grid(nk, m);
+            k_noise_corr<true><<<grid, 256, 0, st>>>(
+                nk, map, D + (size_t)i0 * nd * ntot, nd,
+                scale ? scale + (size_t)i0 * nk : nullptr,
+                weights + i0 * ntot, noise + i0 * ntot, nrow, ncol, wp,
+                C + (size_t)i0 * nk * ntot, scr);
+        }
+        cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(scr, st);
+        NGX_CUDA(e);
+    } else {
+        NGX_CUDA(cudaFuncSetAttribute(
+            k_noise_corr<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int)smem));
+        dim3 grid(nk, n);
+        k_noise_corr<false><<<grid, 256, smem, st>>>(
+            nk, map, D, nd, scale, weights, noise, nrow, ncol, wp, C, nullptr);
+        NGX_LAUNCH_CHECK();
+    }
     k_noise_gram<<<n, 256, 0, st>>>(nk, C, nrow * ncol, B);
     NGX_LAUNCH_CHECK();
     return NGX_OK;

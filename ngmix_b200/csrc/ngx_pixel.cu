@@ -893,8 +893,27 @@ static int launch_loglike(int src, int n, int ngauss, const ngx_gauss *gmix,
                + ((size_t)(nq / 32) * ((ngauss + 31) / 32) + 1) / 2
                + 2 * (size_t)nq + 1)
             + sizeof(int) * ((size_t)nrow * tpr + nrow);
-        if (smt > (size_t)smem_optin_bytes())
-            return fail(NGX_ERR_ARG, "ngx_loglike: stamp too large%s%s");
+        if (smt > (size_t)smem_optin_bytes()) {
+            // the stamp does not fit shared memory: build the reference's
+            // pixel records in a stream-ordered scratch buffer and run the
+            // pixel-record kernel on them (same values, same fdiff order)
+            cudaStream_t st = as_stream(stream);
+            ngx_pixel *pix = nullptr;
+            int32_t *np = nullptr;
+            NGX_CUDA(cudaMallocAsync((void **)&pix,
+                                     sizeof(ngx_pixel) * (size_t)n * ntot,
+                                     st));
+            NGX_CUDA(cudaMallocAsync((void **)&np, sizeof(int32_t) * n, st));
+            k_make_pixels<<<n, 256, 0, st>>>(nrow, ncol, images, weights, jac,
+                                            ignore_zero_weight, pix, np);
+            k_loglike_pixels<<<n, 256, smem, st>>>(ngauss, gmix, pix, ntot, np,
+                                                  out4, fdiff, status);
+            cudaError_t e = cudaGetLastError();
+            cudaFreeAsync(pix, st);
+            cudaFreeAsync(np, st);
+            NGX_CUDA(e);
+            return NGX_OK;
+        }
         NGX_CUDA(cudaFuncSetAttribute(
             k_loglike_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int)smt));

@@ -186,3 +186,82 @@ def test_config2_low_s2n_and_priors(ngx, ora, noise, prior_kind):
                      1e-3 * ref["pars_err"][:, :6])
     assert np.all(np.abs(res["pars"][:, :6] - ref["pars"][:, :6])[ok]
                   <= tol[ok])
+
+
+def test_stamps_larger_than_shared_memory(ngx, ora):
+    """stamps that do not fit an SM's shared memory take the global-memory
+    paths (pixel records for loglike, scratch buffers for EM / admom, the
+    multi-epoch kernel for the analytic LM fit) and give the same answers"""
+    from ngmix_b200 import sims
+    # LM, 200 x 200
+    b = sims.make_lm_batch(3, seed0=808, dims=(200, 200), noise=0.05)
+    res = ngx.lm_fit("exp", b["images"], b["weights"], b["jac"], b["psf"],
+                     b["guess"])
+    ref = ora.lm_fit_batch("exp", b["images"], b["weights"], b["jac"],
+                           b["psf"], b["guess"])
+    assert np.array_equal(res["flags"], ref["flags"])
+    assert np.array_equal(res["nfev"], ref["nfev"])
+    err = np.abs(res["pars"][:, :6] - ref["pars"][:, :6])
+    assert np.all(err <= np.maximum(1e-5 * np.abs(ref["pars"][:, :6]),
+                                    1e-3 * ref["pars_err"][:, :6]))
+    assert np.allclose(res["lnprob"], ref["lnprob"], rtol=1e-9)
+    # forward-difference LM (bdf with prior), 128 x 128: value and base-model
+    # planes in the per-CTA global scratch
+    b = sims.make_bdf_batch(3, seed0=810, dims=(128, 128), noise=0.02)
+    res = ngx.lm_fit("bdf", b["images"], b["weights"], b["jac"], b["psf"],
+                     b["guess"], prior=_bdf_prior(ngx))
+    ref = ora.lm_fit_batch("bdf", b["images"], b["weights"], b["jac"],
+                           b["psf"], b["guess"], prior=ora.make_prior("bdf"))
+    assert np.array_equal(res["flags"], ref["flags"])
+    assert np.array_equal(res["nfev"], ref["nfev"])
+    err = np.abs(res["pars"][:, :7] - ref["pars"][:, :7])
+    assert np.all(err <= np.maximum(1e-5 * np.abs(ref["pars"][:, :7]),
+                                    1e-2 * ref["pars_err"][:, :7]))
+    # loglike + fdiff, 128 x 128 with masked pixels
+    b = sims.make_lm_batch(2, seed0=809, dims=(128, 128), noise=0.05)
+    b["weights"][:, 5:9, 100:120] = 0.0
+    gm0, _ = ngx.gmix_fill("exp", b["guess"])
+    gp, _ = ngx.gmix_fill("full", b["psf"].reshape(2, -1))
+    gm = ngx.gmix_convolve(gm0, gp)
+    ngx.gmix_set_norms(gm)
+    out4, fdiff, st = ngx.loglike(gm, b["images"], b["weights"], b["jac"],
+                                  want_fdiff=True)
+    assert not st.any()
+    for i in range(2):
+        og0, _ = ora.gmix_fill("exp", b["guess"][i])
+        ogp, _ = ora.gmix_fill("full", b["psf"][i].ravel())
+        og = ora.gmix_convolve(og0, ogp)
+        ora.gmix_set_norms(og)
+        pix = ora.make_pixels(b["images"][i], b["weights"][i], b["jac"][i])
+        want = np.zeros(pix.size)
+        ora.fill_fdiff(og, pix, want)
+        o4, _ = ora.get_loglike(og, pix)
+        assert out4[i][3] == pix.size
+        assert np.allclose(out4[i][:3], o4[:3], rtol=1e-11)
+        assert np.abs(fdiff[i][:pix.size] - want).max() \
+            <= 1e-11 * np.abs(want).max()
+    # EM and admom, 100 x 100 / 128 x 128 PSF-like stamps
+    for dims in ((100, 100), (128, 128)):
+        n = 2
+        rng = np.random.RandomState(dims[0])
+        jac = np.array([sims.diag_jacobian((dims[0] - 1) / 2 + 0.2,
+                                           (dims[1] - 1) / 2 - 0.3, 0.263)] * n)
+        full = sims.simple_full_pars([0.0, 0.0, 0.05, -0.03, 4.0, 1.0], "turb")
+        images = np.array([sims.render_full_pars(full, dims, jac[i])
+                           + rng.normal(0, 1e-5, dims) for i in range(n)])
+        weights = np.full(images.shape, 1e10)
+        guess = np.array([[[0.6, 0.0, 0.0, 1.5, 0.0, 1.5],
+                           [0.4, 0.0, 0.0, 3.0, 0.0, 3.0]]] * n)
+        res, pars = ngx.em(images, weights, jac, guess, maxiter=200)
+        ores, opars = ora.em_go_batch(images, weights, jac, guess,
+                                      maxiter=200)
+        assert np.array_equal(res["flags"], ores["flags"])
+        assert np.array_equal(res["numiter"], ores["numiter"])
+        assert np.allclose(pars.reshape(n, -1), opars.reshape(n, -1),
+                           rtol=1e-9, atol=1e-12)
+        ag = np.array([[1.0, 0.0, 0.0, 2.0, 0.0, 2.0]] * n)
+        ares = ngx.admom(images, weights, jac, ag)
+        oam = ora.admom_go_batch(images, weights, jac, ag)
+        assert np.array_equal(ares["flags"], oam["flags"])
+        assert np.array_equal(ares["numiter"], oam["numiter"])
+        assert np.allclose(ares["pars"], oam["pars"], rtol=1e-9, atol=1e-12)

@@ -107,17 +107,20 @@ def test_gpu_fit_batch_noise_images(ng):
     for i in range(recs.size):
         assert _rel(recs["pars_cov"][i][:36].reshape(6, 6),
                     g["exp_res_pars_cov"][i]) < 1e-3
-    # odd sizes / column padding: 5 x 7 kernel check against numpy's fft
+    # odd sizes / column padding (5 x 7) and a stamp larger than shared
+    # memory (110 x 106: staged planes in global scratch) against numpy's fft
     from ngmix_b200 import _lib
     rng = np.random.RandomState(3)
-    D = rng.normal(size=(2, 3, 35))
-    w = rng.uniform(0.5, 2.0, size=(2, 5, 7))
-    nz = rng.normal(size=(2, 5, 7))
-    B = _lib.noise_b(D, w, nz)
-    for i in range(2):
-        K = [np.fft.fft2(w[i] * D[i, a].reshape(5, 7)) for a in range(3)]
-        P = np.abs(np.fft.fft2(nz[i])) ** 2
-        for a in range(3):
-            for b in range(3):
-                want = np.sum(np.conj(K[a]) * K[b] * P).real / 35 ** 2
-                assert abs(B[i, a, b] - want) < 1e-10 * abs(want) + 1e-12
+    for (H, W), n, nk in (((5, 7), 2, 3), ((110, 106), 1, 2)):
+        D = rng.normal(size=(n, nk, H * W))
+        w = rng.uniform(0.5, 2.0, size=(n, H, W))
+        nz = rng.normal(size=(n, H, W))
+        B = _lib.noise_b(D, w, nz)
+        for i in range(n):
+            K = [np.fft.fft2(w[i] * D[i, a].reshape(H, W)) for a in range(nk)]
+            P = np.abs(np.fft.fft2(nz[i])) ** 2
+            for a in range(nk):
+                for b in range(nk):
+                    want = np.sum(np.conj(K[a]) * K[b] * P).real / (H * W) ** 2
+                    assert abs(B[i, a, b] - want) \
+                        < 1e-9 * abs(B[i, a, a] * B[i, b, b]) ** 0.5 + 1e-12
