@@ -59,7 +59,10 @@ def make_inputs(nobj, seed0, dims=DIMS, noise=0.01):
     assert not st.any()
     rng = np.random.RandomState(seed0 + 987654321 % (2 ** 31))
     images += rng.normal(0.0, noise, size=images.shape)
-    b["images"] = images
+    # pixel values as a survey stores them: float32-representable (so the
+    # float32 host path below sees exactly the same numbers)
+    b["images"] = images.astype(np.float32).astype(np.float64)
+    b["weights"] = b["weights"].astype(np.float32).astype(np.float64)
     return b
 
 
@@ -320,6 +323,30 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     assert np.array_equal(r_e2e["flags"], res["flags"])
+    # the same call with float32 host stamps (ngx_lm_fit_host_f32): the same
+    # pixel values, half the bytes over PCIe
+    h_images32 = pinned(b["images"].astype(np.float32))
+    h_weights32 = pinned(b["weights"].astype(np.float32))
+    assert np.array_equal(h_images32.numpy().astype(np.float64), b["images"])
+
+    def step_e2e32():
+        return _lib.lm_fit("exp", h_images32.numpy(), h_weights32.numpy(),
+                           h_jac.numpy(), h_psf.numpy(), h_guess.numpy(),
+                           out=e2e_out)
+
+    for _ in range(2):
+        step_e2e32()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r_e2e32 = step_e2e32()
+    torch.cuda.synchronize()
+    e2e32_s = time.perf_counter() - t0
+    t = torch.tensor([e2e32_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e32_s = float(t.item())
+    assert np.array_equal(r_e2e32["pars"], res["pars"], equal_nan=True)
     h2d = int(h_images.numel() * 8 * 2 + h_jac.numel() * 8
               + h_psf.numel() * 8 + h_guess.numel() * 8)
     d2h = int(nobj * _lib.LM_RESULT_DTYPE.itemsize)
@@ -400,6 +427,12 @@ def main():
                 "d2h_bytes_per_step": d2h,
                 "api": "ngmix_b200._lib.lm_fit -> ngx_lm_fit_host (pinned "
                        "host buffers, chunked H2D overlapped with the fit)"},
+        "e2e_f32_stamps": {
+            "value": world * nobj * args.steps / e2e32_s, "unit": "fits/s",
+            "h2d_bytes_per_step": int(h2d - h_images.numel() * 8),
+            "d2h_bytes_per_step": d2h,
+            "api": "ngx_lm_fit_host_f32: the same stamps held as float32 on "
+                   "the host (bit-identical results), widened on the device"},
         "gpu_launches": args.steps,   # k_lm_fit launches in the timed region
         "roofline": {
             "bound": "fp64", "achieved": achieved / 1e9,

@@ -388,6 +388,15 @@ int ngx_lm_fit_host(int n, int model, const double *images,
                     const double *guess, const ngx_prior *prior,
                     const ngx_lm_pars *lm_pars, int ignore_zero_weight,
                     ngx_lm_result *res);
+/* the same with the stamps as floats on the host (survey pixels are float32 on
+ * disk; the reference widens them in Observation.__init__): half the PCIe
+ * bytes of the call, widened exactly on the device */
+int ngx_lm_fit_host_f32(int n, int model, const float *images,
+                        const float *weights, const ngx_jacobian *jac,
+                        int nrow, int ncol, const double *psf_pars, int npsf,
+                        const double *guess, const ngx_prior *prior,
+                        const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                        ngx_lm_result *res);
 int ngx_em_host(int n, int variant, const double *images,
                 const double *weights, const ngx_jacobian *jac, int nrow,
                 int ncol, const double *guess, int ngauss,

@@ -104,6 +104,7 @@ SYMBOLS = [
     "ngx_lm_fit_multi", "ngx_lm_fit_multi_host",
     "ngx_template_flux", "ngx_template_flux_host",
     "ngx_noise_b", "ngx_noise_b_host", "ngx_noise_cov_host",
+    "ngx_lm_fit_host_f32",
 ]
 
 _lib = None
@@ -380,8 +381,16 @@ def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
     of pinned host memory, which lets the D2H copy run asynchronously).
     """
     init()
-    images = _f8(images)
-    weights = _f8(weights)
+    # float32 stamps (the dtype survey pixels have on disk) go through the
+    # f32 entry point: half the bytes over PCIe, widened on the device
+    f32 = getattr(images, "dtype", None) == np.float32 \
+        and getattr(weights, "dtype", None) == np.float32
+    if f32:
+        images = np.ascontiguousarray(images)
+        weights = np.ascontiguousarray(weights)
+    else:
+        images = _f8(images)
+        weights = _f8(weights)
     if images.ndim == 2:
         images, weights = images[None], weights[None]
     n, H, W = images.shape
@@ -402,7 +411,8 @@ def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
         res = out
         assert res.dtype == LM_RESULT_DTYPE and res.shape == (n,) \
             and res.flags.c_contiguous
-    check(lib().ngx_lm_fit_host(
+    entry = lib().ngx_lm_fit_host_f32 if f32 else lib().ngx_lm_fit_host
+    check(entry(
         C.c_int(n), C.c_int(MODELS[model]), _p(images), _p(weights), _p(jac),
         C.c_int(H), C.c_int(W), _p(psf_pars), C.c_int(npsf), _p(guess),
         C.byref(pr), C.byref(lmp), C.c_int(int(ignore_zero_weight)), _p(res)))

@@ -1486,6 +1486,8 @@ k_lm_fit_multi(LMArgs a) {
 static int *g_counter = nullptr;       // work-queue counter, one per process
 static int g_counter_dev = -1;
 
+static thread_local int g_counter_slot = 0;
+
 static int get_counter(int **out) {
     int dev = 0;
     NGX_CUDA(cudaGetDevice(&dev));
@@ -1493,7 +1495,9 @@ static int get_counter(int **out) {
         NGX_CUDA(cudaMalloc((void **)&g_counter, 64 * sizeof(int)));
         g_counter_dev = dev;
     }
-    *out = g_counter;
+    // 64 counters: launches that may overlap (the two compute streams of the
+    // host pipeline) use different slots
+    *out = g_counter + 16 * g_counter_slot;
     return NGX_OK;
 }
 
@@ -1501,6 +1505,18 @@ struct LMLaunch {
     int threads, blocks;
     size_t smem;
 };
+
+// float -> double, four elements per thread (the f32 host entry point)
+__global__ void k_widen(const float *__restrict__ in, double *__restrict__ out,
+                        size_t n) {
+    size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i + 3 < n && (((uintptr_t)(in + i)) & 15) == 0) {
+        float4 v = *(const float4 *)(in + i);
+        out[i] = v.x; out[i + 1] = v.y; out[i + 2] = v.z; out[i + 3] = v.w;
+    } else {
+        for (size_t k = i; k < n && k < i + 4; k++) out[k] = in[k];
+    }
+}
 
 // stamp_start = 0..n and stamp_band = 0 for n one-stamp objects
 __global__ void k_iota_zero(int n, int32_t *start, int32_t *band) {
@@ -1735,14 +1751,22 @@ int ngx_lm_fit_multi_host(int nobj, int model, const int32_t *stamp_start,
     return NGX_OK;
 }
 
-int ngx_lm_fit_host(int n, int model, const double *images,
-                    const double *weights, const ngx_jacobian *jac, int nrow,
-                    int ncol, const double *psf_pars, int npsf,
-                    const double *guess, const ngx_prior *prior,
-                    const ngx_lm_pars *lm_pars, int ignore_zero_weight,
-                    ngx_lm_result *res) {
-    NGX_REQUIRE(n >= 0 && images && weights && jac && guess && res);
+// the host-buffer pipeline behind ngx_lm_fit_host (stamps as doubles) and
+// ngx_lm_fit_host_f32 (stamps as floats: half the bytes over PCIe, which is
+// what bounds the call; widened to double on the device, exactly)
+static int lm_fit_host_impl(int n, int model, const void *images_v,
+                            const void *weights_v, int f32,
+                            const ngx_jacobian *jac, int nrow, int ncol,
+                            const double *psf_pars, int npsf,
+                            const double *guess, const ngx_prior *prior,
+                            const ngx_lm_pars *lm_pars,
+                            int ignore_zero_weight, ngx_lm_result *res) {
+    NGX_REQUIRE(n >= 0 && images_v && weights_v && jac && guess && res);
     if (n == 0) return NGX_OK;
+    const double *images = (const double *)images_v;
+    const double *weights = (const double *)weights_v;
+    const float *images32 = (const float *)images_v;
+    const float *weights32 = (const float *)weights_v;
     int np = model_npars(model);
     NGX_REQUIRE(np > 0);
     // chunked, double-buffered pipeline: H2D of chunk i+1 overlaps the fit
@@ -1763,12 +1787,19 @@ int ngx_lm_fit_host(int n, int model, const double *images,
     static thread_local double *d_guess[2] = {nullptr, nullptr};
     static thread_local ngx_lm_result *d_res[2] = {nullptr, nullptr};
     static thread_local size_t cap_pix = 0, cap_obj = 0, cap_psf = 0;
+    static thread_local float *d_im32[2] = {nullptr, nullptr};
+    static thread_local float *d_wt32[2] = {nullptr, nullptr};
+    static thread_local size_t cap_pix32 = 0;
     static thread_local ngx_lm_result *h_stage = nullptr;   // pinned
     static thread_local size_t cap_stage = 0;
-    static thread_local cudaStream_t streams[2] = {nullptr, nullptr};
+    // streams[1] copies in; the fits of even / odd chunks run on streams[0] /
+    // streams[2] with their own work-queue counters, so the next chunk's CTAs
+    // fill the tail of the previous chunk's launch
+    static thread_local cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     if (!streams[0]) {
         NGX_CUDA(cudaStreamCreate(&streams[0]));
         NGX_CUDA(cudaStreamCreate(&streams[1]));
+        NGX_CUDA(cudaStreamCreate(&streams[2]));
     }
     size_t need_pix = (size_t)chunk * ntot, need_obj = chunk;
     size_t need_psf = (size_t)chunk * 6 * (npsf > 0 ? npsf : 1);
@@ -1790,6 +1821,15 @@ int ngx_lm_fit_host(int n, int model, const double *images,
         }
         cap_pix = need_pix; cap_obj = need_obj; cap_psf = need_psf;
     }
+    if (f32 && need_pix > cap_pix32) {
+        NGX_CUDA(cudaDeviceSynchronize());
+        for (int b = 0; b < 2; b++) {
+            cudaFree(d_im32[b]); cudaFree(d_wt32[b]);
+            NGX_CUDA(cudaMalloc((void **)&d_im32[b], need_pix * sizeof(float)));
+            NGX_CUDA(cudaMalloc((void **)&d_wt32[b], need_pix * sizeof(float)));
+        }
+        cap_pix32 = need_pix;
+    }
     // results: device -> pinned memory asynchronously.  If the caller's
     // array is itself pinned it is the target, else a pinned staging buffer
     // is copied out by the host while the next chunk runs.
@@ -1804,8 +1844,6 @@ int ngx_lm_fit_host(int n, int model, const double *images,
         cap_stage = n;
     }
     ngx_lm_result *res_dst = res_pinned ? res : h_stage;
-    // the work-queue counter is shared by launches: serialise the kernels on
-    // one stream (streams[0]) and use streams[1] only for copies
     cudaEvent_t up[2], done[2];
     for (int b = 0; b < 2; b++) {
         NGX_CUDA(cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming));
@@ -1817,14 +1855,24 @@ int ngx_lm_fit_host(int n, int model, const double *images,
         int lo = c == 0 ? 0 : first_chunk + (c - 1) * chunk;
         int cn = c == 0 ? first_chunk : (n - lo < chunk ? n - lo : chunk);
         // buffer b is free once the kernel of chunk c-2 has finished and its
-        // results were copied out (both on streams[0])
+        // results were copied out (both on this buffer's compute stream)
+        cudaStream_t ks = streams[b ? 2 : 0];
         NGX_CUDA(cudaStreamWaitEvent(streams[1], done[b], 0));
-        NGX_CUDA(cudaMemcpyAsync(d_im[b], images + lo * ntot,
-                                 cn * ntot * sizeof(double),
-                                 cudaMemcpyHostToDevice, streams[1]));
-        NGX_CUDA(cudaMemcpyAsync(d_wt[b], weights + lo * ntot,
-                                 cn * ntot * sizeof(double),
-                                 cudaMemcpyHostToDevice, streams[1]));
+        if (f32) {
+            NGX_CUDA(cudaMemcpyAsync(d_im32[b], images32 + lo * ntot,
+                                     cn * ntot * sizeof(float),
+                                     cudaMemcpyHostToDevice, streams[1]));
+            NGX_CUDA(cudaMemcpyAsync(d_wt32[b], weights32 + lo * ntot,
+                                     cn * ntot * sizeof(float),
+                                     cudaMemcpyHostToDevice, streams[1]));
+        } else {
+            NGX_CUDA(cudaMemcpyAsync(d_im[b], images + lo * ntot,
+                                     cn * ntot * sizeof(double),
+                                     cudaMemcpyHostToDevice, streams[1]));
+            NGX_CUDA(cudaMemcpyAsync(d_wt[b], weights + lo * ntot,
+                                     cn * ntot * sizeof(double),
+                                     cudaMemcpyHostToDevice, streams[1]));
+        }
         NGX_CUDA(cudaMemcpyAsync(d_jac[b], jac + lo,
                                  cn * sizeof(ngx_jacobian),
                                  cudaMemcpyHostToDevice, streams[1]));
@@ -1837,16 +1885,24 @@ int ngx_lm_fit_host(int n, int model, const double *images,
                                  (size_t)cn * np * sizeof(double),
                                  cudaMemcpyHostToDevice, streams[1]));
         NGX_CUDA(cudaEventRecord(up[b], streams[1]));
-        NGX_CUDA(cudaStreamWaitEvent(streams[0], up[b], 0));
+        NGX_CUDA(cudaStreamWaitEvent(ks, up[b], 0));
+        if (f32) {
+            const size_t cnt = (size_t)cn * ntot;
+            const int blocks = (int)((cnt / 4 + 255) / 256) + 1;
+            k_widen<<<blocks, 256, 0, ks>>>(d_im32[b], d_im[b], cnt);
+            k_widen<<<blocks, 256, 0, ks>>>(d_wt32[b], d_wt[b], cnt);
+            NGX_LAUNCH_CHECK();
+        }
+        g_counter_slot = 1 + b;
         int rc = ngx_lm_fit(cn, model, d_im[b], d_wt[b], d_jac[b], nrow, ncol,
                             npsf > 0 ? d_psf[b] : nullptr, npsf, d_guess[b],
-                            prior, lm_pars, ignore_zero_weight, d_res[b],
-                            streams[0]);
+                            prior, lm_pars, ignore_zero_weight, d_res[b], ks);
+        g_counter_slot = 0;
         if (rc) return rc;
         NGX_CUDA(cudaMemcpyAsync(res_dst + lo, d_res[b],
                                  cn * sizeof(ngx_lm_result),
-                                 cudaMemcpyDeviceToHost, streams[0]));
-        NGX_CUDA(cudaEventRecord(done[b], streams[0]));
+                                 cudaMemcpyDeviceToHost, ks));
+        NGX_CUDA(cudaEventRecord(done[b], ks));
         if (!res_pinned && c > 0) {
             // chunk c-1 is complete once its event fires; chunk c is queued
             int pb = (c - 1) & 1;
@@ -1856,6 +1912,7 @@ int ngx_lm_fit_host(int n, int model, const double *images,
         }
     }
     NGX_CUDA(cudaStreamSynchronize(streams[0]));
+    NGX_CUDA(cudaStreamSynchronize(streams[2]));
     NGX_CUDA(cudaStreamSynchronize(streams[1]));
     if (!res_pinned) {
         int plo = nchunks == 1 ? 0 : first_chunk + (nchunks - 2) * chunk;
@@ -1866,6 +1923,28 @@ int ngx_lm_fit_host(int n, int model, const double *images,
         cudaEventDestroy(done[b]);
     }
     return NGX_OK;
+}
+
+int ngx_lm_fit_host(int n, int model, const double *images,
+                    const double *weights, const ngx_jacobian *jac, int nrow,
+                    int ncol, const double *psf_pars, int npsf,
+                    const double *guess, const ngx_prior *prior,
+                    const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                    ngx_lm_result *res) {
+    return lm_fit_host_impl(n, model, images, weights, 0, jac, nrow, ncol,
+                            psf_pars, npsf, guess, prior, lm_pars,
+                            ignore_zero_weight, res);
+}
+
+int ngx_lm_fit_host_f32(int n, int model, const float *images,
+                        const float *weights, const ngx_jacobian *jac,
+                        int nrow, int ncol, const double *psf_pars, int npsf,
+                        const double *guess, const ngx_prior *prior,
+                        const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                        ngx_lm_result *res) {
+    return lm_fit_host_impl(n, model, images, weights, 1, jac, nrow, ncol,
+                            psf_pars, npsf, guess, prior, lm_pars,
+                            ignore_zero_weight, res);
 }
 
 }  // extern "C"

@@ -150,3 +150,25 @@ def test_run_fit_batch_retries_only_failures(ngx):
                         b["guess"])
     assert not recs["flags"].any()
     assert np.array_equal(recs["pars"], want["pars"])
+
+
+def test_lm_fit_float32_host_stamps(ngx):
+    """float32 host stamps (ngx_lm_fit_host_f32) are widened exactly: the
+    records equal those of the float64 call on the same values, over several
+    pipeline chunks and an odd pixel count"""
+    from ngmix_b200 import sims
+    b = sims.make_lm_batch(1500, seed0=6200, noise=0.05, dims=(21, 23),
+                           truth_images=False)
+    rng = np.random.RandomState(4)
+    gm0, _ = ngx.gmix_fill("exp", b["truth"])
+    gp, _ = ngx.gmix_fill("full", b["psf"].reshape(1500, -1))
+    images, _ = ngx.render(ngx.gmix_convolve(gm0, gp), b["jac"], (21, 23))
+    images += rng.normal(0.0, 0.05, images.shape)
+    im32 = images.astype(np.float32)
+    wt32 = b["weights"].astype(np.float32)
+    wt32[:, 3, 4:7] = 0.0
+    r64 = ngx.lm_fit("exp", im32.astype(np.float64), wt32.astype(np.float64),
+                     b["jac"], b["psf"], b["guess"])
+    r32 = ngx.lm_fit("exp", im32, wt32, b["jac"], b["psf"], b["guess"])
+    _same_records(r32, r64)
+    assert (r32["flags"] == 0).sum() > 1400
