@@ -157,7 +157,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count()
-    nsample = min(NOBJ, 64 * cores)
+    nsample = min(NOBJ, 256 * cores)     # ~0.5 s of CPU work per step
     b = make_inputs_host(nsample, seed0=0)
     times = []
     sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -188,6 +188,10 @@ int ngx_noise_b(int n, int nk, const int32_t *rows, const double *dimages,
 #define NGX_P_FLAT 1      /* a=minval b=maxval */
 #define NGX_P_ERF 2       /* a=minval b=width_at_min c=maxval d=width_at_max */
 #define NGX_P_NORMAL 3    /* a=mean b=sigma */
+#define NGX_P_LOGNORMAL 4 /* a=logmean b=logivar c=lnprob_max d=shift
+                           * (priors/priors.py:674-840) */
+#define NGX_P_TRUNCGAUSS 5 /* a=mean b=sigma c=minval d=maxval
+                            * (priors/priors.py:1046-1150) */
 typedef struct { int32_t kind; int32_t pad; double a, b, c, d; } ngx_prior1d;
 typedef struct {
     int32_t present;      /* 0 = fit without prior */

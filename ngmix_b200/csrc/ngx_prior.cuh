@@ -36,6 +36,22 @@ __device__ __noinline__ int prior1d_lnprob(const ngx_prior1d &p, double val,
         *lnp = -0.5 * diff * diff * s2inv;
         return NGX_ST_OK;
     }
+    case NGX_P_LOGNORMAL: {
+        double v = val - p.d;
+        if (v <= 0.0) return NGX_ST_RANGE_ERROR;
+        double logval = log(v);
+        double dl = logval - p.a;
+        double chi2 = p.b * (dl * dl);
+        *lnp = -0.5 * chi2 - logval - p.c;
+        return NGX_ST_OK;
+    }
+    case NGX_P_TRUNCGAUSS: {
+        if (val < p.c || val > p.d) return NGX_ST_RANGE_ERROR;
+        double ivar = 1.0 / (p.b * p.b);
+        double diff = val - p.a;
+        *lnp = -0.5 * diff * diff * ivar;
+        return NGX_ST_OK;
+    }
     default:
         *lnp = 0.0;
         return NGX_ST_OK;
@@ -47,6 +63,11 @@ __device__ inline int prior1d_fdiff(const ngx_prior1d &p, double val,
     if (p.kind == NGX_P_NORMAL) {
         double sinv = 1.0 / p.b;
         *fd = (val - p.a) * sinv;
+        return NGX_ST_OK;
+    }
+    if (p.kind == NGX_P_TRUNCGAUSS) {
+        if (val < p.c || val > p.d) return NGX_ST_RANGE_ERROR;
+        *fd = (val - p.a) * (1.0 / p.b);
         return NGX_ST_OK;
     }
     double lnp;

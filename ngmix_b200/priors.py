@@ -137,6 +137,95 @@ class Normal(PriorBase):
         return _lib.Prior1D(3, 0, self.mean, self.sigma, 0.0, 0.0)
 
 
+class LogNormal(PriorBase):
+    """log-normal prior in terms of the mean and sigma of the distribution,
+    peak ln(prob) = 0, optional shift (priors/priors.py:674-863)"""
+
+    def __init__(self, mean, sigma, rng=None, shift=None):
+        super().__init__(rng=rng)
+        if mean <= 0:
+            raise ValueError("mean %s is < 0" % mean)
+        self.shift = shift
+        self.mean = mean
+        self.sigma = sigma
+        self.logvar = np.log(1 + sigma ** 2 / mean ** 2)
+        self.logmean = np.log(mean) - 0.5 * self.logvar
+        self.logsigma = np.sqrt(self.logvar)
+        self.logivar = 1.0 / self.logvar
+        self.log_mode = self.logmean - self.logvar
+        self.mode = np.exp(self.log_mode)
+        chi2 = self.logivar * (self.log_mode - self.logmean) ** 2
+        self.lnprob_max = -0.5 * chi2 - self.log_mode
+
+    def get_lnprob_scalar(self, val):
+        if self.shift is not None:
+            val = val - self.shift
+        if val <= 0:
+            raise GMixRangeError("values of val must be > 0")
+        logval = np.log(val)
+        chi2 = self.logivar * (logval - self.logmean) ** 2
+        return -0.5 * chi2 - logval - self.lnprob_max
+
+    def get_prob_scalar(self, val):
+        return np.exp(self.get_lnprob_scalar(val))
+
+    def get_fdiff(self, val):
+        return np.sqrt(max(-2 * self.get_lnprob_scalar(val), 0.0))
+
+    def sample(self, nrand=None):
+        r = np.exp(self.logmean + self.logsigma * self.rng.normal(size=nrand))
+        return r if self.shift is None else r + self.shift
+
+    def _ngx(self):
+        return _lib.Prior1D(4, 0, self.logmean, self.logivar, self.lnprob_max,
+                            0.0 if self.shift is None else self.shift)
+
+
+class TruncatedGaussian(PriorBase):
+    """gaussian restricted to [minval, maxval]; outside raises
+    GMixRangeError (priors/priors.py:1046-1150)"""
+
+    def __init__(self, mean, sigma, minval, maxval, rng=None):
+        super().__init__(rng=rng)
+        self.mean = mean
+        self.sigma = sigma
+        self.ivar = 1.0 / sigma ** 2
+        self.sinv = 1.0 / sigma
+        self.minval = minval
+        self.maxval = maxval
+
+    def _check(self, val):
+        if val < self.minval or val > self.maxval:
+            raise GMixRangeError("value out of range")
+
+    def get_lnprob_scalar(self, val):
+        self._check(val)
+        diff = val - self.mean
+        return -0.5 * diff * diff * self.ivar
+
+    def get_fdiff(self, val):
+        self._check(val)
+        return (val - self.mean) * self.sinv
+
+    def sample(self, nrand=None):
+        """normal draws, keeping those strictly inside the range, in rounds
+        of the number still missing (priors/priors.py:1128-1150)"""
+        n = 1 if nrand is None else nrand
+        out = np.zeros(n)
+        have = 0
+        while have < n:
+            t = self.rng.normal(loc=self.mean, scale=self.sigma,
+                                size=n - have)
+            keep = t[(t > self.minval) & (t < self.maxval)]
+            out[have:have + keep.size] = keep
+            have += keep.size
+        return out[0] if nrand is None else out
+
+    def _ngx(self):
+        return _lib.Prior1D(5, 0, self.mean, self.sigma, self.minval,
+                            self.maxval)
+
+
 class CenPrior(PriorBase):
     """independent gaussians on the two centre coordinates"""
 

@@ -298,6 +298,12 @@ def _get_priors(kind, rng):
     elif kind == "erf":
         T = priors.TwoSidedErf(-1.0, 0.1, 1.0e3, 1.0, rng=rng)
         F = priors.TwoSidedErf(-1.0e2, 1.0, 1.0e9, 1.0e8, rng=rng)
+    elif kind == "lognormal":
+        T = priors.LogNormal(0.5, 0.3, rng=rng)
+        F = priors.LogNormal(100.0, 50.0, rng=rng, shift=-5.0)
+    elif kind == "trunc":
+        T = priors.TruncatedGaussian(0.5, 0.4, 0.0, 5.0, rng=rng)
+        F = priors.LogNormal(100.0, 50.0, rng=rng)
     else:
         raise ValueError(kind)
     return joint_prior.PriorSimpleSep(cen, g, T, F)
@@ -777,6 +783,57 @@ def gen_shape_moments():
     save("shape_moments", **out)
 
 
+def gen_lm_priors2():
+    """LogNormal and TruncatedGaussian priors: low-S/N exp fits where the
+    priors shape the solution, and bdf fits with a truncated fracdev prior"""
+    from ngmix import priors, joint_prior
+    from ngmix.fitting import Fitter
+    out = {}
+    b = sims.make_lm_batch(10, seed0=17000, noise=1.0, dims=(32, 32))
+    for k in ("images", "weights", "jac", "psf", "guess"):
+        out["exp_" + k] = b[k]
+    for pk in ("lognormal", "trunc"):
+        r = _run_lm_set(b, pk)
+        print(pk, "flags", r["flags"], "nfev", r["nfev"])
+        for k, v in r.items():
+            out["exp_%s_%s" % (pk, k)] = v
+    b = sims.make_bdf_batch(4, seed0=17100, dims=(40, 40), noise=0.05)
+    rng = np.random.RandomState(7)
+    prior = joint_prior.PriorBDFSep(
+        cen_prior=priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng),
+        g_prior=priors.GPriorBA(0.3, rng=rng),
+        T_prior=priors.LogNormal(0.5, 0.3, rng=rng),
+        fracdev_prior=priors.TruncatedGaussian(0.5, 0.1, 0.0, 1.0, rng=rng),
+        F_prior=priors.LogNormal(100.0, 50.0, rng=rng))
+    for k in ("images", "weights", "jac", "psf", "guess"):
+        out["bdf_" + k] = b[k]
+    n = b["images"].shape[0]
+    res = dict(flags=np.zeros(n, "i4"), nfev=np.zeros(n, "i4"),
+               ier=np.zeros(n, "i4"), pars=np.zeros((n, 7)),
+               pars_err=np.zeros((n, 7)), lnprob=np.zeros(n))
+    fitter = Fitter(model="bdf", prior=prior)
+    for i in range(n):
+        psf_obs = ngmix.Observation(
+            np.ones((5, 5)),
+            jacobian=ngmix.DiagonalJacobian(row=2, col=2, scale=0.263),
+            gmix=ngmix.GMix(pars=b["psf"][i].ravel()))
+        obs = ngmix.Observation(b["images"][i], weight=b["weights"][i],
+                                jacobian=jac_from_record(b["jac"][i]),
+                                psf=psf_obs)
+        r = fitter.go(obs, b["guess"][i].copy())
+        res["flags"][i] = r["flags"]
+        res["nfev"][i] = r["nfev"]
+        res["ier"][i] = r["ier"]
+        res["pars"][i] = r["pars"]
+        if r["flags"] == 0:
+            res["pars_err"][i] = r["pars_err"]
+            res["lnprob"][i] = r["lnprob"]
+    print("bdf flags", res["flags"], "nfev", res["nfev"])
+    for k, v in res.items():
+        out["bdf_res_" + k] = v
+    save("lm_priors2", **out)
+
+
 def gen_moments():
     """GaussMom (6 and 17 moments) on galaxy stamps, and get_weighted_sums
     with a two-gaussian off-centre weight and a maxrad"""
@@ -1088,6 +1145,7 @@ GENERATORS = {
     "guessers": gen_guessers,
     "noise_cov": gen_noise_cov,
     "shape_moments": gen_shape_moments,
+    "lm_priors2": gen_lm_priors2,
     "moments": gen_moments,
     "lm_multi": gen_lm_multi,
     "psfflux": gen_psfflux,

@@ -54,6 +54,25 @@ static int prior1d_lnprob(const ora_prior1d *p, double val, double *lnp) {
         *lnp = -0.5 * diff * diff * s2inv;
         return ORA_OK;
     }
+    case ORA_P_LOGNORMAL: {
+        /* LogNormal.get_lnprob_scalar, priors/priors.py:741-765:
+         * a=logmean b=logivar c=lnprob_max d=shift */
+        double v = val - p->d;
+        if (v <= 0.0) return ORA_RANGE_ERROR;
+        double logval = log(v);
+        double chi2 = p->b * ((logval - p->a) * (logval - p->a));
+        *lnp = -0.5 * chi2 - logval - p->c;
+        return ORA_OK;
+    }
+    case ORA_P_TRUNCGAUSS: {
+        /* TruncatedGaussian.get_lnprob_scalar, priors/priors.py:1080-1094:
+         * a=mean b=sigma c=minval d=maxval */
+        if (val < p->c || val > p->d) return ORA_RANGE_ERROR;
+        double ivar = 1.0 / (p->b * p->b);
+        double diff = val - p->a;
+        *lnp = -0.5 * diff * diff * ivar;
+        return ORA_OK;
+    }
     default:
         *lnp = 0.0;
         return ORA_OK;
@@ -66,6 +85,12 @@ static int prior1d_fdiff(const ora_prior1d *p, double val, double *fd) {
     if (p->kind == ORA_P_NORMAL) {
         double sinv = 1.0 / p->b;
         *fd = (val - p->a) * sinv;
+        return ORA_OK;
+    }
+    if (p->kind == ORA_P_TRUNCGAUSS) {
+        /* TruncatedGaussian.get_fdiff, priors/priors.py:1115-1126 */
+        if (val < p->c || val > p->d) return ORA_RANGE_ERROR;
+        *fd = (val - p->a) * (1.0 / p->b);
         return ORA_OK;
     }
     double lnp;

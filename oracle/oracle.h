@@ -97,7 +97,8 @@ void ora_deriv_images(const double *gpars, const double *dcov, int ngauss,
                       int npix, double *out);
 
 /* ---- priors for the LM residual vector ---- */
-enum { ORA_P_NONE = 0, ORA_P_FLAT = 1, ORA_P_ERF = 2, ORA_P_NORMAL = 3 };
+enum { ORA_P_NONE = 0, ORA_P_FLAT = 1, ORA_P_ERF = 2, ORA_P_NORMAL = 3,
+       ORA_P_LOGNORMAL = 4, ORA_P_TRUNCGAUSS = 5 };
 typedef struct { int32_t kind; int32_t pad; double a, b, c, d; } ora_prior1d;
 typedef struct {
     int32_t present;       /* 0: no prior */

@@ -241,6 +241,16 @@ def deriv_images(gpars, dcov, vv, uu, area):
 
 
 # ------------------------------------------------------------------ priors
+def _lognormal(mean, sigma, shift=0.0):
+    """LogNormal(mean, sigma, shift) -> (logmean, logivar, lnprob_max,
+    shift), priors/priors.py:688-716"""
+    logvar = np.log(1 + sigma ** 2 / mean ** 2)
+    logmean = np.log(mean) - 0.5 * logvar
+    log_mode = logmean - logvar
+    chi2 = (1.0 / logvar) * (log_mode - logmean) ** 2
+    return Prior1D(4, 0, logmean, 1.0 / logvar, -0.5 * chi2 - log_mode, shift)
+
+
 def make_prior(kind, model="exp"):
     """the prior sets of the golden fixtures (gen_golden._get_priors)"""
     pr = Prior()
@@ -261,6 +271,16 @@ def make_prior(kind, model="exp"):
         pr.T = Prior1D(1, 0, -1.0, 1.0e3, 0, 0)
         pr.fracdev = Prior1D(3, 0, 0.5, 0.1, 0, 0)
         pr.F = Prior1D(1, 0, -100.0, 1.0e9, 0, 0)
+    elif kind == "lognormal":
+        pr.T = _lognormal(0.5, 0.3)
+        pr.F = _lognormal(100.0, 50.0, shift=-5.0)
+    elif kind == "trunc":
+        pr.T = Prior1D(5, 0, 0.5, 0.4, 0.0, 5.0)
+        pr.F = _lognormal(100.0, 50.0)
+    elif kind == "bdf2":
+        pr.T = _lognormal(0.5, 0.3)
+        pr.fracdev = Prior1D(5, 0, 0.5, 0.1, 0.0, 1.0)
+        pr.F = _lognormal(100.0, 50.0)
     elif kind == "bd":
         pr.T = Prior1D(1, 0, -1.0, 1.0e3, 0, 0)
         pr.logTratio = Prior1D(3, 0, 0.0, 0.5, 0, 0)

@@ -300,6 +300,56 @@ def test_fitmodel_calc_fdiff_and_jacobian(ng):
             assert not fm.calc_jacobian(zero).any()
 
 
+def test_fit_batch_lognormal_and_truncated_priors(ng):
+    """LogNormal / TruncatedGaussian priors through the Python prior classes
+    (to_ngx) against the reference's fits"""
+    g = load_golden("lm_priors2")
+    pr = ng.priors
+    cen, gp = pr.CenPrior(0.0, 0.0, 0.263, 0.263), pr.GPriorBA(0.3)
+    sets = {
+        "lognormal": pr.PriorSimpleSep(
+            cen, gp, pr.LogNormal(0.5, 0.3),
+            pr.LogNormal(100.0, 50.0, shift=-5.0)),
+        "trunc": pr.PriorSimpleSep(
+            cen, gp, pr.TruncatedGaussian(0.5, 0.4, 0.0, 5.0),
+            pr.LogNormal(100.0, 50.0)),
+    }
+    for pk, prior in sets.items():
+        recs = ng.fit_batch("exp", g["exp_images"], g["exp_weights"],
+                            g["exp_jac"], g["exp_psf"], g["exp_guess"],
+                            prior=prior)
+        pre = "exp_%s_" % pk
+        assert np.array_equal(recs["flags"], g[pre + "flags"])
+        assert np.array_equal(recs["nfev"], g[pre + "nfev"])
+        assert np.array_equal(recs["ier"], g[pre + "ier"])
+        err = g[pre + "pars_err"]
+        assert np.all(np.abs(recs["pars"][:, :6] - g[pre + "pars"])
+                      <= 1e-3 * err)
+        assert np.allclose(recs["lnprob"], g[pre + "lnprob"], rtol=1e-6)
+        # host-side rows equal the kernel's convention
+        fd = np.zeros(6)
+        assert prior.fill_fdiff(g[pre + "pars"][0], fd) == 5
+    prior = ng.joint_prior.PriorBDFSep(
+        cen, gp, pr.LogNormal(0.5, 0.3),
+        pr.TruncatedGaussian(0.5, 0.1, 0.0, 1.0), pr.LogNormal(100.0, 50.0))
+    recs = ng.fit_batch("bdf", g["bdf_images"], g["bdf_weights"],
+                        g["bdf_jac"], g["bdf_psf"], g["bdf_guess"],
+                        prior=prior)
+    assert np.array_equal(recs["flags"], g["bdf_res_flags"])
+    assert np.array_equal(recs["nfev"], g["bdf_res_nfev"])
+    assert np.all(np.abs(recs["pars"][:, :7] - g["bdf_res_pars"])
+                  <= 1e-2 * g["bdf_res_pars_err"])
+    assert np.allclose(recs["lnprob"], g["bdf_res_lnprob"], rtol=1e-6)
+    # draws of the new priors follow the reference's recipe
+    rng = np.random.RandomState(3)
+    t = pr.TruncatedGaussian(0.5, 0.4, 0.0, 5.0, rng=rng).sample(100)
+    assert t.min() > 0.0 and t.max() < 5.0
+    z = pr.LogNormal(2.0, 0.5, rng=np.random.RandomState(3)).sample(5)
+    z0 = np.random.RandomState(3).normal(size=5)
+    lv = np.log(1 + 0.25 / 4.0)
+    assert np.allclose(z, np.exp(np.log(2.0) - 0.5 * lv + np.sqrt(lv) * z0))
+
+
 def test_em_appendix_b(ng):
     jac = ng.DiagonalJacobian(row=12, col=12, scale=0.263)
     truth = ng.GMix(pars=[60, -0.3, 0.2, 0.12, 0.01, 0.15,

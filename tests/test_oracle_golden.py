@@ -261,6 +261,40 @@ def test_lm_bd(ora, pk):
         assert r["dof"] == g[pk + "_dof"][i]
 
 
+@pytest.mark.parametrize("pk", ["lognormal", "trunc"])
+def test_lm_lognormal_truncated_priors(ora, pk):
+    """LogNormal / TruncatedGaussian T and flux priors on low-S/N exp fits"""
+    g = load_golden("lm_priors2")
+    prior = ora.make_prior(pk)
+    for i in range(g["exp_images"].shape[0]):
+        r = ora.lm_fit("exp", g["exp_images"][i], g["exp_weights"][i],
+                       g["exp_jac"][i], g["exp_psf"][i], g["exp_guess"][i],
+                       prior=prior)
+        pre = "exp_%s_" % pk
+        assert r["flags"] == g[pre + "flags"][i]
+        assert r["nfev"] == g[pre + "nfev"][i]
+        assert r["ier"] == g[pre + "ier"][i]
+        err = g[pre + "pars_err"][i]
+        assert np.all(np.abs(r["pars"][:6] - g[pre + "pars"][i])
+                      <= 1e-5 * err)
+        assert relerr(r["lnprob"], g[pre + "lnprob"][i]) < 1e-8
+
+
+def test_lm_bdf_truncated_fracdev(ora):
+    g = load_golden("lm_priors2")
+    prior = ora.make_prior("bdf2")
+    for i in range(g["bdf_images"].shape[0]):
+        r = ora.lm_fit("bdf", g["bdf_images"][i], g["bdf_weights"][i],
+                       g["bdf_jac"][i], g["bdf_psf"][i], g["bdf_guess"][i],
+                       prior=prior)
+        assert r["flags"] == g["bdf_res_flags"][i]
+        assert r["nfev"] == g["bdf_res_nfev"][i]
+        err = g["bdf_res_pars_err"][i]
+        assert np.all(np.abs(r["pars"][:7] - g["bdf_res_pars"][i])
+                      <= 1e-4 * err)
+        assert relerr(r["lnprob"], g["bdf_res_lnprob"][i]) < 1e-7
+
+
 # ------------------------------------------------------------------ EM
 def test_em(ora):
     g = load_golden("em_admom")
