@@ -205,6 +205,7 @@ typedef struct {
     int32_t pad;
     ngx_prior1d F_more[2];    /* flux priors of bands 1 and 2 */
     ngx_prior1d logTratio;    /* bd only: PriorBDSep, joint_prior.py:267-399 */
+    ngx_prior1d F_extra[4];   /* flux priors of bands 3..6 (nband up to 7) */
 } ngx_prior;
 
 /* DEFAULT_LM_PARS, ngmix/defaults.py:17 */
@@ -223,6 +224,15 @@ typedef struct {
         flux_err;
     double pars[8], pars_err[8], pars_cov0[64], pars_cov[64];
 } ngx_lm_result;
+
+/* the same record with room for 12 parameters: multi-band fits with 4 to 7
+ * bands (ngx_lm_fit_multi_wide) */
+typedef struct {
+    int32_t flags, nfev, ier, npix, dof, njev;
+    double lnprob, s2n_numer, s2n_denom, chi2per, s2n, T, T_err, flux,
+        flux_err;
+    double pars[12], pars_err[12], pars_cov0[144], pars_cov[144];
+} ngx_lm_result_wide;
 
 /* Fitter(model, prior, fit_pars).go(obs, guess) for n stamps
  * (fitting/fitters.py:64-112): FitModel.calc_fdiff/calc_jacobian
@@ -254,6 +264,15 @@ int ngx_lm_fit_multi(int nobj, int model, const int32_t *stamp_start,
                      const double *psf_pars, int npsf, const double *guess,
                      const ngx_prior *prior, const ngx_lm_pars *lm_pars,
                      int ignore_zero_weight, ngx_lm_result *res, void *stream);
+/* the same for 4 to 7 bands (up to 12 parameters, 12-slot records); 1 to 3
+ * bands are accepted too */
+int ngx_lm_fit_multi_wide(int nobj, int model, const int32_t *stamp_start,
+                     const int32_t *stamp_band, int nband,
+                     const double *images, const double *weights,
+                     const ngx_jacobian *jac, int nrow, int ncol,
+                     const double *psf_pars, int npsf, const double *guess,
+                     const ngx_prior *prior, const ngx_lm_pars *lm_pars,
+                     int ignore_zero_weight, ngx_lm_result_wide *res, void *stream);
 
 /* EM: EMFitter*.go (em/em.py:228-317) = prep_image (:95-120) + em_run /
  * em_run_fixcen / em_run_fixcov / em_run_fluxonly (em/em_nb.py:15-1257) */
@@ -428,6 +447,14 @@ int ngx_lm_fit_multi_host(int nobj, int model, const int32_t *stamp_start,
                           const double *guess, const ngx_prior *prior,
                           const ngx_lm_pars *lm_pars, int ignore_zero_weight,
                           ngx_lm_result *res);
+int ngx_lm_fit_multi_wide_host(int nobj, int model, const int32_t *stamp_start,
+                          const int32_t *stamp_band, int nband,
+                          const double *images, const double *weights,
+                          const ngx_jacobian *jac, int nrow, int ncol,
+                          const double *psf_pars, int npsf,
+                          const double *guess, const ngx_prior *prior,
+                          const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                          ngx_lm_result_wide *res);
 
 /* FP64 pipe micro-benchmark used for the roofline denominator: runs a
  * register-resident chain of `iters` x 8 independent DFMAs per thread on a

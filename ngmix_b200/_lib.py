@@ -39,6 +39,11 @@ LM_RESULT_DTYPE = np.dtype([
     ("s2n_denom", "f8"), ("chi2per", "f8"), ("s2n", "f8"), ("T", "f8"),
     ("T_err", "f8"), ("flux", "f8"), ("flux_err", "f8"), ("pars", "f8", 8),
     ("pars_err", "f8", 8), ("pars_cov0", "f8", 64), ("pars_cov", "f8", 64)])
+# ngx_lm_result_wide: the same record with 12 parameter slots (4-7 bands)
+LM_RESULT_WIDE_DTYPE = np.dtype(
+    [(n, LM_RESULT_DTYPE.fields[n][0]) for n in LM_RESULT_DTYPE.names[:15]]
+    + [("pars", "f8", 12), ("pars_err", "f8", 12), ("pars_cov0", "f8", 144),
+       ("pars_cov", "f8", 144)])
 EM_RESULT_DTYPE = np.dtype([("flags", "i4"), ("numiter", "i4"),
                             ("fdiff", "f8"), ("sky", "f8")])
 ADMOM_RESULT_DTYPE = np.dtype([
@@ -68,7 +73,8 @@ class Prior(C.Structure):
                 ("g_sigma", C.c_double), ("T", Prior1D),
                 ("fracdev", Prior1D), ("F", Prior1D),
                 ("nband", C.c_int32), ("pad", C.c_int32),
-                ("F_more", Prior1D * 2), ("logTratio", Prior1D)]
+                ("F_more", Prior1D * 2), ("logTratio", Prior1D),
+                ("F_extra", Prior1D * 4)]
 
 
 class LMPars(C.Structure):
@@ -105,6 +111,7 @@ SYMBOLS = [
     "ngx_template_flux", "ngx_template_flux_host",
     "ngx_noise_b", "ngx_noise_b_host", "ngx_noise_cov_host",
     "ngx_lm_fit_host_f32",
+    "ngx_lm_fit_multi_wide", "ngx_lm_fit_multi_wide_host",
 ]
 
 _lib = None
@@ -426,7 +433,8 @@ def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
     Fitter.go on ObsList / MultiBandObsList input for a batch of objects:
     object i owns stamps stamp_start[i]:stamp_start[i+1] of images/weights
     [ns,H,W] (ordered band by band), stamp_band [ns]; guess [nobj, 5+nband].
-    Returns LM_RESULT_DTYPE [nobj].
+    Returns LM_RESULT_DTYPE [nobj] for 1-3 bands, LM_RESULT_WIDE_DTYPE
+    (12 parameter slots) for 4-7 bands.
     """
     init()
     images = _f8(images)
@@ -446,8 +454,12 @@ def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
         npsf = psf_pars.shape[1]
     pr = prior if prior is not None else Prior()
     lmp = LMPars(maxfev, 1, ftol, xtol)
-    res = np.zeros(nobj, dtype=LM_RESULT_DTYPE)
-    check(lib().ngx_lm_fit_multi_host(
+    wide = nband > 3
+    res = np.zeros(nobj, dtype=LM_RESULT_WIDE_DTYPE if wide
+                   else LM_RESULT_DTYPE)
+    entry = lib().ngx_lm_fit_multi_wide_host if wide \
+        else lib().ngx_lm_fit_multi_host
+    check(entry(
         C.c_int(nobj), C.c_int(MODELS[model]), _p(stamp_start),
         _p(stamp_band), C.c_int(nband), _p(images), _p(weights), _p(jac),
         C.c_int(H), C.c_int(W), _p(psf_pars), C.c_int(npsf), _p(guess),

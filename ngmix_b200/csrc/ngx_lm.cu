@@ -60,7 +60,7 @@ struct LMArgs {
     const double *images, *weights;
     const ngx_jacobian *jac;
     const double *psf, *guess;
-    ngx_lm_result *res;
+    void *res;              // ngx_lm_result[] (or _wide[] for the multi kernel)
     int *counter;
     // objects with several stamps (ngx_lm_fit_multi)
     int nband;
@@ -480,8 +480,11 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
 // perturbations).
 // sums = {A packed (np(np+1)/2), b (np), sum r^2}
 #define CF 2
-#define FD_B0 (LM_MAXP * (LM_MAXP + 1) / 2)
-#define FD_NSUM (FD_B0 + LM_MAXP + 1)
+// the per-thread sums of the forward-difference pass are sized for the
+// single-stamp models (np <= 8), not for the solver's workspace
+#define FD_MAXP 8
+#define FD_B0 (FD_MAXP * (FD_MAXP + 1) / 2)
+#define FD_NSUM (FD_B0 + FD_MAXP + 1)
 template <int NPMAX, int SRC>
 __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
                                         const double *hs, const double *fdm,
@@ -639,11 +642,13 @@ __device__ __noinline__ double prior_fnorm2(const LMArgs &a, const double *x,
 // the epilogue: run_leastsq (leastsqbound.py:70-126) + set_fit_result.
 // Writes straight into the global result record; matrices are staged in the
 // shared-memory workspace of the state (no per-thread local arrays).
+template <typename RES>
 __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
-                                       ngx_lm_result *out) {
+                                       RES *out) {
     LMState *s = &sh->st;
     const int np = a.np;
-    ngx_lm_result &r = *out;
+    RES &r = *out;
+    constexpr int RP = (int)(sizeof(r.pars) / sizeof(double));
     const double qnan = nan("");
     double *cov0 = s->A;        // J^T J is no longer needed
     double *pcov = s->T1;       // after lm_cov0 is done with it
@@ -681,7 +686,7 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
     r.njev = s->njev;
     r.ier = s->info;
 #pragma unroll 1
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < RP; i++) {
         double pv = 0.0, pe = 0.0;
         if (i < np) {
             pv = (s->info > 4) ? NGX_PDEF : s->x[i];
@@ -691,7 +696,7 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
         r.pars_err[i] = pe;
     }
 #pragma unroll 1
-    for (int i = 0; i < 64; i++) {
+    for (int i = 0; i < RP * RP; i++) {
         double c0 = 0.0, c1 = 0.0;
         if (i < np * np) {
             c0 = have_cov ? cov0[i] : qnan;
@@ -892,7 +897,8 @@ k_lm_fit(LMArgs a) {
         int cnt = 0, first = a.ntot, firstq = 0;
         if (warp_id == 0) {
             if (threadIdx.x == 0) {
-                if (pending >= 0) lm_finish(a, &sh, &a.res[pending]);
+                if (pending >= 0)
+                    lm_finish(a, &sh, &((ngx_lm_result *)a.res)[pending]);
                 if (have) {
                     sh.next = atomicAdd(a.counter, 1);
                     sh.jac = a.jac[stamp];
@@ -1061,7 +1067,7 @@ k_lm_fit(LMArgs a) {
         if (sh.npix == 0) {
             // GMixFatalError("no weights > 0") at Observation construction
             if (threadIdx.x == 0) {
-                ngx_lm_result *r = &a.res[stamp];
+                ngx_lm_result *r = &((ngx_lm_result *)a.res)[stamp];
                 memset(r, 0, sizeof(*r));
                 r->flags = NGX_NO_ATTEMPT;
                 for (int i = 0; i < a.np; i++) {
@@ -1197,7 +1203,7 @@ k_lm_fit(LMArgs a) {
 #pragma unroll
                 for (int i = 0; i < FD_NSUM; i++) sums[i] = 0.0;
                 if (!bad_any)
-                    fd_pass<LM_MAXP, WG ? 1 : 0>(a, &sh, hs, fdm, etab, tmask, val,
+                    fd_pass<FD_MAXP, WG ? 1 : 0>(a, &sh, hs, fdm, etab, tmask, val,
                                                  ierr, wts, nullptr,
                                      rowd, cold, sums, mplane);
                 {
@@ -1231,9 +1237,9 @@ k_lm_fit(LMArgs a) {
 #ifdef NGX_PROF
         // the epilogue is timed with the next stamp's staging
         if (threadIdx.x == 0) {
-            lm_finish(a, &sh, &a.res[stamp]);
+            lm_finish(a, &sh, &((ngx_lm_result *)a.res)[stamp]);
             PROF_T(pt_fin);
-            double *o = a.res[stamp].pars_cov0 + 56;
+            double *o = ((ngx_lm_result *)a.res)[stamp].pars_cov0 + 56;
             o[0] = (double)pt_stage; o[1] = (double)pt_mix;
             o[2] = (double)pt_pass; o[3] = (double)pt_solve;
             o[4] = (double)pt_fin;
@@ -1256,10 +1262,11 @@ k_lm_fit(LMArgs a) {
 // sums of the stamp are reduced and scattered into the object's J^T J
 // (flux column 5 + band).  Solver, priors, speculation and epilogue are the
 // single-stamp ones.
+#define MACC_X (LM_MAXP * (LM_MAXP + 1) / 2 + LM_MAXP)
 struct LMMulti {
-    double macc[48];        // object sums: packed J^T J, J^T f, then
-                            // [44] sum r^2, [45] s2n numer, [46] denom,
-                            // [47] r_first^2
+    double macc[MACC_X + 4];    // object sums: packed J^T J (np), J^T f, then
+                                // [MACC_X] sum r^2, [+1] s2n numer, [+2]
+                                // denom, [+3] r_first^2
     double bp[6];           // band parameters of the current stamp
     int first_q_obj, mstatus;
 };
@@ -1270,7 +1277,7 @@ __device__ __forceinline__ bool multi_pars_nonzero(const double *x, int nband) {
     return ok;
 }
 
-template <int CV, int CD>
+template <int CV, int CD, typename RES>
 __global__ void __launch_bounds__(128, 4)
 k_lm_fit_multi(LMArgs a) {
     extern __shared__ double smem_d[];
@@ -1345,7 +1352,7 @@ k_lm_fit_multi(LMArgs a) {
         __syncthreads();
         if (sh.npix == 0 || s1 <= s0) {
             if (threadIdx.x == 0) {
-                ngx_lm_result *r = &a.res[obj];
+                RES *r = &((RES *)a.res)[obj];
                 memset(r, 0, sizeof(*r));
                 r->flags = NGX_NO_ATTEMPT;
                 for (int i = 0; i < np; i++) {
@@ -1366,7 +1373,7 @@ k_lm_fit_multi(LMArgs a) {
             const bool fused = want_f && spec && nonzero
                 && !(sh.st.prered <= sh.st.ftol);
             const bool do_deriv = fused || action == LM_ACT_EVAL_J;
-            if (threadIdx.x < 48) mu.macc[threadIdx.x] = 0.0;
+            if (threadIdx.x < MACC_X + 4) mu.macc[threadIdx.x] = 0.0;
             if (threadIdx.x == 0) mu.mstatus = 0;
             __syncthreads();
             // calc_jacobian raises for T == 0 or a zero flux
@@ -1435,10 +1442,10 @@ k_lm_fit_multi(LMArgs a) {
                             }
                             mu.macc[tri + ga] += t[21 + la];
                         }
-                        mu.macc[44] += t[27];
-                        mu.macc[45] += t[28];
-                        mu.macc[46] += t[29];
-                        if (e == s0) mu.macc[47] = t[30];
+                        mu.macc[MACC_X] += t[27];
+                        mu.macc[MACC_X + 1] += t[28];
+                        mu.macc[MACC_X + 2] += t[29];
+                        if (e == s0) mu.macc[MACC_X + 3] = t[30];
                     }
                 } else {
                     double sums[4] = {0, 0, 0, 0};
@@ -1446,10 +1453,10 @@ k_lm_fit_multi(LMArgs a) {
                                       im, rowd, cold, sums);
                     block_sum_to<4>(sums, scratch, sh.tot);
                     if (threadIdx.x == 0) {
-                        mu.macc[44] += sh.tot[0];
-                        mu.macc[45] += sh.tot[1];
-                        mu.macc[46] += sh.tot[2];
-                        if (e == s0) mu.macc[47] = sh.tot[3];
+                        mu.macc[MACC_X] += sh.tot[0];
+                        mu.macc[MACC_X + 1] += sh.tot[1];
+                        mu.macc[MACC_X + 2] += sh.tot[2];
+                        if (e == s0) mu.macc[MACC_X + 3] = sh.tot[3];
                     }
                 }
                 __syncthreads();
@@ -1459,13 +1466,13 @@ k_lm_fit_multi(LMArgs a) {
                 const int mstatus = mu.mstatus;
                 const int jstatus = mstatus || jstatus0;
                 if (want_f) {
-                    int acc = feed_residual(a, &sh, xp, mu.macc[44],
+                    int acc = feed_residual(a, &sh, xp, mu.macc[MACC_X],
                                                 mstatus);
                     if (acc) {
-                        sh.cur_ssq = mu.macc[44];
-                        sh.cur_num = mu.macc[45];
-                        sh.cur_den = mu.macc[46];
-                        sh.cur_rfirst2 = mu.macc[47];
+                        sh.cur_ssq = mu.macc[MACC_X];
+                        sh.cur_num = mu.macc[MACC_X + 1];
+                        sh.cur_den = mu.macc[MACC_X + 2];
+                        sh.cur_rfirst2 = mu.macc[MACC_X + 3];
                         if (fused && sh.st.action == LM_ACT_EVAL_J)
                             feed_jacobian(a, &sh, mu.macc, jstatus, 1, hs);
                     }
@@ -1478,7 +1485,7 @@ k_lm_fit_multi(LMArgs a) {
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) lm_finish(a, &sh, &a.res[obj]);
+        if (threadIdx.x == 0) lm_finish(a, &sh, &((RES *)a.res)[obj]);
     }
 }
 
@@ -1671,19 +1678,20 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
                              smem_both, st);
 }
 
-int ngx_lm_fit_multi(int nobj, int model, const int32_t *stamp_start,
-                     const int32_t *stamp_band, int nband,
-                     const double *images, const double *weights,
-                     const ngx_jacobian *jac, int nrow, int ncol,
-                     const double *psf_pars, int npsf, const double *guess,
-                     const ngx_prior *prior, const ngx_lm_pars *lm_pars,
-                     int ignore_zero_weight, ngx_lm_result *res,
-                     void *stream) {
+static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
+                             const int32_t *stamp_band, int nband,
+                             const double *images, const double *weights,
+                             const ngx_jacobian *jac, int nrow, int ncol,
+                             const double *psf_pars, int npsf,
+                             const double *guess, const ngx_prior *prior,
+                             const ngx_lm_pars *lm_pars,
+                             int ignore_zero_weight, void *res, int wide,
+                             void *stream) {
     NGX_REQUIRE(nobj >= 0 && stamp_start && stamp_band && images && weights);
     NGX_REQUIRE(jac && guess && res && lm_pars && lm_pars->maxfev > 0);
     NGX_REQUIRE(nrow >= 1 && ncol >= 1 && npsf >= 0 && npsf <= 16);
     NGX_REQUIRE(npsf == 0 || psf_pars);
-    NGX_REQUIRE(nband >= 1 && nband <= 3);
+    NGX_REQUIRE(nband >= 1 && nband <= (wide ? LM_MAXP - 5 : 3));
     NGX_REQUIRE(model == NGX_GAUSS || model == NGX_EXP || model == NGX_DEV);
     NGX_REQUIRE(lm_pars->analytic_jacobian);
     if (nobj == 0) return NGX_OK;
@@ -1715,20 +1723,56 @@ int ngx_lm_fit_multi(int nobj, int model, const int32_t *stamp_start,
     size_t smem = sizeof(double)
         * ((size_t)a.ngauss * REC + nrow + ncol + 48 * nwarps + 8
            + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
-    return config_and_launch(k_lm_fit_multi<3, 2>, a, threads, smem,
-                             as_stream(stream));
+    if (wide)
+        return config_and_launch(k_lm_fit_multi<3, 2, ngx_lm_result_wide>, a,
+                                 threads, smem, as_stream(stream));
+    return config_and_launch(k_lm_fit_multi<3, 2, ngx_lm_result>, a, threads,
+                             smem, as_stream(stream));
 }
 
-int ngx_lm_fit_multi_host(int nobj, int model, const int32_t *stamp_start,
+int ngx_lm_fit_multi(int nobj, int model, const int32_t *stamp_start,
+                     const int32_t *stamp_band, int nband,
+                     const double *images, const double *weights,
+                     const ngx_jacobian *jac, int nrow, int ncol,
+                     const double *psf_pars, int npsf, const double *guess,
+                     const ngx_prior *prior, const ngx_lm_pars *lm_pars,
+                     int ignore_zero_weight, ngx_lm_result *res,
+                     void *stream) {
+    return lm_fit_multi_impl(nobj, model, stamp_start, stamp_band, nband,
+                             images, weights, jac, nrow, ncol, psf_pars, npsf,
+                             guess, prior, lm_pars, ignore_zero_weight, res, 0,
+                             stream);
+}
+
+int ngx_lm_fit_multi_wide(int nobj, int model, const int32_t *stamp_start,
                           const int32_t *stamp_band, int nband,
                           const double *images, const double *weights,
                           const ngx_jacobian *jac, int nrow, int ncol,
                           const double *psf_pars, int npsf,
                           const double *guess, const ngx_prior *prior,
                           const ngx_lm_pars *lm_pars, int ignore_zero_weight,
-                          ngx_lm_result *res) {
+                          ngx_lm_result_wide *res, void *stream) {
+    return lm_fit_multi_impl(nobj, model, stamp_start, stamp_band, nband,
+                             images, weights, jac, nrow, ncol, psf_pars, npsf,
+                             guess, prior, lm_pars, ignore_zero_weight, res, 1,
+                             stream);
+}
+
+}  // extern "C"
+
+template <typename RES>
+static int lm_fit_multi_host_impl(int nobj, int model,
+                                  const int32_t *stamp_start,
+                                  const int32_t *stamp_band, int nband,
+                                  const double *images, const double *weights,
+                                  const ngx_jacobian *jac, int nrow, int ncol,
+                                  const double *psf_pars, int npsf,
+                                  const double *guess, const ngx_prior *prior,
+                                  const ngx_lm_pars *lm_pars,
+                                  int ignore_zero_weight, RES *res,
+                                  int wide) {
     NGX_REQUIRE(nobj >= 0 && stamp_start && stamp_band && images && weights);
-    NGX_REQUIRE(jac && guess && res && nband >= 1 && nband <= 3);
+    NGX_REQUIRE(jac && guess && res && nband >= 1 && nband <= LM_MAXP - 5);
     if (nobj == 0) return NGX_OK;
     const int ns = stamp_start[nobj];
     NGX_REQUIRE(ns >= 0 && stamp_start[0] == 0);
@@ -1738,17 +1782,50 @@ int ngx_lm_fit_multi_host(int nobj, int model, const int32_t *stamp_start,
     DevBuf<ngx_jacobian> dj(ns, jac);
     DevBuf<double> dp(npsf > 0 ? (size_t)ns * npsf * 6 : 0, psf_pars);
     DevBuf<double> dg((size_t)nobj * (5 + nband), guess);
-    DevBuf<ngx_lm_result> dr(nobj);
+    DevBuf<RES> dr(nobj);
     NGX_CUDA(dss.err); NGX_CUDA(dsb.err); NGX_CUDA(di.err); NGX_CUDA(dw.err);
     NGX_CUDA(dj.err); NGX_CUDA(dp.err); NGX_CUDA(dg.err); NGX_CUDA(dr.err);
-    int rc = ngx_lm_fit_multi(nobj, model, dss.d, dsb.d, nband, di.d, dw.d,
-                              dj.d, nrow, ncol, npsf > 0 ? dp.d : nullptr,
-                              npsf, dg.d, prior, lm_pars, ignore_zero_weight,
-                              dr.d, 0);
+    int rc = lm_fit_multi_impl(nobj, model, dss.d, dsb.d, nband, di.d, dw.d,
+                               dj.d, nrow, ncol, npsf > 0 ? dp.d : nullptr,
+                               npsf, dg.d, prior, lm_pars, ignore_zero_weight,
+                               dr.d, wide, 0);
     if (rc) return rc;
     NGX_CUDA(cudaDeviceSynchronize());
     NGX_CUDA(dr.to_host(res));
     return NGX_OK;
+}
+
+extern "C" {
+
+int ngx_lm_fit_multi_host(int nobj, int model, const int32_t *stamp_start,
+                          const int32_t *stamp_band, int nband,
+                          const double *images, const double *weights,
+                          const ngx_jacobian *jac, int nrow, int ncol,
+                          const double *psf_pars, int npsf,
+                          const double *guess, const ngx_prior *prior,
+                          const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                          ngx_lm_result *res) {
+    NGX_REQUIRE(nband <= 3);
+    return lm_fit_multi_host_impl(nobj, model, stamp_start, stamp_band, nband,
+                                  images, weights, jac, nrow, ncol, psf_pars,
+                                  npsf, guess, prior, lm_pars,
+                                  ignore_zero_weight, res, 0);
+}
+
+int ngx_lm_fit_multi_wide_host(int nobj, int model,
+                               const int32_t *stamp_start,
+                               const int32_t *stamp_band, int nband,
+                               const double *images, const double *weights,
+                               const ngx_jacobian *jac, int nrow, int ncol,
+                               const double *psf_pars, int npsf,
+                               const double *guess, const ngx_prior *prior,
+                               const ngx_lm_pars *lm_pars,
+                               int ignore_zero_weight,
+                               ngx_lm_result_wide *res) {
+    return lm_fit_multi_host_impl(nobj, model, stamp_start, stamp_band, nband,
+                                  images, weights, jac, nrow, ncol, psf_pars,
+                                  npsf, guess, prior, lm_pars,
+                                  ignore_zero_weight, res, 1);
 }
 
 // the host-buffer pipeline behind ngx_lm_fit_host (stamps as doubles) and

@@ -28,7 +28,11 @@
 
 namespace ngx {
 
-#define LM_MAXP 8
+// workspace size: 5 shape parameters + up to 7 band fluxes (multi-band fits);
+// the single-stamp models need at most 8
+#ifndef LM_MAXP
+#define LM_MAXP 12
+#endif
 #define LM_EPSMCH 2.220446049250313e-16
 #define LM_DWARF 2.2250738585072014e-308
 

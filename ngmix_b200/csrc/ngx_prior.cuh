@@ -14,7 +14,7 @@
 namespace ngx {
 
 #define NGX_STEP_PRIOR 1.0e-8       // results.py:935
-#define NGX_MAX_PRIOR_ROWS 8
+#define NGX_MAX_PRIOR_ROWS 12
 
 __device__ __noinline__ int prior1d_lnprob(const ngx_prior1d &p, double val,
                                      double *lnp) {
@@ -102,7 +102,8 @@ __host__ __device__ inline int prior_nband(const ngx_prior &pr) {
 }
 // flux prior of a band
 __device__ inline const ngx_prior1d &prior_F(const ngx_prior &pr, int band) {
-    return band == 0 ? pr.F : pr.F_more[band - 1];
+    return band == 0 ? pr.F
+        : band <= 2 ? pr.F_more[band - 1] : pr.F_extra[band - 3];
 }
 // number of residual slots reserved for the prior (results.py:1050-1076)
 __host__ __device__ inline int prior_nslots(int model, const ngx_prior &pr) {
@@ -246,7 +247,7 @@ __device__ __noinline__ int prior_jacobian(int model, const ngx_prior &pr,
                                      const double *f0, double *jp) {
     int nr = prior_nrows(model, pr);
     for (int i = 0; i < nr * np; i++) jp[i] = 0.0;
-    double p[8];
+    double p[LM_MAXP];
     for (int ipar = 0; ipar < np; ipar++) {
         int r = prior_row_of_par(model, ipar);
         double step = NGX_STEP_PRIOR * fmax(1.0, fabs(pars[ipar]));

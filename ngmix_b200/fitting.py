@@ -99,7 +99,8 @@ def fit_batch_multi(model, stamp_start, stamp_band, nband, images, weights,
     stamp_start[i]:stamp_start[i+1] of the [ns, H, W] stamp arrays, ordered
     band by band; stamp_band [ns] gives each stamp's band; guesses
     [nobj, 5 + nband] = (cen1, cen2, g1, g2, T, F_0 .. F_{nband-1}).
-    gauss / exp / dev with the analytic Jacobian, nband <= 3.
+    gauss / exp / dev with the analytic Jacobian, nband <= 7 (records with 12
+    parameter slots from 4 bands on).
     """
     model = get_model_name(get_model_num(model))
     if model not in SIMPLE_ANALYTIC_MODELS:
@@ -504,8 +505,8 @@ class Fitter(object):
             raise NotImplementedError(
                 "multi-epoch / multi-band fits: gauss, exp, dev with the "
                 "analytic jacobian")
-        if nband > 3:
-            raise NotImplementedError("at most 3 bands (8 parameters)")
+        if nband > 7:
+            raise NotImplementedError("at most 7 bands (12 parameters)")
         stamps = [(b, o) for b, ol in enumerate(mb) for o in ol]
         shape = stamps[0][1].image.shape
         has_psf = stamps[0][1].has_psf_gmix()

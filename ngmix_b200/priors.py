@@ -407,8 +407,8 @@ class PriorSimpleSep(object):
         return n
 
     def to_ngx(self):
-        if self.nband > 3:
-            raise NotImplementedError("at most 3 bands (8 parameters)")
+        if self.nband > 7:
+            raise NotImplementedError("at most 7 bands (12 parameters)")
         if not isinstance(self.g_prior, GPriorBA):
             raise NotImplementedError("g prior must be GPriorBA")
         pr = _lib.Prior()
@@ -422,7 +422,10 @@ class PriorSimpleSep(object):
         pr.F = self.F_priors[0]._ngx()
         pr.nband = self.nband
         for b in range(1, self.nband):
-            pr.F_more[b - 1] = self.F_priors[b]._ngx()
+            if b <= 2:
+                pr.F_more[b - 1] = self.F_priors[b]._ngx()
+            else:
+                pr.F_extra[b - 3] = self.F_priors[b]._ngx()
         return pr
 
 

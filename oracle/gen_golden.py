@@ -934,9 +934,6 @@ def _multi_case(rng, nband, nepoch, model, noise, with_prior):
 def gen_lm_multi():
     """Fitter.go on ObsList and MultiBandObsList inputs (multi-epoch,
     1-3 bands), with and without PriorSimpleSep (a flux prior per band)"""
-    from ngmix.fitting import Fitter
-    from ngmix import priors, joint_prior
-    rng = np.random.RandomState(31415)
     configs = [
         # (nband, epochs per band, model, with_prior)
         (1, [3], "exp", False), (1, [3], "exp", True),
@@ -944,6 +941,23 @@ def gen_lm_multi():
         (3, [1, 1, 1], "exp", True), (3, [2, 1, 2], "dev", True),
         (3, [1, 2, 1], "gauss", False), (1, [4], "dev", False),
     ]
+    _gen_multi(configs, 31415, "lm_multi")
+
+
+def gen_lm_multi_wide():
+    """the same with 4 to 7 bands (9 to 12 parameters)"""
+    configs = [
+        (4, [1, 1, 1, 1], "exp", True), (5, [1, 2, 1, 1, 1], "exp", False),
+        (5, [1, 1, 1, 1, 1], "gauss", True), (6, [1, 1, 1, 2, 1, 1], "dev", True),
+        (7, [1, 1, 1, 1, 1, 1, 1], "exp", True),
+    ]
+    _gen_multi(configs, 27182, "lm_multi_wide")
+
+
+def _gen_multi(configs, seed, name):
+    from ngmix.fitting import Fitter
+    from ngmix import priors, joint_prior
+    rng = np.random.RandomState(seed)
     out = {"ncases": np.array(0)}
     icase = 0
     for nband, nep, model, with_prior in configs:
@@ -1000,7 +1014,7 @@ def gen_lm_multi():
             assert len(r["pars"]) == np_
             icase += 1
     out["ncases"] = np.array(icase)
-    save("lm_multi", **out)
+    save(name, **out)
 
 
 def gen_psfflux():
@@ -1148,6 +1162,7 @@ GENERATORS = {
     "lm_priors2": gen_lm_priors2,
     "moments": gen_moments,
     "lm_multi": gen_lm_multi,
+    "lm_multi_wide": gen_lm_multi_wide,
     "psfflux": gen_psfflux,
     "boot": gen_boot,
 }

@@ -280,7 +280,7 @@ static int ctx_prior_jacobian(fitctx *c, const double *pars, double *jac,
     *nrows = 0;
     if (!c->prior || !c->prior->present) return ORA_OK;
     int m = c->fdiff_size, np = c->npars;
-    double f0[8] = {0}, fs[8] = {0}, p[8];
+    double f0[ORA_MAXP] = {0}, fs[ORA_MAXP] = {0}, p[ORA_MAXP];
     int n = prior_fill_fdiff(c->model, c->prior, pars, f0);
     if (n < 0) return ORA_RANGE_ERROR;
     for (int ipar = 0; ipar < np; ipar++) {
@@ -373,7 +373,7 @@ static int cb_jac(void *ctx, int m, int n, const double *x, double *fjac) {
 
 /* symmetric eigenvalues by cyclic Jacobi; returns 0 ok, 1 not finite */
 static int sym_eigvals(int n, const double *a_in, double *ev) {
-    double a[64];
+    double a[ORA_MAXP * ORA_MAXP];
     for (int i = 0; i < n; i++)
         for (int j = 0; j < n; j++) {
             double v = 0.5 * (a_in[i * n + j] + a_in[j * n + i]);
@@ -495,12 +495,12 @@ int ora_lm_fit(int model, const double *image, const double *weight,
     ctx_init(&c, model, pixels, npixv, psf_pars, npsf, prior);
     int np = c.npars, m = c.fdiff_size;
 
-    double x[8];
+    double x[ORA_MAXP];
     for (int i = 0; i < np; i++) x[i] = guess[i];
     double *fvec = (double *)malloc(sizeof(double) * (size_t)m * (np + 1));
     double *fjac = fvec + m;
-    int ipvt[8];
-    double qtf[8];
+    int ipvt[ORA_MAXP];
+    double qtf[ORA_MAXP];
     int nfev = 0, njev = 0, ier;
     int use_dfun = analytic_jacobian
         && (model == ORA_GAUSS || model == ORA_EXP || model == ORA_DEV);
@@ -524,7 +524,7 @@ int ora_lm_fit(int model, const double *image, const double *weight,
     /* cov_x = P R^-1 R^-T P^T (scipy leastsq), None if R is singular */
     int have_cov0 = 0;
     if (ier >= 1 && ier <= 4) {
-        double rinv[64];
+        double rinv[ORA_MAXP * ORA_MAXP];
         int sing = 0;
         for (int j = 0; j < np; j++)
             if (fjac[j + (size_t)j * m] == 0.0) sing = 1;
@@ -540,7 +540,7 @@ int ora_lm_fit(int model, const double *image, const double *weight,
                     rinv[i * np + j] = -s / fjac[i + (size_t)i * m];
                 }
             }
-            double prinv[64];
+            double prinv[ORA_MAXP * ORA_MAXP];
             for (int j = 0; j < np; j++)
                 for (int k = 0; k < np; k++)
                     prinv[ipvt[j] * np + k] = rinv[j * np + k];
@@ -578,7 +578,7 @@ int ora_lm_fit(int model, const double *image, const double *weight,
             for (int i = 0; i < np * np; i++)
                 res->pars_cov[i] = res->pars_cov0[i] * s_sq;
             int cflags = 0;
-            double ev[8];
+            double ev[ORA_MAXP];
             if (sym_eigvals(np, res->pars_cov, ev)) {
                 cflags |= ORA_EIG_NOTFINITE;
             } else {
@@ -744,7 +744,7 @@ static int m_prior_jacobian(mfitctx *m, const double *pars, double *jac,
     *nrows = 0;
     if (!m->prior || !m->prior->present) return ORA_OK;
     int mm = m->fdiff_size, np = m->npars;
-    double f0[8] = {0}, fs[8] = {0}, p[8];
+    double f0[ORA_MAXP] = {0}, fs[ORA_MAXP] = {0}, p[ORA_MAXP];
     int n = m_prior_fill_fdiff(m, pars, f0);
     if (n < 0) return ORA_RANGE_ERROR;
     for (int ipar = 0; ipar < np; ipar++) {
@@ -831,7 +831,7 @@ int ora_lm_fit_multi(int model, int nstamp, const double *images,
     memset(res, 0, sizeof(*res));
     if (!(model == ORA_GAUSS || model == ORA_EXP || model == ORA_DEV))
         return -1;
-    if (nband < 1 || 5 + nband > 8 || nstamp < 1) return -1;
+    if (nband < 1 || 5 + nband > ORA_MAXP || nstamp < 1) return -1;
     int ntot = nrow * ncol;
     mfitctx m;
     memset(&m, 0, sizeof(m));
@@ -862,12 +862,12 @@ int ora_lm_fit_multi(int model, int nstamp, const double *images,
     m.fdiff_size = m.totpix + m.n_prior_pars;
     int np = m.npars, mm = m.fdiff_size;
     if (rc == 0) {
-        double x[8];
+        double x[ORA_MAXP];
         for (int i = 0; i < np; i++) x[i] = guess[i];
         double *fvec = (double *)malloc(sizeof(double) * (size_t)mm * (np + 1));
         double *fjac = fvec + mm;
-        int ipvt[8];
-        double qtf[8];
+        int ipvt[ORA_MAXP];
+        double qtf[ORA_MAXP];
         int nfev = 0, njev = 0;
         int ier = ora_lmder(mcb_fdiff, mcb_jac, &m, mm, np, x, fvec, fjac,
                             ftol, xtol, 0.0, maxfev, 100.0, &nfev, &njev,
@@ -878,7 +878,7 @@ int ora_lm_fit_multi(int model, int nstamp, const double *images,
         for (int i = 0; i < np * np; i++) res->pars_cov0[i] = NAN;
         int have_cov0 = 0;
         if (ier >= 1 && ier <= 4) {
-            double rinv[64];
+            double rinv[ORA_MAXP * ORA_MAXP];
             int sing = 0;
             for (int j = 0; j < np; j++)
                 if (fjac[j + (size_t)j * mm] == 0.0) sing = 1;
@@ -893,7 +893,7 @@ int ora_lm_fit_multi(int model, int nstamp, const double *images,
                         rinv[i * np + j] = -s / fjac[i + (size_t)i * mm];
                     }
                 }
-                double prinv[64];
+                double prinv[ORA_MAXP * ORA_MAXP];
                 for (int j = 0; j < np; j++)
                     for (int k = 0; k < np; k++)
                         prinv[ipvt[j] * np + k] = rinv[j * np + k];
@@ -929,7 +929,7 @@ int ora_lm_fit_multi(int model, int nstamp, const double *images,
                 for (int i = 0; i < np * np; i++)
                     res->pars_cov[i] = res->pars_cov0[i] * s_sq;
                 int cflags = 0;
-                double ev[8];
+                double ev[ORA_MAXP];
                 if (sym_eigvals(np, res->pars_cov, ev)) {
                     cflags |= ORA_EIG_NOTFINITE;
                 } else {

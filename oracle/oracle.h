@@ -112,11 +112,13 @@ typedef struct {
 } ora_prior;
 
 /* ---- LM fit = Fitter.go (fitting/fitters.py:64-112) ---- */
+#define ORA_MAXP 12     /* 5 + 7 bands; matrices are packed npars x npars */
 typedef struct {
     int32_t flags, nfev, ier, npix, dof, njev;
     double lnprob, s2n_numer, s2n_denom, chi2per, s2n, T, T_err, flux,
         flux_err;
-    double pars[8], pars_err[8], pars_cov0[64], pars_cov[64];
+    double pars[ORA_MAXP], pars_err[ORA_MAXP], pars_cov0[ORA_MAXP * ORA_MAXP],
+        pars_cov[ORA_MAXP * ORA_MAXP];
 } ora_lm_result;
 
 int ora_lm_fit(int model, const double *image, const double *weight,

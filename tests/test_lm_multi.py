@@ -11,8 +11,8 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 PAR_TOL = 1e-5
 
 
-def _golden():
-    return np.load(os.path.join(GOLDEN, "lm_multi.npz"))
+def _golden(name="lm_multi"):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
 
 
 def _case(g, k):
@@ -52,8 +52,9 @@ def _check(r, c, np_, exact_counts=True):
                 <= 1e-5 * max(abs(float(c[key])), 1.0), key
 
 
-def test_oracle_multi_matches_reference(ora):
-    g = _golden()
+@pytest.mark.parametrize("name", ["lm_multi", "lm_multi_wide"])
+def test_oracle_multi_matches_reference(ora, name):
+    g = _golden(name)
     for k in range(int(g["ncases"])):
         c = _case(g, k)
         pr, fps = _ora_priors(ora, c)
@@ -84,9 +85,11 @@ def _ngx_prior(c):
 
 
 @pytest.mark.gpu
-def test_gpu_multi_matches_reference(ngx):
+@pytest.mark.parametrize("name", ["lm_multi", "lm_multi_wide"])
+def test_gpu_multi_matches_reference(ngx, name):
+    """1-3 bands (8-parameter records) and 4-7 bands (12-parameter records)"""
     import ngmix_b200 as ngmix
-    g = _golden()
+    g = _golden(name)
     for k in range(int(g["ncases"])):
         c = _case(g, k)
         ns = c["images"].shape[0]
@@ -102,8 +105,9 @@ def test_gpu_fitter_go_obslist_and_mbobs(ngx):
     """the reference-facing call: Fitter.go(ObsList / MultiBandObsList)"""
     import ngmix_b200 as ngmix
     g = _golden()
-    for k in (1, 7, 13, 16):
-        c = _case(g, k)
+    gw = _golden("lm_multi_wide")
+    for c in [_case(g, k) for k in (1, 7, 13, 16)] \
+            + [_case(gw, k) for k in (0, 4, 12)]:
         mbobs = ngmix.MultiBandObsList()
         i = 0
         for b in range(c["nband"]):
