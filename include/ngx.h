@@ -202,7 +202,7 @@ typedef struct {
     ngx_prior1d fracdev;  /* bdf only */
     ngx_prior1d F;        /* flux prior (band 0) */
     int32_t nband;        /* 0 or 1: single band; 2, 3: ngx_lm_fit_multi */
-    int32_t pad;
+    int32_t ncoellip;     /* ngauss of PriorCoellipSame (ngx_lm_fit_coellip) */
     ngx_prior1d F_more[2];    /* flux priors of bands 1 and 2 */
     ngx_prior1d logTratio;    /* bd only: PriorBDSep, joint_prior.py:267-399 */
     ngx_prior1d F_extra[4];   /* flux priors of bands 3..6 (nband up to 7) */
@@ -264,6 +264,26 @@ int ngx_lm_fit_multi(int nobj, int model, const int32_t *stamp_start,
                      const double *psf_pars, int npsf, const double *guess,
                      const ngx_prior *prior, const ngx_lm_pars *lm_pars,
                      int ignore_zero_weight, ngx_lm_result *res, void *stream);
+/* CoellipFitter.go (fitting/fitters.py:120-141, results.py:628-674): ngauss
+ * coelliptical gaussians, guess [n, 4 + 2 ngauss] = (cen1, cen2, g1, g2,
+ * T_1..T_n, F_1..F_n), forward-difference Jacobian, optional
+ * PriorCoellipSame (joint_prior.py:874-1031: cen, g, the T prior on every T_i,
+ * the F prior on every F_i); ngauss <= 4 */
+int ngx_lm_fit_coellip(int n, int ngauss, const double *images,
+                       const double *weights, const ngx_jacobian *jac,
+                       int nrow, int ncol, const double *psf_pars, int npsf,
+                       const double *guess, const ngx_prior *prior,
+                       const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                       ngx_lm_result_wide *res, void *stream);
+int ngx_lm_fit_coellip_host(int n, int ngauss, const double *images,
+                            const double *weights, const ngx_jacobian *jac,
+                            int nrow, int ncol, const double *psf_pars,
+                            int npsf, const double *guess,
+                            const ngx_prior *prior,
+                            const ngx_lm_pars *lm_pars,
+                            int ignore_zero_weight,
+                            ngx_lm_result_wide *res);
+
 /* the same for 4 to 7 bands (up to 12 parameters, 12-slot records); 1 to 3
  * bands are accepted too */
 int ngx_lm_fit_multi_wide(int nobj, int model, const int32_t *stamp_start,

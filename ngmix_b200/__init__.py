@@ -21,7 +21,8 @@ from .observation import (  # noqa: F401
 )
 from . import fitting, em, admom  # noqa: F401
 from .fitting import (  # noqa: F401
-    Fitter, PSFFluxFitter, fit_batch, fit_batch_multi,
+    Fitter, CoellipFitter, PSFFluxFitter, fit_batch, fit_batch_multi,
+    fit_batch_coellip,
 )
 from . import guessers, runners, bootstrap  # noqa: F401
 from .em import EMFitter, run_em, em_batch  # noqa: F401

@@ -72,7 +72,7 @@ class Prior(C.Structure):
                 ("sigma1", C.c_double), ("sigma2", C.c_double),
                 ("g_sigma", C.c_double), ("T", Prior1D),
                 ("fracdev", Prior1D), ("F", Prior1D),
-                ("nband", C.c_int32), ("pad", C.c_int32),
+                ("nband", C.c_int32), ("ncoellip", C.c_int32),
                 ("F_more", Prior1D * 2), ("logTratio", Prior1D),
                 ("F_extra", Prior1D * 4)]
 
@@ -112,6 +112,7 @@ SYMBOLS = [
     "ngx_noise_b", "ngx_noise_b_host", "ngx_noise_cov_host",
     "ngx_lm_fit_host_f32",
     "ngx_lm_fit_multi_wide", "ngx_lm_fit_multi_wide_host",
+    "ngx_lm_fit_coellip", "ngx_lm_fit_coellip_host",
 ]
 
 _lib = None
@@ -421,6 +422,35 @@ def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
     entry = lib().ngx_lm_fit_host_f32 if f32 else lib().ngx_lm_fit_host
     check(entry(
         C.c_int(n), C.c_int(MODELS[model]), _p(images), _p(weights), _p(jac),
+        C.c_int(H), C.c_int(W), _p(psf_pars), C.c_int(npsf), _p(guess),
+        C.byref(pr), C.byref(lmp), C.c_int(int(ignore_zero_weight)), _p(res)))
+    return res
+
+
+def lm_fit_coellip(ngauss, images, weights, jac, psf_pars, guess, prior=None,
+                   maxfev=4000, ftol=1.0e-5, xtol=1.0e-5,
+                   ignore_zero_weight=True):
+    """batched CoellipFitter.go: guess [n, 4 + 2 ngauss]; returns
+    LM_RESULT_WIDE_DTYPE [n]"""
+    init()
+    images = _f8(images)
+    weights = _f8(weights)
+    if images.ndim == 2:
+        images, weights = images[None], weights[None]
+    n, H, W = images.shape
+    jac = as_jac(jac, n)
+    guess = np.atleast_2d(_f8(guess))
+    assert guess.shape == (n, 4 + 2 * ngauss)
+    if psf_pars is None:
+        npsf = 0
+    else:
+        psf_pars = _f8(psf_pars).reshape(n, -1, 6)
+        npsf = psf_pars.shape[1]
+    pr = prior if prior is not None else Prior()
+    lmp = LMPars(maxfev, 0, ftol, xtol)
+    res = np.zeros(n, dtype=LM_RESULT_WIDE_DTYPE)
+    check(lib().ngx_lm_fit_coellip_host(
+        C.c_int(n), C.c_int(ngauss), _p(images), _p(weights), _p(jac),
         C.c_int(H), C.c_int(W), _p(psf_pars), C.c_int(npsf), _p(guess),
         C.byref(pr), C.byref(lmp), C.c_int(int(ignore_zero_weight)), _p(res)))
     return res

@@ -76,7 +76,7 @@ struct LMShared {
     double psf_row, psf_col, psf_ipsum;
     double cur_ssq, cur_rfirst2, cur_num, cur_den;   // at the accepted x
     ngx_jacobian jac;
-    double tot[48];            // block totals of the pass sums
+    double tot[96];            // block totals of the pass sums
     int stamp, next, npix, first_q, status, action, spec;
     int warp_i[32], warp_j[32], warp_k[32];
 };
@@ -99,7 +99,17 @@ __device__ __noinline__ void build_mixture(const LMArgs &a, LMShared *sh,
     int npsf = a.npsf > 0 ? a.npsf : 1;
     int iobj = k / npsf, ipsf = k - iobj * npsf;
     double p, irr0, irc0, icc0;
-    model_component(a.model, h, iobj, &p, &irr0, &irc0, &icc0);
+    if (a.model == NGX_COELLIP) {
+        // gmix_fill_coellip (gmix_nb.py:375-405): pars = (cen1, cen2, g1, g2,
+        // T_1..T_n, F_1..F_n), every gaussian with the shared shape
+        double Thalf = 0.5 * x[4 + iobj];
+        p = x[4 + a.ngauss0 + iobj];
+        irr0 = Thalf * (1 - h.e1);
+        irc0 = Thalf * h.e2;
+        icc0 = Thalf * (1 + h.e1);
+    } else {
+        model_component(a.model, h, iobj, &p, &irr0, &irc0, &icc0);
+    }
     double row = h.row, col = h.col, irr = irr0, irc = irc0, icc = icc0;
     if (a.npsf > 0) {
         const double *q = sh->psf + 6 * ipsf;
@@ -483,8 +493,8 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
 // the per-thread sums of the forward-difference pass are sized for the
 // single-stamp models (np <= 8), not for the solver's workspace
 #define FD_MAXP 8
-#define FD_B0 (FD_MAXP * (FD_MAXP + 1) / 2)
-#define FD_NSUM (FD_B0 + FD_MAXP + 1)
+#define FD_B0_(P) ((P) * ((P) + 1) / 2)
+#define FD_NSUM_(P) (FD_B0_(P) + (P) + 1)
 template <int NPMAX, int SRC>
 __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
                                         const double *hs, const double *fdm,
@@ -494,7 +504,7 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
                                         const double *wt, const double *im,
                                         const double *rowd,
                                         const double *cold,
-                                        double (&sums)[FD_NSUM],
+                                        double (&sums)[FD_NSUM_(NPMAX)],
                                         const double *mbase) {
     const int T = blockDim.x;
     const int np = a.np;
@@ -502,7 +512,7 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
     const int ntile = a.nq >> 5;
     const int nwords = (a.ngauss + 31) >> 5;
 #pragma unroll
-    for (int i = 0; i < FD_NSUM; i++) sums[i] = 0.0;
+    for (int i = 0; i < FD_NSUM_(NPMAX); i++) sums[i] = 0.0;
     double hstep[NPMAX];
 #pragma unroll
     for (int s = 0; s < NPMAX; s++) hstep[s] = s < np ? hs[s] : 1.0;
@@ -594,8 +604,10 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
                     }
 #pragma unroll
                 for (int aa = 0; aa < NPMAX; aa++)
-                    sums[FD_B0 + aa] = fma(j[aa], r, sums[FD_B0 + aa]);
-                sums[FD_B0 + NPMAX] = fma(r, r, sums[FD_B0 + NPMAX]);
+                    sums[FD_B0_(NPMAX) + aa] =
+                        fma(j[aa], r, sums[FD_B0_(NPMAX) + aa]);
+                sums[FD_B0_(NPMAX) + NPMAX] =
+                    fma(r, r, sums[FD_B0_(NPMAX) + NPMAX]);
             }
         }
     }
@@ -846,8 +858,10 @@ __device__ __noinline__ int feed_residual(const LMArgs &a, LMShared *sh,
 // GS: the pixel-value plane (and the base-model plane of the forward-
 // difference mode) live in a per-CTA slice of a global scratch buffer
 // instead of shared memory, for stamps too large to be resident (WG only).
+// FDP: parameter capacity of the forward-difference pass (8 for the galaxy
+// models, 12 for coelliptical mixtures); RES: the result record type.
 template <int MODE, int CV, int CD, int MINB, bool WG, int NT = 128,
-          bool GS = false>
+          bool GS = false, int FDP = FD_MAXP, typename RES = ngx_lm_result>
 __global__ void __launch_bounds__(NT, MINB)
 k_lm_fit(LMArgs a) {
     static_assert(!GS || WG, "GS keeps the weights in global memory");
@@ -870,7 +884,7 @@ k_lm_fit(LMArgs a) {
     double *cold = rowd + a.nrow;
     double *scratch = cold + a.ncol;                         // 48 * nwarps
     double *hs = scratch + 48 * nwarps;                      // 8
-    unsigned *tmask = (unsigned *)(hs + 8);                  // ntile*nwords
+    unsigned *tmask = (unsigned *)(hs + LM_MAXP);            // ntile*nwords
 
     if (nfd) fill_rot_table(etab, 1.0);     // every thread, same values
     // Work queue: stamps are handed out by an atomic counter, one ahead, so
@@ -898,7 +912,7 @@ k_lm_fit(LMArgs a) {
         if (warp_id == 0) {
             if (threadIdx.x == 0) {
                 if (pending >= 0)
-                    lm_finish(a, &sh, &((ngx_lm_result *)a.res)[pending]);
+                    lm_finish(a, &sh, &((RES *)a.res)[pending]);
                 if (have) {
                     sh.next = atomicAdd(a.counter, 1);
                     sh.jac = a.jac[stamp];
@@ -1067,7 +1081,7 @@ k_lm_fit(LMArgs a) {
         if (sh.npix == 0) {
             // GMixFatalError("no weights > 0") at Observation construction
             if (threadIdx.x == 0) {
-                ngx_lm_result *r = &((ngx_lm_result *)a.res)[stamp];
+                RES *r = &((RES *)a.res)[stamp];
                 memset(r, 0, sizeof(*r));
                 r->flags = NGX_NO_ATTEMPT;
                 for (int i = 0; i < a.np; i++) {
@@ -1199,21 +1213,34 @@ k_lm_fit(LMArgs a) {
                 }
                 if (!bad_any) build_tile_masks(a, &sh, mix, tmask, 1.0e-6);
                 __syncthreads();
-                double sums[FD_NSUM];
+                constexpr int FDN = FD_NSUM_(FDP);
+                double sums[FDN];
 #pragma unroll
-                for (int i = 0; i < FD_NSUM; i++) sums[i] = 0.0;
+                for (int i = 0; i < FDN; i++) sums[i] = 0.0;
                 if (!bad_any)
-                    fd_pass<FD_MAXP, WG ? 1 : 0>(a, &sh, hs, fdm, etab, tmask, val,
+                    fd_pass<FDP, WG ? 1 : 0>(a, &sh, hs, fdm, etab, tmask, val,
                                                  ierr, wts, nullptr,
                                      rowd, cold, sums, mplane);
                 {
-                    double s1[32], s2[FD_NSUM - 32];
+                    // block totals, 32 sums at a time
+                    double s1[32];
 #pragma unroll
                     for (int i = 0; i < 32; i++) s1[i] = sums[i];
-#pragma unroll
-                    for (int i = 32; i < FD_NSUM; i++) s2[i - 32] = sums[i];
                     block_sum_to<32>(s1, scratch, sh.tot);
-                    block_sum_to<FD_NSUM - 32>(s2, scratch, sh.tot + 32);
+                    if constexpr (FDN > 64) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) s1[i] = sums[32 + i];
+                        block_sum_to<32>(s1, scratch, sh.tot + 32);
+                        double s3[FDN - 64];
+#pragma unroll
+                        for (int i = 64; i < FDN; i++) s3[i - 64] = sums[i];
+                        block_sum_to<FDN - 64>(s3, scratch, sh.tot + 64);
+                    } else {
+                        double s2[FDN - 32];
+#pragma unroll
+                        for (int i = 32; i < FDN; i++) s2[i - 32] = sums[i];
+                        block_sum_to<FDN - 32>(s2, scratch, sh.tot + 32);
+                    }
                 }
                 if (threadIdx.x == 0) {
                     // feed_jacobian wants {triangle of np, b, r^2} contiguous
@@ -1221,7 +1248,7 @@ k_lm_fit(LMArgs a) {
                     const int tri = np * (np + 1) / 2;
                     for (int i = 0; i < tri; i++) pk[i] = sh.tot[i];
                     for (int i = 0; i <= np; i++)
-                        pk[tri + i] = sh.tot[FD_B0 + i];
+                        pk[tri + i] = sh.tot[FD_B0_(FDP) + i];
                     feed_jacobian(a, &sh, pk, bad_any, 0, hs);
                 }
             }
@@ -1237,9 +1264,9 @@ k_lm_fit(LMArgs a) {
 #ifdef NGX_PROF
         // the epilogue is timed with the next stamp's staging
         if (threadIdx.x == 0) {
-            lm_finish(a, &sh, &((ngx_lm_result *)a.res)[stamp]);
+            lm_finish(a, &sh, &((RES *)a.res)[stamp]);
             PROF_T(pt_fin);
-            double *o = ((ngx_lm_result *)a.res)[stamp].pars_cov0 + 56;
+            double *o = ((RES *)a.res)[stamp].pars_cov0 + 56;
             o[0] = (double)pt_stage; o[1] = (double)pt_mix;
             o[2] = (double)pt_pass; o[3] = (double)pt_solve;
             o[4] = (double)pt_fin;
@@ -1291,7 +1318,7 @@ k_lm_fit_multi(LMArgs a) {
     double *cold = rowd + a.nrow;
     double *scratch = cold + a.ncol;                         // 48 * nwarps
     double *hs = scratch + 48 * nwarps;                      // 8
-    unsigned *tmask = (unsigned *)(hs + 8);
+    unsigned *tmask = (unsigned *)(hs + LM_MAXP);
     const int np = a.np, nband = a.nband;
     const int tri = np * (np + 1) / 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1604,7 +1631,7 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     size_t smem = sizeof(double)
         * ((size_t)a.ngauss * REC + (size_t)nfd * a.ngauss * FDREC
            + (nfd ? 16 + (size_t)a.nq : 0) + (size_t)a.nq + nrow + ncol
-           + 48 * nwarps + 8
+           + 48 * nwarps + LM_MAXP
            + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
     // keep ierr = sqrt(w) in shared memory too when four CTAs (the register
     // limit) still fit on an SM; larger stamps leave the weights in L2
@@ -1721,13 +1748,91 @@ static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
     a.nq = 32 * a.tpr * ((nrow + 3) / 4);
     int nwarps = threads / 32;
     size_t smem = sizeof(double)
-        * ((size_t)a.ngauss * REC + nrow + ncol + 48 * nwarps + 8
+        * ((size_t)a.ngauss * REC + nrow + ncol + 48 * nwarps + LM_MAXP
            + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
     if (wide)
         return config_and_launch(k_lm_fit_multi<3, 2, ngx_lm_result_wide>, a,
                                  threads, smem, as_stream(stream));
     return config_and_launch(k_lm_fit_multi<3, 2, ngx_lm_result>, a, threads,
                              smem, as_stream(stream));
+}
+
+// CoellipFitter.go (fitting/fitters.py:120-141 -> CoellipFitModel,
+// results.py:628-674): n coelliptical gaussians, parameters (cen1, cen2, g1,
+// g2, T_1..T_n, F_1..F_n), forward-difference Jacobian (MINPACK lmdif),
+// optional PriorCoellipSame (prior->ncoellip = ngauss).  ngauss <= 4 (12
+// parameters); the 256-thread kernel with the weights in L2.
+int ngx_lm_fit_coellip(int n, int ngauss, const double *images,
+                       const double *weights, const ngx_jacobian *jac,
+                       int nrow, int ncol, const double *psf_pars, int npsf,
+                       const double *guess, const ngx_prior *prior,
+                       const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                       ngx_lm_result_wide *res, void *stream) {
+    NGX_REQUIRE(n >= 0 && images && weights && jac && guess && res);
+    NGX_REQUIRE(nrow >= 1 && ncol >= 1 && npsf >= 0 && npsf <= 16);
+    NGX_REQUIRE(npsf == 0 || psf_pars);
+    NGX_REQUIRE(lm_pars && lm_pars->maxfev > 0);
+    NGX_REQUIRE(ngauss >= 1 && 4 + 2 * ngauss <= LM_MAXP);
+    if (n == 0) return NGX_OK;
+    LMArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.model = NGX_COELLIP; a.np = 4 + 2 * ngauss;
+    a.ngauss0 = ngauss; a.npsf = npsf;
+    a.ngauss = ngauss * (npsf > 0 ? npsf : 1);
+    a.nrow = nrow; a.ncol = ncol; a.ntot = nrow * ncol;
+    a.ignore_zero_weight = ignore_zero_weight;
+    if (prior) a.prior = *prior;
+    if (a.prior.present) {
+        NGX_REQUIRE(a.prior.g_kind == 1);
+        a.prior.ncoellip = ngauss;
+    }
+    a.lm = *lm_pars;
+    a.images = images; a.weights = weights; a.jac = jac;
+    a.psf = psf_pars; a.guess = guess; a.res = res;
+    a.analytic = 0;
+    NGX_REQUIRE(a.ngauss <= NGX_MAX_GAUSS);
+    int rc = get_counter(&a.counter);
+    if (rc) return rc;
+    const int threads = 256, nwarps = 8;
+    NGX_REQUIRE(threads >= a.ngauss && threads >= 6 * npsf);
+    a.tpr = (ncol + 7) / 8;
+    a.nq = 32 * a.tpr * ((nrow + 3) / 4);
+    const int nfd = a.np + 1;
+    size_t smem = sizeof(double)
+        * ((size_t)a.ngauss * REC + (size_t)nfd * a.ngauss * FDREC
+           + 16 + 2 * (size_t)a.nq + nrow + ncol + 48 * nwarps + LM_MAXP
+           + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
+    return config_and_launch(
+        k_lm_fit<1, 3, 2, 1, true, 256, false, LM_MAXP, ngx_lm_result_wide>,
+        a, threads, smem, as_stream(stream));
+}
+
+int ngx_lm_fit_coellip_host(int n, int ngauss, const double *images,
+                            const double *weights, const ngx_jacobian *jac,
+                            int nrow, int ncol, const double *psf_pars,
+                            int npsf, const double *guess,
+                            const ngx_prior *prior,
+                            const ngx_lm_pars *lm_pars,
+                            int ignore_zero_weight,
+                            ngx_lm_result_wide *res) {
+    NGX_REQUIRE(n >= 0 && images && weights && jac && guess && res);
+    NGX_REQUIRE(ngauss >= 1 && 4 + 2 * ngauss <= LM_MAXP);
+    if (n == 0) return NGX_OK;
+    const size_t ntot = (size_t)nrow * ncol;
+    DevBuf<double> di(n * ntot, images), dw(n * ntot, weights);
+    DevBuf<ngx_jacobian> dj(n, jac);
+    DevBuf<double> dp(npsf > 0 ? (size_t)n * npsf * 6 : 0, psf_pars);
+    DevBuf<double> dg((size_t)n * (4 + 2 * ngauss), guess);
+    DevBuf<ngx_lm_result_wide> dr(n);
+    NGX_CUDA(di.err); NGX_CUDA(dw.err); NGX_CUDA(dj.err); NGX_CUDA(dp.err);
+    NGX_CUDA(dg.err); NGX_CUDA(dr.err);
+    int rc = ngx_lm_fit_coellip(n, ngauss, di.d, dw.d, dj.d, nrow, ncol,
+                                npsf > 0 ? dp.d : nullptr, npsf, dg.d, prior,
+                                lm_pars, ignore_zero_weight, dr.d, 0);
+    if (rc) return rc;
+    NGX_CUDA(cudaDeviceSynchronize());
+    NGX_CUDA(dr.to_host(res));
+    return NGX_OK;
 }
 
 int ngx_lm_fit_multi(int nobj, int model, const int32_t *stamp_start,

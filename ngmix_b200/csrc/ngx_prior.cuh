@@ -108,6 +108,7 @@ __device__ inline const ngx_prior1d &prior_F(const ngx_prior &pr, int band) {
 // number of residual slots reserved for the prior (results.py:1050-1076)
 __host__ __device__ inline int prior_nslots(int model, const ngx_prior &pr) {
     if (!pr.present) return 0;
+    if (model == NGX_COELLIP) return 3 + 2 * pr.ncoellip;
     return (model == NGX_BD ? 6 : 5) + prior_nband(pr);
 }
 // number of rows the prior actually fills
@@ -115,6 +116,7 @@ __host__ __device__ inline int prior_nrows(int model, const ngx_prior &pr) {
     if (!pr.present) return 0;
     if (model == NGX_BDF) return 6;
     if (model == NGX_BD) return 7;
+    if (model == NGX_COELLIP) return 3 + 2 * pr.ncoellip;
     return 4 + prior_nband(pr);
 }
 
@@ -170,12 +172,18 @@ __device__ __noinline__ int prior_row(int model, const ngx_prior &pr,
         st = gprior_lnprob(pr, p[2], p[3], &lnp);
         if (st) return st;
         break;
-    case 3:
-        st = prior1d_lnprob(pr.T, p[4], &lnp);
-        if (st) return st;
-        break;
     default:
-        st = prior1d_lnprob(prior_F(pr, row - 4), p[5 + (row - 4)], &lnp);
+        if (model == NGX_COELLIP) {
+            // PriorCoellipSame.fill_fdiff (joint_prior.py:963-990): the T
+            // prior on every T_i, then the flux prior on every F_i
+            const int ng = pr.ncoellip, k = row - 3;
+            st = k < ng ? prior1d_lnprob(pr.T, p[4 + k], &lnp)
+                        : prior1d_lnprob(pr.F, p[4 + k], &lnp);
+        } else if (row == 3) {
+            st = prior1d_lnprob(pr.T, p[4], &lnp);
+        } else {
+            st = prior1d_lnprob(prior_F(pr, row - 4), p[5 + (row - 4)], &lnp);
+        }
         if (st) return st;
     }
     *out = clip_sqrt(lnp);
@@ -214,6 +222,17 @@ __device__ __noinline__ int prior_lnprob(int model, const ngx_prior &pr,
     double t;
     if (gprior_lnprob(pr, p[2], p[3], &t)) return NGX_ST_RANGE_ERROR;
     lnp += t;
+    if (model == NGX_COELLIP) {
+        // PriorCoellipSame.get_lnprob_scalar, joint_prior.py:941-961
+        const int ng = pr.ncoellip;
+        for (int k = 0; k < 2 * ng; k++) {
+            if (prior1d_lnprob(k < ng ? pr.T : pr.F, p[4 + k], &t))
+                return NGX_ST_RANGE_ERROR;
+            lnp += t;
+        }
+        *out = lnp;
+        return NGX_ST_OK;
+    }
     if (prior1d_lnprob(pr.T, p[4], &t)) return NGX_ST_RANGE_ERROR;
     lnp += t;
     int fi = 5;

@@ -16,7 +16,8 @@ from .gmix import (GMix, get_model_name, get_model_npars, get_model_num,
                    make_gmix_model)
 from .observation import Observation, get_mb_obs
 
-__all__ = ['Fitter', 'FitResult', 'FitModel', 'fit_batch',
+__all__ = ['Fitter', 'CoellipFitter', 'FitResult', 'FitModel', 'fit_batch',
+           'fit_batch_coellip',
            'SIMPLE_ANALYTIC_MODELS', 'get_band_pars', 'get_lm_n_prior_pars']
 
 # models with an analytic Jacobian (fitting/results.py:921)
@@ -137,7 +138,13 @@ _ERRMSG = {
 }
 
 
-def record_to_result(rec, model, npars):
+def record_to_result_n(rec, model, npars):
+    """record_to_result for models whose parameter count is not tabulated
+    (coellip): single band"""
+    return record_to_result(rec, model, npars, nband=1)
+
+
+def record_to_result(rec, model, npars, nband=None):
     """one record of fit_batch -> the reference's result dict"""
     n = npars
     res = {
@@ -164,7 +171,8 @@ def record_to_result(rec, model, npars):
         res["g"] = res["pars"][2:4].copy()
         res["g_cov"] = res["pars_cov"][2:4, 2:4].copy()
         res["g_err"] = res["pars_err"][2:4].copy()
-        nband = n - get_model_npars(model) + 1
+        if nband is None:
+            nband = n - get_model_npars(model) + 1
         if nband > 1:
             # _set_flux, results.py:1079-1109
             start = n - nband
@@ -564,3 +572,94 @@ class Fitter(object):
                     Bk = np.full((len(kp), len(kp)), np.nan)
                 B[np.ix_(kp, kp)] += Bk
         noise_cov.apply_noise_cov(res, B)
+
+
+def fit_batch_coellip(ngauss, images, weights, jacobians, guesses,
+                      psf_pars=None, prior=None, fit_pars=None,
+                      ignore_zero_weight=True):
+    """
+    Fits of n coelliptical gaussians to n stamps in one launch
+    (CoellipFitter.go, fitting/fitters.py:120-141): guesses
+    [n, 4 + 2 ngauss] = (cen1, cen2, g1, g2, T_1..T_n, F_1..F_n),
+    forward-difference Jacobian as in the reference, ngauss <= 4.  Returns
+    records with 12 parameter slots (matrices packed npars x npars).
+    """
+    fp = dict(DEFAULT_LM_PARS)
+    if fit_pars is not None:
+        fp.update(fit_pars)
+    return _lib.lm_fit_coellip(ngauss, images, weights, jacobians, psf_pars,
+                               guesses, prior=_prior_record(prior),
+                               maxfev=fp["maxfev"], ftol=fp["ftol"],
+                               xtol=fp["xtol"],
+                               ignore_zero_weight=ignore_zero_weight)
+
+
+class CoellipFitResult(FitResult):
+    """result of CoellipFitter.go: the run_leastsq keys and fit statistics;
+    as in the reference (CoellipFitModel._set_flux, results.py:646-650) no
+    total flux is derived"""
+
+    def __init__(self, obs, ngauss, result):
+        dict.__init__(self, result)
+        self.obs = get_mb_obs(obs)
+        self.model_name = "coellip"
+        self.nband = 1
+        self.npars = 4 + 2 * ngauss
+
+    def get_band_pars(self, pars, band):
+        return np.array(pars, dtype="f8")
+
+    def get_gmix(self, band=0):
+        from .gmix import GMixCoellip
+        return GMixCoellip(self["pars"])
+
+
+class CoellipFitter(Fitter):
+    """
+    Levenberg-Marquardt fit of ngauss coelliptical gaussians, the psf model
+    of fitting/fitters.py:120-141.
+
+    Parameters
+    ----------
+    ngauss: int
+        number of gaussians, at most 4 here (12 parameters)
+    prior: PriorCoellipSame, optional
+    fit_pars: dict, optional
+    """
+
+    def __init__(self, ngauss, prior=None, fit_pars=None):
+        if ngauss > 4:
+            raise NotImplementedError("at most 4 coelliptical gaussians")
+        self._ngauss = ngauss
+        self.prior = prior
+        self.model_name = "coellip"
+        self.use_noise_image = False
+        self.analytic_jacobian = False
+        self.fit_pars = dict(fit_pars) if fit_pars is not None \
+            else dict(DEFAULT_LM_PARS)
+
+    def go(self, obs, guess):
+        mb = get_mb_obs(obs)
+        assert len(mb) == 1 and len(mb[0]) == 1, \
+            "Coellip can only fit one band, one epoch"
+        o = mb[0][0]
+        npars = 4 + 2 * self._ngauss
+        guess = np.array(guess, dtype="f8")
+        assert guess.size == npars, \
+            "guess has npars=%d, expected %d" % (guess.size, npars)
+        psf_pars = None
+        if o.has_psf_gmix():
+            psf_pars = o.psf.gmix.get_full_pars().reshape(1, -1, 6)
+        from .gmix import GMixCoellip
+        GMixCoellip(guess)          # a guess outside the domain raises
+        rec = fit_batch_coellip(self._ngauss, o.image[None], o.weight[None],
+                                o._jacobian._data, guess[None],
+                                psf_pars=psf_pars, prior=self.prior,
+                                fit_pars=self.fit_pars,
+                                ignore_zero_weight=o.ignore_zero_weight)[0]
+        if rec["flags"] == 1 and rec["nfev"] == 0:
+            raise GMixFatalError("no weights > 0")
+        res = record_to_result_n(rec, "coellip", npars)
+        for k in ("flux", "flux_err", "flux_cov"):
+            res.pop(k, None)
+        return CoellipFitResult(o, self._ngauss, res)

@@ -8,7 +8,7 @@ TPSFFluxGuesser come from the device (ngx_template_flux).
 Built: TFluxGuesser, TPSFFluxGuesser, ParsGuesser (each with the optional
 prior fix-up), TFluxAndPriorGuesser, TPSFFluxAndPriorGuesser, BDFGuesser,
 BDFPSFFluxGuesser, BDGuesser, PriorGuesser, GMixPSFGuesser, SimplePSFGuesser.
-Not built: the galsim-model guessers (R50*) and CoellipPSFGuesser.
+CoellipPSFGuesser.  Not built: the galsim-model guessers (R50*).
 """
 import numpy as np
 
@@ -406,4 +406,48 @@ class SimplePSFGuesser(GMixPSFGuesser):
         guess[2:4] += rng.uniform(low=-0.05, high=0.05, size=2)
         guess[4] = T * rng.uniform(low=0.9, high=1.1)
         guess[5] = flux * rng.uniform(low=0.9, high=1.1)
+        return guess
+
+
+# size and amplitude fractions of the coelliptical guesses, by ngauss
+# (moffat-like profiles, guessers.py:1219-1242; the later of the reference's
+# two 5-gaussian tables is the one in effect)
+_COELLIP_P = {
+    1: [1.0],
+    2: [0.5, 0.5],
+    3: [0.27559669, 0.55817131, 0.166232],
+    4: [0.44534, 0.366951, 0.10506, 0.0826497],
+    5: [0.57874897, 0.32273483, 0.03327272, 0.0341253, 0.03111819],
+}
+_COELLIP_F = {
+    1: [1.0],
+    2: [0.48955064, 1.50658978],
+    3: [0.36123609, 0.8426139, 2.58747785],
+    4: [0.541019, 1.19701, 0.282176, 3.51086],
+    5: [0.27831284, 0.9959897, 5.86989779, 5.63590429, 4.17285878],
+}
+
+
+class CoellipPSFGuesser(GMixPSFGuesser):
+    """[cen1, cen2, g1, g2, T_1..T_n, F_1..F_n] guesses for coelliptical psf
+    fits (guessers.py:1106-1216): centre and shape near zero, sizes and
+    fluxes the table fractions of T and flux within 1 % (10 % for one
+    gaussian), drawn T's first, then fluxes"""
+
+    def __init__(self, rng, ngauss, guess_from_moms=False):
+        super().__init__(rng, ngauss, guess_from_moms=guess_from_moms)
+        self.npars = 4 + 2 * ngauss
+
+    def __call__(self, obs):
+        rng, n = self.rng, self.ngauss
+        T, flux = self._get_T_flux(obs)
+        guess = np.zeros(self.npars)
+        guess[0:2] += rng.uniform(low=-0.01, high=0.01, size=2)
+        guess[2:4] += rng.uniform(low=-0.05, high=0.05, size=2)
+        lo, hi = (0.9, 1.1) if n == 1 else (0.99, 1.01)
+        for i in range(n):
+            guess[4 + i] = T * _COELLIP_F[n][i] * rng.uniform(low=lo, high=hi)
+        for i in range(n):
+            guess[4 + n + i] = flux * _COELLIP_P[n][i] \
+                * rng.uniform(low=lo, high=hi)
         return guess

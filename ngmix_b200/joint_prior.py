@@ -1,2 +1,3 @@
 """joint priors under the reference's module name (ngmix/joint_prior.py)"""
-from .priors import PriorSimpleSep, PriorBDFSep, PriorBDSep  # noqa: F401
+from .priors import (  # noqa: F401
+    PriorSimpleSep, PriorBDFSep, PriorBDSep, PriorCoellipSame)

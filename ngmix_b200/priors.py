@@ -507,3 +507,63 @@ class PriorBDSep(PriorSimpleSep):
         pr.logTratio = self.logTratio_prior._ngx()
         pr.fracdev = self.fracdev_prior._ngx()
         return pr
+
+
+class PriorCoellipSame(PriorSimpleSep):
+    """priors for a coelliptical mixture: centre, shape, the same T prior on
+    every T_i and the same flux prior on every F_i (joint_prior.py:874-1031)"""
+
+    def __init__(self, ngauss, cen_prior, g_prior, T_prior, F_prior):
+        self.ngauss = ngauss
+        self.npars = 4 + 2 * ngauss
+        super().__init__(cen_prior, g_prior, T_prior, F_prior)
+        if self.nband != 1:
+            raise ValueError("coellip only supports one band")
+
+    def _check(self, pars):
+        if len(pars) != self.npars:
+            raise ValueError("pars size %d expected %d"
+                             % (len(pars), self.npars))
+
+    def _lnp_rows(self, pars):
+        n = self.ngauss
+        lnp1, lnp2 = self.cen_prior.get_lnprob_scalar_sep(pars[0], pars[1])
+        rows = [lnp1, lnp2,
+                self.g_prior.get_lnprob_scalar2d(pars[2], pars[3])]
+        rows += [self.T_prior.get_lnprob_scalar(pars[4 + i])
+                 for i in range(n)]
+        rows += [self.F_priors[0].get_lnprob_scalar(pars[4 + n + i])
+                 for i in range(n)]
+        return rows
+
+    def get_lnprob_scalar(self, pars):
+        self._check(pars)
+        return float(np.sum(self._lnp_rows(pars)))
+
+    def fill_fdiff(self, pars, fdiff):
+        self._check(pars)
+        rows = self._lnp_rows(pars)
+        chi2 = -2 * np.array(rows)
+        chi2.clip(min=0.0, max=None, out=chi2)
+        fdiff[0:len(rows)] = np.sqrt(chi2)
+        return len(rows)
+
+    def sample(self, nrand=None):
+        """(joint_prior.py:992-1031; as there, the first size column holds
+        the sum of two T draws)"""
+        n = 1 if nrand is None else nrand
+        ng = self.ngauss
+        samples = np.zeros((n, self.npars))
+        samples[:, 0], samples[:, 1] = self.cen_prior.sample(n)
+        samples[:, 2], samples[:, 3] = self.g_prior.sample2d(n)
+        samples[:, 4] = self.T_prior.sample(n)
+        for i in range(ng):
+            samples[:, 4 + i] += self.T_prior.sample(n)
+        for i in range(ng):
+            samples[:, 4 + ng + i] = self.F_priors[0].sample(n)
+        return samples[0] if nrand is None else samples
+
+    def to_ngx(self):
+        pr = super().to_ngx()
+        pr.ncoellip = self.ngauss
+        return pr

@@ -834,6 +834,61 @@ def gen_lm_priors2():
     save("lm_priors2", **out)
 
 
+def gen_lm_coellip():
+    """CoellipFitter.go (forward-difference LM of n coelliptical gaussians)
+    on PSF stamps, ngauss 1-4, with and without PriorCoellipSame; guesses from
+    the reference's CoellipPSFGuesser"""
+    from ngmix import priors, joint_prior
+    from ngmix.fitting import CoellipFitter
+    from ngmix.guessers import CoellipPSFGuesser
+    b = sims.make_psf_batch(6, seed0=19000)
+    n = b["images"].shape[0]
+    out = {k: b[k] for k in ("images", "weights", "jac")}
+    for ngauss in (1, 2, 3, 4):
+        for pk in ("none", "prior"):
+            rng = np.random.RandomState(100 * ngauss + (pk == "prior"))
+            prior = None
+            if pk == "prior":
+                prior = joint_prior.PriorCoellipSame(
+                    ngauss,
+                    priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng),
+                    priors.GPriorBA(0.3, rng=rng),
+                    priors.TwoSidedErf(-1.0, 0.1, 1.0e3, 1.0, rng=rng),
+                    priors.TwoSidedErf(-1.0e2, 1.0, 1.0e9, 1.0e8, rng=rng))
+            np_ = 4 + 2 * ngauss
+            res = dict(flags=np.zeros(n, "i4"), nfev=np.zeros(n, "i4"),
+                       ier=np.zeros(n, "i4"), pars=np.zeros((n, np_)),
+                       pars_err=np.zeros((n, np_)), guess=np.zeros((n, np_)),
+                       pars_cov=np.zeros((n, np_, np_)),
+                       lnprob=np.zeros(n), s2n=np.zeros(n),
+                       chi2per=np.zeros(n), dof=np.zeros(n, "i4"),
+                       npix=np.zeros(n, "i4"))
+            guesser = CoellipPSFGuesser(rng=rng, ngauss=ngauss)
+            fitter = CoellipFitter(ngauss=ngauss, prior=prior)
+            for i in range(n):
+                obs = ngmix.Observation(
+                    b["images"][i], weight=b["weights"][i],
+                    jacobian=jac_from_record(b["jac"][i]))
+                guess = guesser(obs=obs)
+                r = fitter.go(obs, guess.copy())
+                res["guess"][i] = guess
+                res["flags"][i] = r["flags"]
+                res["nfev"][i] = r["nfev"]
+                res["ier"][i] = r["ier"]
+                res["pars"][i] = r["pars"]
+                if "pars_err" in r:
+                    res["pars_err"][i] = r["pars_err"]
+                    res["pars_cov"][i] = r["pars_cov"]
+                if r["flags"] == 0:
+                    for k in ("lnprob", "s2n", "chi2per", "dof", "npix"):
+                        res[k][i] = r[k]
+            print("coellip", ngauss, pk, "flags", res["flags"], "nfev",
+                  res["nfev"], "ier", res["ier"])
+            for k, v in res.items():
+                out["n%d_%s_%s" % (ngauss, pk, k)] = v
+    save("lm_coellip", **out)
+
+
 def gen_moments():
     """GaussMom (6 and 17 moments) on galaxy stamps, and get_weighted_sums
     with a two-gaussian off-centre weight and a maxrad"""
@@ -1160,6 +1215,7 @@ GENERATORS = {
     "noise_cov": gen_noise_cov,
     "shape_moments": gen_shape_moments,
     "lm_priors2": gen_lm_priors2,
+    "lm_coellip": gen_lm_coellip,
     "moments": gen_moments,
     "lm_multi": gen_lm_multi,
     "lm_multi_wide": gen_lm_multi_wide,

@@ -119,6 +119,8 @@ static int gprior_lnprob(const ora_prior *pr, double g1, double g2,
 static int n_prior_slots(int model, const ora_prior *pr) {
     if (!pr || !pr->present) return 0;
     if (model == ORA_BD) return 7;
+    /* CoellipFitModel._set_n_prior_pars, results.py:652-660 */
+    if (model == ORA_COELLIP) return 3 + 2 * pr->ncoellip;
     return 6;
 }
 
@@ -177,10 +179,23 @@ static int prior_fill_fdiff(int model, const ora_prior *pr, const double *pars,
     double lnp;
     if (gprior_lnprob(pr, pars[2], pars[3], &lnp)) return -1;
     fdiff[index++] = lnp;
-    if (prior1d_lnprob(&pr->T, pars[4], &lnp)) return -1;
-    fdiff[index++] = lnp;
-    if (prior1d_lnprob(&pr->F, pars[5], &lnp)) return -1;
-    fdiff[index++] = lnp;
+    if (model == ORA_COELLIP) {
+        /* PriorCoellipSame.fill_fdiff, joint_prior.py:963-990 */
+        int ng = pr->ncoellip;
+        for (int i = 0; i < ng; i++) {
+            if (prior1d_lnprob(&pr->T, pars[4 + i], &lnp)) return -1;
+            fdiff[index++] = lnp;
+        }
+        for (int i = 0; i < ng; i++) {
+            if (prior1d_lnprob(&pr->F, pars[4 + ng + i], &lnp)) return -1;
+            fdiff[index++] = lnp;
+        }
+    } else {
+        if (prior1d_lnprob(&pr->T, pars[4], &lnp)) return -1;
+        fdiff[index++] = lnp;
+        if (prior1d_lnprob(&pr->F, pars[5], &lnp)) return -1;
+        fdiff[index++] = lnp;
+    }
     for (int i = 0; i < index; i++) {
         double c = -2 * fdiff[i];
         if (c < 0.0) c = 0.0;       /* clip(min=0); NaN passes through */
@@ -201,6 +216,17 @@ static int prior_lnprob(int model, const ora_prior *pr, const double *pars,
     double t;
     if (gprior_lnprob(pr, pars[2], pars[3], &t)) return ORA_RANGE_ERROR;
     lnp += t;
+    if (model == ORA_COELLIP) {
+        /* PriorCoellipSame.get_lnprob_scalar, joint_prior.py:941-961 */
+        int ng = pr->ncoellip;
+        for (int i = 0; i < 2 * ng; i++) {
+            if (prior1d_lnprob(i < ng ? &pr->T : &pr->F, pars[4 + i], &t))
+                return ORA_RANGE_ERROR;
+            lnp += t;
+        }
+        *out = lnp;
+        return ORA_OK;
+    }
     if (prior1d_lnprob(&pr->T, pars[4], &t)) return ORA_RANGE_ERROR;
     lnp += t;
     int fi = 5;
@@ -425,6 +451,11 @@ static int ctx_init(fitctx *c, int model, const ora_pixel *pixels, int npix,
     c->model = model;
     c->npars = ora_model_npars(model);
     c->ngauss0 = ora_model_ngauss(model);
+    if (model == ORA_COELLIP) {
+        /* CoellipFitModel._set_npars, results.py:662-666 */
+        c->ngauss0 = prior ? prior->ncoellip : 0;
+        c->npars = 4 + 2 * c->ngauss0;
+    }
     c->npsf = npsf;
     c->ngauss = c->ngauss0 * (npsf > 0 ? npsf : 1);
     c->pixels = pixels;

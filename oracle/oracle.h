@@ -109,6 +109,8 @@ typedef struct {
     ora_prior1d fracdev;   /* bdf, bd */
     ora_prior1d F;
     ora_prior1d logTratio; /* bd only */
+    int32_t ncoellip;      /* coellip fits: ngauss (read even without prior) */
+    int32_t pad2;
 } ora_prior;
 
 /* ---- LM fit = Fitter.go (fitting/fitters.py:64-112) ---- */

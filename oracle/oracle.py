@@ -43,7 +43,8 @@ class Prior(C.Structure):
                 ("sigma1", C.c_double), ("sigma2", C.c_double),
                 ("g_sigma", C.c_double), ("T", Prior1D),
                 ("fracdev", Prior1D), ("F", Prior1D),
-                ("logTratio", Prior1D)]
+                ("logTratio", Prior1D), ("ncoellip", C.c_int32),
+                ("pad2", C.c_int32)]
 
 
 class LMResult(C.Structure):
@@ -306,6 +307,8 @@ def lm_fit(model, image, weight, jac, psf_pars, guess, prior=None,
         npsf = psf_pars.size // 6
         psf_ptr = _p(psf_pars)
     pr = prior if prior is not None else make_prior("none")
+    if model == "coellip":
+        pr.ncoellip = (guess.size - 4) // 2
     res = np.zeros(1, dtype=LM_RESULT_DTYPE)
     st = lib().ora_lm_fit(
         C.c_int(MODELS[model]), _p(image), _p(weight),
