@@ -225,13 +225,13 @@ typedef struct {
     double pars[8], pars_err[8], pars_cov0[64], pars_cov[64];
 } ngx_lm_result;
 
-/* the same record with room for 12 parameters: multi-band fits with 4 to 7
- * bands (ngx_lm_fit_multi_wide) */
+/* the same record with room for 14 parameters: multi-band fits with 4 to 7
+ * bands (ngx_lm_fit_multi_wide), coelliptical fits (ngx_lm_fit_coellip) */
 typedef struct {
     int32_t flags, nfev, ier, npix, dof, njev;
     double lnprob, s2n_numer, s2n_denom, chi2per, s2n, T, T_err, flux,
         flux_err;
-    double pars[12], pars_err[12], pars_cov0[144], pars_cov[144];
+    double pars[14], pars_err[14], pars_cov0[196], pars_cov[196];
 } ngx_lm_result_wide;
 
 /* Fitter(model, prior, fit_pars).go(obs, guess) for n stamps
@@ -268,7 +268,7 @@ int ngx_lm_fit_multi(int nobj, int model, const int32_t *stamp_start,
  * coelliptical gaussians, guess [n, 4 + 2 ngauss] = (cen1, cen2, g1, g2,
  * T_1..T_n, F_1..F_n), forward-difference Jacobian, optional
  * PriorCoellipSame (joint_prior.py:874-1031: cen, g, the T prior on every T_i,
- * the F prior on every F_i); ngauss <= 4 */
+ * the F prior on every F_i); ngauss <= 5 */
 int ngx_lm_fit_coellip(int n, int ngauss, const double *images,
                        const double *weights, const ngx_jacobian *jac,
                        int nrow, int ncol, const double *psf_pars, int npsf,
@@ -284,7 +284,7 @@ int ngx_lm_fit_coellip_host(int n, int ngauss, const double *images,
                             int ignore_zero_weight,
                             ngx_lm_result_wide *res);
 
-/* the same for 4 to 7 bands (up to 12 parameters, 12-slot records); 1 to 3
+/* the same for 4 to 7 bands (up to 12 parameters, 14-slot records); 1 to 3
  * bands are accepted too */
 int ngx_lm_fit_multi_wide(int nobj, int model, const int32_t *stamp_start,
                      const int32_t *stamp_band, int nband,

@@ -39,11 +39,12 @@ LM_RESULT_DTYPE = np.dtype([
     ("s2n_denom", "f8"), ("chi2per", "f8"), ("s2n", "f8"), ("T", "f8"),
     ("T_err", "f8"), ("flux", "f8"), ("flux_err", "f8"), ("pars", "f8", 8),
     ("pars_err", "f8", 8), ("pars_cov0", "f8", 64), ("pars_cov", "f8", 64)])
-# ngx_lm_result_wide: the same record with 12 parameter slots (4-7 bands)
+# ngx_lm_result_wide: the same record with 14 parameter slots (4-7 bands,
+# coelliptical fits)
 LM_RESULT_WIDE_DTYPE = np.dtype(
     [(n, LM_RESULT_DTYPE.fields[n][0]) for n in LM_RESULT_DTYPE.names[:15]]
-    + [("pars", "f8", 12), ("pars_err", "f8", 12), ("pars_cov0", "f8", 144),
-       ("pars_cov", "f8", 144)])
+    + [("pars", "f8", 14), ("pars_err", "f8", 14), ("pars_cov0", "f8", 196),
+       ("pars_cov", "f8", 196)])
 EM_RESULT_DTYPE = np.dtype([("flags", "i4"), ("numiter", "i4"),
                             ("fdiff", "f8"), ("sky", "f8")])
 ADMOM_RESULT_DTYPE = np.dtype([
@@ -464,7 +465,7 @@ def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
     object i owns stamps stamp_start[i]:stamp_start[i+1] of images/weights
     [ns,H,W] (ordered band by band), stamp_band [ns]; guess [nobj, 5+nband].
     Returns LM_RESULT_DTYPE [nobj] for 1-3 bands, LM_RESULT_WIDE_DTYPE
-    (12 parameter slots) for 4-7 bands.
+    (14 parameter slots) for 4-7 bands.
     """
     init()
     images = _f8(images)

@@ -76,7 +76,7 @@ struct LMShared {
     double psf_row, psf_col, psf_ipsum;
     double cur_ssq, cur_rfirst2, cur_num, cur_den;   // at the accepted x
     ngx_jacobian jac;
-    double tot[96];            // block totals of the pass sums
+    double tot[128];           // block totals of the pass sums
     int stamp, next, npix, first_q, status, action, spec;
     int warp_i[32], warp_j[32], warp_k[32];
 };
@@ -1223,23 +1223,14 @@ k_lm_fit(LMArgs a) {
                                      rowd, cold, sums, mplane);
                 {
                     // block totals, 32 sums at a time
-                    double s1[32];
+                    constexpr int NCH = (FDN + 31) / 32;
 #pragma unroll
-                    for (int i = 0; i < 32; i++) s1[i] = sums[i];
-                    block_sum_to<32>(s1, scratch, sh.tot);
-                    if constexpr (FDN > 64) {
+                    for (int ch = 0; ch < NCH; ch++) {
+                        double s1[32];
 #pragma unroll
-                        for (int i = 0; i < 32; i++) s1[i] = sums[32 + i];
-                        block_sum_to<32>(s1, scratch, sh.tot + 32);
-                        double s3[FDN - 64];
-#pragma unroll
-                        for (int i = 64; i < FDN; i++) s3[i - 64] = sums[i];
-                        block_sum_to<FDN - 64>(s3, scratch, sh.tot + 64);
-                    } else {
-                        double s2[FDN - 32];
-#pragma unroll
-                        for (int i = 32; i < FDN; i++) s2[i - 32] = sums[i];
-                        block_sum_to<FDN - 32>(s2, scratch, sh.tot + 32);
+                        for (int i = 0; i < 32; i++)
+                            s1[i] = 32 * ch + i < FDN ? sums[32 * ch + i] : 0.0;
+                        block_sum_to<32>(s1, scratch, sh.tot + 32 * ch);
                     }
                 }
                 if (threadIdx.x == 0) {
@@ -1718,7 +1709,7 @@ static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
     NGX_REQUIRE(jac && guess && res && lm_pars && lm_pars->maxfev > 0);
     NGX_REQUIRE(nrow >= 1 && ncol >= 1 && npsf >= 0 && npsf <= 16);
     NGX_REQUIRE(npsf == 0 || psf_pars);
-    NGX_REQUIRE(nband >= 1 && nband <= (wide ? LM_MAXP - 5 : 3));
+    NGX_REQUIRE(nband >= 1 && nband <= (wide ? 7 : 3));
     NGX_REQUIRE(model == NGX_GAUSS || model == NGX_EXP || model == NGX_DEV);
     NGX_REQUIRE(lm_pars->analytic_jacobian);
     if (nobj == 0) return NGX_OK;
@@ -1760,7 +1751,7 @@ static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
 // CoellipFitter.go (fitting/fitters.py:120-141 -> CoellipFitModel,
 // results.py:628-674): n coelliptical gaussians, parameters (cen1, cen2, g1,
 // g2, T_1..T_n, F_1..F_n), forward-difference Jacobian (MINPACK lmdif),
-// optional PriorCoellipSame (prior->ncoellip = ngauss).  ngauss <= 4 (12
+// optional PriorCoellipSame (prior->ncoellip = ngauss).  ngauss <= 5 (14
 // parameters); the 256-thread kernel with the weights in L2.
 int ngx_lm_fit_coellip(int n, int ngauss, const double *images,
                        const double *weights, const ngx_jacobian *jac,
@@ -1877,7 +1868,7 @@ static int lm_fit_multi_host_impl(int nobj, int model,
                                   int ignore_zero_weight, RES *res,
                                   int wide) {
     NGX_REQUIRE(nobj >= 0 && stamp_start && stamp_band && images && weights);
-    NGX_REQUIRE(jac && guess && res && nband >= 1 && nband <= LM_MAXP - 5);
+    NGX_REQUIRE(jac && guess && res && nband >= 1 && nband <= 7);
     if (nobj == 0) return NGX_OK;
     const int ns = stamp_start[nobj];
     NGX_REQUIRE(ns >= 0 && stamp_start[0] == 0);

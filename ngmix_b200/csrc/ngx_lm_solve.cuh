@@ -28,10 +28,10 @@
 
 namespace ngx {
 
-// workspace size: 5 shape parameters + up to 7 band fluxes (multi-band fits);
-// the single-stamp models need at most 8
+// workspace size: 5 coelliptical gaussians (4 + 2 * 5 parameters); multi-band
+// fits use up to 5 + 7, the single-stamp galaxy models at most 8
 #ifndef LM_MAXP
-#define LM_MAXP 12
+#define LM_MAXP 14
 #endif
 #define LM_EPSMCH 2.220446049250313e-16
 #define LM_DWARF 2.2250738585072014e-308

@@ -14,7 +14,7 @@
 namespace ngx {
 
 #define NGX_STEP_PRIOR 1.0e-8       // results.py:935
-#define NGX_MAX_PRIOR_ROWS 12
+#define NGX_MAX_PRIOR_ROWS LM_MAXP
 
 __device__ __noinline__ int prior1d_lnprob(const ngx_prior1d &p, double val,
                                      double *lnp) {

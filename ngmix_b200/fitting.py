@@ -100,7 +100,7 @@ def fit_batch_multi(model, stamp_start, stamp_band, nband, images, weights,
     stamp_start[i]:stamp_start[i+1] of the [ns, H, W] stamp arrays, ordered
     band by band; stamp_band [ns] gives each stamp's band; guesses
     [nobj, 5 + nband] = (cen1, cen2, g1, g2, T, F_0 .. F_{nband-1}).
-    gauss / exp / dev with the analytic Jacobian, nband <= 7 (records with 12
+    gauss / exp / dev with the analytic Jacobian, nband <= 7 (records with 14
     parameter slots from 4 bands on).
     """
     model = get_model_name(get_model_num(model))
@@ -581,8 +581,8 @@ def fit_batch_coellip(ngauss, images, weights, jacobians, guesses,
     Fits of n coelliptical gaussians to n stamps in one launch
     (CoellipFitter.go, fitting/fitters.py:120-141): guesses
     [n, 4 + 2 ngauss] = (cen1, cen2, g1, g2, T_1..T_n, F_1..F_n),
-    forward-difference Jacobian as in the reference, ngauss <= 4.  Returns
-    records with 12 parameter slots (matrices packed npars x npars).
+    forward-difference Jacobian as in the reference, ngauss <= 5.  Returns
+    records with 14 parameter slots (matrices packed npars x npars).
     """
     fp = dict(DEFAULT_LM_PARS)
     if fit_pars is not None:
@@ -622,14 +622,14 @@ class CoellipFitter(Fitter):
     Parameters
     ----------
     ngauss: int
-        number of gaussians, at most 4 here (12 parameters)
+        number of gaussians, at most 5
     prior: PriorCoellipSame, optional
     fit_pars: dict, optional
     """
 
     def __init__(self, ngauss, prior=None, fit_pars=None):
-        if ngauss > 4:
-            raise NotImplementedError("at most 4 coelliptical gaussians")
+        if ngauss > 5:
+            raise NotImplementedError("at most 5 coelliptical gaussians")
         self._ngauss = ngauss
         self.prior = prior
         self.model_name = "coellip"

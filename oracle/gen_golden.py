@@ -844,7 +844,7 @@ def gen_lm_coellip():
     b = sims.make_psf_batch(6, seed0=19000)
     n = b["images"].shape[0]
     out = {k: b[k] for k in ("images", "weights", "jac")}
-    for ngauss in (1, 2, 3, 4):
+    for ngauss in (1, 2, 3, 4, 5):
         for pk in ("none", "prior"):
             rng = np.random.RandomState(100 * ngauss + (pk == "prior"))
             prior = None

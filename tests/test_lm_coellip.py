@@ -2,7 +2,7 @@
 Coelliptical-gaussian LM fits (CoellipFitter, PriorCoellipSame,
 CoellipPSFGuesser: ngmix/fitting/fitters.py:120-141, results.py:628-674,
 joint_prior.py:874-1031, guessers.py:1106-1216).  Golden vectors:
-oracle/gen_golden.py --only lm_coellip (reference fits of PSF stamps with 1-4
+oracle/gen_golden.py --only lm_coellip (reference fits of PSF stamps with 1-5
 gaussians, with and without the prior, from the reference guesser's guesses).
 
 The 3- and 4-gaussian fits of a 3-gaussian psf are degenerate (hundreds of
@@ -15,7 +15,7 @@ import pytest
 
 from conftest import load_golden
 
-CASES = [(ng, pk) for ng in (1, 2, 3, 4) for pk in ("none", "prior")]
+CASES = [(ng, pk) for ng in (1, 2, 3, 4, 5) for pk in ("none", "prior")]
 
 
 def _check(r, g, pre, i, np_, par_tol):
@@ -99,6 +99,7 @@ def test_gpu_coellip_matches_reference(ng, ngauss, pk):
     pre = "n%d_%s_" % (ngauss, pk)
     recs = ng.fit_batch_coellip(ngauss, g["images"], g["weights"], g["jac"],
                                 g[pre + "guess"], prior=_prior(ng, ngauss, pk))
+    nclose = 0
     for i in range(recs.size):
         # well-conditioned fits (1, 2 gaussians) follow the reference's
         # iterates and stop within the forward-difference noise of its point
@@ -115,8 +116,18 @@ def test_gpu_coellip_matches_reference(ng, ngauss, pk):
             if int(g[pre + "flags"][i]) == 0:
                 ref, err = g[pre + "pars"][i], g[pre + "pars_err"][i]
                 got = recs["pars"][i][:4 + 2 * ngauss]
-                assert np.all(np.abs(got - ref)
-                              <= np.maximum(1e-5 * np.abs(ref), 0.05 * err))
+                close = np.all(np.abs(got - ref)
+                               <= np.maximum(1e-5 * np.abs(ref), 0.05 * err))
+                nclose += int(close)
+                if ngauss < 5:
+                    assert close
+                else:
+                    # five gaussians on a three-gaussian psf: a flat valley,
+                    # the stopping point is not unique; the fit quality is
+                    assert abs(recs["lnprob"][i] / g[pre + "lnprob"][i] - 1) \
+                        < 5e-3
+    if ngauss == 5:
+        assert nclose >= 4
     if ngauss == 3:
         # the evaluation counts agree on nearly all of them even so
         assert (recs["nfev"] == g[pre + "nfev"]).sum() >= 5
@@ -149,4 +160,4 @@ def test_gpu_coellip_fitter_and_psf_runner(ng):
     assert obs.psf.meta["result"]["flags"] == 0
     assert obs.psf.has_gmix() and len(obs.psf.gmix) == 2
     with pytest.raises(NotImplementedError):
-        ng.CoellipFitter(ngauss=5)
+        ng.CoellipFitter(ngauss=6)
