@@ -257,6 +257,45 @@ def bench_metacal(args, torch, _lib, sims, dev):
             "R11": R11, "R22": R22}
 
 
+def bench_coellip(args, _lib, b):
+    """coelliptical psf fits (CoellipFitter, forward differences) of the PSF
+    stamps, through the host-buffer call"""
+    import ngmix_b200 as ngmix
+    n = min(b["images"].shape[0], 20000)
+    out = {}
+    for ngauss in (2, 3):
+        guess = np.zeros((n, 4 + 2 * ngauss))
+        class _O(object):
+            pass
+        rng = np.random.RandomState(11)
+        guesser = ngmix.guessers.CoellipPSFGuesser(rng=rng, ngauss=ngauss)
+        T = ngmix.moments.fwhm_to_T(0.263 * 3.5)
+        flux = b["images"][:n].sum(axis=(1, 2))
+        for i in range(n):
+            g = np.zeros(4 + 2 * ngauss)
+            g[0:2] = rng.uniform(-0.01, 0.01, 2)
+            g[2:4] = rng.uniform(-0.05, 0.05, 2)
+            fr = ngmix.guessers._COELLIP_F[ngauss]
+            pr = ngmix.guessers._COELLIP_P[ngauss]
+            g[4:4 + ngauss] = T * np.array(fr) * rng.uniform(0.99, 1.01,
+                                                               ngauss)
+            g[4 + ngauss:] = flux[i] * np.array(pr) * rng.uniform(0.99, 1.01,
+                                                                  ngauss)
+            guess[i] = g
+        del guesser
+        _lib.lm_fit_coellip(ngauss, b["images"][:64], b["weights"][:64],
+                            b["jac"][:64], None, guess[:64])
+        t0 = time.perf_counter()
+        r = _lib.lm_fit_coellip(ngauss, b["images"][:n], b["weights"][:n],
+                                b["jac"][:n], None, guess)
+        dt = time.perf_counter() - t0
+        out["ngauss%d" % ngauss] = {
+            "fits_per_s_host_call": n / dt, "n": n,
+            "median_nfev": float(np.median(r["nfev"])),
+            "nonzero_flags": int((r["flags"] != 0).sum())}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nobj", type=int, default=20000)
@@ -352,6 +391,7 @@ def main():
         out["bdf"] = bench_bdf(args, torch, _lib, sims, dev)
     if args.nmcal > 0:
         out["metacal"] = bench_metacal(args, torch, _lib, sims, dev)
+    out["coellip"] = bench_coellip(args, _lib, b)
     print(json.dumps(out))
 
 
