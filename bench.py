@@ -220,6 +220,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: no CPU fallback")
     torch.cuda.set_device(local)
+    numa_node = None
+    orig_affinity = os.sched_getaffinity(0)
+    if world > 1:
+        # one process per GPU: stay on the GPU's own NUMA node, so the pinned
+        # buffers of the end-to-end call are local to its PCIe root
+        from ngmix_b200 import shard
+        numa_node = shard.bind_to_gpu_numa_node(local)
     _lib.init(local)
     if world > 1:
         # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
@@ -414,6 +421,7 @@ def main():
                       "larger than L2" % (alg_bytes / 1e6),
             "parallelism": "objects sharded by index over %d rank(s), no "
                            "collective" % world,
+            "numa_node_rank0": numa_node,
         },
         "model_pixel_evals_per_s": world * (value_evals + deriv_evals)
         / (ms_per_step * 1e-3),
@@ -472,6 +480,7 @@ def main():
         "clocks": clocks,
     }
     if not args.no_cpu:
+        os.sched_setaffinity(0, orig_affinity)    # all host cores again
         cores = os.cpu_count()
         cpu_rate, ns, dt, ores, reps = time_cpu_port(b, cores)
         out["cpu_baseline"] = {

@@ -78,3 +78,46 @@ def run_sharded(fit_fn, arrays, gather=True, group=None):
     if gather:
         return gather_records(local, n_total, group=group)
     return local
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index):
+    """
+    Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so
+    that the pinned host buffers it allocates afterwards (first touch) and the
+    host side of the H2D pipeline stay local to that GPU's PCIe root.  With
+    one process per GPU on a multi-socket host this is what keeps the
+    host-buffer calls from sharing one socket's memory bandwidth.  Returns the
+    node number, or None when the topology cannot be read (nothing changed).
+    """
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        bdf = "%04x:%02x:%02x.0" % (dom, bus, dev)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(
+            open("/sys/devices/system/node/node%d/cpulist" % node).read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
