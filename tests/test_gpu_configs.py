@@ -86,6 +86,57 @@ def test_empty_batch(ngx):
     a = ngx.admom(np.zeros((0, 8, 8)), np.zeros((0, 8, 8)), np.zeros((0, 8)),
                   np.zeros((0, 6)))
     assert a.shape == (0,)
+    # the float32, coelliptical, multi-band (narrow and wide records) and
+    # noise-covariance entry points
+    z32 = np.zeros((0, 8, 8), dtype=np.float32)
+    assert ngx.lm_fit("exp", z32, z32, np.zeros((0, 8)), np.zeros((0, 1, 6)),
+                      np.zeros((0, 6))).shape == (0,)
+    assert ngx.lm_fit_coellip(2, np.zeros((0, 8, 8)), np.zeros((0, 8, 8)),
+                              np.zeros((0, 8)), None,
+                              np.zeros((0, 8))).shape == (0,)
+    for nband in (2, 5):
+        r = ngx.lm_fit_multi("exp", [0], np.zeros(0, "i4"), nband,
+                             np.zeros((0, 8, 8)), np.zeros((0, 8, 8)),
+                             np.zeros((0, 8)), None, np.zeros((0, 5 + nband)))
+        assert r.shape == (0,)
+    assert ngx.noise_b(np.zeros((0, 3, 64)), np.zeros((0, 8, 8)),
+                       np.zeros((0, 8, 8))).shape == (0, 3, 3)
+
+
+def test_tiny_stamps(ngx, ora):
+    """the smallest stamps MINPACK accepts for six parameters (it refuses
+    fewer residuals than parameters): 3 x 3 and 4 x 2 go through every pass
+    and report what the oracle reports; a 1 x 1 stamp runs without faults"""
+    one = ngx.lm_fit("gauss", np.ones((2, 1, 1)), np.ones((2, 1, 1)),
+                     np.array([[0.0, 0.0, 0.263, 0.0, 0.0, 0.263,
+                                0.263 ** 2, 0.263]] * 2), None,
+                     np.array([[0.0, 0.0, 0.0, 0.0, 0.3, 1.0]] * 2))
+    assert np.all(one["flags"] != 0)
+    from ngmix_b200 import sims
+    for dims in ((5, 5), (6, 4)):
+        b = sims.make_lm_batch(6, seed0=990 + dims[0], dims=dims, noise=0.05,
+                               model="gauss")
+        res = ngx.lm_fit("gauss", b["images"], b["weights"], b["jac"],
+                         b["psf"], b["guess"])
+        ref = ora.lm_fit_batch("gauss", b["images"], b["weights"], b["jac"],
+                               b["psf"], b["guess"])
+        # the fitted point and the evaluation counts; the covariance of a
+        # fit this poorly constrained is singular to rounding, so its flag
+        # bits (512, 1024, 2048) are not compared
+        mask = ~np.int32(512 | 1024 | 2048)
+        assert np.array_equal(res["flags"] & mask, ref["flags"] & mask)
+        assert np.array_equal(res["npix"], ref["npix"])
+        assert (res["nfev"] == ref["nfev"]).sum() >= 5
+        gm, _ = ngx.gmix_fill("gauss", b["guess"])
+        ngx.gmix_set_norms(gm)
+        out4, fd, st = ngx.loglike(gm, b["images"], b["weights"], b["jac"],
+                                   want_fdiff=True)
+        assert not st.any() and np.all(out4[:, 3] == dims[0] * dims[1])
+        ag = np.array([[1.0, 0, 0, 0.2, 0, 0.2]] * 6)
+        a = ngx.admom(b["images"], b["weights"], b["jac"], ag)
+        oa = ora.admom_go_batch(b["images"], b["weights"], b["jac"], ag)
+        assert np.array_equal(a["flags"], oa["flags"])
+        assert np.array_equal(a["numiter"], oa["numiter"])
 
 
 @pytest.mark.parametrize("dims", [(31, 47), (16, 16), (9, 11)])
