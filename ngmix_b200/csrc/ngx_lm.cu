@@ -85,7 +85,7 @@ struct LMShared {
 // build the convolved mixture for parameters x: thread k < ngauss owns
 // composed gaussian k = iobj*npsf + ipsf (gmix_convolve_fill's order).
 // sh->status is OR-ed with range errors.
-__device__ __noinline__ void build_mixture(const LMArgs &a, LMShared *sh,
+static __device__ __noinline__ void build_mixture(const LMArgs &a, LMShared *sh,
                                            const double *x, double *mix,
                                            double area,
                                            double *compact = nullptr) {
@@ -633,7 +633,7 @@ __device__ __forceinline__ void block_sum_n(double *v, int nv,
 
 // ---------------------------------------------------------------------
 // prior contributions, thread 0
-__device__ __noinline__ double prior_fnorm2(const LMArgs &a, const double *x,
+static __device__ __noinline__ double prior_fnorm2(const LMArgs &a, const double *x,
                                       int *status, int *ninf) {
     *ninf = 0;
     if (!a.prior.present) return 0.0;
@@ -759,7 +759,7 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
 // state machine (thread 0).  packed = lower triangle row by row, then b.
 // pre: A and b already hold the pixel sums (assemble_normal_eq, run by the
 // whole CTA); only the prior rows are added here.
-__device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
+static __device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
                                            const double *sums, int status,
                                            int analytic, const double *hs,
                                            int pre = 0) {
@@ -836,7 +836,7 @@ __device__ __forceinline__ void assemble_normal_eq(LMShared *sh,
 }
 
 // feed |f| of a residual pass (thread 0); returns 1 if the point is adopted
-__device__ __noinline__ int feed_residual(const LMArgs &a, LMShared *sh,
+static __device__ __noinline__ int feed_residual(const LMArgs &a, LMShared *sh,
                                           const double *xeval, double ssq,
                                           int status) {
     int ninf = 0;
@@ -1531,6 +1531,7 @@ struct LMLaunch {
     size_t smem;
 };
 
+#ifndef NGX_LM_WIDE_TU
 // float -> double, four elements per thread (the f32 host entry point)
 __global__ void k_widen(const float *__restrict__ in, double *__restrict__ out,
                         size_t n) {
@@ -1542,13 +1543,16 @@ __global__ void k_widen(const float *__restrict__ in, double *__restrict__ out,
         for (size_t k = i; k < n && k < i + 4; k++) out[k] = in[k];
     }
 }
+#endif
 
+#ifndef NGX_LM_WIDE_TU
 // stamp_start = 0..n and stamp_band = 0 for n one-stamp objects
 __global__ void k_iota_zero(int n, int32_t *start, int32_t *band) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n) start[i] = i;
     if (i < n) band[i] = 0;
 }
+#endif
 
 template <typename K>
 static int config_and_launch(K kernel, const LMArgs &a, int threads,
@@ -1577,6 +1581,7 @@ using namespace ngx;
 
 extern "C" {
 
+#ifndef NGX_LM_WIDE_TU
 int ngx_lm_fit(int n, int model, const double *images, const double *weights,
                const ngx_jacobian *jac, int nrow, int ncol,
                const double *psf_pars, int npsf, const double *guess,
@@ -1695,6 +1700,7 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     return config_and_launch(k_lm_fit<1, 3, 2, 4, false>, a, threads,
                              smem_both, st);
 }
+#endif
 
 static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
                              const int32_t *stamp_band, int nband,
@@ -1741,13 +1747,20 @@ static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
     size_t smem = sizeof(double)
         * ((size_t)a.ngauss * REC + nrow + ncol + 48 * nwarps + LM_MAXP
            + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
-    if (wide)
-        return config_and_launch(k_lm_fit_multi<3, 2, ngx_lm_result_wide>, a,
-                                 threads, smem, as_stream(stream));
+    // the 8-parameter and the 14-parameter solver workspaces are compiled in
+    // separate translation units (ngx_lm.cu / ngx_lm_wide.cu)
+#ifdef NGX_LM_WIDE_TU
+    NGX_REQUIRE(wide);
+    return config_and_launch(k_lm_fit_multi<3, 2, ngx_lm_result_wide>, a,
+                             threads, smem, as_stream(stream));
+#else
+    NGX_REQUIRE(!wide);
     return config_and_launch(k_lm_fit_multi<3, 2, ngx_lm_result>, a, threads,
                              smem, as_stream(stream));
+#endif
 }
 
+#ifdef NGX_LM_WIDE_TU
 // CoellipFitter.go (fitting/fitters.py:120-141 -> CoellipFitModel,
 // results.py:628-674): n coelliptical gaussians, parameters (cen1, cen2, g1,
 // g2, T_1..T_n, F_1..F_n), forward-difference Jacobian (MINPACK lmdif),
@@ -1797,7 +1810,9 @@ int ngx_lm_fit_coellip(int n, int ngauss, const double *images,
         k_lm_fit<1, 3, 2, 1, true, 256, false, LM_MAXP, ngx_lm_result_wide>,
         a, threads, smem, as_stream(stream));
 }
+#endif
 
+#ifdef NGX_LM_WIDE_TU
 int ngx_lm_fit_coellip_host(int n, int ngauss, const double *images,
                             const double *weights, const ngx_jacobian *jac,
                             int nrow, int ncol, const double *psf_pars,
@@ -1825,7 +1840,9 @@ int ngx_lm_fit_coellip_host(int n, int ngauss, const double *images,
     NGX_CUDA(dr.to_host(res));
     return NGX_OK;
 }
+#endif
 
+#ifndef NGX_LM_WIDE_TU
 int ngx_lm_fit_multi(int nobj, int model, const int32_t *stamp_start,
                      const int32_t *stamp_band, int nband,
                      const double *images, const double *weights,
@@ -1839,7 +1856,9 @@ int ngx_lm_fit_multi(int nobj, int model, const int32_t *stamp_start,
                              guess, prior, lm_pars, ignore_zero_weight, res, 0,
                              stream);
 }
+#endif
 
+#ifdef NGX_LM_WIDE_TU
 int ngx_lm_fit_multi_wide(int nobj, int model, const int32_t *stamp_start,
                           const int32_t *stamp_band, int nband,
                           const double *images, const double *weights,
@@ -1853,6 +1872,7 @@ int ngx_lm_fit_multi_wide(int nobj, int model, const int32_t *stamp_start,
                              guess, prior, lm_pars, ignore_zero_weight, res, 1,
                              stream);
 }
+#endif
 
 }  // extern "C"
 
@@ -1893,6 +1913,7 @@ static int lm_fit_multi_host_impl(int nobj, int model,
 
 extern "C" {
 
+#ifndef NGX_LM_WIDE_TU
 int ngx_lm_fit_multi_host(int nobj, int model, const int32_t *stamp_start,
                           const int32_t *stamp_band, int nband,
                           const double *images, const double *weights,
@@ -1907,7 +1928,9 @@ int ngx_lm_fit_multi_host(int nobj, int model, const int32_t *stamp_start,
                                   npsf, guess, prior, lm_pars,
                                   ignore_zero_weight, res, 0);
 }
+#endif
 
+#ifdef NGX_LM_WIDE_TU
 int ngx_lm_fit_multi_wide_host(int nobj, int model,
                                const int32_t *stamp_start,
                                const int32_t *stamp_band, int nband,
@@ -1923,7 +1946,9 @@ int ngx_lm_fit_multi_wide_host(int nobj, int model,
                                   npsf, guess, prior, lm_pars,
                                   ignore_zero_weight, res, 1);
 }
+#endif
 
+#ifndef NGX_LM_WIDE_TU
 // the host-buffer pipeline behind ngx_lm_fit_host (stamps as doubles) and
 // ngx_lm_fit_host_f32 (stamps as floats: half the bytes over PCIe, which is
 // what bounds the call; widened to double on the device, exactly)
@@ -2097,7 +2122,9 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
     }
     return NGX_OK;
 }
+#endif
 
+#ifndef NGX_LM_WIDE_TU
 int ngx_lm_fit_host(int n, int model, const double *images,
                     const double *weights, const ngx_jacobian *jac, int nrow,
                     int ncol, const double *psf_pars, int npsf,
@@ -2108,7 +2135,9 @@ int ngx_lm_fit_host(int n, int model, const double *images,
                             psf_pars, npsf, guess, prior, lm_pars,
                             ignore_zero_weight, res);
 }
+#endif
 
+#ifndef NGX_LM_WIDE_TU
 int ngx_lm_fit_host_f32(int n, int model, const float *images,
                         const float *weights, const ngx_jacobian *jac,
                         int nrow, int ncol, const double *psf_pars, int npsf,
@@ -2119,5 +2148,6 @@ int ngx_lm_fit_host_f32(int n, int model, const float *images,
                             psf_pars, npsf, guess, prior, lm_pars,
                             ignore_zero_weight, res);
 }
+#endif
 
 }  // extern "C"

@@ -28,10 +28,11 @@
 
 namespace ngx {
 
-// workspace size: 5 coelliptical gaussians (4 + 2 * 5 parameters); multi-band
-// fits use up to 5 + 7, the single-stamp galaxy models at most 8
+// workspace size: the galaxy models and multi-band fits with up to 3 bands
+// need 8; ngx_lm_wide.cu compiles the same code with 14 (5 coelliptical
+// gaussians = 4 + 2 * 5 parameters, multi-band fits with up to 5 + 7)
 #ifndef LM_MAXP
-#define LM_MAXP 14
+#define LM_MAXP 8
 #endif
 #define LM_EPSMCH 2.220446049250313e-16
 #define LM_DWARF 2.2250738585072014e-308

@@ -16,7 +16,7 @@ namespace ngx {
 #define NGX_STEP_PRIOR 1.0e-8       // results.py:935
 #define NGX_MAX_PRIOR_ROWS LM_MAXP
 
-__device__ __noinline__ int prior1d_lnprob(const ngx_prior1d &p, double val,
+static __device__ __noinline__ int prior1d_lnprob(const ngx_prior1d &p, double val,
                                      double *lnp) {
     switch (p.kind) {
     case NGX_P_FLAT:
@@ -80,7 +80,7 @@ __device__ inline int prior1d_fdiff(const ngx_prior1d &p, double val,
     return NGX_ST_OK;
 }
 
-__device__ __noinline__ int gprior_lnprob(const ngx_prior &pr, double g1, double g2,
+static __device__ __noinline__ int gprior_lnprob(const ngx_prior &pr, double g1, double g2,
                                     double *lnp) {
     double sig2 = pr.g_sigma * pr.g_sigma;
     double sig2inv = 1.0 / sig2;
@@ -124,7 +124,7 @@ __host__ __device__ inline int prior_nrows(int model, const ngx_prior &pr) {
 // simple: 0 cen1, 1 cen2, 2 g, 3 T, 4.. F per band   (sqrt(clip(-2 lnp)))
 // bdf   : 0 cen1, 1 cen2, 2 g, 3 T, 4 fracdev, 5 F   (signed get_fdiff)
 // bd    : 0 cen1, 1 cen2, 2 g, 3 T, 4 logTratio, 5 fracdev, 6 F  (signed)
-__device__ __noinline__ int prior_row(int model, const ngx_prior &pr,
+static __device__ __noinline__ int prior_row(int model, const ngx_prior &pr,
                                 const double *p, int row, double *out) {
     double lnp;
     int st;
@@ -211,7 +211,7 @@ __device__ inline int prior_fill_fdiff(int model, const ngx_prior &pr,
 }
 
 // prior.get_lnprob_scalar
-__device__ __noinline__ int prior_lnprob(int model, const ngx_prior &pr,
+static __device__ __noinline__ int prior_lnprob(int model, const ngx_prior &pr,
                                    const double *p, double *out) {
     if (!pr.present) { *out = 0.0; return NGX_ST_OK; }
     double s2inv1 = 1.0 / (pr.sigma1 * pr.sigma1);
@@ -261,7 +261,7 @@ __device__ __noinline__ int prior_lnprob(int model, const ngx_prior &pr,
 // fallback.  Row r depends only on the parameters prior_row_of_par maps to
 // it, so the other entries of the reference's dense difference are exactly
 // (f0 - f0)/step = 0 and are not evaluated.  jp is [nrows][np].
-__device__ __noinline__ int prior_jacobian(int model, const ngx_prior &pr,
+static __device__ __noinline__ int prior_jacobian(int model, const ngx_prior &pr,
                                      const double *pars, int np,
                                      const double *f0, double *jp) {
     int nr = prior_nrows(model, pr);
