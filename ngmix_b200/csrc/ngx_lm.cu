@@ -1807,7 +1807,7 @@ int ngx_lm_fit_coellip(int n, int ngauss, const double *images,
            + 16 + 2 * (size_t)a.nq + nrow + ncol + 48 * nwarps + LM_MAXP
            + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
     return config_and_launch(
-        k_lm_fit<1, 3, 2, 1, true, 256, false, LM_MAXP, ngx_lm_result_wide>,
+        k_lm_fit<1, 3, 2, 2, true, 256, false, LM_MAXP, ngx_lm_result_wide>,
         a, threads, smem, as_stream(stream));
 }
 #endif
