@@ -264,11 +264,10 @@ def bench_coellip(args, _lib, b):
     n = min(b["images"].shape[0], 20000)
     out = {}
     for ngauss in (2, 3):
+        # CoellipPSFGuesser's recipe (guessers.py:1106-1216), vectorised over
+        # the batch instead of one Observation at a time
         guess = np.zeros((n, 4 + 2 * ngauss))
-        class _O(object):
-            pass
         rng = np.random.RandomState(11)
-        guesser = ngmix.guessers.CoellipPSFGuesser(rng=rng, ngauss=ngauss)
         T = ngmix.moments.fwhm_to_T(0.263 * 3.5)
         flux = b["images"][:n].sum(axis=(1, 2))
         for i in range(n):
@@ -282,7 +281,6 @@ def bench_coellip(args, _lib, b):
             g[4 + ngauss:] = flux[i] * np.array(pr) * rng.uniform(0.99, 1.01,
                                                                   ngauss)
             guess[i] = g
-        del guesser
         _lib.lm_fit_coellip(ngauss, b["images"][:64], b["weights"][:64],
                             b["jac"][:64], None, guess[:64])
         t0 = time.perf_counter()
