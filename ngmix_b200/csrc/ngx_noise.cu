@@ -27,7 +27,7 @@ struct NoiseMap {
     int rows[NZ_MAXK];   // which image of D is parameter a's derivative
 };
 
-// grid (nk, n): one CTA correlates one derivative image with the noise image.
+// grid (n, nk): one CTA correlates one derivative image with the noise image.
 // GM: the two staged planes live in a per-CTA slice of a global scratch
 // buffer (stamps too large for shared memory).
 template <bool GM>
@@ -38,7 +38,7 @@ k_noise_corr(int nk, NoiseMap map, const double *__restrict__ D, int nd,
              const double *__restrict__ noise, int nrow, int ncol, int wp,
              double *__restrict__ C, double *gscratch) {
     extern __shared__ double smem_d[];
-    const int a = blockIdx.x, obj = blockIdx.y;
+    const int a = blockIdx.y, obj = blockIdx.x;
     const int ntot = nrow * ncol;
     const int p2 = 2 * wp + 1;                 // odd pitch: rows spread over banks
     double *k2 = GM ? gscratch + ((size_t)obj * nk + a)
@@ -158,7 +158,7 @@ static int noise_b_launch(int n, int nk, const NoiseMap &map, const double *D,
         const size_t ntot = (size_t)nrow * ncol;
         for (int i0 = 0; i0 < n; i0 += chunk) {
             const int m = n - i0 < chunk ? n - i0 : chunk;
-            dim3 grid(nk, m);
+            dim3 grid(m, nk);
             k_noise_corr<true><<<grid, 256, 0, st>>>(
                 nk, map, D + (size_t)i0 * nd * ntot, nd,
                 scale ? scale + (size_t)i0 * nk : nullptr,
@@ -172,7 +172,7 @@ static int noise_b_launch(int n, int nk, const NoiseMap &map, const double *D,
         NGX_CUDA(cudaFuncSetAttribute(
             k_noise_corr<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int)smem));
-        dim3 grid(nk, n);
+        dim3 grid(n, nk);
         k_noise_corr<false><<<grid, 256, smem, st>>>(
             nk, map, D, nd, scale, weights, noise, nrow, ncol, wp, C, nullptr);
         NGX_LAUNCH_CHECK();

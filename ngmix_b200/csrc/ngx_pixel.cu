@@ -219,9 +219,9 @@ __global__ void k_make_pixels(int nrow, int ncol,
 __global__ void k_make_coords(int nrow, int ncol,
                               const ngx_jacobian *__restrict__ jac,
                               ngx_coord *__restrict__ coords) {
-    int obj = blockIdx.y;
+    int obj = blockIdx.x;
     int ntot = nrow * ncol;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = blockIdx.y * blockDim.x + threadIdx.x;
     if (p >= ntot) return;
     ngx_jacobian j = jac[obj];
     int row = p / ncol, col = p - row * ncol;
@@ -243,7 +243,7 @@ __global__ void k_render(int ngauss, const ngx_gauss *__restrict__ gmix,
     GaussV *gv = (GaussV *)(smem_d + 16);       // ngauss
     ngx_gauss *gr = (ngx_gauss *)(gv + ngauss); // ngauss (exact path)
     __shared__ int bad;
-    int obj = blockIdx.y;
+    int obj = blockIdx.x;
     int ntot = nrow * ncol;
     ngx_jacobian j = jac[obj];
     double area = j.scale * j.scale;
@@ -259,13 +259,13 @@ __global__ void k_render(int ngauss, const ngx_gauss *__restrict__ gmix,
     }
     __syncthreads();
     if (bad) {
-        if (threadIdx.x == 0 && blockIdx.x == 0 && status)
+        if (threadIdx.x == 0 && blockIdx.y == 0 && status)
             status[obj] = NGX_ST_RANGE_ERROR;
         return;
     }
-    if (threadIdx.x == 0 && blockIdx.x == 0 && status)
+    if (threadIdx.x == 0 && blockIdx.y == 0 && status)
         status[obj] = NGX_ST_OK;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = blockIdx.y * blockDim.x + threadIdx.x;
     if (p >= ntot) return;
     int row = p / ncol, col = p - row * ncol;
     double v, u;
@@ -632,7 +632,7 @@ __global__ void k_deriv_images(int ngauss, const double *__restrict__ gpars,
     extern __shared__ double smem_d[];
     double *tab = smem_d;             // 16
     double *gc = smem_d + 16;         // ngauss * 16
-    int obj = blockIdx.y;
+    int obj = blockIdx.x;
     int ntot = nrow * ncol;
     ngx_jacobian j = jac[obj];
     double area = j.scale * j.scale;
@@ -656,7 +656,7 @@ __global__ void k_deriv_images(int ngauss, const double *__restrict__ gpars,
         }
     }
     __syncthreads();
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = blockIdx.y * blockDim.x + threadIdx.x;
     if (p >= ntot) return;
     int row = p / ncol, col = p - row * ncol;
     double v, u;
@@ -850,7 +850,7 @@ int ngx_make_coords(int n, int nrow, int ncol, const ngx_jacobian *jac,
                     ngx_coord *coords, void *stream) {
     NGX_REQUIRE(n >= 0 && nrow >= 1 && ncol >= 1 && jac && coords);
     if (n == 0) return NGX_OK;
-    dim3 grid((nrow * ncol + 255) / 256, n);
+    dim3 grid(n, (nrow * ncol + 255) / 256);   // objects on x: no 65535 limit
     k_make_coords<<<grid, 256, 0, as_stream(stream)>>>(nrow, ncol, jac,
                                                        coords);
     NGX_LAUNCH_CHECK();
@@ -866,7 +866,7 @@ int ngx_render(int n, int ngauss, const ngx_gauss *gmix,
     size_t smem = 16 * sizeof(double)
         + (size_t)ngauss * (sizeof(GaussV) + sizeof(ngx_gauss));
     NGX_REQUIRE(smem <= 48 * 1024);
-    dim3 grid((nrow * ncol + 255) / 256, n);
+    dim3 grid(n, (nrow * ncol + 255) / 256);   // objects on x: no 65535 limit
     k_render<<<grid, 256, smem, as_stream(stream)>>>(
         ngauss, gmix, jac, nrow, ncol, fast_exp, images, status);
     NGX_LAUNCH_CHECK();
@@ -959,7 +959,7 @@ int ngx_deriv_images(int n, int ngauss, const double *gpars,
     if (n == 0) return NGX_OK;
     size_t smem = (16 + 16 * (size_t)ngauss) * sizeof(double);
     NGX_REQUIRE(smem <= 48 * 1024);
-    dim3 grid((nrow * ncol + 127) / 128, n);
+    dim3 grid(n, (nrow * ncol + 127) / 128);
     k_deriv_images<<<grid, 128, smem, as_stream(stream)>>>(
         ngauss, gpars, dcov, jac, nrow, ncol, out);
     NGX_LAUNCH_CHECK();

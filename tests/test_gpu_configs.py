@@ -316,3 +316,32 @@ def test_stamps_larger_than_shared_memory(ngx, ora):
         assert np.array_equal(ares["flags"], oam["flags"])
         assert np.array_equal(ares["numiter"], oam["numiter"])
         assert np.allclose(ares["pars"], oam["pars"], rtol=1e-9, atol=1e-12)
+
+
+def test_more_objects_than_a_grid_dimension(ngx):
+    """batches beyond 65 535 objects (the y / z limit of a CUDA grid): the
+    kernels that use a two-dimensional grid keep the objects on x"""
+    n = 70000
+    rng = np.random.RandomState(2)
+    pars = np.zeros((n, 6))
+    pars[:, 4] = rng.uniform(0.2, 0.5, n)
+    pars[:, 5] = rng.uniform(1.0, 2.0, n)
+    jac = np.array([[1.5, 1.5, 0.263, 0.0, 0.0, 0.263, 0.263 ** 2,
+                     0.263]] * n)
+    gm, st = ngx.gmix_fill("gauss", pars)
+    assert not st.any()
+    im, st = ngx.render(gm, jac, (4, 4), fast_exp=True)
+    assert not st.any()
+    tail, _ = ngx.render(gm[-3:], jac[-3:], (4, 4), fast_exp=True)
+    assert np.array_equal(im[-3:], tail) and im[-1].sum() > 0
+    coords = ngx.make_coords((4, 4), jac)
+    assert np.array_equal(coords[-1], coords[0])
+    gpars = np.stack([gm[k] for k in ("p", "row", "col", "irr", "irc", "icc")],
+                     axis=-1)
+    dcov = np.zeros((n, 1, 3, 3))
+    dcov[:, 0, 2, 0] = dcov[:, 0, 2, 2] = 0.5
+    out = ngx.deriv_images(gpars, dcov, jac, (4, 4))
+    assert np.allclose(out[:, 0].reshape(n, 4, 4), im, rtol=1e-12)
+    recs = ngx.lm_fit("gauss", im, np.full(im.shape, 1e4), jac, None,
+                      pars * 1.01)
+    assert (recs["flags"] == 0).sum() > 0.99 * n
