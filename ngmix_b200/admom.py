@@ -9,7 +9,7 @@ vectorised over the batch on the host.
 import numpy as np
 
 from . import _lib, flags as _flags
-from .gexceptions import GMixRangeError
+from .gexceptions import GMixRangeError  # noqa: F401 (re-export)
 from .gmix import GMix, GMixModel
 from .observation import Observation
 from .shape import e1e2_to_g1g2, fwhm_to_T

@@ -12,7 +12,7 @@ import numpy as np
 from . import _lib
 from .defaults import DEFAULT_LM_PARS
 from .gexceptions import GMixFatalError, GMixRangeError
-from .gmix import (GMix, get_model_name, get_model_npars, get_model_num,
+from .gmix import (get_model_name, get_model_npars, get_model_num,
                    make_gmix_model)
 from .observation import Observation, get_mb_obs
 

@@ -2,7 +2,6 @@
 Flag bit values of the fitting results; the values are part of the result
 contract and identical to the reference's (ngmix/flags.py:3-28).
 """
-import numpy as np
 
 NO_ATTEMPT = 2**0
 CEN_SHIFT = 2**1
