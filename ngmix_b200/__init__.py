@@ -27,6 +27,6 @@ from .fitting import (  # noqa: F401
 from . import guessers, runners, bootstrap  # noqa: F401
 from .em import EMFitter, run_em, em_batch  # noqa: F401
 from .admom import AdmomFitter, run_admom, admom_batch  # noqa: F401
-from . import joint_prior, moments, gaussmom  # noqa: F401
+from . import joint_prior, moments, gaussmom, gaussap  # noqa: F401
 from .gaussmom import GaussMom, gaussmom_batch  # noqa: F401
 from .batch import ObservationBatch  # noqa: F401

@@ -193,6 +193,34 @@ class GMix(object):
 
     get_psum = get_flux
 
+    def get_gaussap_flux(self, fwhm=None, sigma=None, T=None):
+        """flux of the mixture under a round gaussian aperture weight
+        (gmix/gmix.py:325-391): every component contributes p times
+        sqrt(det((S^-1 + W^-1)^-1) / det S), capped at 1, with W the weight's
+        covariance; components with det <= 1e-200 count in full"""
+        from . import moments
+        if fwhm is not None:
+            sigma = moments.fwhm_to_sigma(fwhm)
+        elif T is not None:
+            sigma = np.sqrt(T / 2.0)
+        elif sigma is not None:
+            sigma = float(sigma)
+        else:
+            raise ValueError("send weight function sigma, fwhm, or T")
+        gm = self.get_data()
+        winv = 1.0 / sigma ** 2
+        det = gm["det"]
+        fac = np.ones(gm.size)
+        ok = det > 1.0e-200
+        with np.errstate(all="ignore"):
+            # S^-1 + W^-1 for S = [[irr, irc], [irc, icc]]
+            a = gm["icc"][ok] / det[ok] + winv
+            b = -gm["irc"][ok] / det[ok]
+            c = gm["irr"][ok] / det[ok] + winv
+            f = np.sqrt(1.0 / ((a * c - b * b) * det[ok]))
+        fac[ok] = np.where(np.isfinite(f), np.minimum(f, 1.0), 1.0)
+        return float((gm["p"] * fac).sum())
+
     def set_flux(self, psum):
         gm = self._data
         gm["p"] *= psum / gm["p"].sum()

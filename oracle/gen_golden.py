@@ -889,6 +889,43 @@ def gen_lm_coellip():
     save("lm_coellip", **out)
 
 
+def gen_gaussap():
+    """gaussian-aperture fluxes (GMix.get_gaussap_flux, ngmix.gaussap)"""
+    from ngmix import gaussap
+    rng = np.random.RandomState(41)
+    out = {}
+    for model, npars in (("exp", 7), ("dev", 6), ("bdf", 8), ("gauss", 6)):
+        n = 6
+        pars = np.zeros((n, npars))
+        pars[:, 0:2] = rng.uniform(-0.1, 0.1, (n, 2))
+        pars[:, 2:4] = rng.uniform(-0.4, 0.4, (n, 2))
+        pars[:, 4] = rng.uniform(-0.1, 2.0, n)
+        k = 5
+        if model == "bdf":
+            pars[:, 5] = rng.uniform(0.0, 1.0, n)
+            k = 6
+        pars[:, k:] = rng.uniform(1.0, 100.0, (n, npars - k))
+        pars[1, 2] = 0.99
+        pars[1, 3] = 0.5             # |g| > 1: range error
+        mask = np.ones(n, dtype=bool)
+        mask[2] = False
+        flux, flags = gaussap.get_gaussap_flux(pars, model, 2.5, mask=mask,
+                                               verbose=False)
+        out[model + "_pars"], out[model + "_mask"] = pars, mask
+        out[model + "_flux"], out[model + "_flags"] = flux, flags
+    n = 4
+    pars = np.zeros((n, 6))
+    pars[:, 2:4] = rng.uniform(-0.3, 0.3, (n, 2))
+    pars[:, 4] = rng.uniform(0.1, 2.0, n)
+    pars[:, 5] = rng.uniform(1.0, 100.0, n)
+    fd, td = rng.uniform(0, 1, n), rng.uniform(0.5, 2.0, n)
+    flux, flags = gaussap.get_gaussap_flux(pars, "cm", 2.0, fracdev=fd,
+                                           TdByTe=td, verbose=False)
+    out["cm_pars"], out["cm_fracdev"], out["cm_TdByTe"] = pars, fd, td
+    out["cm_flux"], out["cm_flags"] = flux, flags
+    save("gaussap", **out)
+
+
 def gen_moments():
     """GaussMom (6 and 17 moments) on galaxy stamps, and get_weighted_sums
     with a two-gaussian off-centre weight and a maxrad"""
@@ -1216,6 +1253,7 @@ GENERATORS = {
     "shape_moments": gen_shape_moments,
     "lm_priors2": gen_lm_priors2,
     "lm_coellip": gen_lm_coellip,
+    "gaussap": gen_gaussap,
     "moments": gen_moments,
     "lm_multi": gen_lm_multi,
     "lm_multi_wide": gen_lm_multi_wide,

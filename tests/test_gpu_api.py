@@ -446,3 +446,20 @@ def test_batch_api_matches_single(ng):
                             load_golden("em_admom")["em_guess"][:4])
     assert np.array_equal(res["numiter"],
                           load_golden("em_admom")["em_numiter"][:4])
+
+
+def test_gaussap_fluxes(ng):
+    """gaussian-aperture fluxes against the reference (ngmix/gaussap.py,
+    GMix.get_gaussap_flux): values, range-error and not-attempted flags"""
+    g = load_golden("gaussap")
+    for model in ("exp", "dev", "bdf", "gauss"):
+        flux, flags = ng.gaussap.get_gaussap_flux(
+            g[model + "_pars"], model, 2.5, mask=g[model + "_mask"])
+        assert np.array_equal(flags, g[model + "_flags"])
+        assert np.allclose(flux, g[model + "_flux"], rtol=1e-12,
+                           equal_nan=True)
+    flux, flags = ng.gaussap.get_gaussap_flux(
+        g["cm_pars"], "cm", 2.0, fracdev=g["cm_fracdev"],
+        TdByTe=g["cm_TdByTe"])
+    assert np.array_equal(flags, g["cm_flags"])
+    assert np.allclose(flux, g["cm_flux"], rtol=1e-12)
