@@ -57,6 +57,8 @@ assert LM_RESULT_DTYPE.itemsize == 1248 and ADMOM_RESULT_DTYPE.itemsize == 592
 
 MODELS = {"full": 0, "gauss": 1, "turb": 2, "exp": 3, "dev": 4, "bdf": 6,
           "coellip": 7, "cm": 9, "bd": 10}
+# parameters of the models ngx_lm_fit takes (gmix.py model tables)
+MODEL_NPARS = {"gauss": 6, "turb": 6, "exp": 6, "dev": 6, "bdf": 7, "bd": 8}
 EM_VARIANTS = {"full": 0, "fixcen": 1, "fixcov": 2, "fluxonly": 3}
 
 ST_OK, ST_RANGE_ERROR, ST_ZERO_DIV, ST_FATAL = 0, 1, 2, 3
@@ -129,7 +131,8 @@ def build(force=False):
         mt = os.path.getmtime(LIBPATH)
         if all(os.path.getmtime(s) <= mt for s in srcs):
             return LIBPATH
-    subprocess.check_call(["make", "-C", CSRC, "libngx.so"])
+    subprocess.check_call(["make", "-j", str(min(8, os.cpu_count() or 1)),
+                           "-C", CSRC, "libngx.so"])
     return LIBPATH
 
 
@@ -403,14 +406,23 @@ def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
     if images.ndim == 2:
         images, weights = images[None], weights[None]
     n, H, W = images.shape
+    if weights.shape != images.shape:
+        raise ValueError("weights %s and images %s differ in shape"
+                         % (weights.shape, images.shape))
     jac = as_jac(jac, n)
     guess = np.atleast_2d(_f8(guess))
+    if guess.shape != (n, MODEL_NPARS[model]):
+        raise ValueError("guess has shape %s, expected %s for model %s"
+                         % (guess.shape, (n, MODEL_NPARS[model]), model))
     if psf_pars is None:
         npsf = 0
     else:
         psf_pars = _f8(psf_pars)
         npsf = psf_pars.shape[1] if psf_pars.ndim == 3 \
             else psf_pars.size // max(6 * n, 1)
+        if psf_pars.size != n * npsf * 6:
+            raise ValueError("psf_pars has %d values, expected n*npsf*6"
+                             % psf_pars.size)
         psf_pars = psf_pars.reshape(n, npsf, 6)
     pr = prior if prior is not None else Prior()
     lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)

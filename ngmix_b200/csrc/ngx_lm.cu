@@ -1508,21 +1508,18 @@ k_lm_fit_multi(LMArgs a) {
 }
 
 // ---------------------------------------------------------------------
-static int *g_counter = nullptr;       // work-queue counter, one per process
-static int g_counter_dev = -1;
-
-static thread_local int g_counter_slot = 0;
-
-static int get_counter(int **out) {
-    int dev = 0;
-    NGX_CUDA(cudaGetDevice(&dev));
-    if (!g_counter || g_counter_dev != dev) {
-        NGX_CUDA(cudaMalloc((void **)&g_counter, 64 * sizeof(int)));
-        g_counter_dev = dev;
+// Work-queue counter of one launch: a stream-ordered allocation that lives
+// exactly as long as the kernel using it (allocated and zeroed before the
+// launch, freed behind it on the same stream).  Launches on different
+// streams, devices or host threads never share a counter and the library
+// keeps no global state for it.
+static int get_counter(int **out, cudaStream_t st) {
+    NGX_CUDA(cudaMallocAsync((void **)out, 128, st));
+    cudaError_t e = cudaMemsetAsync(*out, 0, sizeof(int), st);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(*out, st);
+        NGX_CUDA(e);
     }
-    // 64 counters: launches that may overlap (the two compute streams of the
-    // host pipeline) use different slots
-    *out = g_counter + 16 * g_counter_slot;
     return NGX_OK;
 }
 
@@ -1555,8 +1552,9 @@ __global__ void k_iota_zero(int n, int32_t *start, int32_t *band) {
 #endif
 
 template <typename K>
-static int config_and_launch(K kernel, const LMArgs &a, int threads,
+static int config_and_launch(K kernel, const LMArgs &a_in, int threads,
                              size_t smem, cudaStream_t stream) {
+    const LMArgs &a0 = a_in;
     if (smem > (size_t)smem_optin_bytes())
         return fail(NGX_ERR_ARG,
                     "ngx_lm_fit: stamp + mixture do not fit shared memory%s%s");
@@ -1568,10 +1566,14 @@ static int config_and_launch(K kernel, const LMArgs &a, int threads,
                                                            threads, smem));
     if (per_sm < 1) per_sm = 1;
     int blocks = sm_count() * per_sm;
-    if (blocks > a.n) blocks = a.n;
-    NGX_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), stream));
+    if (blocks > a0.n) blocks = a0.n;
+    LMArgs a = a_in;
+    int rcc = get_counter(&a.counter, stream);
+    if (rcc) return rcc;
     kernel<<<blocks, threads, smem, stream>>>(a);
-    NGX_LAUNCH_CHECK();
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(a.counter, stream);
+    NGX_CUDA(e);
     return NGX_OK;
 }
 
@@ -1609,8 +1611,6 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     if (a.prior.present) {
         NGX_REQUIRE(a.prior.g_kind == 1);
     }
-    int rc = get_counter(&a.counter);
-    if (rc) return rc;
 
     bool analytic = lm_pars->analytic_jacobian
         && (model == NGX_GAUSS || model == NGX_EXP || model == NGX_DEV);
@@ -1678,10 +1678,15 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
         NGX_CUDA(cudaMallocAsync(
             (void **)&a.gscratch,
             sizeof(double) * (size_t)blocks * (nfd ? 2 : 1) * a.nq, st));
-        NGX_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), st));
+        int rcc = get_counter(&a.counter, st);
+        if (rcc) {
+            cudaFreeAsync(a.gscratch, st);
+            return rcc;
+        }
         kern<<<blocks, 256, smem_g, st>>>(a);
         cudaError_t e = cudaGetLastError();
         cudaFreeAsync(a.gscratch, st);
+        cudaFreeAsync(a.counter, st);
         NGX_CUDA(e);
         return NGX_OK;
     }
@@ -1737,8 +1742,6 @@ static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
     a.psf = psf_pars; a.guess = guess; a.res = res;
     a.stamp_start = stamp_start; a.stamp_band = stamp_band;
     NGX_REQUIRE(a.ngauss <= NGX_MAX_GAUSS);
-    int rc = get_counter(&a.counter);
-    if (rc) return rc;
     int threads = 128;
     NGX_REQUIRE(threads >= a.ngauss && threads >= 6 * npsf);
     a.tpr = (ncol + 7) / 8;
@@ -1795,8 +1798,6 @@ int ngx_lm_fit_coellip(int n, int ngauss, const double *images,
     a.psf = psf_pars; a.guess = guess; a.res = res;
     a.analytic = 0;
     NGX_REQUIRE(a.ngauss <= NGX_MAX_GAUSS);
-    int rc = get_counter(&a.counter);
-    if (rc) return rc;
     const int threads = 256, nwarps = 8;
     NGX_REQUIRE(threads >= a.ngauss && threads >= 6 * npsf);
     a.tpr = (ncol + 7) / 8;
@@ -2091,11 +2092,9 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
             k_widen<<<blocks, 256, 0, ks>>>(d_wt32[b], d_wt[b], cnt);
             NGX_LAUNCH_CHECK();
         }
-        g_counter_slot = 1 + b;
         int rc = ngx_lm_fit(cn, model, d_im[b], d_wt[b], d_jac[b], nrow, ncol,
                             npsf > 0 ? d_psf[b] : nullptr, npsf, d_guess[b],
                             prior, lm_pars, ignore_zero_weight, d_res[b], ks);
-        g_counter_slot = 0;
         if (rc) return rc;
         NGX_CUDA(cudaMemcpyAsync(res_dst + lo, d_res[b],
                                  cn * sizeof(ngx_lm_result),

@@ -85,7 +85,7 @@ def fit_batch(model, images, weights, jacobians, psf_pars, guesses,
             B[ok] = noise_cov.calc_noise_b(
                 model, recs["pars"][ok, :npars], psf_ok,
                 _lib.as_jac(jacobians)[ok], np.asarray(weights)[ok],
-                np.asarray(noise_images)[ok])
+                np.asarray(noise_images)[ok], per_object=True)
             noise_cov.apply_noise_cov_batch(recs, B, npars)
     return recs
 
@@ -179,6 +179,34 @@ def record_to_result(rec, model, npars, nband=None):
             res["flux"] = res["pars"][start:].copy()
             res["flux_cov"] = res["pars_cov"][start:, start:].copy()
             res["flux_err"] = np.sqrt(np.diag(res["flux_cov"]))
+    return res
+
+
+_STAT_KEYS = ("lnprob", "s2n_numer", "s2n_denom", "chi2per", "s2n", "s2n_w",
+              "npix", "dof", "g", "g_cov", "g_err", "T", "T_err", "flux",
+              "flux_err", "flux_cov")
+
+
+def refresh_result_after_noise_cov(res, nband):
+    """The reference applies the noise covariance BEFORE set_fit_result
+    (fitting/fitters.py:105-110), so every key derived from pars_cov comes
+    from the sandwich matrix, and a fit whose sandwich matrix is bad
+    (flags != 0) carries no fit statistics at all (results.py:45-72)."""
+    if res["flags"] != 0:
+        for k in _STAT_KEYS:
+            res.pop(k, None)
+        return res
+    n = res["pars"].size
+    cov, err = res["pars_cov"], res["pars_err"]
+    res["g_cov"] = cov[2:4, 2:4].copy()
+    res["g_err"] = err[2:4].copy()
+    res["T_err"] = float(np.sqrt(cov[4, 4]))
+    if nband > 1:
+        start = n - nband
+        res["flux_cov"] = cov[start:, start:].copy()
+        res["flux_err"] = np.sqrt(np.diag(res["flux_cov"]))
+    else:
+        res["flux_err"] = float(np.sqrt(cov[n - 1, n - 1]))
     return res
 
 
@@ -572,6 +600,7 @@ class Fitter(object):
                     Bk = np.full((len(kp), len(kp)), np.nan)
                 B[np.ix_(kp, kp)] += Bk
         noise_cov.apply_noise_cov(res, B)
+        refresh_result_after_noise_cov(res, nband)
 
 
 def fit_batch_coellip(ngauss, images, weights, jacobians, guesses,

@@ -79,11 +79,15 @@ def model_deriv_data(model, pars, psf_pars):
     return gpars, dcov
 
 
-def _fd_images(model, pars, psf_pars, jac, dims):
+def _fd_images(model, pars, psf_pars, jac, dims, per_object=False):
     """central-difference derivative images of the convolved model with the
-    fast exp, one per parameter (noise_cov.py:203-226): [n, npars, H*W]"""
+    fast exp, one per parameter (noise_cov.py:203-226): [n, npars, H*W].
+    A stepped point outside the model's domain raises for a single object
+    (as the reference does); with per_object the offender's images become
+    NaN instead, so only that object's covariance is flagged."""
     n, npars = pars.shape
     out = np.zeros((n, npars, dims[0] * dims[1]))
+    bad = np.zeros(n, dtype=bool)
     psf = None
     if psf_pars is not None:
         psf, _ = _lib.gmix_fill("full", np.asarray(psf_pars).reshape(n, -1))
@@ -95,20 +99,31 @@ def _fd_images(model, pars, psf_pars, jac, dims):
             p[:, ipar] += sign * step
             gm, st = _lib.gmix_fill(model, p)
             if st.any():
-                raise ValueError("stepped parameters outside the domain")
+                if not per_object:
+                    raise ValueError("stepped parameters outside the domain")
+                bad |= st != 0
+                # any in-domain stand-in keeps the launch going
+                p[st != 0] = pars[st != 0]
+                gm, _ = _lib.gmix_fill(model, p)
             if psf is not None:
                 gm = _lib.gmix_convolve(gm, psf)
             im, st = _lib.render(gm, jac, dims, fast_exp=True)
             if st.any():
-                raise ValueError("stepped parameters outside the domain")
+                if not per_object:
+                    raise ValueError("stepped parameters outside the domain")
+                bad |= st != 0
             ims.append(im.reshape(n, -1))
         out[:, ipar] = (ims[0] - ims[1]) / (2 * step[:, None])
+    out[bad] = np.nan
     return out
 
 
-def calc_noise_b(model, pars, psf_pars, jac, weights, noise):
+def calc_noise_b(model, pars, psf_pars, jac, weights, noise,
+                 per_object=False):
     """B [n, npars, npars] of n single-epoch, single-band fits
-    (noise_cov.py:90-137); weights / noise [n, H, W]"""
+    (noise_cov.py:90-137); weights / noise [n, H, W].  per_object: an object
+    whose derivative images cannot be formed gets a NaN matrix (flagged by
+    sandwich()) instead of aborting the batch."""
     pars = np.atleast_2d(np.asarray(pars, dtype="f8"))
     n, npars = pars.shape
     weights = np.ascontiguousarray(weights, dtype="f8")
@@ -118,8 +133,13 @@ def calc_noise_b(model, pars, psf_pars, jac, weights, noise):
     if model in SIMPLE_ANALYTIC_MODELS and np.all(pars[:, 5] != 0.0):
         gpars, dcov = model_deriv_data(model, pars, psf_pars)
         return _lib.noise_cov_b(gpars, dcov, pars[:, 5], jac, weights, noise)
-    dimages = _fd_images(model, pars, psf_pars, jac, dims)
-    return _lib.noise_b(dimages, weights, noise)
+    dimages = _fd_images(model, pars, psf_pars, jac, dims, per_object)
+    badobj = np.isnan(dimages).any(axis=(1, 2))
+    if badobj.any():
+        dimages[badobj] = 0.0
+    B = _lib.noise_b(dimages, weights, noise)
+    B[badobj] = np.nan
+    return B
 
 
 def check_cov(pcov):
@@ -181,6 +201,14 @@ def apply_noise_cov_batch(recs, B, npars):
             recs["flags"][i] |= cflags
             recs["pars_cov"][i][:n * n] = CDEF
             recs["pars_err"][i][:n] = CDEF
+            # no fit statistics on a flagged fit (results.py:45-72)
+            for k in ("lnprob", "s2n_numer", "s2n_denom", "chi2per", "s2n",
+                      "T", "T_err", "flux", "flux_err"):
+                recs[k][i] = np.nan
+            recs["npix"][i] = 0
+            recs["dof"][i] = 0
         else:
             recs["pars_cov"][i][:n * n] = cov.ravel()
             recs["pars_err"][i][:n] = np.sqrt(np.diag(cov))
+            recs["T_err"][i] = np.sqrt(cov[4, 4])
+            recs["flux_err"][i] = np.sqrt(cov[n - 1, n - 1])
