@@ -14,9 +14,16 @@ fits its own 10 000 stamps (seeded by global index).
 
     python bench.py [--gpus N --steps K --warmup W] [--impl reference]
 
-prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement
-of the reference algorithm (oracle/, kind "port": the reference is Python +
-numba + scipy and cannot travel to the GPU box) with all host threads.
+prints ONE JSON line (rank 0).  Beside the headline numbers the line carries
+"sustained" (the same step back to back for a few seconds) and "configs": the
+other BASELINE.json configs (bench_configs.py: single-fit latency, configs[1]
+at noise 1.0, 100k EM + admom, 1M bdf fits and the 200k x 5 metacal-style
+batch, the last two split over the ranks).
+
+`--impl reference` times the reference's own CPU implementation on all host
+cores: the UNMODIFIED ngmix (numba + scipy) through Fitter.go under
+multiprocessing when oracle/make_ref.sh has staged it into oracle/_ref
+(kind "reference"), else the C restatement in oracle/ (kind "port").
 """
 import argparse
 import json
@@ -151,45 +158,72 @@ def time_cpu_port(b, nthreads, target_s=12.0):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port, all
-    host threads) on a bounded sample of the same workload per step"""
+    """--impl reference: the reference's own CPU implementation of the path
+    on the host cores, on a bounded sample of the same workload per step.
+
+    kind "reference" (default when oracle/_ref is staged): the UNMODIFIED
+    ngmix (numba + scipy MINPACK) through Fitter.go, one process per core
+    with multiprocessing - the north-star's CPU arm (oracle/ref_arm.py).
+    kind "port": the C restatement (oracle/), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count()
-    nsample = min(NOBJ, 256 * cores)     # ~0.5 s of CPU work per step
-    b = make_inputs_host(nsample, seed0=0)
-    times = []
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle
-    oracle.build()
-    for step in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        oracle.lm_fit_batch("exp", b["images"], b["weights"], b["jac"],
-                            b["psf"], b["guess"], nthreads=cores)
-        dt = time.perf_counter() - t0
-        if step >= args.warmup:
-            times.append(dt)
-        # keep the whole run within a few minutes
-        if sum(times) > 120 and len(times) >= 1:
-            break
-    ms = 1e3 * float(np.mean(times))
-    value = nsample / (ms * 1e-3)
+    import ref_arm
+    kind = args.kind
+    if kind == "auto":
+        kind = "reference" if ref_arm.available()[0] else "port"
+    if kind == "reference":
+        nsample = min(NOBJ, 64 * cores)       # ~0.3 s of CPU work per step
+        b = make_inputs_host(nsample, seed0=0)
+        r = ref_arm.time_batch(b, kind="lm", model="exp", nproc=cores,
+                               steps=args.steps, warmup=max(1, args.warmup),
+                               max_seconds=120.0)
+        ms, value, nsteps = r["ms_per_step"], r["value"], r["steps"]
+        sample = ("%d stamps per step, %d processes (multiprocessing, fork) "
+                  "over objects, Fitter.go loop only; %.0f fits/s per core; "
+                  "Observation construction %.0f us per object excluded"
+                  % (nsample, cores, r["per_core_fits_per_s"],
+                     1e6 * r["obs_construction_s_per_object"]))
+        impl_note = "ngmix %s (numba + scipy MINPACK), unmodified" \
+            % getattr(ref_arm.import_ref(), "__version__", "?")
+    else:
+        nsample = min(NOBJ, 256 * cores)     # ~0.5 s of CPU work per step
+        b = make_inputs_host(nsample, seed0=0)
+        times = []
+        import oracle
+        oracle.build()
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            oracle.lm_fit_batch("exp", b["images"], b["weights"], b["jac"],
+                                b["psf"], b["guess"], nthreads=cores)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+            # keep the whole run within a few minutes
+            if sum(times) > 120 and len(times) >= 1:
+                break
+        ms = 1e3 * float(np.mean(times))
+        value = nsample / (ms * 1e-3)
+        nsteps = len(times)
+        sample = "%d stamps per step, %d threads over objects" \
+            % (nsample, cores)
+        impl_note = "C restatement of the reference algorithm (oracle/)"
     out = {
         "impl": "reference",
         "metric": "galaxy LM fits/sec",
         "value": value, "unit": "fits/s", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": args.warmup, "ms_per_step": ms,
+        "steps": nsteps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "exp-model LM fits, 48x48 stamps, 3-gaussian "
-                               "PSF (18 gaussians), analytic Jacobian, "
-                               "no prior; CPU sample of %d stamps per step"
-                               % nsample},
+        "config": {"workload": "configs[1]: exp-model LM fits, 48x48 stamps, "
+                               "3-gaussian PSF (18 gaussians), analytic "
+                               "Jacobian, no prior, noise 0.01; CPU sample "
+                               "of %d stamps per step" % nsample,
+                   "implementation": impl_note},
         "cpu_baseline": {"value": value, "unit": "fits/s", "cores": cores,
-                         "kind": "port",
-                         "sample": "%d stamps per step, %d threads over "
-                                   "objects" % (nsample, cores)},
+                         "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -205,6 +239,18 @@ def main():
     ap.add_argument("--nobj", type=int, default=NOBJ)
     ap.add_argument("--no-cpu", action="store_true",
                     help="skip the cpu_baseline leg")
+    ap.add_argument("--kind", default="auto",
+                    choices=["auto", "reference", "port"],
+                    help="CPU arm: the staged numba reference or the C port")
+    ap.add_argument("--configs", default="all",
+                    help="comma list of extra configs (1,2b,3,4,5), 'all' "
+                         "or 'none'")
+    ap.add_argument("--cfg-steps", type=int, default=2,
+                    help="timed steps of each extra config")
+    ap.add_argument("--npsf", type=int, default=100000)
+    ap.add_argument("--nbdf", type=int, default=1000000)
+    ap.add_argument("--nmcal", type=int, default=200000)
+    ap.add_argument("--sustain-seconds", type=float, default=3.0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -229,8 +275,10 @@ def main():
         numa_node = shard.bind_to_gpu_numa_node(local)
     _lib.init(local)
     if world > 1:
-        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
-        os.environ.pop("NCCL_DEBUG", None)
+        # keep stdout to the one JSON line: NCCL's log (NCCL_DEBUG=INFO /
+        # VERSION prints to stdout by default) goes to stderr instead, where
+        # the rank count stays observable
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     nobj = args.nobj
@@ -388,6 +436,64 @@ def main():
     torch.cuda.synchronize()
     fdiff_ms = f0.elapsed_time(f1) / args.steps
 
+    # ---- sustained rate: the same device-resident step back to back for a
+    # few seconds (the K-step timed region above is ~0.1 s)
+    sustained = None
+    if args.sustain_seconds > 0:
+        nrep = int(max(args.steps, args.sustain_seconds * 1e3
+                       / max(kernel_ms, 1e-3)))
+        s_sampler = ClockSampler(local)
+        if rank == 0:
+            s_sampler.start()
+        barrier()
+        s0 = torch.cuda.Event(enable_timing=True)
+        s1 = torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(nrep):
+            step_device()
+        s1.record(stream)
+        barrier()
+        sus_ms = s0.elapsed_time(s1)
+        t = torch.tensor([sus_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sus_ms = float(t.item())
+        sc = s_sampler.stop() if rank == 0 else None
+        sustained = {"seconds": sus_ms * 1e-3, "steps": nrep,
+                     "fits_per_s": world * nobj * nrep / (sus_ms * 1e-3),
+                     "clocks": sc}
+
+    # ---- the other BASELINE configs (bench_configs.py)
+    import bench_configs
+    sel = args.configs.split(",") if args.configs not in ("all", "none") \
+        else (["1", "2b", "3", "4", "5"] if args.configs == "all" else [])
+    del d_fd, d_out4
+    torch.cuda.empty_cache()
+    cfg_out = {}
+    dd = dist if world > 1 else None
+    runners = (("2b", "config2_noise1", bench_configs.config2_noisy),
+               ("3", "config3_psf_em_admom", bench_configs.config3_psf),
+               ("4", "config4_bdf", bench_configs.config4_bdf),
+               ("5", "config5_metacal", bench_configs.config5_metacal))
+    for key, name, fn in runners:
+        if key not in sel:
+            continue
+        try:
+            cfg_out[name] = fn(args, torch, _lib, dev, rank, world, dd,
+                               dfma_per_s)
+        except Exception as e:       # a failed extra never loses the headline
+            if world > 1:
+                raise
+            cfg_out[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.empty_cache()
+    if "1" in sel and rank == 0:
+        try:
+            cfg_out["config1_single_fit"] = bench_configs.config1_latency(
+                args, _lib)
+        except Exception as e:
+            cfg_out["config1_single_fit"] = {
+                "error": "%s: %s" % (type(e).__name__, e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -478,27 +584,55 @@ def main():
             / (fdiff_ms * 1e-3) / dfma_per_s,
         },
         "clocks": clocks,
+        "sustained": sustained,
+        "configs": cfg_out,
     }
     if not args.no_cpu:
         os.sched_setaffinity(0, orig_affinity)    # all host cores again
         cores = os.cpu_count()
         cpu_rate, ns, dt, ores, reps = time_cpu_port(b, cores)
-        out["cpu_baseline"] = {
+        port = {
             "value": cpu_rate, "unit": "fits/s", "cores": cores,
             "kind": "port",
             "sample": "first %d stamps of the same batch fitted %d times, "
                       "%d threads over objects, %.1f s"
                       % (ns, reps, cores, dt)}
+        out["cpu_baseline"] = port
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_arm
+        if args.kind != "port" and ref_arm.available()[0]:
+            # the north-star arm: unmodified ngmix (numba), one process per
+            # core, on the first stamps of the same batch
+            nref = min(nobj, 128 * cores)
+            bs = {k: b[k][:nref] for k in ("images", "weights", "jac", "psf",
+                                           "guess")}
+            r = ref_arm.time_batch(bs, kind="lm", model="exp", nproc=cores,
+                                   steps=3, warmup=1, max_seconds=60.0)
+            out["cpu_baseline"] = {
+                "value": r["value"], "unit": "fits/s", "cores": cores,
+                "kind": "reference",
+                "sample": "first %d stamps of the same batch, %d steps, %d "
+                          "processes (multiprocessing) over objects, "
+                          "Fitter.go loop only; %.0f fits/s per core"
+                          % (nref, r["steps"], cores,
+                             r["per_core_fits_per_s"])}
+            out["cpu_port"] = port
+            out["cpu_port"]["port_over_reference"] = cpu_rate / r["value"]
+            rr = r["results"]
+            out["parity_vs_reference"] = {
+                "n": int(nref),
+                "flags_equal": int((rr["flags"] == res["flags"][:nref]).sum()),
+                "nfev_equal": int((rr["nfev"] == res["nfev"][:nref]).sum()),
+                "max_rel_dev_T": float(np.max(
+                    np.abs(res["pars"][:nref, 4] - rr["pars"][:, 4])
+                    / np.abs(rr["pars"][:, 4]))),
+                "max_rel_dev_flux": float(np.max(
+                    np.abs(res["pars"][:nref, 5] - rr["pars"][:, 5])
+                    / np.abs(rr["pars"][:, 5]))),
+                "max_abs_dev_g": float(np.max(
+                    np.abs(res["pars"][:nref, 2:4] - rr["pars"][:, 2:4])))}
         # parity on the sample, reported beside the throughput
-        same = (ores["flags"] == res["flags"][:ns])
-        perr = np.abs(res["pars"][:ns, :6] - ores["pars"][:, :6])
-        tol = np.maximum(1e-5 * np.abs(ores["pars"][:, :6]),
-                         1e-3 * ores["pars_err"][:, :6])
-        out["parity_on_sample"] = {
-            "n": int(ns), "flags_equal": int(same.sum()),
-            "nfev_ier_equal": int(((ores["nfev"] == res["nfev"][:ns])
-                                   & (ores["ier"] == res["ier"][:ns])).sum()),
-            "pars_within_1e-5": int(np.all(perr <= tol, axis=1).sum())}
+        out["parity_on_sample"] = bench_configs.lm_parity(res, ores, 6)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

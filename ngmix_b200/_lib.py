@@ -725,3 +725,32 @@ def loglike_device(n, ngauss, d_gmix, d_images, d_weights, d_jac, nrow, ncol,
         C.c_int(nrow), C.c_int(ncol), C.c_int(int(ignore_zero_weight)),
         C.c_void_p(d_out4), C.c_void_p(d_fdiff) if d_fdiff else None,
         C.c_void_p(d_status) if d_status else None, C.c_void_p(stream)))
+
+
+# -------------------------------------------------- device-pointer mixtures
+MODEL_NGAUSS = {"gauss": 1, "turb": 3, "exp": 6, "dev": 10, "bdf": 16,
+                "bd": 16}
+
+
+def gmix_fill_device(model, n, d_pars, npars, ngauss, d_gmix, d_status,
+                     stream=0):
+    """ngx_gmix_fill on device pointers: pars [n, npars] -> gmix [n, ngauss]"""
+    check(lib().ngx_gmix_fill(
+        C.c_int(n), C.c_int(MODELS[model]), C.c_int(ngauss),
+        C.c_void_p(d_pars), C.c_int(npars), C.c_void_p(d_gmix),
+        C.c_void_p(d_status), C.c_void_p(stream)))
+
+
+def gmix_convolve_device(n, nobj, npsf, d_obj, d_psf, d_out, stream=0):
+    check(lib().ngx_gmix_convolve(
+        C.c_int(n), C.c_int(nobj), C.c_int(npsf), C.c_void_p(d_obj),
+        C.c_void_p(d_psf), C.c_void_p(d_out), C.c_void_p(stream)))
+
+
+def render_device(n, ngauss, d_gmix, d_jac, nrow, ncol, fast_exp, d_images,
+                  d_status, stream=0):
+    """adds the mixtures into images [n, nrow, ncol] (asynchronous)"""
+    check(lib().ngx_render(
+        C.c_int(n), C.c_int(ngauss), C.c_void_p(d_gmix), C.c_void_p(d_jac),
+        C.c_int(nrow), C.c_int(ncol), C.c_int(int(fast_exp)),
+        C.c_void_p(d_images), C.c_void_p(d_status), C.c_void_p(stream)))
