@@ -29,6 +29,7 @@
 // thread then advances the MINPACK state machine (ngx_lm_solve.cuh) while
 // the other CTAs resident on the SM keep the fp64 pipe busy.
 #include <cuda_pipeline.h>
+#include <mutex>
 #include "ngx_core.cuh"
 #include "ngx_host.cuh"
 #include "ngx_lm_solve.cuh"
@@ -279,7 +280,7 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
                 const double *tab = mix + REC * k;
                 const double2 *g2 = (const double2 *)(tab + 16);
                 const double2 rc = g2[0], ab = g2[1], cc = g2[2];
-                double x[CV], e[CV];
+                double x[CV], tv[CV], pv[CV];
                 bool ap[CV], anyap = false;
 #pragma unroll
                 for (int c = 0; c < CV; c++) {
@@ -290,19 +291,25 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
                     unsigned slot;
                     bool inr;
                     double f = fexp_split(x[c], &slot, &inr, &ap[c]);
-                    e[c] = tab[slot] * fexp_poly_c(f);
+                    tv[c] = tab[slot];
+                    pv[c] = fexp_poly_c(f);
                     anyap |= ap[c];
                 }
                 if (__any_sync(0xffffffffu, anyap)) {
                     // some lane of some pixel sits in the apodization band
 #pragma unroll
                     for (int c = 0; c < CV; c++) {
+                        double e = tv[c] * pv[c];
                         double w = apod_window_fast(x[c]);
-                        if (ap[c]) e[c] *= w;
+                        if (ap[c]) e *= w;
+                        acc[c] += e;
                     }
-                }
+                } else {
+                    // table entry times polynomial folded into the sum
 #pragma unroll
-                for (int c = 0; c < CV; c++) acc[c] += e[c];
+                    for (int c = 0; c < CV; c++)
+                        acc[c] = fma(tv[c], pv[c], acc[c]);
+                }
             }
         }
 #pragma unroll
@@ -418,14 +425,16 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                         double cv = vl[c] * hq.x;
                         double ea = fma(hqu[c], hqu[c], hab.y);
                         double eb = fma(hqv[c], hqv[c], hab.x);
-                        MA[c] = fma(cv, ea - eb, MA[c]);
-                        MS[c] = fma(cv, ea + eb, MS[c]);
+                        // MA = EA - EB and MS = EA + EB are formed once per
+                        // pixel after the loop (two adds less per gaussian)
+                        MA[c] = fma(cv, ea, MA[c]);
+                        MS[c] = fma(cv, eb, MS[c]);
                         MB[c] = fma(cv, fma(hqv[c], hqu[c], hq.y), MB[c]);
                     } else {
                         // a lane of this tile sits in the apodization
                         // band: the window slope enters the terms that flow
                         // through chi^2, derivs_nb.py:104-114
-                        const double2 hpm = gg[5];  // hb - ha, hb + ha
+                        const double2 hab = gg[4];  // ha, hb
                         double wv = 1.0, wc = 1.0;
                         if (ap[c]) apod_pair(xx[c], &wv, &wc);
                         double vc = vl[c] * wc;
@@ -435,8 +444,8 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                         S2[c] = fma(vc, hqu[c], S2[c]);
                         double cv = vc * hq.x, cw = vw * hq.x;
                         double qu2 = hqu[c] * hqu[c], qv2 = hqv[c] * hqv[c];
-                        MA[c] = fma(cv, qu2 - qv2, fma(cw, hpm.x, MA[c]));
-                        MS[c] = fma(cv, qu2 + qv2, fma(cw, hpm.y, MS[c]));
+                        MA[c] = fma(cv, qu2, fma(cw, hab.y, MA[c]));
+                        MS[c] = fma(cv, qv2, fma(cw, hab.x, MS[c]));
                         MB[c] = fma(cv, hqv[c] * hqu[c],
                                     fma(cw, hq.y, MB[c]));
                     }
@@ -451,7 +460,10 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
                 double d = SRC == 2 ? dval[c] : val[q];
                 // undo the factors folded into the accumulators:
                 // qv = -2 hqv; (q q^T - W) terms carry 4, the cross term 8
-                double ma = 4.0 * MA[c], ms = 4.0 * MS[c], mb = 8.0 * MB[c];
+                // (MA, MS hold EA = sum cv (hqu^2 + b/2), EB = sum cv
+                // (hqv^2 + a/2) at this point)
+                double ma = 4.0 * (MA[c] - MS[c]), ms = 4.0 * (MA[c] + MS[c]),
+                       mb = 8.0 * MB[c];
                 double j[6];
                 j[0] = (-2.0 * S1[c]) * ie;
                 j[1] = (-2.0 * S2[c]) * ie;
@@ -652,13 +664,15 @@ static __device__ __noinline__ double prior_fnorm2(const LMArgs &a, const double
 }
 
 // the epilogue: run_leastsq (leastsqbound.py:70-126) + set_fit_result.
-// Writes straight into the global result record; matrices are staged in the
-// shared-memory workspace of the state (no per-thread local arrays).
+// Entered by the whole warp 0.  Writes straight into the global result
+// record (lane-strided, coalesced); matrices are staged in the shared-memory
+// workspace of the state (no per-thread local arrays).
 template <typename RES>
 __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
                                        RES *out) {
     LMState *s = &sh->st;
     const int np = a.np;
+    const int lane = threadIdx.x & 31;
     RES &r = *out;
     constexpr int RP = (int)(sizeof(r.pars) / sizeof(double));
     const double qnan = nan("");
@@ -666,8 +680,9 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
     double *pcov = s->T1;       // after lm_cov0 is done with it
     int flags = 0;
     int have_cov = 0, have_pcov = 0, have_err = 0;
-    if (s->info > 4) {
-        flags |= 1 << (s->info - 5);
+    const int info = s->info;
+    if (info > 4) {
+        flags |= 1 << (info - 5);
     } else {
         have_cov = lm_cov0(s, cov0);
         if (!have_cov) {
@@ -684,8 +699,11 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
                     > prior_nrows(a.model, a.prior))
                     ssq -= sh->cur_rfirst2;
                 double s_sq = ssq / dof;
+                __syncwarp();
 #pragma unroll 1
-                for (int i = 0; i < np * np; i++) pcov[i] = cov0[i] * s_sq;
+                for (int i = lane; i < np * np; i += 32)
+                    pcov[i] = cov0[i] * s_sq;
+                __syncwarp();
                 have_pcov = 1;
                 int cflags = lm_test_cov(np, pcov, s->T2);
                 if (cflags) flags |= cflags;
@@ -693,22 +711,19 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
             }
         }
     }
-    r.flags = flags;
-    r.nfev = s->nfev;
-    r.njev = s->njev;
-    r.ier = s->info;
+    __syncwarp();
 #pragma unroll 1
-    for (int i = 0; i < RP; i++) {
+    for (int i = lane; i < RP; i += 32) {
         double pv = 0.0, pe = 0.0;
         if (i < np) {
-            pv = (s->info > 4) ? NGX_PDEF : s->x[i];
+            pv = (info > 4) ? NGX_PDEF : s->x[i];
             pe = have_err ? sqrt(pcov[i * np + i]) : NGX_CDEF;
         }
         r.pars[i] = pv;
         r.pars_err[i] = pe;
     }
 #pragma unroll 1
-    for (int i = 0; i < RP * RP; i++) {
+    for (int i = lane; i < RP * RP; i += 32) {
         double c0 = 0.0, c1 = 0.0;
         if (i < np * np) {
             c0 = have_cov ? cov0[i] : qnan;
@@ -717,6 +732,11 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
         r.pars_cov0[i] = c0;
         r.pars_cov[i] = c1;
     }
+    if (lane != 0) return;
+    r.flags = flags;
+    r.nfev = s->nfev;
+    r.njev = s->njev;
+    r.ier = info;
     int npix = 0, dof = 0;
     double lnprob = qnan, num = qnan, den = qnan, chi2per = qnan, s2n = qnan;
     double Tv = qnan, Terr = qnan, flux = qnan, fluxerr = qnan;
@@ -763,8 +783,11 @@ static __device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
                                            const double *sums, int status,
                                            int analytic, const double *hs,
                                            int pre = 0) {
+    // entered by the whole warp 0: lane 0 adds the prior rows, then all
+    // lanes advance the state machine (ngx_lm_solve.cuh)
     double *A = sh->st.A, *b = sh->st.b;
     const int np = a.np;
+    if ((threadIdx.x & 31) == 0) {
     const double *x = sh->st.x;
     int nr = prior_nrows(a.model, a.prior);
     const int status_in = status;
@@ -813,6 +836,8 @@ static __device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
             b[aa] = sv;
         }
     }
+    }
+    __syncwarp();
     lm_feed_j(&sh->st, A, b, analytic ? 0 : np);
 }
 
@@ -835,17 +860,21 @@ __device__ __forceinline__ void assemble_normal_eq(LMShared *sh,
     }
 }
 
-// feed |f| of a residual pass (thread 0); returns 1 if the point is adopted
+// feed |f| of a residual pass (whole warp 0; lane 0 evaluates the prior);
+// returns 1 on every lane if the point is adopted
 static __device__ __noinline__ int feed_residual(const LMArgs &a, LMShared *sh,
                                           const double *xeval, double ssq,
                                           int status) {
-    int ninf = 0;
-    double ps = prior_fnorm2(a, xeval, &status, &ninf);
-    double fnorm;
-    if (status) fnorm = nan("");
-    else if (ninf == 1) fnorm = INFINITY;
-    else if (ninf > 1) fnorm = nan("");
-    else fnorm = sqrt(ssq + ps);
+    double fnorm = 0.0;
+    if ((threadIdx.x & 31) == 0) {
+        int ninf = 0;
+        double ps = prior_fnorm2(a, xeval, &status, &ninf);
+        if (status) fnorm = nan("");
+        else if (ninf == 1) fnorm = INFINITY;
+        else if (ninf > 1) fnorm = nan("");
+        else fnorm = sqrt(ssq + ps);
+    }
+    fnorm = __shfl_sync(0xffffffffu, fnorm, 0);
     return lm_feed_f(&sh->st, fnorm);
 }
 
@@ -910,14 +939,12 @@ k_lm_fit(LMArgs a) {
         //      touches val/ierr and a few words the epilogue does not read
         int cnt = 0, first = a.ntot, firstq = 0;
         if (warp_id == 0) {
-            if (threadIdx.x == 0) {
-                if (pending >= 0)
-                    lm_finish(a, &sh, &((RES *)a.res)[pending]);
-                if (have) {
-                    sh.next = atomicAdd(a.counter, 1);
-                    sh.jac = a.jac[stamp];
-                    sh.status = 0;
-                }
+            if (pending >= 0)
+                lm_finish(a, &sh, &((RES *)a.res)[pending]);
+            if (threadIdx.x == 0 && have) {
+                sh.next = atomicAdd(a.counter, 1);
+                sh.jac = a.jac[stamp];
+                sh.status = 0;
             }
         } else if (have) {
             const double *im = a.images + (size_t)stamp * a.ntot;
@@ -1141,20 +1168,24 @@ k_lm_fit(LMArgs a) {
                 assemble_normal_eq(&sh, sh.tot, jstatus);
                 __syncthreads();
                 PROF_T(pt_pass);
-                if (threadIdx.x == 0) {
+                if (warp_id == 0) {
+                    // the whole warp advances the state machine
                     const double *tot = sh.tot;
+                    const bool lane0 = threadIdx.x == 0;
                     if (want_f) {
                         int acc = feed_residual(a, &sh, xp, tot[27],
                                                 mix_status);
                         if (acc) {
-                            sh.cur_ssq = tot[27];
-                            sh.cur_num = tot[28];
-                            sh.cur_den = tot[29];
-                            sh.cur_rfirst2 = tot[30];
+                            if (lane0) {
+                                sh.cur_ssq = tot[27];
+                                sh.cur_num = tot[28];
+                                sh.cur_den = tot[29];
+                                sh.cur_rfirst2 = tot[30];
+                            }
                             if (sh.st.action == LM_ACT_EVAL_J)
                                 feed_jacobian(a, &sh, tot, jstatus, 1, hs, 1);
                         }
-                        sh.spec = acc;
+                        if (lane0) sh.spec = acc;
                     } else {
                         feed_jacobian(a, &sh, tot, jstatus, 1, hs, 1);
                     }
@@ -1172,17 +1203,19 @@ k_lm_fit(LMArgs a) {
                                                MODE == 1 ? mplane : nullptr);
                 block_sum_to<4>(sums, scratch, sh.tot);
                 PROF_T(pt_pass);
-                if (threadIdx.x == 0) {
+                if (warp_id == 0) {
                     const double *tot = sh.tot;
                     int acc = feed_residual(a, &sh, sh.xeval, tot[0],
                                             sh.status);
-                    if (acc) {
-                        sh.cur_ssq = tot[0];
-                        sh.cur_num = tot[1];
-                        sh.cur_den = tot[2];
-                        sh.cur_rfirst2 = tot[3];
+                    if (threadIdx.x == 0) {
+                        if (acc) {
+                            sh.cur_ssq = tot[0];
+                            sh.cur_num = tot[1];
+                            sh.cur_den = tot[2];
+                            sh.cur_rfirst2 = tot[3];
+                        }
+                        sh.spec = acc;
                     }
-                    sh.spec = acc;
                 }
             } else {
                 // forward differences: base + np perturbed mixtures
@@ -1233,13 +1266,15 @@ k_lm_fit(LMArgs a) {
                         block_sum_to<32>(s1, scratch, sh.tot + 32 * ch);
                     }
                 }
-                if (threadIdx.x == 0) {
+                if (warp_id == 0) {
                     // feed_jacobian wants {triangle of np, b, r^2} contiguous
                     double *pk = sh.st.T2;
                     const int tri = np * (np + 1) / 2;
-                    for (int i = 0; i < tri; i++) pk[i] = sh.tot[i];
-                    for (int i = 0; i <= np; i++)
+                    const int lane = threadIdx.x;
+                    for (int i = lane; i < tri; i += 32) pk[i] = sh.tot[i];
+                    for (int i = lane; i <= np; i += 32)
                         pk[tri + i] = sh.tot[FD_B0_(FDP) + i];
+                    __syncwarp();
                     feed_jacobian(a, &sh, pk, bad_any, 0, hs);
                 }
             }
@@ -1254,8 +1289,8 @@ k_lm_fit(LMArgs a) {
         PROF_T(pt_solve);
 #ifdef NGX_PROF
         // the epilogue is timed with the next stamp's staging
+        if (warp_id == 0) lm_finish(a, &sh, &((RES *)a.res)[stamp]);
         if (threadIdx.x == 0) {
-            lm_finish(a, &sh, &((RES *)a.res)[stamp]);
             PROF_T(pt_fin);
             double *o = ((RES *)a.res)[stamp].pars_cov0 + 56;
             o[0] = (double)pt_stage; o[1] = (double)pt_mix;
@@ -1480,47 +1515,109 @@ k_lm_fit_multi(LMArgs a) {
                 __syncthreads();
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
+            if (warp == 0) {
                 const int mstatus = mu.mstatus;
                 const int jstatus = mstatus || jstatus0;
                 if (want_f) {
                     int acc = feed_residual(a, &sh, xp, mu.macc[MACC_X],
                                                 mstatus);
                     if (acc) {
-                        sh.cur_ssq = mu.macc[MACC_X];
-                        sh.cur_num = mu.macc[MACC_X + 1];
-                        sh.cur_den = mu.macc[MACC_X + 2];
-                        sh.cur_rfirst2 = mu.macc[MACC_X + 3];
+                        if (lane == 0) {
+                            sh.cur_ssq = mu.macc[MACC_X];
+                            sh.cur_num = mu.macc[MACC_X + 1];
+                            sh.cur_den = mu.macc[MACC_X + 2];
+                            sh.cur_rfirst2 = mu.macc[MACC_X + 3];
+                        }
                         if (fused && sh.st.action == LM_ACT_EVAL_J)
                             feed_jacobian(a, &sh, mu.macc, jstatus, 1, hs);
                     }
-                    sh.spec = acc;
+                    if (lane == 0) sh.spec = acc;
                 } else {
                     feed_jacobian(a, &sh, mu.macc, jstatus, 1, hs);
                 }
-                sh.action = sh.st.action;
-                for (int i = 0; i < np; i++) sh.xeval[i] = sh.st.xtrial[i];
+                __syncwarp();
+                if (lane == 0) {
+                    sh.action = sh.st.action;
+                    for (int i = 0; i < np; i++)
+                        sh.xeval[i] = sh.st.xtrial[i];
+                }
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) lm_finish(a, &sh, &((RES *)a.res)[obj]);
+        if (warp == 0) lm_finish(a, &sh, &((RES *)a.res)[obj]);
     }
 }
 
 // ---------------------------------------------------------------------
-// Work-queue counter of one launch: a stream-ordered allocation that lives
-// exactly as long as the kernel using it (allocated and zeroed before the
-// launch, freed behind it on the same stream).  Launches on different
-// streams, devices or host threads never share a counter and the library
-// keeps no global state for it.
-static int get_counter(int **out, cudaStream_t st) {
-    NGX_CUDA(cudaMallocAsync((void **)out, 128, st));
-    cudaError_t e = cudaMemsetAsync(*out, 0, sizeof(int), st);
-    if (e != cudaSuccess) {
-        cudaFreeAsync(*out, st);
-        NGX_CUDA(e);
+// Work-queue counter of one launch.  Each device has a ring of counters
+// (allocated once); a launch takes the next slot whose previous user has
+// finished - known from an event recorded behind that launch on its stream -
+// zeroes it on its own stream and records the slot's event behind its kernel.
+// Launches on different streams, devices or host threads therefore never
+// share a live counter, no launch waits for another stream, and nothing is
+// allocated per call.  (Stream-ordered allocations were tried for this:
+// with the default pool a counter freed on one stream and reused on another
+// makes the second stream wait for the first one's kernel, which serialises
+// the two compute streams of the host pipeline; a private pool without
+// cross-stream reuse maps fresh memory on nearly every call.)
+#define NGX_RING 256
+struct CounterRing {
+    int *base = nullptr;
+    cudaEvent_t ev[NGX_RING];
+    bool used[NGX_RING];
+    unsigned next = 0;
+};
+static std::mutex g_ring_mutex;
+static CounterRing g_rings[64];
+
+static int get_counter(int **out, int *slot_out) {
+    int dev = 0;
+    NGX_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64)
+        return fail(NGX_ERR_ARG, "ngx_lm_fit: device index out of range%s%s");
+    std::lock_guard<std::mutex> lock(g_ring_mutex);
+    CounterRing &r = g_rings[dev];
+    if (!r.base) {
+        NGX_CUDA(cudaMalloc((void **)&r.base, NGX_RING * 32 * sizeof(int)));
+        for (int i = 0; i < NGX_RING; i++) {
+            NGX_CUDA(cudaEventCreateWithFlags(&r.ev[i],
+                                              cudaEventDisableTiming));
+            r.used[i] = false;
+        }
     }
+    int slot = -1;
+    for (int tries = 0; tries < NGX_RING; tries++) {
+        int i = (int)(r.next++ % NGX_RING);
+        if (!r.used[i] || cudaEventQuery(r.ev[i]) == cudaSuccess) {
+            slot = i;
+            break;
+        }
+    }
+    cudaGetLastError();             // cudaErrorNotReady from the queries
+    if (slot < 0) {
+        // every counter is still in flight: wait for the oldest
+        slot = (int)(r.next++ % NGX_RING);
+        NGX_CUDA(cudaEventSynchronize(r.ev[slot]));
+    }
+    r.used[slot] = true;
+    *out = r.base + 32 * slot;
+    *slot_out = slot;
     return NGX_OK;
+}
+
+// zero the counter ahead of the kernel and mark the slot busy until the
+// work queued on `st` so far (the caller records after its launch) is done
+static int counter_begin(int **out, int *slot, cudaStream_t st) {
+    int rc = get_counter(out, slot);
+    if (rc) return rc;
+    NGX_CUDA(cudaMemsetAsync(*out, 0, sizeof(int), st));
+    return NGX_OK;
+}
+static void counter_end(int slot, cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    // the slot is ours until this record: no lock needed for ev[slot]
+    cudaEventRecord(g_rings[dev].ev[slot], st);
 }
 
 struct LMLaunch {
@@ -1568,11 +1665,12 @@ static int config_and_launch(K kernel, const LMArgs &a_in, int threads,
     int blocks = sm_count() * per_sm;
     if (blocks > a0.n) blocks = a0.n;
     LMArgs a = a_in;
-    int rcc = get_counter(&a.counter, stream);
+    int slot = 0;
+    int rcc = counter_begin(&a.counter, &slot, stream);
     if (rcc) return rcc;
     kernel<<<blocks, threads, smem, stream>>>(a);
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(a.counter, stream);
+    counter_end(slot, stream);
     NGX_CUDA(e);
     return NGX_OK;
 }
@@ -1678,15 +1776,16 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
         NGX_CUDA(cudaMallocAsync(
             (void **)&a.gscratch,
             sizeof(double) * (size_t)blocks * (nfd ? 2 : 1) * a.nq, st));
-        int rcc = get_counter(&a.counter, st);
+        int slot = 0;
+        int rcc = counter_begin(&a.counter, &slot, st);
         if (rcc) {
             cudaFreeAsync(a.gscratch, st);
             return rcc;
         }
         kern<<<blocks, 256, smem_g, st>>>(a);
         cudaError_t e = cudaGetLastError();
+        counter_end(slot, st);
         cudaFreeAsync(a.gscratch, st);
-        cudaFreeAsync(a.counter, st);
         NGX_CUDA(e);
         return NGX_OK;
     }

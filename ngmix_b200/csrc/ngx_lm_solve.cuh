@@ -82,56 +82,89 @@ NGX_HD inline double lm_enorm(int n, const double *x) {
     return sqrt(s);
 }
 
+// ---------------------------------------------------------------------
+// Warp-cooperative execution.  On the device the routines below (lm_pchol,
+// lm_qrsolv, lm_lmpar, lm_propose, lm_feed_f, lm_feed_j) are entered by ALL
+// 32 lanes of one converged warp; the state lives in shared memory.
+//   LM_FOR(k, lo, hi)  one iteration per lane (n <= LM_MAXP < 32): loops whose
+//                      iterations are independent (a column each)
+//   LM_ONE             lane 0 only: scalar writes to the shared state
+//   LM_SYNC            __syncwarp(): orders the shared-memory accesses of the
+//                      lanes between a region's writes and the next reads
+// Everything else is computed redundantly (and identically) by every lane.
+// Every per-element operation sequence is the one of the scalar algorithm
+// (each sum is formed by one lane in the original order), so the results are
+// bit-identical to a one-thread run; on the host the macros degenerate to
+// plain loops, which is how tests/test_lm_solve_host.py drives this file.
+// A one-thread solver held each CTA for ~30% of a fit (ncu r1m: 1.94 barrier
+// stalls per issue); the O(n^3) / O(n^2) loops now take O(n^2) / O(n) steps.
+#ifdef __CUDA_ARCH__
+#define LM_LANE ((int)(threadIdx.x & 31))
+#define LM_FOR(k, lo, hi) \
+    for (int k = (lo) + LM_LANE; k < (hi); k += 32)
+#define LM_ONE if (LM_LANE == 0)
+#define LM_SYNC __syncwarp()
+#else
+#define LM_FOR(k, lo, hi) for (int k = (lo); k < (hi); k++)
+#define LM_ONE
+#define LM_SYNC
+#endif
+
 // Pivoted Cholesky A P = P R^T R  (A symmetric n x n, column major, ld
 // LM_MAXP).  Pivot rule of qrfac: at step j take the first column k >= j with
 // the largest remaining norm.  A non-positive pivot leaves a zero row (rank
-// deficiency), as qrfac leaves a zero diagonal.
+// deficiency), as qrfac leaves a zero diagonal.  Lane k owns column k.
 NGX_HD NGX_NI static void lm_pchol(int n, const double *A, double *R, int *ipvt,
                             double *acnorm, double *d) {
-#pragma unroll 1
-    for (int j = 0; j < n; j++) {
+    LM_FOR(j, 0, n) {
         ipvt[j] = j;
-        d[j] = A[j + LM_MAXP * j];
-        acnorm[j] = sqrt(d[j] > 0.0 ? d[j] : 0.0);
+        double dj = A[j + LM_MAXP * j];
+        d[j] = dj;
+        acnorm[j] = sqrt(dj > 0.0 ? dj : 0.0);
 #pragma unroll 1
         for (int i = 0; i < n; i++) R[i + LM_MAXP * j] = 0.0;
     }
+    LM_SYNC;
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
         int kmax = j;
+        double dmax = d[j];
 #pragma unroll 1
-        for (int k = j; k < n; k++)
-            if (d[k] > d[kmax]) kmax = k;
+        for (int k = j + 1; k < n; k++) {
+            double dk = d[k];
+            if (dk > dmax) { kmax = k; dmax = dk; }
+        }
+        LM_SYNC;
         if (kmax != j) {
             // swap columns j and kmax of R (rows < j), d and ipvt
-#pragma unroll 1
-            for (int i = 0; i < j; i++) {
+            LM_FOR(i, 0, j) {
                 double t = R[i + LM_MAXP * j];
                 R[i + LM_MAXP * j] = R[i + LM_MAXP * kmax];
                 R[i + LM_MAXP * kmax] = t;
             }
-            double t = d[j]; d[j] = d[kmax]; d[kmax] = t;
-            int ti = ipvt[j]; ipvt[j] = ipvt[kmax]; ipvt[kmax] = ti;
+            LM_ONE {
+                double t = d[j]; d[j] = d[kmax]; d[kmax] = t;
+                int ti = ipvt[j]; ipvt[j] = ipvt[kmax]; ipvt[kmax] = ti;
+            }
+            LM_SYNC;
         }
-        double piv = d[j];
+        double piv = dmax;
         if (!(piv > 0.0)) {
             // remaining columns are numerically dependent
+            LM_FOR(k, j, n) {
 #pragma unroll 1
-            for (int k = j; k < n; k++) R[j + LM_MAXP * k] = 0.0;
-#pragma unroll 1
-            for (int jj = j; jj < n; jj++)
-#pragma unroll 1
-                for (int k = jj; k < n; k++) R[jj + LM_MAXP * k] = 0.0;
+                for (int jj = j; jj <= k; jj++) R[jj + LM_MAXP * k] = 0.0;
+            }
+            LM_SYNC;
             return;
         }
         double rjj = sqrt(piv);
-        R[j + LM_MAXP * j] = rjj;
         // one reciprocal per row instead of a division per element: a double
-        // division is a ~30-instruction dependent sequence on this thread
+        // division is a ~30-instruction dependent sequence
         double irjj = 1.0 / rjj;
         int pj = ipvt[j];
-#pragma unroll 1
-        for (int k = j + 1; k < n; k++) {
+        LM_ONE R[j + LM_MAXP * j] = rjj;
+        LM_FOR(k, j + 1, n) {
             int pk = ipvt[k];
             double s = A[pj + LM_MAXP * pk];
 #pragma unroll 1
@@ -141,6 +174,7 @@ NGX_HD NGX_NI static void lm_pchol(int n, const double *A, double *R, int *ipvt,
             R[j + LM_MAXP * k] = rjk;
             d[k] -= rjk * rjk;
         }
+        LM_SYNC;
     }
 }
 
@@ -149,168 +183,197 @@ NGX_HD NGX_NI static void lm_qrsolv(int n, double *r, const int *ipvt,
                              const double *diag, const double *qtb, double *x,
                              double *sdiag, double *wa) {
     const int ld = LM_MAXP;
-#pragma unroll 1
-    for (int j = 0; j < n; j++) {
+    LM_FOR(j, 0, n) {
+        // lower triangle <- upper triangle (disjoint), lane j its column
 #pragma unroll 1
         for (int i = j; i < n; i++) r[i + ld * j] = r[j + ld * i];
         x[j] = r[j + ld * j];
         wa[j] = qtb[j];
     }
+    LM_SYNC;
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
         int l = ipvt[j];
-        if (diag[l] != 0.0) {
-#pragma unroll 1
-            for (int k = j; k < n; k++) sdiag[k] = 0.0;
-            sdiag[j] = diag[l];
+        const double dl = diag[l];
+        if (dl != 0.0) {
+            LM_FOR(k, j, n) sdiag[k] = (k == j) ? dl : 0.0;
+            LM_SYNC;
             double qtbpj = 0.0;
 #pragma unroll 1
             for (int k = j; k < n; k++) {
-                if (sdiag[k] == 0.0) continue;
+                const double sk = sdiag[k];
+                if (sk == 0.0) continue;
                 double c, s;
-                double rkk = r[k + ld * k];
-                if (fabs(rkk) < fabs(sdiag[k])) {
-                    double cotan = rkk / sdiag[k];
+                const double rkk = r[k + ld * k];
+                if (fabs(rkk) < fabs(sk)) {
+                    double cotan = rkk / sk;
                     s = 0.5 / sqrt(0.25 + 0.25 * (cotan * cotan));
                     c = s * cotan;
                 } else {
-                    double tn = sdiag[k] / rkk;
+                    double tn = sk / rkk;
                     c = 0.5 / sqrt(0.25 + 0.25 * (tn * tn));
                     s = c * tn;
                 }
-                r[k + ld * k] = c * rkk + s * sdiag[k];
-                double temp = c * wa[k] + s * qtbpj;
-                qtbpj = -s * wa[k] + c * qtbpj;
-                wa[k] = temp;
-#pragma unroll 1
-                for (int i = k + 1; i < n; i++) {
-                    temp = c * r[i + ld * k] + s * sdiag[i];
-                    sdiag[i] = -s * r[i + ld * k] + c * sdiag[i];
-                    r[i + ld * k] = temp;
+                const double wak = wa[k];
+                LM_SYNC;
+                LM_ONE {
+                    r[k + ld * k] = c * rkk + s * sk;
+                    wa[k] = c * wak + s * qtbpj;
                 }
+                qtbpj = -s * wak + c * qtbpj;
+                LM_FOR(i, k + 1, n) {
+                    const double rik = r[i + ld * k], sdi = sdiag[i];
+                    r[i + ld * k] = c * rik + s * sdi;
+                    sdiag[i] = -s * rik + c * sdi;
+                }
+                LM_SYNC;
             }
         }
-        sdiag[j] = r[j + ld * j];
-        r[j + ld * j] = x[j];
+        const double rjj = r[j + ld * j], xj = x[j];
+        LM_SYNC;
+        LM_ONE {
+            sdiag[j] = rjj;
+            r[j + ld * j] = xj;
+        }
+        LM_SYNC;
     }
     int nsing = n;
 #pragma unroll 1
-    for (int j = 0; j < n; j++) {
+    for (int j = 0; j < n; j++)
         if (sdiag[j] == 0.0 && nsing == n) nsing = j;
-        if (nsing < n) wa[j] = 0.0;
-    }
+    LM_FOR(j, nsing, n) wa[j] = 0.0;
+    LM_SYNC;
+    // back substitution: each sum runs over ascending i as in MINPACK, so
+    // the steps stay sequential (the divisions dominate them anyway)
 #pragma unroll 1
     for (int k = 1; k <= nsing; k++) {
         int j = nsing - k;
         double sum = 0.0;
 #pragma unroll 1
         for (int i = j + 1; i < nsing; i++) sum += r[i + ld * j] * wa[i];
-        wa[j] = (wa[j] - sum) / sdiag[j];
+        const double wj = (wa[j] - sum) / sdiag[j];
+        LM_SYNC;
+        LM_ONE wa[j] = wj;
+        LM_SYNC;
     }
-#pragma unroll 1
-    for (int j = 0; j < n; j++) x[ipvt[j]] = wa[j];
+    LM_FOR(j, 0, n) x[ipvt[j]] = wa[j];
+    LM_SYNC;
 }
 
 // MINPACK lmpar
 NGX_HD NGX_NI static void lm_lmpar(int n, double *r, const int *ipvt,
                             const double *diag, const double *qtb,
-                            double delta, double *par, double *x,
+                            double delta, double *par_io, double *x,
                             double *sdiag, double *wa1, double *wa2) {
     const int ld = LM_MAXP;
+    double par = *par_io;
     int nsing = n;
 #pragma unroll 1
-    for (int j = 0; j < n; j++) {
-        wa1[j] = qtb[j];
+    for (int j = 0; j < n; j++)
         if (r[j + ld * j] == 0.0 && nsing == n) nsing = j;
-        if (nsing < n) wa1[j] = 0.0;
-    }
+    LM_FOR(j, 0, n) wa1[j] = j < nsing ? qtb[j] : 0.0;
+    LM_SYNC;
 #pragma unroll 1
     for (int k = 1; k <= nsing; k++) {
         int j = nsing - k;
-        wa1[j] /= r[j + ld * j];
-        double temp = wa1[j];
-#pragma unroll 1
-        for (int i = 0; i < j; i++) wa1[i] -= r[i + ld * j] * temp;
+        const double temp = wa1[j] / r[j + ld * j];
+        LM_SYNC;
+        LM_ONE wa1[j] = temp;
+        LM_FOR(i, 0, j) wa1[i] -= r[i + ld * j] * temp;
+        LM_SYNC;
     }
-#pragma unroll 1
-    for (int j = 0; j < n; j++) x[ipvt[j]] = wa1[j];
+    LM_FOR(j, 0, n) x[ipvt[j]] = wa1[j];
+    LM_SYNC;
 
     int iter = 0;
-#pragma unroll 1
-    for (int j = 0; j < n; j++) wa2[j] = diag[j] * x[j];
+    LM_FOR(j, 0, n) wa2[j] = diag[j] * x[j];
+    LM_SYNC;
     double dxnorm = lm_enorm(n, wa2);
     double fp = dxnorm - delta;
     if (fp <= 0.1 * delta) {
-        *par = 0.0;
+        LM_SYNC;
+        LM_ONE *par_io = 0.0;
+        LM_SYNC;
         return;
     }
     double parl = 0.0;
     if (nsing >= n) {
-#pragma unroll 1
-        for (int j = 0; j < n; j++) {
+        LM_FOR(j, 0, n) {
             int l = ipvt[j];
             wa1[j] = diag[l] * (wa2[l] / dxnorm);
+            sdiag[j] = 0.0;     // running sums of the forward substitution
         }
+        LM_SYNC;
+        // wa1[j] = (wa1[j] - sum_{i<j} r[i,j] wa1[i]) / r[j,j]: lane j adds
+        // its sum's terms as the wa1[i] become final, in ascending i
 #pragma unroll 1
         for (int j = 0; j < n; j++) {
-            double sum = 0.0;
-#pragma unroll 1
-            for (int i = 0; i < j; i++) sum += r[i + ld * j] * wa1[i];
-            wa1[j] = (wa1[j] - sum) / r[j + ld * j];
+            const double wj = (wa1[j] - sdiag[j]) / r[j + ld * j];
+            LM_SYNC;
+            LM_ONE wa1[j] = wj;
+            LM_FOR(i, j + 1, n) sdiag[i] += r[j + ld * i] * wj;
+            LM_SYNC;
         }
         double temp = lm_enorm(n, wa1);
         parl = ((fp / delta) / temp) / temp;
+        LM_SYNC;
     }
-#pragma unroll 1
-    for (int j = 0; j < n; j++) {
+    LM_FOR(j, 0, n) {
         double sum = 0.0;
 #pragma unroll 1
         for (int i = 0; i <= j; i++) sum += r[i + ld * j] * qtb[i];
         wa1[j] = sum / diag[ipvt[j]];
     }
+    LM_SYNC;
     double gnorm = lm_enorm(n, wa1);
     double paru = gnorm / delta;
     if (paru == 0.0) paru = LM_DWARF / lm_min(delta, 0.1);
-    *par = lm_max(*par, parl);
-    *par = lm_min(*par, paru);
-    if (*par == 0.0) *par = gnorm / dxnorm;
+    par = lm_max(par, parl);
+    par = lm_min(par, paru);
+    if (par == 0.0) par = gnorm / dxnorm;
 #pragma unroll 1
     for (;;) {
         iter++;
-        if (*par == 0.0) *par = lm_max(LM_DWARF, 0.001 * paru);
-        double temp = sqrt(*par);
-#pragma unroll 1
-        for (int j = 0; j < n; j++) wa1[j] = temp * diag[j];
+        if (par == 0.0) par = lm_max(LM_DWARF, 0.001 * paru);
+        double temp = sqrt(par);
+        LM_SYNC;
+        LM_FOR(j, 0, n) wa1[j] = temp * diag[j];
+        LM_SYNC;
         lm_qrsolv(n, r, ipvt, wa1, qtb, x, sdiag, wa2);
-#pragma unroll 1
-        for (int j = 0; j < n; j++) wa2[j] = diag[j] * x[j];
+        LM_FOR(j, 0, n) wa2[j] = diag[j] * x[j];
+        LM_SYNC;
         dxnorm = lm_enorm(n, wa2);
         temp = fp;
         fp = dxnorm - delta;
         if (fabs(fp) <= 0.1 * delta
             || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10)
             break;
-#pragma unroll 1
-        for (int j = 0; j < n; j++) {
+        LM_FOR(j, 0, n) {
             int l = ipvt[j];
             wa1[j] = diag[l] * (wa2[l] / dxnorm);
         }
+        LM_SYNC;
 #pragma unroll 1
         for (int j = 0; j < n; j++) {
-            wa1[j] /= sdiag[j];
-            temp = wa1[j];
-#pragma unroll 1
-            for (int i = j + 1; i < n; i++) wa1[i] -= r[i + ld * j] * temp;
+            const double wj = wa1[j] / sdiag[j];
+            LM_SYNC;
+            LM_ONE wa1[j] = wj;
+            LM_FOR(i, j + 1, n) wa1[i] -= r[i + ld * j] * wj;
+            LM_SYNC;
         }
         temp = lm_enorm(n, wa1);
         double parc = ((fp / delta) / temp) / temp;
-        if (fp > 0.0) parl = lm_max(parl, *par);
-        if (fp < 0.0) paru = lm_min(paru, *par);
-        *par = lm_max(parl, *par + parc);
+        if (fp > 0.0) parl = lm_max(parl, par);
+        if (fp < 0.0) paru = lm_min(paru, par);
+        par = lm_max(parl, par + parc);
     }
+    LM_SYNC;
+    LM_ONE *par_io = par;
+    LM_SYNC;
 }
 
 // ---------------------------------------------------------------------
+// (one thread)
 NGX_HD NGX_NI static void lm_init(LMState *s, int n, const double *x0, int maxfev,
                            double ftol, double xtol) {
     s->n = n;
@@ -342,52 +405,73 @@ NGX_HD NGX_NI static void lm_init(LMState *s, int n, const double *x0, int maxfe
 }
 
 // compute the next trial point from the current factorisation (lmpar)
+// (whole warp)
 NGX_HD NGX_NI static void lm_propose(LMState *s) {
     int n = s->n;
     double *p = s->v[4], *wa3 = s->v[5];
     lm_lmpar(n, s->R, s->ipvt, s->diag, s->qtf, s->delta, &s->par, p,
              s->v[1], s->v[2], s->v[3]);
+    LM_FOR(j, 0, n) {
+        const double st = -p[j];
+        s->step[j] = st;
+        s->xtrial[j] = s->x[j] + st;
+        wa3[j] = s->diag[j] * st;
+    }
+    LM_SYNC;
+    const double pnorm = lm_enorm(n, wa3);
+    const double par = s->par, fnorm = s->fnorm;
+    const int first = s->iter == 1;
+    const double delta0 = s->delta;
+    LM_SYNC;
+    // |R P^T p|: wa3[i] += R[i,j] step[ipvt[j]] over ascending j, lane i
+    LM_FOR(j, 0, n) wa3[j] = 0.0;
+    LM_SYNC;
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
-        s->step[j] = -p[j];
-        s->xtrial[j] = s->x[j] + s->step[j];
-        wa3[j] = s->diag[j] * s->step[j];
+        const double temp = s->step[s->ipvt[j]];
+        LM_FOR(i, 0, j + 1) wa3[i] += s->R[i + LM_MAXP * j] * temp;
     }
-    s->pnorm = lm_enorm(n, wa3);
-    if (s->iter == 1) s->delta = lm_min(s->delta, s->pnorm);
-    // |R P^T p|
-#pragma unroll 1
-    for (int j = 0; j < n; j++) wa3[j] = 0.0;
-#pragma unroll 1
-    for (int j = 0; j < n; j++) {
-        double temp = s->step[s->ipvt[j]];
-#pragma unroll 1
-        for (int i = 0; i <= j; i++) wa3[i] += s->R[i + LM_MAXP * j] * temp;
+    LM_SYNC;
+    double temp1 = lm_enorm(n, wa3) / fnorm;
+    double temp2 = (sqrt(par) * pnorm) / fnorm;
+    LM_ONE {
+        s->pnorm = pnorm;
+        if (first) s->delta = lm_min(delta0, pnorm);
+        s->prered = temp1 * temp1 + temp2 * temp2 / 0.5;
+        s->dirder = -(temp1 * temp1 + temp2 * temp2);
+        s->action = LM_ACT_EVAL_F;
     }
-    double temp1 = lm_enorm(n, wa3) / s->fnorm;
-    double temp2 = (sqrt(s->par) * s->pnorm) / s->fnorm;
-    s->prered = temp1 * temp1 + temp2 * temp2 / 0.5;
-    s->dirder = -(temp1 * temp1 + temp2 * temp2);
-    s->action = LM_ACT_EVAL_F;
+    LM_SYNC;
 }
 
 // Feed the result of an EVAL_F pass: fnorm_new = |f(xtrial)| (NaN when the
 // model or prior was out of range: the reference's -inf residual vector has
 // a NaN MINPACK norm).  Returns 1 when the trial point was accepted (or was
 // the initial point), i.e. when the caller must adopt the pass's statistics.
+// (whole warp; every lane returns the same value)
 NGX_HD NGX_NI static int lm_feed_f(LMState *s, double fnorm_new) {
     int n = s->n;
-    s->nfev += 1;
-    if (s->nfev == 1) {
+    const int nfev = s->nfev + 1;
+    if (nfev == 1) {
         // initial evaluation
-        s->fnorm = fnorm_new;
-        s->action = LM_ACT_EVAL_J;
+        LM_SYNC;
+        LM_ONE {
+            s->nfev = nfev;
+            s->fnorm = fnorm_new;
+            s->action = LM_ACT_EVAL_J;
+        }
+        LM_SYNC;
         return 1;
     }
     double fnorm1 = fnorm_new;
+    const double fnorm0 = s->fnorm;
+    double delta = s->delta, par = s->par, xnorm = s->xnorm;
+    const double pnorm = s->pnorm, gnorm = s->gnorm;
+    const double ftol = s->ftol, xtol = s->xtol;
+    const int maxfev = s->maxfev;
     double actred = -1.0;
-    if (0.1 * fnorm1 < s->fnorm) {
-        double r = fnorm1 / s->fnorm;
+    if (0.1 * fnorm1 < fnorm0) {
+        double r = fnorm1 / fnorm0;
         actred = 1.0 - r * r;
     }
     const double prered = s->prered, dirder = s->dirder;
@@ -396,109 +480,142 @@ NGX_HD NGX_NI static int lm_feed_f(LMState *s, double fnorm_new) {
     if (ratio <= 0.25) {
         double temp = 0.5;
         if (actred < 0.0) temp = 0.5 * dirder / (dirder + 0.5 * actred);
-        if (0.1 * fnorm1 >= s->fnorm || temp < 0.1) temp = 0.1;
-        s->delta = temp * lm_min(s->delta, s->pnorm / 0.1);
-        s->par /= temp;
-    } else if (s->par == 0.0 || ratio >= 0.75) {
-        s->delta = s->pnorm / 0.5;
-        s->par *= 0.5;
+        if (0.1 * fnorm1 >= fnorm0 || temp < 0.1) temp = 0.1;
+        delta = temp * lm_min(delta, pnorm / 0.1);
+        par /= temp;
+    } else if (par == 0.0 || ratio >= 0.75) {
+        delta = pnorm / 0.5;
+        par *= 0.5;
     }
     int accepted = 0;
     if (ratio >= 1.0e-4) {
         double *wa2 = s->v[6];
-#pragma unroll 1
-        for (int j = 0; j < n; j++) {
-            s->x[j] = s->xtrial[j];
-            wa2[j] = s->diag[j] * s->x[j];
+        LM_FOR(j, 0, n) {
+            const double xj = s->xtrial[j];
+            s->x[j] = xj;
+            wa2[j] = s->diag[j] * xj;
         }
-        s->xnorm = lm_enorm(n, wa2);
-        s->fnorm = fnorm1;
-        s->iter += 1;
+        LM_SYNC;
+        xnorm = lm_enorm(n, wa2);
         accepted = 1;
     }
     int info = 0;
-    bool small = fabs(actred) <= s->ftol && prered <= s->ftol
+    bool small = fabs(actred) <= ftol && prered <= ftol
         && 0.5 * ratio <= 1.0;
     if (small) info = 1;
-    if (s->delta <= s->xtol * s->xnorm) info = 2;
+    if (delta <= xtol * xnorm) info = 2;
     if (small && info == 2) info = 3;
     if (info == 0) {
-        if (s->nfev >= s->maxfev) info = 5;
+        if (nfev >= maxfev) info = 5;
         if (fabs(actred) <= LM_EPSMCH && prered <= LM_EPSMCH
             && 0.5 * ratio <= 1.0)
             info = 6;
-        if (s->delta <= LM_EPSMCH * s->xnorm) info = 7;
-        if (s->gnorm <= LM_EPSMCH) info = 8;
+        if (delta <= LM_EPSMCH * xnorm) info = 7;
+        if (gnorm <= LM_EPSMCH) info = 8;
     }
-    if (info != 0) {
-        s->info = info;
-        s->action = LM_ACT_DONE;
-        return accepted;
+    LM_SYNC;
+    LM_ONE {
+        s->nfev = nfev;
+        s->delta = delta;
+        s->par = par;
+        if (accepted) {
+            s->xnorm = xnorm;
+            s->fnorm = fnorm1;
+            s->iter += 1;
+        }
+        if (info != 0) {
+            s->info = info;
+            s->action = LM_ACT_DONE;
+        } else if (accepted) {
+            s->action = LM_ACT_EVAL_J;      // back to the outer loop
+        }
     }
-    if (ratio >= 1.0e-4) {
-        s->action = LM_ACT_EVAL_J;      // back to the outer loop
-    } else {
-        lm_propose(s);                  // stay in the inner loop
-    }
+    LM_SYNC;
+    if (info == 0 && !accepted)
+        lm_propose(s);                      // stay in the inner loop
     return accepted;
 }
 
 // Feed the result of an EVAL_J pass at s->x: A = J^T J (column major, ld
 // LM_MAXP), b = J^T f.  extra_nfev is the number of residual evaluations the
 // Jacobian cost (n for forward differences, 0 for the analytic one).
+// (whole warp)
 NGX_HD NGX_NI static void lm_feed_j(LMState *s, const double *A, const double *b,
                              int extra_nfev) {
     int n = s->n;
-    s->njev += 1;
-    s->nfev += extra_nfev;
-    lm_pchol(n, A, s->R, s->ipvt, s->acnorm, s->v[0]);
-    if (s->iter == 1) {
-        double *wa3 = s->v[5];
-#pragma unroll 1
-        for (int j = 0; j < n; j++) {
-            s->diag[j] = s->acnorm[j];
-            if (s->acnorm[j] == 0.0) s->diag[j] = 1.0;
-            wa3[j] = s->diag[j] * s->x[j];
-        }
-        s->xnorm = lm_enorm(n, wa3);
-        s->delta = s->factor * s->xnorm;
-        if (s->delta == 0.0) s->delta = s->factor;
+    const int first = s->iter == 1;
+    const double fnorm = s->fnorm, gtol = s->gtol, factor = s->factor;
+    LM_SYNC;
+    LM_ONE {
+        s->njev += 1;
+        s->nfev += extra_nfev;
     }
-    // qtf = R^-T P^T b
+    lm_pchol(n, A, s->R, s->ipvt, s->acnorm, s->v[0]);
+    double *wa3 = s->v[5], *vv = s->v[6];
+    if (first) {
+        LM_FOR(j, 0, n) {
+            double dj = s->acnorm[j];
+            if (dj == 0.0) dj = 1.0;
+            s->diag[j] = dj;
+            wa3[j] = dj * s->x[j];
+        }
+        LM_SYNC;
+        const double xnorm = lm_enorm(n, wa3);
+        double delta = factor * xnorm;
+        if (delta == 0.0) delta = factor;
+        LM_ONE {
+            s->xnorm = xnorm;
+            s->delta = delta;
+        }
+        LM_SYNC;
+    }
+    // qtf = R^-T P^T b: v[k] loses R[j,k] qtf[j] over ascending j (the order
+    // of the scalar dot-product form), lane k its element
+    LM_FOR(k, 0, n) vv[k] = b[s->ipvt[k]];
+    LM_SYNC;
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
-        double rjj = s->R[j + LM_MAXP * j];
-        double v = b[s->ipvt[j]];
-#pragma unroll 1
-        for (int i = 0; i < j; i++) v -= s->R[i + LM_MAXP * j] * s->qtf[i];
-        s->qtf[j] = (rjj != 0.0) ? v / rjj : 0.0;
+        const double rjj = s->R[j + LM_MAXP * j];
+        const double qj = (rjj != 0.0) ? vv[j] / rjj : 0.0;
+        LM_ONE s->qtf[j] = qj;
+        LM_FOR(k, j + 1, n) vv[k] -= s->R[j + LM_MAXP * k] * qj;
+        LM_SYNC;
     }
     // gnorm = max_j |(J^T f)_j| / (acnorm_j |f|).  MINPACK forms (J^T f)_j as
     // sum_i R[i,j] qtf[i]/|f|; that is b[ipvt_j]/|f| exactly, and gnorm only
     // feeds the gnorm <= gtol (= 0) and gnorm <= eps tests
     double gnorm = 0.0;
-    if (s->fnorm != 0.0) {
-        double ifnorm = 1.0 / s->fnorm;
-#pragma unroll 1
-        for (int j = 0; j < n; j++) {
+    if (fnorm != 0.0) {
+        double ifnorm = 1.0 / fnorm;
+        LM_FOR(j, 0, n) {
             int l = s->ipvt[j];
-            if (s->acnorm[l] != 0.0)
-                gnorm = lm_max(gnorm, fabs((b[l] * ifnorm) / s->acnorm[l]));
+            const double an = s->acnorm[l];
+            wa3[j] = an != 0.0 ? fabs((b[l] * ifnorm) / an) : 0.0;
+        }
+        LM_SYNC;
+#pragma unroll 1
+        for (int j = 0; j < n; j++) gnorm = lm_max(gnorm, wa3[j]);
+    }
+    LM_SYNC;
+    LM_ONE {
+        s->gnorm = gnorm;
+        if (gnorm <= gtol) {
+            s->info = 4;
+            s->action = LM_ACT_DONE;
         }
     }
-    s->gnorm = gnorm;
-    if (gnorm <= s->gtol) {
-        s->info = 4;
-        s->action = LM_ACT_DONE;
+    if (gnorm <= gtol) {
+        LM_SYNC;
         return;
     }
-#pragma unroll 1
-    for (int j = 0; j < n; j++) s->diag[j] = lm_max(s->diag[j], s->acnorm[j]);
+    LM_FOR(j, 0, n) s->diag[j] = lm_max(s->diag[j], s->acnorm[j]);
+    LM_SYNC;
     lm_propose(s);
 }
 
 // cov0 = (J^T J)^-1 = P R^-1 R^-T P^T from the last factorisation (row
 // major n x n out).  Returns 0 when R is singular (scipy: cov_x None).
+// (whole warp: lane j inverts column j of R, then one lane per matrix entry)
 NGX_HD NGX_NI static int lm_cov0(LMState *s, double *cov) {
     int n = s->n;
     const int ld = LM_MAXP;
@@ -506,10 +623,9 @@ NGX_HD NGX_NI static int lm_cov0(LMState *s, double *cov) {
 #pragma unroll 1
     for (int j = 0; j < n; j++)
         if (s->R[j + ld * j] == 0.0) return 0;
+    LM_FOR(j, 0, n) {
 #pragma unroll 1
-    for (int i = 0; i < n * LM_MAXP; i++) rinv[i] = 0.0;
-#pragma unroll 1
-    for (int j = 0; j < n; j++) {
+        for (int i = 0; i < n; i++) rinv[i + ld * j] = 0.0;
         rinv[j + ld * j] = 1.0 / s->R[j + ld * j];
 #pragma unroll 1
         for (int i = j - 1; i >= 0; i--) {
@@ -520,18 +636,21 @@ NGX_HD NGX_NI static int lm_cov0(LMState *s, double *cov) {
             rinv[i + ld * j] = -sum / s->R[i + ld * i];
         }
     }
+    LM_SYNC;
     // row ipvt[j] of P R^-1 is row j of R^-1
+    LM_FOR(q, 0, n * (n + 1) / 2) {
+        // q -> (a, b), b <= a
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= q) a++;
+        int b = q - a * (a + 1) / 2;
+        double sum = 0.0;
 #pragma unroll 1
-    for (int a = 0; a < n; a++)
-#pragma unroll 1
-        for (int b = 0; b <= a; b++) {
-            double sum = 0.0;
-#pragma unroll 1
-            for (int k = 0; k < n; k++)
-                sum += rinv[a + ld * k] * rinv[b + ld * k];
-            cov[s->ipvt[a] * n + s->ipvt[b]] = sum;
-            cov[s->ipvt[b] * n + s->ipvt[a]] = sum;
-        }
+        for (int k = 0; k < n; k++)
+            sum += rinv[a + ld * k] * rinv[b + ld * k];
+        cov[s->ipvt[a] * n + s->ipvt[b]] = sum;
+        cov[s->ipvt[b] * n + s->ipvt[a]] = sum;
+    }
+    LM_SYNC;
     return 1;
 }
 
@@ -539,6 +658,7 @@ NGX_HD NGX_NI static int lm_cov0(LMState *s, double *cov) {
 // construction: a negative eigenvalue exists iff the matrix is not positive
 // semi-definite, decided by a Cholesky sweep with a rounding-level floor.
 // Returns flag bits (NEG_COV_EIG 1024, NEG_COV_DIAG 2048, EIG_NOTFINITE 8192)
+// (whole warp: lane i owns row i of L)
 NGX_HD NGX_NI static int lm_test_cov(int n, const double *cov, double *L) {
     int flags = 0;
 #pragma unroll 1
@@ -559,14 +679,15 @@ NGX_HD NGX_NI static int lm_test_cov(int n, const double *cov, double *L) {
         for (int k = 0; k < j; k++) dsum -= L[j * n + k] * L[j * n + k];
         if (dsum < -tol) { neg = 1; break; }
         double ljj = sqrt(dsum > 0.0 ? dsum : 0.0);
-        L[j * n + j] = ljj;
-#pragma unroll 1
-        for (int i = j + 1; i < n; i++) {
+        LM_SYNC;
+        LM_ONE L[j * n + j] = ljj;
+        LM_FOR(i, j + 1, n) {
             double sum = cov[i * n + j];
 #pragma unroll 1
             for (int k = 0; k < j; k++) sum -= L[i * n + k] * L[j * n + k];
             L[i * n + j] = ljj > 0.0 ? sum / ljj : 0.0;
         }
+        LM_SYNC;
     }
     if (neg || (flags & 2048)) flags |= 1024;
     return flags;

@@ -1238,6 +1238,152 @@ def gen_guessers():
     save("guessers", **{k: np.asarray(v) for k, v in out.items()})
 
 
+class _OneBasedMinpack(object):
+    """scipy >= 1.15 returns a 0-based ipvt from _lmdif/_lmder; the bounded
+    branch of the reference (leastsqbound.py:533-540) still subtracts 1
+    (Fortran convention), which scrambles its covariance under this scipy
+    (SURVEY.md section 7).  This shim hands the reference the 1-based ipvt
+    its code assumes, WITHOUT touching the reference: the fit itself (x, nfev,
+    ier) is unaffected, only cov_x changes - to the intended
+    (J_ext^T J_ext)^-1."""
+
+    def __init__(self, real):
+        self._real = real
+
+    def _fix(self, r):
+        r[1]["ipvt"] = r[1]["ipvt"] + 1
+        return r
+
+    def _lmdif(self, *a):
+        return self._fix(self._real._lmdif(*a))
+
+    def _lmder(self, *a):
+        return self._fix(self._real._lmder(*a))
+
+    def __getattr__(self, k):
+        return getattr(self._real, k)
+
+
+def _bounded_fits(fitter, b, npars):
+    """run the fitter over the batch twice: as the reference runs here, and
+    with the 1-based-ipvt shim (intended covariance)"""
+    import ngmix.fitting.leastsqbound as lsb
+    n = b["images"].shape[0]
+    res = dict(flags=np.zeros(n, "i4"), nfev=np.zeros(n, "i4"),
+               ier=np.zeros(n, "i4"), pars=np.zeros((n, npars)),
+               pars_err=np.zeros((n, npars)),
+               pars_cov0=np.zeros((n, npars, npars)),
+               pars_cov=np.zeros((n, npars, npars)),
+               pars_cov0_asrun=np.zeros((n, npars, npars)),
+               flags_asrun=np.zeros(n, "i4"),
+               lnprob=np.full(n, np.nan), s2n=np.full(n, np.nan),
+               chi2per=np.full(n, np.nan))
+    real = lsb._minpack
+    for shim in (False, True):
+        lsb._minpack = _OneBasedMinpack(real) if shim else real
+        try:
+            for i in range(n):
+                psf_obs = ngmix.Observation(
+                    np.ones((5, 5)),
+                    jacobian=ngmix.DiagonalJacobian(row=2, col=2, scale=0.263),
+                    gmix=ngmix.GMix(pars=b["psf"][i].ravel()))
+                obs = ngmix.Observation(
+                    b["images"][i], weight=b["weights"][i],
+                    jacobian=jac_from_record(b["jac"][i]), psf=psf_obs)
+                r = fitter.go(obs, b["guess"][i].copy())
+                c0 = r["pars_cov0"]
+                c0 = np.nan if c0 is None else c0
+                if not shim:
+                    res["pars_cov0_asrun"][i] = c0
+                    res["flags_asrun"][i] = r["flags"]
+                    res["nfev"][i] = r["nfev"]
+                    res["ier"][i] = r["ier"]
+                    res["pars"][i] = r["pars"]
+                else:
+                    assert r["nfev"] == res["nfev"][i]
+                    assert np.array_equal(r["pars"], res["pars"][i])
+                    res["flags"][i] = r["flags"]
+                    res["pars_err"][i] = r["pars_err"]
+                    res["pars_cov0"][i] = c0
+                    res["pars_cov"][i] = r["pars_cov"]
+                    if r["flags"] == 0:
+                        res["lnprob"][i] = r["lnprob"]
+                        res["s2n"][i] = r["s2n"]
+                        res["chi2per"][i] = r["chi2per"]
+        finally:
+            lsb._minpack = real
+    return res
+
+
+def gen_lm_bounds():
+    """bounded fits (prior members with `bounds`, leastsqbound.py:183-263,
+    445-552): bdf with fracdev in (0, 1) through lmdif, as
+    tests/test_leastsqbound.py:114-176 / tests/_priors.py:24-35, and exp with
+    bounded T and flux through lmder with the analytic jacobian, as
+    tests/test_fitting_lm_jacobian.py:216-250"""
+    from ngmix import priors, joint_prior
+    from ngmix.fitting import Fitter
+    out = {}
+    # ---- bdf, fracdev bounded, forward differences
+    b = sims.make_bdf_batch(8, seed0=9100, dims=(48, 48), noise=0.02)
+    rng = np.random.RandomState(7)
+    prior = joint_prior.PriorBDFSep(
+        cen_prior=priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng),
+        g_prior=priors.GPriorBA(0.3, rng=rng),
+        T_prior=priors.FlatPrior(-1.0, 1.0e3, rng=rng),
+        fracdev_prior=priors.Normal(0.5, 0.3, rng=rng, bounds=[0.0, 1.0]),
+        F_prior=priors.FlatPrior(-100.0, 1.0e9, rng=rng))
+    assert prior.bounds is not None
+    res = _bounded_fits(Fitter(model="bdf", prior=prior), b, 7)
+    print("bounded bdf flags", res["flags"], "asrun", res["flags_asrun"],
+          "nfev", res["nfev"], "ier", res["ier"])
+    for k in ("images", "weights", "jac", "psf", "guess"):
+        out["bdf_" + k] = b[k]
+    for k, v in res.items():
+        out["bdf_res_" + k] = v
+    # ---- exp, T and flux bounded, analytic jacobian
+    b = sims.make_lm_batch(8, seed0=9200, dims=(40, 40), noise=0.05)
+    rng = np.random.RandomState(8)
+    prior = joint_prior.PriorSimpleSep(
+        cen_prior=priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng),
+        g_prior=priors.GPriorBA(0.3, rng=rng),
+        T_prior=priors.Normal(0.4, 1.0, bounds=[0.01, 100.0], rng=rng),
+        F_prior=priors.Normal(100.0, 100.0, bounds=[1.0, 1.0e9], rng=rng))
+    assert prior.bounds is not None
+    for tag, analytic in (("an", True), ("fd", False)):
+        res = _bounded_fits(
+            Fitter(model="exp", prior=prior, analytic_jacobian=analytic),
+            b, 6)
+        print("bounded exp", tag, "flags", res["flags"], "asrun",
+              res["flags_asrun"], "nfev", res["nfev"], "ier", res["ier"])
+        for k, v in res.items():
+            out["exp_%s_res_%s" % (tag, k)] = v
+    for k in ("images", "weights", "jac", "psf", "guess"):
+        out["exp_" + k] = b[k]
+    # ---- exp with tight two-sided bounds and a one-sided lower bound, worse
+    #      guesses: the transforms take part in many iterations
+    b = sims.make_lm_batch(8, seed0=9300, dims=(40, 40), noise=0.5,
+                           guess_frac=0.3)
+    rng = np.random.RandomState(9)
+    prior = joint_prior.PriorSimpleSep(
+        cen_prior=priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng),
+        g_prior=priors.GPriorBA(0.3, rng=rng),
+        T_prior=priors.Normal(0.5, 1.0, bounds=[0.05, 5.0], rng=rng),
+        F_prior=priors.Normal(100.0, 100.0, bounds=[1.0, None], rng=rng))
+    assert prior.bounds is not None
+    for tag, analytic in (("an", True), ("fd", False)):
+        res = _bounded_fits(
+            Fitter(model="exp", prior=prior, analytic_jacobian=analytic),
+            b, 6)
+        print("bounded exp2", tag, "flags", res["flags"], "asrun",
+              res["flags_asrun"], "nfev", res["nfev"], "ier", res["ier"])
+        for k, v in res.items():
+            out["exp2_%s_res_%s" % (tag, k)] = v
+    for k in ("images", "weights", "jac", "psf", "guess"):
+        out["exp2_" + k] = b[k]
+    save("lm_bounds", **out)
+
+
 GENERATORS = {
     "fastexp": gen_fastexp,
     "gmix": gen_gmix,
@@ -1259,6 +1405,7 @@ GENERATORS = {
     "lm_multi_wide": gen_lm_multi_wide,
     "psfflux": gen_psfflux,
     "boot": gen_boot,
+    "lm_bounds": gen_lm_bounds,
 }
 
 if __name__ == "__main__":

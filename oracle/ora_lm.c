@@ -262,7 +262,39 @@ typedef struct {
     /* scratch for the jacobian */
     double *dout;           /* 6 * npix */
     double *vv, *uu, *area;
+    /* bounded fits (leastsqbound.py:183-263): MINPACK works on internal
+     * (unconstrained) parameters; NULL when no prior member has bounds */
+    const ora_bounds *bounds;
 } fitctx;
+
+/* _internal2external_lambda, leastsqbound.py:216-229 */
+static double b_i2e(const ora_bounds *b, int i, double x) {
+    switch (b->type[i]) {
+    case 1: return b->lo[i] - 1.0 + sqrt(x * x + 1.0);
+    case 2: return b->hi[i] + 1.0 - sqrt(x * x + 1.0);
+    case 3: return b->lo[i] + ((b->hi[i] - b->lo[i]) / 2.0) * (sin(x) + 1.0);
+    default: return x;
+    }
+}
+/* _external2internal_lambda, leastsqbound.py:248-261 */
+static double b_e2i(const ora_bounds *b, int i, double x) {
+    double t;
+    switch (b->type[i]) {
+    case 1: t = x - b->lo[i] + 1.0; return sqrt(t * t - 1.0);
+    case 2: t = b->hi[i] - x + 1.0; return sqrt(t * t - 1.0);
+    case 3: return asin((2.0 * (x - b->lo[i]) / (b->hi[i] - b->lo[i])) - 1.0);
+    default: return x;
+    }
+}
+/* _internal2external_grad, leastsqbound.py:183-199 */
+static double b_grad(const ora_bounds *b, int i, double v) {
+    switch (b->type[i]) {
+    case 1: return v / sqrt(v * v + 1.0);
+    case 2: return -v / sqrt(v * v + 1.0);
+    case 3: return (b->hi[i] - b->lo[i]) * cos(v) / 2.0;
+    default: return 1.0;
+    }
+}
 
 /* _fill_gmix_all, results.py:306-347 */
 static int ctx_fill_gmix(fitctx *c, const double *pars) {
@@ -385,15 +417,34 @@ static int ctx_calc_jacobian(fitctx *c, const double *pars, double *jac) {
     return ORA_OK;
 }
 
+/* wfunc / wDfun of leastsqbound (leastsqbound.py:469-489): the residuals at
+ * i2e(x); the jacobian's columns scaled by d(external)/d(internal) */
 static int cb_fdiff(void *ctx, int m, int n, const double *x, double *fvec) {
-    (void)m; (void)n;
-    ctx_calc_fdiff((fitctx *)ctx, x, fvec);
+    (void)m;
+    fitctx *c = (fitctx *)ctx;
+    if (c->bounds) {
+        double xe[ORA_MAXP];
+        for (int i = 0; i < n; i++) xe[i] = b_i2e(c->bounds, i, x[i]);
+        ctx_calc_fdiff(c, xe, fvec);
+        return 0;
+    }
+    ctx_calc_fdiff(c, x, fvec);
     return 0;
 }
 
 static int cb_jac(void *ctx, int m, int n, const double *x, double *fjac) {
-    (void)m; (void)n;
-    ctx_calc_jacobian((fitctx *)ctx, x, fjac);
+    fitctx *c = (fitctx *)ctx;
+    if (c->bounds) {
+        double xe[ORA_MAXP];
+        for (int i = 0; i < n; i++) xe[i] = b_i2e(c->bounds, i, x[i]);
+        ctx_calc_jacobian(c, xe, fjac);
+        for (int j = 0; j < n; j++) {
+            double g = b_grad(c->bounds, j, x[j]);
+            for (int i = 0; i < m; i++) fjac[i + (size_t)j * m] *= g;
+        }
+        return 0;
+    }
+    ctx_calc_jacobian(c, x, fjac);
     return 0;
 }
 
@@ -505,13 +556,17 @@ int ora_lm_calc_jacobian(int model, const ora_pixel *pixels, int npix,
     return st;
 }
 
-/* Fitter.go on one stamp */
-int ora_lm_fit(int model, const double *image, const double *weight,
-               int nrow, int ncol, const ora_jac *jac, const double *psf_pars,
-               int npsf, const double *guess, const ora_prior *prior,
-               int maxfev, double ftol, double xtol, int analytic_jacobian,
-               int ignore_zero_weight, ora_lm_result *res) {
+/* Fitter.go on one stamp; bounds (nullable) = prior.bounds of the reference:
+ * leastsqbound's transformed fit, leastsqbound.py:445-552 */
+int ora_lm_fit_bounded(int model, const double *image, const double *weight,
+                       int nrow, int ncol, const ora_jac *jac,
+                       const double *psf_pars, int npsf, const double *guess,
+                       const ora_prior *prior, const ora_bounds *bounds,
+                       int maxfev, double ftol, double xtol,
+                       int analytic_jacobian, int ignore_zero_weight,
+                       ora_lm_result *res) {
     memset(res, 0, sizeof(*res));
+    if (bounds && !bounds->present) bounds = NULL;
     int ntot = nrow * ncol;
     ora_pixel *pixels = (ora_pixel *)malloc(sizeof(ora_pixel) * (size_t)ntot);
     int npixv = ntot;
@@ -524,10 +579,12 @@ int ora_lm_fit(int model, const double *image, const double *weight,
                     ignore_zero_weight);
     fitctx c;
     ctx_init(&c, model, pixels, npixv, psf_pars, npsf, prior);
+    c.bounds = bounds;
     int np = c.npars, m = c.fdiff_size;
 
     double x[ORA_MAXP];
-    for (int i = 0; i < np; i++) x[i] = guess[i];
+    for (int i = 0; i < np; i++)
+        x[i] = bounds ? b_e2i(bounds, i, guess[i]) : guess[i];
     double *fvec = (double *)malloc(sizeof(double) * (size_t)m * (np + 1));
     double *fjac = fvec + m;
     int ipvt[ORA_MAXP];
@@ -549,6 +606,16 @@ int ora_lm_fit(int model, const double *image, const double *weight,
     res->nfev = nfev;
     res->njev = njev;
     res->ier = ier;
+    if (bounds) {
+        /* x = i2e(x_internal); fjac from internal to external parameters:
+         * column j of R (parameter ipvt[j]) over that parameter's gradient
+         * (leastsqbound.py:531-538, with the 1-based ipvt its code assumes) */
+        for (int j = 0; j < np; j++) {
+            double g = b_grad(bounds, ipvt[j], x[ipvt[j]]);
+            for (int i = 0; i <= j; i++) fjac[i + (size_t)j * m] /= g;
+        }
+        for (int i = 0; i < np; i++) x[i] = b_i2e(bounds, i, x[i]);
+    }
     for (int i = 0; i < np; i++) res->pars[i] = x[i];
     for (int i = 0; i < np * np; i++) res->pars_cov0[i] = NAN;
 
@@ -596,6 +663,7 @@ int ora_lm_fit(int model, const double *image, const double *weight,
         for (int i = 0; i < np; i++) res->pars_err[i] = CDEF;
         for (int i = 0; i < np * np; i++) res->pars_cov[i] = CDEF;
     } else {
+        c.bounds = NULL;            /* func(pars) at the external pars */
         ctx_calc_fdiff(&c, res->pars, fvec);
         int dof = m - c.n_prior_pars - np;
         if (dof == 0) {
@@ -666,6 +734,16 @@ int ora_lm_fit(int model, const double *image, const double *weight,
     ctx_free(&c);
     free(pixels);
     return 0;
+}
+
+int ora_lm_fit(int model, const double *image, const double *weight,
+               int nrow, int ncol, const ora_jac *jac, const double *psf_pars,
+               int npsf, const double *guess, const ora_prior *prior,
+               int maxfev, double ftol, double xtol, int analytic_jacobian,
+               int ignore_zero_weight, ora_lm_result *res) {
+    return ora_lm_fit_bounded(model, image, weight, nrow, ncol, jac, psf_pars,
+                              npsf, guess, prior, NULL, maxfev, ftol, xtol,
+                              analytic_jacobian, ignore_zero_weight, res);
 }
 
 /* ------------------------------------------------------------------ */

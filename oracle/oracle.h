@@ -123,6 +123,21 @@ typedef struct {
         pars_cov[ORA_MAXP * ORA_MAXP];
 } ora_lm_result;
 
+/* prior.bounds of the reference (joint_prior.py:37-61): type 0 none, 1 lower
+ * bound only, 2 upper only, 3 both */
+typedef struct {
+    int32_t present;
+    int32_t type[ORA_MAXP];
+    double lo[ORA_MAXP], hi[ORA_MAXP];
+} ora_bounds;
+
+int ora_lm_fit_bounded(int model, const double *image, const double *weight,
+                       int nrow, int ncol, const ora_jac *jac,
+                       const double *psf_pars, int npsf, const double *guess,
+                       const ora_prior *prior, const ora_bounds *bounds,
+                       int maxfev, double ftol, double xtol,
+                       int analytic_jacobian, int ignore_zero_weight,
+                       ora_lm_result *res);
 int ora_lm_fit(int model, const double *image, const double *weight,
                int nrow, int ncol, const ora_jac *jac, const double *psf_pars,
                int npsf, const double *guess, const ora_prior *prior,
