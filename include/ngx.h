@@ -209,10 +209,24 @@ typedef struct {
 } ngx_prior;
 
 /* DEFAULT_LM_PARS, ngmix/defaults.py:17 */
+#define NGX_MAX_PARS 14
+/* bounds kinds of one parameter (prior.bounds of the reference,
+ * joint_prior.py:37-61; transforms of leastsqbound.py:183-263) */
+#define NGX_B_NONE 0
+#define NGX_B_LOWER 1     /* (min, None) */
+#define NGX_B_UPPER 2     /* (None, max) */
+#define NGX_B_BOTH 3      /* (min, max) */
 typedef struct {
     int32_t maxfev;             /* 4000 */
     int32_t analytic_jacobian;  /* Fitter(analytic_jacobian=True) */
     double ftol, xtol;          /* 1e-5, 1e-5 */
+    /* bounded fit (run_leastsq(bounds=prior.bounds), leastsqbound.py:445-552):
+     * MINPACK iterates on internal, unconstrained parameters; residuals are
+     * evaluated at the external ones.  nbounds = 0: unbounded fit. */
+    int32_t nbounds;            /* 0 or the number of parameters */
+    int32_t btype[NGX_MAX_PARS];
+    int32_t pad_;
+    double blo[NGX_MAX_PARS], bhi[NGX_MAX_PARS];
 } ngx_lm_pars;
 
 /* result record of one fit: the keys of run_leastsq

@@ -82,7 +82,26 @@ class Prior(C.Structure):
 
 class LMPars(C.Structure):
     _fields_ = [("maxfev", C.c_int32), ("analytic_jacobian", C.c_int32),
-                ("ftol", C.c_double), ("xtol", C.c_double)]
+                ("ftol", C.c_double), ("xtol", C.c_double),
+                ("nbounds", C.c_int32), ("btype", C.c_int32 * 14),
+                ("pad_", C.c_int32),
+                ("blo", C.c_double * 14), ("bhi", C.c_double * 14)]
+
+    def set_bounds(self, bounds):
+        """bounds: None or [(min | None, max | None)] per parameter, the
+        reference's prior.bounds (joint_prior.py:37-61)"""
+        self.nbounds = 0
+        if bounds is None:
+            return self
+        if len(bounds) > 14:
+            raise ValueError("at most 14 parameters")
+        self.nbounds = len(bounds)
+        for i, (lo, hi) in enumerate(bounds):
+            self.btype[i] = (1 if lo is not None else 0) \
+                + (2 if hi is not None else 0)
+            self.blo[i] = 0.0 if lo is None else lo
+            self.bhi[i] = 0.0 if hi is None else hi
+        return self
 
 
 class EMConf(C.Structure):
@@ -385,10 +404,12 @@ def noise_cov_b(gpars, dcov, flux, jac, weights, noise):
 # ---------------------------------------------------------------- LM
 def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
            maxfev=4000, ftol=1.0e-5, xtol=1.0e-5, analytic_jacobian=True,
-           ignore_zero_weight=True, out=None):
+           ignore_zero_weight=True, out=None, bounds=None):
     """
     batched Fitter.go through the host-buffer entry point.
-    images/weights [n,H,W]; psf_pars [n,npsf,6] or None; guess [n,npars].
+    images/weights [n,H,W]; psf_pars [n,npsf,6] or None; guess [n,npars];
+    bounds: None or the reference's prior.bounds, [(min | None, max | None)]
+    per parameter (leastsqbound's transformed fit).
     Returns LM_RESULT_DTYPE [n] (written into `out` when given, e.g. a view
     of pinned host memory, which lets the D2H copy run asynchronously).
     """
@@ -426,6 +447,10 @@ def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
         psf_pars = psf_pars.reshape(n, npsf, 6)
     pr = prior if prior is not None else Prior()
     lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)
+    if bounds is not None:
+        if len(bounds) != guess.shape[1]:
+            raise ValueError("length of bounds != number of parameters")
+        lmp.set_bounds(bounds)
     if out is None:
         res = np.empty(n, dtype=LM_RESULT_DTYPE)
     else:
@@ -530,13 +555,14 @@ def lm_fit_multi_device(model, nobj, d_stamp_start, d_stamp_band, nband,
 def lm_fit_device(model, n, d_images, d_weights, d_jac, nrow, ncol, d_psf,
                   npsf, d_guess, d_res, prior=None, maxfev=4000, ftol=1.0e-5,
                   xtol=1.0e-5, analytic_jacobian=True, ignore_zero_weight=True,
-                  stream=0):
+                  stream=0, bounds=None):
     """
     device-pointer entry point: d_* are integer device addresses (for example
     torch tensors' data_ptr()); enqueues on `stream` and returns at once.
     """
     pr = prior if prior is not None else Prior()
     lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)
+    lmp.set_bounds(bounds)
     check(lib().ngx_lm_fit(
         C.c_int(n), C.c_int(MODELS[model]), C.c_void_p(d_images),
         C.c_void_p(d_weights), C.c_void_p(d_jac), C.c_int(nrow),

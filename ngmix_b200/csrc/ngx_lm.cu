@@ -30,6 +30,7 @@
 // the other CTAs resident on the SM keep the fp64 pipe busy.
 #include <cuda_pipeline.h>
 #include <mutex>
+#include <vector>
 #include "ngx_core.cuh"
 #include "ngx_host.cuh"
 #include "ngx_lm_solve.cuh"
@@ -56,6 +57,9 @@ namespace ngx {
 struct LMArgs {
     int n, model, np, ngauss0, npsf, ngauss, nrow, ncol, ntot;
     int ignore_zero_weight, analytic, nq, tpr;
+    // per round a warp moves on by rot_v / rot_d chunk slots (value pass /
+    // derivative and forward-difference passes): see pick_rotation
+    int rot_v, rot_d;
     ngx_prior prior;
     ngx_lm_pars lm;
     const double *images, *weights;
@@ -70,9 +74,48 @@ struct LMArgs {
     double *gscratch;
 };
 
+// bounded fits: leastsqbound's parameter transforms (leastsqbound.py:183-263).
+// MINPACK iterates on internal (unconstrained) parameters, the model and the
+// priors are evaluated at the external ones.
+__device__ __forceinline__ double b_i2e(const ngx_lm_pars &lm, int i,
+                                        double x) {
+    if (lm.nbounds == 0) return x;
+    switch (lm.btype[i]) {
+    case NGX_B_LOWER: return lm.blo[i] - 1.0 + sqrt(x * x + 1.0);
+    case NGX_B_UPPER: return lm.bhi[i] + 1.0 - sqrt(x * x + 1.0);
+    case NGX_B_BOTH:
+        return lm.blo[i] + ((lm.bhi[i] - lm.blo[i]) / 2.0) * (sin(x) + 1.0);
+    default: return x;
+    }
+}
+__device__ __forceinline__ double b_e2i(const ngx_lm_pars &lm, int i,
+                                        double x) {
+    if (lm.nbounds == 0) return x;
+    double t;
+    switch (lm.btype[i]) {
+    case NGX_B_LOWER: t = x - lm.blo[i] + 1.0; return sqrt(t * t - 1.0);
+    case NGX_B_UPPER: t = lm.bhi[i] - x + 1.0; return sqrt(t * t - 1.0);
+    case NGX_B_BOTH:
+        return asin((2.0 * (x - lm.blo[i]) / (lm.bhi[i] - lm.blo[i])) - 1.0);
+    default: return x;
+    }
+}
+// d(external)/d(internal), _internal2external_grad
+__device__ __forceinline__ double b_grad(const ngx_lm_pars &lm, int i,
+                                         double v) {
+    if (lm.nbounds == 0) return 1.0;
+    switch (lm.btype[i]) {
+    case NGX_B_LOWER: return v / sqrt(v * v + 1.0);
+    case NGX_B_UPPER: return -v / sqrt(v * v + 1.0);
+    case NGX_B_BOTH: return (lm.bhi[i] - lm.blo[i]) * cos(v) / 2.0;
+    default: return 1.0;
+    }
+}
+
 struct LMShared {
     LMState st;
-    double xeval[LM_MAXP];
+    double xeval[LM_MAXP];     // external parameters of the trial point
+    double xcur[LM_MAXP];      // external parameters of the accepted point
     double psf[16 * 6];
     double psf_row, psf_col, psf_ipsum;
     double cur_ssq, cur_rfirst2, cur_num, cur_den;   // at the accepted x
@@ -86,11 +129,10 @@ struct LMShared {
 // build the convolved mixture for parameters x: thread k < ngauss owns
 // composed gaussian k = iobj*npsf + ipsf (gmix_convolve_fill's order).
 // sh->status is OR-ed with range errors.
-static __device__ __noinline__ void build_mixture(const LMArgs &a, LMShared *sh,
-                                           const double *x, double *mix,
-                                           double area,
-                                           double *compact = nullptr) {
-    int k = threadIdx.x;
+static __device__ __noinline__ void build_component(const LMArgs &a,
+                                             LMShared *sh, const double *x,
+                                             int k, double *mix, double area,
+                                             double *compact) {
     if (k >= a.ngauss) return;
     ModelHead h = model_head(a.model, x);
     if (h.status != NGX_ST_OK) {
@@ -151,6 +193,15 @@ static __device__ __noinline__ void build_mixture(const LMArgs &a, LMShared *sh,
     // chi^2 < 25 implies |dv| < 5 sqrt(irr), |du| < 5 sqrt(icc)
     g[12] = 5.0 * sqrt(irr); g[13] = 5.0 * sqrt(icc);
     fill_rot_table(mix + REC * k, pn);
+}
+
+// thread k < ngauss owns composed gaussian k
+static __device__ __forceinline__ void build_mixture(const LMArgs &a,
+                                                     LMShared *sh,
+                                                     const double *x,
+                                                     double *mix, double area,
+                                                     double *compact = nullptr) {
+    build_component(a, sh, x, threadIdx.x, mix, area, compact);
 }
 
 // per tile, the bit mask of the gaussians of mixture gc whose footprint can
@@ -261,8 +312,12 @@ __device__ __forceinline__ void value_pass(const LMArgs &a,
     const int ntile = a.nq >> 5;
     const int nwords = (a.ngauss + 31) >> 5;
     sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+    const int nwarps_ = T >> 5;
+    int wslot = warp;
     for (int base = 0; base < a.nq; base += T * CV) {
-        const int q0 = base + warp * CV * 32 + lane;
+        const int q0 = base + wslot * CV * 32 + lane;
+        wslot += a.rot_v;
+        if (wslot >= nwarps_) wslot -= nwarps_;
         double v[CV], u[CV], acc[CV], wgt[CV], dval[CV];
 #pragma unroll
         for (int c = 0; c < CV; c++) {
@@ -377,8 +432,12 @@ __device__ __forceinline__ void deriv_pass(const LMArgs &a,
     g1g2_to_e1e2(g1, g2, &e1, &e2);
     double iT = 1.0 / Tpar, iflux = 1.0 / flux;
 
+    const int nwarps_ = T >> 5;
+    int wslot = warp;
     for (int base = 0; base < a.nq; base += T * CD) {
-        const int q0 = base + warp * CD * 32 + lane;
+        const int q0 = base + wslot * CD * 32 + lane;
+        wslot += a.rot_d;
+        if (wslot >= nwarps_) wslot -= nwarps_;
         double v[CD], u[CD], wgt[CD], dval[CD];
         double S0[CD], S1[CD], S2[CD], MA[CD], MB[CD], MS[CD];
 #pragma unroll
@@ -528,8 +587,12 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
     double hstep[NPMAX];
 #pragma unroll
     for (int s = 0; s < NPMAX; s++) hstep[s] = s < np ? hs[s] : 1.0;
+    const int nwarps_ = T >> 5;
+    int wslot = warp;
     for (int base = 0; base < a.nq; base += T * CF) {
-        const int q0 = base + warp * CF * 32 + lane;
+        const int q0 = base + wslot * CF * 32 + lane;
+        wslot += a.rot_d;
+        if (wslot >= nwarps_) wslot -= nwarps_;
         double v[CF], u[CF], wgt[CF], dval[CF];
 #pragma unroll
         for (int c = 0; c < CF; c++) {
@@ -685,6 +748,18 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
         flags |= 1 << (info - 5);
     } else {
         have_cov = lm_cov0(s, cov0);
+        if (have_cov && a.lm.nbounds) {
+            // fjac from internal to external parameters (leastsqbound.py:
+            // 531-540): (J_ext^T J_ext)^-1 = G (J_int^T J_int)^-1 G
+            __syncwarp();
+#pragma unroll 1
+            for (int i = lane; i < np * np; i += 32) {
+                const int ra = i / np, rb = i - ra * np;
+                cov0[i] *= b_grad(a.lm, ra, s->x[ra])
+                    * b_grad(a.lm, rb, s->x[rb]);
+            }
+            __syncwarp();
+        }
         if (!have_cov) {
             flags |= NGX_LM_SINGULAR_MATRIX;
         } else {
@@ -716,7 +791,7 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
     for (int i = lane; i < RP; i += 32) {
         double pv = 0.0, pe = 0.0;
         if (i < np) {
-            pv = (info > 4) ? NGX_PDEF : s->x[i];
+            pv = (info > 4) ? NGX_PDEF : sh->xcur[i];
             pe = have_err ? sqrt(pcov[i * np + i]) : NGX_CDEF;
         }
         r.pars[i] = pv;
@@ -742,7 +817,7 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
     double Tv = qnan, Terr = qnan, flux = qnan, fluxerr = qnan;
     if (flags == 0) {
         double lnp_prior = 0.0;
-        int bad = prior_lnprob(a.model, a.prior, s->x, &lnp_prior);
+        int bad = prior_lnprob(a.model, a.prior, sh->xcur, &lnp_prior);
         if (bad) {
             lnprob = -INFINITY;
             num = 0.0;
@@ -759,11 +834,11 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
         double chi2 = lnprob / (-0.5);
         dof = npix - np;
         chi2per = chi2 / dof;
-        Tv = s->x[4];
+        Tv = sh->xcur[4];
         Terr = sqrt(pcov[4 * np + 4]);
         // band 0 of a multi-band fit; the last parameter otherwise
         const int fi = a.nband > 1 ? 5 : np - 1;
-        flux = s->x[fi];
+        flux = sh->xcur[fi];
         fluxerr = sqrt(pcov[fi * np + fi]);
     }
     r.npix = npix;
@@ -788,7 +863,9 @@ static __device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
     double *A = sh->st.A, *b = sh->st.b;
     const int np = a.np;
     if ((threadIdx.x & 31) == 0) {
-    const double *x = sh->st.x;
+    // the accepted point in external parameters (st.x is internal)
+    double *x = sh->st.v[6];
+    for (int i = 0; i < np; i++) x[i] = b_i2e(a.lm, i, sh->st.x[i]);
     int nr = prior_nrows(a.model, a.prior);
     const int status_in = status;
     double *f0 = sh->st.v[7];
@@ -804,7 +881,8 @@ static __device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
             double *xp = sh->st.v[8], *fs = sh->st.v[9];
             for (int s = 0; s < np && !status; s++) {
                 for (int i = 0; i < np; i++) xp[i] = x[i];
-                xp[s] = x[s] + hs[s];
+                // lmdif steps the internal parameter
+                xp[s] = b_i2e(a.lm, s, sh->st.x[s] + hs[s]);
                 if (prior_fill_fdiff(a.model, a.prior, xp, fs)) {
                     status = 1;
                     break;
@@ -834,6 +912,17 @@ static __device__ __noinline__ void feed_jacobian(const LMArgs &a, LMShared *sh,
                 for (int r = 0; r < nr; r++)
                     if (isfinite(f0[r])) sv += jp[r * np + aa] * f0[r];
             b[aa] = sv;
+        }
+    }
+    if (analytic && a.lm.nbounds) {
+        // wDfun = Dfun(i2e(x)) * d(external)/d(internal), leastsqbound.py:
+        // 481-486: J^T J and J^T f pick up the gradients of their columns
+        double *g = sh->st.v[8];
+        for (int i = 0; i < np; i++) g[i] = b_grad(a.lm, i, sh->st.x[i]);
+        for (int aa = 0; aa < np; aa++) {
+            for (int bb = 0; bb < np; bb++)
+                A[aa + LM_MAXP * bb] *= g[aa] * g[bb];
+            b[aa] *= g[aa];
         }
     }
     }
@@ -1098,7 +1187,11 @@ k_lm_fit(LMArgs a) {
                     a.lm.maxfev, a.lm.ftol, a.lm.xtol);
             sh.action = sh.st.action;
             sh.spec = 1;
-            for (int i = 0; i < a.np; i++) sh.xeval[i] = sh.st.xtrial[i];
+            for (int i = 0; i < a.np; i++) {
+                const double xe = sh.st.xtrial[i];
+                sh.xeval[i] = sh.xcur[i] = xe;
+                sh.st.x[i] = sh.st.xtrial[i] = b_e2i(a.lm, i, xe);
+            }
             sh.cur_ssq = sh.cur_rfirst2 = sh.cur_num = sh.cur_den = 0.0;
         }
         __syncthreads();
@@ -1132,7 +1225,7 @@ k_lm_fit(LMArgs a) {
             // the point this pass evaluates: the trial point for a residual
             // evaluation, the accepted point for a Jacobian
             const bool want_f = (action == LM_ACT_EVAL_F);
-            const double *xp = want_f ? sh.xeval : sh.st.x;
+            const double *xp = want_f ? sh.xeval : sh.xcur;
             // Speculation: when the previous trial was accepted (and at the
             // very first evaluation) the residual pass also produces the
             // Jacobian at the trial point, which MINPACK asks for next if the
@@ -1229,21 +1322,30 @@ k_lm_fit(LMArgs a) {
                     }
                 }
                 __syncthreads();
-                int bad_any = 0;
-                for (int s = 0; s <= np; s++) {
-                    if (threadIdx.x == 0) {
-                        for (int i = 0; i < np; i++) sh.xeval[i] = sh.st.x[i];
-                        if (s > 0)
-                            sh.xeval[s - 1] = sh.st.x[s - 1] + hs[s - 1];
-                        sh.status = 0;
+                // the base mixture and the np perturbed ones, one composed
+                // gaussian per thread: (np + 1) * ngauss independent jobs
+                // (built one mixture at a time by ngauss threads this was
+                // 3 (np + 1) barriers with most of the CTA idle)
+                {
+                    const int njobs = (np + 1) * a.ngauss;
+                    for (int t = threadIdx.x; t < njobs; t += T) {
+                        const int s = t / a.ngauss, k = t - s * a.ngauss;
+                        double xl[LM_MAXP];
+#pragma unroll 1
+                        for (int i = 0; i < np; i++) {
+                            double xi = sh.xcur[i];
+                            if (i == s - 1)
+                                xi = b_i2e(a.lm, i, sh.st.x[i] + hs[i]);
+                            xl[i] = xi;
+                        }
+                        build_component(a, &sh, xl, k,
+                                        s == 0 ? mix : nullptr, area,
+                                        fdm + (size_t)s * a.ngauss * FDREC);
                     }
-                    __syncthreads();
-                    build_mixture(a, &sh, sh.xeval, s == 0 ? mix : nullptr,
-                                  area, fdm + (size_t)s * a.ngauss * FDREC);
-                    __syncthreads();
-                    bad_any |= sh.status;
-                    __syncthreads();
                 }
+                __syncthreads();
+                const int bad_any = sh.status;
+                __syncthreads();
                 if (!bad_any) build_tile_masks(a, &sh, mix, tmask, 1.0e-6);
                 __syncthreads();
                 constexpr int FDN = FD_NSUM_(FDP);
@@ -1279,10 +1381,12 @@ k_lm_fit(LMArgs a) {
                 }
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                sh.action = sh.st.action;
-                for (int i = 0; i < a.np; i++) sh.xeval[i] = sh.st.xtrial[i];
+            if (threadIdx.x < a.np) {
+                const int i = threadIdx.x;
+                sh.xeval[i] = b_i2e(a.lm, i, sh.st.xtrial[i]);
+                sh.xcur[i] = b_i2e(a.lm, i, sh.st.x[i]);
             }
+            if (threadIdx.x == 0) sh.action = sh.st.action;
             __syncthreads();
             PROF_T(pt_solve);
         }
@@ -1399,7 +1503,11 @@ k_lm_fit_multi(LMArgs a) {
                     a.lm.ftol, a.lm.xtol);
             sh.action = sh.st.action;
             sh.spec = 1;
-            for (int i = 0; i < np; i++) sh.xeval[i] = sh.st.xtrial[i];
+            for (int i = 0; i < np; i++) {
+                const double xe = sh.st.xtrial[i];
+                sh.xeval[i] = sh.xcur[i] = xe;
+                sh.st.x[i] = sh.st.xtrial[i] = b_e2i(a.lm, i, xe);
+            }
             sh.cur_ssq = sh.cur_rfirst2 = sh.cur_num = sh.cur_den = 0.0;
         }
         __syncthreads();
@@ -1421,7 +1529,7 @@ k_lm_fit_multi(LMArgs a) {
             const int spec = sh.spec;
             __syncthreads();
             const bool want_f = (action == LM_ACT_EVAL_F);
-            const double *xp = want_f ? sh.xeval : sh.st.x;
+            const double *xp = want_f ? sh.xeval : sh.xcur;
             const bool nonzero = multi_pars_nonzero(xp, nband);
             const bool fused = want_f && spec && nonzero
                 && !(sh.st.prered <= sh.st.ftol);
@@ -1536,11 +1644,11 @@ k_lm_fit_multi(LMArgs a) {
                     feed_jacobian(a, &sh, mu.macc, jstatus, 1, hs);
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    sh.action = sh.st.action;
-                    for (int i = 0; i < np; i++)
-                        sh.xeval[i] = sh.st.xtrial[i];
+                if (lane < np) {
+                    sh.xeval[lane] = b_i2e(a.lm, lane, sh.st.xtrial[lane]);
+                    sh.xcur[lane] = b_i2e(a.lm, lane, sh.st.x[lane]);
                 }
+                if (lane == 0) sh.action = sh.st.action;
             }
             __syncthreads();
         }
@@ -1648,6 +1756,59 @@ __global__ void k_iota_zero(int n, int32_t *start, int32_t *band) {
 }
 #endif
 
+// Balance of the static tile assignment.  In every round of a pass warp w
+// takes chunk slot (w + rot * round) mod nwarps (C consecutive tiles).  With
+// rot = 0 a warp can sit on the same tile columns in every round - on a 64x64
+// stamp (8 tiles per row, 8 warps) four warps would always get the centre
+// columns, where every gaussian of the mixture is in reach, and the others
+// the edges: 1.5x the mean work on the slowest warp, the rest waiting at the
+// reduction barrier.  The stride is chosen per (stamp size, warps, C) on a
+// proxy cost: gaussians of geometrically spaced radii centred on the stamp,
+// a tile costing one unit per gaussian whose 5-sigma box reaches it.
+static int pick_rotation(int nrow, int ncol, int nwarps, int C) {
+    struct Key { int nrow, ncol, nwarps, C, rot; };
+    static thread_local Key cache[8];
+    static thread_local int ncache = 0;
+    for (int i = 0; i < ncache; i++)
+        if (cache[i].nrow == nrow && cache[i].ncol == ncol
+            && cache[i].nwarps == nwarps && cache[i].C == C)
+            return cache[i].rot;
+    const int tr = (nrow + 3) / 4, tc = (ncol + 7) / 8, ntile = tr * tc;
+    std::vector<float> cost(ntile, 0.0f);
+    const float cr = 0.5f * (nrow - 1), cc = 0.5f * (ncol - 1);
+    for (int k = 0; k < 14; k++) {
+        const float rad = 0.5f * powf(2.0f, 0.5f * k);
+        for (int i = 0; i < tr; i++)
+            for (int j = 0; j < tc; j++) {
+                float r0 = 4.0f * i, r1 = fminf(r0 + 3, nrow - 1.0f);
+                float c0 = 8.0f * j, c1 = fminf(c0 + 7, ncol - 1.0f);
+                float dr = fmaxf(0.0f, fmaxf(r0 - cr, cr - r1));
+                float dc = fmaxf(0.0f, fmaxf(c0 - cc, cc - c1));
+                if (dr <= rad && dc <= rad) cost[i * tc + j] += 1.0f;
+            }
+    }
+    int best = 0;
+    float best_max = 1e30f;
+    for (int rot = 0; rot < nwarps; rot++) {
+        float tot[32] = {0};
+        int rnd = 0;
+        for (int base = 0; base < ntile; base += nwarps * C, rnd++)
+            for (int w = 0; w < nwarps; w++) {
+                int ws = (w + rot * rnd) % nwarps;
+                for (int c = 0; c < C; c++) {
+                    int t = base + ws * C + c;
+                    if (t < ntile) tot[w] += cost[t];
+                }
+            }
+        float mx = 0.0f;
+        for (int w = 0; w < nwarps; w++) mx = fmaxf(mx, tot[w]);
+        if (mx < best_max - 1e-3f) { best_max = mx; best = rot; }
+    }
+    Key k = {nrow, ncol, nwarps, C, best};
+    cache[ncache < 8 ? ncache++ : 7] = k;
+    return best;
+}
+
 template <typename K>
 static int config_and_launch(K kernel, const LMArgs &a_in, int threads,
                              size_t smem, cudaStream_t stream) {
@@ -1665,6 +1826,10 @@ static int config_and_launch(K kernel, const LMArgs &a_in, int threads,
     int blocks = sm_count() * per_sm;
     if (blocks > a0.n) blocks = a0.n;
     LMArgs a = a_in;
+    // CV = 3 tiles per warp and round in the value pass, CD = CF = 2 in the
+    // derivative / forward-difference passes (template arguments below)
+    a.rot_v = pick_rotation(a.nrow, a.ncol, threads / 32, 3);
+    a.rot_d = pick_rotation(a.nrow, a.ncol, threads / 32, 2);
     int slot = 0;
     int rcc = counter_begin(&a.counter, &slot, stream);
     if (rcc) return rcc;
@@ -1906,9 +2071,25 @@ int ngx_lm_fit_coellip(int n, int ngauss, const double *images,
         * ((size_t)a.ngauss * REC + (size_t)nfd * a.ngauss * FDREC
            + 16 + 2 * (size_t)a.nq + nrow + ncol + 48 * nwarps + LM_MAXP
            + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
+    // the per-thread J^T J sums are sized for the fit's own parameter
+    // count (45 for 8 parameters ... 120 for 14): two gaussians run without
+    // the register spills of the 14-parameter instantiation
+    cudaStream_t st = as_stream(stream);
+    if (a.np <= 8)
+        return config_and_launch(
+            k_lm_fit<1, 3, 2, 2, true, 256, false, 8, ngx_lm_result_wide>,
+            a, threads, smem, st);
+    if (a.np <= 10)
+        return config_and_launch(
+            k_lm_fit<1, 3, 2, 2, true, 256, false, 10, ngx_lm_result_wide>,
+            a, threads, smem, st);
+    if (a.np <= 12)
+        return config_and_launch(
+            k_lm_fit<1, 3, 2, 2, true, 256, false, 12, ngx_lm_result_wide>,
+            a, threads, smem, st);
     return config_and_launch(
         k_lm_fit<1, 3, 2, 2, true, 256, false, LM_MAXP, ngx_lm_result_wide>,
-        a, threads, smem, as_stream(stream));
+        a, threads, smem, st);
 }
 #endif
 

@@ -74,7 +74,8 @@ def fit_batch(model, images, weights, jacobians, psf_pars, guesses,
                        prior=_prior_record(prior), maxfev=fp["maxfev"],
                        ftol=fp["ftol"], xtol=fp["xtol"],
                        analytic_jacobian=analytic_jacobian,
-                       ignore_zero_weight=ignore_zero_weight)
+                       ignore_zero_weight=ignore_zero_weight,
+                       bounds=getattr(prior, "bounds", None))
     if noise_images is not None:
         from . import noise_cov
         npars = get_model_npars(model)
@@ -111,6 +112,9 @@ def fit_batch_multi(model, stamp_start, stamp_band, nband, images, weights,
     if fit_pars is not None:
         fp.update(fit_pars)
     pr = _prior_record(prior)
+    if getattr(prior, "bounds", None) is not None:
+        raise NotImplementedError(
+            "bounded fits of objects with several stamps")
     if pr is not None and getattr(prior, "nband", nband) != nband:
         raise ValueError("prior has %d flux priors, data has %d bands"
                          % (prior.nband, nband))
@@ -616,6 +620,8 @@ def fit_batch_coellip(ngauss, images, weights, jacobians, guesses,
     fp = dict(DEFAULT_LM_PARS)
     if fit_pars is not None:
         fp.update(fit_pars)
+    if getattr(prior, "bounds", None) is not None:
+        raise NotImplementedError("bounded coelliptical fits")
     return _lib.lm_fit_coellip(ngauss, images, weights, jacobians, psf_pars,
                                guesses, prior=_prior_record(prior),
                                maxfev=fp["maxfev"], ftol=fp["ftol"],

@@ -361,12 +361,22 @@ class PriorSimpleSep(object):
             self.nband = 1
             F_prior = [F_prior]
         self.F_priors = F_prior
-        self.bounds = None
-        for p in [self.T_prior] + self.F_priors:
+        self.set_bounds()
+
+    def set_bounds(self):
+        """prior.bounds of the reference (joint_prior.py:37-61): (None, None)
+        for the centre and shape, then the (min, max) of every 1-d member
+        that has bounds; None when no member has any.  A fit with bounds
+        runs leastsqbound's transformed parameters (ngx_lm_pars.nbounds)."""
+        bounds = [(None, None)] * 4
+        some = False
+        for p in [self.T_prior] + self._middle_priors() + self.F_priors:
             if p.has_bounds():
-                raise NotImplementedError(
-                    "bounded fits are not in scope (SURVEY.md section 7: the "
-                    "reference's bounded covariance is unpinned)")
+                some = True
+                bounds.append((p.bounds[0], p.bounds[1]))
+            else:
+                bounds.append((None, None))
+        self.bounds = bounds if some else None
 
     def get_lnprob_scalar(self, pars):
         lnp = self.cen_prior.get_lnprob_scalar(pars[0], pars[1])
@@ -435,8 +445,6 @@ class PriorBDFSep(PriorSimpleSep):
     def __init__(self, cen_prior, g_prior, T_prior, fracdev_prior, F_prior):
         self.fracdev_prior = fracdev_prior
         super().__init__(cen_prior, g_prior, T_prior, F_prior)
-        if fracdev_prior.has_bounds():
-            raise NotImplementedError("bounded fits are not in scope")
 
     def get_lnprob_scalar(self, pars):
         lnp = self.cen_prior.get_lnprob_scalar(pars[0], pars[1])
@@ -474,8 +482,6 @@ class PriorBDSep(PriorSimpleSep):
         self.logTratio_prior = logTratio_prior
         self.fracdev_prior = fracdev_prior
         super().__init__(cen_prior, g_prior, T_prior, F_prior)
-        if logTratio_prior.has_bounds() or fracdev_prior.has_bounds():
-            raise NotImplementedError("bounded fits are not in scope")
 
     def get_lnprob_scalar(self, pars):
         lnp = self.cen_prior.get_lnprob_scalar(pars[0], pars[1])
@@ -519,6 +525,20 @@ class PriorCoellipSame(PriorSimpleSep):
         super().__init__(cen_prior, g_prior, T_prior, F_prior)
         if self.nband != 1:
             raise ValueError("coellip only supports one band")
+
+    def set_bounds(self):
+        """(joint_prior.py:887-911) the T and flux bounds repeated for every
+        gaussian; bounded coelliptical fits are not run on the device"""
+        n = getattr(self, "ngauss", 1)
+        bounds = [(None, None)] * 4
+        some = False
+        for p in [self.T_prior] * n + [self.F_priors[0]] * n:
+            if p.has_bounds():
+                some = True
+                bounds.append((p.bounds[0], p.bounds[1]))
+            else:
+                bounds.append((None, None))
+        self.bounds = bounds if some else None
 
     def _check(self, pars):
         if len(pars) != self.npars:

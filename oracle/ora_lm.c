@@ -435,7 +435,7 @@ static int cb_fdiff(void *ctx, int m, int n, const double *x, double *fvec) {
 static int cb_jac(void *ctx, int m, int n, const double *x, double *fjac) {
     fitctx *c = (fitctx *)ctx;
     if (c->bounds) {
-        double xe[ORA_MAXP];
+        double xe[ORA_MAXP] = {0};
         for (int i = 0; i < n; i++) xe[i] = b_i2e(c->bounds, i, x[i]);
         ctx_calc_jacobian(c, xe, fjac);
         for (int j = 0; j < n; j++) {

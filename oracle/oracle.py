@@ -295,9 +295,29 @@ def make_prior(kind, model="exp"):
 
 
 # ------------------------------------------------------------------ LM
+class Bounds(C.Structure):
+    """prior.bounds of the reference (joint_prior.py:37-61)"""
+    _fields_ = [("present", C.c_int32), ("type", C.c_int32 * 14),
+                ("pad", C.c_int32),
+                ("lo", C.c_double * 14), ("hi", C.c_double * 14)]
+
+
+def make_bounds(bounds):
+    b = Bounds()
+    b.present = 0
+    if bounds is None:
+        return b
+    b.present = 1
+    for i, (lo, hi) in enumerate(bounds):
+        b.type[i] = (1 if lo is not None else 0) + (2 if hi is not None else 0)
+        b.lo[i] = 0.0 if lo is None else lo
+        b.hi[i] = 0.0 if hi is None else hi
+    return b
+
+
 def lm_fit(model, image, weight, jac, psf_pars, guess, prior=None,
            maxfev=4000, ftol=1.0e-5, xtol=1.0e-5, analytic_jacobian=True,
-           ignore_zero_weight=True):
+           ignore_zero_weight=True, bounds=None):
     image, weight, jac, guess = _f8(image), _f8(weight), _f8(jac), _f8(guess)
     if psf_pars is None:
         npsf = 0
@@ -310,10 +330,11 @@ def lm_fit(model, image, weight, jac, psf_pars, guess, prior=None,
     if model == "coellip":
         pr.ncoellip = (guess.size - 4) // 2
     res = np.zeros(1, dtype=LM_RESULT_DTYPE)
-    st = lib().ora_lm_fit(
+    bnd = make_bounds(bounds)
+    st = lib().ora_lm_fit_bounded(
         C.c_int(MODELS[model]), _p(image), _p(weight),
         C.c_int(image.shape[0]), C.c_int(image.shape[1]), _p(jac), psf_ptr,
-        C.c_int(npsf), _p(guess), C.byref(pr), C.c_int(maxfev),
+        C.c_int(npsf), _p(guess), C.byref(pr), C.byref(bnd), C.c_int(maxfev),
         C.c_double(ftol), C.c_double(xtol), C.c_int(int(analytic_jacobian)),
         C.c_int(int(ignore_zero_weight)), _p(res))
     assert st == 0, st
