@@ -402,6 +402,50 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e32_s = float(t.item())
     assert np.array_equal(r_e2e32["pars"], res["pars"], equal_nan=True)
+    # the compact survey format: float32 pixels + one weight per stamp (the
+    # bench stamps have a uniform weight map and no masked pixels)
+    h_ws = pinned(b["weights"][:, 0, 0].copy())
+    assert np.array_equal(b["weights"],
+                          np.broadcast_to(h_ws.numpy()[:, None, None],
+                                          b["weights"].shape))
+
+    def step_e2ec():
+        return _lib.lm_fit_compact("exp", h_images32.numpy(), h_ws.numpy(),
+                                   h_jac.numpy(), h_psf.numpy(),
+                                   h_guess.numpy(), out=e2e_out)
+
+    for _ in range(2):
+        step_e2ec()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r_e2ec = step_e2ec()
+    torch.cuda.synchronize()
+    e2ec_s = time.perf_counter() - t0
+    t = torch.tensor([e2ec_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2ec_s = float(t.item())
+    assert np.array_equal(r_e2ec["pars"], res["pars"], equal_nan=True)
+    # pageable float64 arrays (what a caller who did nothing special has)
+    pg_images, pg_weights = b["images"].copy(), b["weights"].copy()
+
+    def step_e2ep():
+        return _lib.lm_fit("exp", pg_images, pg_weights, b["jac"], b["psf"],
+                           b["guess"])
+
+    step_e2ep()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(2, args.steps // 3)):
+        step_e2ep()
+    torch.cuda.synchronize()
+    e2ep_s = (time.perf_counter() - t0) / max(2, args.steps // 3)
+    t = torch.tensor([e2ep_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2ep_s = float(t.item())
+    del pg_images, pg_weights
     h2d = int(h_images.numel() * 8 * 2 + h_jac.numel() * 8
               + h_psf.numel() * 8 + h_guess.numel() * 8)
     d2h = int(nobj * _lib.LM_RESULT_DTYPE.itemsize)
@@ -547,6 +591,18 @@ def main():
             "d2h_bytes_per_step": d2h,
             "api": "ngx_lm_fit_host_f32: the same stamps held as float32 on "
                    "the host (bit-identical results), widened on the device"},
+        "e2e_compact": {
+            "value": world * nobj * args.steps / e2ec_s, "unit": "fits/s",
+            "h2d_bytes_per_step": int(h2d - h_images.numel() * 12
+                                      + nobj * 8),
+            "d2h_bytes_per_step": d2h,
+            "api": "ngx_lm_fit_host_compact (fit_batch with float32 pixels "
+                   "and one weight per stamp): 4 bytes per pixel over PCIe, "
+                   "bit-identical results"},
+        "e2e_pageable": {
+            "value": world * nobj / e2ep_s, "unit": "fits/s",
+            "api": "the float64 call on ordinary (pageable) numpy arrays; "
+                   "ngmix_b200.pinned_empty / pinned() give the pinned rate"},
         "gpu_launches": args.steps,   # k_lm_fit launches in the timed region
         "roofline": {
             "bound": "fp64", "achieved": achieved / 1e9,

@@ -31,6 +31,7 @@
 #ifndef NGX_H
 #define NGX_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -108,6 +109,14 @@ const char *ngx_last_error(void);
 int ngx_init(int device);
 /* sm count, shared memory per block, device name (name may be NULL) */
 int ngx_device_info(int *sm_count, int *smem_optin, char *name, int name_len);
+
+/* page-locked host memory for the *_host entry points (their chunked H2D
+ * copies overlap the fits only from pinned memory): allocate pinned arrays,
+ * or pin arrays the caller already owns for the duration of the calls */
+int ngx_host_alloc(size_t bytes, void **out);
+int ngx_host_free(void *p);
+int ngx_host_register(void *p, size_t bytes);
+int ngx_host_unregister(void *p);
 
 /* ------------------------------------------------------------------ */
 /* mixtures: replace gmix_fill_<model> (gmix_nb.py:307-558), gmix_set_norms
@@ -454,6 +463,23 @@ int ngx_lm_fit_host_f32(int n, int model, const float *images,
                         const double *guess, const ngx_prior *prior,
                         const ngx_lm_pars *lm_pars, int ignore_zero_weight,
                         ngx_lm_result *res);
+/* the compact survey format: float32 pixels, ONE weight per stamp and an
+ * optional good-pixel mask of one bit per pixel (bit k of a stamp = pixel k
+ * in row-major order, most significant bit of each byte first, as
+ * numpy.packbits writes it; NULL = every pixel good).  It stands for the
+ * Observation the reference would build from image.astype(f8) and
+ * weight = where(mask, weight_scalar, 0) (observation.py:114-126,
+ * pixels/pixels.py:6-52: ierr = sqrt(weight), zero-weight pixels dropped);
+ * 4.1 instead of 16 bytes per pixel cross PCIe and the results are
+ * bit-identical to ngx_lm_fit_host on the expanded arrays. */
+int ngx_lm_fit_host_compact(int n, int model, const float *images,
+                            const double *weight_scalar,
+                            const unsigned char *maskbits,
+                            const ngx_jacobian *jac, int nrow, int ncol,
+                            const double *psf_pars, int npsf,
+                            const double *guess, const ngx_prior *prior,
+                            const ngx_lm_pars *lm_pars,
+                            int ignore_zero_weight, ngx_lm_result *res);
 int ngx_em_host(int n, int variant, const double *images,
                 const double *weights, const ngx_jacobian *jac, int nrow,
                 int ncol, const double *guess, int ngauss,

@@ -30,3 +30,4 @@ from .admom import AdmomFitter, run_admom, admom_batch  # noqa: F401
 from . import joint_prior, moments, gaussmom, gaussap  # noqa: F401
 from .gaussmom import GaussMom, gaussmom_batch  # noqa: F401
 from .batch import ObservationBatch  # noqa: F401
+from ._lib import pinned, pinned_empty, pinned_copy  # noqa: F401

@@ -132,7 +132,9 @@ SYMBOLS = [
     "ngx_lm_fit_multi", "ngx_lm_fit_multi_host",
     "ngx_template_flux", "ngx_template_flux_host",
     "ngx_noise_b", "ngx_noise_b_host", "ngx_noise_cov_host",
-    "ngx_lm_fit_host_f32",
+    "ngx_lm_fit_host_f32", "ngx_lm_fit_host_compact",
+    "ngx_host_alloc", "ngx_host_free", "ngx_host_register",
+    "ngx_host_unregister",
     "ngx_lm_fit_multi_wide", "ngx_lm_fit_multi_wide_host",
     "ngx_lm_fit_coellip", "ngx_lm_fit_coellip_host",
 ]
@@ -465,6 +467,62 @@ def lm_fit(model, images, weights, jac, psf_pars, guess, prior=None,
     return res
 
 
+def lm_fit_compact(model, images, weight_scalar, jac, psf_pars, guess,
+                   mask=None, prior=None, maxfev=4000, ftol=1.0e-5,
+                   xtol=1.0e-5, analytic_jacobian=True, out=None, bounds=None):
+    """
+    batched Fitter.go from the compact survey format: images [n,H,W] float32,
+    weight_scalar [n] (one weight per stamp), mask [n,H,W] bool (True = use
+    the pixel; None = all) or already packed bits [n, ceil(H*W/8)] uint8.
+    Equivalent to lm_fit(images.astype(f8), where(mask, weight_scalar, 0)).
+    """
+    init()
+    images = np.ascontiguousarray(images, dtype=np.float32)
+    if images.ndim == 2:
+        images = images[None]
+    n, H, W = images.shape
+    ws = np.ascontiguousarray(np.broadcast_to(
+        np.asarray(weight_scalar, dtype="f8"), (n,)))
+    bits = None
+    if mask is not None:
+        mask = np.asarray(mask)
+        if mask.dtype == np.uint8 and mask.ndim == 2:
+            bits = np.ascontiguousarray(mask)
+        else:
+            if mask.shape != images.shape:
+                raise ValueError("mask %s and images %s differ in shape"
+                                 % (mask.shape, images.shape))
+            bits = np.packbits(mask.reshape(n, -1).astype(bool), axis=1)
+        if bits.shape != (n, (H * W + 7) // 8):
+            raise ValueError("packed mask has shape %s" % (bits.shape,))
+    jac = as_jac(jac, n)
+    guess = np.atleast_2d(_f8(guess))
+    if guess.shape != (n, MODEL_NPARS[model]):
+        raise ValueError("guess has shape %s, expected %s for model %s"
+                         % (guess.shape, (n, MODEL_NPARS[model]), model))
+    if psf_pars is None:
+        npsf = 0
+    else:
+        psf_pars = _f8(psf_pars)
+        npsf = psf_pars.shape[1] if psf_pars.ndim == 3 \
+            else psf_pars.size // max(6 * n, 1)
+        psf_pars = psf_pars.reshape(n, npsf, 6)
+    pr = prior if prior is not None else Prior()
+    lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)
+    lmp.set_bounds(bounds)
+    if out is None:
+        res = np.empty(n, dtype=LM_RESULT_DTYPE)
+    else:
+        res = out
+        assert res.dtype == LM_RESULT_DTYPE and res.shape == (n,) \
+            and res.flags.c_contiguous
+    check(lib().ngx_lm_fit_host_compact(
+        C.c_int(n), C.c_int(MODELS[model]), _p(images), _p(ws), _p(bits),
+        _p(jac), C.c_int(H), C.c_int(W), _p(psf_pars), C.c_int(npsf),
+        _p(guess), C.byref(pr), C.byref(lmp), C.c_int(1), _p(res)))
+    return res
+
+
 def lm_fit_coellip(ngauss, images, weights, jac, psf_pars, guess, prior=None,
                    maxfev=4000, ftol=1.0e-5, xtol=1.0e-5,
                    ignore_zero_weight=True):
@@ -780,3 +838,82 @@ def render_device(n, ngauss, d_gmix, d_jac, nrow, ncol, fast_exp, d_images,
         C.c_int(n), C.c_int(ngauss), C.c_void_p(d_gmix), C.c_void_p(d_jac),
         C.c_int(nrow), C.c_int(ncol), C.c_int(int(fast_exp)),
         C.c_void_p(d_images), C.c_void_p(d_status), C.c_void_p(stream)))
+
+
+# ------------------------------------------------------------ pinned memory
+class _PinnedBlock(object):
+    """owner of one cudaHostAlloc block; freed when the last array viewing
+    it is collected"""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        check(lib().ngx_host_alloc(C.c_size_t(nbytes), C.byref(self.ptr)))
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().ngx_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype="f8"):
+    """numpy array in page-locked host memory (cudaHostAlloc): the input
+    format the host-buffer calls (fit_batch, em_batch, ...) stream from at
+    full PCIe rate, with the copy of one chunk overlapping the fit of the
+    previous one"""
+    init()
+    dtype = np.dtype(dtype)
+    shape = tuple(np.atleast_1d(shape).astype(int))
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    block = _PinnedBlock(max(nbytes, 1))
+    buf = (C.c_char * max(nbytes, 1)).from_address(block.ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape)))
+    arr = arr.reshape(shape)
+    _pinned_owners[id(buf)] = block
+    import weakref
+    weakref.finalize(buf, _pinned_owners.pop, id(buf), None)
+    return arr
+
+
+_pinned_owners = {}
+
+
+def pinned_copy(a):
+    """a copy of `a` in page-locked host memory"""
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
+class pinned(object):
+    """context manager that page-locks arrays the caller already owns
+    (cudaHostRegister) for the duration of the block:
+
+        with ngmix_b200.pinned(images, weights):
+            recs = ngmix_b200.fit_batch(...)
+
+    Registration costs about as much as one pageable copy, so it pays when
+    the arrays are used for more than one call."""
+
+    def __init__(self, *arrays):
+        self.arrays = [a for a in arrays if a is not None]
+        self.done = []
+
+    def __enter__(self):
+        init()
+        for a in self.arrays:
+            if not a.flags.c_contiguous:
+                raise ValueError("only contiguous arrays can be pinned")
+            check(lib().ngx_host_register(C.c_void_p(a.ctypes.data),
+                                          C.c_size_t(a.nbytes)))
+            self.done.append(a)
+        return self
+
+    def __exit__(self, *exc):
+        for a in self.done:
+            lib().ngx_host_unregister(C.c_void_p(a.ctypes.data))
+        self.done = []
+        return False

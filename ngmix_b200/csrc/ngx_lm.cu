@@ -1748,6 +1748,30 @@ __global__ void k_widen(const float *__restrict__ in, double *__restrict__ out,
 #endif
 
 #ifndef NGX_LM_WIDE_TU
+// compact host format -> the engine's planes: float32 pixel values widened,
+// weight = the stamp's scalar weight where the stamp's mask bit is set (bit
+// k of the stamp, most significant bit of each byte first, as numpy.packbits
+// writes it; no mask = all pixels good), 0 elsewhere.  One thread per pixel
+// pair; 4.1 bytes per pixel came over PCIe instead of 16.
+__global__ void k_expand_compact(const float *__restrict__ im32,
+                                 const double *__restrict__ wscalar,
+                                 const unsigned char *__restrict__ mask,
+                                 double *__restrict__ im,
+                                 double *__restrict__ wt, int n, int ntot,
+                                 int nmb) {
+    const size_t total = (size_t)n * ntot;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int s = (int)(i / ntot), k = (int)(i - (size_t)s * ntot);
+        bool good = true;
+        if (mask) good = (mask[(size_t)s * nmb + (k >> 3)] >> (7 - (k & 7))) & 1;
+        im[i] = (double)im32[i];
+        wt[i] = good ? wscalar[s] : 0.0;
+    }
+}
+#endif
+
+#ifndef NGX_LM_WIDE_TU
 // stamp_start = 0..n and stamp_band = 0 for n one-stamp objects
 __global__ void k_iota_zero(int n, int32_t *start, int32_t *band) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2235,6 +2259,7 @@ int ngx_lm_fit_multi_wide_host(int nobj, int model,
 // what bounds the call; widened to double on the device, exactly)
 static int lm_fit_host_impl(int n, int model, const void *images_v,
                             const void *weights_v, int f32,
+                            const unsigned char *maskbits,
                             const ngx_jacobian *jac, int nrow, int ncol,
                             const double *psf_pars, int npsf,
                             const double *guess, const ngx_prior *prior,
@@ -2246,6 +2271,10 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
     const double *weights = (const double *)weights_v;
     const float *images32 = (const float *)images_v;
     const float *weights32 = (const float *)weights_v;
+    // f32 == 2: compact format - float32 pixels, one double weight per stamp
+    // (weights_v), optional packed mask bits
+    const bool compact = f32 == 2;
+    const double *wscalar = (const double *)weights_v;
     int np = model_npars(model);
     NGX_REQUIRE(np > 0);
     // chunked, double-buffered pipeline: H2D of chunk i+1 overlaps the fit
@@ -2269,6 +2298,10 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
     static thread_local float *d_im32[2] = {nullptr, nullptr};
     static thread_local float *d_wt32[2] = {nullptr, nullptr};
     static thread_local size_t cap_pix32 = 0;
+    static thread_local double *d_ws[2] = {nullptr, nullptr};
+    static thread_local unsigned char *d_mask[2] = {nullptr, nullptr};
+    static thread_local size_t cap_ws = 0, cap_mask = 0;
+    const int nmb = (int)((ntot + 7) / 8);
     static thread_local ngx_lm_result *h_stage = nullptr;   // pinned
     static thread_local size_t cap_stage = 0;
     // streams[1] copies in; the fits of even / odd chunks run on streams[0] /
@@ -2309,6 +2342,16 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
         }
         cap_pix32 = need_pix;
     }
+    if (compact && ((size_t)chunk > cap_ws
+                    || (size_t)chunk * nmb > cap_mask)) {
+        NGX_CUDA(cudaDeviceSynchronize());
+        for (int b = 0; b < 2; b++) {
+            cudaFree(d_ws[b]); cudaFree(d_mask[b]);
+            NGX_CUDA(cudaMalloc((void **)&d_ws[b], chunk * sizeof(double)));
+            NGX_CUDA(cudaMalloc((void **)&d_mask[b], (size_t)chunk * nmb));
+        }
+        cap_ws = chunk; cap_mask = (size_t)chunk * nmb;
+    }
     // results: device -> pinned memory asynchronously.  If the caller's
     // array is itself pinned it is the target, else a pinned staging buffer
     // is copied out by the host while the next chunk runs.
@@ -2337,7 +2380,19 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
         // results were copied out (both on this buffer's compute stream)
         cudaStream_t ks = streams[b ? 2 : 0];
         NGX_CUDA(cudaStreamWaitEvent(streams[1], done[b], 0));
-        if (f32) {
+        if (compact) {
+            NGX_CUDA(cudaMemcpyAsync(d_im32[b], images32 + lo * ntot,
+                                     cn * ntot * sizeof(float),
+                                     cudaMemcpyHostToDevice, streams[1]));
+            NGX_CUDA(cudaMemcpyAsync(d_ws[b], wscalar + lo,
+                                     cn * sizeof(double),
+                                     cudaMemcpyHostToDevice, streams[1]));
+            if (maskbits)
+                NGX_CUDA(cudaMemcpyAsync(d_mask[b],
+                                         maskbits + (size_t)lo * nmb,
+                                         (size_t)cn * nmb,
+                                         cudaMemcpyHostToDevice, streams[1]));
+        } else if (f32) {
             NGX_CUDA(cudaMemcpyAsync(d_im32[b], images32 + lo * ntot,
                                      cn * ntot * sizeof(float),
                                      cudaMemcpyHostToDevice, streams[1]));
@@ -2365,7 +2420,15 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
                                  cudaMemcpyHostToDevice, streams[1]));
         NGX_CUDA(cudaEventRecord(up[b], streams[1]));
         NGX_CUDA(cudaStreamWaitEvent(ks, up[b], 0));
-        if (f32) {
+        if (compact) {
+            const size_t cnt = (size_t)cn * ntot;
+            int blocks = (int)((cnt + 255) / 256);
+            if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+            k_expand_compact<<<blocks, 256, 0, ks>>>(
+                d_im32[b], d_ws[b], maskbits ? d_mask[b] : nullptr, d_im[b],
+                d_wt[b], cn, (int)ntot, nmb);
+            NGX_LAUNCH_CHECK();
+        } else if (f32) {
             const size_t cnt = (size_t)cn * ntot;
             const int blocks = (int)((cnt / 4 + 255) / 256) + 1;
             k_widen<<<blocks, 256, 0, ks>>>(d_im32[b], d_im[b], cnt);
@@ -2410,8 +2473,8 @@ int ngx_lm_fit_host(int n, int model, const double *images,
                     const double *guess, const ngx_prior *prior,
                     const ngx_lm_pars *lm_pars, int ignore_zero_weight,
                     ngx_lm_result *res) {
-    return lm_fit_host_impl(n, model, images, weights, 0, jac, nrow, ncol,
-                            psf_pars, npsf, guess, prior, lm_pars,
+    return lm_fit_host_impl(n, model, images, weights, 0, nullptr, jac, nrow,
+                            ncol, psf_pars, npsf, guess, prior, lm_pars,
                             ignore_zero_weight, res);
 }
 #endif
@@ -2423,8 +2486,23 @@ int ngx_lm_fit_host_f32(int n, int model, const float *images,
                         const double *guess, const ngx_prior *prior,
                         const ngx_lm_pars *lm_pars, int ignore_zero_weight,
                         ngx_lm_result *res) {
-    return lm_fit_host_impl(n, model, images, weights, 1, jac, nrow, ncol,
-                            psf_pars, npsf, guess, prior, lm_pars,
+    return lm_fit_host_impl(n, model, images, weights, 1, nullptr, jac, nrow,
+                            ncol, psf_pars, npsf, guess, prior, lm_pars,
+                            ignore_zero_weight, res);
+}
+#endif
+
+#ifndef NGX_LM_WIDE_TU
+int ngx_lm_fit_host_compact(int n, int model, const float *images,
+                            const double *weight_scalar,
+                            const unsigned char *maskbits,
+                            const ngx_jacobian *jac, int nrow, int ncol,
+                            const double *psf_pars, int npsf,
+                            const double *guess, const ngx_prior *prior,
+                            const ngx_lm_pars *lm_pars,
+                            int ignore_zero_weight, ngx_lm_result *res) {
+    return lm_fit_host_impl(n, model, images, weight_scalar, 2, maskbits, jac,
+                            nrow, ncol, psf_pars, npsf, guess, prior, lm_pars,
                             ignore_zero_weight, res);
 }
 #endif

@@ -784,6 +784,30 @@ int ngx_device_info(int *sms, int *smem_optin, char *name, int name_len) {
     return NGX_OK;
 }
 
+// page-locked host memory for the host-buffer entry points: their chunked
+// H2D copies overlap the fits only from pinned memory
+int ngx_host_alloc(size_t bytes, void **out) {
+    NGX_REQUIRE(out);
+    *out = nullptr;
+    if (bytes == 0) return NGX_OK;
+    NGX_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return NGX_OK;
+}
+int ngx_host_free(void *p) {
+    if (p) NGX_CUDA(cudaFreeHost(p));
+    return NGX_OK;
+}
+int ngx_host_register(void *p, size_t bytes) {
+    NGX_REQUIRE(p || bytes == 0);
+    if (bytes == 0) return NGX_OK;
+    NGX_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return NGX_OK;
+}
+int ngx_host_unregister(void *p) {
+    if (p) NGX_CUDA(cudaHostUnregister(p));
+    return NGX_OK;
+}
+
 int ngx_gmix_fill(int n, int model, int ngauss, const double *pars, int npars,
                   ngx_gauss *gmix, int32_t *status, void *stream) {
     NGX_REQUIRE(n >= 0 && pars && gmix);

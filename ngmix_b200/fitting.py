@@ -37,7 +37,7 @@ def _prior_record(prior):
 
 def fit_batch(model, images, weights, jacobians, psf_pars, guesses,
               prior=None, fit_pars=None, analytic_jacobian=True,
-              ignore_zero_weight=True, noise_images=None):
+              ignore_zero_weight=True, noise_images=None, mask=None):
     """
     Levenberg-Marquardt fits of n stamps in one launch.
 
@@ -51,6 +51,12 @@ def fit_batch(model, images, weights, jacobians, psf_pars, guesses,
     psf_pars: [n, npsf, 6] array or None
         full gaussian parameters of each stamp's psf mixture
     guesses: [n, npars] array
+    mask: [n, H, W] bool array, optional
+        True = use the pixel.  With float32 `images` and ONE weight per stamp
+        (`weights` a scalar or an [n] array) this is the compact survey format
+        (ngx_lm_fit_host_compact): 4.1 instead of 16 bytes per pixel cross
+        PCIe; the results equal those of the expanded arrays
+        images.astype(f8), where(mask, weight, 0) bit for bit.
     prior: PriorSimpleSep / PriorBDFSep, optional
     fit_pars: dict with maxfev, ftol, xtol, optional
     noise_images: [n, H, W] array, optional
@@ -70,6 +76,28 @@ def fit_batch(model, images, weights, jacobians, psf_pars, guesses,
     fp = dict(DEFAULT_LM_PARS)
     if fit_pars is not None:
         fp.update(fit_pars)
+    w_arr = np.asarray(weights)
+    if w_arr.ndim <= 1:
+        # one weight per stamp (+ optional mask)
+        images = np.asarray(images)
+        if images.ndim == 2:
+            images = images[None]
+        n = images.shape[0]
+        w_arr = np.broadcast_to(w_arr.astype("f8"), (n,))
+        if images.dtype == np.float32 and noise_images is None \
+                and ignore_zero_weight:
+            return _lib.lm_fit_compact(
+                model, images, w_arr, jacobians, psf_pars, guesses, mask=mask,
+                prior=_prior_record(prior), maxfev=fp["maxfev"],
+                ftol=fp["ftol"], xtol=fp["xtol"],
+                analytic_jacobian=analytic_jacobian,
+                bounds=getattr(prior, "bounds", None))
+        weights = np.empty(images.shape)
+        weights[...] = w_arr[:, None, None]
+        if mask is not None:
+            weights[~np.asarray(mask, dtype=bool)] = 0.0
+    elif mask is not None:
+        weights = np.where(np.asarray(mask, dtype=bool), w_arr, 0.0)
     recs = _lib.lm_fit(model, images, weights, jacobians, psf_pars, guesses,
                        prior=_prior_record(prior), maxfev=fp["maxfev"],
                        ftol=fp["ftol"], xtol=fp["xtol"],

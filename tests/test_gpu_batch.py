@@ -172,3 +172,64 @@ def test_lm_fit_float32_host_stamps(ngx):
     r32 = ngx.lm_fit("exp", im32, wt32, b["jac"], b["psf"], b["guess"])
     _same_records(r32, r64)
     assert (r32["flags"] == 0).sum() > 1400
+
+
+def test_lm_fit_compact_survey_format(ngx):
+    """float32 pixels + one weight per stamp + a packed good-pixel mask
+    (ngx_lm_fit_host_compact) give the records of the expanded float64
+    arrays bit for bit, over several pipeline chunks, through fit_batch too"""
+    import ngmix_b200 as ng
+    from ngmix_b200 import sims
+    n = 1400
+    b = sims.make_lm_batch(n, seed0=6300, noise=0.05, dims=(21, 23),
+                           truth_images=False)
+    rng = np.random.RandomState(5)
+    gm0, _ = ngx.gmix_fill("exp", b["truth"])
+    gp, _ = ngx.gmix_fill("full", b["psf"].reshape(n, -1))
+    images, _ = ngx.render(ngx.gmix_convolve(gm0, gp), b["jac"], (21, 23))
+    images += rng.normal(0.0, 0.05, images.shape)
+    im32 = images.astype(np.float32)
+    wsc = rng.uniform(300.0, 500.0, size=n)
+    mask = rng.uniform(size=im32.shape) > 0.03
+    mask[7] = True
+    wt = np.where(mask, wsc[:, None, None], 0.0)
+    want = ngx.lm_fit("exp", im32.astype(np.float64), wt, b["jac"], b["psf"],
+                      b["guess"])
+    got = ngx.lm_fit_compact("exp", im32, wsc, b["jac"], b["psf"],
+                             b["guess"], mask=mask)
+    _same_records(got, want)
+    got2 = ng.fit_batch("exp", im32, wsc, b["jac"], b["psf"], b["guess"],
+                        mask=mask)
+    _same_records(got2, want)
+    # no mask, scalar weight for the whole batch
+    want3 = ngx.lm_fit("exp", im32.astype(np.float64),
+                       np.full(im32.shape, 400.0), b["jac"], b["psf"],
+                       b["guess"])
+    got3 = ng.fit_batch("exp", im32, 400.0, b["jac"], b["psf"], b["guess"])
+    _same_records(got3, want3)
+    # float64 pixels with a per-stamp weight go through the expanded path
+    got4 = ng.fit_batch("exp", im32.astype(np.float64), wsc, b["jac"],
+                        b["psf"], b["guess"], mask=mask)
+    _same_records(got4, want)
+    assert (want["flags"] == 0).sum() > 1300
+
+
+def test_pinned_host_memory_helpers(ngx):
+    import ngmix_b200 as ng
+    from ngmix_b200 import sims
+    b = sims.make_lm_batch(64, seed0=6400, noise=0.05, dims=(24, 24))
+    want = ngx.lm_fit("exp", b["images"], b["weights"], b["jac"], b["psf"],
+                      b["guess"])
+    pim = ng.pinned_copy(b["images"])
+    pwt = ng.pinned_copy(b["weights"])
+    assert pim.shape == b["images"].shape and pim.dtype == np.float64
+    got = ngx.lm_fit("exp", pim, pwt, b["jac"], b["psf"], b["guess"])
+    _same_records(got, want)
+    im, wt = b["images"].copy(), b["weights"].copy()
+    with ng.pinned(im, wt):
+        got = ngx.lm_fit("exp", im, wt, b["jac"], b["psf"], b["guess"])
+    _same_records(got, want)
+    e = ng.pinned_empty((3, 5), "f4")
+    e[...] = 1.5
+    assert e.sum() == 22.5
+    del e, pim, pwt
