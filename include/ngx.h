@@ -405,6 +405,53 @@ int ngx_template_flux(int nobj, const int32_t *stamp_start,
                       void *stream);
 
 /* ------------------------------------------------------------------ */
+/* The production chain in one device pass (bootstrap.py:43-102 with
+ * PSFRunner(EMFitter, GMixPSFGuesser(ngauss), ntry) and Runner(Fitter(model),
+ * TPSFFluxGuesser(T), ntry); runners.py:116-149, guessers.py:78-144, 205-261,
+ * 767-1051): per object an EM fit of its psf stamp, the psf-template flux of
+ * its image (PSFFluxFitter), a guess drawn from that flux and T, and the LM
+ * fit, each stage retried with fresh guesses while flags != 0.  Guesses come
+ * from Philox4x32-10 keyed by `seed` with counter (object index, try, draw
+ * block, stage): they depend on nothing but (seed, index, try), so results
+ * do not change with batch size or sharding (ngx_chain_draws exposes the
+ * stream).  All device pointers; everything is enqueued on `stream`.
+ *   T_guess [n] central T of the object guesses (NULL: T of the psf mixture)
+ *   psf_pars [n,psf_ngauss,6], psf_res [n], psf_flux [n], guess [n,npars],
+ *   res [n], ntry_used [2,n] (psf, object) are outputs;
+ *   workspace of ngx_bootstrap_workspace_bytes(n, psf_ngauss) bytes.
+ * Objects whose psf fit or psf flux fails get res.flags = NGX_NO_ATTEMPT. */
+size_t ngx_bootstrap_workspace_bytes(int n, int psf_ngauss);
+int ngx_bootstrap(int n, const double *psf_images, const double *psf_weights,
+                  const ngx_jacobian *psf_jac, int psf_nrow, int psf_ncol,
+                  int psf_ngauss, int psf_ntry, const ngx_em_conf *em_conf,
+                  const double *images, const double *weights,
+                  const ngx_jacobian *jac, int nrow, int ncol, int model,
+                  const double *T_guess, int ntry, const ngx_prior *prior,
+                  const ngx_lm_pars *lm_pars, unsigned long long seed,
+                  double *psf_pars, ngx_em_result *psf_res,
+                  ngx_flux_result *psf_flux, double *guess,
+                  ngx_lm_result *res, int32_t *ntry_used, void *workspace,
+                  size_t workspace_bytes, void *stream);
+/* the first ndraw uniform doubles of stream (object i, try, stage) for
+ * i < n: out [n, ndraw]; stage 1 = psf guesses, 2 = object guesses */
+int ngx_chain_draws(int n, unsigned long long seed, int tr, int stage,
+                    int ndraw, double *out, void *stream);
+/* ngx_em / ngx_lm_fit restricted to the objects with todo[i] != 0 (device
+ * array; the records of the others are left untouched): the retry rounds */
+int ngx_em_todo(int n, int variant, const double *images,
+                const double *weights, const ngx_jacobian *jac, int nrow,
+                int ncol, const double *guess, int ngauss,
+                const double *psf_pars, int npsf, const ngx_em_conf *conf,
+                int ignore_zero_weight, const int32_t *todo, double *pars_out,
+                ngx_em_result *res, void *stream);
+int ngx_lm_fit_todo(int n, int model, const double *images,
+                    const double *weights, const ngx_jacobian *jac, int nrow,
+                    int ncol, const double *psf_pars, int npsf,
+                    const double *guess, const ngx_prior *prior,
+                    const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                    const int32_t *todo, ngx_lm_result *res, void *stream);
+
+/* ------------------------------------------------------------------ */
 /* host-buffer variants (synchronous; H2D/D2H inside) */
 int ngx_gmix_fill_host(int n, int model, int ngauss, const double *pars,
                        int npars, ngx_gauss *gmix, int32_t *status);

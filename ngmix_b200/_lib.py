@@ -134,7 +134,8 @@ SYMBOLS = [
     "ngx_noise_b", "ngx_noise_b_host", "ngx_noise_cov_host",
     "ngx_lm_fit_host_f32", "ngx_lm_fit_host_compact",
     "ngx_host_alloc", "ngx_host_free", "ngx_host_register",
-    "ngx_host_unregister",
+    "ngx_host_unregister", "ngx_bootstrap", "ngx_bootstrap_workspace_bytes",
+    "ngx_chain_draws", "ngx_em_todo", "ngx_lm_fit_todo",
     "ngx_lm_fit_multi_wide", "ngx_lm_fit_multi_wide_host",
     "ngx_lm_fit_coellip", "ngx_lm_fit_coellip_host",
 ]
@@ -917,3 +918,45 @@ class pinned(object):
             lib().ngx_host_unregister(C.c_void_p(a.ctypes.data))
         self.done = []
         return False
+
+
+# ----------------------------------------------------------- fitting chain
+
+
+def bootstrap_device(n, d_psf_images, d_psf_weights, d_psf_jac, psf_nrow,
+                     psf_ncol, psf_ngauss, psf_ntry, d_images, d_weights,
+                     d_jac, nrow, ncol, model, d_T_guess, ntry, seed,
+                     d_psf_pars, d_psf_res, d_psf_flux, d_guess, d_res,
+                     d_ntry_used, d_workspace, workspace_bytes, prior=None,
+                     maxfev=4000, ftol=1.0e-5, xtol=1.0e-5,
+                     analytic_jacobian=True, em_tol=1.0e-5, em_miniter=40,
+                     em_maxiter=500, bounds=None, stream=0):
+    """ngx_bootstrap on device pointers (asynchronous on `stream`)"""
+    conf = EMConf(em_tol, em_maxiter, em_miniter, 0.0, 0, 0)
+    pr = prior if prior is not None else Prior()
+    lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)
+    lmp.set_bounds(bounds)
+    check(lib().ngx_bootstrap(
+        C.c_int(n), C.c_void_p(d_psf_images), C.c_void_p(d_psf_weights),
+        C.c_void_p(d_psf_jac), C.c_int(psf_nrow), C.c_int(psf_ncol),
+        C.c_int(psf_ngauss), C.c_int(psf_ntry), C.byref(conf),
+        C.c_void_p(d_images), C.c_void_p(d_weights), C.c_void_p(d_jac),
+        C.c_int(nrow), C.c_int(ncol), C.c_int(MODELS[model]),
+        C.c_void_p(d_T_guess) if d_T_guess else None, C.c_int(ntry),
+        C.byref(pr), C.byref(lmp), C.c_ulonglong(seed),
+        C.c_void_p(d_psf_pars), C.c_void_p(d_psf_res),
+        C.c_void_p(d_psf_flux), C.c_void_p(d_guess), C.c_void_p(d_res),
+        C.c_void_p(d_ntry_used), C.c_void_p(d_workspace),
+        C.c_size_t(workspace_bytes), C.c_void_p(stream)))
+
+
+def bootstrap_workspace_bytes(n, psf_ngauss):
+    f = lib().ngx_bootstrap_workspace_bytes
+    f.restype = C.c_size_t
+    return int(f(C.c_int(n), C.c_int(psf_ngauss)))
+
+
+def chain_draws_device(n, seed, tr, stage, ndraw, d_out, stream=0):
+    check(lib().ngx_chain_draws(C.c_int(n), C.c_ulonglong(seed), C.c_int(tr),
+                                C.c_int(stage), C.c_int(ndraw),
+                                C.c_void_p(d_out), C.c_void_p(stream)))

@@ -236,6 +236,79 @@ class ObservationBatch(object):
             res.append(r)
         return res
 
+    # ------------------------------------------------------ fitting chain
+    def bootstrap(self, psf_batch, model="exp", psf_ngauss=3, psf_ntry=4,
+                  ntry=4, T_guess=None, prior=None, fit_pars=None, seed=0,
+                  em_pars=None, analytic_jacobian=True):
+        """
+        The production chain in one device pass (ngx_bootstrap): for every
+        object an EM fit of its psf stamp (`psf_batch`, same length) from
+        GMixPSFGuesser-style guesses, the psf-template flux of its image, a
+        TPSFFluxGuesser-style guess and the LM fit, each stage retried with a
+        fresh guess while flags != 0 (bootstrap.py:43-102, runners.py:116-149
+        of the reference).  Guesses come from a counter-based generator keyed
+        by (seed, object index, try): results do not depend on batch size or
+        sharding when `index0`-shifted seeds are not used.
+
+        Returns a dict: res (LM records), psf_pars [n, psf_ngauss, 6],
+        psf_res (EM records), psf_flux (flux records), guess [n, npars] (the
+        last guess used), psf_ntry / ntry [n] (tries used).  The psf mixtures
+        also become this batch's psf (set_psf) without leaving the device.
+        """
+        torch = _torch()
+        from .fitting import _prior_record, _LM_MODELS
+        model = get_model_name(get_model_num(model))
+        if model not in _LM_MODELS:
+            raise ValueError("model '%s' cannot be fit with ngx_lm_fit" % model)
+        if len(psf_batch) != self.n:
+            raise ValueError("one psf stamp per object is needed")
+        np_ = get_model_npars(model)
+        fp = dict(DEFAULT_LM_PARS)
+        if fit_pars is not None:
+            fp.update(fit_pars)
+        ep = dict(tol=1.0e-5, miniter=40, maxiter=500)
+        if em_pars is not None:
+            ep.update(em_pars)
+        n = self.n
+        dev = self.device
+        psf_pars = torch.zeros((max(n, 1), psf_ngauss, 6),
+                               dtype=torch.float64, device=dev)
+        guess = torch.zeros((max(n, 1), np_), dtype=torch.float64, device=dev)
+        ntry_used = torch.zeros((2, max(n, 1)), dtype=torch.int32, device=dev)
+        d_res = self._empty_records(_lib.LM_RESULT_DTYPE)
+        d_pres = self._empty_records(_lib.EM_RESULT_DTYPE)
+        d_pflux = self._empty_records(_lib.FLUX_RESULT_DTYPE)
+        wbytes = _lib.bootstrap_workspace_bytes(max(n, 1), psf_ngauss)
+        work = torch.zeros(wbytes, dtype=torch.uint8, device=dev)
+        d_T = 0
+        if T_guess is not None:
+            tg = self._up(np.broadcast_to(np.asarray(T_guess, dtype="f8"),
+                                          (n,)).copy())
+            d_T = tg.data_ptr()
+        if n > 0:
+            _lib.bootstrap_device(
+                n, psf_batch.images.data_ptr(), psf_batch.weights.data_ptr(),
+                psf_batch.jac.data_ptr(), psf_batch.nrow, psf_batch.ncol,
+                psf_ngauss, psf_ntry, self.images.data_ptr(),
+                self.weights.data_ptr(), self.jac.data_ptr(), self.nrow,
+                self.ncol, model, d_T, ntry, int(seed), psf_pars.data_ptr(),
+                d_pres.data_ptr(), d_pflux.data_ptr(), guess.data_ptr(),
+                d_res.data_ptr(), ntry_used.data_ptr(), work.data_ptr(),
+                wbytes, prior=_prior_record(prior), maxfev=fp["maxfev"],
+                ftol=fp["ftol"], xtol=fp["xtol"],
+                analytic_jacobian=analytic_jacobian, em_tol=ep["tol"],
+                em_miniter=ep["miniter"], em_maxiter=ep["maxiter"],
+                bounds=getattr(prior, "bounds", None),
+                stream=self._stream())
+        self.set_psf(psf_pars[:n])
+        nt = ntry_used.cpu().numpy()
+        return dict(res=self._records(d_res, _lib.LM_RESULT_DTYPE),
+                    psf_pars=psf_pars[:n].cpu().numpy(),
+                    psf_res=self._records(d_pres, _lib.EM_RESULT_DTYPE),
+                    psf_flux=self._records(d_pflux, _lib.FLUX_RESULT_DTYPE),
+                    guess=guess[:n].cpu().numpy(),
+                    psf_ntry=nt[0, :n].copy(), ntry=nt[1, :n].copy())
+
     # -------------------------------------------------------------- pixels
     def make_pixels(self):
         """the reference's pixel records (pixels/pixels.py:6-52) for every

@@ -91,7 +91,8 @@ k_em(int n, const double *__restrict__ images,
      int nrow, int ncol, const double *__restrict__ guess, int ngauss_in,
      const double *__restrict__ psf_pars, int npsf_in, ngx_em_conf conf,
      int ignore_zero_weight, double *__restrict__ pars_out,
-     ngx_em_result *__restrict__ res, double *gscratch = nullptr) {
+     ngx_em_result *__restrict__ res, double *gscratch = nullptr,
+     const int32_t *__restrict__ todo = nullptr) {
     extern __shared__ double smem_d[];
     __shared__ EMShared sh;
     constexpr bool DO_CEN = (VARIANT == NGX_EM_FULL || VARIANT == NGX_EM_FIXCOV);
@@ -107,6 +108,8 @@ k_em(int n, const double *__restrict__ images,
     double *contrib = smem_d;
     const int stamp = blockIdx.x;
     if (stamp >= n) return;
+    // retry rounds of the fitting chain: only the stamps still to do
+    if (todo && todo[stamp] == 0) return;
     double *stamp_arrays = contrib + (size_t)nslots * NGX_EM_STRIDE;
     if (GM)
         stamp_arrays = gscratch
@@ -726,6 +729,9 @@ static int pick_threads(int ntot) {
     return 128;
 }
 
+// stamps to fit in the current call (ngx_em_todo); NULL = all
+static thread_local const int32_t *g_em_todo = nullptr;
+
 template <int VARIANT>
 static int launch_em(int n, const double *images, const double *weights,
                      const ngx_jacobian *jac, int nrow, int ncol,
@@ -765,7 +771,7 @@ static int launch_em(int n, const double *images, const double *weights,
                 jac + i0, nrow, ncol, guess + (size_t)i0 * ngauss * 6, ngauss,
                 psf_pars ? psf_pars + (size_t)i0 * np1 * 6 : nullptr, npsf,
                 conf, ignore_zero_weight, pars_out + (size_t)i0 * ngauss * 6,
-                res + i0, scr);
+                res + i0, scr, g_em_todo ? g_em_todo + i0 : nullptr);
         }
         cudaError_t e = cudaGetLastError();
         cudaFreeAsync(scr, stream);
@@ -779,7 +785,8 @@ static int launch_em(int n, const double *images, const double *weights,
             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
         k_em<VARIANT, NG_><<<n, NGX_EM_TILE, smem, stream>>>(                \
             n, images, weights, jac, nrow, ncol, guess, ngauss, psf_pars,    \
-            npsf, conf, ignore_zero_weight, pars_out, res);                  \
+            npsf, conf, ignore_zero_weight, pars_out, res, nullptr,          \
+            g_em_todo);                                                      \
     } while (0)
     // the common mixture sizes get the register-resident variant
     if (ngauss == 1) NGX_EM_LAUNCH(1);
@@ -830,6 +837,20 @@ int ngx_em(int n, int variant, const double *images, const double *weights,
     default:
         return fail(NGX_ERR_ARG, "ngx_em: unknown variant%s%s");
     }
+}
+
+int ngx_em_todo(int n, int variant, const double *images,
+                const double *weights, const ngx_jacobian *jac, int nrow,
+                int ncol, const double *guess, int ngauss,
+                const double *psf_pars, int npsf, const ngx_em_conf *conf,
+                int ignore_zero_weight, const int32_t *todo, double *pars_out,
+                ngx_em_result *res, void *stream) {
+    g_em_todo = todo;
+    int rc = ngx_em(n, variant, images, weights, jac, nrow, ncol, guess,
+                    ngauss, psf_pars, npsf, conf, ignore_zero_weight,
+                    pars_out, res, stream);
+    g_em_todo = nullptr;
+    return rc;
 }
 
 int ngx_admom(int n, const double *images, const double *weights,

@@ -72,6 +72,8 @@ struct LMArgs {
     const int32_t *stamp_start, *stamp_band;
     // stamps too large for shared memory (GS kernels): per-CTA planes
     double *gscratch;
+    // retry rounds of the fitting chain: fit only objects with todo != 0
+    const int32_t *todo;
 };
 
 // bounded fits: leastsqbound's parameter transforms (leastsqbound.py:183-263).
@@ -1016,6 +1018,7 @@ k_lm_fit(LMArgs a) {
 
     for (;;) {
         const bool have = stamp < a.n;
+        const bool skip = have && a.todo && a.todo[stamp] == 0;
 #ifdef NGX_PROF
         long long pt0 = clock64(), pt_mix = 0, pt_pass = 0, pt_solve = 0,
                   pt_stage = 0, pt_fin = 0, ptx;
@@ -1035,7 +1038,7 @@ k_lm_fit(LMArgs a) {
                 sh.jac = a.jac[stamp];
                 sh.status = 0;
             }
-        } else if (have) {
+        } else if (have && !skip) {
             const double *im = a.images + (size_t)stamp * a.ntot;
             const double *wt = a.weights + (size_t)stamp * a.ntot;
             const int t0 = threadIdx.x - 32, TS = T - 32;
@@ -1147,6 +1150,12 @@ k_lm_fit(LMArgs a) {
         pending = -1;
         __syncthreads();
         const int next = sh.next;
+        if (skip) {
+            // nothing to do for this stamp (its record stays as it is)
+            __syncthreads();
+            stamp = next;
+            continue;
+        }
         if (next < a.n) {
             // pull the next stamp into L2 while this one is fitted
             const char *pi = (const char *)(a.images + (size_t)next * a.ntot);
@@ -1459,6 +1468,7 @@ k_lm_fit_multi(LMArgs a) {
         __syncthreads();
         const int obj = sh.stamp;
         if (obj >= a.n) break;
+        if (a.todo && a.todo[obj] == 0) continue;
         const int s0 = a.stamp_start[obj], s1 = a.stamp_start[obj + 1];
 
         // ---- valid pixels of the object, first valid pixel of its first
@@ -1870,7 +1880,24 @@ using namespace ngx;
 
 extern "C" {
 
+// objects to fit in the current call (ngx_lm_fit_todo); NULL = all
+static thread_local const int32_t *g_lm_todo = nullptr;
+
 #ifndef NGX_LM_WIDE_TU
+int ngx_lm_fit_todo(int n, int model, const double *images,
+                    const double *weights, const ngx_jacobian *jac, int nrow,
+                    int ncol, const double *psf_pars, int npsf,
+                    const double *guess, const ngx_prior *prior,
+                    const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                    const int32_t *todo, ngx_lm_result *res, void *stream) {
+    g_lm_todo = todo;
+    int rc = ngx_lm_fit(n, model, images, weights, jac, nrow, ncol, psf_pars,
+                        npsf, guess, prior, lm_pars, ignore_zero_weight, res,
+                        stream);
+    g_lm_todo = nullptr;
+    return rc;
+}
+
 int ngx_lm_fit(int n, int model, const double *images, const double *weights,
                const ngx_jacobian *jac, int nrow, int ncol,
                const double *psf_pars, int npsf, const double *guess,
@@ -1894,6 +1921,7 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     a.lm = *lm_pars;
     a.images = images; a.weights = weights; a.jac = jac;
     a.psf = psf_pars; a.guess = guess; a.res = res;
+    a.todo = g_lm_todo;
     NGX_REQUIRE(a.ngauss <= NGX_MAX_GAUSS);
     if (a.prior.present) {
         NGX_REQUIRE(a.prior.g_kind == 1);
@@ -2029,6 +2057,7 @@ static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
     a.images = images; a.weights = weights; a.jac = jac;
     a.psf = psf_pars; a.guess = guess; a.res = res;
     a.stamp_start = stamp_start; a.stamp_band = stamp_band;
+    a.todo = g_lm_todo;
     NGX_REQUIRE(a.ngauss <= NGX_MAX_GAUSS);
     int threads = 128;
     NGX_REQUIRE(threads >= a.ngauss && threads >= 6 * npsf);
