@@ -628,7 +628,7 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
                     const double2 *g2 =
                         (const double2 *)(recs + FDREC * k);
                     const double2 rc = g2[0], ab = g2[1], cp = g2[2];
-                    double x[CF], e[CF];
+                    double x[CF], tv[CF], pv[CF];
                     bool ap[CF], anyap = false;
 #pragma unroll
                     for (int c = 0; c < CF; c++) {
@@ -641,18 +641,25 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
                         double f = fexp_split(x[c], &slot, &inr, &ap[c]);
                         // (exp(i) pn) P(f): the product the per-gaussian
                         // tables of the other passes hold precomputed
-                        e[c] = (etab[slot] * cp.y) * fexp_poly_c(f);
+                        tv[c] = etab[slot] * cp.y;
+                        pv[c] = fexp_poly_c(f);
                         anyap |= ap[c];
                     }
                     if (__any_sync(0xffffffffu, anyap)) {
 #pragma unroll
                         for (int c = 0; c < CF; c++) {
+                            double e = tv[c] * pv[c];
                             double wv = apod_window_x(x[c]);
-                            if (ap[c]) e[c] *= wv;
+                            if (ap[c]) e *= wv;
+                            mod[s][c] += e;
                         }
-                    }
+                    } else {
+                        // as in the value pass, whose model the differences
+                        // are taken against
 #pragma unroll
-                    for (int c = 0; c < CF; c++) mod[s][c] += e[c];
+                        for (int c = 0; c < CF; c++)
+                            mod[s][c] = fma(tv[c], pv[c], mod[s][c]);
+                    }
                 }
             }
         }

@@ -114,16 +114,17 @@ __host__ __device__ inline int prior_nslots(int model, const ngx_prior &pr) {
 // number of rows the prior actually fills
 __host__ __device__ inline int prior_nrows(int model, const ngx_prior &pr) {
     if (!pr.present) return 0;
-    if (model == NGX_BDF) return 6;
-    if (model == NGX_BD) return 7;
+    if (model == NGX_BDF) return 5 + prior_nband(pr);
+    if (model == NGX_BD) return 6 + prior_nband(pr);
     if (model == NGX_COELLIP) return 3 + 2 * pr.ncoellip;
     return 4 + prior_nband(pr);
 }
 
 // one row of prior.fill_fdiff; row index in the reference's order.
 // simple: 0 cen1, 1 cen2, 2 g, 3 T, 4.. F per band   (sqrt(clip(-2 lnp)))
-// bdf   : 0 cen1, 1 cen2, 2 g, 3 T, 4 fracdev, 5 F   (signed get_fdiff)
-// bd    : 0 cen1, 1 cen2, 2 g, 3 T, 4 logTratio, 5 fracdev, 6 F  (signed)
+// bdf   : 0 cen1, 1 cen2, 2 g, 3 T, 4 fracdev, 5.. F per band (signed
+//         get_fdiff)
+// bd    : 0 cen1, 1 cen2, 2 g, 3 T, 4 logTratio, 5 fracdev, 6.. F per band
 static __device__ __noinline__ int prior_row(int model, const ngx_prior &pr,
                                 const double *p, int row, double *out) {
     double lnp;
@@ -140,7 +141,8 @@ static __device__ __noinline__ int prior_row(int model, const ngx_prior &pr,
         case 3: return prior1d_fdiff(pr.T, p[4], out);
         case 4: return prior1d_fdiff(pr.logTratio, p[5], out);
         case 5: return prior1d_fdiff(pr.fracdev, p[6], out);
-        default: return prior1d_fdiff(pr.F, p[7], out);
+        default:
+            return prior1d_fdiff(prior_F(pr, row - 6), p[7 + (row - 6)], out);
         }
     }
     if (model == NGX_BDF) {
@@ -154,7 +156,8 @@ static __device__ __noinline__ int prior_row(int model, const ngx_prior &pr,
             return 0;
         case 3: return prior1d_fdiff(pr.T, p[4], out);
         case 4: return prior1d_fdiff(pr.fracdev, p[5], out);
-        default: return prior1d_fdiff(pr.F, p[6], out);
+        default:
+            return prior1d_fdiff(prior_F(pr, row - 5), p[6 + (row - 5)], out);
         }
     }
     switch (row) {

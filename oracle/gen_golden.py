@@ -1384,6 +1384,127 @@ def gen_lm_bounds():
     save("lm_bounds", **out)
 
 
+def gen_lm_multi_fd():
+    """Fitter.go on ObsList / MultiBandObsList inputs through lmdif: bdf and
+    bd objects (PriorBDFSep / PriorBDSep with a flux prior per band,
+    joint_prior.py:267-676) and exp objects with analytic_jacobian=False"""
+    from ngmix.fitting import Fitter
+    from ngmix import priors, joint_prior
+    from ngmix_b200.sims import (diag_jacobian, simple_full_pars,
+                                 bdf_full_pars, convolve_full_pars,
+                                 render_full_pars)
+    rng = np.random.RandomState(16180)
+    configs = [
+        # (nband, epochs per band, model, with_prior)
+        (1, [2], "bdf", True), (2, [1, 1], "bdf", True),
+        (3, [1, 2, 1], "bdf", True), (2, [2, 1], "bdf", False),
+        (5, [1, 1, 1, 1, 1], "bdf", True),
+        (2, [1, 1], "bd", True), (1, [3], "bd", True),
+        (2, [1, 2], "exp", True), (3, [1, 1, 1], "exp", False),
+    ]
+    out = {}
+    icase = 0
+    H = W = 32
+    for nband, nep, model, with_prior in configs:
+        for rep in range(2):
+            noise = [0.02, 0.1][rep]
+            g1, g2 = rng.normal(0.0, 0.12, size=2)
+            T = rng.uniform(0.2, 0.8)
+            fracdev = rng.uniform(0.2, 0.8)
+            fluxes = rng.uniform(60.0, 180.0, size=nband)
+            images, weights, jacs, psfs, bands = [], [], [], [], []
+            for b in range(nband):
+                for _ in range(nep[b]):
+                    dy, dx = rng.uniform(-0.5, 0.5, size=2)
+                    jac = diag_jacobian((H - 1) / 2 + dy, (W - 1) / 2 + dx,
+                                        0.263)
+                    ppars = [0.0, 0.0, rng.normal(0, 0.01),
+                             rng.normal(0, 0.01), rng.uniform(0.22, 0.32), 1.0]
+                    psf = simple_full_pars(ppars, "turb")
+                    if model == "exp":
+                        obj = simple_full_pars(
+                            [0.0, 0.0, g1, g2, T, fluxes[b]], "exp")
+                    else:
+                        # bd truth with logTratio = 0 is the bdf mixture
+                        obj = bdf_full_pars(
+                            [0.0, 0.0, g1, g2, T, fracdev, fluxes[b]])
+                    im = render_full_pars(convolve_full_pars(obj, psf),
+                                          (H, W), jac)
+                    images.append(im + rng.normal(0.0, noise, size=im.shape))
+                    wt = np.zeros((H, W)) + 1.0 / noise ** 2
+                    if rng.uniform() < 0.3:
+                        wt[rng.uniform(size=wt.shape) < 0.05] = 0.0
+                    weights.append(wt)
+                    jacs.append(jac)
+                    psfs.append(psf)
+                    bands.append(b)
+            shared = {"exp": [0.0, 0.0, g1, g2, T],
+                      "bdf": [0.0, 0.0, g1, g2, T, fracdev],
+                      "bd": [0.0, 0.0, g1, g2, T, 0.0, fracdev]}[model]
+            truth = np.array(shared + list(fluxes))
+            guess = truth.copy()
+            guess[0:2] = rng.uniform(-0.01, 0.01, size=2)
+            guess[2:] *= 1.0 + rng.uniform(-0.05, 0.05, size=guess.size - 2)
+            if model == "bd":
+                guess[5] = rng.uniform(-0.05, 0.05)
+            mbobs = ngmix.MultiBandObsList()
+            k = 0
+            for b in range(nband):
+                ol = ngmix.ObsList()
+                for _ in range(nep[b]):
+                    psf_obs = ngmix.Observation(
+                        np.zeros((5, 5)) + 1.0,
+                        gmix=ngmix.GMix(pars=psfs[k].ravel()))
+                    ol.append(ngmix.Observation(
+                        images[k], weight=weights[k],
+                        jacobian=jac_from_record(jacs[k]), psf=psf_obs))
+                    k += 1
+                mbobs.append(ol)
+            prior = None
+            if with_prior:
+                cen = priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng)
+                gp = priors.GPriorBA(0.3, rng=rng)
+                Tp = priors.FlatPrior(-1.0, 1.0e3, rng=rng)
+                Fp = [priors.FlatPrior(-100.0, 1.0e9, rng=rng)
+                      for _ in range(nband)]
+                if model == "bdf":
+                    prior = joint_prior.PriorBDFSep(
+                        cen, gp, Tp, priors.Normal(0.5, 0.1, rng=rng), Fp)
+                elif model == "bd":
+                    prior = joint_prior.PriorBDSep(
+                        cen, gp, Tp, priors.Normal(0.0, 0.5, rng=rng),
+                        priors.Normal(0.5, 0.1, rng=rng), Fp)
+                else:
+                    prior = joint_prior.PriorSimpleSep(cen, gp, Tp, Fp)
+            fitter = Fitter(model=model, prior=prior,
+                            analytic_jacobian=False)
+            obs_in = mbobs if nband > 1 else mbobs[0]
+            r = fitter.go(obs=obs_in, guess=guess)
+            p = "c%d_" % icase
+            out[p + "images"] = np.array(images)
+            out[p + "weights"] = np.array(weights)
+            out[p + "jac"], out[p + "psf"] = np.array(jacs), np.array(psfs)
+            out[p + "bands"] = np.array(bands, dtype="i4")
+            out[p + "guess"] = guess
+            out[p + "model"] = np.array(model)
+            out[p + "nband"] = np.array(nband)
+            out[p + "prior"] = np.array(int(with_prior))
+            for key in ("flags", "nfev", "ier", "pars", "pars_cov",
+                        "pars_err"):
+                out[p + key] = np.array(r[key])
+            if r["flags"] == 0:
+                for key in ("lnprob", "s2n", "chi2per", "dof", "npix", "T",
+                            "T_err"):
+                    out[p + key] = np.array(r[key])
+                out[p + "flux"] = np.atleast_1d(r["flux"])
+                out[p + "flux_err"] = np.atleast_1d(r["flux_err"])
+            print(icase, model, nband, nep, "flags", r["flags"], "nfev",
+                  r["nfev"], "ier", r["ier"])
+            icase += 1
+    out["ncases"] = np.array(icase)
+    save("lm_multi_fd", **out)
+
+
 GENERATORS = {
     "fastexp": gen_fastexp,
     "gmix": gen_gmix,
@@ -1406,6 +1527,7 @@ GENERATORS = {
     "psfflux": gen_psfflux,
     "boot": gen_boot,
     "lm_bounds": gen_lm_bounds,
+    "lm_multi_fd": gen_lm_multi_fd,
 }
 
 if __name__ == "__main__":

@@ -761,15 +761,23 @@ typedef struct {
     const ora_prior1d *Fp;          /* flux prior of each band */
 } mfitctx;
 
+/* get_band_pars (results.py:1013-1047): everything up to the fluxes, then
+ * the band's flux; ns = 5 (simple), 6 (bdf), 7 (bd) shared parameters */
+static void m_band_pars_n(int ns, const double *pars, int band, double *bp) {
+    for (int i = 0; i < ns; i++) bp[i] = pars[i];
+    bp[ns] = pars[ns + band];
+}
 static void m_band_pars(const double *pars, int band, double *bp) {
-    for (int i = 0; i < 5; i++) bp[i] = pars[i];
-    bp[5] = pars[5 + band];
+    m_band_pars_n(5, pars, band, bp);
+}
+static int m_nshared(int model) {
+    return model == ORA_BD ? 7 : model == ORA_BDF ? 6 : 5;
 }
 
 static int m_fill_gmix_all(mfitctx *m, const double *pars) {
     for (int i = 0; i < m->nstamp; i++) {
-        double bp[6];
-        m_band_pars(pars, m->band[i], bp);
+        double bp[ORA_MAXP];
+        m_band_pars_n(m_nshared(m->model), pars, m->band[i], bp);
         if (ctx_fill_gmix(&m->c[i], bp)) return ORA_RANGE_ERROR;
     }
     return ORA_OK;
@@ -781,6 +789,33 @@ static int m_prior_fill_fdiff(const mfitctx *m, const double *pars,
     const ora_prior *pr = m->prior;
     if (!pr || !pr->present) return 0;
     int index = 0;
+    if (m->model == ORA_BDF || m->model == ORA_BD) {
+        /* PriorBDFSep / PriorBDSep.fill_fdiff with a flux prior per band
+         * (joint_prior.py:565-599, 364-399): signed rows */
+        double sinv1 = 1.0 / pr->sigma1, sinv2 = 1.0 / pr->sigma2;
+        fdiff[index++] = (pars[0] - pr->cen1) * sinv1;
+        fdiff[index++] = (pars[1] - pr->cen2) * sinv2;
+        double lnpg;
+        if (gprior_lnprob(pr, pars[2], pars[3], &lnpg)) return -1;
+        double c = -2 * lnpg;
+        if (c < 0.0) c = 0.0;
+        fdiff[index++] = sqrt(c);
+        double fd;
+        if (prior1d_fdiff(&pr->T, pars[4], &fd)) return -1;
+        fdiff[index++] = fd;
+        int k = 5;
+        if (m->model == ORA_BD) {
+            if (prior1d_fdiff(&pr->logTratio, pars[k++], &fd)) return -1;
+            fdiff[index++] = fd;
+        }
+        if (prior1d_fdiff(&pr->fracdev, pars[k++], &fd)) return -1;
+        fdiff[index++] = fd;
+        for (int b = 0; b < m->nband; b++) {
+            if (prior1d_fdiff(&m->Fp[b], pars[k + b], &fd)) return -1;
+            fdiff[index++] = fd;
+        }
+        return index;
+    }
     double s2inv1 = 1.0 / (pr->sigma1 * pr->sigma1);
     double s2inv2 = 1.0 / (pr->sigma2 * pr->sigma2);
     double d1 = pr->cen1 - pars[0];
@@ -817,8 +852,19 @@ static int m_prior_lnprob(const mfitctx *m, const double *pars, double *out) {
     lnp += t;
     if (prior1d_lnprob(&pr->T, pars[4], &t)) return ORA_RANGE_ERROR;
     lnp += t;
+    int k = 5;
+    if (m->model == ORA_BD) {
+        if (prior1d_lnprob(&pr->logTratio, pars[k++], &t))
+            return ORA_RANGE_ERROR;
+        lnp += t;
+    }
+    if (m->model == ORA_BD || m->model == ORA_BDF) {
+        if (prior1d_lnprob(&pr->fracdev, pars[k++], &t))
+            return ORA_RANGE_ERROR;
+        lnp += t;
+    }
     for (int b = 0; b < m->nband; b++) {
-        if (prior1d_lnprob(&m->Fp[b], pars[5 + b], &t)) return ORA_RANGE_ERROR;
+        if (prior1d_lnprob(&m->Fp[b], pars[k + b], &t)) return ORA_RANGE_ERROR;
         lnp += t;
     }
     *out = lnp;
@@ -937,17 +983,38 @@ int ora_lm_fit_multi(int model, int nstamp, const double *images,
                      const ora_prior *prior, const ora_prior1d *Fp, int maxfev,
                      double ftol, double xtol, int ignore_zero_weight,
                      ora_lm_result *res) {
+    return ora_lm_fit_multi2(model, nstamp, images, weights, nrow, ncol, jacs,
+                             psf_pars, npsf, bands, nband, guess, prior, Fp,
+                             maxfev, ftol, xtol, 1, ignore_zero_weight, res);
+}
+
+/* the same for every LM model: gauss / exp / dev with the analytic jacobian
+ * (lmder) or, with analytic_jacobian = 0 and always for bdf / bd, MINPACK's
+ * forward differences (lmdif), as Fitter.go chooses (fitters.py:93-98) */
+int ora_lm_fit_multi2(int model, int nstamp, const double *images,
+                      const double *weights, int nrow, int ncol,
+                      const ora_jac *jacs, const double *psf_pars, int npsf,
+                      const int32_t *bands, int nband, const double *guess,
+                      const ora_prior *prior, const ora_prior1d *Fp,
+                      int maxfev, double ftol, double xtol,
+                      int analytic_jacobian, int ignore_zero_weight,
+                      ora_lm_result *res) {
     memset(res, 0, sizeof(*res));
-    if (!(model == ORA_GAUSS || model == ORA_EXP || model == ORA_DEV))
+    const int simple = model == ORA_GAUSS || model == ORA_EXP
+        || model == ORA_DEV;
+    if (!(simple || model == ORA_TURB || model == ORA_BDF || model == ORA_BD))
         return -1;
-    if (nband < 1 || 5 + nband > ORA_MAXP || nstamp < 1) return -1;
+    const int nsh = m_nshared(model);
+    if (nband < 1 || nsh + nband > ORA_MAXP || nstamp < 1) return -1;
     int ntot = nrow * ncol;
     mfitctx m;
     memset(&m, 0, sizeof(m));
     m.model = model; m.nband = nband; m.nstamp = nstamp;
-    m.npars = 5 + nband;
+    m.npars = nsh + nband;
     m.band = bands; m.prior = prior; m.Fp = Fp;
-    m.n_prior_pars = (prior && prior->present) ? 5 + nband : 0;
+    /* results.py:1050-1076: bd 6 + nband, everything else 5 + nband */
+    m.n_prior_pars = (prior && prior->present)
+        ? (model == ORA_BD ? 6 : 5) + nband : 0;
     m.c = (fitctx *)calloc((size_t)nstamp, sizeof(fitctx));
     ora_pixel **pix = (ora_pixel **)calloc((size_t)nstamp, sizeof(*pix));
     int rc = 0;
@@ -978,8 +1045,14 @@ int ora_lm_fit_multi(int model, int nstamp, const double *images,
         int ipvt[ORA_MAXP];
         double qtf[ORA_MAXP];
         int nfev = 0, njev = 0;
-        int ier = ora_lmder(mcb_fdiff, mcb_jac, &m, mm, np, x, fvec, fjac,
+        int ier;
+        if (simple && analytic_jacobian)
+            ier = ora_lmder(mcb_fdiff, mcb_jac, &m, mm, np, x, fvec, fjac,
                             ftol, xtol, 0.0, maxfev, 100.0, &nfev, &njev,
+                            ipvt, qtf);
+        else
+            ier = ora_lmdif(mcb_fdiff, &m, mm, np, x, fvec, fjac, ftol, xtol,
+                            0.0, maxfev, 2.220446049250313e-16, 100.0, &nfev,
                             ipvt, qtf);
         int flags = 0;
         res->nfev = nfev; res->njev = njev; res->ier = ier;
@@ -1097,8 +1170,8 @@ int ora_lm_fit_multi(int model, int nstamp, const double *images,
             res->T = res->pars[4];
             res->T_err = sqrt(res->pars_cov[4 * np + 4]);
             /* band 0; the caller slices pars / pars_cov for more bands */
-            res->flux = res->pars[5];
-            res->flux_err = sqrt(res->pars_cov[5 * np + 5]);
+            res->flux = res->pars[nsh];
+            res->flux_err = sqrt(res->pars_cov[nsh * np + nsh]);
         }
         free(fvec);
     }

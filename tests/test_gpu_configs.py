@@ -345,3 +345,47 @@ def test_more_objects_than_a_grid_dimension(ngx):
     recs = ngx.lm_fit("gauss", im, np.full(im.shape, 1e4), jac, None,
                       pars * 1.01)
     assert (recs["flags"] == 0).sum() > 0.99 * n
+
+
+def test_config4_bdf_parity_2000_stamps(ora):
+    """
+    BASELINE configs[3] at test scale: 2 000 seeded bdf fits on 64x64 stamps
+    (48 gaussians, PriorBDFSep, MINPACK's forward-difference Jacobian) against
+    the oracle on identical pixels.  flags must agree on every stamp.  The
+    forward-difference Jacobian divides 1e-16 rounding differences of the
+    model by steps of 1.5e-8 |x|, so evaluation counts and parameters follow
+    the reference up to that noise: nfev and ier agree on >= 98 % of the
+    stamps (the oracle compiled with fused multiply-adds agrees with itself
+    on the same fraction, profiles/parity_sweep_r2.json), parameters within
+    max(1e-5 |p|, 1e-3 sigma) on >= 97 %, and T and flux within 1e-5 relative
+    on >= 99 %.
+    """
+    import os
+    import torch
+    import bench_configs
+    from ngmix_b200 import _lib, sims_device
+    _lib.init(0)
+    n = 2000
+    dev = torch.device("cuda", 0)
+    t = sims_device.make_bdf_batch_device(n, 4100000, dev)
+    d_res = torch.zeros(n * _lib.LM_RESULT_DTYPE.itemsize, dtype=torch.uint8,
+                        device=dev)
+    _lib.lm_fit_device("bdf", n, t["images"].data_ptr(),
+                       t["weights"].data_ptr(), t["jac"].data_ptr(), 64, 64,
+                       t["psf"].data_ptr(), 3, t["guess"].data_ptr(),
+                       d_res.data_ptr(), prior=bench_configs.bdf_prior(_lib),
+                       analytic_jacobian=False)
+    torch.cuda.synchronize()
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(),
+                        dtype=_lib.LM_RESULT_DTYPE)
+    ref = ora.lm_fit_batch("bdf", t["images"].cpu().numpy(),
+                           t["weights"].cpu().numpy(), t["h_jac"], t["h_psf"],
+                           t["h_guess"], prior=ora.make_prior("bdf"),
+                           nthreads=os.cpu_count())
+    p = bench_configs.lm_parity(res, ref, 7, Tcol=4, Fcol=6)
+    assert p["flags_equal"] == n
+    assert p["n_good"] >= 0.99 * n
+    assert p["nfev_ier_equal"] >= 0.98 * n
+    assert p["pars_within_tol"] >= 0.97 * p["n_good"]
+    assert p["n_rel_dev_T_or_flux_above_1e-5"] <= 0.01 * p["n_good"]
+    assert p["max_abs_dev_g"] < 1e-4

@@ -64,6 +64,33 @@ def test_oracle_multi_matches_reference(ora, name):
         _check(r, c, 5 + c["nband"])
 
 
+def _ora_priors_fd(ora, c):
+    """the priors of gen_golden.gen_lm_multi_fd"""
+    if not c["prior"]:
+        return None, None
+    pr = ora.make_prior("flat")
+    pr.fracdev = ora.Prior1D(3, 0, 0.5, 0.1, 0, 0)
+    pr.logTratio = ora.Prior1D(3, 0, 0.0, 0.5, 0, 0)
+    fps = [ora.Prior1D(1, 0, -100.0, 1.0e9, 0, 0) for _ in range(c["nband"])]
+    return pr, fps
+
+
+NSHARED = {"exp": 5, "bdf": 6, "bd": 7}
+
+
+def test_oracle_multi_fd_matches_reference(ora):
+    """bdf / bd objects with several stamps and bands, and exp objects with
+    analytic_jacobian=False: the lmdif path of Fitter.go on MultiBandObsList"""
+    g = _golden("lm_multi_fd")
+    for k in range(int(g["ncases"])):
+        c = _case(g, k)
+        pr, fps = _ora_priors_fd(ora, c)
+        r = ora.lm_fit_multi(c["model"], c["images"], c["weights"], c["jac"],
+                             c["psf"], c["bands"], c["nband"], c["guess"],
+                             prior=pr, Fpriors=fps, analytic_jacobian=False)
+        _check(r, c, NSHARED[c["model"]] + c["nband"])
+
+
 # ------------------------------------------------------------------ GPU
 @pytest.fixture(scope="module")
 def ngx():
