@@ -555,13 +555,16 @@ def lm_fit_coellip(ngauss, images, weights, jac, psf_pars, guess, prior=None,
 
 def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
                  psf_pars, guess, prior=None, maxfev=4000, ftol=1.0e-5,
-                 xtol=1.0e-5, ignore_zero_weight=True):
+                 xtol=1.0e-5, ignore_zero_weight=True,
+                 analytic_jacobian=True):
     """
     Fitter.go on ObsList / MultiBandObsList input for a batch of objects:
     object i owns stamps stamp_start[i]:stamp_start[i+1] of images/weights
-    [ns,H,W] (ordered band by band), stamp_band [ns]; guess [nobj, 5+nband].
-    Returns LM_RESULT_DTYPE [nobj] for 1-3 bands, LM_RESULT_WIDE_DTYPE
-    (14 parameter slots) for 4-7 bands.
+    [ns,H,W] (ordered band by band), stamp_band [ns]; guess
+    [nobj, nshared + nband] with 5 (gauss, exp, dev, turb), 6 (bdf) or 7 (bd)
+    shared parameters.  bdf, bd, turb and analytic_jacobian=False run
+    MINPACK's forward differences.  Returns LM_RESULT_DTYPE [nobj] for up to
+    8 parameters, LM_RESULT_WIDE_DTYPE (14 parameter slots) beyond.
     """
     init()
     images = _f8(images)
@@ -573,15 +576,18 @@ def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
     nobj = stamp_start.size - 1
     assert stamp_start[0] == 0 and stamp_start[-1] == ns
     assert stamp_band.size == ns
-    guess = _f8(guess).reshape(nobj, 5 + nband)
+    npars = MODEL_NPARS[model] - 1 + nband
+    if npars > 14 or nband > 7:
+        raise ValueError("at most 7 bands and 14 parameters")
+    guess = _f8(guess).reshape(nobj, npars)
     if psf_pars is None:
         npsf = 0
     else:
         psf_pars = _f8(psf_pars).reshape(ns, -1, 6)
         npsf = psf_pars.shape[1]
     pr = prior if prior is not None else Prior()
-    lmp = LMPars(maxfev, 1, ftol, xtol)
-    wide = nband > 3
+    lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)
+    wide = npars > 8
     res = np.zeros(nobj, dtype=LM_RESULT_WIDE_DTYPE if wide
                    else LM_RESULT_DTYPE)
     entry = lib().ngx_lm_fit_multi_wide_host if wide \

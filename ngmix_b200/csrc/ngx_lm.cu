@@ -578,9 +578,11 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
                                         const double *rowd,
                                         const double *cold,
                                         double (&sums)[FD_NSUM_(NPMAX)],
-                                        const double *mbase) {
+                                        const double *mbase, int npl = -1) {
     const int T = blockDim.x;
-    const int np = a.np;
+    // npl: parameters perturbed in this pass when they are not the fit's
+    // (a stamp of a multi-band object: the shared ones and its band's flux)
+    const int np = npl >= 0 ? npl : a.np;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ntile = a.nq >> 5;
     const int nwords = (a.ngauss + 31) >> 5;
@@ -608,7 +610,7 @@ __device__ __forceinline__ void fd_pass(const LMArgs &a, const LMShared *sh,
 #pragma unroll
             for (int c = 0; c < CF; c++) mod[s][c] = 0.0;
             if (s > np) continue;
-            if (s == 0) {
+            if (s == 0 && mbase) {
                 // the base model is the last value pass's (the accepted
                 // point: lmdif calls fdjac2 with its fvec)
 #pragma unroll
@@ -846,7 +848,7 @@ __device__ __noinline__ void lm_finish(const LMArgs &a, LMShared *sh,
         Tv = sh->xcur[4];
         Terr = sqrt(pcov[4 * np + 4]);
         // band 0 of a multi-band fit; the last parameter otherwise
-        const int fi = a.nband > 1 ? 5 : np - 1;
+        const int fi = np - (a.nband > 1 ? a.nband : 1);
         flux = sh->xcur[fi];
         fluxerr = sqrt(pcov[fi * np + fi]);
     }
@@ -1440,7 +1442,8 @@ struct LMMulti {
     double macc[MACC_X + 4];    // object sums: packed J^T J (np), J^T f, then
                                 // [MACC_X] sum r^2, [+1] s2n numer, [+2]
                                 // denom, [+3] r_first^2
-    double bp[6];           // band parameters of the current stamp
+    double bp[LM_MAXP];     // band parameters of the current stamp
+    double hsl[8];          // forward-difference steps of its parameters
     int first_q_obj, mstatus;
 };
 
@@ -1450,7 +1453,12 @@ __device__ __forceinline__ bool multi_pars_nonzero(const double *x, int nband) {
     return ok;
 }
 
-template <int CV, int CD, typename RES>
+// MODE 0: gauss / exp / dev with the analytic Jacobian.  MODE 1: MINPACK's
+// forward differences (bdf, bd, analytic_jacobian = 0): per stamp the base
+// mixture and one per local parameter (the shared ones and the band's flux,
+// stepped by the global parameter's h) are evaluated in one pass and the
+// stamp's (nloc x nloc) block is scattered into the object's J^T J.
+template <int MODE, int CV, int CD, typename RES>
 __global__ void __launch_bounds__(128, 4)
 k_lm_fit_multi(LMArgs a) {
     extern __shared__ double smem_d[];
@@ -1458,16 +1466,20 @@ k_lm_fit_multi(LMArgs a) {
     __shared__ LMMulti mu;
     const int T = blockDim.x;
     const int nwarps = T >> 5;
-    constexpr int NP = 0;
+    const int np = a.np, nband = a.nband;
+    const int nsh = np - nband, nloc = nsh + 1;   // shared / per-stamp pars
+    const int nfd = MODE == 1 ? nloc + 1 : 0;
     double *mix = smem_d;                                    // ngauss*REC
-    double *rowd = mix + (size_t)a.ngauss * REC;
+    double *fdm = mix + (size_t)a.ngauss * REC;      // nfd*ngauss*FDREC
+    double *etab = fdm + (size_t)nfd * a.ngauss * FDREC;     // 16 (MODE 1)
+    double *rowd = etab + (nfd ? 16 : 0);
     double *cold = rowd + a.nrow;
     double *scratch = cold + a.ncol;                         // 48 * nwarps
-    double *hs = scratch + 48 * nwarps;                      // 8
+    double *hs = scratch + 48 * nwarps;                      // LM_MAXP
     unsigned *tmask = (unsigned *)(hs + LM_MAXP);
-    const int np = a.np, nband = a.nband;
     const int tri = np * (np + 1) / 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (nfd) fill_rot_table(etab, 1.0);
 
     for (;;) {
         __syncthreads();
@@ -1547,12 +1559,23 @@ k_lm_fit_multi(LMArgs a) {
             __syncthreads();
             const bool want_f = (action == LM_ACT_EVAL_F);
             const double *xp = want_f ? sh.xeval : sh.xcur;
-            const bool nonzero = multi_pars_nonzero(xp, nband);
-            const bool fused = want_f && spec && nonzero
+            const bool nonzero = MODE == 1 || multi_pars_nonzero(xp, nband);
+            const bool fused = MODE == 0 && want_f && spec && nonzero
                 && !(sh.st.prered <= sh.st.ftol);
             const bool do_deriv = fused || action == LM_ACT_EVAL_J;
             if (threadIdx.x < MACC_X + 4) mu.macc[threadIdx.x] = 0.0;
-            if (threadIdx.x == 0) mu.mstatus = 0;
+            if (threadIdx.x == 0) {
+                mu.mstatus = 0;
+                if (MODE == 1 && do_deriv) {
+                    // fdjac2's steps on the (internal) parameters
+                    const double eps = 1.4901161193847656e-08;
+                    for (int i = 0; i < np; i++) {
+                        double h = eps * fabs(sh.st.x[i]);
+                        if (h == 0.0) h = eps;
+                        hs[i] = h;
+                    }
+                }
+            }
             __syncthreads();
             // calc_jacobian raises for T == 0 or a zero flux
             const int jstatus0 = do_deriv && !nonzero;
@@ -1561,8 +1584,11 @@ k_lm_fit_multi(LMArgs a) {
                 if (threadIdx.x == 0) {
                     sh.jac = a.jac[e];
                     sh.status = 0;
-                    for (int i = 0; i < 5; i++) mu.bp[i] = xp[i];
-                    mu.bp[5] = xp[5 + band];
+                    for (int i = 0; i < nsh; i++) mu.bp[i] = xp[i];
+                    mu.bp[nsh] = xp[nsh + band];
+                    if (MODE == 1)
+                        for (int l = 0; l < nloc; l++)
+                            mu.hsl[l] = hs[l < nsh ? l : nsh + band];
                     sh.first_q = (e == s0) ? mu.first_q_obj : -1;
                 }
                 if (threadIdx.x < 6 * a.npsf)
@@ -1588,17 +1614,74 @@ k_lm_fit_multi(LMArgs a) {
                 }
                 __syncthreads();
                 const double area = sh.jac.scale * sh.jac.scale;
-                build_mixture(a, &sh, mu.bp, mix, area);
+                if (MODE == 1 && do_deriv) {
+                    // base + nloc perturbed mixtures, a gaussian per thread
+                    const int njobs = (nloc + 1) * a.ngauss;
+                    for (int t = threadIdx.x; t < njobs; t += T) {
+                        const int s = t / a.ngauss, k = t - s * a.ngauss;
+                        double xl[LM_MAXP];
+#pragma unroll 1
+                        for (int i = 0; i < nloc; i++) {
+                            double xi = mu.bp[i];
+                            if (i == s - 1) {
+                                const int gi = i < nsh ? i : nsh + band;
+                                xi = b_i2e(a.lm, gi, sh.st.x[gi] + hs[gi]);
+                            }
+                            xl[i] = xi;
+                        }
+                        build_component(a, &sh, xl, k,
+                                        s == 0 ? mix : nullptr, area,
+                                        fdm + (size_t)s * a.ngauss * FDREC);
+                    }
+                } else {
+                    build_mixture(a, &sh, mu.bp, mix, area);
+                }
                 __syncthreads();
                 if (sh.status) {            // uniform: read after the barrier
                     if (threadIdx.x == 0) mu.mstatus = 1;
                     break;
                 }
-                build_tile_masks(a, &sh, mix, tmask, 1.0e-9);
+                build_tile_masks(a, &sh, mix, tmask,
+                                 MODE == 1 && do_deriv ? 1.0e-6 : 1.0e-9);
                 __syncthreads();
                 const double *im = a.images + (size_t)e * a.ntot;
                 const double *wt = a.weights + (size_t)e * a.ntot;
-                if (do_deriv) {
+                if (MODE == 1 && do_deriv) {
+                    constexpr int FDN = FD_NSUM_(FD_MAXP);
+                    double sums[FDN];
+#pragma unroll
+                    for (int i = 0; i < FDN; i++) sums[i] = 0.0;
+                    fd_pass<FD_MAXP, 2>(a, &sh, mu.hsl, fdm, etab, tmask,
+                                        nullptr, nullptr, wt, im, rowd, cold,
+                                        sums, nullptr, nloc);
+                    {
+                        constexpr int NCH = (FDN + 31) / 32;
+#pragma unroll
+                        for (int ch = 0; ch < NCH; ch++) {
+                            double s1[32];
+#pragma unroll
+                            for (int i = 0; i < 32; i++)
+                                s1[i] = 32 * ch + i < FDN ? sums[32 * ch + i]
+                                                          : 0.0;
+                            block_sum_to<32>(s1, scratch, sh.tot + 32 * ch);
+                        }
+                    }
+                    if (threadIdx.x == 0) {
+                        // scatter the stamp's nloc x nloc block: local
+                        // parameter l < nsh is global l, local nsh is the
+                        // band's flux
+                        const double *t = sh.tot;
+                        for (int la = 0; la < nloc; la++) {
+                            int ga = la < nsh ? la : nsh + band;
+                            for (int lb = 0; lb <= la; lb++) {
+                                int gb = lb < nsh ? lb : nsh + band;
+                                mu.macc[ga * (ga + 1) / 2 + gb]
+                                    += t[la * (la + 1) / 2 + lb];
+                            }
+                            mu.macc[tri + ga] += t[FD_B0_(FD_MAXP) + la];
+                        }
+                    }
+                } else if (do_deriv) {
                     double sums[NDSUM];
 #pragma unroll
                     for (int i = 0; i < NDSUM; i++) sums[i] = 0.0;
@@ -1658,7 +1741,7 @@ k_lm_fit_multi(LMArgs a) {
                     }
                     if (lane == 0) sh.spec = acc;
                 } else {
-                    feed_jacobian(a, &sh, mu.macc, jstatus, 1, hs);
+                    feed_jacobian(a, &sh, mu.macc, jstatus, MODE == 0, hs);
                 }
                 __syncwarp();
                 if (lane < np) {
@@ -2043,18 +2126,25 @@ static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
     NGX_REQUIRE(jac && guess && res && lm_pars && lm_pars->maxfev > 0);
     NGX_REQUIRE(nrow >= 1 && ncol >= 1 && npsf >= 0 && npsf <= 16);
     NGX_REQUIRE(npsf == 0 || psf_pars);
-    NGX_REQUIRE(nband >= 1 && nband <= (wide ? 7 : 3));
-    NGX_REQUIRE(model == NGX_GAUSS || model == NGX_EXP || model == NGX_DEV);
-    NGX_REQUIRE(lm_pars->analytic_jacobian);
+    const bool simple = model == NGX_GAUSS || model == NGX_EXP
+        || model == NGX_DEV;
+    NGX_REQUIRE(simple || model == NGX_TURB || model == NGX_BDF
+                || model == NGX_BD);
+    // shared parameters: 5 (simple), 6 (bdf), 7 (bd), then a flux per band
+    const int nsh = model_npars(model) - 1;
+    NGX_REQUIRE(nband >= 1 && nband <= 7 && nsh + nband <= LM_MAXP);
+    // forward differences (Fitter.go, fitters.py:93-98): always for the
+    // models without analytic derivatives
+    const bool analytic = simple && lm_pars->analytic_jacobian;
     if (nobj == 0) return NGX_OK;
     LMArgs a;
     memset(&a, 0, sizeof(a));
-    a.n = nobj; a.model = model; a.np = 5 + nband; a.nband = nband;
+    a.n = nobj; a.model = model; a.np = nsh + nband; a.nband = nband;
     a.ngauss0 = model_ngauss(model); a.npsf = npsf;
     a.ngauss = a.ngauss0 * (npsf > 0 ? npsf : 1);
     a.nrow = nrow; a.ncol = ncol; a.ntot = nrow * ncol;
     a.ignore_zero_weight = ignore_zero_weight;
-    a.analytic = 1;
+    a.analytic = analytic;
     if (prior) a.prior = *prior;
     if (a.prior.present) {
         NGX_REQUIRE(a.prior.g_kind == 1);
@@ -2071,19 +2161,27 @@ static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
     a.tpr = (ncol + 7) / 8;
     a.nq = 32 * a.tpr * ((nrow + 3) / 4);
     int nwarps = threads / 32;
+    const int nfd = analytic ? 0 : nsh + 2;     // base + nloc mixtures
     size_t smem = sizeof(double)
-        * ((size_t)a.ngauss * REC + nrow + ncol + 48 * nwarps + LM_MAXP
+        * ((size_t)a.ngauss * REC + (size_t)nfd * a.ngauss * FDREC
+           + (nfd ? 16 : 0) + nrow + ncol + 48 * nwarps + LM_MAXP
            + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
     // the 8-parameter and the 14-parameter solver workspaces are compiled in
     // separate translation units (ngx_lm.cu / ngx_lm_wide.cu)
 #ifdef NGX_LM_WIDE_TU
     NGX_REQUIRE(wide);
-    return config_and_launch(k_lm_fit_multi<3, 2, ngx_lm_result_wide>, a,
+    if (!analytic)
+        return config_and_launch(k_lm_fit_multi<1, 3, 2, ngx_lm_result_wide>,
+                                 a, threads, smem, as_stream(stream));
+    return config_and_launch(k_lm_fit_multi<0, 3, 2, ngx_lm_result_wide>, a,
                              threads, smem, as_stream(stream));
 #else
     NGX_REQUIRE(!wide);
-    return config_and_launch(k_lm_fit_multi<3, 2, ngx_lm_result>, a, threads,
-                             smem, as_stream(stream));
+    if (!analytic)
+        return config_and_launch(k_lm_fit_multi<1, 3, 2, ngx_lm_result>, a,
+                                 threads, smem, as_stream(stream));
+    return config_and_launch(k_lm_fit_multi<0, 3, 2, ngx_lm_result>, a,
+                             threads, smem, as_stream(stream));
 #endif
 }
 
@@ -2238,7 +2336,7 @@ static int lm_fit_multi_host_impl(int nobj, int model,
     DevBuf<double> di(ns * ntot, images), dw(ns * ntot, weights);
     DevBuf<ngx_jacobian> dj(ns, jac);
     DevBuf<double> dp(npsf > 0 ? (size_t)ns * npsf * 6 : 0, psf_pars);
-    DevBuf<double> dg((size_t)nobj * (5 + nband), guess);
+    DevBuf<double> dg((size_t)nobj * (model_npars(model) - 1 + nband), guess);
     DevBuf<RES> dr(nobj);
     NGX_CUDA(dss.err); NGX_CUDA(dsb.err); NGX_CUDA(di.err); NGX_CUDA(dw.err);
     NGX_CUDA(dj.err); NGX_CUDA(dp.err); NGX_CUDA(dg.err); NGX_CUDA(dr.err);
@@ -2263,7 +2361,7 @@ int ngx_lm_fit_multi_host(int nobj, int model, const int32_t *stamp_start,
                           const double *guess, const ngx_prior *prior,
                           const ngx_lm_pars *lm_pars, int ignore_zero_weight,
                           ngx_lm_result *res) {
-    NGX_REQUIRE(nband <= 3);
+    NGX_REQUIRE(nband >= 1);
     return lm_fit_multi_host_impl(nobj, model, stamp_start, stamp_band, nband,
                                   images, weights, jac, nrow, ncol, psf_pars,
                                   npsf, guess, prior, lm_pars,

@@ -121,21 +121,22 @@ def fit_batch(model, images, weights, jacobians, psf_pars, guesses,
 
 def fit_batch_multi(model, stamp_start, stamp_band, nband, images, weights,
                     jacobians, psf_pars, guesses, prior=None, fit_pars=None,
-                    ignore_zero_weight=True):
+                    ignore_zero_weight=True, analytic_jacobian=True):
     """
     Levenberg-Marquardt fits of objects observed in several epochs and/or
     bands (Fitter.go on ObsList / MultiBandObsList, fitting/results.py:
     212-570) in one launch.  Object i owns stamps
     stamp_start[i]:stamp_start[i+1] of the [ns, H, W] stamp arrays, ordered
     band by band; stamp_band [ns] gives each stamp's band; guesses
-    [nobj, 5 + nband] = (cen1, cen2, g1, g2, T, F_0 .. F_{nband-1}).
-    gauss / exp / dev with the analytic Jacobian, nband <= 7 (records with 14
-    parameter slots from 4 bands on).
+    [nobj, nshared + nband] = (cen1, cen2, g1, g2, T, [fracdev | logTratio,
+    fracdev,] F_0 .. F_{nband-1}).  gauss / exp / dev use the analytic
+    Jacobian unless analytic_jacobian=False; bdf, bd and turb always run
+    MINPACK's forward differences, as Fitter.go does.  nband <= 7 and at most
+    14 parameters (records with 14 parameter slots beyond 8 parameters).
     """
     model = get_model_name(get_model_num(model))
-    if model not in SIMPLE_ANALYTIC_MODELS:
-        raise ValueError("multi-epoch fits need a model with an analytic "
-                         "jacobian: %s" % str(SIMPLE_ANALYTIC_MODELS))
+    if model not in _LM_MODELS:
+        raise ValueError("model '%s' cannot be fit with ngx_lm_fit" % model)
     fp = dict(DEFAULT_LM_PARS)
     if fit_pars is not None:
         fp.update(fit_pars)
@@ -150,7 +151,8 @@ def fit_batch_multi(model, stamp_start, stamp_band, nband, images, weights,
                              weights, jacobians, psf_pars, guesses, prior=pr,
                              maxfev=fp["maxfev"], ftol=fp["ftol"],
                              xtol=fp["xtol"],
-                             ignore_zero_weight=ignore_zero_weight)
+                             ignore_zero_weight=ignore_zero_weight,
+                             analytic_jacobian=analytic_jacobian)
 
 
 _ERRMSG = {
@@ -568,13 +570,8 @@ class Fitter(object):
         guess = np.array(guess, dtype="f8")
         assert guess.size == npars, \
             "guess has npars=%d, expected %d" % (guess.size, npars)
-        if self.model_name not in SIMPLE_ANALYTIC_MODELS \
-                or not self.analytic_jacobian:
-            raise NotImplementedError(
-                "multi-epoch / multi-band fits: gauss, exp, dev with the "
-                "analytic jacobian")
-        if nband > 7:
-            raise NotImplementedError("at most 7 bands (12 parameters)")
+        if nband > 7 or npars > 14:
+            raise NotImplementedError("at most 7 bands and 14 parameters")
         stamps = [(b, o) for b, ol in enumerate(mb) for o in ol]
         shape = stamps[0][1].image.shape
         has_psf = stamps[0][1].has_psf_gmix()
@@ -592,14 +589,16 @@ class Fitter(object):
         if has_psf:
             psf_pars = np.stack([o.psf.gmix.get_full_pars().reshape(-1, 6)
                                  for _, o in stamps])
+        nsh = get_model_npars(self.model_name) - 1
         for b in range(nband):
-            make_gmix_model(np.append(guess[:5], guess[5 + b]),
+            make_gmix_model(np.append(guess[:nsh], guess[nsh + b]),
                             self.model_name)
         izw = all(o.ignore_zero_weight for _, o in stamps)
         rec = fit_batch_multi(self.model_name, [0, len(stamps)], bands, nband,
                               images, weights, jac, psf_pars, guess[None],
                               prior=self.prior, fit_pars=self.fit_pars,
-                              ignore_zero_weight=izw)[0]
+                              ignore_zero_weight=izw,
+                              analytic_jacobian=self.analytic_jacobian)[0]
         if rec["flags"] == 1 and rec["nfev"] == 0:
             raise GMixFatalError("no weights > 0")
         res = record_to_result(rec, self.model_name, npars)

@@ -507,8 +507,6 @@ class PriorBDSep(PriorSimpleSep):
         return len(rows)
 
     def to_ngx(self):
-        if self.nband != 1:
-            raise NotImplementedError("bd fits are single band")
         pr = super().to_ngx()
         pr.logTratio = self.logTratio_prior._ngx()
         pr.fracdev = self.fracdev_prior._ngx()

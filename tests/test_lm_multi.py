@@ -212,3 +212,89 @@ def test_gpu_multi_batch_vs_oracle(ngx, ora):
     recs = ngmix.fit_batch_multi("exp", starts, bands, nband, images, weights,
                                  jac, psf, guesses)
     assert recs["flags"][2] == 1 and recs["nfev"][2] == 0
+
+
+def _ngx_prior_fd(c):
+    """the priors of gen_golden.gen_lm_multi_fd"""
+    import ngmix_b200 as ngmix
+    if not c["prior"]:
+        return None
+    pr = ngmix.priors
+    cen, gp = pr.CenPrior(0.0, 0.0, 0.263, 0.263), pr.GPriorBA(0.3)
+    Tp = pr.FlatPrior(-1.0, 1.0e3)
+    Fp = [pr.FlatPrior(-100.0, 1.0e9) for _ in range(c["nband"])]
+    if c["model"] == "bdf":
+        return ngmix.joint_prior.PriorBDFSep(cen, gp, Tp,
+                                             pr.Normal(0.5, 0.1), Fp)
+    if c["model"] == "bd":
+        return ngmix.joint_prior.PriorBDSep(cen, gp, Tp, pr.Normal(0.0, 0.5),
+                                            pr.Normal(0.5, 0.1), Fp)
+    return ngmix.joint_prior.PriorSimpleSep(cen, gp, Tp, Fp)
+
+
+@pytest.mark.gpu
+def test_gpu_multi_fd_matches_reference(ngx):
+    """bdf / bd objects with several stamps and bands (up to 11 parameters)
+    and exp objects with analytic_jacobian=False: the lmdif path of Fitter.go
+    on MultiBandObsList.  The forward-difference quotients carry the 1e-8
+    noise of the model's last bits, so the covariance is compared at 2e-3."""
+    import ngmix_b200 as ngmix
+    g = _golden("lm_multi_fd")
+    nsame = 0
+    ncases = int(g["ncases"])
+    for k in range(ncases):
+        c = _case(g, k)
+        ns = c["images"].shape[0]
+        np_ = NSHARED[c["model"]] + c["nband"]
+        rec = ngmix.fit_batch_multi(
+            c["model"], [0, ns], c["bands"], c["nband"], c["images"],
+            c["weights"], c["jac"], c["psf"], c["guess"][None],
+            prior=_ngx_prior_fd(c), analytic_jacobian=False)[0]
+        assert int(rec["flags"]) == int(c["flags"])
+        nsame += int(int(rec["nfev"]) == int(c["nfev"])
+                     and int(rec["ier"]) == int(c["ier"]))
+        tol = np.maximum(PAR_TOL * np.abs(c["pars"]), 2e-2 * c["pars_err"])
+        assert np.all(np.abs(rec["pars"][:np_] - c["pars"]) <= tol)
+        assert int(rec["npix"]) == int(c["npix"])
+        assert abs(float(rec["lnprob"]) - float(c["lnprob"])) \
+            <= 1e-5 * abs(float(c["lnprob"]))
+        assert abs(float(rec["flux"]) - float(c["flux"][0])) \
+            <= 1e-4 * abs(float(c["flux"][0]))
+        cov = np.asarray(rec["pars_cov"][:np_ * np_]).reshape(np_, np_)
+        sc = np.sqrt(np.outer(np.diag(c["pars_cov"]), np.diag(c["pars_cov"])))
+        assert np.abs(cov - c["pars_cov"]).max() <= 2e-3 * sc.max()
+    # evaluation counts follow the reference up to forward-difference noise
+    assert nsame >= ncases - 2
+
+
+@pytest.mark.gpu
+def test_gpu_fitter_go_mbobs_bdf(ngx):
+    """Fitter(model='bdf', prior=PriorBDFSep with a flux prior per band).go on
+    a MultiBandObsList"""
+    import ngmix_b200 as ngmix
+    g = _golden("lm_multi_fd")
+    c = _case(g, 4)         # bdf, 3 bands, 4 stamps
+    mbobs = ngmix.MultiBandObsList()
+    i = 0
+    for b in range(c["nband"]):
+        ol = ngmix.ObsList()
+        while i < c["bands"].size and c["bands"][i] == b:
+            j = c["jac"][i]
+            jac = ngmix.Jacobian(row=j[0], col=j[1], dvdrow=j[2], dvdcol=j[3],
+                                 dudrow=j[4], dudcol=j[5])
+            psf_obs = ngmix.Observation(
+                np.zeros((5, 5)) + 1.0,
+                gmix=ngmix.GMix(pars=c["psf"][i].ravel()))
+            ol.append(ngmix.Observation(c["images"][i], weight=c["weights"][i],
+                                        jacobian=jac, psf=psf_obs))
+            i += 1
+        mbobs.append(ol)
+    res = ngmix.Fitter(model="bdf", prior=_ngx_prior_fd(c)).go(
+        obs=mbobs, guess=c["guess"])
+    assert res["flags"] == 0 and res["pars"].size == 9
+    assert np.allclose(res["pars"], c["pars"], rtol=1e-5,
+                       atol=2e-2 * c["pars_err"].max())
+    assert np.allclose(res["flux"], c["flux"], rtol=1e-4)
+    assert res["flux_cov"].shape == (3, 3)
+    gm = res.get_convolved_gmix(band=2, obsnum=0)
+    assert gm.get_data().size == 48
