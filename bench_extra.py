@@ -103,6 +103,16 @@ def bench_multi(args, _lib, sims, torch, dev):
     recs = ngmix.fit_batch_multi("exp", starts, bands, 2, b["images"],
                                  b["weights"], b["jac"], b["psf"], guesses)
     dt = time.perf_counter() - t1
+    # the same call from page-locked host arrays (ngmix_b200.pinned_copy):
+    # pageable copies run at ~10 GB/s and bound the call above
+    pim, pwt = ngmix.pinned_copy(b["images"]), ngmix.pinned_copy(b["weights"])
+    ngmix.fit_batch_multi("exp", starts, bands, 2, pim, pwt, b["jac"],
+                          b["psf"], guesses)
+    t2 = time.perf_counter()
+    ngmix.fit_batch_multi("exp", starts, bands, 2, pim, pwt, b["jac"],
+                          b["psf"], guesses)
+    dt_pinned = time.perf_counter() - t2
+    del pim, pwt
     # device-resident timing of the same workload
     tt = {k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev)
           for k in ("images", "weights", "jac", "psf")}
@@ -135,6 +145,7 @@ def bench_multi(args, _lib, sims, torch, dev):
          "objects_per_s": nobj / (ms * 1e-3),
          "stamps_per_s": 4 * nobj / (ms * 1e-3), "ms_per_step": ms,
          "host_call_objects_per_s": nobj / dt,
+         "host_call_pinned_objects_per_s": nobj / dt_pinned,
          "median_nfev": float(np.median(recs["nfev"]))}
     if not args.no_cpu:
         import oracle

@@ -404,6 +404,19 @@ int ngx_template_flux(int nobj, const int32_t *stamp_start,
                       int ignore_zero_weight, ngx_flux_result *res,
                       void *stream);
 
+/* the same with pixel templates [ns, nrow, ncol] in place of mixtures
+ * (obs.psf.template / obs.template, results.py:834-864) */
+int ngx_template_flux_images(int nobj, const int32_t *stamp_start,
+                             const double *images, const double *weights,
+                             const double *templates, int nrow, int ncol,
+                             int normalize, int ignore_zero_weight,
+                             ngx_flux_result *res, void *stream);
+int ngx_template_flux_images_host(int nobj, const int32_t *stamp_start,
+                                  const double *images, const double *weights,
+                                  const double *templates, int nrow, int ncol,
+                                  int normalize, int ignore_zero_weight,
+                                  ngx_flux_result *res);
+
 /* ------------------------------------------------------------------ */
 /* The production chain in one device pass (bootstrap.py:43-102 with
  * PSFRunner(EMFitter, GMixPSFGuesser(ngauss), ntry) and Runner(Fitter(model),

@@ -136,6 +136,7 @@ SYMBOLS = [
     "ngx_host_alloc", "ngx_host_free", "ngx_host_register",
     "ngx_host_unregister", "ngx_bootstrap", "ngx_bootstrap_workspace_bytes",
     "ngx_chain_draws", "ngx_em_todo", "ngx_lm_fit_todo",
+    "ngx_template_flux_images", "ngx_template_flux_images_host",
     "ngx_lm_fit_multi_wide", "ngx_lm_fit_multi_wide_host",
     "ngx_lm_fit_coellip", "ngx_lm_fit_coellip_host",
 ]
@@ -757,6 +758,25 @@ def template_flux(stamp_start, images, weights, jac, gm_pars, normalize=True,
         C.c_int(nobj), _p(stamp_start), _p(images), _p(weights), _p(jac),
         C.c_int(H), C.c_int(W), _p(gm_pars), C.c_int(gm_pars.shape[1]),
         C.c_int(int(normalize)), C.c_int(int(ignore_zero_weight)), _p(res)))
+    return res
+
+
+def template_flux_images(stamp_start, images, weights, templates,
+                         normalize=True, ignore_zero_weight=True):
+    """batched PSFFluxFitModel.go with pixel templates [ns, H, W]"""
+    init()
+    images, weights, templates = _f8(images), _f8(weights), _f8(templates)
+    ns, H, W = images.shape
+    if templates.shape != images.shape or weights.shape != images.shape:
+        raise ValueError("images, weights and templates differ in shape")
+    stamp_start = np.ascontiguousarray(stamp_start, dtype="i4")
+    nobj = stamp_start.size - 1
+    assert stamp_start[0] == 0 and stamp_start[-1] == ns
+    res = np.zeros(nobj, dtype=FLUX_RESULT_DTYPE)
+    check(lib().ngx_template_flux_images_host(
+        C.c_int(nobj), _p(stamp_start), _p(images), _p(weights),
+        _p(templates), C.c_int(H), C.c_int(W), C.c_int(int(normalize)),
+        C.c_int(int(ignore_zero_weight)), _p(res)))
     return res
 
 

@@ -2332,21 +2332,97 @@ static int lm_fit_multi_host_impl(int nobj, int model,
     const int ns = stamp_start[nobj];
     NGX_REQUIRE(ns >= 0 && stamp_start[0] == 0);
     const size_t ntot = (size_t)nrow * ncol;
-    DevBuf<int32_t> dss(nobj + 1, stamp_start), dsb(ns, stamp_band);
-    DevBuf<double> di(ns * ntot, images), dw(ns * ntot, weights);
-    DevBuf<ngx_jacobian> dj(ns, jac);
-    DevBuf<double> dp(npsf > 0 ? (size_t)ns * npsf * 6 : 0, psf_pars);
-    DevBuf<double> dg((size_t)nobj * (model_npars(model) - 1 + nband), guess);
-    DevBuf<RES> dr(nobj);
-    NGX_CUDA(dss.err); NGX_CUDA(dsb.err); NGX_CUDA(di.err); NGX_CUDA(dw.err);
-    NGX_CUDA(dj.err); NGX_CUDA(dp.err); NGX_CUDA(dg.err); NGX_CUDA(dr.err);
-    int rc = lm_fit_multi_impl(nobj, model, dss.d, dsb.d, nband, di.d, dw.d,
-                               dj.d, nrow, ncol, npsf > 0 ? dp.d : nullptr,
-                               npsf, dg.d, prior, lm_pars, ignore_zero_weight,
-                               dr.d, wide, 0);
-    if (rc) return rc;
-    NGX_CUDA(cudaDeviceSynchronize());
-    NGX_CUDA(dr.to_host(res));
+    const int np = model_npars(model) - 1 + nband;
+    // chunks of objects, double buffered: the copy of chunk c + 1 runs while
+    // chunk c is fitted (one unpipelined copy of the whole batch was 8x
+    // slower than the kernel: 38k vs 314k objects/s on 2 bands x 2 epochs)
+    int chunk = 4 * sm_count();
+    if (chunk > nobj) chunk = nobj;
+    size_t max_st = 0;          // most stamps in any chunk
+    for (int lo = 0; lo < nobj; lo += chunk) {
+        int hi = lo + chunk < nobj ? lo + chunk : nobj;
+        size_t m = (size_t)(stamp_start[hi] - stamp_start[lo]);
+        if (m > max_st) max_st = m;
+    }
+    cudaStream_t st[2];
+    NGX_CUDA(cudaStreamCreate(&st[0]));
+    NGX_CUDA(cudaStreamCreate(&st[1]));
+    int rc = NGX_OK;
+    {
+        DevBuf<int32_t> dss0(chunk + 1), dss1(chunk + 1);
+        DevBuf<int32_t> dsb0(max_st), dsb1(max_st);
+        DevBuf<double> di0(max_st * ntot), di1(max_st * ntot);
+        DevBuf<double> dw0(max_st * ntot), dw1(max_st * ntot);
+        DevBuf<ngx_jacobian> dj0(max_st), dj1(max_st);
+        const size_t npf = npsf > 0 ? (size_t)npsf * 6 : 0;
+        DevBuf<double> dp0(max_st * npf), dp1(max_st * npf);
+        DevBuf<double> dg0((size_t)chunk * np), dg1((size_t)chunk * np);
+        DevBuf<RES> dr0(chunk), dr1(chunk);
+        cudaError_t e = dss0.err;
+        for (cudaError_t x : {dss1.err, dsb0.err, dsb1.err, di0.err, di1.err,
+                              dw0.err, dw1.err, dj0.err, dj1.err, dp0.err,
+                              dp1.err, dg0.err, dg1.err, dr0.err, dr1.err})
+            if (e == cudaSuccess) e = x;
+        if (e != cudaSuccess) {
+            cudaStreamDestroy(st[0]); cudaStreamDestroy(st[1]);
+            NGX_CUDA(e);
+        }
+        std::vector<int32_t> rebased[2];
+        for (int lo = 0, c = 0; lo < nobj && rc == NGX_OK; lo += chunk, c++) {
+            const int b = c & 1;
+            const int hi = lo + chunk < nobj ? lo + chunk : nobj;
+            const int cn = hi - lo;
+            const int s0 = stamp_start[lo];
+            const size_t m = (size_t)(stamp_start[hi] - s0);
+            cudaStream_t q = st[b];
+            int32_t *dss = b ? dss1.d : dss0.d, *dsb = b ? dsb1.d : dsb0.d;
+            double *di = b ? di1.d : di0.d, *dw = b ? dw1.d : dw0.d;
+            ngx_jacobian *dj = b ? dj1.d : dj0.d;
+            double *dp = b ? dp1.d : dp0.d, *dg = b ? dg1.d : dg0.d;
+            RES *dr = b ? dr1.d : dr0.d;
+            // the rebased starts live in a host vector reused every second
+            // chunk: wait for its previous copy before overwriting
+            // (buffer set b was last used by chunk c - 2 on the same stream)
+            cudaStreamSynchronize(q);
+            rebased[b].resize(cn + 1);
+            for (int i = 0; i <= cn; i++)
+                rebased[b][i] = stamp_start[lo + i] - s0;
+            cudaMemcpyAsync(dss, rebased[b].data(), sizeof(int32_t) * (cn + 1),
+                            cudaMemcpyHostToDevice, q);
+            cudaMemcpyAsync(dsb, stamp_band + s0, sizeof(int32_t) * m,
+                            cudaMemcpyHostToDevice, q);
+            cudaMemcpyAsync(di, images + (size_t)s0 * ntot,
+                            sizeof(double) * m * ntot, cudaMemcpyHostToDevice,
+                            q);
+            cudaMemcpyAsync(dw, weights + (size_t)s0 * ntot,
+                            sizeof(double) * m * ntot, cudaMemcpyHostToDevice,
+                            q);
+            cudaMemcpyAsync(dj, jac + s0, sizeof(ngx_jacobian) * m,
+                            cudaMemcpyHostToDevice, q);
+            if (npf)
+                cudaMemcpyAsync(dp, psf_pars + (size_t)s0 * npf,
+                                sizeof(double) * m * npf,
+                                cudaMemcpyHostToDevice, q);
+            cudaMemcpyAsync(dg, guess + (size_t)lo * np,
+                            sizeof(double) * (size_t)cn * np,
+                            cudaMemcpyHostToDevice, q);
+            rc = lm_fit_multi_impl(cn, model, dss, dsb, nband, di, dw, dj,
+                                   nrow, ncol, npf ? dp : nullptr, npsf, dg,
+                                   prior, lm_pars, ignore_zero_weight, dr,
+                                   wide, q);
+            if (rc == NGX_OK)
+                cudaMemcpyAsync(res + lo, dr, sizeof(RES) * cn,
+                                cudaMemcpyDeviceToHost, q);
+        }
+        cudaError_t e0 = cudaStreamSynchronize(st[0]);
+        cudaError_t e1 = cudaStreamSynchronize(st[1]);
+        cudaStreamDestroy(st[0]);
+        cudaStreamDestroy(st[1]);
+        if (rc) return rc;
+        NGX_CUDA(e0);
+        NGX_CUDA(e1);
+        NGX_CUDA(cudaGetLastError());
+    }
     return NGX_OK;
 }
 

@@ -340,11 +340,141 @@ k_template_flux(const int32_t *__restrict__ stamp_start,
     }
 }
 
+// the same with pixel templates instead of mixtures (PSFFluxFitModel with
+// obs.psf.template / obs.template, results.py:758-767, 834-864): the model of
+// a stamp is its template image, normalised to unit sum when asked
+// (`template *= 1 / template.sum()`), and in the second pass
+// `template * (norm * flux) / template.sum()`.
+__global__ void __launch_bounds__(128)
+k_template_flux_images(const int32_t *__restrict__ stamp_start,
+                       const double *__restrict__ images,
+                       const double *__restrict__ weights,
+                       const double *__restrict__ templates, int nrow,
+                       int ncol, int normalize, int ignore_zero_weight,
+                       ngx_flux_result *__restrict__ res) {
+    __shared__ double tot[8];
+    __shared__ double scratch[32 * 4];
+    __shared__ double flux_s;
+    const int obj = blockIdx.x;
+    const int s0 = stamp_start[obj], s1 = stamp_start[obj + 1];
+    const int ntot = nrow * ncol;
+    double xcorr = 0.0, msq = 0.0, chi2 = 0.0, totpix = 0.0, effpix = 0.0;
+    for (int ipass = 1; ipass <= 2; ipass++) {
+        for (int e = s0; e < s1; e++) {
+            const double *im = images + (size_t)e * ntot;
+            const double *wt = weights + (size_t)e * ntot;
+            const double *tp = templates + (size_t)e * ntot;
+            // template.sum(), then the sum of the normalised template
+            double a1[1] = {0.0};
+            for (int p = threadIdx.x; p < ntot; p += blockDim.x) a1[0] += tp[p];
+            block_sum_to<1>(a1, scratch, tot);
+            const double tsum = tot[0];
+            const double s1n = normalize ? 1.0 / tsum : 1.0;
+            const double norm = normalize ? 1.0 : tsum;
+            __syncthreads();
+            a1[0] = 0.0;
+            for (int p = threadIdx.x; p < ntot; p += blockDim.x)
+                a1[0] += tp[p] * s1n;
+            block_sum_to<1>(a1, scratch, tot);
+            const double msum = tot[0];
+            __syncthreads();
+            const double s2 = ipass == 2 ? (norm * flux_s) / msum : 1.0;
+            double acc[5] = {0, 0, 0, 0, 0};
+            for (int p = threadIdx.x; p < ntot; p += blockDim.x) {
+                double model = tp[p] * s1n;
+                if (ipass == 2) model *= s2;
+                double d = im[p], w = wt[p];
+                if (ipass == 1) {
+                    acc[0] += model * d * w;
+                    acc[1] += model * model * w;
+                    if (!(ignore_zero_weight && w <= 0.0)) acc[2] += 1.0;
+                    if (w > 0) acc[3] += 1.0;
+                } else {
+                    double diff = model - d;
+                    acc[4] += diff * diff * w;
+                }
+            }
+            block_sum_to<5>(acc, scratch, tot);
+            xcorr += tot[0]; msq += tot[1];
+            totpix += tot[2]; effpix += tot[3];
+            chi2 += tot[4];
+            __syncthreads();
+        }
+        if (ipass == 1) {
+            if (msq == 0) break;
+            if (threadIdx.x == 0) flux_s = xcorr / msq;
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        ngx_flux_result r;
+        r.pad = 0;
+        int flags = 0;
+        double flux = -9.999e9, flux_err = 9.999e9;
+        if (msq != 0) flux = xcorr / msq;
+        double dof = effpix - 1;
+        if (dof <= 0) dof = 1.0e-6;
+        r.chi2per = chi2 / dof;
+        r.dof = dof;
+        if (msq == 0 || totpix == 1) {
+            flags |= 1 << 14;               // DIV_ZERO
+        } else {
+            double arg = chi2 / msq / (totpix - 1);
+            if (arg >= 0.0) flux_err = sqrt(arg);
+            else flags |= 1 << 6;           // BAD_VAR
+        }
+        r.flags = flags;
+        r.flux = flux;
+        r.flux_err = flux_err;
+        res[obj] = r;
+    }
+}
+
 }  // namespace ngx
 
 using namespace ngx;
 
 extern "C" {
+
+int ngx_template_flux_images(int nobj, const int32_t *stamp_start,
+                             const double *images, const double *weights,
+                             const double *templates, int nrow, int ncol,
+                             int normalize, int ignore_zero_weight,
+                             ngx_flux_result *res, void *stream) {
+    NGX_REQUIRE(nobj >= 0 && stamp_start && images && weights && templates);
+    NGX_REQUIRE(res && nrow >= 1 && ncol >= 1);
+    if (nobj == 0) return NGX_OK;
+    k_template_flux_images<<<nobj, 128, 0, as_stream(stream)>>>(
+        stamp_start, images, weights, templates, nrow, ncol, normalize,
+        ignore_zero_weight, res);
+    NGX_LAUNCH_CHECK();
+    return NGX_OK;
+}
+
+int ngx_template_flux_images_host(int nobj, const int32_t *stamp_start,
+                                  const double *images, const double *weights,
+                                  const double *templates, int nrow, int ncol,
+                                  int normalize, int ignore_zero_weight,
+                                  ngx_flux_result *res) {
+    NGX_REQUIRE(nobj >= 0 && stamp_start && images && weights && templates);
+    NGX_REQUIRE(res);
+    if (nobj == 0) return NGX_OK;
+    const int ns = stamp_start[nobj];
+    const size_t ntot = (size_t)nrow * ncol;
+    DevBuf<int32_t> dss(nobj + 1, stamp_start);
+    DevBuf<double> di(ns * ntot, images), dw(ns * ntot, weights);
+    DevBuf<double> dt(ns * ntot, templates);
+    DevBuf<ngx_flux_result> dr(nobj);
+    NGX_CUDA(dss.err); NGX_CUDA(di.err); NGX_CUDA(dw.err); NGX_CUDA(dt.err);
+    NGX_CUDA(dr.err);
+    int rc = ngx_template_flux_images(nobj, dss.d, di.d, dw.d, dt.d, nrow,
+                                      ncol, normalize, ignore_zero_weight,
+                                      dr.d, 0);
+    if (rc) return rc;
+    NGX_CUDA(cudaDeviceSynchronize());
+    NGX_CUDA(dr.to_host(res));
+    return NGX_OK;
+}
 
 int ngx_weighted_sums(int n, int ngauss, const ngx_gauss *gmix,
                       const double *images, const double *weights,

@@ -453,7 +453,8 @@ class PSFFluxFitter(object):
     Template flux by zero-lag cross-correlation (fitting/fitters.py:144-181,
     results.py:676-805) through ngx_template_flux: with do_psf the psf
     mixtures of the observation(s) are the templates ("psf flux"), otherwise
-    the observations' own mixtures.  Pixel templates are not supported.
+    the observations' own mixtures; without a mixture the pixel template
+    (obs.psf.template / obs.template) is used (ngx_template_flux_images).
     """
 
     def __init__(self, do_psf=True, normalize_psf=True):
@@ -468,6 +469,12 @@ class PSFFluxFitter(object):
             obslist = list(obs)
         else:
             raise ValueError("obs should be Observation or ObsList")
+        first = obslist[0].psf if self.do_psf else obslist[0]
+        if not first.has_gmix():
+            # pixel templates (results.py:834-864)
+            if getattr(first, "template", None) is None:
+                raise ValueError("neither gmix or template image are set")
+            return self._go_templates(obslist)
         gms = []
         for o in obslist:
             src = o.psf if self.do_psf else o
@@ -494,6 +501,30 @@ class PSFFluxFitter(object):
                 "chi2per": float(rec["chi2per"]), "dof": float(rec["dof"]),
                 "flux": float(rec["flux"]),
                 "flux_err": float(rec["flux_err"])}
+
+
+def _psfflux_go_templates(self, obslist):
+    """PSFFluxFitModel with pixel templates: obs.psf.template (do_psf) or
+    obs.template, through ngx_template_flux_images"""
+    tps = [np.asarray((o.psf if self.do_psf else o).template, dtype="f8")
+           for o in obslist]
+    shape = obslist[0].image.shape
+    if any(o.image.shape != shape for o in obslist) \
+            or any(t.shape != shape for t in tps):
+        raise NotImplementedError(
+            "all stamps and templates must share their size")
+    normalize = self.normalize_psf if self.do_psf else True
+    rec = _lib.template_flux_images(
+        [0, len(obslist)], np.stack([o.image for o in obslist]),
+        np.stack([o.weight for o in obslist]), np.stack(tps),
+        normalize=normalize,
+        ignore_zero_weight=all(o.ignore_zero_weight for o in obslist))[0]
+    return {"model": "template", "flags": int(rec["flags"]),
+            "chi2per": float(rec["chi2per"]), "dof": float(rec["dof"]),
+            "flux": float(rec["flux"]), "flux_err": float(rec["flux_err"])}
+
+
+PSFFluxFitter._go_templates = _psfflux_go_templates
 
 
 class Fitter(object):

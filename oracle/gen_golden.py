@@ -1505,6 +1505,55 @@ def gen_lm_multi_fd():
     save("lm_multi_fd", **out)
 
 
+def gen_psfflux_template():
+    """PSFFluxFitter.go with pixel templates (obs.psf.template / obs.template,
+    fitting/results.py:834-864) on single observations and ObsLists"""
+    from ngmix.fitting import PSFFluxFitter
+    b = sims.make_lm_batch(8, seed0=9450, noise=0.05, dims=(24, 24))
+    rng = np.random.RandomState(95)
+    b["weights"][1][rng.uniform(size=b["weights"][1].shape) < 0.2] = 0.0
+    # psf templates: the psf mixture rendered on the object's own grid
+    templates = np.zeros_like(b["images"])
+    for i in range(8):
+        gm = ngmix.GMix(pars=b["psf"][i].ravel())
+        templates[i] = gm.make_image((24, 24),
+                                     jacobian=jac_from_record(b["jac"][i]))
+        templates[i] *= rng.uniform(0.5, 2.0)
+    out = {k: b[k] for k in ("images", "weights", "jac")}
+    out["templates"] = templates
+    groups = [[0], [1], [2, 3, 4], [5, 6, 7]]
+    out["ngroups"] = np.array(len(groups))
+    for do_psf in (True, False):
+        for normalize in (True, False):
+            tag = "p%d_n%d_" % (int(do_psf), int(normalize))
+            res = {k: np.zeros(len(groups)) for k in
+                   ("flags", "flux", "flux_err", "chi2per", "dof")}
+            for ig, grp in enumerate(groups):
+                ol = ngmix.ObsList()
+                for i in grp:
+                    obs = ngmix.Observation(
+                        b["images"][i], weight=b["weights"][i],
+                        jacobian=jac_from_record(b["jac"][i]))
+                    if do_psf:
+                        psf_obs = ngmix.Observation(np.zeros((5, 5)) + 1.0)
+                        psf_obs.template = templates[i]
+                        obs.set_psf(psf_obs)
+                    else:
+                        obs.template = templates[i]
+                    ol.append(obs)
+                obs_in = ol if len(grp) > 1 else ol[0]
+                r = PSFFluxFitter(do_psf=do_psf,
+                                  normalize_psf=normalize).go(obs=obs_in)
+                for k in res:
+                    res[k][ig] = r[k]
+            for k, v in res.items():
+                out[tag + k] = v
+            print(tag, res["flux"], res["flags"])
+    for ig, grp in enumerate(groups):
+        out["g%d" % ig] = np.array(grp)
+    save("psfflux_template", **out)
+
+
 GENERATORS = {
     "fastexp": gen_fastexp,
     "gmix": gen_gmix,
@@ -1528,6 +1577,7 @@ GENERATORS = {
     "boot": gen_boot,
     "lm_bounds": gen_lm_bounds,
     "lm_multi_fd": gen_lm_multi_fd,
+    "psfflux_template": gen_psfflux_template,
 }
 
 if __name__ == "__main__":

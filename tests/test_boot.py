@@ -190,3 +190,37 @@ def test_gpu_bootstrap_failed_psf(ngx):
                     guesser=ngmix.guessers.TFluxGuesser(rng, 0.3, 100.0))
     with pytest.raises(ngmix.gexceptions.BootPSFFailure):
         bootstrap(obs, runner, psf_runner=psf_runner)
+
+
+@pytest.mark.gpu
+def test_gpu_psf_flux_fitter_pixel_templates(ngx):
+    """PSFFluxFitter with pixel templates (obs.psf.template / obs.template,
+    fitting/results.py:834-864) against the reference's fluxes"""
+    import ngmix_b200 as ng
+    g = _load("psfflux_template")
+    for do_psf in (True, False):
+        for normalize in (True, False):
+            tag = "p%d_n%d_" % (int(do_psf), int(normalize))
+            for ig in range(int(g["ngroups"])):
+                ol = ng.ObsList()
+                for i in g["g%d" % ig]:
+                    rec = g["jac"][i]
+                    jac = ng.Jacobian(row=rec[0], col=rec[1], dvdrow=rec[2],
+                                      dvdcol=rec[3], dudrow=rec[4],
+                                      dudcol=rec[5])
+                    obs = ng.Observation(g["images"][i],
+                                         weight=g["weights"][i], jacobian=jac)
+                    if do_psf:
+                        psf_obs = ng.Observation(np.zeros((5, 5)) + 1.0)
+                        psf_obs.template = g["templates"][i]
+                        obs.set_psf(psf_obs)
+                    else:
+                        obs.template = g["templates"][i]
+                    ol.append(obs)
+                obs_in = ol if len(ol) > 1 else ol[0]
+                r = ng.PSFFluxFitter(do_psf=do_psf,
+                                     normalize_psf=normalize).go(obs=obs_in)
+                assert r["flags"] == int(g[tag + "flags"][ig])
+                for k in ("flux", "flux_err", "chi2per", "dof"):
+                    assert abs(r[k] - g[tag + k][ig]) \
+                        <= 1e-11 * abs(g[tag + k][ig]), (tag, ig, k)
