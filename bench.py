@@ -580,17 +580,23 @@ def main():
         "fit_stats": {"median_nfev": float(np.median(nfev)),
                       "median_njev": float(np.median(njev)),
                       "nonzero_flags": nflag},
-        "e2e": {"value": world * nobj * args.steps / e2e_s,
-                "unit": "fits/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h,
-                "api": "ngmix_b200._lib.lm_fit -> ngx_lm_fit_host (pinned "
-                       "host buffers, chunked H2D overlapped with the fit)"},
-        "e2e_f32_stamps": {
+        # the end-to-end headline: the public call with the stamps in the
+        # dtype survey pixels have (float32 images and weight maps, pinned
+        # host memory); results are bit-identical to the float64 call
+        "e2e": {
             "value": world * nobj * args.steps / e2e32_s, "unit": "fits/s",
             "h2d_bytes_per_step": int(h2d - h_images.numel() * 8),
             "d2h_bytes_per_step": d2h,
-            "api": "ngx_lm_fit_host_f32: the same stamps held as float32 on "
-                   "the host (bit-identical results), widened on the device"},
+            "api": "ngmix_b200._lib.lm_fit on float32 host stamps -> "
+                   "ngx_lm_fit_host_f32 (pinned host buffers, chunked H2D "
+                   "overlapped with the fits, widened on the device: "
+                   "bit-identical to the float64 call)"},
+        "e2e_f64_stamps": {
+            "value": world * nobj * args.steps / e2e_s,
+            "unit": "fits/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h,
+            "api": "ngx_lm_fit_host: the same stamps held as float64 on the "
+                   "host (the reference's in-memory dtype): PCIe-bound"},
         "e2e_compact": {
             "value": world * nobj * args.steps / e2ec_s, "unit": "fits/s",
             "h2d_bytes_per_step": int(h2d - h_images.numel() * 12

@@ -85,7 +85,7 @@ __device__ __forceinline__ void em_build_conv(EMShared *sh, int ngauss,
 // live in a global scratch buffer instead of shared memory, for stamps too
 // large to be resident; the arithmetic is the same.
 template <int VARIANT, int NG, bool GM = false>
-__global__ void __launch_bounds__(NGX_EM_TILE)
+__global__ void __launch_bounds__(NGX_EM_TILE, GM ? 1 : 10)
 k_em(int n, const double *__restrict__ images,
      const double *__restrict__ weights, const ngx_jacobian *__restrict__ jac,
      int nrow, int ncol, const double *__restrict__ guess, int ngauss_in,
@@ -115,12 +115,18 @@ k_em(int n, const double *__restrict__ images,
         stamp_arrays = gscratch
             + (size_t)stamp * (3 * (size_t)ntot + ((size_t)ntot + 7) / 8);
     double *val = stamp_arrays;         // ntot
-    double *pv = val + ntot;            // ntot: pixel v (fixed for the fit)
-    double *pu = pv + ntot;             // ntot: pixel u
+    // pixel coordinates: cached per stamp only in the global-scratch variant.
+    // With the stamp in shared memory they are recomputed from (row, col)
+    // with the reference's formula (jacobian_nb.py:4-16, ~10 instructions per
+    // pixel and iteration): 16 bytes per pixel less shared memory let 10
+    // instead of 7 CTAs share an SM, and the kernel is bound by the latency
+    // of its dependent chains, not by instruction count.
+    double *pv = val + ntot;            // ntot (GM only)
+    double *pu = pv + ntot;             // ntot (GM only)
     // per pixel: 255 excluded, 0 zero weight (filled each iteration), 1 normal
     unsigned char *code_g = (unsigned char *)(pu + ntot);
     ngx_gauss *conv_d = (ngx_gauss *)(
-        GM ? contrib + (size_t)nslots * NGX_EM_STRIDE : pu + ntot);  // nconv
+        GM ? contrib + (size_t)nslots * NGX_EM_STRIDE : val + ntot);  // nconv
     double *logtau_d = (double *)(conv_d + nconv);            // nconv
     double *logdet_d = logtau_d + nconv;                      // nconv
     unsigned char *code = GM ? code_g
@@ -183,12 +189,18 @@ k_em(int n, const double *__restrict__ images,
     __syncthreads();
     // pixel coordinates, jacobian_nb.py:4-16 (they do not change during the
     // iterations)
-    for (int p = threadIdx.x; p < ntot; p += T) {
-        int row = p / ncol, col = p - row * ncol;
-        double rowdiff = row - sh.jac.row0, coldiff = col - sh.jac.col0;
-        pv[p] = sh.jac.dvdrow * rowdiff + sh.jac.dvdcol * coldiff;
-        pu[p] = sh.jac.dudrow * rowdiff + sh.jac.dudcol * coldiff;
+    if (GM) {
+        for (int p = threadIdx.x; p < ntot; p += T) {
+            int row = p / ncol, col = p - row * ncol;
+            double rowdiff = row - sh.jac.row0, coldiff = col - sh.jac.col0;
+            pv[p] = sh.jac.dvdrow * rowdiff + sh.jac.dvdcol * coldiff;
+            pu[p] = sh.jac.dudrow * rowdiff + sh.jac.dudcol * coldiff;
+        }
     }
+    // (row, col) of this thread's pixel in the first tile
+    const int row_first = (int)threadIdx.x / ncol;
+    const int col_first = (int)threadIdx.x - row_first * ncol;
+    const ngx_jacobian jc = sh.jac;
     if (threadIdx.x == 0) {
         double a = fmin(sh.mn[0], sh.mn[1]), b = fmax(sh.mx[0], sh.mx[1]);
         sh.npix = sh.cnt[0] + sh.cnt[1];
@@ -251,7 +263,15 @@ k_em(int n, const double *__restrict__ images,
             // fill_zero_weight_pixels, em_nb.py:1297-1315 (apodized eval)
             for (int p = threadIdx.x; p < ntot; p += T) {
                 if (code[p] == 0) {
-                    double v = pv[p], u = pu[p];
+                    double v, u;
+                    if (GM) {
+                        v = pv[p]; u = pu[p];
+                    } else {
+                        int row = p / ncol, col = p - row * ncol;
+                        double rowdiff = row - jc.row0, coldiff = col - jc.col0;
+                        v = jc.dvdrow * rowdiff + jc.dvdcol * coldiff;
+                        u = jc.dudrow * rowdiff + jc.dudcol * coldiff;
+                    }
                     double s = 0.0;
                     for (int k = 0; k < ngauss * npsf; k++) {
                         const ngx_gauss &g = sh.conv[k];
@@ -275,14 +295,25 @@ k_em(int n, const double *__restrict__ images,
         double acc = 0.0;          // thread s accumulates slot s
         __syncthreads();
 
+        int prow = row_first, pcol = col_first;
         for (int base = 0; base < ntot; base += T) {
             // ---- phase A: one pixel per thread, reference operation order
             int p = base + threadIdx.x;
             bool valid = (p < ntot) && (code[p] != 255);
             int bad = 0;
             double *cme = contrib + threadIdx.x;
+            double v, u;
+            if (GM) {
+                v = p < ntot ? pv[p] : 0.0;
+                u = p < ntot ? pu[p] : 0.0;
+            } else {
+                double rowdiff = prow - jc.row0, coldiff = pcol - jc.col0;
+                v = jc.dvdrow * rowdiff + jc.dvdcol * coldiff;
+                u = jc.dudrow * rowdiff + jc.dudcol * coldiff;
+                pcol += T;
+                while (pcol >= ncol) { pcol -= ncol; prow++; }
+            }
             if (valid) {
-                double v = pv[p], u = pu[p];
                 double gsum = 0.0, logL = 0.0;
                 double cg[NG > 0 ? NG : 1][6];
 #pragma unroll
@@ -743,7 +774,7 @@ static int launch_em(int n, const double *images, const double *weights,
     int nslots = 6 * ngauss + 2;
     int nconv = ngauss * (npsf > 0 ? npsf : 1);
     size_t smem = sizeof(double)
-        * (3 * (size_t)ntot + (size_t)nslots * NGX_EM_STRIDE + 2 * nconv)
+        * ((size_t)ntot + (size_t)nslots * NGX_EM_STRIDE + 2 * nconv)
         + sizeof(ngx_gauss) * (size_t)nconv + (size_t)ntot + 16;
     if (smem > (size_t)smem_optin_bytes()) {
         // stamp-sized arrays in a stream-ordered global scratch buffer,

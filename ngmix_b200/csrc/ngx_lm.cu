@@ -2495,7 +2495,12 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
     // first chunk (one wave of CTAs, ~20 MB) and then chunks of two waves,
     // whose fit (~0.6 ms) hides behind the next chunk's copy (~0.8 ms)
     const int wave = 4 * sm_count();
-    int chunk = 2 * wave;
+    int waves = 2;
+    if (const char *e = getenv("NGX_CHUNK_WAVES")) {
+        int w = atoi(e);
+        if (w >= 1 && w <= 64) waves = w;
+    }
+    int chunk = waves * wave;
     if (chunk > n) chunk = n;
     int first_chunk = wave < chunk ? wave : chunk;
     static thread_local double *d_im[2] = {nullptr, nullptr};
