@@ -38,6 +38,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = [None]      # set when stdout is redirected (multi-rank runs)
+
+
+def emit(line):
+    """print the result line on the process's original stdout"""
+    if _REAL_STDOUT[0] is None:
+        print(line)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT[0], (line + "\n").encode())
+
+
 NOBJ = 10000
 DIMS = (48, 48)
 NGAUSS = 18
@@ -275,10 +288,14 @@ def main():
         numa_node = shard.bind_to_gpu_numa_node(local)
     _lib.init(local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's log (NCCL_DEBUG=INFO /
-        # VERSION prints to stdout by default) goes to stderr instead, where
-        # the rank count stays observable
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # keep stdout to the one JSON line without switching NCCL's log off:
+        # NCCL writes its NCCL_DEBUG lines (version, INFO with the rank
+        # count) to file descriptor 1, so descriptor 1 is pointed at stderr
+        # for the rest of the run and the JSON line goes to a private copy of
+        # the original stdout
+        sys.stdout.flush()
+        _REAL_STDOUT[0] = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     nobj = args.nobj
@@ -450,6 +467,24 @@ def main():
               + h_psf.numel() * 8 + h_guess.numel() * 8)
     d2h = int(nobj * _lib.LM_RESULT_DTYPE.itemsize)
 
+    # ---- the host's host-to-device ceiling with all ranks copying at once
+    # (pinned memory, the stamps themselves): what bounds the end-to-end
+    # calls when several GPUs share one host
+    barrier()
+    c0 = torch.cuda.Event(enable_timing=True)
+    c1 = torch.cuda.Event(enable_timing=True)
+    c0.record(stream)
+    for _ in range(4):
+        d_images.copy_(h_images, non_blocking=True)
+        d_weights.copy_(h_weights, non_blocking=True)
+    c1.record(stream)
+    barrier()
+    cp_ms = c0.elapsed_time(c1)
+    t = torch.tensor([cp_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    h2d_gbs = world * 8 * h_images.numel() * 8 / (float(t.item()) * 1e-3) / 1e9
+
     # ---- the stand-alone fdiff kernel (fill_fdiff + get_loglike fused,
     # ngx_loglike) on the same stamps, at the guess mixtures
     gm0, _ = _lib.gmix_fill("exp", b["guess"])
@@ -605,6 +640,15 @@ def main():
             "api": "ngx_lm_fit_host_compact (fit_batch with float32 pixels "
                    "and one weight per stamp): 4 bytes per pixel over PCIe, "
                    "bit-identical results"},
+        "host_h2d_ceiling": {
+            "aggregate_gbs": h2d_gbs,
+            "note": "pinned host-to-device copies of the stamps by all %d "
+                    "rank(s) at once; fits/s bound = this / bytes per fit "
+                    "(37.1 KB float64, 18.7 KB float32, 9.4 KB compact)"
+                    % world,
+            "e2e_bound_f64_fits_per_s": h2d_gbs * 1e9 / (h2d / nobj),
+            "e2e_bound_f32_fits_per_s": h2d_gbs * 1e9
+            / ((h2d - h_images.numel() * 8) / nobj)},
         "e2e_pageable": {
             "value": world * nobj / e2ep_s, "unit": "fits/s",
             "api": "the float64 call on ordinary (pageable) numpy arrays; "
@@ -695,7 +739,7 @@ def main():
                     np.abs(res["pars"][:nref, 2:4] - rr["pars"][:, 2:4])))}
         # parity on the sample, reported beside the throughput
         out["parity_on_sample"] = bench_configs.lm_parity(res, ores, 6)
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
