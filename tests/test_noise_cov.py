@@ -85,6 +85,13 @@ def test_gpu_fitter_use_noise_image(ng, tag, model):
         assert np.all(np.abs(r["pars_err"] / want - 1) < 1e-3), \
             (r["pars_err"], want)
         assert _rel(r["pars_cov"], g[tag + "_res_pars_cov"][i]) < 1e-3
+        # the reference applies the sandwich BEFORE set_fit_result
+        # (fitters.py:105-110): every derived key comes from it
+        cov = g[tag + "_res_pars_cov"][i]
+        assert abs(r["T_err"] / np.sqrt(cov[4, 4]) - 1) < 1e-3
+        assert abs(r["flux_err"] / np.sqrt(cov[-1, -1]) - 1) < 1e-3
+        assert _rel(r["g_cov"], cov[2:4, 2:4]) < 1e-3
+        assert np.all(np.abs(r["g_err"] / want[2:4] - 1) < 1e-3)
         # and it is not the plain covariance
         assert np.any(np.abs(r["pars_err"] / g[tag + "_res_pars_err_plain"][i]
                              - 1) > 0.05)
@@ -107,6 +114,18 @@ def test_gpu_fit_batch_noise_images(ng):
     for i in range(recs.size):
         assert _rel(recs["pars_cov"][i][:36].reshape(6, 6),
                     g["exp_res_pars_cov"][i]) < 1e-3
+        cov = g["exp_res_pars_cov"][i]
+        assert abs(recs["T_err"][i] / np.sqrt(cov[4, 4]) - 1) < 1e-3
+        assert abs(recs["flux_err"][i] / np.sqrt(cov[5, 5]) - 1) < 1e-3
+    # an object whose stepped parameters leave the model's domain flags only
+    # itself (the reference: NaN covariance -> covariance flags)
+    from ngmix_b200 import noise_cov
+    B = noise_cov.calc_noise_b(
+        "bdf", np.array([[0.0, 0.0, 0.1, 0.1, 0.3, 0.5, 100.0],
+                         [0.0, 0.0, 0.7, 0.71409284, 0.3, 0.5, 100.0]]),
+        g["bdf_psf"][:2], g["bdf_jac"][:2], g["bdf_weights"][:2],
+        g["bdf_noise"][:2], per_object=True)
+    assert np.all(np.isfinite(B[0])) and np.all(np.isnan(B[1]))
     # odd sizes / column padding (5 x 7) and a stamp larger than shared
     # memory (110 x 106: staged planes in global scratch) against numpy's fft
     from ngmix_b200 import _lib
