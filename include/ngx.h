@@ -540,6 +540,14 @@ int ngx_lm_fit_host_compact(int n, int model, const float *images,
                             const double *guess, const ngx_prior *prior,
                             const ngx_lm_pars *lm_pars,
                             int ignore_zero_weight, ngx_lm_result *res);
+/* device-pointer expansion of the compact format into the engine's float64
+ * planes (ObservationBatch.from_arrays with float32 pixels, one weight per
+ * stamp and a mask): images32 [n,nrow,ncol], weight_scalar [n], maskbits
+ * [n, ceil(nrow*ncol/8)] or NULL -> images, weights [n,nrow,ncol] */
+int ngx_expand_compact(int n, int nrow, int ncol, const float *images32,
+                       const double *weight_scalar,
+                       const unsigned char *maskbits, double *images,
+                       double *weights, void *stream);
 int ngx_em_host(int n, int variant, const double *images,
                 const double *weights, const ngx_jacobian *jac, int nrow,
                 int ncol, const double *guess, int ngauss,

@@ -137,6 +137,7 @@ SYMBOLS = [
     "ngx_host_unregister", "ngx_bootstrap", "ngx_bootstrap_workspace_bytes",
     "ngx_chain_draws", "ngx_em_todo", "ngx_lm_fit_todo",
     "ngx_template_flux_images", "ngx_template_flux_images_host",
+    "ngx_expand_compact",
     "ngx_lm_fit_multi_wide", "ngx_lm_fit_multi_wide_host",
     "ngx_lm_fit_coellip", "ngx_lm_fit_coellip_host",
 ]
@@ -986,3 +987,12 @@ def chain_draws_device(n, seed, tr, stage, ndraw, d_out, stream=0):
     check(lib().ngx_chain_draws(C.c_int(n), C.c_ulonglong(seed), C.c_int(tr),
                                 C.c_int(stage), C.c_int(ndraw),
                                 C.c_void_p(d_out), C.c_void_p(stream)))
+
+
+def expand_compact_device(n, nrow, ncol, d_images32, d_wscalar, d_mask,
+                          d_images, d_weights, stream=0):
+    """ngx_expand_compact on device pointers (asynchronous)"""
+    check(lib().ngx_expand_compact(
+        C.c_int(n), C.c_int(nrow), C.c_int(ncol), C.c_void_p(d_images32),
+        C.c_void_p(d_wscalar), C.c_void_p(d_mask) if d_mask else None,
+        C.c_void_p(d_images), C.c_void_p(d_weights), C.c_void_p(stream)))

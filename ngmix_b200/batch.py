@@ -55,15 +55,59 @@ class ObservationBatch(object):
     # ------------------------------------------------------------ building
     @classmethod
     def from_arrays(cls, images, weights, jacobians, psf_pars=None, device=0,
-                    ignore_zero_weight=True):
+                    ignore_zero_weight=True, mask=None):
         """
         images, weights: [n, H, W] (numpy, pinned or pageable, or torch)
         jacobians: [n, 8] rows (row0, col0, dvdrow, dvdcol, dudrow, dudcol,
             det, scale) or Jacobian records
         psf_pars: [n, npsf, 6] full gaussian parameters, optional
+        mask: [n, H, W] bool, optional (True = use the pixel)
+
+        Compact survey format: float32 `images` with ONE weight per stamp
+        (`weights` a scalar or an [n] array) and an optional mask are uploaded
+        as they are (4.1 bytes per pixel) and expanded on the device to the
+        planes the reference's Observation would hold: image.astype(f8) and
+        where(mask, weight, 0) (observation.py:114-126, pixels/pixels.py:6-52).
         """
+        w_arr = None if _torch().is_tensor(weights) else np.asarray(weights)
+        if w_arr is not None and w_arr.ndim <= 1:
+            return cls._from_compact(images, w_arr, jacobians, psf_pars,
+                                     device, ignore_zero_weight, mask)
+        if mask is not None:
+            weights = np.where(np.asarray(mask, dtype=bool), w_arr, 0.0)
         return cls(images, weights, jacobians, psf_pars=psf_pars,
                    device=device, ignore_zero_weight=ignore_zero_weight)
+
+    @classmethod
+    def _from_compact(cls, images, w_arr, jacobians, psf_pars, device,
+                      ignore_zero_weight, mask):
+        torch = _torch()
+        _lib.init(device)
+        dev = torch.device("cuda", device)
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        if images.ndim != 3:
+            raise ValueError("images must be [n, H, W]")
+        n, H, W = images.shape
+        ws = np.ascontiguousarray(np.broadcast_to(w_arr.astype("f8"), (n,)))
+        d_im32 = torch.from_numpy(images).to(dev, non_blocking=True)
+        d_ws = torch.from_numpy(ws).to(dev, non_blocking=True)
+        d_mask = None
+        if mask is not None:
+            mask = np.asarray(mask, dtype=bool)
+            if mask.shape != images.shape:
+                raise ValueError("mask and images differ in shape")
+            d_mask = torch.from_numpy(
+                np.packbits(mask.reshape(n, -1), axis=1)).to(dev)
+        d_im = torch.empty((n, H, W), dtype=torch.float64, device=dev)
+        d_wt = torch.empty((n, H, W), dtype=torch.float64, device=dev)
+        if n > 0:
+            _lib.expand_compact_device(
+                n, H, W, d_im32.data_ptr(), d_ws.data_ptr(),
+                d_mask.data_ptr() if d_mask is not None else 0,
+                d_im.data_ptr(), d_wt.data_ptr(),
+                stream=torch.cuda.current_stream(dev).cuda_stream)
+        return cls(d_im, d_wt, jacobians, psf_pars=psf_pars, device=device,
+                   ignore_zero_weight=ignore_zero_weight)
 
     @classmethod
     def from_observations(cls, obslist, device=0):

@@ -2708,6 +2708,24 @@ int ngx_lm_fit_host_f32(int n, int model, const float *images,
 #endif
 
 #ifndef NGX_LM_WIDE_TU
+int ngx_expand_compact(int n, int nrow, int ncol, const float *images32,
+                       const double *weight_scalar,
+                       const unsigned char *maskbits, double *images,
+                       double *weights, void *stream) {
+    NGX_REQUIRE(n >= 0 && nrow >= 1 && ncol >= 1);
+    NGX_REQUIRE(images32 && weight_scalar && images && weights);
+    if (n == 0) return NGX_OK;
+    const size_t ntot = (size_t)nrow * ncol;
+    const size_t cnt = (size_t)n * ntot;
+    int blocks = (int)((cnt + 255) / 256 < (size_t)(8 * sm_count())
+                           ? (cnt + 255) / 256 : (size_t)(8 * sm_count()));
+    k_expand_compact<<<blocks, 256, 0, as_stream(stream)>>>(
+        images32, weight_scalar, maskbits, images, weights, n, (int)ntot,
+        (int)((ntot + 7) / 8));
+    NGX_LAUNCH_CHECK();
+    return NGX_OK;
+}
+
 int ngx_lm_fit_host_compact(int n, int model, const float *images,
                             const double *weight_scalar,
                             const unsigned char *maskbits,

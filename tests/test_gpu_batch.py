@@ -201,6 +201,10 @@ def test_lm_fit_compact_survey_format(ngx):
     got2 = ng.fit_batch("exp", im32, wsc, b["jac"], b["psf"], b["guess"],
                         mask=mask)
     _same_records(got2, want)
+    # the same format into a device-resident batch
+    ob = ng.ObservationBatch.from_arrays(im32, wsc, b["jac"],
+                                         psf_pars=b["psf"], mask=mask)
+    _same_records(ob.fit("exp", b["guess"]), want)
     # no mask, scalar weight for the whole batch
     want3 = ngx.lm_fit("exp", im32.astype(np.float64),
                        np.full(im32.shape, 400.0), b["jac"], b["psf"],
