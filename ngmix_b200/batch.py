@@ -88,7 +88,7 @@ class ObservationBatch(object):
         if images.ndim != 3:
             raise ValueError("images must be [n, H, W]")
         n, H, W = images.shape
-        ws = np.ascontiguousarray(np.broadcast_to(w_arr.astype("f8"), (n,)))
+        ws = np.array(np.broadcast_to(w_arr.astype("f8"), (n,)))
         d_im32 = torch.from_numpy(images).to(dev, non_blocking=True)
         d_ws = torch.from_numpy(ws).to(dev, non_blocking=True)
         d_mask = None

@@ -29,6 +29,7 @@
 // thread then advances the MINPACK state machine (ngx_lm_solve.cuh) while
 // the other CTAs resident on the SM keep the fp64 pipe busy.
 #include <cuda_pipeline.h>
+#include <chrono>
 #include <mutex>
 #include <vector>
 #include "ngx_core.cuh"
@@ -74,7 +75,73 @@ struct LMArgs {
     double *gscratch;
     // retry rounds of the fitting chain: fit only objects with todo != 0
     const int32_t *todo;
+    // streamed host input (lm_fit_host_stream): the stamps arrive by DMA while
+    // the kernel runs.  ready[c] becomes 1 by a copy ordered after the stamps
+    // of chunk c (wait_ready has the chunk boundaries) and their jacobians,
+    // psfs and guesses.  src 0: images / weights are double planes; 1: float planes
+    // (im32, wt32); 2: float pixels, one weight per stamp (wscalar) and
+    // optional mask bits (numpy.packbits order, nmb bytes per stamp).
+    // done_count[c] counts the finished records of [c * done_chunk, ...); the
+    // CTA that completes a chunk raises host_done[c] (mapped pinned memory) so
+    // the host can start that chunk's device-to-host copy at once.
+    const int *ready;
+    int ready_chunk, src, nmb, done_chunk;
+    const float *im32, *wt32;
+    const double *wscalar;
+    const unsigned char *maskbits;
+    int *done_count, *host_done, *err;
 };
+
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];"
+                 : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// wait until the chunk of `stamp` has arrived (a few seconds at most: a feed
+// that stalls marks the call as failed instead of hanging the device)
+// chunks: [0,S) [S,2S) [2S,4S) [4S,8S) and then 8S = ready_chunk stamps each,
+// S = ready_chunk / 8 (short first chunks: the first CTAs start after ~50 us
+// of copying; long later ones: few copies to set up)
+__device__ __forceinline__ const int *ready_flag(const LMArgs &a, int stamp) {
+    const int C = a.ready_chunk, S = C >> 3;
+    const int idx = stamp >= C ? 3 + stamp / C
+        : (stamp < S ? 0 : stamp < 2 * S ? 1 : stamp < 4 * S ? 2 : 3);
+    return a.ready + idx;
+}
+__device__ __forceinline__ bool chunk_arrived(const LMArgs &a, int stamp) {
+    return *(const volatile int *)ready_flag(a, stamp) != 0;
+}
+static __device__ __noinline__ void wait_ready(const LMArgs &a, int stamp) {
+    const int *f = ready_flag(a, stamp);
+    if (ld_acquire_sys(f)) return;
+    const unsigned long long t0 = global_ns();
+    for (;;) {
+        __nanosleep(400);
+        if (ld_acquire_sys(f)) return;
+        if (global_ns() - t0 > 4000000000ull) {
+            *(volatile int *)a.err = 1;
+            return;
+        }
+    }
+}
+// one thread, after the record of `stamp` is complete
+__device__ __forceinline__ void mark_done(const LMArgs &a, int stamp) {
+    if (!a.done_count) return;
+    __threadfence();
+    const int c = stamp / a.done_chunk;
+    int size = a.n - c * a.done_chunk;
+    if (size > a.done_chunk) size = a.done_chunk;
+    if (atomicAdd(a.done_count + c, 1) + 1 == size) {
+        __threadfence_system();
+        *(volatile int *)(a.host_done + c) = 1;
+    }
+}
 
 // bounded fits: leastsqbound's parameter transforms (leastsqbound.py:183-263).
 // MINPACK iterates on internal (unconstrained) parameters, the model and the
@@ -1040,14 +1107,22 @@ k_lm_fit(LMArgs a) {
         //      touches val/ierr and a few words the epilogue does not read
         int cnt = 0, first = a.ntot, firstq = 0;
         if (warp_id == 0) {
-            if (pending >= 0)
+            if (pending >= 0) {
                 lm_finish(a, &sh, &((RES *)a.res)[pending]);
+                if (a.done_count) {
+                    __threadfence();
+                    __syncwarp();
+                    if (threadIdx.x == 0) mark_done(a, pending);
+                }
+            }
             if (threadIdx.x == 0 && have) {
                 sh.next = atomicAdd(a.counter, 1);
+                if (a.ready) wait_ready(a, stamp);
                 sh.jac = a.jac[stamp];
                 sh.status = 0;
             }
         } else if (have && !skip) {
+            if (a.ready) wait_ready(a, stamp);
             const double *im = a.images + (size_t)stamp * a.ntot;
             const double *wt = a.weights + (size_t)stamp * a.ntot;
             const int t0 = threadIdx.x - 32, TS = T - 32;
@@ -1102,6 +1177,56 @@ k_lm_fit(LMArgs a) {
                         }
                         if (!valid) val[q] = 0.0;
                     }
+                }
+            } else if (a.src != 0) {
+                // float stamps straight from the host's format, widened here
+                // (exactly): asynchronous 4-byte copies into the low half of
+                // each pixel's shared-memory slot, converted in place by the
+                // thread that fetched them - no intermediate double planes
+                // in HBM
+                const float *im32 = a.im32 + (size_t)stamp * a.ntot;
+                const float *wt32 = a.wt32 + (size_t)stamp * a.ntot;
+                const unsigned char *mb = (a.src == 2 && a.maskbits)
+                    ? a.maskbits + (size_t)stamp * a.nmb : nullptr;
+                for (int q = t0; q < a.nq; q += TS) {
+                    int row, col;
+                    q_to_rowcol(q, a.tpr, &row, &col);
+                    if (row < a.nrow && col < a.ncol) {
+                        int p = row * a.ncol + col;
+                        __pipeline_memcpy_async(&val[q], &im32[p],
+                                                sizeof(float));
+                        if (a.src == 1)
+                            __pipeline_memcpy_async(&ierr[q], &wt32[p],
+                                                    sizeof(float));
+                    }
+                }
+                __pipeline_commit();
+                const double ws = a.src == 2 ? a.wscalar[stamp] : 0.0;
+                if (t0 < 6 * a.npsf)
+                    sh.psf[t0] = a.psf[(size_t)stamp * 6 * a.npsf + t0];
+                __pipeline_wait_prior(0);
+                for (int q = t0; q < a.nq; q += TS) {
+                    int row, col;
+                    q_to_rowcol(q, a.tpr, &row, &col);
+                    double vv = 0.0, ie = 0.0;
+                    if (row < a.nrow && col < a.ncol) {
+                        const int p = row * a.ncol + col;
+                        double w;
+                        if (a.src == 1)
+                            w = (double)*(const float *)&ierr[q];
+                        else
+                            w = (!mb || ((mb[p >> 3] >> (7 - (p & 7))) & 1))
+                                ? ws : 0.0;
+                        const bool valid = !(a.ignore_zero_weight && w <= 0.0);
+                        if (valid) {
+                            vv = (double)*(const float *)&val[q];
+                            ie = sqrt(w < 0.0 ? 0.0 : w);
+                            cnt++;
+                            if (p < first) { first = p; firstq = q; }
+                        }
+                    }
+                    val[q] = vv;
+                    ierr[q] = ie;
                 }
             } else {
                 // both planes as asynchronous 8-byte copies (LDGSTS) straight
@@ -1161,15 +1286,22 @@ k_lm_fit(LMArgs a) {
         const int next = sh.next;
         if (skip) {
             // nothing to do for this stamp (its record stays as it is)
+            if (threadIdx.x == 0) mark_done(a, stamp);
             __syncthreads();
             stamp = next;
             continue;
         }
-        if (next < a.n) {
+        if (next < a.n && (!a.ready || chunk_arrived(a, next))) {
             // pull the next stamp into L2 while this one is fitted
             const char *pi = (const char *)(a.images + (size_t)next * a.ntot);
             const char *pw = (const char *)(a.weights + (size_t)next * a.ntot);
-            const size_t bytes = (size_t)a.ntot * sizeof(double);
+            size_t bytes = (size_t)a.ntot * sizeof(double);
+            if (a.src != 0) {
+                pi = (const char *)(a.im32 + (size_t)next * a.ntot);
+                pw = a.src == 1 ? (const char *)(a.wt32 + (size_t)next * a.ntot)
+                                : pi;
+                bytes = (size_t)a.ntot * sizeof(float);
+            }
             for (size_t off = (size_t)threadIdx.x * 128; off < bytes;
                  off += (size_t)T * 128) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + off));
@@ -1226,6 +1358,7 @@ k_lm_fit(LMArgs a) {
                     r->pars[i] = NGX_PDEF;
                     r->pars_err[i] = NGX_CDEF;
                 }
+                mark_done(a, stamp);
             }
             __syncthreads();
             stamp = next;
@@ -1970,8 +2103,37 @@ using namespace ngx;
 
 extern "C" {
 
+#ifndef NGX_LM_WIDE_TU
+// shared memory of k_lm_fit without the ierr plane (*smem); returns whether
+// the weights stay in global memory: ierr = sqrt(w) is kept in shared memory
+// too when four CTAs (the register limit) still fit on an SM, larger stamps
+// leave the weights in L2
+static bool lm_weights_global(int ngauss, int nfd, int nq, int nrow, int ncol,
+                              int nwarps, size_t *smem) {
+    *smem = sizeof(double)
+        * ((size_t)ngauss * REC + (size_t)nfd * ngauss * FDREC
+           + (nfd ? 16 + (size_t)nq : 0) + (size_t)nq + nrow + ncol
+           + 48 * nwarps + LM_MAXP
+           + ((size_t)(nq / 32) * ((ngauss + 31) / 32) + 1) / 2);
+    size_t per_cta = *smem + sizeof(double) * (size_t)nq + sizeof(LMShared)
+        + 1024;
+    return 4 * per_cta > (size_t)smem_optin_bytes() + 1024;
+}
+#endif
+
 // objects to fit in the current call (ngx_lm_fit_todo); NULL = all
 static thread_local const int32_t *g_lm_todo = nullptr;
+
+// streamed input of the current call (lm_fit_host_stream); NULL = resident
+struct LMFeed {
+    const int *ready;
+    int ready_chunk, src, nmb, done_chunk;
+    const float *im32, *wt32;
+    const double *wscalar;
+    const unsigned char *maskbits;
+    int *done_count, *host_done, *err;
+};
+static thread_local const LMFeed *g_lm_feed = nullptr;
 
 #ifndef NGX_LM_WIDE_TU
 int ngx_lm_fit_todo(int n, int model, const double *images,
@@ -2012,6 +2174,14 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     a.images = images; a.weights = weights; a.jac = jac;
     a.psf = psf_pars; a.guess = guess; a.res = res;
     a.todo = g_lm_todo;
+    const LMFeed *feed = g_lm_feed;
+    if (feed) {
+        a.ready = feed->ready; a.ready_chunk = feed->ready_chunk;
+        a.src = feed->src; a.nmb = feed->nmb; a.done_chunk = feed->done_chunk;
+        a.im32 = feed->im32; a.wt32 = feed->wt32; a.wscalar = feed->wscalar;
+        a.maskbits = feed->maskbits; a.done_count = feed->done_count;
+        a.host_done = feed->host_done; a.err = feed->err;
+    }
     NGX_REQUIRE(a.ngauss <= NGX_MAX_GAUSS);
     if (a.prior.present) {
         NGX_REQUIRE(a.prior.g_kind == 1);
@@ -2028,18 +2198,12 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
     a.nq = 32 * a.tpr * ((nrow + 3) / 4);
     int nfd = analytic ? 0 : np + 1;
     int nwarps = threads / 32;
-    // shared memory without the ierr plane
-    size_t smem = sizeof(double)
-        * ((size_t)a.ngauss * REC + (size_t)nfd * a.ngauss * FDREC
-           + (nfd ? 16 + (size_t)a.nq : 0) + (size_t)a.nq + nrow + ncol
-           + 48 * nwarps + LM_MAXP
-           + ((size_t)(a.nq / 32) * ((a.ngauss + 31) / 32) + 1) / 2);
-    // keep ierr = sqrt(w) in shared memory too when four CTAs (the register
-    // limit) still fit on an SM; larger stamps leave the weights in L2
+    size_t smem = 0;
+    bool wg = lm_weights_global(a.ngauss, nfd, a.nq, nrow, ncol, nwarps, &smem);
     size_t smem_both = smem + sizeof(double) * (size_t)a.nq;
-    size_t per_cta = smem_both + sizeof(LMShared) + 1024;
-    bool wg = 4 * per_cta > (size_t)smem_optin_bytes() + 1024;
     cudaStream_t st = as_stream(stream);
+    // a streamed feed is staged by the kernels that keep both planes resident
+    NGX_REQUIRE(!feed || !wg);
     if (analytic && smem + sizeof(LMShared) + 1024
             > (size_t)smem_optin_bytes()) {
         // the stamp does not fit shared memory even without the weights:
@@ -2464,6 +2628,341 @@ int ngx_lm_fit_multi_wide_host(int nobj, int model,
 #endif
 
 #ifndef NGX_LM_WIDE_TU
+// ---------------------------------------------------------------------
+// Streamed host-buffer pipeline (pinned stamps that fit the resident
+// kernels).  ONE persistent launch per batch of up to NGX_STREAM_BATCH
+// stamps: the copy engine writes the stamps in the host's own format
+// (double planes, float planes or the compact format) chunk by chunk, each
+// chunk followed by a 4-byte copy that raises its ready flag; the CTAs take
+// stamps from the work queue in order and wait for the flag of a stamp's
+// chunk before staging it into shared memory (float stamps are widened
+// there: no intermediate planes in HBM, no expansion kernels).  Finished
+// records are counted per chunk of 1024; the CTA that completes a chunk
+// raises a flag in mapped pinned memory and the host, polling, starts that
+// chunk's device-to-host copy while the fits go on.  Against one launch per
+// chunk this removes the launch tails (a fit takes ~0.25 ms, so every
+// chunk launch ended with SMs draining) and the per-chunk expansion passes.
+struct StreamBuf {
+    void *in_a = nullptr, *in_b = nullptr;      // image / weight planes
+    ngx_jacobian *jac = nullptr;
+    double *psf = nullptr, *guess = nullptr, *ws = nullptr;
+    unsigned char *mask = nullptr;
+    ngx_lm_result *res = nullptr;
+    int *flags = nullptr;                       // ready | done_count
+    size_t cap_a = 0, cap_b = 0, cap_obj = 0, cap_psf = 0, cap_mask = 0,
+           cap_flags = 0;
+    cudaEvent_t small_up = nullptr, drained = nullptr;
+};
+
+static int grow_dev(void **p, size_t *cap, size_t need) {
+    if (need <= *cap) return NGX_OK;
+    NGX_CUDA(cudaDeviceSynchronize());
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    NGX_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return NGX_OK;
+}
+
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes attr;
+    bool ok = cudaPointerGetAttributes(&attr, p) == cudaSuccess
+        && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return ok;
+}
+
+static bool lm_stream_eligible(int model, int nrow, int ncol, int npsf,
+                               const ngx_lm_pars *lm_pars) {
+    if (const char *e = getenv("NGX_NO_STREAM"))
+        if (atoi(e)) return false;
+    int np = model_npars(model), ng0 = model_ngauss(model);
+    if (np <= 0 || ng0 <= 0 || model == NGX_CM || !lm_pars) return false;
+    const bool analytic = lm_pars->analytic_jacobian
+        && (model == NGX_GAUSS || model == NGX_EXP || model == NGX_DEV);
+    const int ngauss = ng0 * (npsf > 0 ? npsf : 1);
+    const int threads = nrow * ncol <= 1024 ? 64 : 128;
+    const int nq = 32 * ((ncol + 7) / 8) * ((nrow + 3) / 4);
+    size_t smem = 0;
+    return !lm_weights_global(ngauss, analytic ? 0 : np + 1, nq, nrow, ncol,
+                              threads / 32, &smem);
+}
+
+static int lm_fit_host_stream(int n, int model, const void *images_v,
+                              const void *weights_v, int f32,
+                              const unsigned char *maskbits,
+                              const ngx_jacobian *jac, int nrow, int ncol,
+                              const double *psf_pars, int npsf,
+                              const double *guess, const ngx_prior *prior,
+                              const ngx_lm_pars *lm_pars,
+                              int ignore_zero_weight, ngx_lm_result *res) {
+    const int np = model_npars(model);
+    const size_t ntot = (size_t)nrow * ncol;
+    const int nmb = (int)((ntot + 7) / 8);
+    const size_t esz = f32 ? sizeof(float) : sizeof(double);
+    const bool compact = f32 == 2;
+    int batch = 32768;
+    if (const char *e = getenv("NGX_STREAM_BATCH")) {
+        int w = atoi(e);
+        if (w >= 1) batch = w;
+    }
+    if (batch > n) batch = n;
+    // input chunks (wait_ready): S, S, 2S, 4S and then 8S stamps each
+    const int S = sm_count(), rchunk = 8 * S;
+    const int dchunk = 1024;
+    const int max_rc = 4 + (batch + rchunk - 1) / rchunk;
+    const int max_dc = (batch + dchunk - 1) / dchunk;
+
+    static thread_local StreamBuf sb[2];
+    static thread_local cudaStream_t cs = nullptr, ks[2] = {nullptr, nullptr},
+                                     ds = nullptr;
+    static thread_local int *h_flags = nullptr;   // mapped: done flags, err
+    static thread_local int *h_one = nullptr;     // pinned constant 1
+    static thread_local size_t cap_hflags = 0;
+    static thread_local ngx_lm_result *h_stage = nullptr;
+    static thread_local size_t cap_stage = 0;
+    if (!cs) {
+        NGX_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        NGX_CUDA(cudaStreamCreateWithFlags(&ks[0], cudaStreamNonBlocking));
+        NGX_CUDA(cudaStreamCreateWithFlags(&ks[1], cudaStreamNonBlocking));
+        NGX_CUDA(cudaStreamCreateWithFlags(&ds, cudaStreamNonBlocking));
+        NGX_CUDA(cudaHostAlloc((void **)&h_one, sizeof(int),
+                               cudaHostAllocDefault));
+        *h_one = 1;
+        for (int b = 0; b < 2; b++) {
+            NGX_CUDA(cudaEventCreateWithFlags(&sb[b].small_up,
+                                              cudaEventDisableTiming));
+            NGX_CUDA(cudaEventCreateWithFlags(&sb[b].drained,
+                                              cudaEventDisableTiming));
+        }
+    }
+    const size_t need_hflags = 2 * (size_t)(max_dc + 1);
+    if (need_hflags > cap_hflags) {
+        NGX_CUDA(cudaDeviceSynchronize());
+        if (h_flags) cudaFreeHost(h_flags);
+        h_flags = nullptr;
+        cap_hflags = 0;
+        NGX_CUDA(cudaHostAlloc((void **)&h_flags, need_hflags * sizeof(int),
+                               cudaHostAllocMapped));
+        cap_hflags = need_hflags;
+    }
+    const bool res_pinned = is_pinned(res);
+    if (!res_pinned && (size_t)n > cap_stage) {
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr;
+        cap_stage = 0;
+        NGX_CUDA(cudaMallocHost((void **)&h_stage,
+                                (size_t)n * sizeof(ngx_lm_result)));
+        cap_stage = n;
+    }
+    ngx_lm_result *res_dst = res_pinned ? res : h_stage;
+    const int nbatch = (n + batch - 1) / batch;
+    // results of the previous done-chunk wait in the staging buffer until
+    // their copy has finished (pageable result arrays)
+    cudaEvent_t d2h_ev[2] = {nullptr, nullptr};
+    if (!res_pinned)
+        for (int i = 0; i < 2; i++)
+            NGX_CUDA(cudaEventCreateWithFlags(&d2h_ev[i],
+                                              cudaEventDisableTiming));
+    int rc = NGX_OK;
+    int owed_lo = -1, owed_n = 0, owed_ev = 0, nd2h = 0;
+
+    // queue the input copies of batch k and launch its kernel
+    auto enqueue = [&](int k) -> int {
+        StreamBuf &B = sb[k & 1];
+        const int lo = k * batch;
+        const int cn = n - lo < batch ? n - lo : batch;
+        int *hf = h_flags + (size_t)(k & 1) * (max_dc + 1);
+        int r;
+        if ((r = grow_dev(&B.in_a, &B.cap_a, (size_t)cn * ntot * esz))) return r;
+        if (!compact
+            && (r = grow_dev(&B.in_b, &B.cap_b, (size_t)cn * ntot * esz)))
+            return r;
+        if (compact && maskbits
+            && (r = grow_dev((void **)&B.mask, &B.cap_mask, (size_t)cn * nmb)))
+            return r;
+        if ((size_t)cn > B.cap_obj) {
+            NGX_CUDA(cudaDeviceSynchronize());
+            cudaFree(B.jac); cudaFree(B.guess); cudaFree(B.ws); cudaFree(B.res);
+            B.jac = nullptr; B.guess = nullptr; B.ws = nullptr; B.res = nullptr;
+            B.cap_obj = 0;
+            NGX_CUDA(cudaMalloc((void **)&B.jac, cn * sizeof(ngx_jacobian)));
+            NGX_CUDA(cudaMalloc((void **)&B.guess,
+                                (size_t)cn * 8 * sizeof(double)));
+            NGX_CUDA(cudaMalloc((void **)&B.ws, cn * sizeof(double)));
+            NGX_CUDA(cudaMalloc((void **)&B.res, cn * sizeof(ngx_lm_result)));
+            B.cap_obj = cn;
+        }
+        if (npsf > 0
+            && (r = grow_dev((void **)&B.psf, &B.cap_psf,
+                             (size_t)cn * 6 * npsf * sizeof(double))))
+            return r;
+        if ((r = grow_dev((void **)&B.flags, &B.cap_flags,
+                          (size_t)(max_rc + max_dc) * sizeof(int))))
+            return r;
+        int *d_ready = B.flags, *d_done = B.flags + max_rc;
+        // the buffers are free once the records of batch k-2 are on the host
+        NGX_CUDA(cudaStreamWaitEvent(cs, B.drained, 0));
+        NGX_CUDA(cudaMemsetAsync(B.flags, 0,
+                                 (size_t)(max_rc + max_dc) * sizeof(int), cs));
+        for (int i = 0; i <= max_dc; i++) hf[i] = 0;
+        NGX_CUDA(cudaEventRecord(B.small_up, cs));
+        NGX_CUDA(cudaStreamWaitEvent(ks[k & 1], B.small_up, 0));
+        LMFeed feed;
+        memset(&feed, 0, sizeof(feed));
+        feed.ready = d_ready; feed.ready_chunk = rchunk;
+        feed.src = f32; feed.nmb = nmb; feed.done_chunk = dchunk;
+        feed.im32 = (const float *)B.in_a;
+        feed.wt32 = (const float *)B.in_b;
+        feed.wscalar = B.ws;
+        feed.maskbits = (compact && maskbits) ? B.mask : nullptr;
+        feed.done_count = d_done;
+        NGX_CUDA(cudaHostGetDevicePointer((void **)&feed.host_done, hf, 0));
+        feed.err = feed.host_done + max_dc;
+        g_lm_feed = &feed;
+        r = ngx_lm_fit(cn, model, (const double *)B.in_a,
+                       (const double *)(compact ? B.in_a : B.in_b), B.jac,
+                       nrow, ncol, npsf > 0 ? B.psf : nullptr, npsf, B.guess,
+                       prior, lm_pars, ignore_zero_weight, B.res, ks[k & 1]);
+        g_lm_feed = nullptr;
+        if (r) return r;
+        for (int c = 0, slo = 0; slo < cn; c++) {
+            const int want = c < 2 ? S : c == 2 ? 2 * S : c == 3 ? 4 * S
+                                                         : rchunk;
+            const int sn = cn - slo < want ? cn - slo : want;
+            const size_t g = (size_t)(lo + slo);
+            NGX_CUDA(cudaMemcpyAsync((char *)B.in_a + (size_t)slo * ntot * esz,
+                                     (const char *)images_v + g * ntot * esz,
+                                     (size_t)sn * ntot * esz,
+                                     cudaMemcpyHostToDevice, cs));
+            if (compact) {
+                NGX_CUDA(cudaMemcpyAsync(
+                    B.ws + slo, (const double *)weights_v + g,
+                    sn * sizeof(double), cudaMemcpyHostToDevice, cs));
+                if (maskbits)
+                    NGX_CUDA(cudaMemcpyAsync(
+                        B.mask + (size_t)slo * nmb, maskbits + g * nmb,
+                        (size_t)sn * nmb, cudaMemcpyHostToDevice, cs));
+            } else {
+                NGX_CUDA(cudaMemcpyAsync(
+                    (char *)B.in_b + (size_t)slo * ntot * esz,
+                    (const char *)weights_v + g * ntot * esz,
+                    (size_t)sn * ntot * esz, cudaMemcpyHostToDevice, cs));
+            }
+            if (c == 0 || (c >= 4 && (c - 4) % 8 == 0)) {
+                // the small per-stamp arrays: of the first 8S stamps, then
+                // of eight chunks at a time
+                const int gw = c == 0 ? rchunk : 8 * rchunk;
+                const int gn = cn - slo < gw ? cn - slo : gw;
+                NGX_CUDA(cudaMemcpyAsync(B.jac + slo, jac + g,
+                                         gn * sizeof(ngx_jacobian),
+                                         cudaMemcpyHostToDevice, cs));
+                if (npsf > 0)
+                    NGX_CUDA(cudaMemcpyAsync(
+                        B.psf + (size_t)slo * 6 * npsf,
+                        psf_pars + g * 6 * npsf,
+                        (size_t)gn * 6 * npsf * sizeof(double),
+                        cudaMemcpyHostToDevice, cs));
+                NGX_CUDA(cudaMemcpyAsync(B.guess + (size_t)slo * np,
+                                         guess + g * np,
+                                         (size_t)gn * np * sizeof(double),
+                                         cudaMemcpyHostToDevice, cs));
+            }
+            NGX_CUDA(cudaMemcpyAsync(d_ready + c, h_one, sizeof(int),
+                                     cudaMemcpyHostToDevice, cs));
+            slo += sn;
+        }
+        return NGX_OK;
+    };
+
+    // staged records whose copy has finished go to the caller's array
+    auto flush_owed = [&]() -> int {
+        if (owed_lo < 0) return NGX_OK;
+        NGX_CUDA(cudaEventSynchronize(d2h_ev[owed_ev]));
+        memcpy(res + owed_lo, h_stage + owed_lo,
+               (size_t)owed_n * sizeof(*res));
+        owed_lo = -1;
+        return NGX_OK;
+    };
+
+    const bool trace_d = getenv("NGX_STREAM_TRACE") != nullptr;
+    auto now_us2 = []() {
+        return std::chrono::duration<double, std::micro>(
+            std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    const double t_begin2 = now_us2();
+    // copy the records of batch k out as its chunks complete
+    auto drain = [&](int k) -> int {
+        StreamBuf &B = sb[k & 1];
+        const int lo = k * batch;
+        const int cn = n - lo < batch ? n - lo : batch;
+        const int ndc = (cn + dchunk - 1) / dchunk;
+        volatile int *hf = h_flags + (size_t)(k & 1) * (max_dc + 1);
+        bool finished = false;
+        for (int c = 0; c < ndc; c++) {
+            while (!finished && !hf[c]) {
+                cudaError_t q = cudaStreamQuery(ks[k & 1]);
+                if (q == cudaSuccess) finished = true;
+                else if (q != cudaErrorNotReady) NGX_CUDA(q);
+            }
+            const int slo = c * dchunk;
+            const int sn = cn - slo < dchunk ? cn - slo : dchunk;
+            if (trace_d)
+                fprintf(stderr, "[ngx stream] records %d.. done at %.0f us%s\n",
+                        lo + slo, now_us2() - t_begin2,
+                        finished ? " (kernel finished)" : "");
+            NGX_CUDA(cudaMemcpyAsync(res_dst + lo + slo, B.res + slo,
+                                     sn * sizeof(ngx_lm_result),
+                                     cudaMemcpyDeviceToHost, ds));
+            if (!res_pinned) {
+                const int e = nd2h++ & 1;
+                NGX_CUDA(cudaEventRecord(d2h_ev[e], ds));
+                int r = flush_owed();
+                if (r) return r;
+                owed_lo = lo + slo; owed_n = sn; owed_ev = e;
+            }
+        }
+        NGX_CUDA(cudaStreamSynchronize(ks[k & 1]));
+        NGX_CUDA(cudaEventRecord(B.drained, ds));
+        if (hf[max_dc])
+            return fail(NGX_ERR_CUDA,
+                        "ngx_lm_fit_host: the stamp feed stalled%s%s");
+        return NGX_OK;
+    };
+
+    const bool trace = getenv("NGX_STREAM_TRACE") != nullptr;
+    auto now_us = []() {
+        return std::chrono::duration<double, std::micro>(
+            std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    const double t_begin = trace ? now_us() : 0.0;
+    for (int k = 0; k < nbatch && !rc; k++) {
+        rc = enqueue(k);
+        if (trace)
+            fprintf(stderr, "[ngx stream] batch %d queued at %.0f us\n", k,
+                    now_us() - t_begin);
+        if (!rc && k > 0) rc = drain(k - 1);
+    }
+    if (!rc) rc = drain(nbatch - 1);
+    if (trace)
+        fprintf(stderr, "[ngx stream] kernels done at %.0f us\n",
+                now_us() - t_begin);
+    if (!rc) rc = flush_owed();
+    cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(ks[0]);
+    cudaStreamSynchronize(ks[1]);
+    cudaStreamSynchronize(ds);
+    if (trace)
+        fprintf(stderr, "[ngx stream] call done at %.0f us\n",
+                now_us() - t_begin);
+    if (!res_pinned)
+        for (int i = 0; i < 2; i++) cudaEventDestroy(d2h_ev[i]);
+    return rc;
+}
+#endif
+
+#ifndef NGX_LM_WIDE_TU
 // the host-buffer pipeline behind ngx_lm_fit_host (stamps as doubles) and
 // ngx_lm_fit_host_f32 (stamps as floats: half the bytes over PCIe, which is
 // what bounds the call; widened to double on the device, exactly)
@@ -2477,6 +2976,14 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
                             int ignore_zero_weight, ngx_lm_result *res) {
     NGX_REQUIRE(n >= 0 && images_v && weights_v && jac && guess && res);
     if (n == 0) return NGX_OK;
+    NGX_REQUIRE(nrow >= 1 && ncol >= 1 && npsf >= 0 && npsf <= 16);
+    NGX_REQUIRE(lm_pars && lm_pars->maxfev > 0);
+    if (is_pinned(images_v) && (f32 == 2 || is_pinned(weights_v))
+        && lm_stream_eligible(model, nrow, ncol, npsf, lm_pars))
+        return lm_fit_host_stream(n, model, images_v, weights_v, f32,
+                                  maskbits, jac, nrow, ncol, psf_pars, npsf,
+                                  guess, prior, lm_pars, ignore_zero_weight,
+                                  res);
     const double *images = (const double *)images_v;
     const double *weights = (const double *)weights_v;
     const float *images32 = (const float *)images_v;

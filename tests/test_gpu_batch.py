@@ -237,3 +237,55 @@ def test_pinned_host_memory_helpers(ngx):
     e[...] = 1.5
     assert e.sum() == 22.5
     del e, pim, pwt
+
+
+def test_streamed_host_pipeline(ngx, monkeypatch):
+    """pinned stamps take the streamed pipeline (one persistent launch fed by
+    the copy engine, csrc/ngx_lm.cu:lm_fit_host_stream): the same records, to
+    the bit, as the chunked pipeline, for every host format, ragged chunk
+    boundaries, several batches per call, stamps without a usable pixel and a
+    forward-difference model"""
+    import ngmix_b200 as ng
+    from ngmix_b200 import sims
+    from ngmix_b200.flags import NO_ATTEMPT
+    n = 1501
+    b = sims.make_lm_batch(n, seed0=8800, noise=0.05)
+    im32 = b["images"].astype(np.float32)
+    wt32 = b["weights"].astype(np.float32)
+    wt32[7] = 0.0                      # GMixFatalError("no weights > 0")
+    wt32[1500] = 0.0
+    wt32[33, 10:20, 5:9] = 0.0
+    mask = np.random.RandomState(5).uniform(size=im32.shape) > 0.03
+    wsc = wt32[:, 0, 0].astype(np.float64)
+    wsc[7] = 1.0
+    pin = ng.pinned_copy
+    cases = {
+        "f64": (ngx.lm_fit, (pin(im32.astype("f8")), pin(wt32.astype("f8"))), {}),
+        "f32": (ngx.lm_fit, (pin(im32), pin(wt32)), {}),
+        "compact": (ngx.lm_fit_compact, (pin(im32), pin(wsc)), {"mask": mask}),
+    }
+    small = (pin(b["jac"]), pin(b["psf"]), pin(b["guess"]))
+    for name, (fn, planes, kw) in cases.items():
+        monkeypatch.setenv("NGX_NO_STREAM", "1")
+        want = fn("exp", *planes, *small, **kw)
+        monkeypatch.setenv("NGX_NO_STREAM", "0")
+        _same_records(fn("exp", *planes, *small, **kw), want)
+        # pageable small arrays and a pinned result array
+        out = ng.pinned_empty((n,), ngx.LM_RESULT_DTYPE)
+        got = fn("exp", *planes, b["jac"], b["psf"], b["guess"], out=out, **kw)
+        _same_records(got, want)
+        # several batches per call, the last one short
+        monkeypatch.setenv("NGX_STREAM_BATCH", "400")
+        _same_records(fn("exp", *planes, *small, **kw), want)
+        monkeypatch.delenv("NGX_STREAM_BATCH")
+        if name != "compact":
+            assert want["flags"][7] == NO_ATTEMPT
+            assert want["flags"][1500] == NO_ATTEMPT
+        assert (want["flags"] == 0).sum() > 1400
+    # forward differences (lmdif) from streamed stamps
+    bb = sims.make_bdf_batch(300, seed0=8900, dims=(40, 40))
+    args = [pin(bb[k]) for k in ("images", "weights", "jac", "psf", "guess")]
+    monkeypatch.setenv("NGX_NO_STREAM", "1")
+    want = ngx.lm_fit("bdf", *args)
+    monkeypatch.setenv("NGX_NO_STREAM", "0")
+    _same_records(ngx.lm_fit("bdf", *args), want)
