@@ -623,8 +623,9 @@ def main():
             "h2d_bytes_per_step": int(h2d - h_images.numel() * 8),
             "d2h_bytes_per_step": d2h,
             "api": "ngmix_b200._lib.lm_fit on float32 host stamps -> "
-                   "ngx_lm_fit_host_f32 (pinned host buffers, chunked H2D "
-                   "overlapped with the fits, widened on the device: "
+                   "ngx_lm_fit_host_f32 (pinned host buffers; one "
+                   "persistent launch consumes the stamps as the copy "
+                   "engine lands them and widens them while staging: "
                    "bit-identical to the float64 call)"},
         "e2e_f64_stamps": {
             "value": world * nobj * args.steps / e2e_s,
