@@ -652,7 +652,8 @@ def main():
             / ((h2d - h_images.numel() * 8) / nobj)},
         "e2e_pageable": {
             "value": world * nobj / e2ep_s, "unit": "fits/s",
-            "api": "the float64 call on ordinary (pageable) numpy arrays; "
+            "api": "the float64 call on ordinary (pageable) numpy arrays: "
+                   "staged into pinned slots by a pool of host threads; "
                    "ngmix_b200.pinned_empty / pinned() give the pinned rate"},
         "gpu_launches": args.steps,   # k_lm_fit launches in the timed region
         "roofline": {

@@ -1,0 +1,93 @@
+// A small pool of host threads that copies a block of pageable memory into a
+// pinned staging buffer in parallel.  cudaMemcpy from pageable memory stages
+// through the driver on one thread (~10 GB/s); a few threads reach several
+// times that, which is what bounds the *_host calls on ordinary numpy arrays.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include <string.h>
+#include <stdlib.h>
+#include <unistd.h>
+
+namespace ngx {
+
+class CopyPool {
+public:
+    // the process-wide pool (recreated in a forked child, whose threads are
+    // gone); `use` serialises callers
+    static CopyPool &get() {
+        static std::mutex mk;
+        static CopyPool *pool = nullptr;
+        std::lock_guard<std::mutex> g(mk);
+        if (!pool || pool->pid_ != getpid()) pool = new CopyPool();
+        return *pool;
+    }
+    int nthreads() const { return (int)workers_.size() + 1; }
+
+    // dst[0:bytes) = src[0:bytes), split over the pool and the caller
+    void copy(void *dst, const void *src, size_t bytes) {
+        const int nt = nthreads();
+        if (nt == 1 || bytes < (size_t)1 << 20) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        std::lock_guard<std::mutex> use(use_);
+        size_t piece = (bytes / nt + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            dst_ = (char *)dst; src_ = (const char *)src;
+            bytes_ = bytes; piece_ = piece;
+            pending_.store(nt - 1, std::memory_order_relaxed);
+            gen_++;
+        }
+        cv_.notify_all();
+        run_piece(0);
+        while (pending_.load(std::memory_order_acquire) != 0)
+            std::this_thread::yield();
+    }
+
+private:
+    CopyPool() : pid_(getpid()) {
+        int nt = 6;
+        if (const char *e = getenv("NGX_STAGE_THREADS")) nt = atoi(e);
+        unsigned hw = std::thread::hardware_concurrency();
+        if (hw && nt > (int)hw) nt = (int)hw;
+        if (nt < 1) nt = 1;
+        if (nt > 32) nt = 32;
+        for (int i = 1; i < nt; i++)
+            workers_.emplace_back([this, i] { loop(i); });
+        for (auto &w : workers_) w.detach();
+    }
+    void run_piece(int i) {
+        size_t lo = piece_ * (size_t)i;
+        if (lo >= bytes_) return;
+        size_t n = bytes_ - lo < piece_ ? bytes_ - lo : piece_;
+        memcpy(dst_ + lo, src_ + lo, n);
+    }
+    void loop(int i) {
+        unsigned long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+            }
+            run_piece(i);
+            pending_.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    pid_t pid_;
+    std::vector<std::thread> workers_;
+    std::mutex m_, use_;
+    std::condition_variable cv_;
+    unsigned long gen_ = 0;
+    std::atomic<int> pending_{0};
+    char *dst_ = nullptr;
+    const char *src_ = nullptr;
+    size_t bytes_ = 0, piece_ = 0;
+};
+
+}  // namespace ngx

@@ -30,10 +30,12 @@
 // the other CTAs resident on the SM keep the fp64 pipe busy.
 #include <cuda_pipeline.h>
 #include <chrono>
+#include <functional>
 #include <mutex>
 #include <vector>
 #include "ngx_core.cuh"
 #include "ngx_host.cuh"
+#include "ngx_copy_pool.h"
 #include "ngx_lm_solve.cuh"
 #include "ngx_prior.cuh"
 
@@ -2747,6 +2749,22 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
                                cudaHostAllocMapped));
         cap_hflags = need_hflags;
     }
+    // pageable stamps go through a ring of pinned slots, filled by a few host
+    // threads (ngx_copy_pool.h) while the copy engine drains the other slots
+    const bool in_pinned = is_pinned(images_v)
+        && (compact || is_pinned(weights_v));
+    constexpr int NSLOT = 4;
+    constexpr size_t SLOT_BYTES = (size_t)16 << 20;
+    static thread_local char *ring = nullptr;
+    static thread_local cudaEvent_t slot_ev[NSLOT];
+    static thread_local unsigned ring_next = 0;
+    if (!in_pinned && !ring) {
+        NGX_CUDA(cudaHostAlloc((void **)&ring, NSLOT * SLOT_BYTES,
+                               cudaHostAllocDefault));
+        for (int i = 0; i < NSLOT; i++)
+            NGX_CUDA(cudaEventCreateWithFlags(&slot_ev[i],
+                                              cudaEventDisableTiming));
+    }
     const bool res_pinned = is_pinned(res);
     if (!res_pinned && (size_t)n > cap_stage) {
         if (h_stage) cudaFreeHost(h_stage);
@@ -2767,6 +2785,37 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
                                               cudaEventDisableTiming));
     int rc = NGX_OK;
     int owed_lo = -1, owed_n = 0, owed_ev = 0, nd2h = 0;
+
+    int next_c[2] = {0, 0};     // next done-chunk to copy out, per buffer
+    std::function<int(int, bool)> drain;
+    int cur_batch = -1;
+    // a large host-to-device copy on the copy stream
+    auto h2d = [&](void *dst, const void *src, size_t bytes) -> int {
+        if (in_pinned) {
+            NGX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice,
+                                     cs));
+            return NGX_OK;
+        }
+        CopyPool &pool = CopyPool::get();
+        for (size_t off = 0; off < bytes; off += SLOT_BYTES) {
+            const size_t nb = bytes - off < SLOT_BYTES ? bytes - off
+                                                       : SLOT_BYTES;
+            const int slot = (int)(ring_next++ % NSLOT);
+            NGX_CUDA(cudaEventSynchronize(slot_ev[slot]));
+            pool.copy(ring + slot * SLOT_BYTES, (const char *)src + off, nb);
+            NGX_CUDA(cudaMemcpyAsync((char *)dst + off,
+                                     ring + slot * SLOT_BYTES, nb,
+                                     cudaMemcpyHostToDevice, cs));
+            NGX_CUDA(cudaEventRecord(slot_ev[slot], cs));
+            // records that are ready leave while the host is busy copying
+            for (int kk = cur_batch - 1; kk <= cur_batch; kk++)
+                if (kk >= 0) {
+                    int r = drain(kk, false);
+                    if (r) return r;
+                }
+        }
+        return NGX_OK;
+    };
 
     // queue the input copies of batch k and launch its kernel
     auto enqueue = [&](int k) -> int {
@@ -2802,6 +2851,7 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
                           (size_t)(max_rc + max_dc) * sizeof(int))))
             return r;
         int *d_ready = B.flags, *d_done = B.flags + max_rc;
+        next_c[k & 1] = 0;
         // the buffers are free once the records of batch k-2 are on the host
         NGX_CUDA(cudaStreamWaitEvent(cs, B.drained, 0));
         NGX_CUDA(cudaMemsetAsync(B.flags, 0,
@@ -2827,15 +2877,16 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
                        prior, lm_pars, ignore_zero_weight, B.res, ks[k & 1]);
         g_lm_feed = nullptr;
         if (r) return r;
+        cur_batch = k;
         for (int c = 0, slo = 0; slo < cn; c++) {
             const int want = c < 2 ? S : c == 2 ? 2 * S : c == 3 ? 4 * S
                                                          : rchunk;
             const int sn = cn - slo < want ? cn - slo : want;
             const size_t g = (size_t)(lo + slo);
-            NGX_CUDA(cudaMemcpyAsync((char *)B.in_a + (size_t)slo * ntot * esz,
-                                     (const char *)images_v + g * ntot * esz,
-                                     (size_t)sn * ntot * esz,
-                                     cudaMemcpyHostToDevice, cs));
+            if ((r = h2d((char *)B.in_a + (size_t)slo * ntot * esz,
+                         (const char *)images_v + g * ntot * esz,
+                         (size_t)sn * ntot * esz)))
+                return r;
             if (compact) {
                 NGX_CUDA(cudaMemcpyAsync(
                     B.ws + slo, (const double *)weights_v + g,
@@ -2844,11 +2895,10 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
                     NGX_CUDA(cudaMemcpyAsync(
                         B.mask + (size_t)slo * nmb, maskbits + g * nmb,
                         (size_t)sn * nmb, cudaMemcpyHostToDevice, cs));
-            } else {
-                NGX_CUDA(cudaMemcpyAsync(
-                    (char *)B.in_b + (size_t)slo * ntot * esz,
-                    (const char *)weights_v + g * ntot * esz,
-                    (size_t)sn * ntot * esz, cudaMemcpyHostToDevice, cs));
+            } else if ((r = h2d((char *)B.in_b + (size_t)slo * ntot * esz,
+                                (const char *)weights_v + g * ntot * esz,
+                                (size_t)sn * ntot * esz))) {
+                return r;
             }
             if (c == 0 || (c >= 4 && (c - 4) % 8 == 0)) {
                 // the small per-stamp arrays: of the first 8S stamps, then
@@ -2892,19 +2942,21 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
             std::chrono::steady_clock::now().time_since_epoch()).count();
     };
     const double t_begin2 = now_us2();
-    // copy the records of batch k out as its chunks complete
-    auto drain = [&](int k) -> int {
+    // copy the records of batch k out as its chunks complete (block = false:
+    // only those that are complete now)
+    drain = [&](int k, bool block) -> int {
         StreamBuf &B = sb[k & 1];
         const int lo = k * batch;
         const int cn = n - lo < batch ? n - lo : batch;
         const int ndc = (cn + dchunk - 1) / dchunk;
         volatile int *hf = h_flags + (size_t)(k & 1) * (max_dc + 1);
         bool finished = false;
-        for (int c = 0; c < ndc; c++) {
+        for (int &c = next_c[k & 1]; c < ndc; c++) {
             while (!finished && !hf[c]) {
                 cudaError_t q = cudaStreamQuery(ks[k & 1]);
                 if (q == cudaSuccess) finished = true;
                 else if (q != cudaErrorNotReady) NGX_CUDA(q);
+                else if (!block) return NGX_OK;
             }
             const int slo = c * dchunk;
             const int sn = cn - slo < dchunk ? cn - slo : dchunk;
@@ -2923,6 +2975,7 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
                 owed_lo = lo + slo; owed_n = sn; owed_ev = e;
             }
         }
+        if (!block) return NGX_OK;
         NGX_CUDA(cudaStreamSynchronize(ks[k & 1]));
         NGX_CUDA(cudaEventRecord(B.drained, ds));
         if (hf[max_dc])
@@ -2942,9 +2995,9 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
         if (trace)
             fprintf(stderr, "[ngx stream] batch %d queued at %.0f us\n", k,
                     now_us() - t_begin);
-        if (!rc && k > 0) rc = drain(k - 1);
+        if (!rc && k > 0) rc = drain(k - 1, true);
     }
-    if (!rc) rc = drain(nbatch - 1);
+    if (!rc) rc = drain(nbatch - 1, true);
     if (trace)
         fprintf(stderr, "[ngx stream] kernels done at %.0f us\n",
                 now_us() - t_begin);
@@ -2978,8 +3031,7 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
     if (n == 0) return NGX_OK;
     NGX_REQUIRE(nrow >= 1 && ncol >= 1 && npsf >= 0 && npsf <= 16);
     NGX_REQUIRE(lm_pars && lm_pars->maxfev > 0);
-    if (is_pinned(images_v) && (f32 == 2 || is_pinned(weights_v))
-        && lm_stream_eligible(model, nrow, ncol, npsf, lm_pars))
+    if (lm_stream_eligible(model, nrow, ncol, npsf, lm_pars))
         return lm_fit_host_stream(n, model, images_v, weights_v, f32,
                                   maskbits, jac, nrow, ncol, psf_pars, npsf,
                                   guess, prior, lm_pars, ignore_zero_weight,

@@ -274,8 +274,15 @@ def test_streamed_host_pipeline(ngx, monkeypatch):
         out = ng.pinned_empty((n,), ngx.LM_RESULT_DTYPE)
         got = fn("exp", *planes, b["jac"], b["psf"], b["guess"], out=out, **kw)
         _same_records(got, want)
+        # ordinary (pageable) numpy stamps: staged through pinned slots by
+        # the copy pool (csrc/ngx_copy_pool.h)
+        pageable = [np.array(p) for p in planes]
+        _same_records(fn("exp", *pageable, b["jac"], b["psf"], b["guess"],
+                         **kw), want)
         # several batches per call, the last one short
         monkeypatch.setenv("NGX_STREAM_BATCH", "400")
+        _same_records(fn("exp", *pageable, b["jac"], b["psf"], b["guess"],
+                         **kw), want)
         _same_records(fn("exp", *planes, *small, **kw), want)
         monkeypatch.delenv("NGX_STREAM_BATCH")
         if name != "compact":
