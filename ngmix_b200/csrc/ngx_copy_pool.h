@@ -30,7 +30,7 @@ public:
     // dst[0:bytes) = src[0:bytes), split over the pool and the caller
     void copy(void *dst, const void *src, size_t bytes) {
         const int nt = nthreads();
-        if (nt == 1 || bytes < (size_t)1 << 20) {
+        if (nt == 1 || bytes < (size_t)2 << 20) {
             memcpy(dst, src, bytes);
             return;
         }

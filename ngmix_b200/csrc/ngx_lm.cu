@@ -3031,7 +3031,17 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
     if (n == 0) return NGX_OK;
     NGX_REQUIRE(nrow >= 1 && ncol >= 1 && npsf >= 0 && npsf <= 16);
     NGX_REQUIRE(lm_pars && lm_pars->maxfev > 0);
-    if (lm_stream_eligible(model, nrow, ncol, npsf, lm_pars))
+    // streaming pays once there is more than one chunk to overlap: two waves
+    // of pinned stamps; pageable ones from ~32 MB (below that the driver's
+    // own staging copy is as fast as waking the copy pool)
+    const size_t plane_bytes = (size_t)n * nrow * ncol
+        * (f32 ? sizeof(float) : sizeof(double)) * (f32 == 2 ? 1 : 2);
+    const bool pinned_in = is_pinned(images_v)
+        && (f32 == 2 || is_pinned(weights_v));
+    const bool worth = pinned_in ? n >= 2 * sm_count()
+                                 : plane_bytes >= ((size_t)32 << 20);
+    if ((worth || getenv("NGX_STREAM_ALWAYS"))
+        && lm_stream_eligible(model, nrow, ncol, npsf, lm_pars))
         return lm_fit_host_stream(n, model, images_v, weights_v, f32,
                                   maskbits, jac, nrow, ncol, psf_pars, npsf,
                                   guess, prior, lm_pars, ignore_zero_weight,

@@ -265,6 +265,8 @@ def test_streamed_host_pipeline(ngx, monkeypatch):
         "compact": (ngx.lm_fit_compact, (pin(im32), pin(wsc)), {"mask": mask}),
     }
     small = (pin(b["jac"]), pin(b["psf"]), pin(b["guess"]))
+    # small calls keep the chunked pipeline unless told otherwise
+    monkeypatch.setenv("NGX_STREAM_ALWAYS", "1")
     for name, (fn, planes, kw) in cases.items():
         monkeypatch.setenv("NGX_NO_STREAM", "1")
         want = fn("exp", *planes, *small, **kw)
