@@ -3,8 +3,10 @@
 // through the driver on one thread (~10 GB/s); a few threads reach several
 // times that, which is what bounds the *_host calls on ordinary numpy arrays.
 #pragma once
+#include <cuda_runtime.h>
 #include <atomic>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -88,6 +90,62 @@ private:
     char *dst_ = nullptr;
     const char *src_ = nullptr;
     size_t bytes_ = 0, piece_ = 0;
+};
+
+// Host-to-device copies of pageable memory through a ring of pinned slots: the
+// pool fills a free slot while the copy engine drains the others.  One ring
+// per calling thread.
+class StageRing {
+public:
+    static constexpr int NSLOT = 4;
+    static constexpr size_t SLOT_BYTES = (size_t)16 << 20;
+    static StageRing &get() {
+        static thread_local StageRing r;
+        return r;
+    }
+    // dst (device) = src (pageable host), asynchronously on `st`; `between`
+    // runs after every piece (the caller's chance to do other host work)
+    cudaError_t h2d(void *dst, const void *src, size_t bytes, cudaStream_t st,
+                    const std::function<int()> *between = nullptr,
+                    int *between_rc = nullptr) {
+        if (!ring_) {
+            cudaError_t e = cudaHostAlloc((void **)&ring_, NSLOT * SLOT_BYTES,
+                                          cudaHostAllocDefault);
+            if (e != cudaSuccess) { ring_ = nullptr; return e; }
+            for (int i = 0; i < NSLOT; i++) {
+                e = cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        CopyPool &pool = CopyPool::get();
+        for (size_t off = 0; off < bytes; off += SLOT_BYTES) {
+            const size_t nb = bytes - off < SLOT_BYTES ? bytes - off
+                                                       : SLOT_BYTES;
+            const int slot = (int)(next_++ % NSLOT);
+            cudaError_t e = cudaEventSynchronize(ev_[slot]);
+            if (e != cudaSuccess) return e;
+            char *s = ring_ + (size_t)slot * SLOT_BYTES;
+            pool.copy(s, (const char *)src + off, nb);
+            e = cudaMemcpyAsync((char *)dst + off, s, nb,
+                                cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+            e = cudaEventRecord(ev_[slot], st);
+            if (e != cudaSuccess) return e;
+            if (between) {
+                int r = (*between)();
+                if (r) {
+                    if (between_rc) *between_rc = r;
+                    return cudaSuccess;
+                }
+            }
+        }
+        return cudaSuccess;
+    }
+
+private:
+    char *ring_ = nullptr;
+    cudaEvent_t ev_[NSLOT];
+    unsigned next_ = 0;
 };
 
 }  // namespace ngx

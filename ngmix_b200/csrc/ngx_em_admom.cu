@@ -936,21 +936,25 @@ int ngx_em_host(int n, int variant, const double *images,
                 ngx_em_result *res) {
     NGX_REQUIRE(n >= 0 && images && weights && jac && guess && conf);
     if (n == 0) return NGX_OK;
-    size_t ntot = (size_t)n * nrow * ncol;
-    DevBuf<double> di(ntot, images), dw(ntot, weights);
     DevBuf<ngx_jacobian> dj(n, jac);
     DevBuf<double> dg((size_t)n * ngauss * 6, guess);
     DevBuf<double> dp(npsf > 0 ? (size_t)n * npsf * 6 : 0, psf_pars);
     DevBuf<double> dout((size_t)n * ngauss * 6);
     DevBuf<ngx_em_result> dr(n);
-    NGX_CUDA(di.err); NGX_CUDA(dw.err); NGX_CUDA(dj.err); NGX_CUDA(dg.err);
+    NGX_CUDA(dj.err); NGX_CUDA(dg.err);
     NGX_CUDA(dp.err); NGX_CUDA(dout.err); NGX_CUDA(dr.err);
     NGX_CUDA(dout.zero());
-    int rc = ngx_em(n, variant, di.d, dw.d, dj.d, nrow, ncol, dg.d, ngauss,
-                    npsf > 0 ? dp.d : nullptr, npsf, conf, ignore_zero_weight,
-                    dout.d, dr.d, 0);
+    int rc = planes_pipeline(
+        n, (size_t)nrow * ncol, images, weights,
+        [&](int lo, int cn, const double *di, const double *dw,
+            cudaStream_t q) {
+            return ngx_em(cn, variant, di, dw, dj.d + lo, nrow, ncol,
+                          dg.d + (size_t)lo * ngauss * 6, ngauss,
+                          npsf > 0 ? dp.d + (size_t)lo * npsf * 6 : nullptr,
+                          npsf, conf, ignore_zero_weight,
+                          dout.d + (size_t)lo * ngauss * 6, dr.d + lo, q);
+        });
     if (rc) return rc;
-    NGX_CUDA(cudaDeviceSynchronize());
     NGX_CUDA(dout.to_host(pars_out));
     NGX_CUDA(dr.to_host(res));
     return NGX_OK;
@@ -962,16 +966,18 @@ int ngx_admom_host(int n, const double *images, const double *weights,
                    ngx_admom_result *res) {
     NGX_REQUIRE(n >= 0 && images && weights && jac && guess && conf && res);
     if (n == 0) return NGX_OK;
-    size_t ntot = (size_t)n * nrow * ncol;
-    DevBuf<double> di(ntot, images), dw(ntot, weights);
     DevBuf<ngx_jacobian> dj(n, jac);
     DevBuf<double> dg((size_t)n * 6, guess);
     DevBuf<ngx_admom_result> dr(n);
-    NGX_CUDA(di.err); NGX_CUDA(dw.err); NGX_CUDA(dj.err); NGX_CUDA(dg.err);
-    NGX_CUDA(dr.err);
-    int rc = ngx_admom(n, di.d, dw.d, dj.d, nrow, ncol, dg.d, conf, dr.d, 0);
+    NGX_CUDA(dj.err); NGX_CUDA(dg.err); NGX_CUDA(dr.err);
+    int rc = planes_pipeline(
+        n, (size_t)nrow * ncol, images, weights,
+        [&](int lo, int cn, const double *di, const double *dw,
+            cudaStream_t q) {
+            return ngx_admom(cn, di, dw, dj.d + lo, nrow, ncol,
+                             dg.d + (size_t)lo * 6, conf, dr.d + lo, q);
+        });
     if (rc) return rc;
-    NGX_CUDA(cudaDeviceSynchronize());
     NGX_CUDA(dr.to_host(res));
     return NGX_OK;
 }

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../../include/ngx.h"
+#include "ngx_copy_pool.h"
 
 namespace ngx {
 
@@ -70,5 +71,77 @@ struct DevBuf {
 
 int sm_count();          // cached SM count of the current device
 int smem_optin_bytes();  // cached max opt-in dynamic shared memory per block
+
+// Host planes -> device in chunks of ~32 MB on two streams, each chunk's
+// kernel queued behind its own copies: the copy of chunk c + 1 overlaps the
+// fits of chunk c (pinned planes directly; pageable ones through the pinned
+// slots of ngx_copy_pool.h, filled by a few host threads - the driver's own
+// staging copy runs on one thread at ~10 GB/s, which is four times the
+// kernel's time for admom).  launch(lo, cn, images, weights, stream) queues
+// the work for stamps [lo, lo + cn) whose planes are at the given device
+// addresses.
+template <typename F>
+static int planes_pipeline(int n, size_t npix, const double *images,
+                           const double *weights, F launch) {
+    static thread_local double *d_im[2] = {nullptr, nullptr};
+    static thread_local double *d_wt[2] = {nullptr, nullptr};
+    static thread_local size_t cap = 0;
+    static thread_local cudaStream_t st[2] = {nullptr, nullptr};
+    int chunk = (int)(((size_t)32 << 20) / (npix * sizeof(double)));
+    if (chunk < 4 * sm_count()) chunk = 4 * sm_count();
+    if (chunk > n) chunk = n;
+    const size_t need = (size_t)chunk * npix * sizeof(double);
+    if (!st[0]) {
+        NGX_CUDA(cudaStreamCreate(&st[0]));
+        NGX_CUDA(cudaStreamCreate(&st[1]));
+    }
+    if (need > cap) {
+        NGX_CUDA(cudaDeviceSynchronize());
+        for (int b = 0; b < 2; b++) {
+            cudaFree(d_im[b]); cudaFree(d_wt[b]);
+            d_im[b] = d_wt[b] = nullptr;
+        }
+        cap = 0;
+        for (int b = 0; b < 2; b++) {
+            NGX_CUDA(cudaMalloc((void **)&d_im[b], need));
+            NGX_CUDA(cudaMalloc((void **)&d_wt[b], need));
+        }
+        cap = need;
+    }
+    cudaPointerAttributes pa, pb;
+    const bool pinned = cudaPointerGetAttributes(&pa, images) == cudaSuccess
+        && pa.type == cudaMemoryTypeHost
+        && cudaPointerGetAttributes(&pb, weights) == cudaSuccess
+        && pb.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    int rc = NGX_OK;
+    for (int lo = 0, c = 0; lo < n && rc == NGX_OK; lo += chunk, c++) {
+        const int b = c & 1;
+        const int cn = n - lo < chunk ? n - lo : chunk;
+        const size_t bytes = (size_t)cn * npix * sizeof(double);
+        // buffer set b was last read by the kernels of chunk c - 2, queued
+        // on this same stream
+        if (pinned) {
+            NGX_CUDA(cudaMemcpyAsync(d_im[b], images + (size_t)lo * npix,
+                                     bytes, cudaMemcpyHostToDevice, st[b]));
+            NGX_CUDA(cudaMemcpyAsync(d_wt[b], weights + (size_t)lo * npix,
+                                     bytes, cudaMemcpyHostToDevice, st[b]));
+        } else {
+            NGX_CUDA(StageRing::get().h2d(d_im[b],
+                                          images + (size_t)lo * npix, bytes,
+                                          st[b]));
+            NGX_CUDA(StageRing::get().h2d(d_wt[b],
+                                          weights + (size_t)lo * npix, bytes,
+                                          st[b]));
+        }
+        rc = launch(lo, cn, d_im[b], d_wt[b], st[b]);
+    }
+    cudaError_t e0 = cudaStreamSynchronize(st[0]);
+    cudaError_t e1 = cudaStreamSynchronize(st[1]);
+    if (rc) return rc;
+    NGX_CUDA(e0);
+    NGX_CUDA(e1);
+    return NGX_OK;
+}
 
 }  // namespace ngx

@@ -35,7 +35,6 @@
 #include <vector>
 #include "ngx_core.cuh"
 #include "ngx_host.cuh"
-#include "ngx_copy_pool.h"
 #include "ngx_lm_solve.cuh"
 #include "ngx_prior.cuh"
 
@@ -2429,19 +2428,23 @@ int ngx_lm_fit_coellip_host(int n, int ngauss, const double *images,
     NGX_REQUIRE(n >= 0 && images && weights && jac && guess && res);
     NGX_REQUIRE(ngauss >= 1 && 4 + 2 * ngauss <= LM_MAXP);
     if (n == 0) return NGX_OK;
-    const size_t ntot = (size_t)nrow * ncol;
-    DevBuf<double> di(n * ntot, images), dw(n * ntot, weights);
     DevBuf<ngx_jacobian> dj(n, jac);
     DevBuf<double> dp(npsf > 0 ? (size_t)n * npsf * 6 : 0, psf_pars);
     DevBuf<double> dg((size_t)n * (4 + 2 * ngauss), guess);
     DevBuf<ngx_lm_result_wide> dr(n);
-    NGX_CUDA(di.err); NGX_CUDA(dw.err); NGX_CUDA(dj.err); NGX_CUDA(dp.err);
-    NGX_CUDA(dg.err); NGX_CUDA(dr.err);
-    int rc = ngx_lm_fit_coellip(n, ngauss, di.d, dw.d, dj.d, nrow, ncol,
-                                npsf > 0 ? dp.d : nullptr, npsf, dg.d, prior,
-                                lm_pars, ignore_zero_weight, dr.d, 0);
+    NGX_CUDA(dj.err); NGX_CUDA(dp.err); NGX_CUDA(dg.err); NGX_CUDA(dr.err);
+    const int npg = 4 + 2 * ngauss;
+    int rc = planes_pipeline(
+        n, (size_t)nrow * ncol, images, weights,
+        [&](int lo, int cn, const double *di, const double *dw,
+            cudaStream_t q) {
+            return ngx_lm_fit_coellip(
+                cn, ngauss, di, dw, dj.d + lo, nrow, ncol,
+                npsf > 0 ? dp.d + (size_t)lo * npsf * 6 : nullptr, npsf,
+                dg.d + (size_t)lo * npg, prior, lm_pars, ignore_zero_weight,
+                dr.d + lo, q);
+        });
     if (rc) return rc;
-    NGX_CUDA(cudaDeviceSynchronize());
     NGX_CUDA(dr.to_host(res));
     return NGX_OK;
 }
@@ -2534,6 +2537,13 @@ static int lm_fit_multi_host_impl(int nobj, int model,
             NGX_CUDA(e);
         }
         std::vector<int32_t> rebased[2];
+        cudaPointerAttributes pa, pb;
+        const bool planes_pinned =
+            cudaPointerGetAttributes(&pa, images) == cudaSuccess
+            && pa.type == cudaMemoryTypeHost
+            && cudaPointerGetAttributes(&pb, weights) == cudaSuccess
+            && pb.type == cudaMemoryTypeHost;
+        cudaGetLastError();
         for (int lo = 0, c = 0; lo < nobj && rc == NGX_OK; lo += chunk, c++) {
             const int b = c & 1;
             const int hi = lo + chunk < nobj ? lo + chunk : nobj;
@@ -2557,12 +2567,21 @@ static int lm_fit_multi_host_impl(int nobj, int model,
                             cudaMemcpyHostToDevice, q);
             cudaMemcpyAsync(dsb, stamp_band + s0, sizeof(int32_t) * m,
                             cudaMemcpyHostToDevice, q);
-            cudaMemcpyAsync(di, images + (size_t)s0 * ntot,
-                            sizeof(double) * m * ntot, cudaMemcpyHostToDevice,
-                            q);
-            cudaMemcpyAsync(dw, weights + (size_t)s0 * ntot,
-                            sizeof(double) * m * ntot, cudaMemcpyHostToDevice,
-                            q);
+            if (planes_pinned) {
+                cudaMemcpyAsync(di, images + (size_t)s0 * ntot,
+                                sizeof(double) * m * ntot,
+                                cudaMemcpyHostToDevice, q);
+                cudaMemcpyAsync(dw, weights + (size_t)s0 * ntot,
+                                sizeof(double) * m * ntot,
+                                cudaMemcpyHostToDevice, q);
+            } else {
+                // pageable planes: through pinned slots filled by the copy
+                // pool (the driver's own staging copy runs on one thread)
+                StageRing::get().h2d(di, images + (size_t)s0 * ntot,
+                                     sizeof(double) * m * ntot, q);
+                StageRing::get().h2d(dw, weights + (size_t)s0 * ntot,
+                                     sizeof(double) * m * ntot, q);
+            }
             cudaMemcpyAsync(dj, jac + s0, sizeof(ngx_jacobian) * m,
                             cudaMemcpyHostToDevice, q);
             if (npf)
@@ -2753,18 +2772,6 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
     // threads (ngx_copy_pool.h) while the copy engine drains the other slots
     const bool in_pinned = is_pinned(images_v)
         && (compact || is_pinned(weights_v));
-    constexpr int NSLOT = 4;
-    constexpr size_t SLOT_BYTES = (size_t)16 << 20;
-    static thread_local char *ring = nullptr;
-    static thread_local cudaEvent_t slot_ev[NSLOT];
-    static thread_local unsigned ring_next = 0;
-    if (!in_pinned && !ring) {
-        NGX_CUDA(cudaHostAlloc((void **)&ring, NSLOT * SLOT_BYTES,
-                               cudaHostAllocDefault));
-        for (int i = 0; i < NSLOT; i++)
-            NGX_CUDA(cudaEventCreateWithFlags(&slot_ev[i],
-                                              cudaEventDisableTiming));
-    }
     const bool res_pinned = is_pinned(res);
     if (!res_pinned && (size_t)n > cap_stage) {
         if (h_stage) cudaFreeHost(h_stage);
@@ -2796,25 +2803,18 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
                                      cs));
             return NGX_OK;
         }
-        CopyPool &pool = CopyPool::get();
-        for (size_t off = 0; off < bytes; off += SLOT_BYTES) {
-            const size_t nb = bytes - off < SLOT_BYTES ? bytes - off
-                                                       : SLOT_BYTES;
-            const int slot = (int)(ring_next++ % NSLOT);
-            NGX_CUDA(cudaEventSynchronize(slot_ev[slot]));
-            pool.copy(ring + slot * SLOT_BYTES, (const char *)src + off, nb);
-            NGX_CUDA(cudaMemcpyAsync((char *)dst + off,
-                                     ring + slot * SLOT_BYTES, nb,
-                                     cudaMemcpyHostToDevice, cs));
-            NGX_CUDA(cudaEventRecord(slot_ev[slot], cs));
-            // records that are ready leave while the host is busy copying
+        // records that are ready leave while the host is busy copying
+        const std::function<int()> between = [&]() -> int {
             for (int kk = cur_batch - 1; kk <= cur_batch; kk++)
                 if (kk >= 0) {
                     int r = drain(kk, false);
                     if (r) return r;
                 }
-        }
-        return NGX_OK;
+            return NGX_OK;
+        };
+        int brc = NGX_OK;
+        NGX_CUDA(StageRing::get().h2d(dst, src, bytes, cs, &between, &brc));
+        return brc;
     };
 
     // queue the input copies of batch k and launch its kernel

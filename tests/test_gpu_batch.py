@@ -67,6 +67,36 @@ def test_batch_em_admom_equal_host_call(ngx):
     assert np.all(npix == 625) and pix.shape == (32, 625)
 
 
+def test_em_admom_host_calls_pipelined(ngx):
+    """the host calls move the planes in chunks on two streams (pageable
+    planes through the copy pool): several chunks, a short last one, pageable
+    and pinned planes give the records of the resident batch"""
+    import ngmix_b200 as ngmix
+    from ngmix_b200 import sims
+    n = 15000          # chunks of 6710 stamps at 25x25
+    b = sims.make_psf_batch(64, seed0=8300)
+    rep = (n + 63) // 64
+    tile = lambda a: np.ascontiguousarray(
+        np.concatenate([a] * rep, axis=0)[:n])
+    im, wt, jac = tile(b["images"]), tile(b["weights"]), tile(b["jac"])
+    im += np.random.RandomState(1).normal(0.0, 1e-5, size=im.shape)
+    ag = tile(b["am_guess"])
+    eg = tile(b["em_guess"])
+    ob = ngmix.ObservationBatch.from_arrays(im, wt, jac)
+    want = ob.admom(ag)
+    _same_records(ngx.admom(im, wt, jac, ag), want)
+    pim, pwt = ngmix.pinned_copy(im), ngmix.pinned_copy(wt)
+    _same_records(ngx.admom(pim, pwt, jac, ag), want)
+    conf_kw = dict(maxiter=40)
+    wres, wpars = ob.em(eg, **conf_kw)
+    res, pars = ngx.em(im, wt, jac, eg, **conf_kw)
+    _same_records(res, wres)
+    assert np.array_equal(pars, wpars)
+    res, pars = ngx.em(pim, pwt, jac, eg, **conf_kw)
+    _same_records(res, wres)
+    assert np.array_equal(pars, wpars)
+
+
 def test_psf_em_to_galaxy_fit_chain_on_device(ngx):
     """PSF stamps -> EM mixtures (device) -> psf of the galaxy batch -> LM"""
     import ngmix_b200 as ngmix

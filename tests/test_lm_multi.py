@@ -214,6 +214,27 @@ def test_gpu_multi_batch_vs_oracle(ngx, ora):
     assert recs["flags"][2] == 1 and recs["nfev"][2] == 0
 
 
+@pytest.mark.gpu
+def test_gpu_multi_pageable_equals_pinned(ngx):
+    """pageable planes are staged through pinned slots by the copy pool
+    (csrc/ngx_copy_pool.h): the same records as from pinned planes"""
+    import ngmix_b200 as ngmix
+    from ngmix_b200 import sims
+    nobj, nep = 700, 3
+    b = sims.make_lm_batch(nobj * nep, seed0=78000, noise=0.05)
+    starts = np.arange(nobj + 1) * nep
+    bands = np.zeros(nobj * nep, dtype="i4")
+    guess = b["guess"][::nep].copy()
+    args = (b["jac"], b["psf"], guess)
+    pageable = ngmix.fit_batch_multi("exp", starts, bands, 1, b["images"],
+                                     b["weights"], *args)
+    pim = ngmix.pinned_copy(b["images"])
+    pwt = ngmix.pinned_copy(b["weights"])
+    pinned = ngmix.fit_batch_multi("exp", starts, bands, 1, pim, pwt, *args)
+    assert pageable.tobytes() == pinned.tobytes()
+    assert (pinned["flags"] == 0).sum() > 650
+
+
 def _ngx_prior_fd(c):
     """the priors of gen_golden.gen_lm_multi_fd"""
     import ngmix_b200 as ngmix
