@@ -2513,30 +2513,61 @@ static int lm_fit_multi_host_impl(int nobj, int model,
         size_t m = (size_t)(stamp_start[hi] - stamp_start[lo]);
         if (m > max_st) max_st = m;
     }
-    cudaStream_t st[2];
-    NGX_CUDA(cudaStreamCreate(&st[0]));
-    NGX_CUDA(cudaStreamCreate(&st[1]));
+    // streams and device buffers persist per calling thread (allocation and
+    // release per call cost more than the fits of a small batch, and
+    // cudaFree synchronises the device)
+    static thread_local cudaStream_t st[2] = {nullptr, nullptr};
+    static thread_local char *arena[2] = {nullptr, nullptr};
+    static thread_local size_t arena_cap = 0;
+    if (!st[0]) {
+        NGX_CUDA(cudaStreamCreate(&st[0]));
+        NGX_CUDA(cudaStreamCreate(&st[1]));
+    }
+    const size_t npf = npsf > 0 ? (size_t)npsf * 6 : 0;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_ss = 0;
+    const size_t o_sb = o_ss + al(sizeof(int32_t) * (chunk + 1));
+    const size_t o_im = o_sb + al(sizeof(int32_t) * max_st);
+    const size_t o_wt = o_im + al(sizeof(double) * max_st * ntot);
+    const size_t o_jac = o_wt + al(sizeof(double) * max_st * ntot);
+    const size_t o_psf = o_jac + al(sizeof(ngx_jacobian) * max_st);
+    const size_t o_g = o_psf + al(sizeof(double) * max_st * npf);
+    const size_t o_res = o_g + al(sizeof(double) * (size_t)chunk * np);
+    const size_t need = o_res + al(sizeof(RES) * (size_t)chunk);
+    if (need > arena_cap) {
+        NGX_CUDA(cudaDeviceSynchronize());
+        for (int b = 0; b < 2; b++) {
+            cudaFree(arena[b]);
+            arena[b] = nullptr;
+        }
+        arena_cap = 0;
+        for (int b = 0; b < 2; b++)
+            NGX_CUDA(cudaMalloc((void **)&arena[b], need));
+        arena_cap = need;
+    }
     int rc = NGX_OK;
     {
-        DevBuf<int32_t> dss0(chunk + 1), dss1(chunk + 1);
-        DevBuf<int32_t> dsb0(max_st), dsb1(max_st);
-        DevBuf<double> di0(max_st * ntot), di1(max_st * ntot);
-        DevBuf<double> dw0(max_st * ntot), dw1(max_st * ntot);
-        DevBuf<ngx_jacobian> dj0(max_st), dj1(max_st);
-        const size_t npf = npsf > 0 ? (size_t)npsf * 6 : 0;
-        DevBuf<double> dp0(max_st * npf), dp1(max_st * npf);
-        DevBuf<double> dg0((size_t)chunk * np), dg1((size_t)chunk * np);
-        DevBuf<RES> dr0(chunk), dr1(chunk);
-        cudaError_t e = dss0.err;
-        for (cudaError_t x : {dss1.err, dsb0.err, dsb1.err, di0.err, di1.err,
-                              dw0.err, dw1.err, dj0.err, dj1.err, dp0.err,
-                              dp1.err, dg0.err, dg1.err, dr0.err, dr1.err})
-            if (e == cudaSuccess) e = x;
-        if (e != cudaSuccess) {
-            cudaStreamDestroy(st[0]); cudaStreamDestroy(st[1]);
-            NGX_CUDA(e);
-        }
         std::vector<int32_t> rebased[2];
+        // records come back asynchronously: into the caller's array when it
+        // is pinned, else into a pinned staging array (a device-to-host copy
+        // into pageable memory would block the host until the chunk's fits
+        // are done and keep the next chunk's copies from being queued)
+        static thread_local RES *h_stage = nullptr;
+        static thread_local size_t cap_stage = 0;
+        cudaPointerAttributes pr;
+        const bool res_pinned =
+            cudaPointerGetAttributes(&pr, res) == cudaSuccess
+            && pr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (!res_pinned && (size_t)nobj > cap_stage) {
+            if (h_stage) cudaFreeHost(h_stage);
+            h_stage = nullptr;
+            cap_stage = 0;
+            NGX_CUDA(cudaMallocHost((void **)&h_stage,
+                                    sizeof(RES) * (size_t)nobj));
+            cap_stage = nobj;
+        }
+        RES *res_dst = res_pinned ? res : h_stage;
         cudaPointerAttributes pa, pb;
         const bool planes_pinned =
             cudaPointerGetAttributes(&pa, images) == cudaSuccess
@@ -2551,11 +2582,12 @@ static int lm_fit_multi_host_impl(int nobj, int model,
             const int s0 = stamp_start[lo];
             const size_t m = (size_t)(stamp_start[hi] - s0);
             cudaStream_t q = st[b];
-            int32_t *dss = b ? dss1.d : dss0.d, *dsb = b ? dsb1.d : dsb0.d;
-            double *di = b ? di1.d : di0.d, *dw = b ? dw1.d : dw0.d;
-            ngx_jacobian *dj = b ? dj1.d : dj0.d;
-            double *dp = b ? dp1.d : dp0.d, *dg = b ? dg1.d : dg0.d;
-            RES *dr = b ? dr1.d : dr0.d;
+            char *A = arena[b];
+            int32_t *dss = (int32_t *)(A + o_ss), *dsb = (int32_t *)(A + o_sb);
+            double *di = (double *)(A + o_im), *dw = (double *)(A + o_wt);
+            ngx_jacobian *dj = (ngx_jacobian *)(A + o_jac);
+            double *dp = (double *)(A + o_psf), *dg = (double *)(A + o_g);
+            RES *dr = (RES *)(A + o_res);
             // the rebased starts live in a host vector reused every second
             // chunk: wait for its previous copy before overwriting
             // (buffer set b was last used by chunk c - 2 on the same stream)
@@ -2596,17 +2628,17 @@ static int lm_fit_multi_host_impl(int nobj, int model,
                                    prior, lm_pars, ignore_zero_weight, dr,
                                    wide, q);
             if (rc == NGX_OK)
-                cudaMemcpyAsync(res + lo, dr, sizeof(RES) * cn,
+                cudaMemcpyAsync(res_dst + lo, dr, sizeof(RES) * cn,
                                 cudaMemcpyDeviceToHost, q);
         }
         cudaError_t e0 = cudaStreamSynchronize(st[0]);
         cudaError_t e1 = cudaStreamSynchronize(st[1]);
-        cudaStreamDestroy(st[0]);
-        cudaStreamDestroy(st[1]);
         if (rc) return rc;
         NGX_CUDA(e0);
         NGX_CUDA(e1);
         NGX_CUDA(cudaGetLastError());
+        if (res_dst != res)
+            memcpy(res, res_dst, sizeof(RES) * (size_t)nobj);
     }
     return NGX_OK;
 }
