@@ -509,7 +509,7 @@ struct AMShared {
 // GM: pixel values and variances in a global scratch buffer (stamps too large
 // for shared memory)
 template <bool GM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_admom(int n, const double *__restrict__ images,
         const double *__restrict__ weights,
         const ngx_jacobian *__restrict__ jac, int nrow, int ncol,
@@ -594,8 +594,10 @@ k_admom(int n, const double *__restrict__ images,
                 cs[3] += 1.0;
             }
         }
-        block_sum<4>(cs, scratch);
+        block_sum_to<4>(cs, scratch, sh.red);
         if (threadIdx.x == 0) {
+            cs[0] = sh.red[0]; cs[1] = sh.red[1]; cs[2] = sh.red[2];
+            cs[3] = sh.red[3];
             // clear_result + censums bookkeeping
             out.npix = (int)cs[3];
             out.wsum = 0.0;
@@ -666,27 +668,34 @@ k_admom(int n, const double *__restrict__ images,
                 ms[36] += 1.0;
             }
         }
-        block_sum<37>(ms, scratch);
+        // halving-butterfly reductions, one value per lane (32 + 5 sums): the
+        // unrolled 37 x 5 shuffle trees were most of the kernel's code
+        {
+            double hi[5] = {ms[32], ms[33], ms[34], ms[35], ms[36]};
+            block_sum_to<32>(*(double (*)[32])ms, scratch, sh.red);
+            block_sum_to<5>(hi, scratch, sh.red + 32);
+        }
         if (threadIdx.x == 0) {
-            out.npix = (int)ms[36];
-            out.wsum = ms[35];
-            for (int k = 0; k < 7; k++) out.sums[k] = ms[k];
+            const double *R = sh.red;     // the 37 block totals
+            out.npix = (int)R[36];
+            out.wsum = R[35];
+            for (int k = 0; k < 7; k++) out.sums[k] = R[k];
             int q = 7;
             for (int a = 0; a < 7; a++)
                 for (int b = 0; b <= a; b++) {
-                    out.sums_cov[a * 7 + b] = ms[q];
-                    out.sums_cov[b * 7 + a] = ms[q];
+                    out.sums_cov[a * 7 + b] = R[q];
+                    out.sums_cov[b * 7 + a] = R[q];
                     q++;
                 }
             for (int k = 0; k < 6; k++) out.pars[k] = nan("");
             out.rho4 = nan("");
-            if (ms[5] <= 0.0) {
+            if (R[5] <= 0.0) {
                 sh.flags = NGX_NONPOS_FLUX;
                 sh.done = 1;
             } else {
-                double finv = 1.0 / ms[5];
-                double M1 = ms[2] * finv, M2 = ms[3] * finv;
-                double Tm = ms[4] * finv;
+                double finv = 1.0 / R[5];
+                double M1 = R[2] * finv, M2 = R[3] * finv;
+                double Tm = R[4] * finv;
                 double Irr = 0.5 * (Tm - M1), Icc = 0.5 * (Tm + M1);
                 double Irc = 0.5 * M2;
                 if (Tm <= 0.0) {
@@ -703,7 +712,7 @@ k_admom(int n, const double *__restrict__ images,
                         out.pars[3] = 2.0 * sh.wt.irc;
                         out.pars[4] = sh.wt.icc + sh.wt.irr;
                         out.pars[5] = 1.0;
-                        out.rho4 = ms[6] / ms[5];
+                        out.rho4 = R[6] / R[5];
                         sh.done = 1;
                     } else {
                         if (!conf.cenonly) {
