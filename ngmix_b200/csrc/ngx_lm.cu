@@ -2398,6 +2398,34 @@ int ngx_lm_fit_coellip(int n, int ngauss, const double *images,
     // count (45 for 8 parameters ... 120 for 14): two gaussians run without
     // the register spills of the 14-parameter instantiation
     cudaStream_t st = as_stream(stream);
+    if (a.ntot <= 1024 && a.ngauss <= 64 && 6 * npsf <= 64
+        && !getenv("NGX_COELLIP_256")) {
+        // psf-sized stamps (the usual input of CoellipFitter): 28 tiles keep
+        // two warps busy, not eight (at 256 threads 6.5 of every 7.5 warp
+        // cycles waited at a barrier, profiles/ncu_kernels_r2b.txt); both
+        // planes resident, eight CTAs per SM
+        const int t64 = 64;
+        size_t smem64 = smem - sizeof(double) * 48 * (nwarps - 2)
+            + sizeof(double) * (size_t)a.nq;
+        if (a.np <= 8)
+            return config_and_launch(
+                k_lm_fit<1, 3, 2, 8, false, 64, false, 8, ngx_lm_result_wide>,
+                a, t64, smem64, st);
+        if (a.np <= 10)
+            return config_and_launch(
+                k_lm_fit<1, 3, 2, 8, false, 64, false, 10,
+                         ngx_lm_result_wide>,
+                a, t64, smem64, st);
+        if (a.np <= 12)
+            return config_and_launch(
+                k_lm_fit<1, 3, 2, 8, false, 64, false, 12,
+                         ngx_lm_result_wide>,
+                a, t64, smem64, st);
+        return config_and_launch(
+            k_lm_fit<1, 3, 2, 8, false, 64, false, LM_MAXP,
+                     ngx_lm_result_wide>,
+            a, t64, smem64, st);
+    }
     if (a.np <= 8)
         return config_and_launch(
             k_lm_fit<1, 3, 2, 2, true, 256, false, 8, ngx_lm_result_wide>,

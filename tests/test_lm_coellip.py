@@ -148,7 +148,14 @@ def test_degenerate_coellip_fits_are_chaotic(ora, tmp_path):
 @pytest.mark.parametrize("ngauss,pk", CASES)
 def test_gpu_coellip_matches_reference(ng, ngauss, pk):
     """
-    1 and 2 gaussians: flags, nfev, ier and parameters follow the reference.
+    1 and 2 gaussians: flags, nfev, ier and parameters follow the reference,
+    up to the forward-difference noise floor: the oracle itself, compiled with
+    FMA contraction, differs from its unfused build in the evaluation count of
+    0.2-0.4 % of such fits (one lmdif iteration more or less at the ftol /
+    xtol boundary, the same optimum), and the CUDA kernels differ from the
+    oracle at the same rate (profiles/coellip_parity_r2b.json, 2 x 2000 fits;
+    test_gpu_coellip_evaluation_counts_at_the_noise_floor).  A golden fit may
+    therefore end one iteration apart if it ends at the same point.
     3 to 5 gaussians on a 3-gaussian psf are degenerate (hundreds of
     evaluations along a flat valley) and chaotic in the last bit of the model
     values (test_degenerate_coellip_fits_are_chaotic): there parity means the
@@ -159,9 +166,22 @@ def test_gpu_coellip_matches_reference(ng, ngauss, pk):
     pre = "n%d_%s_" % (ngauss, pk)
     recs = ng.fit_batch_coellip(ngauss, g["images"], g["weights"], g["jac"],
                                 g[pre + "guess"], prior=_prior(ng, ngauss, pk))
+    apart = 0
     for i in range(recs.size):
         if ngauss <= 2:
-            _check(recs[i], g, pre, i, 4 + 2 * ngauss, 0.05)
+            np_ = 4 + 2 * ngauss
+            dn = abs(int(recs["nfev"][i]) - int(g[pre + "nfev"][i]))
+            if dn == 0:
+                _check(recs[i], g, pre, i, np_, 0.05)
+                continue
+            # one lmdif iteration = 1 + npars evaluations
+            apart += 1
+            assert dn <= np_ + 1
+            assert int(recs["flags"][i]) == 0 == int(g[pre + "flags"][i])
+            ref, err = g[pre + "pars"][i], g[pre + "pars_err"][i]
+            assert np.all(np.abs(recs["pars"][i][:np_] - ref)
+                          <= np.maximum(1e-5 * np.abs(ref), 0.05 * err))
+            assert abs(recs["lnprob"][i] / g[pre + "lnprob"][i] - 1) < 1e-5
             continue
         mask = ~np.int32(512 | 1024 | 2048)
         assert int(recs["flags"][i]) & mask == \
@@ -169,6 +189,48 @@ def test_gpu_coellip_matches_reference(ng, ngauss, pk):
         if int(g[pre + "flags"][i]) == 0 and int(recs["flags"][i]) == 0:
             assert abs(recs["lnprob"][i] / g[pre + "lnprob"][i] - 1) < 5e-3
             assert int(recs["dof"][i]) == int(g[pre + "dof"][i])
+    assert apart <= 1
+
+
+@pytest.mark.gpu
+def test_gpu_coellip_evaluation_counts_at_the_noise_floor(ng, ora):
+    """400 one- and two-gaussian fits of psf stamps against the oracle: the
+    same flags everywhere, the same evaluation counts on >= 98.5 % (the
+    oracle's own FMA noise floor is 99.6 - 99.8 %), >= 99 % of the fits within
+    0.05 sigma, all within 0.2 sigma and 1e-5 in ln(prob)"""
+    from ngmix_b200 import sims, _lib
+    n = 400
+    b = sims.make_psf_batch(n, seed0=515151)
+    T = ng.moments.fwhm_to_T(0.263 * 3.5)
+    flux = b["images"].sum(axis=(1, 2))
+    for ngauss in (1, 2):
+        np_ = 4 + 2 * ngauss
+        rng = np.random.RandomState(11)
+        guess = np.zeros((n, np_))
+        guess[:, 0:2] = rng.uniform(-0.01, 0.01, (n, 2))
+        guess[:, 2:4] = rng.uniform(-0.05, 0.05, (n, 2))
+        fr = np.array(ng.guessers._COELLIP_F[ngauss])
+        pr = np.array(ng.guessers._COELLIP_P[ngauss])
+        guess[:, 4:4 + ngauss] = T * fr * rng.uniform(0.99, 1.01, (n, ngauss))
+        guess[:, 4 + ngauss:] = flux[:, None] * pr \
+            * rng.uniform(0.99, 1.01, (n, ngauss))
+        r = _lib.lm_fit_coellip(ngauss, b["images"], b["weights"], b["jac"],
+                                None, guess)
+        same = close = 0
+        for i in range(n):
+            o = ora.lm_fit("coellip", b["images"][i], b["weights"][i],
+                           b["jac"][i], None, guess[i],
+                           prior=ora.make_prior("none"))
+            assert int(r["flags"][i]) == int(o["flags"]) == 0
+            same += int(r["nfev"][i] == o["nfev"])
+            dev = np.abs(r["pars"][i][:np_] - o["pars"][:np_])
+            floor = 1e-5 * np.abs(o["pars"][:np_])
+            close += int(np.all(dev <= np.maximum(
+                floor, 0.05 * o["pars_err"][:np_])))
+            assert np.all(dev <= np.maximum(floor, 0.2 * o["pars_err"][:np_]))
+            assert abs(r["lnprob"][i] / o["lnprob"] - 1) < 1e-5
+        assert same >= int(0.985 * n), same
+        assert close >= int(0.99 * n), close
 
 
 @pytest.mark.gpu
