@@ -125,6 +125,9 @@ static __device__ __noinline__ void wait_ready(const LMArgs &a, int stamp) {
     for (;;) {
         __nanosleep(400);
         if (ld_acquire_sys(f)) return;
+        // a failed call (the host raises err when it cannot queue the rest
+        // of the feed) releases every waiter at once
+        if (*(volatile int *)a.err) return;
         if (global_ns() - t0 > 4000000000ull) {
             *(volatile int *)a.err = 1;
             return;
@@ -2853,6 +2856,10 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
     int rc = NGX_OK;
     int owed_lo = -1, owed_n = 0, owed_ev = 0, nd2h = 0;
 
+    // test hook: stop queueing the feed at input chunk NGX_STREAM_FAIL_AT
+    // (the call must fail promptly and leave the device usable)
+    int fail_at = -1;
+    if (const char *e = getenv("NGX_STREAM_FAIL_AT")) fail_at = atoi(e);
     int next_c[2] = {0, 0};     // next done-chunk to copy out, per buffer
     std::function<int(int, bool)> drain;
     int cur_batch = -1;
@@ -2943,6 +2950,10 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
                                                          : rchunk;
             const int sn = cn - slo < want ? cn - slo : want;
             const size_t g = (size_t)(lo + slo);
+            if (fail_at >= 0 && c == fail_at)
+                return fail(NGX_ERR_CUDA,
+                            "ngx_lm_fit_host: feed interrupted (test hook "
+                            "NGX_STREAM_FAIL_AT)%s%s");
             if ((r = h2d((char *)B.in_a + (size_t)slo * ntot * esz,
                          (const char *)images_v + g * ntot * esz,
                          (size_t)sn * ntot * esz)))
@@ -3062,6 +3073,11 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
         fprintf(stderr, "[ngx stream] kernels done at %.0f us\n",
                 now_us() - t_begin);
     if (!rc) rc = flush_owed();
+    if (rc) {
+        // release kernels that still wait for stamps that will not come
+        for (int b = 0; b < 2; b++)
+            ((volatile int *)h_flags)[(size_t)b * (max_dc + 1) + max_dc] = 1;
+    }
     cudaStreamSynchronize(cs);
     cudaStreamSynchronize(ks[0]);
     cudaStreamSynchronize(ks[1]);

@@ -328,3 +328,25 @@ def test_streamed_host_pipeline(ngx, monkeypatch):
     want = ngx.lm_fit("bdf", *args)
     monkeypatch.setenv("NGX_NO_STREAM", "0")
     _same_records(ngx.lm_fit("bdf", *args), want)
+
+
+def test_streamed_pipeline_failure_releases_the_device(ngx, monkeypatch):
+    """a feed that stops half way (test hook) must fail the call promptly -
+    the resident kernel's waiters are released through the error flag, not
+    by the 4 s timeout per stamp - and the next call must work"""
+    import time
+    import ngmix_b200 as ng
+    from ngmix_b200 import sims
+    n = 3000
+    b = sims.make_lm_batch(n, seed0=8850, noise=0.05)
+    pin = ng.pinned_copy
+    args = [pin(b[k].astype("f4") if k in ("images", "weights") else b[k])
+            for k in ("images", "weights", "jac", "psf", "guess")]
+    want = ngx.lm_fit("exp", *args)
+    monkeypatch.setenv("NGX_STREAM_FAIL_AT", "3")
+    t0 = time.perf_counter()
+    with pytest.raises(Exception):
+        ngx.lm_fit("exp", *args)
+    assert time.perf_counter() - t0 < 3.0
+    monkeypatch.delenv("NGX_STREAM_FAIL_AT")
+    _same_records(ngx.lm_fit("exp", *args), want)
