@@ -558,7 +558,7 @@ def lm_fit_coellip(ngauss, images, weights, jac, psf_pars, guess, prior=None,
 def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
                  psf_pars, guess, prior=None, maxfev=4000, ftol=1.0e-5,
                  xtol=1.0e-5, ignore_zero_weight=True,
-                 analytic_jacobian=True):
+                 analytic_jacobian=True, bounds=None):
     """
     Fitter.go on ObsList / MultiBandObsList input for a batch of objects:
     object i owns stamps stamp_start[i]:stamp_start[i+1] of images/weights
@@ -589,6 +589,7 @@ def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
         npsf = psf_pars.shape[1]
     pr = prior if prior is not None else Prior()
     lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)
+    lmp.set_bounds(bounds)
     wide = npars > 8
     res = np.zeros(nobj, dtype=LM_RESULT_WIDE_DTYPE if wide
                    else LM_RESULT_DTYPE)

@@ -141,9 +141,6 @@ def fit_batch_multi(model, stamp_start, stamp_band, nband, images, weights,
     if fit_pars is not None:
         fp.update(fit_pars)
     pr = _prior_record(prior)
-    if getattr(prior, "bounds", None) is not None:
-        raise NotImplementedError(
-            "bounded fits of objects with several stamps")
     if pr is not None and getattr(prior, "nband", nband) != nband:
         raise ValueError("prior has %d flux priors, data has %d bands"
                          % (prior.nband, nband))
@@ -152,7 +149,8 @@ def fit_batch_multi(model, stamp_start, stamp_band, nband, images, weights,
                              maxfev=fp["maxfev"], ftol=fp["ftol"],
                              xtol=fp["xtol"],
                              ignore_zero_weight=ignore_zero_weight,
-                             analytic_jacobian=analytic_jacobian)
+                             analytic_jacobian=analytic_jacobian,
+                             bounds=getattr(prior, "bounds", None))
 
 
 _ERRMSG = {

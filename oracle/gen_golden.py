@@ -1505,6 +1505,141 @@ def gen_lm_multi_fd():
     save("lm_multi_fd", **out)
 
 
+def gen_lm_multi_bounds():
+    """Fitter.go on ObsList / MultiBandObsList inputs with prior.bounds
+    (leastsqbound's transforms, fitters.py:99-108 -> run_leastsq(bounds=)):
+    exp objects with bounded T and per-band fluxes through lmder and lmdif,
+    bdf objects with fracdev in (0, 1) through lmdif.  Run with the
+    1-based-ipvt shim (see _OneBasedMinpack); the fit itself is asserted
+    identical without it."""
+    import ngmix.fitting.leastsqbound as lsb
+    from ngmix.fitting import Fitter
+    from ngmix import priors, joint_prior
+    from ngmix_b200.sims import (diag_jacobian, simple_full_pars,
+                                 bdf_full_pars, convolve_full_pars,
+                                 render_full_pars)
+    rng = np.random.RandomState(27182)
+    configs = [
+        # (nband, epochs per band, model, analytic jacobian)
+        (1, [3], "exp", True), (2, [1, 2], "exp", True),
+        (3, [1, 1, 1], "exp", True), (2, [1, 1], "exp", False),
+        (2, [1, 1], "bdf", False), (1, [2], "bdf", False),
+    ]
+    out = {}
+    icase = 0
+    H = W = 32
+    real = lsb._minpack
+    for nband, nep, model, analytic in configs:
+        for rep in range(2):
+            noise = [0.02, 0.2][rep]
+            g1, g2 = rng.normal(0.0, 0.12, size=2)
+            T = rng.uniform(0.2, 0.8)
+            fracdev = rng.uniform(0.2, 0.8)
+            fluxes = rng.uniform(60.0, 180.0, size=nband)
+            images, weights, jacs, psfs, bands = [], [], [], [], []
+            for b in range(nband):
+                for _ in range(nep[b]):
+                    dy, dx = rng.uniform(-0.5, 0.5, size=2)
+                    jac = diag_jacobian((H - 1) / 2 + dy, (W - 1) / 2 + dx,
+                                        0.263)
+                    ppars = [0.0, 0.0, rng.normal(0, 0.01),
+                             rng.normal(0, 0.01), rng.uniform(0.22, 0.32), 1.0]
+                    psf = simple_full_pars(ppars, "turb")
+                    if model == "exp":
+                        obj = simple_full_pars(
+                            [0.0, 0.0, g1, g2, T, fluxes[b]], "exp")
+                    else:
+                        obj = bdf_full_pars(
+                            [0.0, 0.0, g1, g2, T, fracdev, fluxes[b]])
+                    im = render_full_pars(convolve_full_pars(obj, psf),
+                                          (H, W), jac)
+                    images.append(im + rng.normal(0.0, noise, size=im.shape))
+                    weights.append(np.zeros((H, W)) + 1.0 / noise ** 2)
+                    jacs.append(jac)
+                    psfs.append(psf)
+                    bands.append(b)
+            shared = {"exp": [0.0, 0.0, g1, g2, T],
+                      "bdf": [0.0, 0.0, g1, g2, T, fracdev]}[model]
+            truth = np.array(shared + list(fluxes))
+            guess = truth.copy()
+            guess[0:2] = rng.uniform(-0.01, 0.01, size=2)
+            guess[2:] *= 1.0 + rng.uniform(-0.2, 0.2, size=guess.size - 2)
+            mbobs = ngmix.MultiBandObsList()
+            k = 0
+            for b in range(nband):
+                ol = ngmix.ObsList()
+                for _ in range(nep[b]):
+                    psf_obs = ngmix.Observation(
+                        np.zeros((5, 5)) + 1.0,
+                        gmix=ngmix.GMix(pars=psfs[k].ravel()))
+                    ol.append(ngmix.Observation(
+                        images[k], weight=weights[k],
+                        jacobian=jac_from_record(jacs[k]), psf=psf_obs))
+                    k += 1
+                mbobs.append(ol)
+            cen = priors.CenPrior(0.0, 0.0, 0.263, 0.263, rng=rng)
+            gp = priors.GPriorBA(0.3, rng=rng)
+            if model == "exp" and rep == 0:
+                Tp = priors.Normal(0.4, 1.0, bounds=[0.01, 100.0], rng=rng)
+                Fp = [priors.Normal(100.0, 100.0, bounds=[1.0, 1.0e9],
+                                    rng=rng) for _ in range(nband)]
+                prior = joint_prior.PriorSimpleSep(cen, gp, Tp, Fp)
+            elif model == "exp":
+                # tight two-sided and one-sided bounds: the transforms take
+                # part in many iterations
+                Tp = priors.Normal(0.5, 1.0, bounds=[0.05, 5.0], rng=rng)
+                Fp = [priors.Normal(100.0, 100.0, bounds=[1.0, None],
+                                    rng=rng) for _ in range(nband)]
+                prior = joint_prior.PriorSimpleSep(cen, gp, Tp, Fp)
+            else:
+                Tp = priors.FlatPrior(-1.0, 1.0e3, rng=rng)
+                Fp = [priors.FlatPrior(-100.0, 1.0e9, rng=rng)
+                      for _ in range(nband)]
+                prior = joint_prior.PriorBDFSep(
+                    cen, gp, Tp,
+                    priors.Normal(0.5, 0.3, rng=rng, bounds=[0.0, 1.0]), Fp)
+            assert prior.bounds is not None
+            fitter = Fitter(model=model, prior=prior,
+                            analytic_jacobian=analytic)
+            obs_in = mbobs if nband > 1 else mbobs[0]
+            r0 = fitter.go(obs=obs_in, guess=guess.copy())
+            lsb._minpack = _OneBasedMinpack(real)
+            try:
+                r = fitter.go(obs=obs_in, guess=guess.copy())
+            finally:
+                lsb._minpack = real
+            assert r["nfev"] == r0["nfev"]
+            assert np.array_equal(r["pars"], r0["pars"])
+            p = "c%d_" % icase
+            out[p + "images"] = np.array(images)
+            out[p + "weights"] = np.array(weights)
+            out[p + "jac"], out[p + "psf"] = np.array(jacs), np.array(psfs)
+            out[p + "bands"] = np.array(bands, dtype="i4")
+            out[p + "guess"] = guess
+            out[p + "model"] = np.array(model)
+            out[p + "nband"] = np.array(nband)
+            out[p + "analytic"] = np.array(int(analytic))
+            out[p + "bounds"] = np.array(
+                [[np.nan if v is None else v for v in bb]
+                 for bb in prior.bounds])
+            out[p + "flags_asrun"] = np.array(r0["flags"])
+            for key in ("flags", "nfev", "ier", "pars", "pars_cov",
+                        "pars_err"):
+                out[p + key] = np.array(r[key])
+            if r["flags"] == 0:
+                for key in ("lnprob", "s2n", "chi2per", "dof", "npix", "T",
+                            "T_err"):
+                    out[p + key] = np.array(r[key])
+                out[p + "flux"] = np.atleast_1d(r["flux"])
+                out[p + "flux_err"] = np.atleast_1d(r["flux_err"])
+            print(icase, model, nband, nep, "analytic", analytic, "flags",
+                  r["flags"], "asrun", r0["flags"], "nfev", r["nfev"], "ier",
+                  r["ier"])
+            icase += 1
+    out["ncases"] = np.array(icase)
+    save("lm_multi_bounds", **out)
+
+
 def gen_psfflux_template():
     """PSFFluxFitter.go with pixel templates (obs.psf.template / obs.template,
     fitting/results.py:834-864) on single observations and ObsLists"""
@@ -1577,6 +1712,7 @@ GENERATORS = {
     "boot": gen_boot,
     "lm_bounds": gen_lm_bounds,
     "lm_multi_fd": gen_lm_multi_fd,
+    "lm_multi_bounds": gen_lm_multi_bounds,
     "psfflux_template": gen_psfflux_template,
 }
 

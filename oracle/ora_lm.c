@@ -759,6 +759,7 @@ typedef struct {
     const int32_t *band;            /* band of each stamp */
     const ora_prior *prior;         /* cen, g, T (F unused) */
     const ora_prior1d *Fp;          /* flux prior of each band */
+    const ora_bounds *bounds;       /* leastsqbound's transforms, or NULL */
 } mfitctx;
 
 /* get_band_pars (results.py:1013-1047): everything up to the fluxes, then
@@ -962,14 +963,33 @@ static int m_calc_jacobian(mfitctx *m, const double *pars, double *jac) {
     return ORA_OK;
 }
 
+/* with bounds MINPACK iterates on internal parameters (leastsqbound.py:
+ * 445-552 wfunc / wDfun), exactly as for one stamp above */
 static int mcb_fdiff(void *ctx, int mm, int n, const double *x, double *fvec) {
-    (void)mm; (void)n;
-    m_calc_fdiff((mfitctx *)ctx, x, fvec);
+    (void)mm;
+    mfitctx *m = (mfitctx *)ctx;
+    if (m->bounds) {
+        double xe[ORA_MAXP] = {0};
+        for (int i = 0; i < n; i++) xe[i] = b_i2e(m->bounds, i, x[i]);
+        m_calc_fdiff(m, xe, fvec);
+        return 0;
+    }
+    m_calc_fdiff(m, x, fvec);
     return 0;
 }
 static int mcb_jac(void *ctx, int mm, int n, const double *x, double *fjac) {
-    (void)mm; (void)n;
-    m_calc_jacobian((mfitctx *)ctx, x, fjac);
+    mfitctx *m = (mfitctx *)ctx;
+    if (m->bounds) {
+        double xe[ORA_MAXP] = {0};
+        for (int i = 0; i < n; i++) xe[i] = b_i2e(m->bounds, i, x[i]);
+        m_calc_jacobian(m, xe, fjac);
+        for (int j = 0; j < n; j++) {
+            double g = b_grad(m->bounds, j, x[j]);
+            for (int i = 0; i < mm; i++) fjac[i + (size_t)j * mm] *= g;
+        }
+        return 0;
+    }
+    m_calc_jacobian(m, x, fjac);
     return 0;
 }
 
@@ -999,7 +1019,26 @@ int ora_lm_fit_multi2(int model, int nstamp, const double *images,
                       int maxfev, double ftol, double xtol,
                       int analytic_jacobian, int ignore_zero_weight,
                       ora_lm_result *res) {
+    return ora_lm_fit_multi_bounded(model, nstamp, images, weights, nrow, ncol,
+                                    jacs, psf_pars, npsf, bands, nband, guess,
+                                    prior, Fp, NULL, maxfev, ftol, xtol,
+                                    analytic_jacobian, ignore_zero_weight,
+                                    res);
+}
+
+/* ... and with prior.bounds (run_leastsq(..., bounds=fit_model.bounds),
+ * fitters.py:99-108): NULL or !present = unbounded */
+int ora_lm_fit_multi_bounded(int model, int nstamp, const double *images,
+                             const double *weights, int nrow, int ncol,
+                             const ora_jac *jacs, const double *psf_pars,
+                             int npsf, const int32_t *bands, int nband,
+                             const double *guess, const ora_prior *prior,
+                             const ora_prior1d *Fp, const ora_bounds *bounds,
+                             int maxfev, double ftol, double xtol,
+                             int analytic_jacobian, int ignore_zero_weight,
+                             ora_lm_result *res) {
     memset(res, 0, sizeof(*res));
+    if (bounds && !bounds->present) bounds = NULL;
     const int simple = model == ORA_GAUSS || model == ORA_EXP
         || model == ORA_DEV;
     if (!(simple || model == ORA_TURB || model == ORA_BDF || model == ORA_BD))
@@ -1039,7 +1078,9 @@ int ora_lm_fit_multi2(int model, int nstamp, const double *images,
     int np = m.npars, mm = m.fdiff_size;
     if (rc == 0) {
         double x[ORA_MAXP];
-        for (int i = 0; i < np; i++) x[i] = guess[i];
+        m.bounds = bounds;
+        for (int i = 0; i < np; i++)
+            x[i] = bounds ? b_e2i(bounds, i, guess[i]) : guess[i];
         double *fvec = (double *)malloc(sizeof(double) * (size_t)mm * (np + 1));
         double *fjac = fvec + mm;
         int ipvt[ORA_MAXP];
@@ -1056,6 +1097,15 @@ int ora_lm_fit_multi2(int model, int nstamp, const double *images,
                             ipvt, qtf);
         int flags = 0;
         res->nfev = nfev; res->njev = njev; res->ier = ier;
+        if (bounds) {
+            /* leastsqbound.py:531-538 with the 1-based ipvt its code assumes */
+            for (int j = 0; j < np; j++) {
+                double g = b_grad(bounds, ipvt[j], x[ipvt[j]]);
+                for (int i = 0; i <= j; i++) fjac[i + (size_t)j * mm] /= g;
+            }
+            for (int i = 0; i < np; i++) x[i] = b_i2e(bounds, i, x[i]);
+            m.bounds = NULL;        /* everything below is at external pars */
+        }
         for (int i = 0; i < np; i++) res->pars[i] = x[i];
         for (int i = 0; i < np * np; i++) res->pars_cov0[i] = NAN;
         int have_cov0 = 0;

@@ -162,6 +162,16 @@ int ora_lm_fit_multi2(int model, int nstamp, const double *images,
                      double ftol, double xtol, int analytic_jacobian, int ignore_zero_weight,
                      ora_lm_result *res);
 
+int ora_lm_fit_multi_bounded(int model, int nstamp, const double *images,
+                             const double *weights, int nrow, int ncol,
+                             const ora_jac *jacs, const double *psf_pars,
+                             int npsf, const int32_t *bands, int nband,
+                             const double *guess, const ora_prior *prior,
+                             const ora_prior1d *Fp, const ora_bounds *bounds,
+                             int maxfev, double ftol, double xtol,
+                             int analytic_jacobian, int ignore_zero_weight,
+                             ora_lm_result *res);
+
 /* residual vector and jacobian of FitModel (results.py:439-570) */
 int ora_lm_calc_fdiff(int model, const ora_pixel *pixels, int npix,
                       const double *psf_pars, int npsf, const ora_prior *prior,

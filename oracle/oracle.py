@@ -503,7 +503,7 @@ def weighted_sums(image, weight, jac, wt_pars, maxrad, nmom=6,
 def lm_fit_multi(model, images, weights, jacs, psf_pars, bands, nband, guess,
                  prior=None, Fpriors=None, maxfev=4000, ftol=1.0e-5,
                  xtol=1.0e-5, ignore_zero_weight=True,
-                 analytic_jacobian=True):
+                 analytic_jacobian=True, bounds=None):
     """Fitter.go on the stamps of ONE object (ObsList / MultiBandObsList):
     images [ns,H,W] ordered band by band, bands [ns] int, guess [5+nband],
     Fpriors a list of nband Prior1D (used with `prior`)"""
@@ -521,10 +521,12 @@ def lm_fit_multi(model, images, weights, jacs, psf_pars, bands, nband, guess,
     for b in range(nband):
         fp[b] = Fpriors[b] if Fpriors is not None else pr.F
     res = np.zeros(1, dtype=LM_RESULT_DTYPE)
-    st = lib().ora_lm_fit_multi2(
+    bnd = make_bounds(bounds)
+    st = lib().ora_lm_fit_multi_bounded(
         C.c_int(MODELS[model]), C.c_int(ns), _p(images), _p(weights),
         C.c_int(H), C.c_int(W), _p(jacs), psf_ptr, C.c_int(npsf), _p(bands),
-        C.c_int(nband), _p(guess), C.byref(pr), fp, C.c_int(maxfev),
+        C.c_int(nband), _p(guess), C.byref(pr), fp, C.byref(bnd),
+        C.c_int(maxfev),
         C.c_double(ftol), C.c_double(xtol), C.c_int(int(analytic_jacobian)),
         C.c_int(int(ignore_zero_weight)), _p(res))
     assert st == 0, st

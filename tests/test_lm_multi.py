@@ -91,6 +91,43 @@ def test_oracle_multi_fd_matches_reference(ora):
         _check(r, c, NSHARED[c["model"]] + c["nband"])
 
 
+def _bcase(g, k):
+    p = "c%d_" % k
+    d = {key[len(p):]: g[key] for key in g.files if key.startswith(p)}
+    d["model"] = str(d["model"])
+    d["nband"] = int(d["nband"])
+    d["analytic"] = bool(int(d["analytic"]))
+    d["rep"] = k % 2
+    d["bounds_list"] = [tuple(None if np.isnan(v) else float(v) for v in bb)
+                        for bb in d["bounds"]]
+    return d
+
+
+def test_oracle_multi_bounded_matches_reference(ora):
+    """prior.bounds on ObsList / MultiBandObsList fits (leastsqbound's
+    transforms around the multi-stamp residuals): exp through lmder and
+    lmdif, bdf through lmdif; golden from the reference with the 1-based
+    ipvt its covariance code assumes (gen_golden.gen_lm_multi_bounds)"""
+    g = _golden("lm_multi_bounds")
+    for k in range(int(g["ncases"])):
+        c = _bcase(g, k)
+        pr = ora.make_prior("flat")
+        if c["model"] == "exp":
+            pr.T = ora.Prior1D(3, 0, [0.4, 0.5][c["rep"]], 1.0, 0, 0)
+            fps = [ora.Prior1D(3, 0, 100.0, 100.0, 0, 0)
+                   for _ in range(c["nband"])]
+        else:
+            pr.fracdev = ora.Prior1D(3, 0, 0.5, 0.3, 0, 0)
+            fps = [ora.Prior1D(1, 0, -100.0, 1.0e9, 0, 0)
+                   for _ in range(c["nband"])]
+        r = ora.lm_fit_multi(c["model"], c["images"], c["weights"], c["jac"],
+                             c["psf"], c["bands"], c["nband"], c["guess"],
+                             prior=pr, Fpriors=fps,
+                             analytic_jacobian=c["analytic"],
+                             bounds=c["bounds_list"])
+        _check(r, c, NSHARED[c["model"]] + c["nband"])
+
+
 # ------------------------------------------------------------------ GPU
 @pytest.fixture(scope="module")
 def ngx():
@@ -286,6 +323,57 @@ def test_gpu_multi_fd_matches_reference(ngx):
         assert np.abs(cov - c["pars_cov"]).max() <= 2e-3 * sc.max()
     # evaluation counts follow the reference up to forward-difference noise
     assert nsame >= ncases - 2
+
+
+@pytest.mark.gpu
+def test_gpu_multi_bounded_matches_reference(ngx):
+    """bounded fits of objects with several stamps (prior.bounds through
+    fit_batch_multi): analytic cases follow the reference in flags, nfev, ier
+    and parameters; forward-difference cases up to the fd noise floor"""
+    import ngmix_b200 as ngmix
+    pr = ngmix.priors
+    g = _golden("lm_multi_bounds")
+    nsame = nfd = 0
+    for k in range(int(g["ncases"])):
+        c = _bcase(g, k)
+        ns = c["images"].shape[0]
+        np_ = NSHARED[c["model"]] + c["nband"]
+        cen, gp = pr.CenPrior(0.0, 0.0, 0.263, 0.263), pr.GPriorBA(0.3)
+        if c["model"] == "exp" and c["rep"] == 0:
+            prior = ngmix.joint_prior.PriorSimpleSep(
+                cen, gp, pr.Normal(0.4, 1.0, bounds=[0.01, 100.0]),
+                [pr.Normal(100.0, 100.0, bounds=[1.0, 1.0e9])
+                 for _ in range(c["nband"])])
+        elif c["model"] == "exp":
+            prior = ngmix.joint_prior.PriorSimpleSep(
+                cen, gp, pr.Normal(0.5, 1.0, bounds=[0.05, 5.0]),
+                [pr.Normal(100.0, 100.0, bounds=[1.0, None])
+                 for _ in range(c["nband"])])
+        else:
+            prior = ngmix.joint_prior.PriorBDFSep(
+                cen, gp, pr.FlatPrior(-1.0, 1.0e3),
+                pr.Normal(0.5, 0.3, bounds=[0.0, 1.0]),
+                [pr.FlatPrior(-100.0, 1.0e9) for _ in range(c["nband"])])
+        assert [tuple(b) for b in prior.bounds] == c["bounds_list"]
+        rec = ngmix.fit_batch_multi(
+            c["model"], [0, ns], c["bands"], c["nband"], c["images"],
+            c["weights"], c["jac"], c["psf"], c["guess"][None], prior=prior,
+            analytic_jacobian=c["analytic"])[0]
+        if c["analytic"]:
+            _check(rec, c, np_)
+            continue
+        nfd += 1
+        assert int(rec["flags"]) == int(c["flags"])
+        nsame += int(int(rec["nfev"]) == int(c["nfev"])
+                     and int(rec["ier"]) == int(c["ier"]))
+        tol = np.maximum(PAR_TOL * np.abs(c["pars"]), 2e-2 * c["pars_err"])
+        assert np.all(np.abs(rec["pars"][:np_] - c["pars"]) <= tol)
+        assert abs(float(rec["lnprob"]) - float(c["lnprob"])) \
+            <= 1e-5 * abs(float(c["lnprob"]))
+        cov = np.asarray(rec["pars_cov"][:np_ * np_]).reshape(np_, np_)
+        sc = np.sqrt(np.outer(np.diag(c["pars_cov"]), np.diag(c["pars_cov"])))
+        assert np.abs(cov - c["pars_cov"]).max() <= 2e-3 * sc.max()
+    assert nsame >= nfd - 1
 
 
 @pytest.mark.gpu
