@@ -215,10 +215,13 @@ typedef struct {
     ngx_prior1d F_more[2];    /* flux priors of bands 1 and 2 */
     ngx_prior1d logTratio;    /* bd only: PriorBDSep, joint_prior.py:267-399 */
     ngx_prior1d F_extra[4];   /* flux priors of bands 3..6 (nband up to 7) */
+    ngx_prior1d F_xwide[5];   /* flux priors of bands 7..11
+                               * (ngx_lm_fit_multi_xwide, nband up to 12) */
 } ngx_prior;
 
 /* DEFAULT_LM_PARS, ngmix/defaults.py:17 */
-#define NGX_MAX_PARS 14
+#define NGX_MAX_PARS 20
+#define NGX_MAX_BANDS 12
 /* bounds kinds of one parameter (prior.bounds of the reference,
  * joint_prior.py:37-61; transforms of leastsqbound.py:183-263) */
 #define NGX_B_NONE 0
@@ -256,6 +259,15 @@ typedef struct {
         flux_err;
     double pars[14], pars_err[14], pars_cov0[196], pars_cov[196];
 } ngx_lm_result_wide;
+
+/* ... and for 20: multi-band fits with 8 to 12 bands
+ * (ngx_lm_fit_multi_xwide) */
+typedef struct {
+    int32_t flags, nfev, ier, npix, dof, njev;
+    double lnprob, s2n_numer, s2n_denom, chi2per, s2n, T, T_err, flux,
+        flux_err;
+    double pars[20], pars_err[20], pars_cov0[400], pars_cov[400];
+} ngx_lm_result_xwide;
 
 /* Fitter(model, prior, fit_pars).go(obs, guess) for n stamps
  * (fitting/fitters.py:64-112): FitModel.calc_fdiff/calc_jacobian
@@ -316,6 +328,17 @@ int ngx_lm_fit_multi_wide(int nobj, int model, const int32_t *stamp_start,
                      const double *psf_pars, int npsf, const double *guess,
                      const ngx_prior *prior, const ngx_lm_pars *lm_pars,
                      int ignore_zero_weight, ngx_lm_result_wide *res, void *stream);
+
+/* ... and for 8 to 12 bands (the reference has no limit on the number of
+ * bands, results.py:212-260; up to 19 parameters, 20-slot records); fewer
+ * bands are accepted too */
+int ngx_lm_fit_multi_xwide(int nobj, int model, const int32_t *stamp_start,
+                     const int32_t *stamp_band, int nband,
+                     const double *images, const double *weights,
+                     const ngx_jacobian *jac, int nrow, int ncol,
+                     const double *psf_pars, int npsf, const double *guess,
+                     const ngx_prior *prior, const ngx_lm_pars *lm_pars,
+                     int ignore_zero_weight, ngx_lm_result_xwide *res, void *stream);
 
 /* EM: EMFitter*.go (em/em.py:228-317) = prep_image (:95-120) + em_run /
  * em_run_fixcen / em_run_fixcov / em_run_fluxonly (em/em_nb.py:15-1257) */
@@ -583,6 +606,15 @@ int ngx_lm_fit_multi_wide_host(int nobj, int model, const int32_t *stamp_start,
                           const double *guess, const ngx_prior *prior,
                           const ngx_lm_pars *lm_pars, int ignore_zero_weight,
                           ngx_lm_result_wide *res);
+
+int ngx_lm_fit_multi_xwide_host(int nobj, int model, const int32_t *stamp_start,
+                          const int32_t *stamp_band, int nband,
+                          const double *images, const double *weights,
+                          const ngx_jacobian *jac, int nrow, int ncol,
+                          const double *psf_pars, int npsf,
+                          const double *guess, const ngx_prior *prior,
+                          const ngx_lm_pars *lm_pars, int ignore_zero_weight,
+                          ngx_lm_result_xwide *res);
 
 /* FP64 pipe micro-benchmark used for the roofline denominator: runs a
  * register-resident chain of `iters` x 8 independent DFMAs per thread on a

@@ -45,6 +45,11 @@ LM_RESULT_WIDE_DTYPE = np.dtype(
     [(n, LM_RESULT_DTYPE.fields[n][0]) for n in LM_RESULT_DTYPE.names[:15]]
     + [("pars", "f8", 14), ("pars_err", "f8", 14), ("pars_cov0", "f8", 196),
        ("pars_cov", "f8", 196)])
+# ngx_lm_result_xwide: 20 parameter slots (8-12 bands)
+LM_RESULT_XWIDE_DTYPE = np.dtype(
+    [(n, LM_RESULT_DTYPE.fields[n][0]) for n in LM_RESULT_DTYPE.names[:15]]
+    + [("pars", "f8", 20), ("pars_err", "f8", 20), ("pars_cov0", "f8", 400),
+       ("pars_cov", "f8", 400)])
 EM_RESULT_DTYPE = np.dtype([("flags", "i4"), ("numiter", "i4"),
                             ("fdiff", "f8"), ("sky", "f8")])
 ADMOM_RESULT_DTYPE = np.dtype([
@@ -77,15 +82,15 @@ class Prior(C.Structure):
                 ("fracdev", Prior1D), ("F", Prior1D),
                 ("nband", C.c_int32), ("ncoellip", C.c_int32),
                 ("F_more", Prior1D * 2), ("logTratio", Prior1D),
-                ("F_extra", Prior1D * 4)]
+                ("F_extra", Prior1D * 4), ("F_xwide", Prior1D * 5)]
 
 
 class LMPars(C.Structure):
     _fields_ = [("maxfev", C.c_int32), ("analytic_jacobian", C.c_int32),
                 ("ftol", C.c_double), ("xtol", C.c_double),
-                ("nbounds", C.c_int32), ("btype", C.c_int32 * 14),
+                ("nbounds", C.c_int32), ("btype", C.c_int32 * 20),
                 ("pad_", C.c_int32),
-                ("blo", C.c_double * 14), ("bhi", C.c_double * 14)]
+                ("blo", C.c_double * 20), ("bhi", C.c_double * 20)]
 
     def set_bounds(self, bounds):
         """bounds: None or [(min | None, max | None)] per parameter, the
@@ -93,8 +98,8 @@ class LMPars(C.Structure):
         self.nbounds = 0
         if bounds is None:
             return self
-        if len(bounds) > 14:
-            raise ValueError("at most 14 parameters")
+        if len(bounds) > 20:
+            raise ValueError("at most 20 parameters")
         self.nbounds = len(bounds)
         for i, (lo, hi) in enumerate(bounds):
             self.btype[i] = (1 if lo is not None else 0) \
@@ -139,6 +144,7 @@ SYMBOLS = [
     "ngx_template_flux_images", "ngx_template_flux_images_host",
     "ngx_expand_compact",
     "ngx_lm_fit_multi_wide", "ngx_lm_fit_multi_wide_host",
+    "ngx_lm_fit_multi_xwide", "ngx_lm_fit_multi_xwide_host",
     "ngx_lm_fit_coellip", "ngx_lm_fit_coellip_host",
 ]
 
@@ -566,7 +572,8 @@ def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
     [nobj, nshared + nband] with 5 (gauss, exp, dev, turb), 6 (bdf) or 7 (bd)
     shared parameters.  bdf, bd, turb and analytic_jacobian=False run
     MINPACK's forward differences.  Returns LM_RESULT_DTYPE [nobj] for up to
-    8 parameters, LM_RESULT_WIDE_DTYPE (14 parameter slots) beyond.
+    8 parameters, LM_RESULT_WIDE_DTYPE (14 parameter slots) up to 7 bands and
+    14 parameters, LM_RESULT_XWIDE_DTYPE (20 slots) up to 12 bands.
     """
     init()
     images = _f8(images)
@@ -579,8 +586,8 @@ def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
     assert stamp_start[0] == 0 and stamp_start[-1] == ns
     assert stamp_band.size == ns
     npars = MODEL_NPARS[model] - 1 + nband
-    if npars > 14 or nband > 7:
-        raise ValueError("at most 7 bands and 14 parameters")
+    if npars > 20 or nband > 12:
+        raise ValueError("at most 12 bands and 20 parameters")
     guess = _f8(guess).reshape(nobj, npars)
     if psf_pars is None:
         npsf = 0
@@ -590,11 +597,13 @@ def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
     pr = prior if prior is not None else Prior()
     lmp = LMPars(maxfev, int(analytic_jacobian), ftol, xtol)
     lmp.set_bounds(bounds)
-    wide = npars > 8
-    res = np.zeros(nobj, dtype=LM_RESULT_WIDE_DTYPE if wide
-                   else LM_RESULT_DTYPE)
-    entry = lib().ngx_lm_fit_multi_wide_host if wide \
-        else lib().ngx_lm_fit_multi_host
+    if npars > 14 or nband > 7:
+        dtype, entry = LM_RESULT_XWIDE_DTYPE, lib().ngx_lm_fit_multi_xwide_host
+    elif npars > 8:
+        dtype, entry = LM_RESULT_WIDE_DTYPE, lib().ngx_lm_fit_multi_wide_host
+    else:
+        dtype, entry = LM_RESULT_DTYPE, lib().ngx_lm_fit_multi_host
+    res = np.zeros(nobj, dtype=dtype)
     check(entry(
         C.c_int(nobj), C.c_int(MODELS[model]), _p(stamp_start),
         _p(stamp_band), C.c_int(nband), _p(images), _p(weights), _p(jac),

@@ -1700,7 +1700,8 @@ k_lm_fit_multi(LMArgs a) {
             const bool fused = MODE == 0 && want_f && spec && nonzero
                 && !(sh.st.prered <= sh.st.ftol);
             const bool do_deriv = fused || action == LM_ACT_EVAL_J;
-            if (threadIdx.x < MACC_X + 4) mu.macc[threadIdx.x] = 0.0;
+            for (int i = threadIdx.x; i < MACC_X + 4; i += blockDim.x)
+                mu.macc[i] = 0.0;
             if (threadIdx.x == 0) {
                 mu.mstatus = 0;
                 if (MODE == 1 && do_deriv) {
@@ -2300,7 +2301,8 @@ static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
                 || model == NGX_BD);
     // shared parameters: 5 (simple), 6 (bdf), 7 (bd), then a flux per band
     const int nsh = model_npars(model) - 1;
-    NGX_REQUIRE(nband >= 1 && nband <= 7 && nsh + nband <= LM_MAXP);
+    NGX_REQUIRE(nband >= 1 && nband <= (LM_MAXP >= 20 ? NGX_MAX_BANDS : 7)
+                && nsh + nband <= LM_MAXP);
     // forward differences (Fitter.go, fitters.py:93-98): always for the
     // models without analytic derivatives
     const bool analytic = simple && lm_pars->analytic_jacobian;
@@ -2353,7 +2355,7 @@ static int lm_fit_multi_impl(int nobj, int model, const int32_t *stamp_start,
 #endif
 }
 
-#ifdef NGX_LM_WIDE_TU
+#if defined(NGX_LM_WIDE_TU) && !defined(NGX_LM_XWIDE_TU)
 // CoellipFitter.go (fitting/fitters.py:120-141 -> CoellipFitModel,
 // results.py:628-674): n coelliptical gaussians, parameters (cen1, cen2, g1,
 // g2, T_1..T_n, F_1..F_n), forward-difference Jacobian (MINPACK lmdif),
@@ -2447,7 +2449,7 @@ int ngx_lm_fit_coellip(int n, int ngauss, const double *images,
 }
 #endif
 
-#ifdef NGX_LM_WIDE_TU
+#if defined(NGX_LM_WIDE_TU) && !defined(NGX_LM_XWIDE_TU)
 int ngx_lm_fit_coellip_host(int n, int ngauss, const double *images,
                             const double *weights, const ngx_jacobian *jac,
                             int nrow, int ncol, const double *psf_pars,
@@ -2527,7 +2529,7 @@ static int lm_fit_multi_host_impl(int nobj, int model,
                                   int ignore_zero_weight, RES *res,
                                   int wide) {
     NGX_REQUIRE(nobj >= 0 && stamp_start && stamp_band && images && weights);
-    NGX_REQUIRE(jac && guess && res && nband >= 1 && nband <= 7);
+    NGX_REQUIRE(jac && guess && res && nband >= 1 && nband <= NGX_MAX_BANDS);
     if (nobj == 0) return NGX_OK;
     const int ns = stamp_start[nobj];
     NGX_REQUIRE(ns >= 0 && stamp_start[0] == 0);

@@ -103,7 +103,8 @@ __host__ __device__ inline int prior_nband(const ngx_prior &pr) {
 // flux prior of a band
 __device__ inline const ngx_prior1d &prior_F(const ngx_prior &pr, int band) {
     return band == 0 ? pr.F
-        : band <= 2 ? pr.F_more[band - 1] : pr.F_extra[band - 3];
+        : band <= 2 ? pr.F_more[band - 1]
+        : band <= 6 ? pr.F_extra[band - 3] : pr.F_xwide[band - 7];
 }
 // number of residual slots reserved for the prior (results.py:1050-1076)
 __host__ __device__ inline int prior_nslots(int model, const ngx_prior &pr) {

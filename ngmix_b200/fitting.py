@@ -131,8 +131,9 @@ def fit_batch_multi(model, stamp_start, stamp_band, nband, images, weights,
     [nobj, nshared + nband] = (cen1, cen2, g1, g2, T, [fracdev | logTratio,
     fracdev,] F_0 .. F_{nband-1}).  gauss / exp / dev use the analytic
     Jacobian unless analytic_jacobian=False; bdf, bd and turb always run
-    MINPACK's forward differences, as Fitter.go does.  nband <= 7 and at most
-    14 parameters (records with 14 parameter slots beyond 8 parameters).
+    MINPACK's forward differences, as Fitter.go does.  nband <= 12 and at most
+    20 parameters (records with 14 parameter slots beyond 8 parameters, 20
+    beyond 14 parameters or 7 bands).
     """
     model = get_model_name(get_model_num(model))
     if model not in _LM_MODELS:
@@ -599,8 +600,8 @@ class Fitter(object):
         guess = np.array(guess, dtype="f8")
         assert guess.size == npars, \
             "guess has npars=%d, expected %d" % (guess.size, npars)
-        if nband > 7 or npars > 14:
-            raise NotImplementedError("at most 7 bands and 14 parameters")
+        if nband > 12 or npars > 20:
+            raise NotImplementedError("at most 12 bands and 20 parameters")
         stamps = [(b, o) for b, ol in enumerate(mb) for o in ol]
         shape = stamps[0][1].image.shape
         has_psf = stamps[0][1].has_psf_gmix()

@@ -417,8 +417,8 @@ class PriorSimpleSep(object):
         return n
 
     def to_ngx(self):
-        if self.nband > 7:
-            raise NotImplementedError("at most 7 bands (12 parameters)")
+        if self.nband > 12:
+            raise NotImplementedError("at most 12 bands")
         if not isinstance(self.g_prior, GPriorBA):
             raise NotImplementedError("g prior must be GPriorBA")
         pr = _lib.Prior()
@@ -434,8 +434,10 @@ class PriorSimpleSep(object):
         for b in range(1, self.nband):
             if b <= 2:
                 pr.F_more[b - 1] = self.F_priors[b]._ngx()
-            else:
+            elif b <= 6:
                 pr.F_extra[b - 3] = self.F_priors[b]._ngx()
+            else:
+                pr.F_xwide[b - 7] = self.F_priors[b]._ngx()
         return pr
 
 

@@ -1046,6 +1046,16 @@ def gen_lm_multi_wide():
     _gen_multi(configs, 27182, "lm_multi_wide")
 
 
+def gen_lm_multi_xwide():
+    """the same with 8 to 12 bands (13 to 17 parameters): the reference has
+    no limit on the number of bands (results.py:212-260)"""
+    configs = [
+        (8, [1] * 8, "exp", True), (9, [1, 2, 1, 1, 1, 1, 1, 1, 1], "gauss", False),
+        (10, [1] * 10, "exp", True), (12, [1] * 12, "dev", True),
+    ]
+    _gen_multi(configs, 16180, "lm_multi_xwide")
+
+
 def _gen_multi(configs, seed, name):
     from ngmix.fitting import Fitter
     from ngmix import priors, joint_prior
@@ -1401,6 +1411,8 @@ def gen_lm_multi_fd():
         (5, [1, 1, 1, 1, 1], "bdf", True),
         (2, [1, 1], "bd", True), (1, [3], "bd", True),
         (2, [1, 2], "exp", True), (3, [1, 1, 1], "exp", False),
+        # 8 and 9 bands: 14 and 16 parameters (ngx_lm_fit_multi_xwide)
+        (8, [1] * 8, "bdf", True), (9, [1] * 9, "bd", True),
     ]
     out = {}
     icase = 0
@@ -1711,6 +1723,7 @@ GENERATORS = {
     "psfflux": gen_psfflux,
     "boot": gen_boot,
     "lm_bounds": gen_lm_bounds,
+    "lm_multi_xwide": gen_lm_multi_xwide,
     "lm_multi_fd": gen_lm_multi_fd,
     "lm_multi_bounds": gen_lm_multi_bounds,
     "psfflux_template": gen_psfflux_template,

@@ -114,7 +114,8 @@ typedef struct {
 } ora_prior;
 
 /* ---- LM fit = Fitter.go (fitting/fitters.py:64-112) ---- */
-#define ORA_MAXP 14     /* 4 + 2 * 5 (coellip); matrices are packed npars x npars */
+#define ORA_MAXP 20     /* 7 shared + 12 band fluxes (multi-band bd); coellip needs 14;
+                         * matrices are packed npars x npars */
 typedef struct {
     int32_t flags, nfev, ier, npix, dof, njev;
     double lnprob, s2n_numer, s2n_denom, chi2per, s2n, T, T_err, flux,

@@ -54,18 +54,18 @@ class LMResult(C.Structure):
                 ("s2n_denom", C.c_double), ("chi2per", C.c_double),
                 ("s2n", C.c_double), ("T", C.c_double), ("T_err", C.c_double),
                 ("flux", C.c_double), ("flux_err", C.c_double),
-                ("pars", C.c_double * 14), ("pars_err", C.c_double * 14),
-                ("pars_cov0", C.c_double * 196),
-                ("pars_cov", C.c_double * 196)]
+                ("pars", C.c_double * 20), ("pars_err", C.c_double * 20),
+                ("pars_cov0", C.c_double * 400),
+                ("pars_cov", C.c_double * 400)]
 
 
 LM_RESULT_DTYPE = np.dtype([
     ("flags", "i4"), ("nfev", "i4"), ("ier", "i4"), ("npix", "i4"),
     ("dof", "i4"), ("njev", "i4"), ("lnprob", "f8"), ("s2n_numer", "f8"),
     ("s2n_denom", "f8"), ("chi2per", "f8"), ("s2n", "f8"), ("T", "f8"),
-    ("T_err", "f8"), ("flux", "f8"), ("flux_err", "f8"), ("pars", "f8", 14),
-    ("pars_err", "f8", 14), ("pars_cov0", "f8", 196),
-    ("pars_cov", "f8", 196)])
+    ("T_err", "f8"), ("flux", "f8"), ("flux_err", "f8"), ("pars", "f8", 20),
+    ("pars_err", "f8", 20), ("pars_cov0", "f8", 400),
+    ("pars_cov", "f8", 400)])
 
 EM_RESULT_DTYPE = np.dtype([("flags", "i4"), ("numiter", "i4"),
                             ("fdiff", "f8"), ("sky", "f8")])
@@ -297,9 +297,9 @@ def make_prior(kind, model="exp"):
 # ------------------------------------------------------------------ LM
 class Bounds(C.Structure):
     """prior.bounds of the reference (joint_prior.py:37-61)"""
-    _fields_ = [("present", C.c_int32), ("type", C.c_int32 * 14),
+    _fields_ = [("present", C.c_int32), ("type", C.c_int32 * 20),
                 ("pad", C.c_int32),
-                ("lo", C.c_double * 14), ("hi", C.c_double * 14)]
+                ("lo", C.c_double * 20), ("hi", C.c_double * 20)]
 
 
 def make_bounds(bounds):

@@ -52,7 +52,8 @@ def _check(r, c, np_, exact_counts=True):
                 <= 1e-5 * max(abs(float(c[key])), 1.0), key
 
 
-@pytest.mark.parametrize("name", ["lm_multi", "lm_multi_wide"])
+@pytest.mark.parametrize("name", ["lm_multi", "lm_multi_wide",
+                                  "lm_multi_xwide"])
 def test_oracle_multi_matches_reference(ora, name):
     g = _golden(name)
     for k in range(int(g["ncases"])):
@@ -149,7 +150,8 @@ def _ngx_prior(c):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["lm_multi", "lm_multi_wide"])
+@pytest.mark.parametrize("name", ["lm_multi", "lm_multi_wide",
+                                  "lm_multi_xwide"])
 def test_gpu_multi_matches_reference(ngx, name):
     """1-3 bands (8-parameter records) and 4-7 bands (12-parameter records)"""
     import ngmix_b200 as ngmix
