@@ -19,8 +19,20 @@ python profiles/ncu_lines.py gpurun_out/prof_lm_$TAG.ncu-rep > gpurun_out/ncu_lm
 timeout 900 ncu --set full --clock-control none --profile-from-start off -f -o gpurun_out/prof_kernels_$TAG python profiles/capture_kernels.py > gpurun_out/capture_$TAG.log 2>&1
 python profiles/ncu_multi.py gpurun_out/prof_kernels_$TAG.ncu-rep > gpurun_out/ncu_kernels_$TAG.txt 2>&1
 rm -f gpurun_out/prof_kernels_$TAG.ncu-rep
+timeout 400 ncu --set full --clock-control none -k regex:k_admom -s 1 -c 1 -f -o gpurun_out/prof_admom_$TAG python profiles/capture_admom.py > /dev/null 2>&1
+python profiles/ncu_multi.py gpurun_out/prof_admom_$TAG.ncu-rep > gpurun_out/ncu_admom_$TAG.txt 2>&1
 timeout 900 python bench_extra.py > gpurun_out/bench_extra_$TAG.json 2> gpurun_out/bench_extra_$TAG.err; tail -c 300 gpurun_out/bench_extra_$TAG.err
-timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_chain.py tests/test_lm_bounds.py tests/test_lm_multi.py -m gpu -x -q > gpurun_out/sanitizer_memcheck_$TAG.log 2>&1; tail -3 gpurun_out/sanitizer_memcheck_$TAG.log
+# the host-buffer pipelines: streamed vs chunked, pageable arrays, several batches / two host threads
+timeout 600 python profiles/stream_vs_chunked.py > gpurun_out/stream_vs_chunked_$TAG.txt 2>&1; tail -3 gpurun_out/stream_vs_chunked_$TAG.txt
+timeout 300 python profiles/pageable_sweep.py > gpurun_out/pageable_$TAG.txt 2>&1
+for t in 2 4 8 12; do NGX_STAGE_THREADS=$t timeout 300 python profiles/pageable_sweep.py >> gpurun_out/pageable_$TAG.txt 2>&1; done
+timeout 600 python profiles/stress_stream.py > gpurun_out/stress_stream_$TAG.txt 2>&1; tail -2 gpurun_out/stress_stream_$TAG.txt
+timeout 300 python profiles/multi_host_timing.py > gpurun_out/multi_host_$TAG.txt 2>&1
+# parity at scale of the kernels changed in this tag
+timeout 600 python profiles/admom_sweep.py > gpurun_out/admom_sweep_$TAG.json 2> gpurun_out/admom_sweep_$TAG.err
+timeout 600 python profiles/coellip_parity.py 2>/dev/null | tail -1 > gpurun_out/coellip_parity_$TAG.json
+timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_chain.py tests/test_lm_bounds.py tests/test_lm_multi.py "tests/test_gpu_batch.py::test_streamed_pipeline_failure_releases_the_device" "tests/test_gpu_batch.py::test_em_admom_host_calls_pipelined" -m gpu -x -q > gpurun_out/sanitizer_memcheck_$TAG.log 2>&1; tail -3 gpurun_out/sanitizer_memcheck_$TAG.log
 timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_chain.py tests/test_lm_bounds.py "tests/test_lm_multi.py::test_gpu_multi_fd_matches_reference" -m gpu -x -q > gpurun_out/sanitizer_racecheck_$TAG.log 2>&1; tail -3 gpurun_out/sanitizer_racecheck_$TAG.log
+for tool in memcheck racecheck; do timeout 600 compute-sanitizer --tool $tool python profiles/sanitize_stream.py > gpurun_out/sanitizer_stream_${tool}_$TAG.log 2>&1; tail -2 gpurun_out/sanitizer_stream_${tool}_$TAG.log; done
 timeout 300 compute-sanitizer --tool racecheck python __graft_entry__.py smoke > gpurun_out/sanitizer_racecheck_smoke_$TAG.log 2>&1; tail -2 gpurun_out/sanitizer_racecheck_smoke_$TAG.log
 ls -la gpurun_out; du -sh gpurun_out
