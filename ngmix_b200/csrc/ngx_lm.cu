@@ -91,6 +91,10 @@ struct LMArgs {
     const double *wscalar;
     const unsigned char *maskbits;
     int *done_count, *host_done, *err;
+    // the error flag the waiters poll: in device memory (polling the mapped
+    // host flag from every waiting thread floods PCIe and starves the very
+    // copies being waited for); `err` above is written once, on a timeout
+    int *err_dev;
 };
 
 __device__ __forceinline__ int ld_acquire_sys(const int *p) {
@@ -127,8 +131,9 @@ static __device__ __noinline__ void wait_ready(const LMArgs &a, int stamp) {
         if (ld_acquire_sys(f)) return;
         // a failed call (the host raises err when it cannot queue the rest
         // of the feed) releases every waiter at once
-        if (*(volatile int *)a.err) return;
+        if (*(volatile int *)a.err_dev) return;
         if (global_ns() - t0 > 4000000000ull) {
+            *(volatile int *)a.err_dev = 1;
             *(volatile int *)a.err = 1;
             return;
         }
@@ -2136,7 +2141,7 @@ struct LMFeed {
     const float *im32, *wt32;
     const double *wscalar;
     const unsigned char *maskbits;
-    int *done_count, *host_done, *err;
+    int *done_count, *host_done, *err, *err_dev;
 };
 static thread_local const LMFeed *g_lm_feed = nullptr;
 
@@ -2186,6 +2191,7 @@ int ngx_lm_fit(int n, int model, const double *images, const double *weights,
         a.im32 = feed->im32; a.wt32 = feed->wt32; a.wscalar = feed->wscalar;
         a.maskbits = feed->maskbits; a.done_count = feed->done_count;
         a.host_done = feed->host_done; a.err = feed->err;
+        a.err_dev = feed->err_dev;
     }
     NGX_REQUIRE(a.ngauss <= NGX_MAX_GAUSS);
     if (a.prior.present) {
@@ -2917,14 +2923,15 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
                              (size_t)cn * 6 * npsf * sizeof(double))))
             return r;
         if ((r = grow_dev((void **)&B.flags, &B.cap_flags,
-                          (size_t)(max_rc + max_dc) * sizeof(int))))
+                          (size_t)(max_rc + max_dc + 1) * sizeof(int))))
             return r;
         int *d_ready = B.flags, *d_done = B.flags + max_rc;
         next_c[k & 1] = 0;
         // the buffers are free once the records of batch k-2 are on the host
         NGX_CUDA(cudaStreamWaitEvent(cs, B.drained, 0));
         NGX_CUDA(cudaMemsetAsync(B.flags, 0,
-                                 (size_t)(max_rc + max_dc) * sizeof(int), cs));
+                                 (size_t)(max_rc + max_dc + 1) * sizeof(int),
+                                 cs));
         for (int i = 0; i <= max_dc; i++) hf[i] = 0;
         NGX_CUDA(cudaEventRecord(B.small_up, cs));
         NGX_CUDA(cudaStreamWaitEvent(ks[k & 1], B.small_up, 0));
@@ -2939,6 +2946,7 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
         feed.done_count = d_done;
         NGX_CUDA(cudaHostGetDevicePointer((void **)&feed.host_done, hf, 0));
         feed.err = feed.host_done + max_dc;
+        feed.err_dev = B.flags + max_rc + max_dc;
         g_lm_feed = &feed;
         r = ngx_lm_fit(cn, model, (const double *)B.in_a,
                        (const double *)(compact ? B.in_a : B.in_b), B.jac,
@@ -3076,9 +3084,14 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
                 now_us() - t_begin);
     if (!rc) rc = flush_owed();
     if (rc) {
-        // release kernels that still wait for stamps that will not come
+        // release kernels that still wait for stamps that will not come: the
+        // device-side flag the waiters poll, raised by a copy on the record
+        // stream (the copy stream may be the one that failed)
         for (int b = 0; b < 2; b++)
-            ((volatile int *)h_flags)[(size_t)b * (max_dc + 1) + max_dc] = 1;
+            if (sb[b].flags && sb[b].cap_flags
+                    >= (size_t)(max_rc + max_dc + 1) * sizeof(int))
+                cudaMemcpyAsync(sb[b].flags + max_rc + max_dc, h_one,
+                                sizeof(int), cudaMemcpyHostToDevice, ds);
     }
     cudaStreamSynchronize(cs);
     cudaStreamSynchronize(ks[0]);
