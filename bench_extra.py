@@ -301,7 +301,35 @@ def bench_coellip(args, _lib, b):
                                     b["jac"][:n], None, guess)
             dts.append(time.perf_counter() - t0)
         dt = float(np.median(dts))
+        # the kernel alone, stamps resident (CUDA events)
+        import torch
+        dev = torch.device("cuda", 0)
+        tt = {k: torch.from_numpy(np.ascontiguousarray(b[k][:n])).to(dev)
+              for k in ("images", "weights", "jac")}
+        d_g = torch.from_numpy(guess).to(dev)
+        d_res = torch.zeros(n * _lib.LM_RESULT_WIDE_DTYPE.itemsize,
+                            dtype=torch.uint8, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def fn():
+            _lib.lm_fit_coellip_device(
+                ngauss, n, tt["images"].data_ptr(), tt["weights"].data_ptr(),
+                tt["jac"].data_ptr(), 25, 25, 0, 0, d_g.data_ptr(),
+                d_res.data_ptr(), stream=st)
+
+        fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        kms = e0.elapsed_time(e1) / 3
+        del tt, d_g, d_res
         out["ngauss%d" % ngauss] = {
+            "fits_per_s": n / (kms * 1e-3), "ms_per_step": kms,
             "fits_per_s_host_call": n / dt, "n": n,
             "calls_s": [float(x) for x in dts],
             "median_nfev": float(np.median(r["nfev"])),

@@ -612,6 +612,24 @@ def lm_fit_multi(model, stamp_start, stamp_band, nband, images, weights, jac,
     return res
 
 
+def lm_fit_coellip_device(ngauss, n, d_images, d_weights, d_jac, nrow, ncol,
+                          d_psf, npsf, d_guess, d_res, prior=None,
+                          maxfev=4000, ftol=1.0e-5, xtol=1.0e-5,
+                          ignore_zero_weight=True, stream=0):
+    """device-pointer coelliptical fit (asynchronous); d_res holds
+    LM_RESULT_WIDE_DTYPE records"""
+    pr = prior if prior is not None else Prior()
+    pr.ncoellip = ngauss
+    lmp = LMPars(maxfev, 0, ftol, xtol)
+    check(lib().ngx_lm_fit_coellip(
+        C.c_int(n), C.c_int(ngauss), C.c_void_p(d_images),
+        C.c_void_p(d_weights), C.c_void_p(d_jac), C.c_int(nrow), C.c_int(ncol),
+        C.c_void_p(d_psf) if npsf else None, C.c_int(npsf),
+        C.c_void_p(d_guess), C.byref(pr), C.byref(lmp),
+        C.c_int(int(ignore_zero_weight)), C.c_void_p(d_res),
+        C.c_void_p(stream)))
+
+
 def lm_fit_multi_device(model, nobj, d_stamp_start, d_stamp_band, nband,
                         d_images, d_weights, d_jac, nrow, ncol, d_psf, npsf,
                         d_guess, d_res, prior=None, maxfev=4000, ftol=1.0e-5,
