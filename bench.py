@@ -60,8 +60,8 @@ INSTR_VALUE, INSTR_DERIV = 16.0, 30.0      # fused fp64 instructions, ours
 
 
 # DRAM traffic of one k_lm_fit launch over NCU_LAUNCH_STAMPS stamps, from the
-# committed ncu capture (profiles/ncu_lm_fit_r2b.txt)
-NCU_DRAM_BYTES_PER_LAUNCH = 377495808 + 85357824
+# committed ncu capture (profiles/ncu_lm_fit_r2c.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = 377513728 + 114496000
 NCU_LAUNCH_STAMPS = 10000
 
 
@@ -672,11 +672,11 @@ def main():
             "hbm_frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one k_lm_fit
             # launch of this workload (10 000 stamps per rank) from the
-            # ncu --set full capture in profiles/ncu_lm_fit_r2b.txt:
+            # ncu --set full capture in profiles/ncu_lm_fit_r2c.txt:
             # 372.9 MB read + 58.0 MB written; algorithmic 384 MB + records
             "traffic": (NCU_DRAM_BYTES_PER_LAUNCH
                         if nobj == NCU_LAUNCH_STAMPS else None),
-            "traffic_source": "ncu capture profiles/ncu_lm_fit_r2b.txt "
+            "traffic_source": "ncu capture profiles/ncu_lm_fit_r2c.txt "
                               "(not measured in this run)",
         },
         "fdiff_kernel": {

@@ -153,7 +153,7 @@ def test_gpu_coellip_matches_reference(ng, ngauss, pk):
     FMA contraction, differs from its unfused build in the evaluation count of
     0.2-0.4 % of such fits (one lmdif iteration more or less at the ftol /
     xtol boundary, the same optimum), and the CUDA kernels differ from the
-    oracle at the same rate (profiles/coellip_parity_r2b.json, 2 x 2000 fits;
+    oracle at the same rate (profiles/coellip_parity_r2c.json, 2 x 2000 fits;
     test_gpu_coellip_evaluation_counts_at_the_noise_floor).  A golden fit may
     therefore end one iteration apart if it ends at the same point.
     3 to 5 gaussians on a 3-gaussian psf are degenerate (hundreds of
