@@ -350,3 +350,30 @@ def test_streamed_pipeline_failure_releases_the_device(ngx, monkeypatch):
     assert time.perf_counter() - t0 < 3.0
     monkeypatch.delenv("NGX_STREAM_FAIL_AT")
     _same_records(ngx.lm_fit("exp", *args), want)
+
+
+def test_streamed_pipeline_is_not_slower_than_chunked(ngx, monkeypatch):
+    """guard against feeding mistakes (a waiter polling host memory once
+    starved the copies it waited for: 50x slower, same records)"""
+    import time
+    import ngmix_b200 as ng
+    from ngmix_b200 import sims
+    n = 6000
+    b = sims.make_lm_batch(n, seed0=8870, noise=0.05)
+    pin = ng.pinned_copy
+    args = [pin(b[k].astype("f4") if k in ("images", "weights") else b[k])
+            for k in ("images", "weights", "jac", "psf", "guess")]
+    out = ng.pinned_empty((n,), ngx.LM_RESULT_DTYPE)
+
+    def best(mode):
+        monkeypatch.setenv("NGX_NO_STREAM", mode)
+        ngx.lm_fit("exp", *args, out=out)
+        ts = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            ngx.lm_fit("exp", *args, out=out)
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    chunked, streamed = best("1"), best("0")
+    assert streamed < 1.5 * chunked, (streamed, chunked)
