@@ -2947,14 +2947,24 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
         NGX_CUDA(cudaHostGetDevicePointer((void **)&feed.host_done, hf, 0));
         feed.err = feed.host_done + max_dc;
         feed.err_dev = B.flags + max_rc + max_dc;
-        g_lm_feed = &feed;
-        r = ngx_lm_fit(cn, model, (const double *)B.in_a,
-                       (const double *)(compact ? B.in_a : B.in_b), B.jac,
-                       nrow, ncol, npsf > 0 ? B.psf : nullptr, npsf, B.guess,
-                       prior, lm_pars, ignore_zero_weight, B.res, ks[k & 1]);
-        g_lm_feed = nullptr;
-        if (r) return r;
-        cur_batch = k;
+        auto launch = [&]() -> int {
+            g_lm_feed = &feed;
+            int lr = ngx_lm_fit(cn, model, (const double *)B.in_a,
+                                (const double *)(compact ? B.in_a : B.in_b),
+                                B.jac, nrow, ncol,
+                                npsf > 0 ? B.psf : nullptr, npsf, B.guess,
+                                prior, lm_pars, ignore_zero_weight, B.res,
+                                ks[k & 1]);
+            g_lm_feed = nullptr;
+            return lr;
+        };
+        // Pinned stamps: every copy of the batch is queued (asynchronously,
+        // ~70 us of host time - about when the first chunk lands) BEFORE the
+        // launch, so the call also works under tools that make launches
+        // synchronous (Nsight Compute).  Pageable stamps are staged by host
+        // threads as the fits go on, so there the kernel has to start first.
+        if (!in_pinned && (r = launch())) return r;
+        cur_batch = in_pinned ? k - 1 : k;
         for (int c = 0, slo = 0; slo < cn; c++) {
             const int want = c < 2 ? S : c == 2 ? 2 * S : c == 3 ? 4 * S
                                                          : rchunk;
@@ -3004,6 +3014,8 @@ static int lm_fit_host_stream(int n, int model, const void *images_v,
                                      cudaMemcpyHostToDevice, cs));
             slo += sn;
         }
+        if (in_pinned && (r = launch())) return r;
+        cur_batch = k;
         return NGX_OK;
     };
 
@@ -3129,8 +3141,16 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
         * (f32 ? sizeof(float) : sizeof(double)) * (f32 == 2 ? 1 : 2);
     const bool pinned_in = is_pinned(images_v)
         && (f32 == 2 || is_pinned(weights_v));
-    const bool worth = pinned_in ? n >= 2 * sm_count()
-                                 : plane_bytes >= ((size_t)32 << 20);
+    // Pageable stamps are staged while the resident kernel already runs; a
+    // tool that makes launches synchronous (Nsight Compute: it announces
+    // itself to the target through these variables) would stall that feed,
+    // so there they keep the chunked pipeline.  Pinned stamps are queued
+    // before the launch and stream everywhere.
+    const bool sync_launches = getenv("NV_NSIGHT_INJECTION_PORT_BASE")
+        || getenv("NV_TPS_LAUNCH_TOKEN");
+    const bool worth = pinned_in
+        ? n >= 2 * sm_count()
+        : plane_bytes >= ((size_t)32 << 20) && !sync_launches;
     if ((worth || getenv("NGX_STREAM_ALWAYS"))
         && lm_stream_eligible(model, nrow, ncol, npsf, lm_pars))
         return lm_fit_host_stream(n, model, images_v, weights_v, f32,

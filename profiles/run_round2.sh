@@ -13,6 +13,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader; nproc
 timeout 300 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err
 timeout 300 python bench.py --impl reference --kind port --steps 3 --warmup 1 > gpurun_out/bench_refport_$TAG.json 2>> gpurun_out/bench_ref_$TAG.err
 NGX_NO_STREAM=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu --configs none --sustain-seconds 0 > /dev/null 2>&1
+# the same command with the host calls streaming (pinned batches queue their copies before the launch, pageable ones fall back to chunks under the profiler)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_e2e_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu --configs none --sustain-seconds 0 > /dev/null 2>&1
 NGX_NO_STREAM=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_lm_fit -s 3 -c 1 -f -o gpurun_out/prof_lm_$TAG python bench.py --steps 2 --warmup 3 --no-cpu --configs none --sustain-seconds 0 > /dev/null 2>&1
 python profiles/ncu_summary.py gpurun_out/prof_lm_$TAG.ncu-rep > gpurun_out/ncu_lm_fit_$TAG.txt 2>&1
 python profiles/ncu_lines.py gpurun_out/prof_lm_$TAG.ncu-rep > gpurun_out/ncu_lm_fit_lines_$TAG.txt 2>&1
