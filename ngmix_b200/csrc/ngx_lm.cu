@@ -3142,12 +3142,14 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
     const bool pinned_in = is_pinned(images_v)
         && (f32 == 2 || is_pinned(weights_v));
     // Pageable stamps are staged while the resident kernel already runs; a
-    // tool that makes launches synchronous (Nsight Compute: it announces
-    // itself to the target through these variables) would stall that feed,
+    // tool or setting that makes launches synchronous (Nsight Compute, which
+    // announces itself to the target through these variables;
+    // CUDA_LAUNCH_BLOCKING) would stall that feed,
     // so there they keep the chunked pipeline.  Pinned stamps are queued
     // before the launch and stream everywhere.
+    const char *clb = getenv("CUDA_LAUNCH_BLOCKING");
     const bool sync_launches = getenv("NV_NSIGHT_INJECTION_PORT_BASE")
-        || getenv("NV_TPS_LAUNCH_TOKEN");
+        || getenv("NV_TPS_LAUNCH_TOKEN") || (clb && atoi(clb) != 0);
     const bool worth = pinned_in
         ? n >= 2 * sm_count()
         : plane_bytes >= ((size_t)32 << 20) && !sync_launches;
