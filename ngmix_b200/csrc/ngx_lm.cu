@@ -3150,10 +3150,10 @@ static int lm_fit_host_impl(int n, int model, const void *images_v,
     const char *clb = getenv("CUDA_LAUNCH_BLOCKING");
     const bool sync_launches = getenv("NV_NSIGHT_INJECTION_PORT_BASE")
         || getenv("NV_TPS_LAUNCH_TOKEN") || (clb && atoi(clb) != 0);
-    const bool worth = pinned_in
-        ? n >= 2 * sm_count()
-        : plane_bytes >= ((size_t)32 << 20) && !sync_launches;
+    const bool worth = pinned_in ? n >= 2 * sm_count()
+                                 : plane_bytes >= ((size_t)32 << 20);
     if ((worth || getenv("NGX_STREAM_ALWAYS"))
+        && (pinned_in || !sync_launches)
         && lm_stream_eligible(model, nrow, ncol, npsf, lm_pars))
         return lm_fit_host_stream(n, model, images_v, weights_v, f32,
                                   maskbits, jac, nrow, ncol, psf_pars, npsf,
