@@ -12,9 +12,41 @@
 #include <vector>
 #include <string.h>
 #include <stdlib.h>
+#include <stdint.h>
 #include <unistd.h>
 
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define NGX_NT_COPY 1
+#endif
+
 namespace ngx {
+
+// memcpy into a pinned staging slot that nobody on the host will read: with
+// non-temporal stores the destination lines are not read for ownership first
+// and do not evict the caller's data from the caches (a third less memory
+// traffic per staged byte; the copy engine reads the slot from DRAM anyway)
+inline void stage_copy(char *dst, const char *src, size_t n) {
+#ifdef NGX_NT_COPY
+    if (n >= 4096 && ((uintptr_t)dst & 15) == 0) {
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64) {
+            __m128i a = _mm_loadu_si128((const __m128i *)(src + i));
+            __m128i b = _mm_loadu_si128((const __m128i *)(src + i + 16));
+            __m128i c = _mm_loadu_si128((const __m128i *)(src + i + 32));
+            __m128i d = _mm_loadu_si128((const __m128i *)(src + i + 48));
+            _mm_stream_si128((__m128i *)(dst + i), a);
+            _mm_stream_si128((__m128i *)(dst + i + 16), b);
+            _mm_stream_si128((__m128i *)(dst + i + 32), c);
+            _mm_stream_si128((__m128i *)(dst + i + 48), d);
+        }
+        _mm_sfence();
+        if (i < n) memcpy(dst + i, src + i, n - i);
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
 
 class CopyPool {
 public:
@@ -33,9 +65,11 @@ public:
     void copy(void *dst, const void *src, size_t bytes) {
         const int nt = nthreads();
         if (nt == 1 || bytes < (size_t)2 << 20) {
-            memcpy(dst, src, bytes);
+            if (getenv("NGX_STAGE_MEMCPY")) memcpy(dst, src, bytes);
+            else stage_copy((char *)dst, (const char *)src, bytes);
             return;
         }
+        plain_ = getenv("NGX_STAGE_MEMCPY") != nullptr;
         std::lock_guard<std::mutex> use(use_);
         size_t piece = (bytes / nt + 4095) & ~(size_t)4095;
         {
@@ -67,7 +101,8 @@ private:
         size_t lo = piece_ * (size_t)i;
         if (lo >= bytes_) return;
         size_t n = bytes_ - lo < piece_ ? bytes_ - lo : piece_;
-        memcpy(dst_ + lo, src_ + lo, n);
+        if (plain_) memcpy(dst_ + lo, src_ + lo, n);
+        else stage_copy(dst_ + lo, src_ + lo, n);
     }
     void loop(int i) {
         unsigned long seen = 0;
@@ -90,6 +125,7 @@ private:
     char *dst_ = nullptr;
     const char *src_ = nullptr;
     size_t bytes_ = 0, piece_ = 0;
+    bool plain_ = false;
 };
 
 // Host-to-device copies of pageable memory through a ring of pinned slots: the
