@@ -356,7 +356,7 @@ def test_config4_bdf_parity_2000_stamps(ora):
     model by steps of 1.5e-8 |x|, so evaluation counts and parameters follow
     the reference up to that noise: nfev and ier agree on >= 98 % of the
     stamps (the oracle compiled with fused multiply-adds agrees with itself
-    on the same fraction, profiles/parity_sweep_r2.json), parameters within
+    on the same fraction, profiles/parity_sweep_r2c.json), parameters within
     max(1e-5 |p|, 1e-3 sigma) on >= 97 %, and T and flux within 1e-5 relative
     on >= 99 %.
     """
