@@ -82,6 +82,21 @@ def main():
         tl["jac"].data_ptr(), 48, 48, tl["psf"].data_ptr(), 3,
         tl["guess"].data_ptr(), d_rl.data_ptr(), stream=s)))
 
+    # the stand-alone fdiff / loglike / s2n pass on the same stamps, at the
+    # guess mixtures (what bench.py reports as fdiff_kernel)
+    gm0, _ = _lib.gmix_fill("exp", tl["h_guess"])
+    gp, _ = _lib.gmix_fill("full", tl["h_psf"].reshape(nl, -1))
+    gmc = _lib.gmix_convolve(gm0, gp)
+    _lib.gmix_set_norms(gmc)
+    d_gmc = torch.from_numpy(
+        np.frombuffer(gmc.tobytes(), dtype=np.uint8).copy()).to(dev)
+    d_o4 = torch.zeros(nl * 4, dtype=torch.float64, device=dev)
+    d_fd = torch.zeros(nl * 48 * 48, dtype=torch.float64, device=dev)
+    jobs.append(("loglike_tiled", lambda: _lib.loglike_device(
+        nl, 18, d_gmc.data_ptr(), tl["images"].data_ptr(),
+        tl["weights"].data_ptr(), tl["jac"].data_ptr(), 48, 48,
+        d_o4.data_ptr(), d_fdiff=d_fd.data_ptr(), stream=s)))
+
     # ---- multi-epoch / multi-band: 2 bands x 2 epochs
     nobj = nl // 4
     starts = torch.arange(0, 4 * nobj + 1, 4, dtype=torch.int32, device=dev)
